@@ -1,0 +1,305 @@
+/*
+ * sqlrs_b200 — C ABI of the B200-native execution backend for Fedomn/sqlrs.
+ *
+ * This header is the drop-in boundary.  Every entry point is
+ * `extern "C"`, takes plain pointers / sizes / Arrow C-Data structs, and
+ * replaces one piece of the reference's Rust operator interface.  The
+ * reference has no FFI of its own (it is pure Rust), so each function cites the
+ * Rust item a maintainer's `arrow::ffi` shim would forward to it
+ * (INTEGRATION.md shows that shim).
+ *
+ * The same ABI is compiled twice:
+ *   - libsqlrs_b200.so      (sqlrs_b200/csrc, CUDA sm_100a)  — symbols sqlrs_*
+ *   - liboracle.so          (oracle/, CPU restatement, test infrastructure only)
+ *                                                            — symbols sqlrs_oracle_*
+ * so that the parity tests drive both through identical calls.
+ *
+ * Ownership rules (Arrow C Data Interface):
+ *   - input `ArrowArray` / `ArrowDeviceArray` structs are MOVED into the callee
+ *     (it copies the struct, sets `release = NULL` in the caller's copy and
+ *     calls the original release callback once it no longer needs the buffers —
+ *     possibly after the call returns, when an async H2D copy is still in
+ *     flight);
+ *   - input `ArrowSchema` structs are only BORROWED for the duration of the call;
+ *   - output structs are filled by the callee and carry its release callbacks.
+ *
+ * Error convention (reference: `Result<RecordBatch, ExecutorError>`,
+ * src/executor/mod.rs:67-85): every function returns an `int` status, 0 = ok;
+ * `sqlrs_last_error()` returns the thread-local message.  The library never
+ * aborts the process; places where the reference panics (`todo!()`,
+ * `unimplemented!()`, `expect`) return SQLRS_ERR_UNSUPPORTED / SQLRS_ERR_INTERNAL
+ * so a shim can fall back to the CPU operator.
+ *
+ * Threading (reference: BoxStream is Send + 'static, polled by one task):
+ * handles are single-owner, not thread-safe, movable between threads between
+ * calls (no thread-affine CUDA state: the device is set on every call and all
+ * work goes to the handle's stream).
+ */
+#ifndef SQLRS_B200_H
+#define SQLRS_B200_H
+
+#include <stdint.h>
+#include "arrow_c_data.h"
+
+#ifdef SQLRS_ORACLE_BUILD
+#define SQLRS_API(name) sqlrs_oracle_##name
+#else
+#define SQLRS_API(name) sqlrs_##name
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQLRS_ABI_VERSION 1
+
+/* ---- status codes: ExecutorError, src/executor/mod.rs:67-85 ------------------- */
+#define SQLRS_OK 0
+#define SQLRS_ERR_INTERNAL 1    /* ExecutorError::InternalError(String) */
+#define SQLRS_ERR_ARROW 2       /* ExecutorError::Arrow(ArrowError): DivideByZero, schema mismatch ... */
+#define SQLRS_ERR_UNSUPPORTED 3 /* the reference panics here (todo!/unimplemented!) or the GPU path lacks the dtype */
+#define SQLRS_ERR_INVALID_ARG 4
+#define SQLRS_ERR_CUDA 5
+
+/* ---- the type universe of the v1 executor: ScalarValue, src/types/mod.rs:23-36 - */
+#define SQLRS_DT_NULL 0
+#define SQLRS_DT_BOOL 1
+#define SQLRS_DT_INT32 2
+#define SQLRS_DT_INT64 3
+#define SQLRS_DT_FLOAT64 4
+#define SQLRS_DT_UTF8 5 /* oracle: full support; CUDA library: SQLRS_ERR_UNSUPPORTED */
+
+/* ---- expression bytecode: flattened BoundExpr, src/binder/expression/mod.rs:18-27
+ * Postfix order: children first (left then right), then the node.  `Alias` is
+ * dropped by the host when flattening (evaluator.rs:25 evaluates the inner expr).
+ * Operand types must already match — the binder inserts TypeCast nodes
+ * (src/binder/expression/binary_op.rs:27-56). */
+#define SQLRS_OP_INPUT_REF 1 /* BoundExpr::InputRef{index, return_type}   evaluator.rs:15 */
+#define SQLRS_OP_CONSTANT 2  /* BoundExpr::Constant(ScalarValue)           evaluator.rs:21 */
+#define SQLRS_OP_CAST 3      /* BoundExpr::TypeCast{expr, cast_type}       evaluator.rs:23 */
+#define SQLRS_OP_ADD 10      /* BinaryOperator::Plus      array_compute.rs:76 (wrapping ints) */
+#define SQLRS_OP_SUB 11      /* BinaryOperator::Minus     array_compute.rs:77 */
+#define SQLRS_OP_MUL 12      /* BinaryOperator::Multiply  array_compute.rs:78 */
+#define SQLRS_OP_DIV 13      /* BinaryOperator::Divide    array_compute.rs:79 (DivideByZero -> SQLRS_ERR_ARROW) */
+#define SQLRS_OP_GT 20       /* gt_dyn     array_compute.rs:80 */
+#define SQLRS_OP_LT 21       /* lt_dyn     array_compute.rs:81 */
+#define SQLRS_OP_GE 22       /* gt_eq_dyn  array_compute.rs:82 */
+#define SQLRS_OP_LE 23       /* lt_eq_dyn  array_compute.rs:83 */
+#define SQLRS_OP_EQ 24       /* eq_dyn     array_compute.rs:84 */
+#define SQLRS_OP_NE 25       /* neq_dyn    array_compute.rs:85 */
+#define SQLRS_OP_AND 30      /* and_kleene array_compute.rs:86 (Boolean only, else InternalError) */
+#define SQLRS_OP_OR 31       /* or_kleene  array_compute.rs:87 */
+
+typedef struct sqlrs_expr_node {
+  int32_t op;       /* SQLRS_OP_* */
+  int32_t dtype;    /* result type: INPUT_REF -> column type, CONSTANT -> scalar type,
+                       CAST -> cast_type, binary op -> return_type */
+  int32_t index;    /* INPUT_REF: column index into the input batch */
+  int32_t is_null;  /* CONSTANT: 1 = ScalarValue::X(None) */
+  int64_t imm_bits; /* CONSTANT: bool / i32 / i64 value, or the IEEE-754 bits of an f64 */
+  const char* str;  /* CONSTANT of SQLRS_DT_UTF8: NUL-terminated UTF-8, else NULL */
+} sqlrs_expr_node;
+
+typedef struct sqlrs_expr {
+  const sqlrs_expr_node* nodes;
+  int32_t n_nodes; /* 0 = "no expression" where an expression is optional */
+} sqlrs_expr;
+
+/* ---- aggregates: BoundAggFunc, src/binder/expression/agg_func.rs:10-34 --------- */
+#define SQLRS_AGG_COUNT 0 /* CountAccumulator  aggregate/count.rs:10-29 */
+#define SQLRS_AGG_SUM 1   /* SumAccumulator    aggregate/sum.rs:36-97 */
+#define SQLRS_AGG_MIN 2   /* MinAccumulator    aggregate/min_max.rs:111-133 */
+#define SQLRS_AGG_MAX 3   /* MaxAccumulator    aggregate/min_max.rs:135-157 */
+
+typedef struct sqlrs_agg_desc {
+  int32_t func;         /* SQLRS_AGG_* */
+  int32_t distinct;     /* BoundAggFunc::distinct (oracle only; CUDA: SQLRS_ERR_UNSUPPORTED) */
+  int32_t return_dtype; /* BoundAggFunc::return_type */
+  int32_t reserved;
+  sqlrs_expr arg;       /* exprs[0] — only the first argument is evaluated (hash_agg.rs:65) */
+  const char* name;     /* output field name, e.g. "Sum(b)" (evaluator.rs:52-56); computed by the host */
+} sqlrs_agg_desc;
+
+/* ---- JoinType, src/binder/table/join.rs:17-24 ---------------------------------- */
+#define SQLRS_JOIN_INNER 0
+#define SQLRS_JOIN_LEFT 1
+#define SQLRS_JOIN_RIGHT 2
+#define SQLRS_JOIN_FULL 3
+
+/* ---- behaviour switches for the reference quirks K1/K2 ----- */
+#define SQLRS_COUNT_REFERENCE_OVERWRITE 0 /* count.rs:22 assigns: value = count in the LAST batch touching the group */
+#define SQLRS_COUNT_SQL_ACCUMULATE 1      /* += (SQL semantics) */
+#define SQLRS_MATCH_HASH_ONLY 0           /* hash_agg.rs:87-110 / hash_join.rs:222-233: 64-bit row hash is the identity */
+#define SQLRS_MATCH_HASH_AND_KEY 1        /* also compare key values; NULL keys never join (SQL semantics) */
+
+#define SQLRS_FLAG_NO_FUSION 1   /* plan API: never pick a fused pipeline, run operator by operator */
+#define SQLRS_FLAG_DEVICE_OUTPUT 2 /* reserved */
+
+typedef struct sqlrs_options {
+  int32_t count_mode; /* default SQLRS_COUNT_REFERENCE_OVERWRITE */
+  int32_t match_mode; /* default SQLRS_MATCH_HASH_ONLY */
+  int32_t device_id;  /* CUDA ordinal, -1 = current device (ignored by the oracle) */
+  int32_t flags;      /* SQLRS_FLAG_* */
+  void* stream;       /* cudaStream_t to launch on; NULL = library-owned non-blocking stream */
+} sqlrs_options;
+
+/* ---- library -------------------------------------------------------------------- */
+int SQLRS_API(abi_version)(void);
+const char* SQLRS_API(last_error)(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t SQLRS_API(kernel_launches)(void);
+
+/* row hashes exactly as create_hashes (src/executor/aggregate/hash_utils.rs:161-220)
+ * with RandomState::with_seeds(0,0,0,0): `columns` is a struct array whose children
+ * are the key columns; writes `length` u64 into out_hashes (host memory). */
+int SQLRS_API(create_hashes)(struct ArrowArray* columns, const struct ArrowSchema* schema,
+                             uint64_t* out_hashes);
+
+/* BoundExpr::eval_column (src/executor/evaluator.rs:13-28): evaluates one expression
+ * over a batch, returns a 1-column batch. */
+int SQLRS_API(eval_expr)(const sqlrs_expr* expr, const sqlrs_options* options,
+                         struct ArrowArray* batch, const struct ArrowSchema* schema,
+                         struct ArrowArray* out, struct ArrowSchema* out_schema);
+
+/* ---- FilterExecutor{expr, child}, src/executor/filter.rs:7-26 --------------------
+ * one output batch per input batch, row order preserved, NULL predicate drops the row */
+typedef struct sqlrs_filter sqlrs_filter;
+int SQLRS_API(filter_create)(const sqlrs_expr* predicate, const sqlrs_options* options,
+                             sqlrs_filter** out);
+int SQLRS_API(filter_execute)(sqlrs_filter* f, struct ArrowArray* batch,
+                              const struct ArrowSchema* schema, struct ArrowArray* out,
+                              struct ArrowSchema* out_schema);
+void SQLRS_API(filter_destroy)(sqlrs_filter* f);
+
+/* ---- SimpleAggExecutor{agg_funcs, child}, src/executor/aggregate/simple_agg.rs:10-65
+ * push every child batch in order, then finish -> exactly one 1-row batch.
+ * finish with zero pushed batches is an error (simple_agg.rs:63 unwraps None). */
+typedef struct sqlrs_simple_agg sqlrs_simple_agg;
+int SQLRS_API(simple_agg_create)(const sqlrs_agg_desc* aggs, int32_t n_aggs,
+                                 const sqlrs_options* options, sqlrs_simple_agg** out);
+int SQLRS_API(simple_agg_push)(sqlrs_simple_agg* a, struct ArrowArray* batch,
+                               const struct ArrowSchema* schema);
+int SQLRS_API(simple_agg_finish)(sqlrs_simple_agg* a, struct ArrowArray* out,
+                                 struct ArrowSchema* out_schema);
+void SQLRS_API(simple_agg_destroy)(sqlrs_simple_agg* a);
+
+/* ---- HashAggExecutor{agg_funcs, group_by, child}, src/executor/aggregate/hash_agg.rs:15-150
+ * output: one batch, columns = group keys then aggregates, rows in first-appearance
+ * order of the group (hash_agg.rs:98,134).  finish with zero pushed batches is an
+ * error (hash_agg.rs:125 unwraps None). */
+typedef struct sqlrs_hash_agg sqlrs_hash_agg;
+int SQLRS_API(hash_agg_create)(const sqlrs_agg_desc* aggs, int32_t n_aggs,
+                               const sqlrs_expr* group_by, const char* const* group_names,
+                               int32_t n_group_by, const sqlrs_options* options,
+                               sqlrs_hash_agg** out);
+int SQLRS_API(hash_agg_push)(sqlrs_hash_agg* a, struct ArrowArray* batch,
+                             const struct ArrowSchema* schema);
+int SQLRS_API(hash_agg_finish)(sqlrs_hash_agg* a, struct ArrowArray* out,
+                               struct ArrowSchema* out_schema);
+void SQLRS_API(hash_agg_destroy)(sqlrs_hash_agg* a);
+
+/* ---- HashJoinExecutor{left_child, right_child, join_type, join_condition,
+ *      join_output_schema}, src/executor/join/hash_join.rs:16-23,147-323 -----------
+ * left child = build side: push all its batches (build_push), then stream the right
+ * child through probe (one output batch per probe batch, hash_join.rs:208-292), then
+ * finish yields the Left/Full tail of unmatched build rows (hash_join.rs:296-322).
+ * *has_batch = 0 where the reference yields nothing (empty build side :183-185,
+ * Inner/Right tail).  `join_output_schema` = the struct schema of the joined row
+ * (all left fields then all right fields, names "table.col", catalog/mod.rs:131-138). */
+typedef struct sqlrs_hash_join sqlrs_hash_join;
+int SQLRS_API(hash_join_create)(int32_t join_type, const sqlrs_expr* left_keys,
+                                const sqlrs_expr* right_keys, int32_t n_keys,
+                                const sqlrs_expr* filter, /* NULL or n_nodes==0: no non-equi filter */
+                                const struct ArrowSchema* join_output_schema,
+                                const sqlrs_options* options, sqlrs_hash_join** out);
+int SQLRS_API(hash_join_build_push)(sqlrs_hash_join* j, struct ArrowArray* batch,
+                                    const struct ArrowSchema* schema);
+int SQLRS_API(hash_join_probe)(sqlrs_hash_join* j, struct ArrowArray* batch,
+                               const struct ArrowSchema* schema, struct ArrowArray* out,
+                               struct ArrowSchema* out_schema, int32_t* has_batch);
+int SQLRS_API(hash_join_finish)(sqlrs_hash_join* j, struct ArrowArray* out,
+                                struct ArrowSchema* out_schema, int32_t* has_batch);
+void SQLRS_API(hash_join_destroy)(sqlrs_hash_join* j);
+
+/* ---- whole physical sub-plan: what ExecutorBuilder::build(plan) (src/executor/mod.rs:45-47,
+ *      visit_* :87-200) wires together.  Handing the GPU the subtree instead of one
+ *      operator lets it keep intermediates in HBM and pick a fused pipeline
+ *      (scan->filter->agg, scan->filter->join->join->agg) when the shape is registered;
+ *      otherwise it composes the per-operator kernels above.  Results are identical
+ *      either way. ------------------------------------------------------------------ */
+#define SQLRS_NODE_SCAN 1       /* PhysicalTableScan: batches pushed by the host per table_slot */
+#define SQLRS_NODE_FILTER 2     /* PhysicalFilter     mod.rs:139-149 */
+#define SQLRS_NODE_SIMPLE_AGG 3 /* PhysicalSimpleAgg  mod.rs:151-161 */
+#define SQLRS_NODE_HASH_AGG 4   /* PhysicalHashAgg    mod.rs:163-174 */
+#define SQLRS_NODE_HASH_JOIN 5  /* PhysicalHashJoin   mod.rs:103-114 (child0 = left = build) */
+
+typedef struct sqlrs_plan_node {
+  int32_t kind;   /* SQLRS_NODE_* */
+  int32_t child0; /* index into the node array, -1 = none */
+  int32_t child1; /* HASH_JOIN: right (probe) child */
+  int32_t table_slot; /* SCAN */
+  sqlrs_expr predicate; /* FILTER; HASH_JOIN: optional non-equi filter */
+  const sqlrs_agg_desc* aggs; /* SIMPLE_AGG / HASH_AGG */
+  int32_t n_aggs;
+  int32_t n_group_by;
+  const sqlrs_expr* group_by; /* HASH_AGG */
+  const char* const* group_names;
+  int32_t join_type; /* HASH_JOIN */
+  int32_t n_keys;
+  const sqlrs_expr* left_keys;
+  const sqlrs_expr* right_keys;
+  const struct ArrowSchema* join_output_schema;
+} sqlrs_plan_node;
+
+typedef struct sqlrs_plan sqlrs_plan;
+int SQLRS_API(plan_create)(const sqlrs_plan_node* nodes, int32_t n_nodes, int32_t root,
+                           const sqlrs_options* options, sqlrs_plan** out);
+/* one call per batch of the table bound to `table_slot`, in stream order */
+int SQLRS_API(plan_push_table)(sqlrs_plan* p, int32_t table_slot, struct ArrowArray* batch,
+                               const struct ArrowSchema* schema);
+/* same with buffers already resident in HBM (zero copy; device pointers in buffers[]) */
+int SQLRS_API(plan_push_table_device)(sqlrs_plan* p, int32_t table_slot,
+                                      struct ArrowDeviceArray* batch,
+                                      const struct ArrowSchema* schema);
+/* runs the plan over everything pushed so far; work is enqueued on the plan's stream
+ * and complete when the call returns only for host-visible results (plan_next syncs) */
+int SQLRS_API(plan_execute)(sqlrs_plan* p);
+/* pull the result stream (try_collect, src/executor/mod.rs:58-64) */
+int SQLRS_API(plan_next)(sqlrs_plan* p, struct ArrowArray* out, struct ArrowSchema* out_schema,
+                         int32_t* has_batch);
+/* forget pushed tables / operator state, keep plan + device scratch (repeated runs) */
+int SQLRS_API(plan_reset)(sqlrs_plan* p);
+/* human-readable: which pipeline (fused / generic) and kernels the plan runs with */
+const char* SQLRS_API(plan_describe)(sqlrs_plan* p);
+void SQLRS_API(plan_destroy)(sqlrs_plan* p);
+
+/* ---- synthetic TPC-H-shaped tables: counter-based, identical in the
+ *      CUDA generator (writes straight into HBM) and the oracle's CPU generator ------ */
+#define SQLRS_TPCH_CUSTOMER 0 /* c_custkey i64, c_mktsegment i64 */
+#define SQLRS_TPCH_ORDERS 1   /* o_orderkey, o_custkey, o_orderdate, o_shippriority (all i64) */
+#define SQLRS_TPCH_LINEITEM 2 /* l_orderkey i64, l_quantity f64, l_extendedprice f64, l_discount f64,
+                                 l_tax f64, l_returnflag i64, l_linestatus i64, l_shipdate i64,
+                                 l_quantity_i64 i64 */
+#define SQLRS_TPCH_FLAGS_8GROUP 0 /* returnflag = u mod 4, linestatus = (u>>2) mod 2 */
+#define SQLRS_TPCH_FLAGS_SPEC 1   /* derived from dates as in the TPC-H spec (4 populated groups) */
+
+typedef struct sqlrs_tpch_dims {
+  int64_t n_customer; /* 150 000 x SF */
+  int64_t n_orders;   /* 1 500 000 x SF */
+  int32_t flags_mode; /* SQLRS_TPCH_FLAGS_* */
+  int32_t reserved;
+} sqlrs_tpch_dims;
+
+int32_t SQLRS_API(tpch_num_columns)(int32_t table);
+int64_t SQLRS_API(tpch_num_rows)(const sqlrs_tpch_dims* dims, int32_t table);
+/* fills rows [row_begin, row_end) of every column of `table`; columns[c] points to
+ * (row_end-row_begin) 8-byte values — device memory for the CUDA library (enqueued on
+ * `stream`), host memory for the oracle. */
+int SQLRS_API(tpch_generate)(const sqlrs_tpch_dims* dims, int32_t table, int64_t row_begin,
+                             int64_t row_end, void* const* columns, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SQLRS_B200_H */

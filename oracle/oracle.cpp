@@ -1,0 +1,373 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// The C ABI of include/sqlrs_b200.h compiled with SQLRS_ORACLE_BUILD (symbols sqlrs_oracle_*),
+// backed by the CPU restatement in ops.hpp.  Built into oracle/liboracle.so by oracle/Makefile.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs load it.
+//
+// Parity status: the reference cannot be compiled here (no cargo/rustc; it
+// needs nightly-2022-07-29 + arrow `simd`), so this restatement is pinned by the reference's own
+// golden tests instead — hash KAT (hash_utils.rs:229-247), HashAgg two-chunk test
+// (hash_agg.rs:182-222), the 8 HashJoin tables (hash_join.rs:423-750), the executor e2e tests
+// (executor/mod.rs:271-396) and the v1 .slt files over tests/csv — see tests/test_oracle_golden.py.
+// UNPINNED by any reference test: COUNT over >1 batch (K1), float SUM order, 64-bit collisions (K2),
+// NULL-key joins (K3), Int32/Boolean/Utf8 hash_one, multi-batch joins, Float64 min/max NaN.
+#define SQLRS_ORACLE_BUILD 1
+#include <chrono>
+#include <deque>
+#include <map>
+#include <thread>
+
+#include "../include/sqlrs_b200.h"
+#include "../include/sqlrs_tpch_spec.h"
+#include "arrow_io.hpp"
+#include "ops.hpp"
+
+using namespace oracle;
+
+static thread_local std::string g_last_error;
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    f();
+    g_last_error.clear();
+    return SQLRS_OK;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return SQLRS_ERR_INTERNAL;
+  }
+}
+
+// take ownership of an input ArrowArray (moved into the callee), import, release
+static Batch consume_batch(ArrowArray* array, const ArrowSchema* schema) {
+  if (!array || !array->release) fail(SQLRS_ERR_INVALID_ARG, "input ArrowArray is NULL or already released");
+  struct Guard {
+    ArrowArray* a;
+    ~Guard() {
+      if (a->release) a->release(a);
+    }
+  } guard{array};
+  return import_batch(array, schema);
+}
+
+static std::vector<AggDesc> copy_aggs(const sqlrs_agg_desc* aggs, int32_t n) {
+  std::vector<AggDesc> out;
+  if (n > 0 && !aggs) fail(SQLRS_ERR_INVALID_ARG, "aggs is NULL");
+  for (int32_t k = 0; k < n; k++) out.push_back(copy_agg(aggs[k]));
+  return out;
+}
+static std::vector<Expr> copy_exprs(const sqlrs_expr* e, int32_t n) {
+  std::vector<Expr> out;
+  if (n > 0 && !e) fail(SQLRS_ERR_INVALID_ARG, "expression array is NULL");
+  for (int32_t k = 0; k < n; k++) out.push_back(copy_expr(&e[k]));
+  return out;
+}
+static std::vector<std::string> copy_names(const char* const* names, int32_t n) {
+  std::vector<std::string> out;
+  for (int32_t k = 0; k < n; k++) out.push_back(names && names[k] ? names[k] : "");
+  return out;
+}
+
+struct sqlrs_filter {
+  Expr predicate;
+};
+struct sqlrs_simple_agg {
+  SimpleAgg impl;
+};
+struct sqlrs_hash_agg {
+  HashAgg impl;
+};
+struct sqlrs_hash_join {
+  HashJoin impl;
+};
+
+static HashJoin make_join(int32_t join_type, const sqlrs_expr* lk, const sqlrs_expr* rk, int32_t n_keys,
+                          const sqlrs_expr* filter, const ArrowSchema* out_schema, const sqlrs_options* options) {
+  if (join_type < SQLRS_JOIN_INNER || join_type > SQLRS_JOIN_FULL) fail(SQLRS_ERR_INVALID_ARG, "bad join type");
+  if (n_keys < 1) fail(SQLRS_ERR_INTERNAL, "HashJoin must has on condition");
+  HashJoin j;
+  j.join_type = join_type;
+  j.left_keys = copy_exprs(lk, n_keys);
+  j.right_keys = copy_exprs(rk, n_keys);
+  if (filter && filter->n_nodes > 0) j.filter = copy_expr(filter);
+  j.out_fields = import_fields(out_schema);
+  j.opt = copy_options(options);
+  return j;
+}
+
+// ------------------------------------------------------------------ plan
+struct PlanNode {
+  sqlrs_plan_node raw;
+  Expr predicate;
+  std::vector<AggDesc> aggs;
+  std::vector<Expr> group_by, left_keys, right_keys;
+  std::vector<std::string> group_names;
+  std::vector<Field> join_fields;
+};
+struct sqlrs_plan {
+  std::vector<PlanNode> nodes;
+  int root = 0;
+  Options opt;
+  sqlrs_options raw_opt{};
+  std::map<int, std::vector<Batch>> tables;
+  std::deque<Batch> results;
+  std::string description;
+
+  std::vector<Batch> run(int idx) {
+    if (idx < 0 || idx >= (int)nodes.size()) fail(SQLRS_ERR_INVALID_ARG, "plan: child index out of range");
+    PlanNode& n = nodes[idx];
+    switch (n.raw.kind) {
+      case SQLRS_NODE_SCAN: return tables[n.raw.table_slot];
+      case SQLRS_NODE_FILTER: {
+        std::vector<Batch> out;
+        for (const Batch& b : run(n.raw.child0)) out.push_back(filter_batch(n.predicate, b));
+        return out;
+      }
+      case SQLRS_NODE_SIMPLE_AGG: {
+        SimpleAgg a(n.aggs, opt);
+        for (const Batch& b : run(n.raw.child0)) a.push(b);
+        return {a.finish()};
+      }
+      case SQLRS_NODE_HASH_AGG: {
+        HashAgg a(n.aggs, n.group_by, n.group_names, opt);
+        for (const Batch& b : run(n.raw.child0)) a.push(b);
+        return {a.finish()};
+      }
+      case SQLRS_NODE_HASH_JOIN: {
+        HashJoin j;
+        j.join_type = n.raw.join_type;
+        j.left_keys = n.left_keys;
+        j.right_keys = n.right_keys;
+        j.filter = n.predicate;
+        j.out_fields = n.join_fields;
+        j.opt = opt;
+        for (const Batch& b : run(n.raw.child0)) j.build_push(b);
+        std::vector<Batch> out;
+        for (const Batch& b : run(n.raw.child1)) {
+          Batch r;
+          if (j.probe(b, &r)) out.push_back(r);
+        }
+        Batch tail;
+        if (j.finish(&tail)) out.push_back(tail);
+        return out;
+      }
+    }
+    fail(SQLRS_ERR_INVALID_ARG, "plan: unknown node kind");
+  }
+};
+
+extern "C" {
+
+int sqlrs_oracle_abi_version(void) { return SQLRS_ABI_VERSION; }
+const char* sqlrs_oracle_last_error(void) { return g_last_error.c_str(); }
+int64_t sqlrs_oracle_kernel_launches(void) { return 0; }
+
+int sqlrs_oracle_create_hashes(ArrowArray* columns, const ArrowSchema* schema, uint64_t* out_hashes) {
+  return guarded([&] {
+    Batch b = consume_batch(columns, schema);
+    std::vector<uint64_t> h(b.n, 0);
+    create_hashes(b.cols, h);
+    if (b.n) std::memcpy(out_hashes, h.data(), sizeof(uint64_t) * b.n);
+  });
+}
+
+int sqlrs_oracle_eval_expr(const sqlrs_expr* expr, const sqlrs_options*, ArrowArray* batch, const ArrowSchema* schema,
+                           ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] {
+    Batch b = consume_batch(batch, schema);
+    Expr e = copy_expr(expr);
+    ColPtr c = eval_expr(e, b);
+    Batch r;
+    r.n = b.n;
+    r.cols.push_back(c);
+    r.fields.push_back(Field{"expr", c->dtype, true});
+    export_batch(r, out, out_schema);
+  });
+}
+
+int sqlrs_oracle_filter_create(const sqlrs_expr* predicate, const sqlrs_options*, sqlrs_filter** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    Expr e = copy_expr(predicate);
+    if (e.empty()) fail(SQLRS_ERR_INVALID_ARG, "filter needs a predicate");
+    *out = new sqlrs_filter{e};
+  });
+}
+int sqlrs_oracle_filter_execute(sqlrs_filter* f, ArrowArray* batch, const ArrowSchema* schema, ArrowArray* out,
+                                ArrowSchema* out_schema) {
+  return guarded([&] {
+    Batch b = consume_batch(batch, schema);
+    export_batch(filter_batch(f->predicate, b), out, out_schema);
+  });
+}
+void sqlrs_oracle_filter_destroy(sqlrs_filter* f) { delete f; }
+
+int sqlrs_oracle_simple_agg_create(const sqlrs_agg_desc* aggs, int32_t n_aggs, const sqlrs_options* options,
+                                   sqlrs_simple_agg** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_simple_agg{SimpleAgg(copy_aggs(aggs, n_aggs), copy_options(options))};
+  });
+}
+int sqlrs_oracle_simple_agg_push(sqlrs_simple_agg* a, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] { a->impl.push(consume_batch(batch, schema)); });
+}
+int sqlrs_oracle_simple_agg_finish(sqlrs_simple_agg* a, ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] { export_batch(a->impl.finish(), out, out_schema); });
+}
+void sqlrs_oracle_simple_agg_destroy(sqlrs_simple_agg* a) { delete a; }
+
+int sqlrs_oracle_hash_agg_create(const sqlrs_agg_desc* aggs, int32_t n_aggs, const sqlrs_expr* group_by,
+                                 const char* const* group_names, int32_t n_group_by, const sqlrs_options* options,
+                                 sqlrs_hash_agg** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_hash_agg{HashAgg(copy_aggs(aggs, n_aggs), copy_exprs(group_by, n_group_by),
+                                      copy_names(group_names, n_group_by), copy_options(options))};
+  });
+}
+int sqlrs_oracle_hash_agg_push(sqlrs_hash_agg* a, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] { a->impl.push(consume_batch(batch, schema)); });
+}
+int sqlrs_oracle_hash_agg_finish(sqlrs_hash_agg* a, ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] { export_batch(a->impl.finish(), out, out_schema); });
+}
+void sqlrs_oracle_hash_agg_destroy(sqlrs_hash_agg* a) { delete a; }
+
+int sqlrs_oracle_hash_join_create(int32_t join_type, const sqlrs_expr* left_keys, const sqlrs_expr* right_keys,
+                                  int32_t n_keys, const sqlrs_expr* filter, const ArrowSchema* join_output_schema,
+                                  const sqlrs_options* options, sqlrs_hash_join** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_hash_join{make_join(join_type, left_keys, right_keys, n_keys, filter, join_output_schema, options)};
+  });
+}
+int sqlrs_oracle_hash_join_build_push(sqlrs_hash_join* j, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] { j->impl.build_push(consume_batch(batch, schema)); });
+}
+int sqlrs_oracle_hash_join_probe(sqlrs_hash_join* j, ArrowArray* batch, const ArrowSchema* schema, ArrowArray* out,
+                                 ArrowSchema* out_schema, int32_t* has_batch) {
+  return guarded([&] {
+    Batch b = consume_batch(batch, schema);
+    Batch r;
+    bool has = j->impl.probe(b, &r);
+    if (has_batch) *has_batch = has;
+    if (has) export_batch(r, out, out_schema);
+  });
+}
+int sqlrs_oracle_hash_join_finish(sqlrs_hash_join* j, ArrowArray* out, ArrowSchema* out_schema, int32_t* has_batch) {
+  return guarded([&] {
+    Batch r;
+    bool has = j->impl.finish(&r);
+    if (has_batch) *has_batch = has;
+    if (has) export_batch(r, out, out_schema);
+  });
+}
+void sqlrs_oracle_hash_join_destroy(sqlrs_hash_join* j) { delete j; }
+
+int sqlrs_oracle_plan_create(const sqlrs_plan_node* nodes, int32_t n_nodes, int32_t root, const sqlrs_options* options,
+                             sqlrs_plan** out) {
+  return guarded([&] {
+    if (!out || !nodes || n_nodes < 1 || root < 0 || root >= n_nodes) fail(SQLRS_ERR_INVALID_ARG, "bad plan");
+    auto* p = new sqlrs_plan();
+    std::unique_ptr<sqlrs_plan> hold(p);
+    p->opt = copy_options(options);
+    p->root = root;
+    for (int32_t k = 0; k < n_nodes; k++) {
+      PlanNode n;
+      n.raw = nodes[k];
+      n.predicate = copy_expr(&nodes[k].predicate);
+      n.aggs = copy_aggs(nodes[k].aggs, nodes[k].n_aggs);
+      n.group_by = copy_exprs(nodes[k].group_by, nodes[k].n_group_by);
+      n.group_names = copy_names(nodes[k].group_names, nodes[k].n_group_by);
+      if (nodes[k].kind == SQLRS_NODE_HASH_JOIN) {
+        n.left_keys = copy_exprs(nodes[k].left_keys, nodes[k].n_keys);
+        n.right_keys = copy_exprs(nodes[k].right_keys, nodes[k].n_keys);
+        n.join_fields = import_fields(nodes[k].join_output_schema);
+      }
+      p->nodes.push_back(std::move(n));
+    }
+    p->description = "oracle: operator-at-a-time CPU restatement";
+    *out = hold.release();
+  });
+}
+int sqlrs_oracle_plan_push_table(sqlrs_plan* p, int32_t table_slot, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] { p->tables[table_slot].push_back(consume_batch(batch, schema)); });
+}
+int sqlrs_oracle_plan_push_table_device(sqlrs_plan*, int32_t, ArrowDeviceArray*, const ArrowSchema*) {
+  g_last_error = "the oracle takes host batches only";
+  return SQLRS_ERR_UNSUPPORTED;
+}
+int sqlrs_oracle_plan_execute(sqlrs_plan* p) {
+  return guarded([&] {
+    p->results.clear();
+    for (Batch& b : p->run(p->root)) p->results.push_back(std::move(b));
+  });
+}
+int sqlrs_oracle_plan_next(sqlrs_plan* p, ArrowArray* out, ArrowSchema* out_schema, int32_t* has_batch) {
+  return guarded([&] {
+    if (p->results.empty()) {
+      if (has_batch) *has_batch = 0;
+      return;
+    }
+    export_batch(p->results.front(), out, out_schema);
+    p->results.pop_front();
+    if (has_batch) *has_batch = 1;
+  });
+}
+int sqlrs_oracle_plan_reset(sqlrs_plan* p) {
+  return guarded([&] {
+    p->tables.clear();
+    p->results.clear();
+  });
+}
+const char* sqlrs_oracle_plan_describe(sqlrs_plan* p) { return p->description.c_str(); }
+void sqlrs_oracle_plan_destroy(sqlrs_plan* p) { delete p; }
+
+// ------------------------------------------------------------------ synthetic tables
+int32_t sqlrs_oracle_tpch_num_columns(int32_t table) {
+  switch (table) {
+    case SQLRS_TPCH_CUSTOMER: return SQLRS_CUSTOMER_NCOLS;
+    case SQLRS_TPCH_ORDERS: return SQLRS_ORDERS_NCOLS;
+    case SQLRS_TPCH_LINEITEM: return SQLRS_LINEITEM_NCOLS;
+  }
+  return -1;
+}
+int64_t sqlrs_oracle_tpch_num_rows(const sqlrs_tpch_dims* dims, int32_t table) {
+  if (!dims) return -1;
+  switch (table) {
+    case SQLRS_TPCH_CUSTOMER: return dims->n_customer;
+    case SQLRS_TPCH_ORDERS: return dims->n_orders;
+    case SQLRS_TPCH_LINEITEM: return sqlrs_tpch_lineitem_rows(dims->n_orders);
+  }
+  return -1;
+}
+int sqlrs_oracle_tpch_generate(const sqlrs_tpch_dims* dims, int32_t table, int64_t row_begin, int64_t row_end,
+                               void* const* columns, void*) {
+  return guarded([&] {
+    int32_t ncols = sqlrs_oracle_tpch_num_columns(table);
+    int64_t nrows = sqlrs_oracle_tpch_num_rows(dims, table);
+    if (ncols < 0 || nrows < 0) fail(SQLRS_ERR_INVALID_ARG, "bad table / dims");
+    if (row_begin < 0 || row_end < row_begin || row_end > nrows) fail(SQLRS_ERR_INVALID_ARG, "row range out of bounds");
+    for (int32_t c = 0; c < ncols; c++) {
+      uint64_t* dst = (uint64_t*)columns[c];
+      if (!dst) continue;  // NULL = column not wanted
+      // input production only (never timed): split the row range over the host threads
+      int64_t total = row_end - row_begin;
+      int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::thread::hardware_concurrency(), total / 65536));
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nt; t++) {
+        int64_t lo = row_begin + total * t / nt, hi = row_begin + total * (t + 1) / nt;
+        pool.emplace_back([=] {
+          for (int64_t r = lo; r < hi; r++)
+            dst[r - row_begin] = sqlrs_tpch_cell(table, c, r, dims->n_customer, dims->flags_mode);
+        });
+      }
+      for (auto& th : pool) th.join();
+    }
+  });
+}
+
+}  // extern "C"
