@@ -298,6 +298,19 @@ int64_t SQLRS_API(tpch_num_rows)(const sqlrs_tpch_dims* dims, int32_t table);
 int SQLRS_API(tpch_generate)(const sqlrs_tpch_dims* dims, int32_t table, int64_t row_begin,
                              int64_t row_end, void* const* columns, void* stream);
 
+/* ---- diagnostics / build check (need no GPU): the CUDA source the library generates for an
+ *      operator over batches of `input_schema` (nullable fields are assumed to carry a validity
+ *      bitmap), optionally compiled with NVRTC for sm_100a into the on-disk module cache.
+ *      *source_out is malloc'ed; release it with sqlrs_free.  The oracle build returns
+ *      SQLRS_ERR_UNSUPPORTED. ------------------------------------------------------------------ */
+int SQLRS_API(debug_compile_agg)(const sqlrs_agg_desc* aggs, int32_t n_aggs, const sqlrs_expr* group_by,
+                                 int32_t n_group_by, const sqlrs_expr* fused_predicate,
+                                 const struct ArrowSchema* input_schema, const sqlrs_options* options,
+                                 int32_t compile, char** source_out);
+int SQLRS_API(debug_compile_eval)(const sqlrs_expr* exprs, int32_t n_exprs, int32_t as_keep_mask,
+                                  const struct ArrowSchema* input_schema, int32_t compile, char** source_out);
+void SQLRS_API(free)(void* p);
+
 #ifdef __cplusplus
 }
 #endif

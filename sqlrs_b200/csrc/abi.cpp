@@ -1,0 +1,346 @@
+// sqlrs_b200 — the extern "C" boundary of include/sqlrs_b200.h (symbols sqlrs_*), CUDA build.
+// Every entry point catches C++ exceptions and maps them to the status codes of the header; the
+// library never aborts the process (the reference panics in several of these places).
+#include "../../include/sqlrs_tpch_spec.h"
+#include "join.hpp"
+#include "kernels_aot.hpp"
+#include "ops.hpp"
+#include "plan.hpp"
+
+using namespace sq;
+
+static thread_local std::string g_last_error;
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    f();
+    g_last_error.clear();
+    return SQLRS_OK;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    cudaGetLastError();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    cudaGetLastError();
+    return SQLRS_ERR_INTERNAL;
+  }
+}
+
+static std::vector<ExprCopy> copy_exprs(const sqlrs_expr* e, int32_t n) {
+  std::vector<ExprCopy> out;
+  if (n > 0 && !e) fail(SQLRS_ERR_INVALID_ARG, "expression array is NULL");
+  for (int32_t k = 0; k < n; k++) out.push_back(copy_expr(&e[k]));
+  return out;
+}
+static std::vector<std::string> copy_names(const char* const* names, int32_t n) {
+  std::vector<std::string> out;
+  for (int32_t k = 0; k < n; k++) out.push_back(names && names[k] ? names[k] : "");
+  return out;
+}
+
+struct sqlrs_filter {
+  FilterOp op;
+  sqlrs_filter(const ExprCopy& p, const Options& o) : op(p, o) {}
+};
+struct sqlrs_simple_agg {
+  AggOp op;
+  sqlrs_simple_agg(std::vector<AggSpec> a, const Options& o) : op(std::move(a), {}, {}, true, {}, o) {}
+};
+struct sqlrs_hash_agg {
+  AggOp op;
+  sqlrs_hash_agg(std::vector<AggSpec> a, std::vector<ExprCopy> g, std::vector<std::string> names, const Options& o)
+      : op(std::move(a), std::move(g), std::move(names), false, {}, o) {}
+};
+struct sqlrs_hash_join {
+  JoinOp op;
+  sqlrs_hash_join(int type, std::vector<ExprCopy> lk, std::vector<ExprCopy> rk, ExprCopy filter, std::vector<Field> fields,
+                  const Options& o)
+      : op(type, std::move(lk), std::move(rk), std::move(filter), std::move(fields), o) {}
+};
+struct sqlrs_plan {
+  Plan impl;
+  sqlrs_plan(const sqlrs_plan_node* nodes, int32_t n, int32_t root, const Options& o) : impl(nodes, n, root, o) {}
+};
+
+extern "C" {
+
+int sqlrs_abi_version(void) { return SQLRS_ABI_VERSION; }
+const char* sqlrs_last_error(void) { return g_last_error.c_str(); }
+int64_t sqlrs_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int sqlrs_create_hashes(ArrowArray* columns, const ArrowSchema* schema, uint64_t* out_hashes) {
+  return guarded([&] {
+    Options opt;
+    Ctx ctx(opt);
+    DBatch b = import_batch_host(ctx, columns, schema);
+    EvalRequest req;
+    for (size_t c = 0; c < b.cols.size(); c++) {
+      ExprNodeCopy n;
+      n.op = SQLRS_OP_INPUT_REF;
+      n.index = (int)c;
+      n.dtype = b.cols[c].dtype;
+      req.exprs.push_back(ExprCopy{n});
+      req.is_key.push_back(true);
+    }
+    req.outs.push_back({OUT_HASH, 0});
+    EvalProgram prog(std::move(req));
+    EvalResult r = prog.run(ctx, b, "create_hashes");
+    if (b.n) SQ_CUDA(cudaMemcpyAsync(out_hashes, r.cols[0].data, (size_t)b.n * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+  });
+}
+
+int sqlrs_eval_expr(const sqlrs_expr* expr, const sqlrs_options* options, ArrowArray* batch, const ArrowSchema* schema, ArrowArray* out,
+                    ArrowSchema* out_schema) {
+  return guarded([&] {
+    Ctx ctx(copy_options(options));
+    DBatch b = import_batch_host(ctx, batch, schema);
+    EvalRequest req;
+    req.exprs.push_back(copy_expr(expr));
+    req.is_key.push_back(false);
+    req.outs.push_back({OUT_VALUE, 0});
+    EvalProgram prog(std::move(req));
+    EvalResult r = prog.run(ctx, b, "expression");
+    DBatch res;
+    res.n = b.n;
+    res.cols.push_back(r.cols[0]);
+    res.fields.push_back(Field{"expr", r.cols[0].dtype, true});
+    export_batch_host(ctx, res, out, out_schema);
+  });
+}
+
+int sqlrs_filter_create(const sqlrs_expr* predicate, const sqlrs_options* options, sqlrs_filter** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_filter(copy_expr(predicate), copy_options(options));
+  });
+}
+int sqlrs_filter_execute(sqlrs_filter* f, ArrowArray* batch, const ArrowSchema* schema, ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] {
+    if (!f) fail(SQLRS_ERR_INVALID_ARG, "filter handle is NULL");
+    f->op.ctx().activate();
+    DBatch b = import_batch_host(f->op.ctx(), batch, schema);
+    DBatch r = f->op.execute(b);
+    export_batch_host(f->op.ctx(), r, out, out_schema);
+  });
+}
+void sqlrs_filter_destroy(sqlrs_filter* f) { delete f; }
+
+int sqlrs_simple_agg_create(const sqlrs_agg_desc* aggs, int32_t n_aggs, const sqlrs_options* options, sqlrs_simple_agg** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_simple_agg(copy_aggs(aggs, n_aggs), copy_options(options));
+  });
+}
+int sqlrs_simple_agg_push(sqlrs_simple_agg* a, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!a) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    a->op.ctx().activate();
+    a->op.push(import_batch_host(a->op.ctx(), batch, schema));
+  });
+}
+int sqlrs_simple_agg_finish(sqlrs_simple_agg* a, ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] {
+    if (!a) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    a->op.finish_host(out, out_schema);
+  });
+}
+void sqlrs_simple_agg_destroy(sqlrs_simple_agg* a) { delete a; }
+
+int sqlrs_hash_agg_create(const sqlrs_agg_desc* aggs, int32_t n_aggs, const sqlrs_expr* group_by, const char* const* group_names,
+                          int32_t n_group_by, const sqlrs_options* options, sqlrs_hash_agg** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_hash_agg(copy_aggs(aggs, n_aggs), copy_exprs(group_by, n_group_by), copy_names(group_names, n_group_by),
+                              copy_options(options));
+  });
+}
+int sqlrs_hash_agg_push(sqlrs_hash_agg* a, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!a) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    a->op.ctx().activate();
+    a->op.push(import_batch_host(a->op.ctx(), batch, schema));
+  });
+}
+int sqlrs_hash_agg_finish(sqlrs_hash_agg* a, ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] {
+    if (!a) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    a->op.finish_host(out, out_schema);
+  });
+}
+void sqlrs_hash_agg_destroy(sqlrs_hash_agg* a) { delete a; }
+
+int sqlrs_hash_join_create(int32_t join_type, const sqlrs_expr* left_keys, const sqlrs_expr* right_keys, int32_t n_keys,
+                           const sqlrs_expr* filter, const ArrowSchema* join_output_schema, const sqlrs_options* options,
+                           sqlrs_hash_join** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    if (join_type < SQLRS_JOIN_INNER || join_type > SQLRS_JOIN_FULL) fail(SQLRS_ERR_INVALID_ARG, "bad join type");
+    if (n_keys < 1) fail(SQLRS_ERR_INTERNAL, "HashJoin must has on condition");
+    ExprCopy flt;
+    if (filter && filter->n_nodes > 0) flt = copy_expr(filter);
+    *out = new sqlrs_hash_join(join_type, copy_exprs(left_keys, n_keys), copy_exprs(right_keys, n_keys), flt,
+                               import_fields(join_output_schema), copy_options(options));
+  });
+}
+int sqlrs_hash_join_build_push(sqlrs_hash_join* j, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!j) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    j->op.ctx().activate();
+    j->op.build_push(import_batch_host(j->op.ctx(), batch, schema));
+  });
+}
+int sqlrs_hash_join_probe(sqlrs_hash_join* j, ArrowArray* batch, const ArrowSchema* schema, ArrowArray* out, ArrowSchema* out_schema,
+                          int32_t* has_batch) {
+  return guarded([&] {
+    if (!j) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    j->op.ctx().activate();
+    DBatch b = import_batch_host(j->op.ctx(), batch, schema);
+    DBatch r;
+    bool has = j->op.probe(b, &r);
+    if (has_batch) *has_batch = has;
+    if (has) export_batch_host(j->op.ctx(), r, out, out_schema);
+    else j->op.ctx().sync();
+  });
+}
+int sqlrs_hash_join_finish(sqlrs_hash_join* j, ArrowArray* out, ArrowSchema* out_schema, int32_t* has_batch) {
+  return guarded([&] {
+    if (!j) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    j->op.ctx().activate();
+    DBatch r;
+    bool has = j->op.finish(&r);
+    if (has_batch) *has_batch = has;
+    if (has) export_batch_host(j->op.ctx(), r, out, out_schema);
+  });
+}
+void sqlrs_hash_join_destroy(sqlrs_hash_join* j) { delete j; }
+
+int sqlrs_plan_create(const sqlrs_plan_node* nodes, int32_t n_nodes, int32_t root, const sqlrs_options* options, sqlrs_plan** out) {
+  return guarded([&] {
+    if (!out || !nodes || n_nodes < 1 || root < 0 || root >= n_nodes) fail(SQLRS_ERR_INVALID_ARG, "bad plan");
+    *out = new sqlrs_plan(nodes, n_nodes, root, copy_options(options));
+  });
+}
+int sqlrs_plan_push_table(sqlrs_plan* p, int32_t table_slot, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.ctx().activate();
+    p->impl.push_table(table_slot, import_batch_host(p->impl.ctx(), batch, schema));
+  });
+}
+int sqlrs_plan_push_table_device(sqlrs_plan* p, int32_t table_slot, ArrowDeviceArray* batch, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.ctx().activate();
+    p->impl.push_table(table_slot, import_batch_device(p->impl.ctx(), batch, schema));
+  });
+}
+int sqlrs_plan_execute(sqlrs_plan* p) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.ctx().activate();
+    p->impl.execute();
+  });
+}
+int sqlrs_plan_next(sqlrs_plan* p, ArrowArray* out, ArrowSchema* out_schema, int32_t* has_batch) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.ctx().activate();
+    bool has = p->impl.next(out, out_schema);
+    if (has_batch) *has_batch = has;
+  });
+}
+int sqlrs_plan_reset(sqlrs_plan* p) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.reset();
+  });
+}
+const char* sqlrs_plan_describe(sqlrs_plan* p) { return p ? p->impl.describe() : ""; }
+void sqlrs_plan_destroy(sqlrs_plan* p) { delete p; }
+
+// ------------------------------------------------------------------ synthetic tables
+int32_t sqlrs_tpch_num_columns(int32_t table) {
+  switch (table) {
+    case SQLRS_TPCH_CUSTOMER: return SQLRS_CUSTOMER_NCOLS;
+    case SQLRS_TPCH_ORDERS: return SQLRS_ORDERS_NCOLS;
+    case SQLRS_TPCH_LINEITEM: return SQLRS_LINEITEM_NCOLS;
+  }
+  return -1;
+}
+int64_t sqlrs_tpch_num_rows(const sqlrs_tpch_dims* dims, int32_t table) {
+  if (!dims) return -1;
+  switch (table) {
+    case SQLRS_TPCH_CUSTOMER: return dims->n_customer;
+    case SQLRS_TPCH_ORDERS: return dims->n_orders;
+    case SQLRS_TPCH_LINEITEM: return sqlrs_tpch_lineitem_rows(dims->n_orders);
+  }
+  return -1;
+}
+int sqlrs_tpch_generate(const sqlrs_tpch_dims* dims, int32_t table, int64_t row_begin, int64_t row_end, void* const* columns,
+                        void* stream) {
+  return guarded([&] {
+    int32_t ncols = sqlrs_tpch_num_columns(table);
+    int64_t nrows = sqlrs_tpch_num_rows(dims, table);
+    if (ncols < 0 || nrows < 0) fail(SQLRS_ERR_INVALID_ARG, "bad table / dims");
+    if (row_begin < 0 || row_end < row_begin || row_end > nrows) fail(SQLRS_ERR_INVALID_ARG, "row range out of bounds");
+    for (int32_t c = 0; c < ncols; c++) {
+      if (!columns[c]) continue;  // NULL = column not wanted
+      launch_tpch_generate(table, c, row_begin, row_end - row_begin, dims->n_customer, dims->flags_mode, (uint64_t*)columns[c],
+                           (cudaStream_t)stream);
+    }
+  });
+}
+
+// ------------------------------------------------------------------ diagnostics (no GPU needed)
+static std::vector<ColInfo> cols_of_schema(const ArrowSchema* schema) {
+  std::vector<ColInfo> cols;
+  for (const Field& f : import_fields(schema)) cols.push_back(ColInfo{f.dtype, f.nullable, f.nullable});
+  return cols;
+}
+static char* dup_string(const std::string& s) {
+  char* p = (char*)std::malloc(s.size() + 1);
+  if (!p) fail(SQLRS_ERR_INTERNAL, "out of host memory");
+  std::memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+
+int sqlrs_debug_compile_agg(const sqlrs_agg_desc* aggs, int32_t n_aggs, const sqlrs_expr* group_by, int32_t n_group_by,
+                            const sqlrs_expr* fused_predicate, const ArrowSchema* input_schema, const sqlrs_options* options,
+                            int32_t compile, char** source_out) {
+  return guarded([&] {
+    Options opt = copy_options(options);
+    opt.device_id = -2;  // offline: code generation only
+    ExprCopy pred;
+    if (fused_predicate && fused_predicate->n_nodes > 0) pred = copy_expr(fused_predicate);
+    std::vector<std::string> names((size_t)n_group_by);
+    AggOp op(copy_aggs(aggs, n_aggs), copy_exprs(group_by, n_group_by), names, n_group_by == 0, pred, opt);
+    std::string gen = op.debug_source(cols_of_schema(input_schema));
+    if (compile) jit_compile_to_cubin("agg", gen, nullptr);
+    if (source_out) *source_out = dup_string(jit_full_source("agg", gen));
+  });
+}
+
+int sqlrs_debug_compile_eval(const sqlrs_expr* exprs, int32_t n_exprs, int32_t as_keep_mask, const ArrowSchema* input_schema,
+                             int32_t compile, char** source_out) {
+  return guarded([&] {
+    EvalRequest req;
+    for (int32_t k = 0; k < n_exprs; k++) {
+      req.exprs.push_back(copy_expr(&exprs[k]));
+      req.is_key.push_back(false);
+      req.outs.push_back({as_keep_mask ? OUT_KEEP : OUT_VALUE, k});
+    }
+    EvalProgram prog(std::move(req));
+    std::vector<int> od, ed;
+    std::vector<bool> on;
+    std::string gen = prog.source_for(cols_of_schema(input_schema), &od, &on, &ed);
+    if (compile) jit_compile_to_cubin("eval", gen, nullptr);
+    if (source_out) *source_out = dup_string(jit_full_source("eval", gen));
+  });
+}
+
+void sqlrs_free(void* p) { std::free(p); }
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// sqlrs_b200 — shared host-side plumbing of the CUDA library: status/error type, CUDA error
+// checks, the launch counter behind sqlrs_kernel_launches(), small helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sqlrs_b200.h"
+
+namespace sq {
+
+// ExecutorError (reference src/executor/mod.rs:67-85) carried as status code + message.
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+[[noreturn]] inline void fail(int code, const std::string& m) { throw Error(code, m); }
+
+#define SQ_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      ::sq::fail(SQLRS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));             \
+  } while (0)
+
+extern std::atomic<int64_t> g_kernel_launches;
+inline void count_launch(int64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+inline const char* dtype_name(int dt) {
+  switch (dt) {
+    case SQLRS_DT_NULL: return "Null";
+    case SQLRS_DT_BOOL: return "Boolean";
+    case SQLRS_DT_INT32: return "Int32";
+    case SQLRS_DT_INT64: return "Int64";
+    case SQLRS_DT_FLOAT64: return "Float64";
+    case SQLRS_DT_UTF8: return "Utf8";
+  }
+  return "?";
+}
+inline bool is_numeric(int dt) { return dt == SQLRS_DT_INT32 || dt == SQLRS_DT_INT64 || dt == SQLRS_DT_FLOAT64; }
+// bytes per value of the fixed-width device layout (Boolean is bit-packed: 0 here)
+inline int dtype_width(int dt) {
+  switch (dt) {
+    case SQLRS_DT_INT32: return 4;
+    case SQLRS_DT_INT64:
+    case SQLRS_DT_FLOAT64: return 8;
+  }
+  return 0;
+}
+inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t bitmap_words(int64_t n) { return div_up(n, 32); }  // device bitmaps are u32-word granular
+
+struct Options {
+  int count_mode = SQLRS_COUNT_REFERENCE_OVERWRITE;
+  int match_mode = SQLRS_MATCH_HASH_ONLY;
+  int device_id = -1;
+  int flags = 0;
+  cudaStream_t stream = nullptr;  // user stream, or nullptr = library-owned
+};
+inline Options copy_options(const sqlrs_options* o) {
+  Options r;
+  if (o) {
+    r.count_mode = o->count_mode;
+    r.match_mode = o->match_mode;
+    r.device_id = o->device_id;
+    r.flags = o->flags;
+    r.stream = (cudaStream_t)o->stream;
+  }
+  return r;
+}
+
+}  // namespace sq

@@ -1,0 +1,302 @@
+// sqlrs_b200 JIT skeleton "agg": fused Filter -> expression -> GROUP BY / aggregate over one batch.
+// Replaces the reference's per-batch "hash rows -> HashMap -> take per group -> update_batch"
+// (src/executor/aggregate/hash_agg.rs:33-150, simple_agg.rs:27-65, accumulators sum.rs / count.rs /
+// min_max.rs) and, when the child is a Filter, filter.rs:14-26 as well: every input column is read
+// once, nothing is materialised.
+//
+// Generated in front of this file:
+//   SQ_NCOLS, SQ_NKEYS (K), SQ_NACC (W accumulator words per group), SQ_MATCH_KEYS, SQ_BLOCK (T),
+//   SQ_SLOTS (S), SQ_UNROLL (R), struct SqIn, struct SqRow {pass, h, kb[K], knull, args...},
+//   sq_row(in, r, o, e0, e1), sq_acc_identity(w), sq_acc_update(a, stride, o),
+//   sq_acc_reduce(w, x, y), sq_acc_merge_global(p, w, x, batch_no)
+//
+// Two kernels over the same row program:
+//  * sq_agg_small  — few groups (<= SQ_SLOTS per CTA): every thread owns a PRIVATE copy of the
+//    accumulators in shared memory ([word][slot][thread], 8-byte lanes -> conflict-free), so the hot
+//    loop has no atomics at all; group slots come from a tiny CTA-shared open-addressed table.
+//    CTA partials go to a scratch area, sq_agg_merge folds them into the operator's table in HBM.
+//    HBM-bound: algorithmic bytes = 8 B x referenced columns per row.
+//  * sq_agg_global — many groups: open-addressed table in HBM, one find-or-insert + native 64-bit
+//    atomics per row and accumulator word.
+// Group identity = the reference's 64-bit row hash (quirk K2), optionally plus the key tuple
+// (SQLRS_MATCH_HASH_AND_KEY).  First-appearance order is kept as the minimum global row id.
+
+struct SqTable {      // the operator's persistent group table in HBM (SoA, capacity = power of two)
+  u32* state;         // 0 empty, 1 being written, 2 ready
+  u64* hash;          // group identity (row hash)
+  u64* min_row;       // first global row id of the group
+  u64* keys;          // [K][capacity] raw key bits (NULL cells 0)
+  u32* knull;         // null mask of the key tuple
+  u64* acc;           // [W][capacity]
+  u32* new_slots;     // slots inserted since the last key fix-up
+  u32* counters;      // [0] groups, [1] new_slots length, [2] status bits
+  u32 capacity;
+};
+#define SQ_STATUS_OVERFLOW 1u   /* sq_agg_small: more groups than SQ_SLOTS in some CTA */
+#define SQ_STATUS_FULL 2u       /* table ran out of slots (host sized it wrongly) */
+
+struct SqPartial {    // CTA partials of sq_agg_small: [cta][slot]
+  u32* state;
+  u64* hash;
+  u64* min_row;
+  u64* keys;          // [(cta*S+slot)*K + k]
+  u32* knull;
+  u64* acc;           // [(cta*S+slot)*W + w]
+};
+
+__device__ __forceinline__ bool sq_keys_equal(const u64* a, u32 an, const u64* b, u32 bn) {
+#if SQ_MATCH_KEYS
+  if (an != bn) return false;
+#pragma unroll
+  for (int k = 0; k < SQ_NKEYS; k++)
+    if (a[k] != b[k]) return false;
+#endif
+  return true;
+}
+
+// find-or-insert in the HBM table; returns the slot or -1 (table full)
+__device__ __forceinline__ int sq_table_upsert(const SqTable& t, u64 h, const u64* kb, u32 knull) {
+  const u32 mask = t.capacity - 1;
+  u32 s = sq_mix32(h) & mask;
+  for (u32 probes = 0; probes <= mask;) {
+    u32 st = *((volatile u32*)&t.state[s]);
+    if (st == 0) {
+      if (atomicCAS(&t.state[s], 0u, 1u) == 0u) {
+        t.hash[s] = h;
+#pragma unroll
+        for (int k = 0; k < SQ_NKEYS; k++) t.keys[(size_t)k * t.capacity + s] = kb[k];
+        t.knull[s] = knull;
+        __threadfence();
+        atomicExch(&t.state[s], 2u);
+        atomicAdd(&t.counters[0], 1u);
+        t.new_slots[atomicAdd(&t.counters[1], 1u)] = s;
+        return (int)s;
+      }
+      continue;  // lost the race: look at the slot again
+    }
+    if (st == 1) continue;  // another thread is publishing this slot
+    __threadfence();
+    if (*((volatile u64*)&t.hash[s]) == h) {
+#if SQ_MATCH_KEYS
+      u64 other[SQ_NKEYS > 0 ? SQ_NKEYS : 1];
+#pragma unroll
+      for (int k = 0; k < SQ_NKEYS; k++) other[k] = *((volatile u64*)&t.keys[(size_t)k * t.capacity + s]);
+      if (sq_keys_equal(other, *((volatile u32*)&t.knull[s]), kb, knull)) return (int)s;
+#else
+      return (int)s;
+#endif
+    }
+    s = (s + 1) & mask;
+    probes++;
+  }
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory layout of sq_agg_small
+//   u64 acc[(W+1)][S][T]   word W = min row id
+//   u64 thash[S]; u64 tkeys[S][K]; u32 tknull[S]; u32 tstate[S]; u32 flags
+#define SQ_ACC_WORDS (SQ_NACC + 1)
+#define SQ_SMEM_ACC_BYTES ((size_t)SQ_ACC_WORDS * SQ_SLOTS * SQ_BLOCK * 8)
+
+extern "C" __global__ void __launch_bounds__(SQ_BLOCK) sq_agg_small(SqIn in, i64 n, i64 row_base, SqPartial part,
+                                                                     u32* __restrict__ status, u32* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char sq_smem[];
+  u64* acc = (u64*)sq_smem;
+  u64* thash = acc + (size_t)SQ_ACC_WORDS * SQ_SLOTS * SQ_BLOCK;
+  u64* tkeys = thash + SQ_SLOTS;
+  u32* tknull = (u32*)(tkeys + SQ_SLOTS * (SQ_NKEYS > 0 ? SQ_NKEYS : 1));
+  u32* tstate = tknull + SQ_SLOTS;
+  u32* flags = tstate + SQ_SLOTS;
+  const int tid = threadIdx.x;
+
+  if ((*((volatile u32*)status) & SQ_STATUS_OVERFLOW) != 0u) return;  // sticky: the global kernel owns this operator now
+
+#pragma unroll
+  for (int w = 0; w < SQ_ACC_WORDS; w++) {
+    const u64 ident = (w == SQ_NACC) ? SQ_EMPTY_ROW : sq_acc_identity(w);
+#pragma unroll
+    for (int s = 0; s < SQ_SLOTS; s++) acc[((size_t)w * SQ_SLOTS + s) * SQ_BLOCK + tid] = ident;
+  }
+  if (tid < SQ_SLOTS) tstate[tid] = 0u;
+  if (tid == 0) *flags = 0u;
+  __syncthreads();
+
+  bool any_err = false;
+  const i64 tile = (i64)SQ_BLOCK * SQ_UNROLL;
+  for (i64 base = (i64)blockIdx.x * tile; base < n; base += (i64)gridDim.x * tile) {
+    SqRow o[SQ_UNROLL];
+    bool live[SQ_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SQ_UNROLL; u++) {
+      const i64 r = base + (i64)u * SQ_BLOCK + tid;
+      const bool inb = r < n;
+      bool e0 = false, e1 = false;
+      sq_row(in, inb ? r : n - 1, o[u], e0, e1);
+      live[u] = inb && o[u].pass;
+      any_err |= (inb && e0) || (live[u] && e1);
+    }
+#pragma unroll
+    for (int u = 0; u < SQ_UNROLL; u++) {
+      if (!live[u]) continue;
+      int slot = 0;
+#if SQ_NKEYS > 0
+      // CTA-shared slot table: claim (CAS 0->1), write identity, publish (2); readers of a slot
+      // being written spin — independent thread scheduling guarantees the writer progresses
+      slot = -1;
+      u32 s = sq_mix32(o[u].h) & (SQ_SLOTS - 1);
+      for (int probes = 0; probes < SQ_SLOTS;) {
+        const u32 st = *((volatile u32*)&tstate[s]);
+        if (st == 0u) {
+          if (atomicCAS(&tstate[s], 0u, 1u) == 0u) {
+            thash[s] = o[u].h;
+#pragma unroll
+            for (int k = 0; k < SQ_NKEYS; k++) tkeys[s * SQ_NKEYS + k] = o[u].kb[k];
+            tknull[s] = o[u].knull;
+            __threadfence_block();
+            atomicExch(&tstate[s], 2u);
+            slot = (int)s;
+            break;
+          }
+          continue;
+        }
+        if (st == 1u) continue;
+        __threadfence_block();
+        if (*((volatile u64*)&thash[s]) == o[u].h) {
+#if SQ_MATCH_KEYS
+          u64 other[SQ_NKEYS];
+#pragma unroll
+          for (int k = 0; k < SQ_NKEYS; k++) other[k] = *((volatile u64*)&tkeys[s * SQ_NKEYS + k]);
+          if (sq_keys_equal(other, *((volatile u32*)&tknull[s]), o[u].kb, o[u].knull)) {
+            slot = (int)s;
+            break;
+          }
+#else
+          slot = (int)s;
+          break;
+#endif
+        }
+        s = (s + 1) & (SQ_SLOTS - 1);
+        probes++;
+      }
+      if (slot < 0) {  // more than SQ_SLOTS groups: the host reruns this batch on the HBM table
+        *((volatile u32*)flags) = 1u;
+        continue;
+      }
+#endif
+      u64* a = acc + (size_t)slot * SQ_BLOCK + tid;
+      sq_acc_update(a, SQ_SLOTS * SQ_BLOCK, o[u]);
+      u64* mr = a + (size_t)SQ_NACC * SQ_SLOTS * SQ_BLOCK;
+      const u64 gr = (u64)(row_base + base + (i64)u * SQ_BLOCK + tid);
+      if (gr < *mr) *mr = gr;
+    }
+  }
+  if (any_err) atomicOr(err, 1u);
+  __syncthreads();
+  if (*((volatile u32*)flags) != 0u) {
+    if (tid == 0) atomicOr(status, SQ_STATUS_OVERFLOW);
+    // still publish an empty partial so that the merge sees a defined state
+    if (tid < SQ_SLOTS) part.state[(size_t)blockIdx.x * SQ_SLOTS + tid] = 0u;
+    return;
+  }
+
+  // fold the T private copies: one warp per (word, slot), lanes stride over the threads
+  const int lane = tid & 31, wid = tid >> 5;
+  for (int item = wid; item < SQ_ACC_WORDS * SQ_SLOTS; item += SQ_BLOCK / 32) {
+    const int w = item / SQ_SLOTS, s = item % SQ_SLOTS;
+    const u64* src = acc + ((size_t)w * SQ_SLOTS + s) * SQ_BLOCK;
+    u64 x = src[lane];
+    for (int t = lane + 32; t < SQ_BLOCK; t += 32) x = (w == SQ_NACC) ? (src[t] < x ? src[t] : x) : sq_acc_reduce(w, x, src[t]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const u64 y = __shfl_xor_sync(SQ_FULL, x, d);
+      x = (w == SQ_NACC) ? (y < x ? y : x) : sq_acc_reduce(w, x, y);
+    }
+    if (lane == 0) {
+      const size_t e = (size_t)blockIdx.x * SQ_SLOTS + s;
+      if (w == SQ_NACC) part.min_row[e] = x;
+      else part.acc[e * SQ_NACC + w] = x;
+    }
+  }
+  if (tid < SQ_SLOTS) {
+    const size_t e = (size_t)blockIdx.x * SQ_SLOTS + tid;
+#if SQ_NKEYS > 0
+    part.state[e] = tstate[tid];
+    part.hash[e] = thash[tid];
+    part.knull[e] = tknull[tid];
+#pragma unroll
+    for (int k = 0; k < SQ_NKEYS; k++) part.keys[e * SQ_NKEYS + k] = tkeys[tid * SQ_NKEYS + k];
+#else
+    part.state[e] = tid == 0 ? 2u : 0u;
+    part.hash[e] = 0ULL;
+    part.knull[e] = 0u;
+#endif
+  }
+}
+
+// folds the CTA partials of one batch into the operator's table; one thread per (cta, slot)
+extern "C" __global__ void __launch_bounds__(128) sq_agg_merge(SqPartial part, int n_entries, SqTable table, i64 batch_no,
+                                                                u32* __restrict__ status) {
+  if ((*((volatile u32*)status) & SQ_STATUS_OVERFLOW) != 0u) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  if (part.state[e] != 2u) return;
+  const u64 mr = part.min_row[e];
+  if (mr == SQ_EMPTY_ROW) return;  // slot claimed but no surviving row (cannot happen; defensive)
+  u64 kb[SQ_NKEYS > 0 ? SQ_NKEYS : 1];
+#pragma unroll
+  for (int k = 0; k < SQ_NKEYS; k++) kb[k] = part.keys[(size_t)e * SQ_NKEYS + k];
+  const int slot = sq_table_upsert(table, part.hash[e], kb, part.knull[e]);
+  if (slot < 0) {
+    atomicOr(status, SQ_STATUS_FULL);
+    return;
+  }
+  atomicMin(&table.min_row[slot], mr);
+#pragma unroll
+  for (int w = 0; w < SQ_NACC; w++)
+    sq_acc_merge_global(&table.acc[(size_t)w * table.capacity + slot], w, part.acc[(size_t)e * SQ_NACC + w], batch_no);
+}
+
+// many groups: straight into the HBM table
+extern "C" __global__ void __launch_bounds__(256) sq_agg_global(SqIn in, i64 n, i64 row_base, SqTable table, i64 batch_no,
+                                                                 u32* __restrict__ status, u32* __restrict__ err) {
+  bool any_err = false;
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    SqRow o;
+    bool e0 = false, e1 = false;
+    sq_row(in, r, o, e0, e1);
+    any_err |= e0 || (o.pass && e1);
+    if (!o.pass) continue;
+    const int slot = sq_table_upsert(table, o.h, o.kb, o.knull);
+    if (slot < 0) {
+      atomicOr(status, SQ_STATUS_FULL);
+      continue;
+    }
+    atomicMin(&table.min_row[slot], (u64)(row_base + r));
+    u64 local[SQ_NACC > 0 ? SQ_NACC : 1];
+#pragma unroll
+    for (int w = 0; w < SQ_NACC; w++) local[w] = sq_acc_identity(w);
+    sq_acc_update(local, 1, o);
+#pragma unroll
+    for (int w = 0; w < SQ_NACC; w++) sq_acc_merge_global(&table.acc[(size_t)w * table.capacity + slot], w, local[w], batch_no);
+  }
+  if (any_err) atomicOr(err, 1u);
+}
+
+// quirk K2 exactness: with hash-only identity a group may hold rows with different key tuples and
+// the reference reports the keys of its FIRST row (hash_agg.rs:92-96).  After a batch, the slots
+// inserted during it get the key bits of their minimum row.
+extern "C" __global__ void __launch_bounds__(128) sq_agg_fixkeys(SqIn in, i64 n, i64 row_base, SqTable table, u32 n_new) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_new) return;
+  const u32 slot = table.new_slots[i];
+  const i64 r = (i64)(table.min_row[slot]) - row_base;
+  if (r < 0 || r >= n) return;
+  SqRow o;
+  bool e0 = false, e1 = false;
+  sq_row(in, r, o, e0, e1);
+#pragma unroll
+  for (int k = 0; k < SQ_NKEYS; k++) table.keys[(size_t)k * table.capacity + slot] = o.kb[k];
+  table.knull[slot] = o.knull;
+}

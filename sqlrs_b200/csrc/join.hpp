@@ -1,0 +1,35 @@
+// sqlrs_b200 — HashJoinExecutor on the GPU (reference src/executor/join/hash_join.rs:16-323).
+// Build side = left child, fully drained and kept resident; one output batch per probe batch in the
+// reference's row order (probe-row order, per probe row the build rows in insertion order); Left/Full
+// tail of unmatched build rows at finish.
+#pragma once
+#include "ops.hpp"
+
+namespace sq {
+
+class JoinOp {
+ public:
+  JoinOp(int join_type, std::vector<ExprCopy> left_keys, std::vector<ExprCopy> right_keys, ExprCopy filter,
+         std::vector<Field> out_fields, const Options& opt);
+  ~JoinOp();
+  void build_push(const DBatch& batch);
+  bool probe(const DBatch& right, DBatch* out);  // false where the reference yields nothing (empty build side)
+  bool finish(DBatch* out);                      // Left/Full tail
+  Ctx& ctx() { return ctx_; }
+
+ private:
+  struct Impl;
+  void seal();
+  DBatch build_batch(const DBatch& right, const int64_t* li, bool li_nullable, const uint32_t* ri, int64_t m);
+  void check_schema(DBatch& b);
+
+  Ctx ctx_;
+  Options opt_;
+  int join_type_;
+  std::vector<ExprCopy> left_keys_, right_keys_;
+  ExprCopy filter_;
+  std::vector<Field> out_fields_;
+  std::unique_ptr<Impl> impl_;
+};
+
+}  // namespace sq

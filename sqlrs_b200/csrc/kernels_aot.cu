@@ -1,0 +1,341 @@
+// sqlrs_b200 — ahead-of-time compiled CUDA kernels for sm_100a: synthetic table generator,
+// bitmap utilities, warp-ballot stream compaction, gathers (arrow `take`), group-table maintenance.
+// All of it is HBM-bound integer / byte work: coalesced 4/8-byte lanes, whole-word bitmap stores
+// through __ballot_sync, grids sized in multiples of the SM count.
+#include "kernels_aot.hpp"
+
+#include "../../include/sqlrs_tpch_spec.h"
+
+namespace sq {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+inline unsigned grid_for(int64_t items, int per_block, int64_t cap = 148 * 32) {
+  int64_t g = div_up(items, per_block);
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (unsigned)g;
+}
+
+// ------------------------------------------------------------------ generator
+__global__ void __launch_bounds__(kBlock) k_tpch_generate(int table, int col, int64_t row_begin, int64_t n, int64_t n_customer,
+                                                           int flags_mode, uint64_t* __restrict__ dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = sqlrs_tpch_cell(table, col, row_begin + i, n_customer, flags_mode);
+}
+
+// ------------------------------------------------------------------ bitmaps
+__global__ void __launch_bounds__(kBlock) k_count_bits(const uint32_t* __restrict__ bm, int64_t n, unsigned long long* out) {
+  const int64_t words = (n + 31) >> 5;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long local = 0;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += stride) {
+    uint32_t v = bm[w];
+    if (w == words - 1 && (n & 31)) v &= (1u << (n & 31)) - 1u;
+    local += __popc(v);
+  }
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+// one thread per destination word; partial first/last words are OR-ed in atomically
+__global__ void __launch_bounds__(kBlock) k_bitmap_append(uint32_t* __restrict__ dst, int64_t dst_off, const uint32_t* __restrict__ src,
+                                                           int64_t n) {
+  const int64_t first_word = dst_off >> 5, last_word = (dst_off + n - 1) >> 5;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t src_words = (n + 31) >> 5;
+  for (int64_t w = first_word + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w <= last_word; w += stride) {
+    // destination word w covers destination bits [w*32, w*32+32) = source bits [w*32-dst_off, ...)
+    const int64_t s0 = w * 32 - dst_off;  // may be negative for the first word
+    uint32_t v = 0;
+    if (!src) {
+      v = 0xffffffffu;
+    } else {
+      const int64_t sw = s0 >> 5;  // floor
+      const int sh = (int)(s0 & 31);
+      const uint32_t lo = (sw >= 0 && sw < src_words) ? src[sw] : 0u;
+      const uint32_t hi = (sw + 1 >= 0 && sw + 1 < src_words) ? src[sw + 1] : 0u;
+      v = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+    }
+    // mask to the valid source range [0, n)
+    uint32_t mask = 0xffffffffu;
+    if (s0 < 0) mask &= 0xffffffffu << (int)(-s0);
+    const int64_t end = s0 + 32 - n;  // bits past the end
+    if (end > 0) mask &= end >= 32 ? 0u : (0xffffffffu >> (int)end);
+    v &= mask;
+    if (mask == 0xffffffffu) dst[w] = v;
+    else if (v) atomicOr(&dst[w], v);
+  }
+}
+
+// ------------------------------------------------------------------ compaction
+constexpr int kChunkWords = 64;  // 2048 rows per warp-chunk
+
+__global__ void __launch_bounds__(kBlock) k_compact_count(const uint32_t* __restrict__ keep, int64_t n_words, int64_t n_chunks,
+                                                           uint32_t* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (kBlock / 32);
+  for (int64_t c = warp; c < n_chunks; c += nwarps) {
+    const int64_t w0 = c * kChunkWords;
+    uint32_t cnt = 0;
+    for (int j = lane; j < kChunkWords; j += 32)
+      if (w0 + j < n_words) cnt += __popc(keep[w0 + j]);
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if (lane == 0) counts[c] = cnt;
+  }
+}
+
+// exclusive scan of m u32 counts into u64 offsets; one CTA walks the array with a running carry
+__global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t* __restrict__ counts, int64_t m, unsigned long long* __restrict__ offsets,
+                                                    unsigned long long* __restrict__ total) {
+  __shared__ unsigned long long warp_sums[32];
+  __shared__ unsigned long long carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < m; base += 1024) {
+    const int64_t i = base + tid;
+    const unsigned long long v = i < m ? counts[i] : 0;
+    unsigned long long x = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long s = warp_sums[lane];
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, s, d);
+        if (lane >= d) s += y;
+      }
+      warp_sums[lane] = s;  // inclusive
+    }
+    __syncthreads();
+    const unsigned long long carry = carry_s;
+    const unsigned long long before = carry + (wid ? warp_sums[wid - 1] : 0) + (x - v);
+    if (i < m) offsets[i] = before;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sums[31];
+    __syncthreads();
+  }
+  if (tid == 0) *total = carry_s;
+}
+
+__global__ void __launch_bounds__(kBlock) k_compact_write(const uint32_t* __restrict__ keep, int64_t n_words, int64_t n_chunks,
+                                                           const unsigned long long* __restrict__ offsets, uint32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (kBlock / 32);
+  for (int64_t c = warp; c < n_chunks; c += nwarps) {
+    unsigned long long off = offsets[c];
+    const int64_t w0 = c * kChunkWords;
+    // lanes fetch two words each, then the warp walks the 64 words with the bits spread over lanes
+    const uint32_t mine0 = (w0 + lane < n_words) ? keep[w0 + lane] : 0u;
+    const uint32_t mine1 = (w0 + 32 + lane < n_words) ? keep[w0 + 32 + lane] : 0u;
+    for (int j = 0; j < kChunkWords; j++) {
+      const uint32_t word = __shfl_sync(0xffffffffu, j < 32 ? mine0 : mine1, j & 31);
+      if (word == 0u) continue;
+      if ((word >> lane) & 1u) out[off + __popc(word & ((1u << lane) - 1u))] = (uint32_t)((w0 + j) * 32 + lane);
+      off += __popc(word);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ gather
+template <typename Idx>
+__device__ __forceinline__ bool idx_ok(Idx i);
+template <>
+__device__ __forceinline__ bool idx_ok<uint32_t>(uint32_t) { return true; }
+template <>
+__device__ __forceinline__ bool idx_ok<int64_t>(int64_t i) { return i >= 0; }
+
+// WIDTH: 8 / 4 bytes, 0 = bit-packed Boolean values
+template <int WIDTH, typename Idx>
+__global__ void __launch_bounds__(kBlock) k_gather(const void* __restrict__ src, const uint32_t* __restrict__ src_valid,
+                                                    const Idx* __restrict__ idx, int64_t m, void* __restrict__ dst,
+                                                    uint32_t* __restrict__ dst_valid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t m_up = (m + 31) & ~(int64_t)31;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m_up; k += stride) {
+    const bool inb = k < m;
+    Idx i = inb ? idx[k] : (Idx)0;
+    const bool ok = inb && idx_ok<Idx>(i);
+    const uint64_t r = ok ? (uint64_t)i : 0;
+    bool valid = ok;
+    if (ok && src_valid) valid = (src_valid[r >> 5] >> (r & 31)) & 1u;
+    if (WIDTH == 8) {
+      if (inb) ((uint64_t*)dst)[k] = ok ? ((const uint64_t*)src)[r] : 0ULL;
+    } else if (WIDTH == 4) {
+      if (inb) ((uint32_t*)dst)[k] = ok ? ((const uint32_t*)src)[r] : 0u;
+    } else {
+      const bool bit = ok && ((((const uint32_t*)src)[r >> 5] >> (r & 31)) & 1u);
+      const uint32_t w = __ballot_sync(0xffffffffu, bit);
+      if (lane == 0) ((uint32_t*)dst)[k >> 5] = w;
+    }
+    if (dst_valid) {
+      const uint32_t w = __ballot_sync(0xffffffffu, valid);
+      if (lane == 0) dst_valid[k >> 5] = w;
+    }
+  }
+}
+
+template <typename Idx>
+void launch_gather_t(int width, const void* src, const uint32_t* src_valid, const Idx* idx, int64_t m, void* dst, uint32_t* dst_valid,
+                     cudaStream_t stream) {
+  if (m <= 0) return;
+  unsigned grid = grid_for(m, kBlock);
+  if (width == 8) k_gather<8, Idx><<<grid, kBlock, 0, stream>>>(src, src_valid, idx, m, dst, dst_valid);
+  else if (width == 4) k_gather<4, Idx><<<grid, kBlock, 0, stream>>>(src, src_valid, idx, m, dst, dst_valid);
+  else k_gather<0, Idx><<<grid, kBlock, 0, stream>>>(src, src_valid, idx, m, dst, dst_valid);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(kBlock) k_fill_u64(uint64_t* __restrict__ dst, int64_t n, uint64_t value) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = value;
+}
+
+__global__ void __launch_bounds__(kBlock) k_idx_valid(const int64_t* __restrict__ idx, int64_t m, uint32_t* __restrict__ valid_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t m_up = (m + 31) & ~(int64_t)31;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m_up; k += stride) {
+    const uint32_t w = __ballot_sync(0xffffffffu, k < m && idx[k] >= 0);
+    if (lane == 0) valid_out[k >> 5] = w;
+  }
+}
+
+// ------------------------------------------------------------------ group table maintenance
+__global__ void __launch_bounds__(kBlock) k_table_compact(TableView t, int n_keys, int n_acc, uint64_t* out_hash, uint64_t* out_min_row,
+                                                           uint64_t* out_keys, uint32_t* out_knull, uint64_t* out_acc, uint32_t max_out,
+                                                           uint32_t* out_count) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
+    if (t.state[s] != 2u) continue;
+    const uint32_t o = atomicAdd(out_count, 1u);
+    if (o >= max_out) continue;
+    out_hash[o] = t.hash[s];
+    out_min_row[o] = t.min_row[s];
+    out_knull[o] = t.knull[s];
+    for (int k = 0; k < n_keys; k++) out_keys[(size_t)k * max_out + o] = t.keys[(size_t)k * t.capacity + s];
+    for (int w = 0; w < n_acc; w++) out_acc[(size_t)w * max_out + o] = t.acc[(size_t)w * t.capacity + s];
+  }
+}
+
+__device__ __forceinline__ uint32_t mix32(uint64_t h) {  // same spreader as sq_mix32 (csrc/jit/prelude.cuh)
+  h ^= h >> 33;
+  h *= 0xff51afd7ed558ccdULL;
+  h ^= h >> 29;
+  return (uint32_t)h;
+}
+
+// every source slot is a distinct group already: claim the first free slot on its probe path
+__global__ void __launch_bounds__(kBlock) k_table_rehash(TableView from, TableView to, int n_keys, int n_acc) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t mask = to.capacity - 1;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < from.capacity; s += stride) {
+    if (from.state[s] != 2u) continue;
+    const uint64_t h = from.hash[s];
+    uint32_t d = mix32(h) & mask;
+    while (atomicCAS(&to.state[d], 0u, 2u) != 0u) d = (d + 1) & mask;
+    to.hash[d] = h;
+    to.min_row[d] = from.min_row[s];
+    to.knull[d] = from.knull[s];
+    for (int k = 0; k < n_keys; k++) to.keys[(size_t)k * to.capacity + d] = from.keys[(size_t)k * from.capacity + s];
+    for (int w = 0; w < n_acc; w++) to.acc[(size_t)w * to.capacity + d] = from.acc[(size_t)w * from.capacity + s];
+  }
+}
+
+}  // namespace
+
+void launch_tpch_generate(int table, int col, int64_t row_begin, int64_t n, int64_t n_customer, int flags_mode, uint64_t* dst,
+                          cudaStream_t stream) {
+  if (n <= 0) return;
+  k_tpch_generate<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(table, col, row_begin, n, n_customer, flags_mode, dst);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+void launch_count_bits(const uint32_t* bitmap, int64_t n, unsigned long long* out, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_count_bits<<<grid_for((n + 31) / 32, kBlock, 148 * 4), kBlock, 0, stream>>>(bitmap, n, out);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+void launch_bitmap_append(uint32_t* dst, int64_t dst_bit_off, const uint32_t* src, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_bitmap_append<<<grid_for((n + 63) / 32, kBlock, 148 * 4), kBlock, 0, stream>>>(dst, dst_bit_off, src, n);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+size_t compact_num_chunks(int64_t n) { return (size_t)div_up(div_up(n, 32), kChunkWords); }
+
+void launch_compact_count(const uint32_t* keep, int64_t n, uint32_t* chunk_counts, cudaStream_t stream) {
+  if (n <= 0) return;
+  int64_t chunks = (int64_t)compact_num_chunks(n);
+  k_compact_count<<<grid_for(chunks, kBlock / 32, 148 * 8), kBlock, 0, stream>>>(keep, div_up(n, 32), chunks, chunk_counts);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+void launch_scan_u32(const uint32_t* counts, int64_t m, unsigned long long* offsets, unsigned long long* total, cudaStream_t stream) {
+  k_scan_u32<<<1, 1024, 0, stream>>>(counts, m, offsets, total);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+void launch_compact_write(const uint32_t* keep, int64_t n, const unsigned long long* chunk_offsets, uint32_t* out_idx, cudaStream_t stream) {
+  if (n <= 0) return;
+  int64_t chunks = (int64_t)compact_num_chunks(n);
+  k_compact_write<<<grid_for(chunks, kBlock / 32, 148 * 8), kBlock, 0, stream>>>(keep, div_up(n, 32), chunks, chunk_offsets, out_idx);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+void launch_gather_u32idx(int width, const void* src, const uint32_t* src_valid, const uint32_t* idx, int64_t m, void* dst,
+                          uint32_t* dst_valid, cudaStream_t stream) {
+  launch_gather_t<uint32_t>(width, src, src_valid, idx, m, dst, dst_valid, stream);
+}
+void launch_gather_i64idx(int width, const void* src, const uint32_t* src_valid, const int64_t* idx, int64_t m, void* dst,
+                          uint32_t* dst_valid, cudaStream_t stream) {
+  launch_gather_t<int64_t>(width, src, src_valid, idx, m, dst, dst_valid, stream);
+}
+
+void launch_fill_u64(uint64_t* dst, int64_t n, uint64_t value, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_fill_u64<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(dst, n, value);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+void launch_iota_filter_valid(const int64_t* idx, int64_t m, uint32_t* valid_out, cudaStream_t stream) {
+  if (m <= 0) return;
+  k_idx_valid<<<grid_for(m, kBlock), kBlock, 0, stream>>>(idx, m, valid_out);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+void launch_table_compact(const TableView& t, int n_keys, int n_acc, uint64_t* out_hash, uint64_t* out_min_row, uint64_t* out_keys,
+                          uint32_t* out_knull, uint64_t* out_acc, uint32_t max_out, uint32_t* out_count, cudaStream_t stream) {
+  k_table_compact<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, out_hash, out_min_row, out_keys, out_knull,
+                                                                                 out_acc, max_out, out_count);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+void launch_table_rehash(const TableView& from, const TableView& to, int n_keys, int n_acc, cudaStream_t stream) {
+  k_table_rehash<<<grid_for(from.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(from, to, n_keys, n_acc);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+}  // namespace sq

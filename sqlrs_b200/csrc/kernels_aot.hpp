@@ -1,0 +1,94 @@
+// sqlrs_b200 — launchers of the ahead-of-time compiled kernels (kernels_aot.cu): everything that
+// does not depend on a plan's expressions.  All launches are asynchronous on `stream`.
+#pragma once
+#include "common.hpp"
+
+namespace sq {
+
+// ---- synthetic TPC-H-shaped tables straight into HBM (include/sqlrs_tpch_spec.h)
+void launch_tpch_generate(int table, int col, int64_t row_begin, int64_t n, int64_t n_customer, int flags_mode, uint64_t* dst,
+                          cudaStream_t stream);
+
+// ---- bitmaps
+// number of set bits among the first n bits -> *out (device u64, accumulated with atomicAdd: zero it first)
+void launch_count_bits(const uint32_t* bitmap, int64_t n, unsigned long long* out, cudaStream_t stream);
+// dst[dst_bit_off .. +n) = src[0 .. n) (src == nullptr: all ones); dst must be zero-initialised there
+void launch_bitmap_append(uint32_t* dst, int64_t dst_bit_off, const uint32_t* src, int64_t n, cudaStream_t stream);
+
+// ---- stream compaction: keep-bitmap -> ascending list of kept row ids (warp ballot/popc)
+// chunk_counts: u32[ceil(n/2048)]; chunk_offsets: u64[same]; total: u64
+size_t compact_num_chunks(int64_t n);
+void launch_compact_count(const uint32_t* keep, int64_t n, uint32_t* chunk_counts, cudaStream_t stream);
+void launch_scan_u32(const uint32_t* counts, int64_t m, unsigned long long* offsets, unsigned long long* total, cudaStream_t stream);
+void launch_compact_write(const uint32_t* keep, int64_t n, const unsigned long long* chunk_offsets, uint32_t* out_idx,
+                          cudaStream_t stream);
+
+// ---- gather (arrow compute::take): index < 0 (i64) is a NULL index -> NULL row
+void launch_gather_u32idx(int width, const void* src, const uint32_t* src_valid, const uint32_t* idx, int64_t m, void* dst,
+                          uint32_t* dst_valid, cudaStream_t stream);
+void launch_gather_i64idx(int width, const void* src, const uint32_t* src_valid, const int64_t* idx, int64_t m, void* dst,
+                          uint32_t* dst_valid, cudaStream_t stream);
+
+// ---- misc
+void launch_fill_u64(uint64_t* dst, int64_t n, uint64_t value, cudaStream_t stream);
+void launch_iota_filter_valid(const int64_t* idx, int64_t m, uint32_t* valid_out, cudaStream_t stream);
+
+// ---- group table maintenance (layout: struct SqTable of csrc/jit/agg.cuh)
+struct TableView {
+  uint32_t* state;
+  uint64_t* hash;
+  uint64_t* min_row;
+  uint64_t* keys;
+  uint32_t* knull;
+  uint64_t* acc;
+  uint32_t* new_slots;
+  uint32_t* counters;
+  uint32_t capacity;
+};
+// dense copy of the occupied slots: out arrays sized by the group count; *out_count (device u32, zeroed)
+void launch_table_compact(const TableView& t, int n_keys, int n_acc, uint64_t* out_hash, uint64_t* out_min_row, uint64_t* out_keys,
+                          uint32_t* out_knull, uint64_t* out_acc, uint32_t max_out, uint32_t* out_count, cudaStream_t stream);
+// re-insert every occupied slot of `from` into the (empty, initialised) table `to`
+void launch_table_rehash(const TableView& from, const TableView& to, int n_keys, int n_acc, cudaStream_t stream);
+
+}  // namespace sq
+
+// =================================================================== hash join (kernels_join.cu)
+namespace sq {
+
+// Open-addressed table over the DISTINCT build keys; each slot owns a contiguous, ascending range
+// of build row ids (CSR), so a probe emits its matches already in build insertion order.
+struct JoinTableView {
+  int64_t* slot_rep;      // representative build row of the slot's key, -1 = empty
+  uint32_t* slot_count;   // build rows with that key
+  uint64_t* slot_start;   // first position of the slot's range in `rows`
+  int64_t* rows;          // build row ids grouped by slot, ascending within a slot
+  uint32_t capacity;      // power of two
+  const uint64_t* h;      // [n_build] row hashes of the build side (create_hashes)
+  const uint64_t* keys;   // [n_keys][n_build] raw key bits (match_keys only)
+  const uint32_t* knull;  // [n_build] null mask of the key tuple (match_keys only)
+  int64_t n_build;
+  int n_keys;
+  int match_keys;         // SQLRS_MATCH_HASH_AND_KEY: compare key tuples, NULL never joins
+};
+
+void launch_scan_u32_large(const uint32_t* counts, int64_t m, unsigned long long* offsets, unsigned long long* total,
+                           unsigned long long* scratch /* >= ceil(m/4096)+1 */, cudaStream_t stream);
+size_t scan_scratch_entries(int64_t m);
+
+void launch_join_insert(const JoinTableView& t, int32_t* row_slot, uint32_t* max_count, cudaStream_t stream);
+void launch_join_fill(const JoinTableView& t, const int32_t* row_slot, uint32_t* slot_fill, cudaStream_t stream);
+void launch_join_sort_ranges(const JoinTableView& t, cudaStream_t stream);
+// stable fallback for heavily duplicated keys: rows = build row ids sorted by (slot, row id)
+void join_fill_sorted(const JoinTableView& t, const int32_t* row_slot, cudaStream_t stream);
+void launch_join_probe_count(const JoinTableView& t, const uint64_t* ph, const uint64_t* pkeys, const uint32_t* pknull, int64_t n_probe,
+                             int keep_unmatched, int32_t* slot_of, uint32_t* out_count, cudaStream_t stream);
+void launch_join_probe_write(const JoinTableView& t, const int32_t* slot_of, const unsigned long long* offsets, int64_t n_probe,
+                             int keep_unmatched, int64_t* li, uint32_t* ri, cudaStream_t stream);
+// bitmap[idx[k]] = 1 for every k (idx < 0 skipped)
+void launch_mark_bits_i64(const int64_t* idx, int64_t m, uint32_t* bitmap, cudaStream_t stream);
+void launch_mark_bits_u32(const uint32_t* idx, int64_t m, uint32_t* bitmap, cudaStream_t stream);
+// dst = ~src over the first n bits (bits past n cleared)
+void launch_bitmap_not(const uint32_t* src, int64_t n, uint32_t* dst, cudaStream_t stream);
+
+}  // namespace sq

@@ -1,0 +1,357 @@
+// sqlrs_b200 — hash join build / probe kernels for sm_100a (reference src/executor/join/hash_join.rs).
+// Build (:161-187): instead of HashMap<u64, Vec<usize>> the distinct keys go into an open-addressed
+// table and the build row ids into a CSR array grouped by key, ascending per key — so the probe
+// (:208-248) emits (build row, probe row) pairs exactly in the reference's order with a
+// count -> scan -> write pass and no per-row allocation.  All kernels are HBM-latency bound
+// (random 8-byte reads of the table); grids are multiples of the SM count.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels_aot.hpp"
+
+namespace sq {
+namespace {
+
+constexpr int kBlock = 256;
+inline unsigned grid_for(int64_t items, int per_block, int64_t cap = 148 * 16) {
+  int64_t g = div_up(items, per_block);
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (unsigned)g;
+}
+
+__device__ __forceinline__ uint32_t mix32(uint64_t h) {
+  h ^= h >> 33;
+  h *= 0xff51afd7ed558ccdULL;
+  h ^= h >> 29;
+  return (uint32_t)h;
+}
+
+// does build row `b` carry the identity (h, keys)?  keys/knull of the other side given by pointer+index
+__device__ __forceinline__ bool same_key(const JoinTableView& t, int64_t b, uint64_t h, const uint64_t* okeys, int64_t ostride, int64_t oi) {
+  if (t.h[b] != h) return false;
+  if (!t.match_keys) return true;
+  for (int k = 0; k < t.n_keys; k++)
+    if (t.keys[(size_t)k * t.n_build + b] != okeys[(size_t)k * ostride + oi]) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(kBlock) k_join_insert(JoinTableView t, int32_t* __restrict__ row_slot, uint32_t* __restrict__ max_count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint32_t mask = t.capacity - 1;
+  uint32_t local_max = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.n_build; i += stride) {
+    if (t.match_keys && t.knull[i] != 0u) {  // SQL semantics: a NULL key never joins
+      row_slot[i] = -1;
+      continue;
+    }
+    const uint64_t h = t.h[i];
+    uint32_t s = mix32(h) & mask;
+    for (;;) {
+      long long rep = *((volatile long long*)&t.slot_rep[s]);
+      if (rep < 0) {
+        const long long old = (long long)atomicCAS((unsigned long long*)&t.slot_rep[s], (unsigned long long)-1LL, (unsigned long long)i);
+        rep = old < 0 ? i : old;
+      }
+      if (rep == i || same_key(t, rep, h, t.keys, t.n_build, i)) break;
+      s = (s + 1) & mask;
+    }
+    row_slot[i] = (int32_t)s;
+    const uint32_t c = atomicAdd(&t.slot_count[s], 1u) + 1u;
+    local_max = c > local_max ? c : local_max;
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    const uint32_t o = __shfl_xor_sync(0xffffffffu, local_max, d);
+    local_max = o > local_max ? o : local_max;
+  }
+  if ((threadIdx.x & 31) == 0 && local_max) atomicMax(max_count, local_max);
+}
+
+__global__ void __launch_bounds__(kBlock) k_join_fill(JoinTableView t, const int32_t* __restrict__ row_slot, uint32_t* __restrict__ slot_fill) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.n_build; i += stride) {
+    const int32_t s = row_slot[i];
+    if (s < 0) continue;
+    const uint64_t pos = t.slot_start[s] + atomicAdd(&slot_fill[s], 1u);
+    t.rows[pos] = i;
+  }
+}
+
+// ranges are short (bounded by the caller): insertion sort by one thread
+__global__ void __launch_bounds__(kBlock) k_join_sort_ranges(JoinTableView t) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
+    const uint32_t c = t.slot_count[s];
+    if (c < 2) continue;
+    int64_t* r = t.rows + t.slot_start[s];
+    for (uint32_t a = 1; a < c; a++) {
+      const int64_t v = r[a];
+      uint32_t b = a;
+      while (b > 0 && r[b - 1] > v) {
+        r[b] = r[b - 1];
+        b--;
+      }
+      r[b] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_join_probe_count(JoinTableView t, const uint64_t* __restrict__ ph, const uint64_t* __restrict__ pkeys,
+                                                              const uint32_t* __restrict__ pknull, int64_t n_probe, int keep_unmatched,
+                                                              int32_t* __restrict__ slot_of, uint32_t* __restrict__ out_count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint32_t mask = t.capacity - 1;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_probe; r += stride) {
+    int32_t found = -1;
+    if (!(t.match_keys && pknull[r] != 0u)) {
+      const uint64_t h = ph[r];
+      uint32_t s = mix32(h) & mask;
+      for (uint32_t probes = 0; probes <= mask; probes++) {
+        const int64_t rep = t.slot_rep[s];
+        if (rep < 0) break;
+        if (same_key(t, rep, h, pkeys, n_probe, r)) {
+          found = (int32_t)s;
+          break;
+        }
+        s = (s + 1) & mask;
+      }
+    }
+    slot_of[r] = found;
+    const uint32_t c = found >= 0 ? t.slot_count[found] : 0u;
+    out_count[r] = c ? c : (keep_unmatched ? 1u : 0u);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_join_probe_write(JoinTableView t, const int32_t* __restrict__ slot_of,
+                                                              const unsigned long long* __restrict__ offsets, int64_t n_probe, int keep_unmatched,
+                                                              int64_t* __restrict__ li, uint32_t* __restrict__ ri) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_probe; r += stride) {
+    const int32_t s = slot_of[r];
+    unsigned long long o = offsets[r];
+    if (s >= 0) {
+      const uint32_t c = t.slot_count[s];
+      const int64_t* src = t.rows + t.slot_start[s];
+      for (uint32_t j = 0; j < c; j++) {
+        li[o + j] = src[j];
+        ri[o + j] = (uint32_t)r;
+      }
+    } else if (keep_unmatched) {  // Right/Full: (NULL, row), hash_join.rs:242-246
+      li[o] = -1;
+      ri[o] = (uint32_t)r;
+    }
+  }
+}
+
+template <typename Idx>
+__global__ void __launch_bounds__(kBlock) k_mark_bits(const Idx* __restrict__ idx, int64_t m, uint32_t* __restrict__ bitmap) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
+    const long long i = (long long)idx[k];
+    if (i < 0) continue;
+    atomicOr(&bitmap[i >> 5], 1u << (i & 31));
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_bitmap_not(const uint32_t* __restrict__ src, int64_t n, uint32_t* __restrict__ dst) {
+  const int64_t words = (n + 31) >> 5;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += stride) {
+    uint32_t v = ~src[w];
+    if (w == words - 1 && (n & 31)) v &= (1u << (n & 31)) - 1u;
+    dst[w] = v;
+  }
+}
+
+// ---- large exclusive scan: 4096-entry chunks -> chunk sums -> scan of sums -> apply
+constexpr int kScanChunk = 4096;
+
+__global__ void __launch_bounds__(kBlock) k_scan_chunk_sums(const uint32_t* __restrict__ counts, int64_t m, unsigned long long* __restrict__ sums) {
+  __shared__ unsigned long long warp_sums[kBlock / 32];
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk;
+  unsigned long long local = 0;
+  for (int j = threadIdx.x; j < kScanChunk; j += kBlock)
+    if (base + j < m) local += counts[base + j];
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int w = 0; w < kBlock / 32; w++) s += warp_sums[w];
+    sums[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_u64_inplace(unsigned long long* __restrict__ v, int64_t m, unsigned long long* __restrict__ total) {
+  __shared__ unsigned long long warp_sums[32];
+  __shared__ unsigned long long carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < m; base += 1024) {
+    const int64_t i = base + tid;
+    const unsigned long long x0 = i < m ? v[i] : 0;
+    unsigned long long x = x0;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long s = warp_sums[lane];
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, s, d);
+        if (lane >= d) s += y;
+      }
+      warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const unsigned long long carry = carry_s;
+    if (i < m) v[i] = carry + (wid ? warp_sums[wid - 1] : 0) + (x - x0);
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sums[31];
+    __syncthreads();
+  }
+  if (tid == 0) *total = carry_s;
+}
+
+// one CTA per chunk: 256 threads x 16 consecutive entries
+__global__ void __launch_bounds__(kBlock) k_scan_chunk_apply(const uint32_t* __restrict__ counts, int64_t m, const unsigned long long* __restrict__ chunk_base,
+                                                              unsigned long long* __restrict__ offsets) {
+  __shared__ unsigned long long warp_sums[kBlock / 32];
+  const int per = kScanChunk / kBlock;  // 16
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * per;
+  unsigned long long vals[per];
+  unsigned long long local = 0;
+#pragma unroll
+  for (int j = 0; j < per; j++) {
+    vals[j] = (base + j < m) ? counts[base + j] : 0;
+    local += vals[j];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long x = local;
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  unsigned long long before = chunk_base[blockIdx.x] + (x - local);
+  for (int w = 0; w < wid; w++) before += warp_sums[w];
+#pragma unroll
+  for (int j = 0; j < per; j++) {
+    if (base + j < m) offsets[base + j] = before;
+    before += vals[j];
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_iota_i64(int64_t* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = i;
+}
+__global__ void __launch_bounds__(kBlock) k_slot_keys(const int32_t* __restrict__ row_slot, int64_t n, uint32_t capacity, uint32_t* __restrict__ keys) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    keys[i] = row_slot[i] < 0 ? capacity : (uint32_t)row_slot[i];  // NULL-key rows sort past every slot
+}
+
+#define SQ_LAUNCH_CHECK()   \
+  do {                      \
+    count_launch();         \
+    SQ_CUDA(cudaGetLastError()); \
+  } while (0)
+
+}  // namespace
+
+size_t scan_scratch_entries(int64_t m) { return (size_t)div_up(m, kScanChunk) + 1; }
+
+void launch_scan_u32_large(const uint32_t* counts, int64_t m, unsigned long long* offsets, unsigned long long* total,
+                           unsigned long long* scratch, cudaStream_t stream) {
+  if (m <= 0) {
+    SQ_CUDA(cudaMemsetAsync(total, 0, 8, stream));
+    return;
+  }
+  const int64_t chunks = div_up(m, kScanChunk);
+  k_scan_chunk_sums<<<(unsigned)chunks, kBlock, 0, stream>>>(counts, m, scratch);
+  SQ_LAUNCH_CHECK();
+  k_scan_u64_inplace<<<1, 1024, 0, stream>>>(scratch, chunks, total);
+  SQ_LAUNCH_CHECK();
+  k_scan_chunk_apply<<<(unsigned)chunks, kBlock, 0, stream>>>(counts, m, scratch, offsets);
+  SQ_LAUNCH_CHECK();
+}
+
+void launch_join_insert(const JoinTableView& t, int32_t* row_slot, uint32_t* max_count, cudaStream_t stream) {
+  if (t.n_build <= 0) return;
+  k_join_insert<<<grid_for(t.n_build, kBlock), kBlock, 0, stream>>>(t, row_slot, max_count);
+  SQ_LAUNCH_CHECK();
+}
+void launch_join_fill(const JoinTableView& t, const int32_t* row_slot, uint32_t* slot_fill, cudaStream_t stream) {
+  if (t.n_build <= 0) return;
+  k_join_fill<<<grid_for(t.n_build, kBlock), kBlock, 0, stream>>>(t, row_slot, slot_fill);
+  SQ_LAUNCH_CHECK();
+}
+void launch_join_sort_ranges(const JoinTableView& t, cudaStream_t stream) {
+  k_join_sort_ranges<<<grid_for(t.capacity, kBlock), kBlock, 0, stream>>>(t);
+  SQ_LAUNCH_CHECK();
+}
+
+void join_fill_sorted(const JoinTableView& t, const int32_t* row_slot, cudaStream_t stream) {
+  // stable LSD radix sort of (slot, row id): equal slots keep ascending row ids
+  const int64_t n = t.n_build;
+  if (n <= 0) return;
+  uint32_t *k_in = nullptr, *k_out = nullptr;
+  int64_t *v_in = nullptr, *v_out = nullptr;
+  SQ_CUDA(cudaMallocAsync(&k_in, (size_t)n * 4, stream));
+  SQ_CUDA(cudaMallocAsync(&k_out, (size_t)n * 4, stream));
+  SQ_CUDA(cudaMallocAsync(&v_in, (size_t)n * 8, stream));
+  SQ_CUDA(cudaMallocAsync(&v_out, (size_t)n * 8, stream));
+  k_slot_keys<<<grid_for(n, kBlock), kBlock, 0, stream>>>(row_slot, n, t.capacity, k_in);
+  SQ_LAUNCH_CHECK();
+  k_iota_i64<<<grid_for(n, kBlock), kBlock, 0, stream>>>(v_in, n);
+  SQ_LAUNCH_CHECK();
+  int bits = 1;
+  while ((1ull << bits) <= t.capacity) bits++;
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, bits, stream);
+  void* tmp = nullptr;
+  SQ_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, stream));
+  SQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, bits, stream));
+  count_launch(4);
+  // rows of NULL-key build rows (slot = capacity) sort last and are never referenced by a slot range
+  SQ_CUDA(cudaMemcpyAsync(t.rows, v_out, (size_t)n * 8, cudaMemcpyDeviceToDevice, stream));
+  cudaFreeAsync(tmp, stream);
+  cudaFreeAsync(k_in, stream);
+  cudaFreeAsync(k_out, stream);
+  cudaFreeAsync(v_in, stream);
+  cudaFreeAsync(v_out, stream);
+}
+
+void launch_join_probe_count(const JoinTableView& t, const uint64_t* ph, const uint64_t* pkeys, const uint32_t* pknull, int64_t n_probe,
+                             int keep_unmatched, int32_t* slot_of, uint32_t* out_count, cudaStream_t stream) {
+  if (n_probe <= 0) return;
+  k_join_probe_count<<<grid_for(n_probe, kBlock), kBlock, 0, stream>>>(t, ph, pkeys, pknull, n_probe, keep_unmatched, slot_of, out_count);
+  SQ_LAUNCH_CHECK();
+}
+void launch_join_probe_write(const JoinTableView& t, const int32_t* slot_of, const unsigned long long* offsets, int64_t n_probe,
+                             int keep_unmatched, int64_t* li, uint32_t* ri, cudaStream_t stream) {
+  if (n_probe <= 0) return;
+  k_join_probe_write<<<grid_for(n_probe, kBlock), kBlock, 0, stream>>>(t, slot_of, offsets, n_probe, keep_unmatched, li, ri);
+  SQ_LAUNCH_CHECK();
+}
+void launch_mark_bits_i64(const int64_t* idx, int64_t m, uint32_t* bitmap, cudaStream_t stream) {
+  if (m <= 0) return;
+  k_mark_bits<int64_t><<<grid_for(m, kBlock), kBlock, 0, stream>>>(idx, m, bitmap);
+  SQ_LAUNCH_CHECK();
+}
+void launch_mark_bits_u32(const uint32_t* idx, int64_t m, uint32_t* bitmap, cudaStream_t stream) {
+  if (m <= 0) return;
+  k_mark_bits<uint32_t><<<grid_for(m, kBlock), kBlock, 0, stream>>>(idx, m, bitmap);
+  SQ_LAUNCH_CHECK();
+}
+void launch_bitmap_not(const uint32_t* src, int64_t n, uint32_t* dst, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_bitmap_not<<<grid_for(div_up(n, 32), kBlock), kBlock, 0, stream>>>(src, n, dst);
+  SQ_LAUNCH_CHECK();
+}
+
+}  // namespace sq

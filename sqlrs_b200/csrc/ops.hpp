@@ -1,0 +1,128 @@
+// sqlrs_b200 — the operators behind the C ABI, working on device batches.
+//   EvalProgram  BoundExpr::eval_column            reference src/executor/evaluator.rs:13-28
+//   FilterOp     FilterExecutor                    src/executor/filter.rs:7-26
+//   AggOp        SimpleAggExecutor/HashAggExecutor src/executor/aggregate/{simple_agg.rs:10-65,hash_agg.rs:15-150}
+//   JoinOp       HashJoinExecutor                  src/executor/join/hash_join.rs:16-323
+#pragma once
+#include <map>
+
+#include "codegen.hpp"
+#include "device.hpp"
+#include "jit.hpp"
+
+namespace sq {
+
+std::vector<ColInfo> col_infos(const DBatch& b);
+std::string gen_input_decls(const std::vector<ColInfo>& cols);
+
+// ---- generic "evaluate expressions into columns" program -----------------------------------
+enum OutKind {
+  OUT_VALUE = 0,  // typed column with validity
+  OUT_KEEP = 1,   // Boolean "valid && true" mask, bit-packed, never NULL (the Filter keep-mask)
+  OUT_HASH = 2,   // u64 create_hashes() over ALL expressions of the request marked is_key
+  OUT_RAWBITS = 3,// u64 raw key bits of one expression (NULL -> 0)
+  OUT_NULLMASK = 4// u32 null mask over the is_key expressions
+};
+struct EvalRequest {
+  std::vector<ExprCopy> exprs;
+  std::vector<bool> is_key;      // per expr: participates in OUT_HASH / OUT_NULLMASK
+  struct Out {
+    int kind;
+    int expr;  // index into exprs (OUT_VALUE / OUT_KEEP / OUT_RAWBITS)
+  };
+  std::vector<Out> outs;
+};
+struct EvalResult {
+  std::vector<DCol> cols;           // one per requested output (u64/u32 outputs typed INT64/INT32)
+  std::vector<int> expr_dtypes;     // static dtype of every expression
+};
+class EvalProgram {
+ public:
+  explicit EvalProgram(EvalRequest req) : req_(std::move(req)) {}
+  EvalResult run(Ctx& ctx, const DBatch& batch, const char* what);
+  std::string source_for(const std::vector<ColInfo>& cols, std::vector<int>* out_dtypes, std::vector<bool>* out_nullable,
+                         std::vector<int>* expr_dtypes);
+
+ private:
+  struct Compiled {
+    JitKernel* kernel = nullptr;
+    std::vector<int> out_dtypes, expr_dtypes;
+    std::vector<bool> out_nullable;
+  };
+  EvalRequest req_;
+  std::map<std::string, Compiled> cache_;
+};
+
+void check_error_flag(Ctx& ctx, const BufPtr& err, const char* what);  // syncs; throws ERR_ARROW "Divide by zero error"
+
+// take / filter helpers on whole batches
+DCol gather_col_u32(Ctx& ctx, const DCol& src, const uint32_t* idx, int64_t m);
+DCol gather_col_i64(Ctx& ctx, const DCol& src, const int64_t* idx, int64_t m, bool idx_may_be_null);
+// keep-bitmap -> (device u32 index list, count); synchronises to learn the count
+BufPtr compact_indices(Ctx& ctx, const uint32_t* keep, int64_t n, int64_t* out_count);
+DCol concat_cols(Ctx& ctx, const std::vector<DCol>& parts, int dtype);
+
+// ---- Filter -------------------------------------------------------------------------------------
+class FilterOp {
+ public:
+  FilterOp(const ExprCopy& predicate, const Options& opt);
+  DBatch execute(const DBatch& in);
+  Ctx& ctx() { return ctx_; }
+
+ private:
+  Ctx ctx_;
+  EvalProgram prog_;
+};
+DBatch filter_batch(Ctx& ctx, EvalProgram& prog, const DBatch& in);
+
+// ---- aggregates ------------------------------------------------------------------------------------
+struct AggSpec {
+  int func = 0, distinct = 0, return_dtype = 0;
+  ExprCopy arg;
+  std::string name;
+};
+std::vector<AggSpec> copy_aggs(const sqlrs_agg_desc* aggs, int32_t n);
+
+class AggOp {
+ public:
+  // group_by empty + simple = SimpleAggExecutor; `predicate` non-empty = fused Filter below the aggregate
+  AggOp(std::vector<AggSpec> aggs, std::vector<ExprCopy> group_by, std::vector<std::string> group_names, bool simple,
+        ExprCopy fused_predicate, const Options& opt);
+  ~AggOp();
+  void push(const DBatch& batch);
+  DBatch finish_device();                                      // result as a (small) device batch
+  void finish_host(ArrowArray* out, ArrowSchema* out_schema);  // result straight to host Arrow
+  Ctx& ctx() { return ctx_; }
+  std::string describe() const;
+  std::string debug_source(const std::vector<ColInfo>& cols);  // generated CUDA for batches of that schema (no GPU needed)
+  // partial/final split for multi-GPU execution: the raw group table as a batch
+  // [hash, min_row, knull, key bits..., accumulator words...] and its merge into another operator
+  DBatch export_partials();
+  void merge_partials(const DBatch& partials);
+
+ private:
+  struct Compiled;
+  struct Table;
+  Compiled& compiled_for(const DBatch& batch);
+  std::string generate(const std::vector<ColInfo>& cols, Compiled& comp);
+  void ensure_table(uint32_t min_capacity);
+  void grow_table(uint32_t min_capacity);
+  void build_output(std::vector<Field>* fields, struct HostGroups* groups);
+
+  Ctx ctx_;
+  Options opt_;
+  std::vector<AggSpec> aggs_;
+  std::vector<ExprCopy> group_by_;
+  std::vector<std::string> group_names_;
+  bool simple_;
+  ExprCopy predicate_;
+  std::map<std::string, std::unique_ptr<Compiled>> cache_;
+  std::unique_ptr<Table> table_;
+  int64_t rows_seen_ = 0, batches_seen_ = 0;
+  bool seen_batch_ = false;
+  bool use_global_ = false;
+  std::vector<int> key_dtypes_;
+  std::string last_path_;
+};
+
+}  // namespace sq

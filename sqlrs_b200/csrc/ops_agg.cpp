@@ -1,0 +1,595 @@
+// sqlrs_b200 — SimpleAggExecutor / HashAggExecutor on the GPU (fused with a Filter child when the
+// plan has one).  Reference: src/executor/aggregate/{simple_agg.rs:27-65, hash_agg.rs:33-150,
+// sum.rs:16-97, count.rs:10-29, min_max.rs:47-157}; kernels: csrc/jit/agg.cuh.
+#include <algorithm>
+
+#include "kernels_aot.hpp"
+#include "ops.hpp"
+
+namespace sq {
+
+std::vector<AggSpec> copy_aggs(const sqlrs_agg_desc* aggs, int32_t n) {
+  std::vector<AggSpec> out;
+  if (n > 0 && !aggs) fail(SQLRS_ERR_INVALID_ARG, "aggs is NULL");
+  for (int32_t k = 0; k < n; k++) {
+    AggSpec a;
+    a.func = aggs[k].func;
+    a.distinct = aggs[k].distinct;
+    a.return_dtype = aggs[k].return_dtype;
+    a.arg = copy_expr(&aggs[k].arg);
+    a.name = aggs[k].name ? aggs[k].name : "";
+    out.push_back(a);
+  }
+  return out;
+}
+
+namespace {
+
+enum WordOp { W_ADD_U64, W_ADD_F64, W_MIN_I64, W_MAX_I64, W_COUNT_EPOCH };
+
+struct WordPlan {
+  int op;
+};
+struct AggPlan {
+  int func, out_dtype, arg_dtype;
+  int value_word = -1;   // main accumulator word
+  int nvalid_word = -1;  // number of non-NULL inputs (only when the argument can be NULL)
+  bool f64_sortable = false;
+};
+
+constexpr uint64_t kEpochShift = 40;
+constexpr uint64_t kEpochMask = (1ULL << kEpochShift) - 1;
+
+uint64_t word_identity(int op) {
+  switch (op) {
+    case W_MIN_I64: return 0x7fffffffffffffffULL;
+    case W_MAX_I64: return 0x8000000000000000ULL;
+  }
+  return 0;
+}
+
+inline uint32_t next_pow2(uint64_t v) {
+  uint64_t p = 1024;
+  while (p < v) p <<= 1;
+  if (p > (1ULL << 31)) fail(SQLRS_ERR_INTERNAL, "group table would exceed 2^31 slots");
+  return (uint32_t)p;
+}
+
+struct SqInBlob {
+  std::vector<const void*> blob;
+  SqInBlob(const DBatch& b, int64_t row_start) {
+    size_t n = b.cols.size() ? b.cols.size() : 1;
+    blob.assign(2 * n, nullptr);
+    for (size_t c = 0; c < b.cols.size(); c++) {
+      const DCol& col = b.cols[c];
+      if (col.data) {
+        if (col.dtype == SQLRS_DT_BOOL) blob[c] = (const uint32_t*)col.data + (row_start >> 5);
+        else blob[c] = (const uint8_t*)col.data + (size_t)row_start * dtype_width(col.dtype);
+      }
+      if (col.valid) blob[n + c] = col.valid + (row_start >> 5);
+    }
+  }
+  void* ptr() { return blob.data(); }
+};
+
+}  // namespace
+
+struct HostGroups {
+  uint32_t n = 0;
+  std::vector<uint64_t> hash, min_row, keys, acc;  // keys [K][n], acc [W][n]
+  std::vector<uint32_t> knull;
+};
+
+struct AggOp::Compiled {
+  JitKernel *small = nullptr, *merge = nullptr, *global = nullptr, *fixkeys = nullptr;
+  std::vector<AggPlan> aggs;
+  std::vector<WordPlan> words;
+  std::vector<int> key_dtypes;
+  int block = 128, slots = 8, unroll = 4;
+  size_t small_smem = 0;
+  int small_grid = 0;
+  bool small_ok = true;
+};
+
+struct AggOp::Table {
+  uint32_t capacity = 0;
+  int n_keys = 0, n_acc = 0;
+  BufPtr state, hash, min_row, keys, knull, acc, new_slots, counters;
+  std::vector<uint64_t> identities;
+  TableView view() const {
+    TableView v;
+    v.state = (uint32_t*)state->p;
+    v.hash = (uint64_t*)hash->p;
+    v.min_row = (uint64_t*)min_row->p;
+    v.keys = (uint64_t*)keys->p;
+    v.knull = (uint32_t*)knull->p;
+    v.acc = (uint64_t*)acc->p;
+    v.new_slots = (uint32_t*)new_slots->p;
+    v.counters = (uint32_t*)counters->p;
+    v.capacity = capacity;
+    return v;
+  }
+};
+
+AggOp::AggOp(std::vector<AggSpec> aggs, std::vector<ExprCopy> group_by, std::vector<std::string> group_names, bool simple,
+             ExprCopy fused_predicate, const Options& opt)
+    : ctx_(opt), opt_(opt), aggs_(std::move(aggs)), group_by_(std::move(group_by)), group_names_(std::move(group_names)),
+      simple_(simple), predicate_(std::move(fused_predicate)) {
+  if (group_by_.size() > 16) fail(SQLRS_ERR_UNSUPPORTED, "more than 16 group-by keys");
+  for (const AggSpec& a : aggs_) {
+    if (a.func < SQLRS_AGG_COUNT || a.func > SQLRS_AGG_MAX) fail(SQLRS_ERR_INVALID_ARG, "unknown aggregate function");
+    if (a.distinct && (a.func == SQLRS_AGG_COUNT || a.func == SQLRS_AGG_SUM))
+      fail(SQLRS_ERR_UNSUPPORTED, "DISTINCT aggregates are not supported by the CUDA backend yet (SURVEY §8f rank 4)");
+  }
+}
+AggOp::~AggOp() = default;
+
+// ------------------------------------------------------------------ code generation
+AggOp::Compiled& AggOp::compiled_for(const DBatch& batch) {
+  std::vector<ColInfo> cols = col_infos(batch);
+  std::string sig = RowProgram(cols).signature();
+  auto it = cache_.find(sig);
+  if (it != cache_.end()) return *it->second;
+
+  auto comp = std::make_unique<Compiled>();
+  std::string src = generate(cols, *comp);
+  comp->small = comp->small_ok ? jit_get("agg", src, "sq_agg_small") : nullptr;
+  comp->merge = jit_get("agg", src, "sq_agg_merge");
+  comp->global = jit_get("agg", src, "sq_agg_global");
+  comp->fixkeys = jit_get("agg", src, "sq_agg_fixkeys");
+  if (comp->small_ok) {
+    int per_sm = jit_max_blocks_per_sm(comp->small, comp->block, comp->small_smem);
+    if (per_sm < 1) comp->small_ok = false;
+    comp->small_grid = device_sm_count(ctx_.device) * std::max(per_sm, 1);
+  }
+  if (!key_dtypes_.empty() && key_dtypes_ != comp->key_dtypes) fail(SQLRS_ERR_ARROW, "group key types changed between batches");
+  if (!cache_.empty()) {
+    const Compiled& first = *cache_.begin()->second;
+    bool same = first.words.size() == comp->words.size();
+    for (size_t w = 0; same && w < first.words.size(); w++) same = first.words[w].op == comp->words[w].op;
+    if (!same) fail(SQLRS_ERR_ARROW, "batch schema changed between batches (a column declared non-nullable contains nulls?)");
+  }
+  Compiled& ref = *comp;
+  cache_[sig] = std::move(comp);
+  return ref;
+}
+
+std::string AggOp::debug_source(const std::vector<ColInfo>& cols) {
+  Compiled c;
+  return generate(cols, c);
+}
+
+// the row program + accumulator glue for csrc/jit/agg.cuh (pure: no device access)
+std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref) {
+  Compiled* comp = &comp_ref;
+  RowProgram prog(cols);
+  const bool fused = !predicate_.empty();
+  std::string pass = "true";
+  if (fused) {
+    Val p = prog.compile(predicate_, 0);
+    if (p.dtype != SQLRS_DT_BOOL) fail(SQLRS_ERR_INTERNAL, "filter executor expected evaluate boolean array");
+    pass = "(n" + std::to_string(p.id) + " && v" + std::to_string(p.id) + ")";
+  }
+  const int ec = fused ? 1 : 0;
+  // hash_agg.rs:63-73: aggregate arguments first, then the group keys
+  std::vector<Val> args;
+  for (const AggSpec& a : aggs_) args.push_back(prog.compile(a.arg, ec));
+  std::vector<Val> keys;
+  for (const ExprCopy& g : group_by_) keys.push_back(prog.compile(g, ec));
+  for (const Val& k : keys) comp->key_dtypes.push_back(k.dtype);
+
+  // accumulator words
+  std::ostringstream upd;  // body of sq_acc_update
+  for (size_t j = 0; j < aggs_.size(); j++) {
+    const AggSpec& a = aggs_[j];
+    AggPlan p;
+    p.func = a.func;
+    p.arg_dtype = args[j].dtype;
+    Val v = args[j];
+    auto add_word = [&](int op) {
+      comp->words.push_back(WordPlan{op});
+      return (int)comp->words.size() - 1;
+    };
+    switch (a.func) {
+      case SQLRS_AGG_COUNT: {
+        p.out_dtype = SQLRS_DT_INT64;
+        p.value_word = add_word(opt_.count_mode == SQLRS_COUNT_REFERENCE_OVERWRITE ? W_COUNT_EPOCH : W_ADD_U64);
+        upd << "  a[" << p.value_word << " * stride] += " << (v.dtype == SQLRS_DT_NULL ? std::string("0ULL") : "(o.an" + std::to_string(j) + " ? 1ULL : 0ULL)")
+            << ";\n";
+        break;
+      }
+      case SQLRS_AGG_SUM: {
+        // sum.rs:54 casts to the return type, arrow `sum` skips NULLs, ints wrap (release build)
+        if (v.dtype == SQLRS_DT_UTF8 || a.return_dtype == SQLRS_DT_UTF8) fail(SQLRS_ERR_UNSUPPORTED, "unsupported sum type: Utf8");
+        Val c = prog.cast(v, a.return_dtype);
+        if (!is_numeric(c.dtype)) fail(SQLRS_ERR_UNSUPPORTED, std::string("unsupported sum type: ") + dtype_name(c.dtype));
+        if (c.dtype == SQLRS_DT_INT32)
+          fail(SQLRS_ERR_UNSUPPORTED, "not expected Int32 and Int32 for sum");  // sum.rs:84 unimplemented!
+        p.out_dtype = c.dtype;
+        std::string vn = "o.a" + std::to_string(j), nn = "o.an" + std::to_string(j);
+        if (c.dtype == SQLRS_DT_FLOAT64) {
+          p.value_word = add_word(W_ADD_F64);
+          upd << "  if (" << nn << ") { double* p = (double*)(a + " << p.value_word << " * stride); *p = __dadd_rn(*p, " << vn << "); }\n";
+        } else {
+          p.value_word = add_word(W_ADD_U64);
+          upd << "  if (" << nn << ") a[" << p.value_word << " * stride] += (u64)" << vn << ";\n";
+        }
+        if (c.decl_null) {
+          p.nvalid_word = add_word(W_ADD_U64);
+          upd << "  a[" << p.nvalid_word << " * stride] += " << nn << " ? 1ULL : 0ULL;\n";
+        }
+        args[j] = c;
+        break;
+      }
+      case SQLRS_AGG_MIN:
+      case SQLRS_AGG_MAX: {
+        if (v.dtype == SQLRS_DT_UTF8) fail(SQLRS_ERR_UNSUPPORTED, "Utf8 min/max is not supported by the CUDA backend yet");
+        if (!is_numeric(v.dtype)) fail(SQLRS_ERR_UNSUPPORTED, std::string("unsupported min/max type: ") + dtype_name(v.dtype));
+        if (v.dtype != a.return_dtype)
+          fail(SQLRS_ERR_UNSUPPORTED, std::string("unsupported min_max scalar type: ") + dtype_name(a.return_dtype));
+        p.out_dtype = v.dtype;
+        const bool is_min = a.func == SQLRS_AGG_MIN;
+        p.value_word = add_word(is_min ? W_MIN_I64 : W_MAX_I64);
+        p.f64_sortable = v.dtype == SQLRS_DT_FLOAT64;
+        std::string vn = "o.a" + std::to_string(j), nn = "o.an" + std::to_string(j);
+        std::string as_i64 = p.f64_sortable ? "sq_f64_sortable(" + vn + ")" : "(i64)" + vn;
+        upd << "  if (" << nn << ") { i64* p = (i64*)(a + " << p.value_word << " * stride); const i64 x = " << as_i64 << "; if (x "
+            << (is_min ? "<" : ">") << " *p) *p = x; }\n";
+        if (v.decl_null) {
+          p.nvalid_word = add_word(W_ADD_U64);
+          upd << "  a[" << p.nvalid_word << " * stride] += " << nn << " ? 1ULL : 0ULL;\n";
+        }
+        break;
+      }
+    }
+    comp->aggs.push_back(p);
+  }
+  const int K = (int)keys.size(), W = (int)comp->words.size();
+  if (W > 48) fail(SQLRS_ERR_UNSUPPORTED, "too many aggregate accumulators for one operator (max 48 words)");
+  const int hash_id = prog.emit_row_hash(keys);
+  std::vector<int> raw_ids;
+  for (const Val& k : keys) raw_ids.push_back(prog.emit_raw_bits(k));
+
+  // launch shape of sq_agg_small: S slots, T threads, private accumulators in shared memory
+  comp->slots = K == 0 ? 1 : 8;
+  comp->unroll = 4;
+  comp->block = 128;
+  auto smem_for = [&](int T) {
+    return (size_t)(W + 1) * comp->slots * T * 8 + (size_t)comp->slots * (8 + 8 * std::max(K, 1) + 4 + 4) + 16;
+  };
+  if (smem_for(256) <= 100 * 1024) comp->block = 256;
+  while (comp->block > 32 && smem_for(comp->block) > 200 * 1024) comp->block /= 2;
+  comp->small_ok = smem_for(comp->block) <= 200 * 1024;
+  comp->small_smem = smem_for(comp->block);
+
+  std::ostringstream s;
+  s << gen_input_decls(cols);
+  s << "#define SQ_NKEYS " << K << "\n#define SQ_NACC " << W << "\n";
+  s << "#define SQ_MATCH_KEYS " << (opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY ? 1 : 0) << "\n";
+  s << "#define SQ_BLOCK " << comp->block << "\n#define SQ_SLOTS " << comp->slots << "\n#define SQ_UNROLL " << comp->unroll << "\n";
+  s << "struct SqRow {\n  bool pass; u64 h; u64 kb[" << std::max(K, 1) << "]; u32 knull;\n";
+  for (size_t j = 0; j < aggs_.size(); j++) s << "  " << ctype_of(args[j].dtype) << " a" << j << "; bool an" << j << ";\n";
+  s << "};\n";
+  s << "__device__ __forceinline__ void sq_row(const SqIn& in, i64 r, SqRow& o, bool& e0, bool& e1) {\n";
+  s << prog.body_str();
+  s << "  o.pass = " << pass << ";\n  o.h = v" << hash_id << ";\n";
+  if (K == 0) s << "  o.kb[0] = 0ULL;\n";
+  std::string knull = "0u";
+  for (int k = 0; k < K; k++) {
+    s << "  o.kb[" << k << "] = v" << raw_ids[k] << ";\n";
+    knull += " | (n" + std::to_string(keys[k].id) + " ? 0u : " + std::to_string(1u << k) + "u)";
+  }
+  s << "  o.knull = " << knull << ";\n";
+  for (size_t j = 0; j < aggs_.size(); j++)
+    s << "  o.a" << j << " = v" << args[j].id << "; o.an" << j << " = n" << args[j].id << ";\n";
+  s << "}\n";
+  s << "__device__ __forceinline__ u64 sq_acc_identity(int w) {\n  switch (w) {\n";
+  for (int w = 0; w < W; w++)
+    if (word_identity(comp->words[w].op) != 0) s << "    case " << w << ": return 0x" << std::hex << word_identity(comp->words[w].op) << std::dec << "ULL;\n";
+  s << "  }\n  return 0ULL;\n}\n";
+  s << "__device__ __forceinline__ void sq_acc_update(u64* a, int stride, const SqRow& o) {\n" << upd.str() << "}\n";
+  s << "__device__ __forceinline__ u64 sq_acc_reduce(int w, u64 x, u64 y) {\n  switch (w) {\n";
+  for (int w = 0; w < W; w++) {
+    s << "    case " << w << ": ";
+    switch (comp->words[w].op) {
+      case W_ADD_U64:
+      case W_COUNT_EPOCH: s << "return x + y;\n"; break;
+      case W_ADD_F64: s << "return (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((i64)x), __longlong_as_double((i64)y)));\n"; break;
+      case W_MIN_I64: s << "return (u64)(((i64)y < (i64)x) ? (i64)y : (i64)x);\n"; break;
+      case W_MAX_I64: s << "return (u64)(((i64)y > (i64)x) ? (i64)y : (i64)x);\n"; break;
+    }
+  }
+  s << "  }\n  return x;\n}\n";
+  s << "__device__ __forceinline__ void sq_acc_merge_global(u64* p, int w, u64 x, i64 batch_no) {\n  switch (w) {\n";
+  for (int w = 0; w < W; w++) {
+    s << "    case " << w << ": ";
+    switch (comp->words[w].op) {
+      case W_ADD_U64: s << "if (x) atomicAdd(p, x); break;\n"; break;
+      case W_ADD_F64: s << "atomicAdd((double*)p, __longlong_as_double((i64)x)); break;\n"; break;
+      case W_MIN_I64: s << "atomicMin((i64*)p, (i64)x); break;\n"; break;
+      case W_MAX_I64: s << "atomicMax((i64*)p, (i64)x); break;\n"; break;
+      case W_COUNT_EPOCH:
+        // CountAccumulator::update_batch ASSIGNS (count.rs:22, quirk K1): the value is the count of the
+        // last batch that touched the group.  Word = (batch epoch << 40) | count within that batch.
+        s << "{ const u64 ep = (u64)(batch_no + 1) << " << kEpochShift << "; u64 old = *p;\n"
+          << "      for (;;) { const u64 nv = ((old >> " << kEpochShift << ") == (u64)(batch_no + 1)) ? old + x : (ep | x);\n"
+          << "        const u64 prev = atomicCAS(p, old, nv); if (prev == old) break; old = prev; } break; }\n";
+        break;
+    }
+  }
+  s << "  }\n}\n";
+
+  return s.str();
+}
+
+std::string AggOp::describe() const { return last_path_; }
+
+// ------------------------------------------------------------------ table
+void AggOp::ensure_table(uint32_t min_capacity) {
+  if (table_ && table_->capacity >= min_capacity) return;
+  grow_table(min_capacity);
+}
+
+void AggOp::grow_table(uint32_t min_capacity) {
+  const Compiled& c = *cache_.begin()->second;
+  auto t = std::make_unique<Table>();
+  t->capacity = next_pow2(min_capacity);
+  t->n_keys = (int)c.key_dtypes.size();
+  t->n_acc = (int)c.words.size();
+  const size_t cap = t->capacity;
+  t->state = dev_alloc_zero(ctx_, cap * 4);
+  t->hash = dev_alloc(ctx_, cap * 8);
+  t->min_row = dev_alloc(ctx_, cap * 8);
+  t->keys = dev_alloc_zero(ctx_, cap * 8 * std::max(t->n_keys, 1));
+  t->knull = dev_alloc_zero(ctx_, cap * 4);
+  t->acc = dev_alloc(ctx_, cap * 8 * std::max(t->n_acc, 1));
+  t->new_slots = dev_alloc(ctx_, cap * 4);
+  t->counters = dev_alloc_zero(ctx_, 16);
+  SQ_CUDA(cudaMemsetAsync(t->min_row->p, 0xff, cap * 8, ctx_.stream));
+  for (int w = 0; w < t->n_acc; w++) {
+    uint64_t ident = word_identity(c.words[w].op);
+    if (ident == 0) SQ_CUDA(cudaMemsetAsync((uint64_t*)t->acc->p + (size_t)w * cap, 0, cap * 8, ctx_.stream));
+    else launch_fill_u64((uint64_t*)t->acc->p + (size_t)w * cap, (int64_t)cap, ident, ctx_.stream);
+  }
+  if (table_) {
+    launch_table_rehash(table_->view(), t->view(), t->n_keys, t->n_acc, ctx_.stream);
+    // carry the counters: groups, pending new-slot list is dropped (fix-up ran before any growth), status
+    SQ_CUDA(cudaMemcpyAsync(t->counters->p, table_->counters->p, 4, cudaMemcpyDeviceToDevice, ctx_.stream));
+    SQ_CUDA(cudaMemcpyAsync((uint32_t*)t->counters->p + 2, (uint32_t*)table_->counters->p + 2, 4, cudaMemcpyDeviceToDevice, ctx_.stream));
+  }
+  table_ = std::move(t);
+}
+
+// ------------------------------------------------------------------ push
+void AggOp::push(const DBatch& batch) {
+  ctx_.activate();
+  ctx_.reap();
+  Compiled& c = compiled_for(batch);
+  if (key_dtypes_.empty()) key_dtypes_ = c.key_dtypes;
+  seen_batch_ = true;
+  const int64_t n = batch.n;
+  const int64_t batch_no = batches_seen_++;
+  const int64_t row_base = rows_seen_;
+  rows_seen_ += n;
+  if (n == 0) return;
+  if (n >= (1LL << 32)) fail(SQLRS_ERR_INVALID_ARG, "a batch may hold fewer than 2^32 rows (reference index width, hash_agg.rs:109)");
+  const int K = (int)c.key_dtypes.size();
+  BufPtr err = dev_alloc_zero(ctx_, 4);
+  void* errp = err->p;
+  uint32_t host_counters[4] = {0, 0, 0, 0};
+  auto read_counters = [&]() {
+    SQ_CUDA(cudaMemcpyAsync(host_counters, table_->counters->p, 12, cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    if (host_counters[2] & 2u) fail(SQLRS_ERR_INTERNAL, "group table overflow (internal sizing error)");
+  };
+  // key fix-up for the groups that appeared since the last flush (hash-only identity: the reference
+  // reports the keys of a group's FIRST row), then reset the list.  Must run before the table is
+  // re-hashed (slot numbers change) and at the end of every batch (the rows are gone afterwards).
+  auto flush_new_slots = [&]() {
+    const uint32_t n_new = host_counters[1];
+    if (n_new == 0 || !table_) return;
+    if (K > 0 && opt_.match_mode == SQLRS_MATCH_HASH_ONLY) {
+      SqInBlob in_all(batch, 0);
+      int64_t n_all = n, rb_all = row_base;
+      TableView tv_all = table_->view();
+      uint32_t nn = n_new;
+      void* fargs[] = {in_all.ptr(), &n_all, &rb_all, &tv_all, &nn};
+      jit_launch(c.fixkeys, (unsigned)div_up(n_new, 128), 128, 0, ctx_.stream, fargs);
+    }
+    SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 1, 0, 4, ctx_.stream));
+    host_counters[1] = 0;
+  };
+  uint32_t groups_before = 0;
+  if (table_) {
+    read_counters();
+    groups_before = host_counters[0];
+  }
+
+  bool done = false;
+  if (!use_global_ && c.small_ok) {
+    const int grid = (int)std::min<int64_t>(c.small_grid, std::max<int64_t>(1, div_up(n, (int64_t)c.block * c.unroll)));
+    const size_t entries = (size_t)grid * c.slots;
+    ensure_table((uint32_t)std::min<uint64_t>(2ULL * (groups_before + entries) + 1024, 1ULL << 31));
+    BufPtr p_state = dev_alloc(ctx_, entries * 4), p_hash = dev_alloc(ctx_, entries * 8), p_min = dev_alloc(ctx_, entries * 8);
+    BufPtr p_keys = dev_alloc(ctx_, entries * 8 * std::max(K, 1)), p_knull = dev_alloc(ctx_, entries * 4);
+    BufPtr p_acc = dev_alloc(ctx_, entries * 8 * std::max<size_t>(c.words.size(), 1));
+    struct {
+      void *state, *hash, *min_row, *keys, *knull, *acc;
+    } part = {p_state->p, p_hash->p, p_min->p, p_keys->p, p_knull->p, p_acc->p};
+    SqInBlob in(batch, 0);
+    int64_t n_arg = n, rb = row_base, bn = batch_no;
+    void* status = (uint32_t*)table_->counters->p + 2;
+    TableView tv = table_->view();
+    int n_entries = (int)entries;
+    void* args_small[] = {in.ptr(), &n_arg, &rb, &part, &status, &errp};
+    jit_launch(c.small, (unsigned)grid, (unsigned)c.block, c.small_smem, ctx_.stream, args_small);
+    void* args_merge[] = {&part, &n_entries, &tv, &bn, &status};
+    jit_launch(c.merge, (unsigned)div_up(n_entries, 128), 128, 0, ctx_.stream, args_merge);
+    read_counters();
+    if (host_counters[2] & 1u) {
+      use_global_ = true;  // more groups than the shared-memory path holds: this and later batches use the HBM table
+      uint32_t zero = 0;
+      SQ_CUDA(cudaMemcpyAsync((uint32_t*)table_->counters->p + 2, &zero, 4, cudaMemcpyHostToDevice, ctx_.stream));
+      SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    } else {
+      done = true;
+      last_path_ = "sq_agg_small (private shared-memory accumulators, " + std::to_string(c.slots) + " slots x " + std::to_string(c.block) +
+                   " threads, grid " + std::to_string(grid) + ") + sq_agg_merge";
+    }
+  }
+  if (!done) {
+    use_global_ = true;
+    const int64_t chunk = 1LL << 22;
+    for (int64_t start = 0; start < n; start += chunk) {
+      const int64_t len = std::min(chunk, n - start);
+      uint32_t groups_now = 0;
+      if (table_) {
+        read_counters();
+        groups_now = host_counters[0];
+        flush_new_slots();
+      }
+      ensure_table((uint32_t)std::min<uint64_t>(2ULL * ((uint64_t)groups_now + (uint64_t)len) + 1024, 1ULL << 31));
+      SqInBlob in(batch, start);
+      int64_t n_arg = len, rb = row_base + start, bn = batch_no;
+      void* status = (uint32_t*)table_->counters->p + 2;
+      TableView tv = table_->view();
+      void* args[] = {in.ptr(), &n_arg, &rb, &tv, &bn, &status, &errp};
+      const int sms = device_sm_count(ctx_.device);
+      unsigned grid = (unsigned)std::min<int64_t>(div_up(len, 256), (int64_t)sms * 8);
+      jit_launch(c.global, grid, 256, 0, ctx_.stream, args);
+    }
+    read_counters();
+    last_path_ = "sq_agg_global (open-addressed table in HBM, capacity " + std::to_string(table_->capacity) + ")";
+  }
+  read_counters();
+  flush_new_slots();
+  check_error_flag(ctx_, err, "aggregate argument");
+}
+
+// ------------------------------------------------------------------ finish
+void AggOp::build_output(std::vector<Field>* fields, HostGroups* g) {
+  if (!seen_batch_) fail(SQLRS_ERR_INTERNAL, "called `Option::unwrap()` on a `None` value (no input batch)");
+  ctx_.activate();
+  const Compiled& c = *cache_.begin()->second;
+  const int K = (int)c.key_dtypes.size(), W = (int)c.words.size();
+  g->n = 0;
+  if (table_) {
+    uint32_t counters[4] = {0, 0, 0, 0};
+    SQ_CUDA(cudaMemcpyAsync(counters, table_->counters->p, 12, cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    const uint32_t n = counters[0];
+    if (n > 0) {
+      BufPtr d_hash = dev_alloc(ctx_, (size_t)n * 8), d_min = dev_alloc(ctx_, (size_t)n * 8);
+      BufPtr d_keys = dev_alloc(ctx_, (size_t)n * 8 * std::max(K, 1)), d_knull = dev_alloc(ctx_, (size_t)n * 4);
+      BufPtr d_acc = dev_alloc(ctx_, (size_t)n * 8 * std::max(W, 1)), d_cnt = dev_alloc_zero(ctx_, 4);
+      launch_table_compact(table_->view(), K, W, (uint64_t*)d_hash->p, (uint64_t*)d_min->p, (uint64_t*)d_keys->p, (uint32_t*)d_knull->p,
+                           (uint64_t*)d_acc->p, n, (uint32_t*)d_cnt->p, ctx_.stream);
+      g->n = n;
+      g->hash.resize(n);
+      g->min_row.resize(n);
+      g->keys.resize((size_t)n * std::max(K, 1));
+      g->knull.resize(n);
+      g->acc.resize((size_t)n * std::max(W, 1));
+      SQ_CUDA(cudaMemcpyAsync(g->hash.data(), d_hash->p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx_.stream));
+      SQ_CUDA(cudaMemcpyAsync(g->min_row.data(), d_min->p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx_.stream));
+      if (K) SQ_CUDA(cudaMemcpyAsync(g->keys.data(), d_keys->p, (size_t)n * 8 * K, cudaMemcpyDeviceToHost, ctx_.stream));
+      SQ_CUDA(cudaMemcpyAsync(g->knull.data(), d_knull->p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx_.stream));
+      if (W) SQ_CUDA(cudaMemcpyAsync(g->acc.data(), d_acc->p, (size_t)n * 8 * W, cudaMemcpyDeviceToHost, ctx_.stream));
+      ctx_.sync();
+    }
+  }
+  fields->clear();
+  for (int k = 0; k < K; k++) fields->push_back(Field{k < (int)group_names_.size() ? group_names_[k] : "", c.key_dtypes[k], true});
+  for (size_t j = 0; j < aggs_.size(); j++) fields->push_back(Field{aggs_[j].name, c.aggs[j].out_dtype, true});
+}
+
+static double sortable_to_f64(int64_t s) {
+  int64_t b = s ^ ((s >> 63) & 0x7fffffffffffffffLL);
+  double d;
+  std::memcpy(&d, &b, 8);
+  return d;
+}
+
+void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
+  std::vector<Field> fields;
+  HostGroups g;
+  build_output(&fields, &g);
+  const Compiled& c = *cache_.begin()->second;
+  const int K = (int)c.key_dtypes.size(), W = (int)c.words.size();
+  const uint32_t n = g.n;
+  // first-appearance order (hash_agg.rs:98,134) = ascending first global row id
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return g.min_row[a] < g.min_row[b]; });
+  const bool synth_row = simple_ && n == 0;  // SimpleAgg over batches without a surviving row: one row of initial values
+  const int64_t rows = synth_row ? 1 : n;
+  std::vector<HostCol> cols(fields.size());
+  for (int k = 0; k < K; k++) {
+    HostCol& col = cols[k];
+    col.dtype = c.key_dtypes[k];
+    if (col.dtype == SQLRS_DT_NULL)
+      fail(SQLRS_ERR_ARROW, "NotYetImplemented: not support Null as group by key");  // types/mod.rs:241-245
+    bool any_null = false;
+    for (uint32_t i = 0; i < n; i++) any_null |= (g.knull[order[i]] >> k) & 1u;
+    if (any_null) col.valid.assign(n, 1);
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t e = order[i];
+      const uint64_t bits = g.keys[(size_t)k * n + e];
+      const bool is_null = (g.knull[e] >> k) & 1u;
+      if (is_null) col.valid[i] = 0;
+      if (col.dtype == SQLRS_DT_FLOAT64) {
+        double d;
+        std::memcpy(&d, &bits, 8);
+        col.f.push_back(is_null ? 0.0 : d);
+      } else {
+        col.i.push_back(is_null ? 0 : (int64_t)bits);
+      }
+    }
+  }
+  for (size_t j = 0; j < aggs_.size(); j++) {
+    HostCol& col = cols[K + j];
+    const AggPlan& p = c.aggs[j];
+    col.dtype = p.out_dtype;
+    std::vector<uint8_t> valid(rows, 1);
+    bool any_null = false;
+    for (int64_t i = 0; i < rows; i++) {
+      uint64_t word = 0, nvalid = 1;
+      if (!synth_row) {
+        const uint32_t e = order[i];
+        word = g.acc[(size_t)p.value_word * n + e];
+        if (p.nvalid_word >= 0) nvalid = g.acc[(size_t)p.nvalid_word * n + e];
+      } else {
+        word = word_identity(c.words[p.value_word].op);
+        nvalid = 0;
+      }
+      if (p.func == SQLRS_AGG_COUNT) {
+        col.i.push_back((int64_t)(c.words[p.value_word].op == W_COUNT_EPOCH ? (word & kEpochMask) : word));
+        continue;
+      }
+      const bool is_null = nvalid == 0;
+      if (is_null) {
+        valid[i] = 0;
+        any_null = true;
+      }
+      if (col.dtype == SQLRS_DT_FLOAT64) {
+        double d;
+        if (p.f64_sortable) d = sortable_to_f64((int64_t)word);
+        else std::memcpy(&d, &word, 8);
+        col.f.push_back(is_null ? 0.0 : d);
+      } else {
+        col.i.push_back(is_null ? 0 : (int64_t)word);
+      }
+    }
+    if (any_null) col.valid = valid;
+  }
+  (void)W;
+  export_host_columns(fields, cols, rows, out, out_schema);
+}
+
+DBatch AggOp::finish_device() { fail(SQLRS_ERR_UNSUPPORTED, "aggregate results are produced on the host"); }
+
+// ------------------------------------------------------------------ partial / final (multi-GPU)
+DBatch AggOp::export_partials() { fail(SQLRS_ERR_UNSUPPORTED, "export_partials: not built yet"); }
+void AggOp::merge_partials(const DBatch&) { fail(SQLRS_ERR_UNSUPPORTED, "merge_partials: not built yet"); }
+
+}  // namespace sq

@@ -1,0 +1,278 @@
+// sqlrs_b200 — HashJoinExecutor on the GPU (see join.hpp; kernels: kernels_join.cu, csrc/jit/eval.cuh).
+#include "join.hpp"
+
+#include "kernels_aot.hpp"
+
+namespace sq {
+
+struct JoinOp::Impl {
+  // build side
+  std::vector<DBatch> left_batches;
+  std::vector<std::vector<DCol>> left_key_parts;  // per batch: [hash, (raw bits x K, nullmask)]
+  int64_t left_rows = 0;
+  bool sealed = false;
+  DBatch left_single;
+  DCol h_all, knull_all;
+  BufPtr keys_all;  // [K][n_build]
+  // table
+  BufPtr slot_rep, slot_count, slot_start, rows;
+  uint32_t capacity = 0;
+  BufPtr visited_left;  // bitmap over build rows (Left/Full)
+  std::unique_ptr<EvalProgram> left_prog, right_prog, filter_prog;
+  JoinTableView view{};
+};
+
+static EvalRequest key_request(const std::vector<ExprCopy>& keys, bool match_keys) {
+  EvalRequest r;
+  for (const ExprCopy& k : keys) {
+    r.exprs.push_back(k);
+    r.is_key.push_back(true);
+  }
+  r.outs.push_back({OUT_HASH, 0});
+  if (match_keys) {
+    for (size_t k = 0; k < keys.size(); k++) r.outs.push_back({OUT_RAWBITS, (int)k});
+    r.outs.push_back({OUT_NULLMASK, 0});
+  }
+  return r;
+}
+
+JoinOp::JoinOp(int join_type, std::vector<ExprCopy> left_keys, std::vector<ExprCopy> right_keys, ExprCopy filter,
+               std::vector<Field> out_fields, const Options& opt)
+    : ctx_(opt), opt_(opt), join_type_(join_type), left_keys_(std::move(left_keys)), right_keys_(std::move(right_keys)),
+      filter_(std::move(filter)), out_fields_(std::move(out_fields)), impl_(new Impl()) {
+  if (left_keys_.size() != right_keys_.size() || left_keys_.empty()) fail(SQLRS_ERR_INTERNAL, "HashJoin must has on condition");
+  if (left_keys_.size() > 16) fail(SQLRS_ERR_UNSUPPORTED, "more than 16 join keys");
+  const bool mk = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
+  impl_->left_prog = std::make_unique<EvalProgram>(key_request(left_keys_, mk));
+  impl_->right_prog = std::make_unique<EvalProgram>(key_request(right_keys_, mk));
+  if (!filter_.empty()) {
+    EvalRequest r;
+    r.exprs.push_back(filter_);
+    r.is_key.push_back(false);
+    r.outs.push_back({OUT_KEEP, 0});
+    impl_->filter_prog = std::make_unique<EvalProgram>(std::move(r));
+  }
+}
+JoinOp::~JoinOp() = default;
+
+// hash_join.rs:161-181
+void JoinOp::build_push(const DBatch& batch) {
+  if (impl_->sealed) fail(SQLRS_ERR_INVALID_ARG, "hash_join: build_push after probe");
+  ctx_.reap();
+  EvalResult keys = impl_->left_prog->run(ctx_, batch, "join key");
+  impl_->left_key_parts.push_back(keys.cols);
+  impl_->left_batches.push_back(batch);
+  impl_->left_rows += batch.n;
+}
+
+// concat_batches (:187) + the hash table over the build side
+void JoinOp::seal() {
+  Impl& im = *impl_;
+  if (im.sealed) return;
+  im.sealed = true;
+  if (im.left_batches.empty()) return;
+  const int64_t n = im.left_rows;
+  const int K = (int)left_keys_.size();
+  const bool mk = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
+  im.left_single.fields = im.left_batches[0].fields;
+  im.left_single.n = n;
+  for (size_t c = 0; c < im.left_single.fields.size(); c++) {
+    std::vector<DCol> parts;
+    for (const DBatch& b : im.left_batches) {
+      if (b.cols.size() != im.left_single.fields.size()) fail(SQLRS_ERR_ARROW, "concat_batches: schema mismatch");
+      parts.push_back(b.cols[c]);
+    }
+    im.left_single.cols.push_back(concat_cols(ctx_, parts, im.left_batches[0].cols[c].dtype));
+  }
+  {
+    std::vector<DCol> parts;
+    for (auto& p : im.left_key_parts) parts.push_back(p[0]);
+    im.h_all = concat_cols(ctx_, parts, SQLRS_DT_INT64);
+  }
+  if (mk) {
+    im.keys_all = dev_alloc(ctx_, (size_t)std::max<int64_t>(n, 1) * 8 * K);
+    for (int k = 0; k < K; k++) {
+      int64_t off = 0;
+      for (auto& p : im.left_key_parts) {
+        if (p[1 + k].n)
+          SQ_CUDA(cudaMemcpyAsync((uint64_t*)im.keys_all->p + (size_t)k * n + off, p[1 + k].data, (size_t)p[1 + k].n * 8,
+                                  cudaMemcpyDeviceToDevice, ctx_.stream));
+        off += p[1 + k].n;
+      }
+    }
+    std::vector<DCol> parts;
+    for (auto& p : im.left_key_parts) parts.push_back(p[1 + K]);
+    im.knull_all = concat_cols(ctx_, parts, SQLRS_DT_INT32);
+  }
+  im.left_batches.clear();
+  im.left_key_parts.clear();
+
+  // table: capacity >= 2 x build rows
+  uint64_t cap = 1024;
+  while (cap < 2ULL * (uint64_t)n) cap <<= 1;
+  if (cap > (1ULL << 30)) fail(SQLRS_ERR_UNSUPPORTED, "join build side too large for one table (> 2^29 rows)");
+  im.capacity = (uint32_t)cap;
+  im.slot_rep = dev_alloc(ctx_, cap * 8);
+  SQ_CUDA(cudaMemsetAsync(im.slot_rep->p, 0xff, cap * 8, ctx_.stream));
+  im.slot_count = dev_alloc_zero(ctx_, cap * 4);
+  im.slot_start = dev_alloc(ctx_, cap * 8);
+  im.rows = dev_alloc(ctx_, (size_t)std::max<int64_t>(n, 1) * 8);
+  JoinTableView& v = im.view;
+  v.slot_rep = (int64_t*)im.slot_rep->p;
+  v.slot_count = (uint32_t*)im.slot_count->p;
+  v.slot_start = (uint64_t*)im.slot_start->p;
+  v.rows = (int64_t*)im.rows->p;
+  v.capacity = im.capacity;
+  v.h = (const uint64_t*)im.h_all.data;
+  v.keys = mk ? (const uint64_t*)im.keys_all->p : nullptr;
+  v.knull = mk ? (const uint32_t*)im.knull_all.data : nullptr;
+  v.n_build = n;
+  v.n_keys = K;
+  v.match_keys = mk ? 1 : 0;
+  if (n > 0) {
+    BufPtr row_slot = dev_alloc(ctx_, (size_t)n * 4);
+    BufPtr misc = dev_alloc_zero(ctx_, 16);  // [0] max count, [8] total
+    launch_join_insert(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
+    BufPtr scratch = dev_alloc(ctx_, scan_scratch_entries((int64_t)cap) * 8);
+    launch_scan_u32_large(v.slot_count, (int64_t)cap, (unsigned long long*)v.slot_start, (unsigned long long*)misc->p + 1,
+                          (unsigned long long*)scratch->p, ctx_.stream);
+    uint32_t max_count = 0;
+    SQ_CUDA(cudaMemcpyAsync(&max_count, misc->p, 4, cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    if (max_count <= 64) {
+      BufPtr fill = dev_alloc_zero(ctx_, cap * 4);
+      launch_join_fill(v, (const int32_t*)row_slot->p, (uint32_t*)fill->p, ctx_.stream);
+      if (max_count > 1) launch_join_sort_ranges(v, ctx_.stream);
+    } else {
+      join_fill_sorted(v, (const int32_t*)row_slot->p, ctx_.stream);
+    }
+  }
+  if (join_type_ == SQLRS_JOIN_LEFT || join_type_ == SQLRS_JOIN_FULL) im.visited_left = dev_alloc_zero(ctx_, (size_t)bitmap_words(n) * 4 + 4);
+}
+
+// build_batch, hash_join.rs:25-45: all left columns by (nullable) build index, all right columns by probe index
+DBatch JoinOp::build_batch(const DBatch& right, const int64_t* li, bool li_nullable, const uint32_t* ri, int64_t m) {
+  DBatch out;
+  out.fields = out_fields_;
+  out.n = m;
+  for (const DCol& c : impl_->left_single.cols) out.cols.push_back(gather_col_i64(ctx_, c, li, m, li_nullable));
+  for (const DCol& c : right.cols) out.cols.push_back(gather_col_u32(ctx_, c, ri, m));
+  check_schema(out);
+  return out;
+}
+
+// RecordBatch::try_new(schema, columns): column count / types / declared nullability must agree
+void JoinOp::check_schema(DBatch& b) {
+  if (b.cols.size() != out_fields_.size()) fail(SQLRS_ERR_ARROW, "number of columns must match number of fields in schema");
+  for (size_t c = 0; c < b.cols.size(); c++) {
+    if (b.cols[c].dtype != out_fields_[c].dtype)
+      fail(SQLRS_ERR_ARROW, std::string("column types must match schema types, expected ") + dtype_name(out_fields_[c].dtype) +
+                                " but found " + dtype_name(b.cols[c].dtype));
+    if (!out_fields_[c].nullable && null_count_of(ctx_, b.cols[c]) > 0)
+      fail(SQLRS_ERR_ARROW, "Column '" + out_fields_[c].name + "' is declared as non-nullable but contains null values");
+  }
+}
+
+// one probe batch, hash_join.rs:208-292
+bool JoinOp::probe(const DBatch& right, DBatch* result) {
+  seal();
+  Impl& im = *impl_;
+  if (im.capacity == 0) return false;  // empty build side: no left batch at all (:183-185)
+  ctx_.reap();
+  const int K = (int)right_keys_.size();
+  const bool mk = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
+  const bool keep_right = join_type_ == SQLRS_JOIN_RIGHT || join_type_ == SQLRS_JOIN_FULL;
+  const int64_t n = right.n;
+  if (n >= (1LL << 32)) fail(SQLRS_ERR_INVALID_ARG, "a probe batch may hold fewer than 2^32 rows (hash_join.rs:219)");
+  EvalResult rk = im.right_prog->run(ctx_, right, "join key");
+  BufPtr pkeys;
+  if (mk && n > 0) {
+    pkeys = dev_alloc(ctx_, (size_t)n * 8 * K);
+    for (int k = 0; k < K; k++)
+      SQ_CUDA(cudaMemcpyAsync((uint64_t*)pkeys->p + (size_t)k * n, rk.cols[1 + k].data, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx_.stream));
+  }
+  int64_t total = 0;
+  BufPtr li, ri;
+  if (n > 0) {
+    BufPtr slot_of = dev_alloc(ctx_, (size_t)n * 4), counts = dev_alloc(ctx_, (size_t)n * 4);
+    BufPtr offsets = dev_alloc(ctx_, (size_t)n * 8 + 8);
+    BufPtr scratch = dev_alloc(ctx_, scan_scratch_entries(n) * 8);
+    launch_join_probe_count(im.view, (const uint64_t*)rk.cols[0].data, mk ? (const uint64_t*)pkeys->p : nullptr,
+                            mk ? (const uint32_t*)rk.cols[1 + K].data : nullptr, n, keep_right ? 1 : 0, (int32_t*)slot_of->p,
+                            (uint32_t*)counts->p, ctx_.stream);
+    unsigned long long* total_d = (unsigned long long*)offsets->p + n;
+    launch_scan_u32_large((const uint32_t*)counts->p, n, (unsigned long long*)offsets->p, total_d, (unsigned long long*)scratch->p, ctx_.stream);
+    unsigned long long t = 0;
+    SQ_CUDA(cudaMemcpyAsync(&t, total_d, 8, cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    total = (int64_t)t;
+    if (total >= (1LL << 32)) fail(SQLRS_ERR_UNSUPPORTED, "join output of one probe batch exceeds 2^32 rows");
+    li = dev_alloc(ctx_, (size_t)std::max<int64_t>(total, 1) * 8);
+    ri = dev_alloc(ctx_, (size_t)std::max<int64_t>(total, 1) * 4);
+    launch_join_probe_write(im.view, (const int32_t*)slot_of->p, (const unsigned long long*)offsets->p, n, keep_right ? 1 : 0,
+                            (int64_t*)li->p, (uint32_t*)ri->p, ctx_.stream);
+  } else {
+    li = dev_alloc(ctx_, 8);
+    ri = dev_alloc(ctx_, 4);
+  }
+
+  if (!filter_.empty()) {  // apply_join_filter, :47-127
+    DBatch inter = build_batch(right, (const int64_t*)li->p, keep_right, (const uint32_t*)ri->p, total);
+    EvalResult mask = im.filter_prog->run(ctx_, inter, "join filter");
+    int64_t kept = 0;
+    BufPtr pos = compact_indices(ctx_, (const uint32_t*)mask.cols[0].data, total, &kept);
+    int64_t extra = 0;
+    BufPtr unvisited;
+    if (keep_right && n > 0) {  // :73-121 — right rows that lost all their matches come back with a NULL left side
+      BufPtr fr = dev_alloc(ctx_, (size_t)std::max<int64_t>(kept, 1) * 4);
+      launch_gather_u32idx(4, ri->p, nullptr, (const uint32_t*)pos->p, kept, fr->p, nullptr, ctx_.stream);
+      BufPtr visited = dev_alloc_zero(ctx_, (size_t)bitmap_words(n) * 4);
+      launch_mark_bits_u32((const uint32_t*)fr->p, kept, (uint32_t*)visited->p, ctx_.stream);
+      BufPtr inv = dev_alloc(ctx_, (size_t)bitmap_words(n) * 4);
+      launch_bitmap_not((const uint32_t*)visited->p, n, (uint32_t*)inv->p, ctx_.stream);
+      unvisited = compact_indices(ctx_, (const uint32_t*)inv->p, n, &extra);
+    }
+    const int64_t m = kept + extra;
+    BufPtr fl = dev_alloc(ctx_, (size_t)std::max<int64_t>(m, 1) * 8), fr = dev_alloc(ctx_, (size_t)std::max<int64_t>(m, 1) * 4);
+    launch_gather_u32idx(8, li->p, nullptr, (const uint32_t*)pos->p, kept, fl->p, nullptr, ctx_.stream);
+    launch_gather_u32idx(4, ri->p, nullptr, (const uint32_t*)pos->p, kept, fr->p, nullptr, ctx_.stream);
+    if (extra > 0) {
+      SQ_CUDA(cudaMemsetAsync((int64_t*)fl->p + kept, 0xff, (size_t)extra * 8, ctx_.stream));  // -1 = NULL index
+      SQ_CUDA(cudaMemcpyAsync((uint32_t*)fr->p + kept, unvisited->p, (size_t)extra * 4, cudaMemcpyDeviceToDevice, ctx_.stream));
+    }
+    li = fl;
+    ri = fr;
+    total = m;
+  }
+  if (im.visited_left && total > 0) launch_mark_bits_i64((const int64_t*)li->p, total, (uint32_t*)im.visited_left->p, ctx_.stream);  // :274-282
+  *result = build_batch(right, (const int64_t*)li->p, keep_right, (const uint32_t*)ri->p, total);  // :284-291
+  return true;
+}
+
+// Left/Full tail, hash_join.rs:296-322
+bool JoinOp::finish(DBatch* result) {
+  seal();
+  Impl& im = *impl_;
+  if (im.capacity == 0) return false;
+  if (!(join_type_ == SQLRS_JOIN_LEFT || join_type_ == SQLRS_JOIN_FULL)) return false;
+  const int64_t n = im.left_rows;
+  int64_t m = 0;
+  BufPtr idx;
+  if (n > 0) {
+    BufPtr inv = dev_alloc(ctx_, (size_t)bitmap_words(n) * 4);
+    launch_bitmap_not((const uint32_t*)im.visited_left->p, n, (uint32_t*)inv->p, ctx_.stream);
+    idx = compact_indices(ctx_, (const uint32_t*)inv->p, n, &m);
+  } else {
+    idx = dev_alloc(ctx_, 4);
+  }
+  DBatch out;
+  out.fields = out_fields_;
+  out.n = m;
+  for (const DCol& c : im.left_single.cols) out.cols.push_back(gather_col_u32(ctx_, c, (const uint32_t*)idx->p, m));
+  for (size_t c = im.left_single.cols.size(); c < out_fields_.size(); c++) out.cols.push_back(null_col(ctx_, out_fields_[c].dtype, m));
+  check_schema(out);
+  *result = out;
+  return true;
+}
+
+}  // namespace sq

@@ -1,0 +1,54 @@
+// sqlrs_b200 — a physical sub-plan on the GPU: what ExecutorBuilder::build(plan) wires together in
+// the reference (src/executor/mod.rs:45-47, visit_* :87-200).  Tables stay resident in HBM, the
+// intermediate batches never leave the device, and Filter directly below an aggregate is fused
+// into the aggregate's row program (one pass over the scan, nothing materialised).
+#pragma once
+#include <deque>
+#include <map>
+
+#include "join.hpp"
+#include "ops.hpp"
+
+namespace sq {
+
+class Plan {
+ public:
+  Plan(const sqlrs_plan_node* nodes, int32_t n_nodes, int32_t root, const Options& opt);
+  ~Plan() { reset(); }
+  void push_table(int slot, DBatch batch);
+  void execute();
+  bool next(ArrowArray* out, ArrowSchema* out_schema);
+  void reset();
+  const char* describe() const { return description_.c_str(); }
+  Ctx& ctx() { return ctx_; }
+
+ private:
+  struct Node {
+    int kind = 0, child0 = -1, child1 = -1, table_slot = 0, join_type = 0;
+    ExprCopy predicate;
+    std::vector<AggSpec> aggs;
+    std::vector<ExprCopy> group_by, left_keys, right_keys;
+    std::vector<std::string> group_names;
+    std::vector<Field> join_fields;
+    // operators kept across execute() calls so that repeated runs reuse compiled kernels
+    std::unique_ptr<EvalProgram> filter_prog;
+  };
+  struct Result {
+    bool on_host = false;
+    ArrowArray arr{};
+    ArrowSchema sch{};
+    DBatch dev;
+  };
+  std::vector<DBatch> run(int idx);
+  void run_agg_to_host(int idx, Result* res);
+
+  Ctx ctx_;
+  Options opt_;
+  std::vector<Node> nodes_;
+  int root_ = 0;
+  std::map<int, std::vector<DBatch>> tables_;
+  std::deque<Result> results_;
+  std::string description_;
+};
+
+}  // namespace sq

@@ -1,0 +1,210 @@
+"""Host-side mirror of the reference's physical plan nodes and ExecutorBuilder.
+
+Reference: `PhysicalTableScan`, `PhysicalFilter`, `PhysicalSimpleAgg`, `PhysicalHashAgg`,
+`PhysicalHashJoin` (src/optimizer/plan_node/physical_*.rs) and
+`ExecutorBuilder::build(plan) -> BoxedExecutor` (src/executor/mod.rs:36-56, visit_* :87-200).
+Handing the library the whole sub-plan (sqlrs_plan_* of include/sqlrs_b200.h) keeps tables and
+intermediates in HBM and lets it fuse Filter into the aggregate above it.  This file contains no
+compute: it flattens the tree into `sqlrs_plan_node` records and moves Arrow data across the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import pyarrow as pa
+
+from . import ffi
+from .executor import JOIN_TYPES, JoinCondition
+from .expr import AggArray, BoundExpr, ExprArray, NameArray
+
+
+class PlanNode:
+    def output_schema(self, tables: Dict[int, pa.Schema]) -> pa.Schema:
+        raise NotImplementedError
+
+
+@dataclass
+class PhysicalTableScan(PlanNode):
+    """PhysicalTableScan (src/optimizer/plan_node/physical_table_scan.rs): batches are pushed per table slot."""
+    table_slot: int
+
+    def output_schema(self, tables):
+        return tables[self.table_slot]
+
+
+@dataclass
+class PhysicalFilter(PlanNode):
+    """PhysicalFilter{expr, input} (physical_filter.rs:8-20)"""
+    expr: BoundExpr
+    child: PlanNode
+
+    def output_schema(self, tables):
+        return self.child.output_schema(tables)
+
+
+@dataclass
+class PhysicalSimpleAgg(PlanNode):
+    """PhysicalSimpleAgg{agg_funcs, input} (physical_simple_agg.rs)"""
+    agg_funcs: Sequence[BoundExpr]
+    child: PlanNode
+
+    def output_schema(self, tables):
+        s = self.child.output_schema(tables)
+        return pa.schema([a.eval_field(s) for a in self.agg_funcs])
+
+
+@dataclass
+class PhysicalHashAgg(PlanNode):
+    """PhysicalHashAgg{agg_funcs, group_by, input} (physical_hash_agg.rs:8-20)"""
+    agg_funcs: Sequence[BoundExpr]
+    group_by: Sequence[BoundExpr]
+    child: PlanNode
+
+    def output_schema(self, tables):
+        s = self.child.output_schema(tables)
+        return pa.schema([g.eval_field(s) for g in self.group_by] + [a.eval_field(s) for a in self.agg_funcs])
+
+
+@dataclass
+class PhysicalHashJoin(PlanNode):
+    """PhysicalHashJoin{left, right, join_type, join_condition, join_output_columns} (physical_hash_join.rs:9-41)"""
+    left: PlanNode
+    right: PlanNode
+    join_type: str
+    join_condition: JoinCondition
+    join_output_schema: pa.Schema
+
+    def output_schema(self, tables):
+        return self.join_output_schema
+
+
+class GpuPlan:
+    """A built plan: push tables, execute, collect (try_collect, src/executor/mod.rs:58-64)."""
+
+    def __init__(self, lib: ffi.Library, root: PlanNode, table_schemas: Dict[int, pa.Schema], options=None):
+        self.lib = lib
+        self.options = options if options is not None else lib.options()
+        self._keep: list = []
+        nodes: List[ffi.PlanNode] = []
+
+        def add(node: PlanNode) -> int:
+            rec = ffi.PlanNode()
+            rec.child0 = rec.child1 = -1
+            if isinstance(node, PhysicalTableScan):
+                rec.kind, rec.table_slot = ffi.NODE_SCAN, node.table_slot
+            elif isinstance(node, PhysicalFilter):
+                rec.kind = ffi.NODE_FILTER
+                rec.child0 = add(node.child)
+                flat = node.expr.flatten()
+                self._keep.append(flat)
+                rec.predicate = flat.c
+            elif isinstance(node, (PhysicalSimpleAgg, PhysicalHashAgg)):
+                child_schema = node.child.output_schema(table_schemas)
+                rec.child0 = add(node.child)
+                aggs = AggArray(node.agg_funcs, child_schema)
+                self._keep.append(aggs)
+                rec.aggs, rec.n_aggs = aggs.ptr, aggs.n
+                if isinstance(node, PhysicalHashAgg):
+                    rec.kind = ffi.NODE_HASH_AGG
+                    groups = ExprArray(node.group_by)
+                    names = NameArray([g.eval_field(child_schema).name for g in node.group_by])
+                    self._keep += [groups, names]
+                    rec.group_by, rec.group_names, rec.n_group_by = groups.ptr, names.ptr, groups.n
+                else:
+                    rec.kind = ffi.NODE_SIMPLE_AGG
+            elif isinstance(node, PhysicalHashJoin):
+                if node.join_type not in JOIN_TYPES:
+                    raise ffi.ExecutorError(ffi.ERR_INTERNAL, "Cross join should not be in HashJoinExecutor")
+                rec.kind = ffi.NODE_HASH_JOIN
+                rec.child0 = add(node.left)
+                rec.child1 = add(node.right)
+                rec.join_type = JOIN_TYPES[node.join_type]
+                lk = ExprArray([l for l, _ in node.join_condition.on])
+                rk = ExprArray([r for _, r in node.join_condition.on])
+                self._keep += [lk, rk]
+                rec.left_keys, rec.right_keys, rec.n_keys = lk.ptr, rk.ptr, lk.n
+                if node.join_condition.filter is not None:
+                    flat = node.join_condition.filter.flatten()
+                    self._keep.append(flat)
+                    rec.predicate = flat.c
+                sch = ffi.export_schema(node.join_output_schema)
+                self._keep.append(sch)
+                rec.join_output_schema = C.pointer(sch)
+            else:
+                raise TypeError(f"unknown plan node {node!r}")
+            nodes.append(rec)
+            return len(nodes) - 1
+
+        root_idx = add(root)
+        arr = (ffi.PlanNode * len(nodes))(*nodes)
+        self._keep.append(arr)
+        self.handle = C.c_void_p()
+        try:
+            lib.check(lib.plan_create(arr, len(nodes), root_idx, C.byref(self.options), C.byref(self.handle)))
+        finally:
+            for k in self._keep:
+                if isinstance(k, ffi.ArrowSchema):
+                    ffi.release_schema(k)
+
+    def push_table(self, table_slot: int, batch: pa.RecordBatch):
+        arr, sch = ffi.export_batch(batch)
+        try:
+            self.lib.check(self.lib.plan_push_table(self.handle, table_slot, C.byref(arr), C.byref(sch)))
+        finally:
+            ffi.release_schema(sch)
+
+    def push_table_device(self, table_slot: int, device_batch):
+        """`device_batch`: tpch.DeviceTable (columns resident in HBM); zero copy."""
+        darr, sch = device_batch.export()
+        try:
+            self.lib.check(self.lib.plan_push_table_device(self.handle, table_slot, C.byref(darr), C.byref(sch)))
+        finally:
+            ffi.release_schema(sch)
+
+    def execute(self):
+        self.lib.check(self.lib.plan_execute(self.handle))
+
+    def collect(self) -> List[pa.RecordBatch]:
+        out = []
+        has = C.c_int32(0)
+        while True:
+            arr, sch = ffi.ArrowArray(), ffi.ArrowSchema()
+            self.lib.check(self.lib.plan_next(self.handle, C.byref(arr), C.byref(sch), C.byref(has)))
+            if not has.value:
+                return out
+            out.append(ffi.import_batch(arr, sch))
+
+    def run(self) -> List[pa.RecordBatch]:
+        self.execute()
+        return self.collect()
+
+    def reset(self):
+        self.lib.check(self.lib.plan_reset(self.handle))
+
+    def describe(self) -> str:
+        s = self.lib.plan_describe(self.handle)
+        return s.decode() if s else ""
+
+    def close(self):
+        if self.handle:
+            self.lib.plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ExecutorBuilder:
+    """ExecutorBuilder::new(storage).build(plan) (src/executor/mod.rs:36-56)"""
+
+    def __init__(self, lib: Optional[ffi.Library] = None, options=None):
+        self.lib = lib if lib is not None else ffi.load()
+        self.options = options
+
+    def build(self, plan: PlanNode, table_schemas: Dict[int, pa.Schema]) -> GpuPlan:
+        return GpuPlan(self.lib, plan, table_schemas, self.options)
