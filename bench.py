@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — TPC-H-shaped Q1' (Filter + 8-group HashAgg over lineitem) through the sqlrs_b200 C ABI.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port, 1 core)
+
+A "step" is one pass of the hot path (fused scan+filter+group-by+aggregate) over the whole synthetic
+lineitem table of scale factor --sf (default 100: the size BASELINE.json's metric is quoted on; it fits
+one B200).  With N GPUs the rows are split into N contiguous shards (strong scaling: total work fixed),
+each rank aggregates its shard, partial groups are exchanged by key hash (all-to-all) and merged.
+`value` = rows/s with inputs resident in HBM; `e2e` = the same call with HOST (pinned) Arrow buffers,
+H2D copies inside the timed region.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_oracle():
+    """CPU restatement of the reference's executor — used ONLY for cpu_baseline / --impl reference."""
+    from sqlrs_b200.host import ffi
+
+    path = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    return ffi.Library(path, "sqlrs_oracle_")
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for k, nme in enumerate(names):
+                    if s[2 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def q1_on_host_batches(lib, plan_root, schemas, table, batch_rows, opts):
+    """One Q1' pass of a HOST build of the ABI over `table`, fed in batches like the reference's scan."""
+    import pyarrow as pa
+
+    from sqlrs_b200.host.plan import ExecutorBuilder
+
+    p = ExecutorBuilder(lib, lib.options(**opts)).build(plan_root, schemas)
+    t0 = time.perf_counter()
+    for off in range(0, table.num_rows, batch_rows):
+        p.push_table(0, table.slice(off, batch_rows))
+    res = pa.Table.from_batches(p.run())
+    dt = time.perf_counter() - t0
+    p.close()
+    return dt, res
+
+
+def cpu_port_run(sample_rows, batch_rows, steps, warmup, sf, kind_note=""):
+    """Times the oracle port (1 core, like the reference's single-threaded executor) on a bounded sample."""
+    from sqlrs_b200.host import ffi, tpch
+
+    oracle = load_oracle()
+    d = tpch.dims(sf)
+    n_total = tpch.num_rows(oracle, d, tpch.LINEITEM)
+    n = min(sample_rows, n_total)
+    table = tpch.host_table(oracle, d, tpch.LINEITEM, 0, n, columns=tpch.Q1_COLUMNS)
+    plan_root, schemas = tpch.q1_plan()
+    opts = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    try:
+        os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[0]})
+    except Exception:
+        pass
+    times = []
+    for k in range(warmup + steps):
+        dt, _ = q1_on_host_batches(oracle, plan_root, schemas, table, batch_rows, opts)
+        if k >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"rows_per_s": n * len(times) / total, "ms_per_step": 1e3 * total / len(times), "rows": n, "batch_rows": batch_rows}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sample = args.ref_rows
+    r = cpu_port_run(sample, 1024, args.steps, max(1, min(args.warmup, 1)), args.sf)
+    line = {
+        "impl": "reference", "metric": "tpch_q1_rows_per_sec", "value": r["rows_per_s"], "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64+i64", "data": "synthetic",
+        "config": {"workload": f"tpch_q1_sf{args.sf:g}", "note": "reference CPU path = C++ restatement of sqlrs v1 Filter+HashAgg (the Rust crate needs nightly-2022-07-29, "
+                   "unbuildable here); single-threaded like the reference's executor; 1024-row batches (src/storage/csv.rs:105)"},
+        "cpu_baseline": {"value": r["rows_per_s"], "unit": "rows/s", "cores": 1, "kind": "port",
+                         "sample": f"first {r['rows']} lineitem rows of SF{args.sf:g} per step, batch {r['batch_rows']} rows"},
+        "e2e": {"value": r["rows_per_s"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args, rank, world, local_rank):
+    import pyarrow as pa
+    import torch
+
+    from sqlrs_b200.host import distributed as sqdist
+    from sqlrs_b200.host import ffi, tpch
+    from sqlrs_b200.host.plan import ExecutorBuilder
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    lib = ffi.load()
+    d = tpch.dims(args.sf)
+    n_total = tpch.num_rows(lib, d, tpch.LINEITEM)
+    lo, hi = n_total * rank // world, n_total * (rank + 1) // world
+    n_local = hi - lo
+    stream = torch.cuda.Stream(device=dev)
+    plan_root, schemas = tpch.q1_plan()
+    bytes_per_row = tpch.q1_bytes_per_row()
+
+    with torch.cuda.stream(stream):
+        table = tpch.device_table(lib, d, tpch.LINEITEM, lo, hi, columns=tpch.Q1_COLUMNS, device=dev)
+        opts = lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY, device_id=local_rank,
+                           flags=ffi.FLAG_TIMING, stream=C.c_void_p(stream.cuda_stream))
+        plan = ExecutorBuilder(lib, opts).build(plan_root, schemas)
+        kernel_ms, kernel_launches = [0.0], [0]
+        group = sqdist.TorchGroup(dist, dev) if world > 1 else None
+
+        def step(timed):
+            plan.push_table_device(0, table)
+            if world > 1:
+                res = sqdist.sharded_aggregate(plan, group, lo)
+            else:
+                plan.execute()
+                res = plan.collect()
+            if timed:
+                ms, nl = plan.scan_kernel_ms()
+                kernel_ms[0] += ms
+                kernel_launches[0] += nl
+            plan.reset()
+            return res
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        for _ in range(args.warmup):
+            result = step(False)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = lib.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            result = step(True)
+        e1.record(stream)
+        barrier()
+        launches = lib.kernel_launches() - launches0
+        elapsed_ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed_ms = float(t.item())
+        describe = plan.describe()
+
+        # ---- e2e: the same call with HOST (pinned) Arrow buffers; H2D inside the timed region
+        e2e = None
+        if args.e2e_steps > 0:
+            host_cols = []
+            for t_dev in table.tensors:
+                h = torch.empty(t_dev.shape, dtype=t_dev.dtype, pin_memory=True)
+                h.copy_(t_dev)
+                host_cols.append(h)
+            torch.cuda.synchronize(dev)
+            arrays = []
+            for h, f in zip(host_cols, table.schema):
+                a = h.numpy()
+                if pa.types.is_floating(f.type):
+                    a = a.view("float64")
+                arrays.append(pa.array(a))
+            host_batch = pa.RecordBatch.from_arrays(arrays, schema=table.schema)
+
+            def e2e_step():
+                plan.push_table(0, host_batch)
+                if world > 1:
+                    res = sqdist.sharded_aggregate(plan, group, lo)
+                else:
+                    plan.execute()
+                    res = plan.collect()
+                plan.reset()
+                return res
+
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e_result = e2e_step()
+            barrier()
+            e2e_s = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_s = float(t.item())
+            out_bytes = sum(b.nbytes for b in e2e_result) if e2e_result else 0
+            e2e = {"value": n_total * args.e2e_steps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": n_local * bytes_per_row,
+                   "d2h_bytes_per_step": int(out_bytes), "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
+                   "note": "pinned host Arrow buffers -> sqlrs_plan_push_table (H2D) -> execute -> result to host, per rank shard"}
+            del host_batch, arrays, host_cols
+        plan.close()
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    ms_per_step = elapsed_ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+    k_ms = kernel_ms[0] / max(kernel_launches[0], 1)
+    achieved = (n_local * bytes_per_row) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    line = {
+        "metric": "tpch_q1_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64+i64",
+        "data": "synthetic",
+        "config": {"workload": f"tpch_q1_sf{args.sf:g}", "rows": n_total, "rows_per_gpu": n_local, "columns_read": len(tpch.Q1_COLUMNS),
+                   "bytes_per_row": bytes_per_row, "groups": len(result[0]) if result else None, "count_mode": "sql_accumulate",
+                   "match_mode": "hash_and_key", "l2": "inputs (%.1f GB per GPU) are larger than the 126 MB L2" % (n_local * bytes_per_row / 1e9),
+                   "pipeline": describe},
+        "hbm_gbs_whole_step": n_total * bytes_per_row / (ms_per_step * 1e-3) / 1e9,
+        "roofline": {"bound": "hbm", "kernel": "sq_agg_small", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if achieved else None, "frac_of_8TBs": achieved / 8000.0 if achieved else None, "peak_source": peak_src,
+                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": n_local * bytes_per_row, "traffic": None},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if world == 1 and args.cpu_rows > 0:
+        r = cpu_port_run(args.cpu_rows, 1024, 1, 0, args.sf)
+        line["cpu_baseline"] = {"value": r["rows_per_s"], "unit": "rows/s", "cores": 1, "kind": "port",
+                                "sample": f"first {r['rows']} lineitem rows of SF{args.sf:g}, one pass, batch 1024 rows, C++ restatement of the sqlrs v1 executor"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sf", type=float, default=100.0)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-rows", type=int, default=48_000_000, help="rows of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--ref-rows", type=int, default=12_000_000, help="rows per step of --impl reference")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        log(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,6 +134,7 @@ typedef struct sqlrs_agg_desc {
 
 #define SQLRS_FLAG_NO_FUSION 1   /* plan API: never pick a fused pipeline, run operator by operator */
 #define SQLRS_FLAG_DEVICE_OUTPUT 2 /* reserved */
+#define SQLRS_FLAG_TIMING 4 /* bracket the dominant scan kernels with CUDA events (sqlrs_plan_scan_kernel_ms) */
 
 typedef struct sqlrs_options {
   int32_t count_mode; /* default SQLRS_COUNT_REFERENCE_OVERWRITE */
@@ -272,6 +273,20 @@ int SQLRS_API(plan_reset)(sqlrs_plan* p);
 /* human-readable: which pipeline (fused / generic) and kernels the plan runs with */
 const char* SQLRS_API(plan_describe)(sqlrs_plan* p);
 void SQLRS_API(plan_destroy)(sqlrs_plan* p);
+/* ---- partial / final aggregation for plans sharded over several GPUs.  The plan
+ *      root must be an aggregate.  Each rank: push its shard, execute_partial (row_base = global row
+ *      id of the shard's first row, keeps first-appearance order global), export_partials -> a host
+ *      batch of un-finalised groups whose column 0 ("hash", int64) is the group identity to
+ *      radix-partition on, the rest is opaque to the host; after the exchange: clear_partials,
+ *      merge_partials for every received batch (its own share included), finish_partial, plan_next. */
+int SQLRS_API(plan_execute_partial)(sqlrs_plan* p, int64_t row_base);
+int SQLRS_API(plan_export_partials)(sqlrs_plan* p, struct ArrowArray* out, struct ArrowSchema* out_schema);
+int SQLRS_API(plan_clear_partials)(sqlrs_plan* p);
+int SQLRS_API(plan_merge_partials)(sqlrs_plan* p, struct ArrowArray* partials, const struct ArrowSchema* schema);
+int SQLRS_API(plan_finish_partial)(sqlrs_plan* p);
+/* SQLRS_FLAG_TIMING: device time (ms, CUDA events on the plan's stream) the dominant scan kernel(s) of the
+ * last plan_execute took, and how many launches that covers — bench.py's roofline numerator/denominator */
+double SQLRS_API(plan_scan_kernel_ms)(sqlrs_plan* p, int64_t* n_launches);
 
 /* ---- synthetic TPC-H-shaped tables: counter-based, identical in the
  *      CUDA generator (writes straight into HBM) and the oracle's CPU generator ------ */

@@ -255,7 +255,9 @@ struct HashAgg {
     uint64_t hash;
     std::vector<Scalar> keys;
     std::vector<Accumulator> accs;
+    int64_t first_row = 0;  // global row id of the group's first row (orders merged partial groups)
   };
+  int64_t rows_seen = 0;
   std::vector<Group> groups;                               // group_hashs order (first appearance)
   std::unordered_map<uint64_t, std::vector<int>> by_hash;  // hash -> group ids (1 id in HASH_ONLY mode)
   std::vector<int> key_dtypes;
@@ -277,6 +279,7 @@ struct HashAgg {
     }
     Group g;
     g.hash = hash;
+    g.first_row = rows_seen + row;
     for (const ColPtr& k : keys) g.keys.push_back(Scalar::from_column(*k, row));  // :92-96
     for (const AggDesc& d : aggs) g.accs.emplace_back(d, opt.count_mode);         // :89
     groups.push_back(std::move(g));
@@ -311,6 +314,87 @@ struct HashAgg {
       const std::vector<uint32_t>& idx = rows_of[g];
       for (size_t k = 0; k < aggs.size(); k++) groups[g].accs[k].update_batch(take(*columns[k], idx));
     }
+    rows_seen += batch.n;
+  }
+
+  // ---- partial / final split (multi-process group-by; NOT part of the reference):
+  // un-finalised groups as a batch [hash, min_row, keys..., per aggregate: state value, count]
+  Batch export_partials() const {
+    if (!seen_batch) fail(SQLRS_ERR_INTERNAL, "called `Option::unwrap()` on a `None` value (no input batch)");
+    if (opt.count_mode != SQLRS_COUNT_SQL_ACCUMULATE) fail(SQLRS_ERR_UNSUPPORTED, "partial/final COUNT needs SQLRS_COUNT_SQL_ACCUMULATE");
+    Batch out;
+    std::vector<std::shared_ptr<Column>> cols;
+    auto add = [&](const std::string& name, int dtype) {
+      auto c = std::make_shared<Column>();
+      c->dtype = dtype;
+      cols.push_back(c);
+      out.fields.push_back(Field{name, dtype, true});
+    };
+    add("hash", SQLRS_DT_INT64);
+    add("min_row", SQLRS_DT_INT64);
+    for (size_t k = 0; k < group_by.size(); k++) add("key" + std::to_string(k), key_dtypes[k]);
+    for (size_t k = 0; k < aggs.size(); k++) {
+      if (aggs[k].distinct) fail(SQLRS_ERR_UNSUPPORTED, "partial/final DISTINCT aggregates");
+      add("state" + std::to_string(k), agg_output_dtype(aggs[k]));
+      add("count" + std::to_string(k), SQLRS_DT_INT64);
+    }
+    auto i64 = [](int64_t v) {
+      Scalar s = Scalar::null_of(SQLRS_DT_INT64);
+      s.is_null = false;
+      s.i = v;
+      return s;
+    };
+    for (const Group& g : groups) {
+      size_t c = 0;
+      append_scalar(*cols[c++], i64((int64_t)g.hash));
+      append_scalar(*cols[c++], i64(g.first_row));
+      for (const Scalar& k : g.keys) append_scalar(*cols[c++], k);
+      for (const Accumulator& a : g.accs) {
+        append_scalar(*cols[c++], a.evaluate());
+        append_scalar(*cols[c++], i64(a.count));
+      }
+    }
+    out.n = (int64_t)groups.size();
+    for (auto& c : cols) {
+      c->normalize();
+      out.cols.push_back(c);
+    }
+    return out;
+  }
+  void clear_partials() {
+    groups.clear();
+    by_hash.clear();
+  }
+  void merge_partials(const Batch& p) {
+    const size_t K = group_by.size();
+    if (p.cols.size() != 2 + K + 2 * aggs.size()) fail(SQLRS_ERR_INVALID_ARG, "partials batch has the wrong number of columns");
+    if (!seen_batch) {
+      for (size_t k = 0; k < K; k++) key_dtypes.push_back(p.cols[2 + k]->dtype);
+      seen_batch = true;
+    }
+    std::vector<ColPtr> keys(p.cols.begin() + 2, p.cols.begin() + 2 + K);
+    for (int64_t r = 0; r < p.n; r++) {
+      const int64_t saved = rows_seen;
+      rows_seen = p.cols[1]->i[r];  // find_or_create stamps first_row = rows_seen + row
+      const size_t before = groups.size();
+      int gid = find_or_create((uint64_t)p.cols[0]->i[r], keys, 0 * r + r);
+      if (groups.size() != before) groups[gid].first_row = p.cols[1]->i[r];
+      rows_seen = saved;
+      Group& g = groups[gid];
+      if (p.cols[1]->i[r] < g.first_row) {
+        g.first_row = p.cols[1]->i[r];
+        if (opt.match_mode == SQLRS_MATCH_HASH_ONLY)
+          for (size_t k = 0; k < K; k++) g.keys[k] = Scalar::from_column(*keys[k], r);
+      }
+      for (size_t k = 0; k < aggs.size(); k++) {
+        Accumulator& a = g.accs[k];
+        Scalar v = Scalar::from_column(*p.cols[2 + K + 2 * k], r);
+        a.count += p.cols[2 + K + 2 * k + 1]->i[r];
+        if (a.func == SQLRS_AGG_SUM) a.result = Accumulator::sum_result(a.result, v);
+        else if (a.func == SQLRS_AGG_MIN) a.result = Accumulator::min_max_merge(a.result, v, true);
+        else if (a.func == SQLRS_AGG_MAX) a.result = Accumulator::min_max_merge(a.result, v, false);
+      }
+    }
   }
 
   Batch finish() {  // :124-149
@@ -329,7 +413,12 @@ struct HashAgg {
       cols.push_back(c);
       out.fields.push_back(Field{d.name, c->dtype, true});
     }
-    for (const Group& g : groups) {
+    // first-appearance order; already sorted unless partial groups were merged in
+    std::vector<const Group*> ordered;
+    for (const Group& g : groups) ordered.push_back(&g);
+    std::stable_sort(ordered.begin(), ordered.end(), [](const Group* a, const Group* b) { return a->first_row < b->first_row; });
+    for (const Group* gp : ordered) {
+      const Group& g = *gp;
       for (size_t k = 0; k < g.keys.size(); k++) append_scalar(*cols[k], g.keys[k]);
       for (size_t k = 0; k < g.accs.size(); k++) append_scalar(*cols[g.keys.size() + k], g.accs[k].evaluate());
     }

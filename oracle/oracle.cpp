@@ -114,6 +114,7 @@ struct sqlrs_plan {
   std::map<int, std::vector<Batch>> tables;
   std::deque<Batch> results;
   std::string description;
+  std::unique_ptr<HashAgg> partial;
 
   std::vector<Batch> run(int idx) {
     if (idx < 0 || idx >= (int)nodes.size()) fail(SQLRS_ERR_INVALID_ARG, "plan: child index out of range");
@@ -325,6 +326,44 @@ int sqlrs_oracle_plan_reset(sqlrs_plan* p) {
 }
 const char* sqlrs_oracle_plan_describe(sqlrs_plan* p) { return p->description.c_str(); }
 void sqlrs_oracle_plan_destroy(sqlrs_plan* p) { delete p; }
+int sqlrs_oracle_plan_execute_partial(sqlrs_plan* p, int64_t row_base) {
+  return guarded([&] {
+    PlanNode& n = p->nodes[p->root];
+    if (n.raw.kind != SQLRS_NODE_HASH_AGG) fail(SQLRS_ERR_UNSUPPORTED, "oracle: execute_partial needs a HashAgg root");
+    p->partial.reset(new HashAgg(n.aggs, n.group_by, n.group_names, p->opt));
+    p->partial->rows_seen = row_base;
+    for (const Batch& b : p->run(n.raw.child0)) p->partial->push(b);
+  });
+}
+int sqlrs_oracle_plan_export_partials(sqlrs_plan* p, ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] {
+    if (!p->partial) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
+    export_batch(p->partial->export_partials(), out, out_schema);
+  });
+}
+int sqlrs_oracle_plan_clear_partials(sqlrs_plan* p) {
+  return guarded([&] {
+    if (!p->partial) fail(SQLRS_ERR_INVALID_ARG, "clear_partials before execute_partial");
+    p->partial->clear_partials();
+  });
+}
+int sqlrs_oracle_plan_merge_partials(sqlrs_plan* p, ArrowArray* partials, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!p->partial) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
+    p->partial->merge_partials(consume_batch(partials, schema));
+  });
+}
+int sqlrs_oracle_plan_finish_partial(sqlrs_plan* p) {
+  return guarded([&] {
+    if (!p->partial) fail(SQLRS_ERR_INVALID_ARG, "finish before execute_partial");
+    p->results.push_back(p->partial->finish());
+    p->partial.reset();
+  });
+}
+double sqlrs_oracle_plan_scan_kernel_ms(sqlrs_plan*, int64_t* n_launches) {
+  if (n_launches) *n_launches = 0;
+  return 0.0;
+}
 
 // ------------------------------------------------------------------ synthetic tables
 int32_t sqlrs_oracle_tpch_num_columns(int32_t table) {

@@ -260,6 +260,45 @@ int sqlrs_plan_reset(sqlrs_plan* p) {
 }
 const char* sqlrs_plan_describe(sqlrs_plan* p) { return p ? p->impl.describe() : ""; }
 void sqlrs_plan_destroy(sqlrs_plan* p) { delete p; }
+int sqlrs_plan_execute_partial(sqlrs_plan* p, int64_t row_base) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.ctx().activate();
+    p->impl.execute_partial(row_base);
+  });
+}
+int sqlrs_plan_export_partials(sqlrs_plan* p, ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.ctx().activate();
+    p->impl.export_partials(out, out_schema);
+  });
+}
+int sqlrs_plan_clear_partials(sqlrs_plan* p) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.clear_partials();
+  });
+}
+int sqlrs_plan_merge_partials(sqlrs_plan* p, ArrowArray* partials, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.ctx().activate();
+    p->impl.merge_partials(import_batch_host(p->impl.ctx(), partials, schema));
+  });
+}
+int sqlrs_plan_finish_partial(sqlrs_plan* p) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.ctx().activate();
+    p->impl.finish_partial();
+  });
+}
+double sqlrs_plan_scan_kernel_ms(sqlrs_plan* p, int64_t* n_launches) {
+  if (!p) return 0.0;
+  if (n_launches) *n_launches = p->impl.scan_kernel_launches();
+  return p->impl.scan_kernel_ms();
+}
 
 // ------------------------------------------------------------------ synthetic tables
 int32_t sqlrs_tpch_num_columns(int32_t table) {

@@ -284,6 +284,17 @@ int RowProgram::emit_raw_bits(const Val& v) {
   return id;
 }
 
+int RowProgram::emit_mix_hash(const std::vector<int>& raw_ids, const std::vector<Val>& keys) {
+  int id = fresh();
+  body_ << "  unsigned long long " << vname(id) << " = 0x9e3779b97f4a7c15ULL;\n";
+  for (size_t k = 0; k < raw_ids.size(); k++) {
+    body_ << "  " << vname(id) << " = (" << vname(id) << " ^ " << vname(raw_ids[k]) << (keys[k].maybe_null ? " ^ (" + nname(keys[k].id) + " ? 0ULL : 0x5bd1e995ULL)" : std::string(""))
+          << ") * 0xff51afd7ed558ccdULL;\n";
+    body_ << "  " << vname(id) << " ^= " << vname(id) << " >> 32;\n";
+  }
+  return id;
+}
+
 // create_hashes, hash_utils.rs:161-220, RandomState::with_seeds(0,0,0,0): a single key column is
 // hash_one(v); several fold combine_hashes from 0; a NULL cell leaves the running hash untouched
 // (quirk K3); a Null-typed column hashes the constant 1 (hash_null, :18-29).

@@ -52,6 +52,8 @@ class RowProgram {
   int emit_row_hash(const std::vector<Val>& keys);
   // raw 64-bit pattern of a value (i32 sign-extended, bool 0/1, f64 bits) -> u64 value id
   int emit_raw_bits(const Val& v);
+  // cheap placement hash over raw key bits + null flags (only valid where key tuples are compared too)
+  int emit_mix_hash(const std::vector<int>& raw_ids, const std::vector<Val>& keys);
   Val cast(const Val& a, int to);  // arrow compute::cast (also used by SUM: sum.rs:54)
   int fresh() { return next_id_++; }
   std::ostringstream& body() { return body_; }

@@ -94,20 +94,81 @@ __device__ __forceinline__ int sq_table_upsert(const SqTable& t, u64 h, const u6
 
 // ------------------------------------------------------------------------------------------
 // shared-memory layout of sq_agg_small
-//   u64 acc[(W+1)][S][T]   word W = min row id
-//   u64 thash[S]; u64 tkeys[S][K]; u32 tknull[S]; u32 tstate[S]; u32 flags
+//   u64 acc[(W+1)][S][T]   private accumulators, word W = min row id
+//   CTA-shared slot table with SQ_TSLOTS = 4*S entries (load factor <= 1/4, so a lookup is almost
+//   always one probe): u64 thash[TS]; u64 tkeys[TS][K]; u32 tknull[TS]; u32 tstate[TS]; u32 tgroup[TS]
+//   u32 ngroups; u32 flags
 #define SQ_ACC_WORDS (SQ_NACC + 1)
-#define SQ_SMEM_ACC_BYTES ((size_t)SQ_ACC_WORDS * SQ_SLOTS * SQ_BLOCK * 8)
+#define SQ_TSLOTS (4 * SQ_SLOTS)
+
+struct SqSlotTable {
+  u64* thash;
+  u64* tkeys;
+  u32* tknull;
+  u32* tstate;  // 0 empty, 1 being written, 2 ready
+  u32* tgroup;  // dense group index < SQ_SLOTS (position of the private accumulators)
+  u32* ngroups;
+};
+
+// group index of the row's key in the CTA-shared table, inserting it if new; -1 = more than
+// SQ_SLOTS groups.  Claim (CAS 0->1), write identity + group index, publish (2): a reader that meets a
+// slot being written spins — independent thread scheduling lets the writer lane progress.
+__device__ __forceinline__ int sq_small_lookup(const SqSlotTable& t, const SqRow& o) {
+#if SQ_NKEYS == 0
+  return 0;
+#else
+  u32 s = sq_mix32(o.h) & (SQ_TSLOTS - 1);
+  for (int probes = 0; probes < SQ_TSLOTS;) {
+    const u32 st = *((volatile u32*)&t.tstate[s]);
+    if (st == 2u) {
+      if (*((volatile u64*)&t.thash[s]) == o.h) {
+#if SQ_MATCH_KEYS
+        bool same = *((volatile u32*)&t.tknull[s]) == o.knull;
+#pragma unroll
+        for (int k = 0; k < SQ_NKEYS; k++) same = same && (*((volatile u64*)&t.tkeys[s * SQ_NKEYS + k]) == o.kb[k]);
+        if (same) return (int)*((volatile u32*)&t.tgroup[s]);
+#else
+        return (int)*((volatile u32*)&t.tgroup[s]);
+#endif
+      }
+      s = (s + 1) & (SQ_TSLOTS - 1);
+      probes++;
+      continue;
+    }
+    if (st == 0u && atomicCAS(&t.tstate[s], 0u, 1u) == 0u) {
+      const u32 g = atomicAdd(t.ngroups, 1u);
+      if (g >= SQ_SLOTS) {       // too many groups for the private accumulators: leave the slot unusable
+        t.thash[s] = o.h;
+        t.tgroup[s] = 0xffffffffu;
+      } else {
+        t.thash[s] = o.h;
+#pragma unroll
+        for (int k = 0; k < SQ_NKEYS; k++) t.tkeys[s * SQ_NKEYS + k] = o.kb[k];
+        t.tknull[s] = o.knull;
+        t.tgroup[s] = g;
+      }
+      __threadfence_block();
+      atomicExch(&t.tstate[s], 2u);
+      return g >= SQ_SLOTS ? -1 : (int)g;
+    }
+    // st == 1 (or lost the claim): look again
+  }
+  return -1;
+#endif
+}
 
 extern "C" __global__ void __launch_bounds__(SQ_BLOCK) sq_agg_small(SqIn in, i64 n, i64 row_base, SqPartial part,
                                                                      u32* __restrict__ status, u32* __restrict__ err) {
   extern __shared__ __align__(16) unsigned char sq_smem[];
   u64* acc = (u64*)sq_smem;
-  u64* thash = acc + (size_t)SQ_ACC_WORDS * SQ_SLOTS * SQ_BLOCK;
-  u64* tkeys = thash + SQ_SLOTS;
-  u32* tknull = (u32*)(tkeys + SQ_SLOTS * (SQ_NKEYS > 0 ? SQ_NKEYS : 1));
-  u32* tstate = tknull + SQ_SLOTS;
-  u32* flags = tstate + SQ_SLOTS;
+  SqSlotTable tab;
+  tab.thash = acc + (size_t)SQ_ACC_WORDS * SQ_SLOTS * SQ_BLOCK;
+  tab.tkeys = tab.thash + SQ_TSLOTS;
+  tab.tknull = (u32*)(tab.tkeys + SQ_TSLOTS * (SQ_NKEYS > 0 ? SQ_NKEYS : 1));
+  tab.tstate = tab.tknull + SQ_TSLOTS;
+  tab.tgroup = tab.tstate + SQ_TSLOTS;
+  tab.ngroups = tab.tgroup + SQ_TSLOTS;
+  u32* flags = tab.ngroups + 1;
   const int tid = threadIdx.x;
 
   if ((*((volatile u32*)status) & SQ_STATUS_OVERFLOW) != 0u) return;  // sticky: the global kernel owns this operator now
@@ -118,13 +179,18 @@ extern "C" __global__ void __launch_bounds__(SQ_BLOCK) sq_agg_small(SqIn in, i64
 #pragma unroll
     for (int s = 0; s < SQ_SLOTS; s++) acc[((size_t)w * SQ_SLOTS + s) * SQ_BLOCK + tid] = ident;
   }
-  if (tid < SQ_SLOTS) tstate[tid] = 0u;
-  if (tid == 0) *flags = 0u;
+  for (int s = tid; s < SQ_TSLOTS; s += SQ_BLOCK) tab.tstate[s] = 0u;
+  if (tid == 0) {
+    *tab.ngroups = 0u;
+    *flags = 0u;
+  }
   __syncthreads();
 
   bool any_err = false;
+  bool overflow = false;
   const i64 tile = (i64)SQ_BLOCK * SQ_UNROLL;
   for (i64 base = (i64)blockIdx.x * tile; base < n; base += (i64)gridDim.x * tile) {
+    // all loads of the tile are issued before the first use: SQ_UNROLL x columns requests in flight per thread
     SqRow o[SQ_UNROLL];
     bool live[SQ_UNROLL];
 #pragma unroll
@@ -138,69 +204,34 @@ extern "C" __global__ void __launch_bounds__(SQ_BLOCK) sq_agg_small(SqIn in, i64
     }
 #pragma unroll
     for (int u = 0; u < SQ_UNROLL; u++) {
-      if (!live[u]) continue;
-      int slot = 0;
-#if SQ_NKEYS > 0
-      // CTA-shared slot table: claim (CAS 0->1), write identity, publish (2); readers of a slot
-      // being written spin — independent thread scheduling guarantees the writer progresses
-      slot = -1;
-      u32 s = sq_mix32(o[u].h) & (SQ_SLOTS - 1);
-      for (int probes = 0; probes < SQ_SLOTS;) {
-        const u32 st = *((volatile u32*)&tstate[s]);
-        if (st == 0u) {
-          if (atomicCAS(&tstate[s], 0u, 1u) == 0u) {
-            thash[s] = o[u].h;
-#pragma unroll
-            for (int k = 0; k < SQ_NKEYS; k++) tkeys[s * SQ_NKEYS + k] = o[u].kb[k];
-            tknull[s] = o[u].knull;
-            __threadfence_block();
-            atomicExch(&tstate[s], 2u);
-            slot = (int)s;
-            break;
-          }
-          continue;
-        }
-        if (st == 1u) continue;
-        __threadfence_block();
-        if (*((volatile u64*)&thash[s]) == o[u].h) {
-#if SQ_MATCH_KEYS
-          u64 other[SQ_NKEYS];
-#pragma unroll
-          for (int k = 0; k < SQ_NKEYS; k++) other[k] = *((volatile u64*)&tkeys[s * SQ_NKEYS + k]);
-          if (sq_keys_equal(other, *((volatile u32*)&tknull[s]), o[u].kb, o[u].knull)) {
-            slot = (int)s;
-            break;
-          }
-#else
-          slot = (int)s;
-          break;
-#endif
-        }
-        s = (s + 1) & (SQ_SLOTS - 1);
-        probes++;
+      int g = -1;
+      if (live[u]) {
+        g = sq_small_lookup(tab, o[u]);
+        overflow |= g < 0;
       }
-      if (slot < 0) {  // more than SQ_SLOTS groups: the host reruns this batch on the HBM table
-        *((volatile u32*)flags) = 1u;
-        continue;
+      // the lookup is the only divergent code: reconverge before the (uniform, predicated) accumulate —
+      // without this the warp stays split per group and every later load is replayed per fragment
+      __syncwarp();
+      if (g >= 0) {
+        u64* a = acc + (size_t)g * SQ_BLOCK + tid;
+        sq_acc_update(a, SQ_SLOTS * SQ_BLOCK, o[u]);
+        u64* mr = a + (size_t)SQ_NACC * SQ_SLOTS * SQ_BLOCK;
+        const u64 gr = (u64)(row_base + base + (i64)u * SQ_BLOCK + tid);
+        if (gr < *mr) *mr = gr;
       }
-#endif
-      u64* a = acc + (size_t)slot * SQ_BLOCK + tid;
-      sq_acc_update(a, SQ_SLOTS * SQ_BLOCK, o[u]);
-      u64* mr = a + (size_t)SQ_NACC * SQ_SLOTS * SQ_BLOCK;
-      const u64 gr = (u64)(row_base + base + (i64)u * SQ_BLOCK + tid);
-      if (gr < *mr) *mr = gr;
+      __syncwarp();
     }
   }
   if (any_err) atomicOr(err, 1u);
+  if (overflow) *((volatile u32*)flags) = 1u;
   __syncthreads();
-  if (*((volatile u32*)flags) != 0u) {
+  if (*((volatile u32*)flags) != 0u) {  // the host reruns this batch on the HBM table
     if (tid == 0) atomicOr(status, SQ_STATUS_OVERFLOW);
-    // still publish an empty partial so that the merge sees a defined state
     if (tid < SQ_SLOTS) part.state[(size_t)blockIdx.x * SQ_SLOTS + tid] = 0u;
     return;
   }
 
-  // fold the T private copies: one warp per (word, slot), lanes stride over the threads
+  // fold the T private copies: one warp per (word, group), lanes stride over the threads
   const int lane = tid & 31, wid = tid >> 5;
   for (int item = wid; item < SQ_ACC_WORDS * SQ_SLOTS; item += SQ_BLOCK / 32) {
     const int w = item / SQ_SLOTS, s = item % SQ_SLOTS;
@@ -218,20 +249,29 @@ extern "C" __global__ void __launch_bounds__(SQ_BLOCK) sq_agg_small(SqIn in, i64
       else part.acc[e * SQ_NACC + w] = x;
     }
   }
-  if (tid < SQ_SLOTS) {
-    const size_t e = (size_t)blockIdx.x * SQ_SLOTS + tid;
+  // identity of each dense group: scatter from the slot table
+  if (tid < SQ_SLOTS) part.state[(size_t)blockIdx.x * SQ_SLOTS + tid] = 0u;
+  __syncthreads();
 #if SQ_NKEYS > 0
-    part.state[e] = tstate[tid];
-    part.hash[e] = thash[tid];
-    part.knull[e] = tknull[tid];
+  for (int s = tid; s < SQ_TSLOTS; s += SQ_BLOCK) {
+    if (tab.tstate[s] != 2u) continue;
+    const u32 g = tab.tgroup[s];
+    if (g >= SQ_SLOTS) continue;
+    const size_t e = (size_t)blockIdx.x * SQ_SLOTS + g;
+    part.state[e] = 2u;
+    part.hash[e] = tab.thash[s];
+    part.knull[e] = tab.tknull[s];
 #pragma unroll
-    for (int k = 0; k < SQ_NKEYS; k++) part.keys[e * SQ_NKEYS + k] = tkeys[tid * SQ_NKEYS + k];
+    for (int k = 0; k < SQ_NKEYS; k++) part.keys[e * SQ_NKEYS + k] = tab.tkeys[s * SQ_NKEYS + k];
+  }
 #else
-    part.state[e] = tid == 0 ? 2u : 0u;
+  if (tid == 0) {
+    const size_t e = (size_t)blockIdx.x * SQ_SLOTS;
+    part.state[e] = 2u;
     part.hash[e] = 0ULL;
     part.knull[e] = 0u;
-#endif
   }
+#endif
 }
 
 // folds the CTA partials of one batch into the operator's table; one thread per (cta, slot)
@@ -262,24 +302,32 @@ extern "C" __global__ void __launch_bounds__(256) sq_agg_global(SqIn in, i64 n, 
                                                                  u32* __restrict__ status, u32* __restrict__ err) {
   bool any_err = false;
   const i64 stride = (i64)gridDim.x * blockDim.x;
-  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+  // warp-uniform trip count (the tail is predicated) so that __syncwarp can reconverge the warp
+  // after the divergent find-or-insert
+  for (i64 base = (i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+    const i64 r = base + (threadIdx.x & 31);
+    const bool inb = r < n;
     SqRow o;
     bool e0 = false, e1 = false;
-    sq_row(in, r, o, e0, e1);
-    any_err |= e0 || (o.pass && e1);
-    if (!o.pass) continue;
-    const int slot = sq_table_upsert(table, o.h, o.kb, o.knull);
-    if (slot < 0) {
-      atomicOr(status, SQ_STATUS_FULL);
-      continue;
+    sq_row(in, inb ? r : n - 1, o, e0, e1);
+    const bool live = inb && o.pass;
+    any_err |= (inb && e0) || (live && e1);
+    int slot = -1;
+    if (live) {
+      slot = sq_table_upsert(table, o.h, o.kb, o.knull);
+      if (slot < 0) atomicOr(status, SQ_STATUS_FULL);
     }
-    atomicMin(&table.min_row[slot], (u64)(row_base + r));
-    u64 local[SQ_NACC > 0 ? SQ_NACC : 1];
+    __syncwarp();
+    if (slot >= 0) {
+      atomicMin(&table.min_row[slot], (u64)(row_base + r));
+      u64 local[SQ_NACC > 0 ? SQ_NACC : 1];
 #pragma unroll
-    for (int w = 0; w < SQ_NACC; w++) local[w] = sq_acc_identity(w);
-    sq_acc_update(local, 1, o);
+      for (int w = 0; w < SQ_NACC; w++) local[w] = sq_acc_identity(w);
+      sq_acc_update(local, 1, o);
 #pragma unroll
-    for (int w = 0; w < SQ_NACC; w++) sq_acc_merge_global(&table.acc[(size_t)w * table.capacity + slot], w, local[w], batch_no);
+      for (int w = 0; w < SQ_NACC; w++) sq_acc_merge_global(&table.acc[(size_t)w * table.capacity + slot], w, local[w], batch_no);
+    }
+    __syncwarp();
   }
   if (any_err) atomicOr(err, 1u);
 }

@@ -253,7 +253,84 @@ __global__ void __launch_bounds__(kBlock) k_table_rehash(TableView from, TableVi
   }
 }
 
+// partial -> final merge (multi-GPU group-by): every partial row is a distinct group of
+// its producer; find-or-insert it here and fold its accumulator words in with the word's operator.
+// ops[w]: 0 add u64, 1 add f64, 2 min i64, 3 max i64.
+__global__ void __launch_bounds__(kBlock) k_table_merge(TableView t, int n_keys, int n_acc, const int* __restrict__ ops, int match_keys,
+                                                         const uint64_t* __restrict__ hash, const uint64_t* __restrict__ min_row,
+                                                         const uint32_t* __restrict__ knull, const uint64_t* __restrict__ keys,
+                                                         const uint64_t* __restrict__ acc, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint32_t mask = t.capacity - 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t h = hash[i];
+    const uint32_t kn = knull[i];
+    uint32_t s = mix32(h) & mask;
+    int slot = -1;
+    for (uint32_t probes = 0; probes <= mask;) {
+      const uint32_t st = *((volatile uint32_t*)&t.state[s]);
+      if (st == 0u) {
+        if (atomicCAS(&t.state[s], 0u, 1u) == 0u) {
+          t.hash[s] = h;
+          for (int k = 0; k < n_keys; k++) t.keys[(size_t)k * t.capacity + s] = keys[(size_t)k * n + i];
+          t.knull[s] = kn;
+          __threadfence();
+          atomicExch(&t.state[s], 2u);
+          atomicAdd(&t.counters[0], 1u);
+          slot = (int)s;
+          break;
+        }
+        continue;
+      }
+      if (st == 1u) continue;
+      __threadfence();
+      if (*((volatile uint64_t*)&t.hash[s]) == h) {
+        bool same = true;
+        if (match_keys) {
+          same = *((volatile uint32_t*)&t.knull[s]) == kn;
+          for (int k = 0; same && k < n_keys; k++) same = *((volatile uint64_t*)&t.keys[(size_t)k * t.capacity + s]) == keys[(size_t)k * n + i];
+        }
+        if (same) {
+          slot = (int)s;
+          break;
+        }
+      }
+      s = (s + 1) & mask;
+      probes++;
+    }
+    if (slot < 0) {
+      atomicOr(&t.counters[2], 2u);
+      continue;
+    }
+    // first-appearance order: the smaller global row id wins; with hash-only identity its keys win too
+    const unsigned long long old = atomicMin((unsigned long long*)&t.min_row[slot], (unsigned long long)min_row[i]);
+    if (!match_keys && min_row[i] < old) {
+      for (int k = 0; k < n_keys; k++) t.keys[(size_t)k * t.capacity + slot] = keys[(size_t)k * n + i];
+      t.knull[slot] = kn;
+    }
+    for (int w = 0; w < n_acc; w++) {
+      const uint64_t x = acc[(size_t)w * n + i];
+      uint64_t* p = &t.acc[(size_t)w * t.capacity + slot];
+      switch (ops[w]) {
+        case 0: atomicAdd((unsigned long long*)p, (unsigned long long)x); break;
+        case 1: atomicAdd((double*)p, __longlong_as_double((long long)x)); break;
+        case 2: atomicMin((long long*)p, (long long)x); break;
+        case 3: atomicMax((long long*)p, (long long)x); break;
+      }
+    }
+  }
+}
+
 }  // namespace
+
+void launch_table_merge(const TableView& t, int n_keys, int n_acc, const int* ops, int match_keys, const uint64_t* hash,
+                        const uint64_t* min_row, const uint32_t* knull, const uint64_t* keys, const uint64_t* acc, int64_t n,
+                        cudaStream_t stream) {
+  if (n <= 0) return;
+  k_table_merge<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, ops, match_keys, hash, min_row, knull, keys, acc, n);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
 
 void launch_tpch_generate(int table, int col, int64_t row_begin, int64_t n, int64_t n_customer, int flags_mode, uint64_t* dst,
                           cudaStream_t stream) {

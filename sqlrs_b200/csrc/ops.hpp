@@ -97,8 +97,10 @@ class AggOp {
   std::string debug_source(const std::vector<ColInfo>& cols);  // generated CUDA for batches of that schema (no GPU needed)
   // partial/final split for multi-GPU execution: the raw group table as a batch
   // [hash, min_row, knull, key bits..., accumulator words...] and its merge into another operator
-  DBatch export_partials();
+  void export_partials(ArrowArray* out, ArrowSchema* out_schema);
+  void clear_partials();
   void merge_partials(const DBatch& partials);
+  void set_row_base(int64_t first_global_row) { rows_seen_ = first_global_row; }
 
  private:
   struct Compiled;
@@ -123,6 +125,12 @@ class AggOp {
   bool use_global_ = false;
   std::vector<int> key_dtypes_;
   std::string last_path_;
+  double scan_kernel_ms_ = 0;      // SQLRS_FLAG_TIMING: device time of the scan kernels (CUDA events on ctx_.stream)
+  int64_t scan_kernel_launches_ = 0;
+
+ public:
+  double scan_kernel_ms() const { return scan_kernel_ms_; }
+  int64_t scan_kernel_launches() const { return scan_kernel_launches_; }
 };
 
 }  // namespace sq

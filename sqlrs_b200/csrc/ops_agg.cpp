@@ -72,6 +72,33 @@ struct SqInBlob {
   void* ptr() { return blob.data(); }
 };
 
+// CUDA events around the dominant scan kernel on the operator's own stream (SQLRS_FLAG_TIMING)
+struct ScanTimer {
+  cudaStream_t stream;
+  bool enabled;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ScanTimer(cudaStream_t s, bool on) : stream(s), enabled(on) {
+    if (!enabled) return;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, stream);
+  }
+  void stop() {
+    if (enabled) cudaEventRecord(e1, stream);
+  }
+  double elapsed_ms() {  // call after the stream has been synchronised
+    if (!enabled) return 0.0;
+    float ms = 0.f;
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    return ms;
+  }
+  ~ScanTimer() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  }
+};
+
 }  // namespace
 
 struct HostGroups {
@@ -246,16 +273,18 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
   }
   const int K = (int)keys.size(), W = (int)comp->words.size();
   if (W > 48) fail(SQLRS_ERR_UNSUPPORTED, "too many aggregate accumulators for one operator (max 48 words)");
-  const int hash_id = prog.emit_row_hash(keys);
   std::vector<int> raw_ids;
   for (const Val& k : keys) raw_ids.push_back(prog.emit_raw_bits(k));
+  // group identity: the reference's row hash when it IS the identity (hash-only, quirk K2); with key
+  // comparison any hash places the group, so a cheaper multiply-xorshift mix of the key bits is used
+  const int hash_id = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY ? prog.emit_mix_hash(raw_ids, keys) : prog.emit_row_hash(keys);
 
   // launch shape of sq_agg_small: S slots, T threads, private accumulators in shared memory
   comp->slots = K == 0 ? 1 : 8;
   comp->unroll = 4;
   comp->block = 128;
   auto smem_for = [&](int T) {
-    return (size_t)(W + 1) * comp->slots * T * 8 + (size_t)comp->slots * (8 + 8 * std::max(K, 1) + 4 + 4) + 16;
+    return (size_t)(W + 1) * comp->slots * T * 8 + (size_t)4 * comp->slots * (8 + 8 * std::max(K, 1) + 4 + 4 + 4) + 16;
   };
   if (smem_for(256) <= 100 * 1024) comp->block = 256;
   while (comp->block > 32 && smem_for(comp->block) > 200 * 1024) comp->block /= 2;
@@ -422,10 +451,14 @@ void AggOp::push(const DBatch& batch) {
     TableView tv = table_->view();
     int n_entries = (int)entries;
     void* args_small[] = {in.ptr(), &n_arg, &rb, &part, &status, &errp};
+    ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
     jit_launch(c.small, (unsigned)grid, (unsigned)c.block, c.small_smem, ctx_.stream, args_small);
+    timer.stop();
     void* args_merge[] = {&part, &n_entries, &tv, &bn, &status};
     jit_launch(c.merge, (unsigned)div_up(n_entries, 128), 128, 0, ctx_.stream, args_merge);
     read_counters();
+    scan_kernel_ms_ += timer.elapsed_ms();
+    scan_kernel_launches_ += timer.enabled ? 1 : 0;
     if (host_counters[2] & 1u) {
       use_global_ = true;  // more groups than the shared-memory path holds: this and later batches use the HBM table
       uint32_t zero = 0;
@@ -456,7 +489,14 @@ void AggOp::push(const DBatch& batch) {
       void* args[] = {in.ptr(), &n_arg, &rb, &tv, &bn, &status, &errp};
       const int sms = device_sm_count(ctx_.device);
       unsigned grid = (unsigned)std::min<int64_t>(div_up(len, 256), (int64_t)sms * 8);
+      ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
       jit_launch(c.global, grid, 256, 0, ctx_.stream, args);
+      timer.stop();
+      if (timer.enabled) {
+        SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+        scan_kernel_ms_ += timer.elapsed_ms();
+        scan_kernel_launches_++;
+      }
     }
     read_counters();
     last_path_ = "sq_agg_global (open-addressed table in HBM, capacity " + std::to_string(table_->capacity) + ")";
@@ -563,7 +603,14 @@ void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
         nvalid = 0;
       }
       if (p.func == SQLRS_AGG_COUNT) {
-        col.i.push_back((int64_t)(c.words[p.value_word].op == W_COUNT_EPOCH ? (word & kEpochMask) : word));
+        uint64_t cnt = word;
+        if (c.words[p.value_word].op == W_COUNT_EPOCH) {
+          cnt = word & kEpochMask;
+          // SimpleAgg updates its single accumulator set with EVERY batch, empty ones included
+          // (simple_agg.rs:34-54), so under the overwrite quirk only the last batch counts
+          if (simple_ && (word >> kEpochShift) != (uint64_t)batches_seen_) cnt = 0;
+        }
+        col.i.push_back((int64_t)cnt);
         continue;
       }
       const bool is_null = nvalid == 0;
@@ -589,7 +636,90 @@ void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
 DBatch AggOp::finish_device() { fail(SQLRS_ERR_UNSUPPORTED, "aggregate results are produced on the host"); }
 
 // ------------------------------------------------------------------ partial / final (multi-GPU)
-DBatch AggOp::export_partials() { fail(SQLRS_ERR_UNSUPPORTED, "export_partials: not built yet"); }
-void AggOp::merge_partials(const DBatch&) { fail(SQLRS_ERR_UNSUPPORTED, "merge_partials: not built yet"); }
+// The un-finalised group table as a host batch: [hash i64, min_row i64, knull i32, key bits i64 x K,
+// accumulator words i64 x W].  Column 0 is the group identity the exchange radix-partitions on.
+void AggOp::export_partials(ArrowArray* out, ArrowSchema* out_schema) {
+  if (opt_.count_mode == SQLRS_COUNT_REFERENCE_OVERWRITE)
+    for (const AggSpec& a : aggs_)
+      if (a.func == SQLRS_AGG_COUNT)
+        fail(SQLRS_ERR_UNSUPPORTED, "partial/final COUNT needs SQLRS_COUNT_SQL_ACCUMULATE (the overwrite quirk K1 is defined on one batch stream)");
+  std::vector<Field> fields;
+  HostGroups g;
+  build_output(&fields, &g);
+  const Compiled& c = *cache_.begin()->second;
+  const int K = (int)c.key_dtypes.size(), W = (int)c.words.size();
+  const uint32_t n = g.n;
+  std::vector<Field> pf;
+  std::vector<HostCol> cols;
+  auto add_i64 = [&](const std::string& name, const uint64_t* src) {
+    HostCol col;
+    col.dtype = SQLRS_DT_INT64;
+    col.i.assign((const int64_t*)src, (const int64_t*)src + n);
+    cols.push_back(std::move(col));
+    pf.push_back(Field{name, SQLRS_DT_INT64, false});
+  };
+  add_i64("hash", g.hash.data());
+  add_i64("min_row", g.min_row.data());
+  {
+    HostCol col;
+    col.dtype = SQLRS_DT_INT32;
+    for (uint32_t i = 0; i < n; i++) col.i.push_back((int64_t)g.knull[i]);
+    cols.push_back(std::move(col));
+    pf.push_back(Field{"knull", SQLRS_DT_INT32, false});
+  }
+  for (int k = 0; k < K; k++) add_i64("key" + std::to_string(k), g.keys.data() + (size_t)k * n);
+  for (int w = 0; w < W; w++) add_i64("acc" + std::to_string(w), g.acc.data() + (size_t)w * n);
+  export_host_columns(pf, cols, n, out, out_schema);
+}
+
+void AggOp::clear_partials() {
+  ctx_.activate();
+  table_.reset();
+  use_global_ = false;
+}
+
+// folds a batch of partial groups (layout of export_partials, device resident) into the table
+void AggOp::merge_partials(const DBatch& p) {
+  ctx_.activate();
+  if (cache_.empty()) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before any batch was aggregated (accumulator layout unknown)");
+  const Compiled& c = *cache_.begin()->second;
+  const int K = (int)c.key_dtypes.size(), W = (int)c.words.size();
+  if ((int)p.cols.size() != 3 + K + W) fail(SQLRS_ERR_INVALID_ARG, "partials batch has the wrong number of columns");
+  for (size_t k = 0; k < p.cols.size(); k++)
+    if (p.cols[k].dtype != (k == 2 ? SQLRS_DT_INT32 : SQLRS_DT_INT64) || p.cols[k].valid)
+      fail(SQLRS_ERR_INVALID_ARG, "partials batch has the wrong column types");
+  const int64_t n = p.n;
+  seen_batch_ = true;
+  if (n == 0) return;
+  uint32_t groups_now = 0;
+  if (table_) {
+    SQ_CUDA(cudaMemcpyAsync(&groups_now, table_->counters->p, 4, cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+  }
+  ensure_table((uint32_t)std::min<uint64_t>(2ULL * ((uint64_t)groups_now + (uint64_t)n) + 1024, 1ULL << 31));
+  std::vector<int> ops;
+  for (const WordPlan& w : c.words) {
+    switch (w.op) {
+      case W_ADD_U64: ops.push_back(0); break;
+      case W_ADD_F64: ops.push_back(1); break;
+      case W_MIN_I64: ops.push_back(2); break;
+      case W_MAX_I64: ops.push_back(3); break;
+      default: fail(SQLRS_ERR_UNSUPPORTED, "partial/final COUNT needs SQLRS_COUNT_SQL_ACCUMULATE");
+    }
+  }
+  BufPtr d_ops = dev_alloc(ctx_, std::max<size_t>(ops.size(), 1) * 4);
+  if (!ops.empty()) SQ_CUDA(cudaMemcpyAsync(d_ops->p, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice, ctx_.stream));
+  // gather the K key columns / W word columns into [K][n] / [W][n] blocks
+  BufPtr d_keys = dev_alloc(ctx_, (size_t)std::max(K, 1) * n * 8), d_acc = dev_alloc(ctx_, (size_t)std::max(W, 1) * n * 8);
+  for (int k = 0; k < K; k++)
+    SQ_CUDA(cudaMemcpyAsync((uint64_t*)d_keys->p + (size_t)k * n, p.cols[3 + k].data, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx_.stream));
+  for (int w = 0; w < W; w++)
+    SQ_CUDA(cudaMemcpyAsync((uint64_t*)d_acc->p + (size_t)w * n, p.cols[3 + K + w].data, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx_.stream));
+  launch_table_merge(table_->view(), K, W, (const int*)d_ops->p, opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY ? 1 : 0,
+                     (const uint64_t*)p.cols[0].data, (const uint64_t*)p.cols[1].data, (const uint32_t*)p.cols[2].data,
+                     (const uint64_t*)d_keys->p, (const uint64_t*)d_acc->p, n, ctx_.stream);
+  SQ_CUDA(cudaStreamSynchronize(ctx_.stream));  // `ops` (pageable) and the staging buffers stay alive until here
+  SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 1, 0, 4, ctx_.stream));
+}
 
 }  // namespace sq

@@ -58,6 +58,7 @@ void Plan::reset() {
   }
   results_.clear();
   tables_.clear();
+  partial_op_.reset();
 }
 
 // aggregate at `idx` -> host Arrow.  A Filter directly below is fused into the aggregate's row
@@ -79,6 +80,51 @@ void Plan::run_agg_to_host(int idx, Result* res) {
   op.finish_host(&res->arr, &res->sch);
   res->on_host = true;
   description_ += op.describe() + "; ";
+  scan_kernel_ms_ = op.scan_kernel_ms();
+  scan_kernel_launches_ = op.scan_kernel_launches();
+}
+
+// ---- partial / final split for multi-GPU group-by: run everything below the root
+// aggregate on this rank's shard and keep the group table un-finalised
+void Plan::execute_partial(int64_t row_base) {
+  description_.clear();
+  ctx_.reap();
+  Node& n = nodes_[root_];
+  if (n.kind != SQLRS_NODE_SIMPLE_AGG && n.kind != SQLRS_NODE_HASH_AGG)
+    fail(SQLRS_ERR_INVALID_ARG, "execute_partial: the plan root must be an aggregate");
+  const bool simple = n.kind == SQLRS_NODE_SIMPLE_AGG;
+  int child = n.child0;
+  ExprCopy fused;
+  if (!(opt_.flags & SQLRS_FLAG_NO_FUSION) && nodes_[child].kind == SQLRS_NODE_FILTER) {
+    fused = nodes_[child].predicate;
+    child = nodes_[child].child0;
+    description_ += "[Filter+" + std::string(simple ? "SimpleAgg" : "HashAgg") + " fused, partial] ";
+  }
+  partial_op_ = std::make_unique<AggOp>(n.aggs, n.group_by, n.group_names, simple, fused, opt_);
+  partial_op_->set_row_base(row_base);
+  for (const DBatch& b : run(child)) partial_op_->push(b);
+  description_ += partial_op_->describe() + "; ";
+  scan_kernel_ms_ = partial_op_->scan_kernel_ms();
+  scan_kernel_launches_ = partial_op_->scan_kernel_launches();
+}
+void Plan::export_partials(ArrowArray* out, ArrowSchema* out_schema) {
+  if (!partial_op_) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
+  partial_op_->export_partials(out, out_schema);
+}
+void Plan::clear_partials() {
+  if (!partial_op_) fail(SQLRS_ERR_INVALID_ARG, "clear_partials before execute_partial");
+  partial_op_->clear_partials();
+}
+void Plan::merge_partials(const DBatch& partials) {
+  if (!partial_op_) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
+  partial_op_->merge_partials(partials);
+}
+void Plan::finish_partial() {
+  if (!partial_op_) fail(SQLRS_ERR_INVALID_ARG, "finish before execute_partial");
+  results_.emplace_back();
+  partial_op_->finish_host(&results_.back().arr, &results_.back().sch);
+  results_.back().on_host = true;
+  partial_op_.reset();
 }
 
 std::vector<DBatch> Plan::run(int idx) {

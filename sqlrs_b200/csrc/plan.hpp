@@ -19,7 +19,14 @@ class Plan {
   void execute();
   bool next(ArrowArray* out, ArrowSchema* out_schema);
   void reset();
+  void execute_partial(int64_t row_base);
+  void export_partials(ArrowArray* out, ArrowSchema* out_schema);
+  void clear_partials();
+  void merge_partials(const DBatch& partials);
+  void finish_partial();
   const char* describe() const { return description_.c_str(); }
+  double scan_kernel_ms() const { return scan_kernel_ms_; }
+  int64_t scan_kernel_launches() const { return scan_kernel_launches_; }
   Ctx& ctx() { return ctx_; }
 
  private:
@@ -48,7 +55,10 @@ class Plan {
   int root_ = 0;
   std::map<int, std::vector<DBatch>> tables_;
   std::deque<Result> results_;
+  std::unique_ptr<AggOp> partial_op_;  // execute_partial .. finish_partial
   std::string description_;
+  double scan_kernel_ms_ = 0;
+  int64_t scan_kernel_launches_ = 0;
 };
 
 }  // namespace sq

@@ -1,0 +1,143 @@
+"""Multi-GPU execution of a plan whose root is an aggregate.
+
+One process per GPU (torch.distributed; NCCL over NVLink on the GPU box, gloo in the CPU tests).
+Scan, filter and the partial aggregation stay GPU-local; the only exchange is the group-by's:
+
+  1. every rank aggregates its contiguous row shard           sqlrs_plan_execute_partial
+  2. partial groups are radix-partitioned by their identity hash (owner = hash mod world) and
+     exchanged all-to-all; the owner folds them               sqlrs_plan_merge_partials
+  3. the (now disjoint) owner-merged groups are gathered on rank 0, which finalises them in the
+     reference's first-appearance order (minimum global row id) sqlrs_plan_finish_partial
+
+The reference has no distributed execution; results equal the single-process ones (integers
+bit-exact, float sums up to summation order).  This module contains no compute — partial groups
+cross the C ABI as opaque Arrow batches whose column 0 is the partitioning hash.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+import pyarrow as pa
+
+from . import ffi
+
+
+def _to_bytes(batch: pa.RecordBatch) -> bytes:
+    sink = pa.BufferOutputStream()
+    with pa.ipc.new_stream(sink, batch.schema) as w:
+        w.write_batch(batch)
+    return sink.getvalue().to_pybytes()
+
+
+def _from_bytes(data: bytes) -> pa.RecordBatch:
+    with pa.ipc.open_stream(pa.py_buffer(data)) as r:
+        batches = [b for b in r]
+    if len(batches) == 1:
+        return batches[0]
+    return pa.Table.from_batches(batches).combine_chunks().to_batches()[0]
+
+
+class TorchGroup:
+    """Byte-level all-to-all / gather on top of torch.distributed (works with nccl and gloo)."""
+
+    def __init__(self, dist, device):
+        import torch
+
+        self.torch, self.dist, self.device = torch, dist, device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.native_a2a = dist.get_backend() == "nccl"
+
+    def _tensor(self, data: bytes):
+        t = self.torch.frombuffer(bytearray(data), dtype=self.torch.uint8) if data else self.torch.empty(0, dtype=self.torch.uint8)
+        return t.to(self.device)
+
+    def all_to_all_bytes(self, payloads: List[bytes]) -> List[bytes]:
+        torch, dist, W = self.torch, self.dist, self.world
+        send_sizes = torch.tensor([len(p) for p in payloads], dtype=torch.int64, device=self.device)
+        if self.native_a2a:
+            recv_sizes = torch.empty(W, dtype=torch.int64, device=self.device)
+            dist.all_to_all_single(recv_sizes, send_sizes)
+            rs = recv_sizes.tolist()
+            send = self._tensor(b"".join(payloads))
+            recv = torch.empty(sum(rs), dtype=torch.uint8, device=self.device)
+            dist.all_to_all_single(recv, send, output_split_sizes=rs, input_split_sizes=[len(p) for p in payloads])
+            data = recv.cpu().numpy().tobytes()
+            out, off = [], 0
+            for s in rs:
+                out.append(data[off:off + s])
+                off += s
+            return out
+        # gloo has no all_to_all: all-gather the size matrix and the (padded) send buffers, slice locally
+        sizes = [torch.empty(W, dtype=torch.int64, device=self.device) for _ in range(W)]
+        dist.all_gather(sizes, send_sizes)
+        matrix = [s.tolist() for s in sizes]  # matrix[src][dst]
+        max_total = max(sum(row) for row in matrix)
+        send = torch.zeros(max(max_total, 1), dtype=torch.uint8, device=self.device)
+        joined = b"".join(payloads)
+        if joined:
+            send[:len(joined)] = self._tensor(joined)
+        bufs = [torch.empty_like(send) for _ in range(W)]
+        dist.all_gather(bufs, send)
+        out = []
+        for src in range(W):
+            off = sum(matrix[src][:self.rank])
+            out.append(bufs[src][off:off + matrix[src][self.rank]].cpu().numpy().tobytes())
+        return out
+
+    def gather_bytes(self, payload: bytes, dst: int = 0) -> Optional[List[bytes]]:
+        torch, dist, W = self.torch, self.dist, self.world
+        size = torch.tensor([len(payload)], dtype=torch.int64, device=self.device)
+        sizes = [torch.empty(1, dtype=torch.int64, device=self.device) for _ in range(W)]
+        dist.all_gather(sizes, size)
+        sz = [int(s.item()) for s in sizes]
+        send = torch.zeros(max(max(sz), 1), dtype=torch.uint8, device=self.device)
+        if payload:
+            send[:len(payload)] = self._tensor(payload)
+        bufs = [torch.empty_like(send) for _ in range(W)]
+        dist.all_gather(bufs, send)
+        if self.rank != dst:
+            return None
+        return [bufs[r][:sz[r]].cpu().numpy().tobytes() for r in range(W)]
+
+
+def _export_partials(plan) -> pa.RecordBatch:
+    arr, sch = ffi.ArrowArray(), ffi.ArrowSchema()
+    plan.lib.check(plan.lib.plan_export_partials(plan.handle, C.byref(arr), C.byref(sch)))
+    return ffi.import_batch(arr, sch)
+
+
+def _merge_partials(plan, batch: pa.RecordBatch):
+    arr, sch = ffi.export_batch(batch)
+    try:
+        plan.lib.check(plan.lib.plan_merge_partials(plan.handle, C.byref(arr), C.byref(sch)))
+    finally:
+        ffi.release_schema(sch)
+
+
+def partition_by_owner(partials: pa.RecordBatch, world: int) -> List[pa.RecordBatch]:
+    """Radix partition on the identity hash (column 0, the u64 row hash carried as int64)."""
+    h = np.asarray(partials.column(0).to_numpy(zero_copy_only=False)).view(np.uint64)
+    owner = (h % np.uint64(world)).astype(np.int64)
+    return [partials.filter(pa.array(owner == r)) for r in range(world)]
+
+
+def sharded_aggregate(plan, group: TorchGroup, row_base: int = 0) -> List[pa.RecordBatch]:
+    """Runs `plan` (root = aggregate) over the shard pushed on this rank; rank 0 returns the final batches."""
+    lib = plan.lib
+    lib.check(lib.plan_execute_partial(plan.handle, row_base))
+    local = _export_partials(plan)
+    received = group.all_to_all_bytes([_to_bytes(p) for p in partition_by_owner(local, group.world)])
+    lib.check(lib.plan_clear_partials(plan.handle))
+    for data in received:
+        _merge_partials(plan, _from_bytes(data))
+    owned = _export_partials(plan)
+    gathered = group.gather_bytes(_to_bytes(owned), dst=0)
+    lib.check(lib.plan_clear_partials(plan.handle))
+    if gathered is not None:
+        for data in gathered:
+            _merge_partials(plan, _from_bytes(data))
+    lib.check(lib.plan_finish_partial(plan.handle))
+    result = plan.collect()
+    return result if group.rank == 0 else []

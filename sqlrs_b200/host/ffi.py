@@ -26,6 +26,7 @@ JOIN_INNER, JOIN_LEFT, JOIN_RIGHT, JOIN_FULL = 0, 1, 2, 3
 COUNT_REFERENCE_OVERWRITE, COUNT_SQL_ACCUMULATE = 0, 1
 MATCH_HASH_ONLY, MATCH_HASH_AND_KEY = 0, 1
 FLAG_NO_FUSION = 1
+FLAG_TIMING = 4
 NODE_SCAN, NODE_FILTER, NODE_SIMPLE_AGG, NODE_HASH_AGG, NODE_HASH_JOIN = 1, 2, 3, 4, 5
 TPCH_CUSTOMER, TPCH_ORDERS, TPCH_LINEITEM = 0, 1, 2
 TPCH_FLAGS_8GROUP, TPCH_FLAGS_SPEC = 0, 1
@@ -200,6 +201,12 @@ _SIGNATURES = {
     "plan_reset": (C.c_int, [C.c_void_p]),
     "plan_describe": (C.c_char_p, [C.c_void_p]),
     "plan_destroy": (None, [C.c_void_p]),
+    "plan_execute_partial": (C.c_int, [C.c_void_p, C.c_int64]),
+    "plan_export_partials": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema)]),
+    "plan_clear_partials": (C.c_int, [C.c_void_p]),
+    "plan_merge_partials": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema)]),
+    "plan_finish_partial": (C.c_int, [C.c_void_p]),
+    "plan_scan_kernel_ms": (C.c_double, [C.c_void_p, P(C.c_int64)]),
     "tpch_num_columns": (C.c_int32, [C.c_int32]),
     "tpch_num_rows": (C.c_int64, [P(TpchDims), C.c_int32]),
     "tpch_generate": (C.c_int, [P(TpchDims), C.c_int32, C.c_int64, C.c_int64, P(C.c_void_p), C.c_void_p]),

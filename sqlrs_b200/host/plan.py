@@ -183,6 +183,12 @@ class GpuPlan:
     def reset(self):
         self.lib.check(self.lib.plan_reset(self.handle))
 
+    def scan_kernel_ms(self):
+        """(device ms, launches) of the dominant scan kernel(s) in the last execute (needs FLAG_TIMING)."""
+        n = C.c_int64(0)
+        ms = self.lib.plan_scan_kernel_ms(self.handle, C.byref(n))
+        return float(ms), int(n.value)
+
     def describe(self) -> str:
         s = self.lib.plan_describe(self.handle)
         return s.decode() if s else ""

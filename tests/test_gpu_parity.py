@@ -1,0 +1,364 @@
+"""Parity of the CUDA path with the CPU oracle, through the C ABI, on seeded random inputs.
+Integer / Boolean / index results bit-exact (row order included); Float64 sums within 1e-9 relative
+(north-star tolerance: 1e-6).  Covers the edge cases the reference tests and the ones it leaves
+unpinned: NULLs, empty and sliced batches, several batches per side, the quirks
+K1/K2/K3 in both behaviour modes, hash-table growth, heavy key duplication."""
+import ctypes as C
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from sqlrs_b200.host import executor as ex
+from sqlrs_b200.host import ffi, tpch
+from sqlrs_b200.host.expr import AggFunc, BinaryOp, Constant, InputRef, TypeCast, bind_binary_op
+from sqlrs_b200.host.plan import ExecutorBuilder
+from util import assert_batches_match, rows_of
+
+pytestmark = pytest.mark.gpu
+I32, I64, F64, BOOL = ffi.DT_INT32, ffi.DT_INT64, ffi.DT_FLOAT64, ffi.DT_BOOL
+PA = {I32: pa.int32(), I64: pa.int64(), F64: pa.float64(), BOOL: pa.bool_()}
+FTOL = 1e-9
+
+
+def random_batch(rng, n, dtypes, null_frac=0.15, small_ints=False, names=None):
+    arrays = []
+    for dt in dtypes:
+        if dt == F64:
+            v = np.round(rng.normal(0, 100, n), 2)
+        elif dt == BOOL:
+            v = rng.integers(0, 2, n).astype(bool)
+        elif dt == I32:
+            v = rng.integers(-6, 7, n).astype(np.int32) if small_ints else rng.integers(-2**31, 2**31 - 1, n).astype(np.int32)
+        else:
+            v = rng.integers(-6, 7, n).astype(np.int64) if small_ints else rng.integers(-2**62, 2**62, n).astype(np.int64)
+        mask = rng.random(n) < null_frac if null_frac > 0 else None
+        arrays.append(pa.array(v, type=PA[dt], mask=mask))
+    names = names or [f"c{i}" for i in range(len(dtypes))]
+    return pa.RecordBatch.from_arrays(arrays, names=names)
+
+
+def both(fn, cuda_lib, oracle):
+    return fn(cuda_lib), fn(oracle)
+
+
+# ------------------------------------------------------------------ expressions
+def random_expr(rng, dtypes, want, depth):
+    """A random well-typed BoundExpr of result type `want` over columns of `dtypes`."""
+    cols = [i for i, d in enumerate(dtypes) if d == want]
+    if depth == 0 or rng.random() < 0.25:
+        if cols and rng.random() < 0.8:
+            return InputRef(int(rng.choice(cols)), want)
+        if want == BOOL:
+            return Constant(bool(rng.integers(0, 2)))
+        if want == F64:
+            return Constant(float(np.round(rng.normal(0, 10), 1)))
+        v = int(rng.integers(-5, 6))
+        if rng.random() < 0.1:
+            return Constant(None, want)
+        return Constant(v, want)
+    if want == BOOL:
+        kind = rng.choice(["cmp", "logic", "cast"])
+        if kind == "cmp":
+            t = int(rng.choice([I32, I64, F64, BOOL]))
+            op = str(rng.choice([">", "<", ">=", "<=", "=", "<>"]))
+            return BinaryOp(op, random_expr(rng, dtypes, t, depth - 1), random_expr(rng, dtypes, t, depth - 1), BOOL)
+        if kind == "logic":
+            return BinaryOp(str(rng.choice(["AND", "OR"])), random_expr(rng, dtypes, BOOL, depth - 1), random_expr(rng, dtypes, BOOL, depth - 1), BOOL)
+        return TypeCast(random_expr(rng, dtypes, int(rng.choice([I32, I64, F64])), depth - 1), BOOL)
+    if rng.random() < 0.25:
+        src = int(rng.choice([t for t in (I32, I64, F64, BOOL) if t != want]))
+        return TypeCast(random_expr(rng, dtypes, src, depth - 1), want)
+    op = str(rng.choice(["+", "-", "*"]))
+    return BinaryOp(op, random_expr(rng, dtypes, want, depth - 1), random_expr(rng, dtypes, want, depth - 1), want)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_expressions(cuda_lib, oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    dtypes = [I32, I64, F64, BOOL, I64, F64, I32, BOOL]
+    n = int(rng.choice([0, 1, 31, 32, 33, 1000, 4097]))
+    b = random_batch(rng, n, dtypes, null_frac=float(rng.choice([0.0, 0.2])))
+    for _ in range(6):
+        want = int(rng.choice([I32, I64, F64, BOOL]))
+        e = random_expr(rng, dtypes, want, 3)
+        got, exp = both(lambda l: ex.eval_column(e, b, lib=l), cuda_lib, oracle)
+        assert got.type == exp.type, (e, got.type, exp.type)
+        assert got.to_pylist() == exp.to_pylist() or all(
+            (g == w) or (g is not None and w is not None and g != g and w != w) for g, w in zip(got.to_pylist(), exp.to_pylist())), e
+
+
+def test_integer_division_and_divide_by_zero(cuda_lib, oracle):
+    b = pa.RecordBatch.from_arrays([pa.array([7, -7, -2**63, 5, None], pa.int64()), pa.array([2, 2, -1, None, 0], pa.int64())], names=["a", "b"])
+    e = BinaryOp("/", InputRef(0, I64), InputRef(1, I64), I64)
+    got, exp = both(lambda l: ex.eval_column(e, b, lib=l).to_pylist(), cuda_lib, oracle)
+    assert got == exp == [3, -3, -2**63, None, None]
+    bad = pa.RecordBatch.from_arrays([pa.array([1, 2], pa.int64()), pa.array([1, 0], pa.int64())], names=["a", "b"])
+    for lib in (cuda_lib, oracle):
+        with pytest.raises(ffi.ExecutorError) as err:
+            ex.eval_column(e, bad, lib=lib)
+        assert err.value.code == ffi.ERR_ARROW and "Divide by zero" in err.value.message
+
+
+def test_type_errors_match_the_oracle(cuda_lib, oracle):
+    b = random_batch(np.random.default_rng(5), 10, [I32, I64, F64, BOOL])
+    cases = [BinaryOp("+", InputRef(0, I32), InputRef(1, I64), I64), BinaryOp(">", InputRef(0, I32), InputRef(2, F64), BOOL),
+             BinaryOp("AND", InputRef(0, I32), InputRef(3, BOOL), BOOL), BinaryOp("+", InputRef(3, BOOL), InputRef(3, BOOL), BOOL),
+             InputRef(9, I64)]
+    for e in cases:
+        codes = []
+        for lib in (cuda_lib, oracle):
+            with pytest.raises(ffi.ExecutorError) as err:
+                ex.eval_column(e, b, lib=lib)
+            codes.append(err.value.code)
+        assert codes[0] == codes[1], (e, codes)
+
+
+# ------------------------------------------------------------------ filter
+@pytest.mark.parametrize("seed", range(6))
+def test_filter_random_and_sliced(cuda_lib, oracle, seed):
+    rng = np.random.default_rng(2000 + seed)
+    dtypes = [I64, F64, I32, BOOL, I64]
+    n = int(rng.choice([1, 63, 64, 65, 5000, 70001]))
+    full = random_batch(rng, n + 37, dtypes, null_frac=0.2, small_ints=True)
+    b = full.slice(int(rng.integers(0, 37)), n)  # non-zero offsets, unaligned bitmaps (Limit slices batches: limit.rs:69)
+    pred = BinaryOp("OR", bind_binary_op(InputRef(0, I64), ">", Constant(0)),
+                    BinaryOp("AND", InputRef(3, BOOL), BinaryOp("<", InputRef(1, F64), Constant(10.0), BOOL), BOOL), BOOL)
+    got, exp = both(lambda l: ex.try_collect(ex.FilterExecutor(pred, [b, b.slice(0, 0), full], lib=l).execute()), cuda_lib, oracle)
+    assert len(got) == len(exp) == 3
+    assert_batches_match(got, exp)
+
+
+# ------------------------------------------------------------------ aggregates
+def agg_funcs_for(dtypes):
+    out = []
+    for i, dt in enumerate(dtypes):
+        if dt == I64:
+            out += [AggFunc("Sum", [InputRef(i, dt)]), AggFunc("Min", [InputRef(i, dt)]), AggFunc("Max", [InputRef(i, dt)]), AggFunc("Count", [InputRef(i, dt)])]
+        elif dt == F64:
+            out += [AggFunc("Sum", [InputRef(i, dt)]), AggFunc("Min", [InputRef(i, dt)]), AggFunc("Max", [InputRef(i, dt)])]
+        elif dt == I32:
+            out += [AggFunc("Min", [InputRef(i, dt)]), AggFunc("Max", [InputRef(i, dt)]), AggFunc("Count", [InputRef(i, dt)]),
+                    AggFunc("Sum", [TypeCast(InputRef(i, dt), I64)])]
+        else:
+            out += [AggFunc("Count", [InputRef(i, dt)])]
+    return out
+
+
+@pytest.mark.parametrize("count_mode", [ffi.COUNT_REFERENCE_OVERWRITE, ffi.COUNT_SQL_ACCUMULATE])
+@pytest.mark.parametrize("match_mode", [ffi.MATCH_HASH_ONLY, ffi.MATCH_HASH_AND_KEY])
+@pytest.mark.parametrize("cardinality", [3, 13, 4000])
+def test_hash_agg_random(cuda_lib, oracle, count_mode, match_mode, cardinality):
+    """several nullable batches; 3 groups stay in shared memory, 13 overflow to the HBM table mid-stream, 4000 grow it"""
+    rng = np.random.default_rng(cardinality * 7 + count_mode * 3 + match_mode)
+    dtypes = [I64, I32, F64, I64, BOOL, I32]
+    batches = []
+    for n in (700, 0, 2500, 33, 9000):
+        b = random_batch(rng, n, dtypes, null_frac=0.1)
+        k0 = pa.array(rng.integers(0, cardinality, n).astype(np.int64), mask=rng.random(n) < 0.05)
+        k1 = pa.array(rng.integers(0, 2, n).astype(np.int32))
+        batches.append(pa.RecordBatch.from_arrays([k0, k1] + b.columns[2:], names=b.schema.names))
+    aggs = agg_funcs_for(dtypes)[:14]
+    groups = [InputRef(0, I64), InputRef(1, I32)]
+
+    def run(l):
+        return ex.try_collect(ex.HashAggExecutor(aggs, groups, batches, lib=l, options=l.options(count_mode=count_mode, match_mode=match_mode)).execute())
+
+    got, exp = both(run, cuda_lib, oracle)
+    assert_batches_match(got, exp, rtol=FTOL)
+
+
+def test_simple_agg_random_and_empty(cuda_lib, oracle):
+    rng = np.random.default_rng(77)
+    dtypes = [I64, F64, I32, BOOL]
+    aggs = agg_funcs_for(dtypes)
+    for batches in ([random_batch(rng, 5000, dtypes), random_batch(rng, 1, dtypes), random_batch(rng, 0, dtypes)],
+                    [random_batch(rng, 0, dtypes)], [random_batch(rng, 100, dtypes, null_frac=1.0)]):
+        for cm in (ffi.COUNT_REFERENCE_OVERWRITE, ffi.COUNT_SQL_ACCUMULATE):
+            got, exp = both(lambda l: ex.try_collect(ex.SimpleAggExecutor(aggs, batches, lib=l, options=l.options(count_mode=cm)).execute()), cuda_lib, oracle)
+            assert_batches_match(got, exp, rtol=FTOL)
+    for lib in (cuda_lib, oracle):  # simple_agg.rs:63 / hash_agg.rs:125 unwrap None when the child yields nothing
+        with pytest.raises(ffi.ExecutorError):
+            ex.try_collect(ex.SimpleAggExecutor(aggs, [], lib=lib).execute())
+        with pytest.raises(ffi.ExecutorError):
+            ex.try_collect(ex.HashAggExecutor(aggs, [InputRef(0, I64)], [], lib=lib).execute())
+
+
+def test_quirk_k2_k3_hash_only_groups(cuda_lib, oracle):
+    """combine_hashes is symmetric in two same-typed columns: (0,1) and (1,0) share a row hash, so the reference
+    (hash-only identity) merges them and reports the keys of the group's FIRST row; a NULL key keeps hash 0."""
+    b = pa.RecordBatch.from_arrays([pa.array([1, 0, 0, 1, None, 5], pa.int64()), pa.array([0, 1, 1, 0, 0, None], pa.int64()),
+                                    pa.array([10, 20, 30, 40, 50, 60], pa.int64())], names=["a", "b", "v"])
+    aggs, groups = [AggFunc("Sum", [InputRef(2, I64)]), AggFunc("Count", [InputRef(2, I64)])], [InputRef(0, I64), InputRef(1, I64)]
+    for mm, n_groups in ((ffi.MATCH_HASH_ONLY, 3), (ffi.MATCH_HASH_AND_KEY, 4)):
+        got, exp = both(lambda l: ex.try_collect(ex.HashAggExecutor(aggs, groups, [b], lib=l, options=l.options(match_mode=mm)).execute()), cuda_lib, oracle)
+        assert_batches_match(got, exp)
+        assert got[0].num_rows == n_groups
+    first = rows_of(ex.try_collect(ex.HashAggExecutor(aggs, groups, [b], lib=cuda_lib).execute()))[0]
+    assert first == (1, 0, 100, 4)
+
+
+def test_quirk_k1_count_overwrites(cuda_lib, oracle):
+    """count.rs:22 assigns: COUNT = non-NULL count of the LAST batch that touched the group"""
+    b1 = pa.RecordBatch.from_arrays([pa.array([1, 1, 2], pa.int64()), pa.array([1, None, 3], pa.int64())], names=["k", "v"])
+    b2 = pa.RecordBatch.from_arrays([pa.array([1, 3], pa.int64()), pa.array([7, 8], pa.int64())], names=["k", "v"])
+    aggs, groups = [AggFunc("Count", [InputRef(1, I64)]), AggFunc("Sum", [InputRef(1, I64)])], [InputRef(0, I64)]
+    got = rows_of(ex.try_collect(ex.HashAggExecutor(aggs, groups, [b1, b2], lib=cuda_lib).execute()))
+    exp = rows_of(ex.try_collect(ex.HashAggExecutor(aggs, groups, [b1, b2], lib=oracle).execute()))
+    assert got == exp == [(1, 1, 8), (2, 1, 3), (3, 1, 8)]
+    sql = cuda_lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE)
+    assert rows_of(ex.try_collect(ex.HashAggExecutor(aggs, groups, [b1, b2], lib=cuda_lib, options=sql).execute())) == [(1, 2, 8), (2, 1, 3), (3, 1, 8)]
+
+
+# ------------------------------------------------------------------ joins
+def _joined_schema(left, right, nullable=True):
+    return pa.schema([pa.field("l." + f.name, f.type, nullable) for f in left.schema] + [pa.field("r." + f.name, f.type, nullable) for f in right.schema])
+
+
+@pytest.mark.parametrize("join_type", ["Inner", "Left", "Right", "Full"])
+@pytest.mark.parametrize("match_mode", [ffi.MATCH_HASH_ONLY, ffi.MATCH_HASH_AND_KEY])
+@pytest.mark.parametrize("with_filter", [False, True])
+def test_hash_join_random(cuda_lib, oracle, join_type, match_mode, with_filter):
+    """duplicates on both sides, NULL keys, two key columns, several batches per side, exact output order"""
+    rng = np.random.default_rng(hash((join_type, match_mode, with_filter)) % 2**31)
+    dtypes = [I64, I32, F64, I64]
+
+    def side(n):
+        b = random_batch(rng, n, dtypes, null_frac=0.1, small_ints=True)
+        return b
+
+    lefts = [side(300), side(0), side(41)]
+    rights = [side(500), side(64), side(0), side(1)]
+    cond = ex.JoinCondition([(InputRef(0, I64), InputRef(0, I64)), (InputRef(1, I32), InputRef(1, I32))],
+                            BinaryOp(">", InputRef(2, F64), InputRef(6, F64), BOOL) if with_filter else None)
+    schema = _joined_schema(lefts[0], rights[0])
+
+    def run(l):
+        return ex.try_collect(ex.HashJoinExecutor(lefts, rights, join_type, cond, schema, lib=l, options=l.options(match_mode=match_mode)).execute())
+
+    got, exp = both(run, cuda_lib, oracle)
+    assert len(got) == len(exp)
+    assert_batches_match(got, exp)
+
+
+def test_hash_join_heavy_duplicates_and_growth(cuda_lib, oracle):
+    """one build key repeated 500x (stable radix-sort path for the CSR), many distinct keys around it"""
+    rng = np.random.default_rng(9)
+    keys = np.concatenate([np.full(500, 7), rng.integers(0, 20000, 30000)]).astype(np.int64)
+    rng.shuffle(keys)
+    left = pa.RecordBatch.from_arrays([pa.array(keys), pa.array(np.arange(len(keys), dtype=np.int64))], names=["k", "lrow"])
+    pk = np.concatenate([np.full(3, 7), rng.integers(0, 25000, 5000)]).astype(np.int64)
+    right = pa.RecordBatch.from_arrays([pa.array(pk), pa.array(np.arange(len(pk), dtype=np.int64))], names=["k", "rrow"])
+    cond = ex.JoinCondition([(InputRef(0, I64), InputRef(0, I64))])
+    schema = _joined_schema(left, right)
+    for jt in ("Inner", "Full"):
+        got, exp = both(lambda l: ex.try_collect(ex.HashJoinExecutor([left], [right], jt, cond, schema, lib=l).execute()), cuda_lib, oracle)
+        assert_batches_match(got, exp)
+
+
+def test_join_schema_errors_match(cuda_lib, oracle):
+    """RecordBatch::try_new: a non-nullable output field that receives NULLs is an Arrow error"""
+    left = pa.RecordBatch.from_arrays([pa.array([1, 2], pa.int64())], names=["a"])
+    right = pa.RecordBatch.from_arrays([pa.array([2, 3], pa.int64())], names=["b"])
+    schema = _joined_schema(left, right, nullable=False)
+    cond = ex.JoinCondition([(InputRef(0, I64), InputRef(0, I64))])
+    for lib in (cuda_lib, oracle):
+        assert rows_of(ex.try_collect(ex.HashJoinExecutor([left], [right], "Inner", cond, schema, lib=lib).execute())) == [(2, 2)]
+        with pytest.raises(ffi.ExecutorError) as err:
+            ex.try_collect(ex.HashJoinExecutor([left], [right], "Right", cond, schema, lib=lib).execute())
+        assert err.value.code == ffi.ERR_ARROW
+
+
+# ------------------------------------------------------------------ the benchmark plans, small scale
+def _tables(oracle, d):
+    return {0: tpch.host_table(oracle, d, tpch.CUSTOMER, columns=tpch.Q3_CUSTOMER_COLUMNS),
+            1: tpch.host_table(oracle, d, tpch.ORDERS, columns=tpch.Q3_ORDERS_COLUMNS),
+            2: tpch.host_table(oracle, d, tpch.LINEITEM, columns=tpch.Q3_LINEITEM_COLUMNS)}
+
+
+def _run_plan(lib, plan, schemas, tables, batch_rows=None, **opts):
+    p = ExecutorBuilder(lib, lib.options(**opts)).build(plan, schemas)
+    for slot, t in tables.items():
+        step = batch_rows or max(t.num_rows, 1)
+        for off in range(0, max(t.num_rows, 1), step):
+            p.push_table(slot, t.slice(off, step))
+    out = p.run()
+    desc = p.describe()
+    p.close()
+    return out, desc
+
+
+@pytest.mark.parametrize("flags_mode", [ffi.TPCH_FLAGS_8GROUP, ffi.TPCH_FLAGS_SPEC])
+@pytest.mark.parametrize("modes", [(ffi.COUNT_SQL_ACCUMULATE, ffi.MATCH_HASH_AND_KEY), (ffi.COUNT_REFERENCE_OVERWRITE, ffi.MATCH_HASH_ONLY)])
+def test_q1_plan_matches_oracle(cuda_lib, oracle, flags_mode, modes):
+    d = tpch.dims(0.05, flags_mode)
+    plan, schemas = tpch.q1_plan()
+    table = {0: tpch.host_table(oracle, d, tpch.LINEITEM, columns=tpch.Q1_COLUMNS)}
+    for fl in (0, ffi.FLAG_NO_FUSION):
+        for batch_rows in (None, 65536):
+            got, desc = _run_plan(cuda_lib, plan, schemas, table, batch_rows, count_mode=modes[0], match_mode=modes[1], flags=fl)
+            exp, _ = _run_plan(oracle, plan, schemas, table, batch_rows, count_mode=modes[0], match_mode=modes[1])
+            assert_batches_match(got, exp, rtol=FTOL)
+            assert ("fused" in desc) == (fl == 0)
+
+
+def test_q3_plan_matches_oracle(cuda_lib, oracle):
+    d = tpch.dims(0.05)
+    plan, schemas = tpch.q3_plan()
+    tables = _tables(oracle, d)
+    for batch_rows in (None, 100_000):
+        got, _ = _run_plan(cuda_lib, plan, schemas, tables, batch_rows, count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+        exp, _ = _run_plan(oracle, plan, schemas, tables, batch_rows, count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+        assert got[0].num_rows > 100
+        assert_batches_match(got, exp, rtol=FTOL)
+
+
+def test_generator_is_bit_identical_on_device(cuda_lib, oracle):
+    import torch
+
+    d = tpch.dims(0.02)
+    for table in (tpch.CUSTOMER, tpch.ORDERS, tpch.LINEITEM):
+        n = tpch.num_rows(oracle, d, table)
+        lo, hi = n // 3, n - 5
+        host = tpch.host_table(oracle, d, table, lo, hi)
+        dev = tpch.device_table(cuda_lib, d, table, lo, hi)
+        for c, t in enumerate(dev.tensors):
+            want = host.column(c).to_numpy()
+            assert np.array_equal(t.cpu().numpy(), want.view(np.int64)), (table, c)
+
+
+# ------------------------------------------------------------------ full size: properties that need no oracle pass
+def test_q1_full_size_properties(cuda_lib):
+    """BASELINE config 2 size (SF10, ~60 M rows, resident in HBM): integer checksums and linearity"""
+    import torch
+
+    d = tpch.dims(10)
+    n = tpch.num_rows(cuda_lib, d, tpch.LINEITEM)
+    plan, schemas = tpch.q1_plan()
+    opts = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+
+    def run(lo, hi):
+        t = tpch.device_table(cuda_lib, d, tpch.LINEITEM, lo, hi, columns=tpch.Q1_COLUMNS)
+        p = ExecutorBuilder(cuda_lib, cuda_lib.options(**opts)).build(plan, schemas)
+        p.push_table_device(0, t)
+        out = pa.Table.from_batches(p.run()).to_pydict()
+        p.close()
+        return {(a, b): [out[c][i] for c in list(out)[2:]] for i, (a, b) in enumerate(zip(out["l_returnflag"], out["l_linestatus"]))}, t
+
+    whole, table = run(0, n)
+    assert len(whole) == 8
+    ship = table.tensors[tpch.Q1_COLUMNS.index(7)]
+    qty = table.tensors[tpch.Q1_COLUMNS.index(8)]
+    keep = ship <= tpch.Q1_SHIPDATE_MAX
+    assert sum(v[5] for v in whole.values()) == int(keep.sum().item())            # count of counts
+    assert sum(v[4] for v in whole.values()) == int(qty[keep].sum().item())        # checksum of the integer sums
+    for v in whole.values():
+        assert v[0] == float(v[4])   # SUM(l_quantity) over doubles of small integers is exact and equals the int64 sum
+    del table
+    torch.cuda.empty_cache()
+    a, _ = run(0, n // 3)
+    b, _ = run(n // 3, n)
+    for k, v in whole.items():       # linearity: two shards add up (ints exactly, float sums to rounding)
+        assert v[4] == a[k][4] + b[k][4] and v[5] == a[k][5] + b[k][5]
+        for j in range(4):
+            assert abs(v[j] - (a[k][j] + b[k][j])) <= 1e-9 * abs(v[j])

@@ -1,0 +1,254 @@
+"""The reference's own golden vectors for the hot path, replayed through the C ABI.
+
+Every case runs against the CPU oracle (pins the oracle to the reference; `-m "not gpu"`) and, on the
+GPU box, against the CUDA library (`-m gpu`).  Fixtures are the reference's test data:
+  hash KAT               src/executor/aggregate/hash_utils.rs:229-247
+  HashAgg two chunks     src/executor/aggregate/hash_agg.rs:182-222
+  HashJoin 8 tables      src/executor/join/hash_join.rs:393-403,423-750
+  executor e2e           src/executor/mod.rs:271-396
+  SLT over tests/csv     tests/slt/{aggregation,filter,join,join_filter}.slt
+Utf8 columns are outside the CUDA backend's scope: string cases run on the
+oracle only, numeric projections of the same tables on both.
+"""
+import pyarrow as pa
+import pytest
+
+from sqlrs_b200.host import executor as ex
+from sqlrs_b200.host import ffi
+from sqlrs_b200.host.expr import AggFunc, BinaryOp, Constant, InputRef, bind_binary_op
+from util import batch, rows_of
+
+I32, I64, F64, BOOL = ffi.DT_INT32, ffi.DT_INT64, ffi.DT_FLOAT64, ffi.DT_BOOL
+N = None
+
+
+# ---------------------------------------------------------------- fixtures = the reference's data
+def employee_numeric():
+    """tests/csv/employee.csv, numeric columns: id, salary, department_id (row 4 has NULL salary / department_id)."""
+    return batch(["id", "salary", "department_id"], [1, 2, 3, 4], [12000, 10000, 11500, N], [1, 2, 4, N])
+
+
+def department_numeric():
+    return batch(["id"], [1, 2, 3, 4])
+
+
+def t1():
+    return batch(["a", "b", "c"], [0, 1, 2, 2], [4, 5, 7, 8], [7, 8, 9, 1])
+
+
+def t2():
+    return batch(["a", "b", "c"], [10, 20, 30, 40], [2, 2, 3, 4], [7, 5, 6, 6])
+
+
+def mem_employee():
+    """src/executor/mod.rs:220-243 (numeric columns): id, salary"""
+    return batch(["id", "salary"], [1, 2, 3, 4], [100, 100, 200, 400], nullable=False)
+
+
+# ---------------------------------------------------------------- hash KAT
+def test_hash_kat(lib):
+    """hash_utils.rs:229-247: two identical Float64 columns -> pinned u64 hashes"""
+    a = pa.array([0.12, 0.5, 1.0, 444.7])
+    assert ex.create_hashes([a, a], lib=lib) == [13192744372685867462, 5527281222425499956, 3851526787237496334, 1092489821776418240]
+
+
+def test_hash_single_column_and_null(lib):
+    """hash_utils.rs:81-104,167: one column = raw hash_one; a NULL cell keeps the initial 0 (quirk K3)"""
+    h = ex.create_hashes([pa.array([0, 1, None, 2, -1, 10471], pa.int64())], lib=lib)
+    assert h == [1838465364428186174, 11003429890058878283, 0, 12908271710217070096, 7568711536646566273, 15327478874182264267]
+
+
+# ---------------------------------------------------------------- HashAgg
+def test_hash_agg_two_chunks(lib):
+    """hash_agg.rs:182-222: a=[1,1,2], b=[1,1,3] twice; sum(b) group by a -> (1,4),(2,6); header a | Sum(b)"""
+    b = batch(["a", "b"], [1, 1, 2], [1, 1, 3], nullable=False)
+    op = ex.HashAggExecutor([AggFunc("Sum", [InputRef(1, I64)])], [InputRef(0, I64)], [b, b], lib=lib)
+    out = ex.try_collect(op.execute())
+    assert len(out) == 1 and out[0].schema.names == ["a", "Sum(b)"]
+    assert rows_of(out) == [(1, 4), (2, 6)]
+
+
+def test_executor_hash_agg(lib):
+    """mod.rs:317-350: select salary, count(id), sum(id), max(id), min(id) from employee group by salary"""
+    idc, sal = InputRef(0, I64), InputRef(1, I64)
+    op = ex.HashAggExecutor([AggFunc("Count", [idc]), AggFunc("Sum", [idc]), AggFunc("Max", [idc]), AggFunc("Min", [idc])], [sal],
+                            [mem_employee()], lib=lib)
+    out = ex.try_collect(op.execute())
+    assert out[0].schema.names == ["salary", "Count(id)", "Sum(id)", "Max(id)", "Min(id)"]
+    assert rows_of(out) == [(100, 2, 3, 2, 1), (200, 1, 3, 3, 3), (400, 1, 4, 4, 4)]
+
+
+def test_executor_simple_agg(lib):
+    """mod.rs:293-313: select sum(salary) from employee -> 800"""
+    op = ex.SimpleAggExecutor([AggFunc("Sum", [InputRef(1, I64)])], [mem_employee()], lib=lib)
+    assert rows_of(ex.try_collect(op.execute())) == [(800,)]
+
+
+def test_executor_filter(lib):
+    """mod.rs:271-291: ... where id = 1 -> the first row"""
+    pred = bind_binary_op(InputRef(0, I64), "=", Constant(1))
+    out = ex.try_collect(ex.FilterExecutor(pred, [mem_employee()], lib=lib).execute())
+    assert rows_of(out) == [(1, 100)]
+
+
+def test_slt_aggregation_simple(lib):
+    """aggregation.slt:1-11 — incl. BASELINE config 1: sum(salary), count(salary) ... where id > 1 -> 21500, 2"""
+    emp = employee_numeric()
+    idc, sal = InputRef(0, I64), InputRef(1, I64)
+    assert rows_of(ex.try_collect(ex.SimpleAggExecutor([AggFunc("Sum", [sal])], [emp], lib=lib).execute())) == [(33500,)]
+    filtered = ex.FilterExecutor(bind_binary_op(idc, ">", Constant(1)), [emp], lib=lib).execute()
+    aggs = [AggFunc("Sum", [sal]), AggFunc("Sum", [bind_binary_op(idc, "+", Constant(1))]), AggFunc("Count", [idc]), AggFunc("Count", [sal])]
+    out = ex.try_collect(ex.SimpleAggExecutor(aggs, filtered, lib=lib).execute())
+    assert out[0].schema.names == ["Sum(salary)", "Sum(id+Int64(1))", "Count(id)", "Count(salary)"]
+    assert rows_of(out) == [(21500, 12, 3, 2)]
+    out = ex.try_collect(ex.SimpleAggExecutor([AggFunc("Max", [sal]), AggFunc("Min", [idc])], [emp], lib=lib).execute())
+    assert rows_of(out) == [(12000, 1)]
+
+
+def test_slt_aggregation_group_by_with_null_group(lib):
+    """aggregation.slt:19-26: group by salary — the NULL salary forms its own group, SUM/MAX/MIN of it are NULL"""
+    idc, sal = InputRef(0, I64), InputRef(1, I64)
+    op = ex.HashAggExecutor([AggFunc("Count", [idc]), AggFunc("Sum", [sal]), AggFunc("Max", [sal]), AggFunc("Min", [sal])], [sal],
+                            [employee_numeric()], lib=lib)
+    assert rows_of(ex.try_collect(op.execute())) == [(12000, 1, 12000, 12000, 12000), (10000, 1, 10000, 10000, 10000),
+                                                      (11500, 1, 11500, 11500, 11500), (N, 1, N, N, N)]
+
+
+def test_slt_aggregation_two_keys(lib):
+    """aggregation.slt:36-43 (numeric projection): group by department_id, id"""
+    idc, sal, dep = InputRef(0, I64), InputRef(1, I64), InputRef(2, I64)
+    op = ex.HashAggExecutor([AggFunc("Count", [dep]), AggFunc("Sum", [sal])], [dep, idc], [employee_numeric()], lib=lib)
+    assert rows_of(ex.try_collect(op.execute())) == [(1, 1, 1, 12000), (2, 2, 1, 10000), (4, 3, 1, 11500), (N, 4, 0, N)]
+
+
+def test_slt_filter(lib):
+    """filter.slt:1-19"""
+    emp = employee_numeric()
+    idc = InputRef(0, I64)
+    gt2 = bind_binary_op(idc, ">", Constant(2))
+    ids = lambda pred: [r[0] for r in rows_of(ex.try_collect(ex.FilterExecutor(pred, [emp], lib=lib).execute()))]
+    assert ids(gt2) == [3, 4]
+    assert ids(BinaryOp("AND", gt2, bind_binary_op(idc, "<", Constant(4)))) == [3]
+    assert ids(BinaryOp("OR", bind_binary_op(idc, ">", Constant(3)), bind_binary_op(idc, "=", Constant(1)))) == [1, 4]
+
+
+# ---------------------------------------------------------------- HashJoin: hash_join.rs tests
+def _i32_table(names, *cols):
+    return batch(names, *cols, types=[pa.int32()] * 3, nullable=False)
+
+
+def _join_schema(left, lname, right, rname, join_type):
+    lnull, rnull = {"Inner": (False, False), "Left": (False, True), "Right": (True, False), "Full": (True, True)}[join_type]
+    fields = [pa.field(f"{lname}.{f.name}", f.type, lnull) for f in left.schema] + [pa.field(f"{rname}.{f.name}", f.type, rnull) for f in right.schema]
+    return pa.schema(fields)
+
+
+JOIN_EXPECTED = {  # hash_join.rs:442-450, 473-483, 506-515, 538-549
+    "Inner": [(1, 4, 7, 10, 4, 70), (2, 5, 8, 20, 5, 80), (3, 5, 9, 20, 5, 80)],
+    "Left": [(1, 4, 7, 10, 4, 70), (2, 5, 8, 20, 5, 80), (3, 5, 9, 20, 5, 80), (0, 0, 10, N, N, N), (4, 8, 10, N, N, N)],
+    "Right": [(1, 4, 7, 10, 4, 70), (2, 5, 8, 20, 5, 80), (3, 5, 9, 20, 5, 80), (N, N, N, 30, 6, 90)],
+    "Full": [(1, 4, 7, 10, 4, 70), (2, 5, 8, 20, 5, 80), (3, 5, 9, 20, 5, 80), (N, N, N, 30, 6, 90), (0, 0, 10, N, N, N), (4, 8, 10, N, N, N)],
+}
+
+
+@pytest.mark.parametrize("join_type", ["Inner", "Left", "Right", "Full"])
+def test_hash_join_results(lib, join_type):
+    left = _i32_table(["a1", "b1", "c1"], [0, 1, 2, 3, 4], [0, 4, 5, 5, 8], [10, 7, 8, 9, 10])
+    right = _i32_table(["a2", "b1", "c2"], [10, 20, 30], [4, 5, 6], [70, 80, 90])
+    schema = _join_schema(left, "l", right, "r", join_type)
+    cond = ex.JoinCondition([(InputRef(1, I32), InputRef(1, I32))])
+    out = ex.try_collect(ex.HashJoinExecutor([left], [right], join_type, cond, schema, lib=lib).execute())
+    assert out[0].schema.names == ["l.a1", "l.b1", "l.c1", "r.a2", "r.b1", "r.c2"]
+    assert rows_of(out) == JOIN_EXPECTED[join_type]
+
+
+JOIN_FILTER_EXPECTED = {  # hash_join.rs:620-627, 657-667, 697-706, 736-748 (key l.a = r.b, filter l.c > r.c)
+    "Inner": [(2, 7, 9, 10, 2, 7), (2, 7, 9, 20, 2, 5)],
+    "Left": [(2, 7, 9, 10, 2, 7), (2, 7, 9, 20, 2, 5), (0, 4, 7, N, N, N), (1, 5, 8, N, N, N), (2, 8, 1, N, N, N)],
+    "Right": [(2, 7, 9, 10, 2, 7), (2, 7, 9, 20, 2, 5), (N, N, N, 30, 3, 6), (N, N, N, 40, 4, 6)],
+    "Full": [(2, 7, 9, 10, 2, 7), (2, 7, 9, 20, 2, 5), (N, N, N, 30, 3, 6), (N, N, N, 40, 4, 6), (0, 4, 7, N, N, N), (1, 5, 8, N, N, N), (2, 8, 1, N, N, N)],
+}
+JOIN_NOFILTER_T1T2 = {  # tests/slt/join_filter.slt: t1.a = t2.b without the non-equi part
+    "Inner": [(2, 7, 9, 10, 2, 7), (2, 8, 1, 10, 2, 7), (2, 7, 9, 20, 2, 5), (2, 8, 1, 20, 2, 5)],
+    "Left": [(2, 7, 9, 10, 2, 7), (2, 8, 1, 10, 2, 7), (2, 7, 9, 20, 2, 5), (2, 8, 1, 20, 2, 5), (0, 4, 7, N, N, N), (1, 5, 8, N, N, N)],
+    "Right": [(2, 7, 9, 10, 2, 7), (2, 8, 1, 10, 2, 7), (2, 7, 9, 20, 2, 5), (2, 8, 1, 20, 2, 5), (N, N, N, 30, 3, 6), (N, N, N, 40, 4, 6)],
+    "Full": [(2, 7, 9, 10, 2, 7), (2, 8, 1, 10, 2, 7), (2, 7, 9, 20, 2, 5), (2, 8, 1, 20, 2, 5), (N, N, N, 30, 3, 6), (N, N, N, 40, 4, 6),
+             (0, 4, 7, N, N, N), (1, 5, 8, N, N, N)],
+}
+
+
+@pytest.mark.parametrize("join_type", ["Inner", "Left", "Right", "Full"])
+def test_hash_join_filter_results_i32(lib, join_type):
+    """hash_join.rs:564-748 — Int32 tables, non-equi filter l.c > r.c over the joined row"""
+    left = _i32_table(["a", "b", "c"], [0, 1, 2, 2], [4, 5, 7, 8], [7, 8, 9, 1])
+    right = _i32_table(["a", "b", "c"], [10, 20, 30, 40], [2, 2, 3, 4], [7, 5, 6, 6])
+    schema = _join_schema(left, "l", right, "r", join_type)
+    cond = ex.JoinCondition([(InputRef(0, I32), InputRef(1, I32))], BinaryOp(">", InputRef(2, I32), InputRef(5, I32)))
+    out = ex.try_collect(ex.HashJoinExecutor([left], [right], join_type, cond, schema, lib=lib).execute())
+    assert rows_of(out) == JOIN_FILTER_EXPECTED[join_type]
+
+
+@pytest.mark.parametrize("join_type", ["Inner", "Left", "Right", "Full"])
+@pytest.mark.parametrize("with_filter", [False, True])
+def test_slt_join_filter_t1_t2(lib, join_type, with_filter):
+    """tests/slt/join_filter.slt:10-91 over tests/csv/t1.csv, t2.csv (Int64 from CSV inference)"""
+    left, right = t1(), t2()
+    schema = _join_schema(left, "t1", right, "t2", join_type)
+    flt = BinaryOp(">", InputRef(2, I64), InputRef(5, I64)) if with_filter else None
+    cond = ex.JoinCondition([(InputRef(0, I64), InputRef(1, I64))], flt)
+    out = ex.try_collect(ex.HashJoinExecutor([left], [right], join_type, cond, schema, lib=lib).execute())
+    assert rows_of(out) == (JOIN_FILTER_EXPECTED if with_filter else JOIN_NOFILTER_T1T2)[join_type]
+
+
+SLT_EMP_DEPT = {  # tests/slt/join.slt:1-40 projected on (employee.id, employee.department_id, department.id)
+    "Left": [(1, 1, 1), (2, 2, 2), (3, 4, 4), (4, N, N)],
+    "Right": [(1, 1, 1), (2, 2, 2), (N, N, 3), (3, 4, 4)],
+    "Inner": [(1, 1, 1), (2, 2, 2), (3, 4, 4)],
+    "Full": [(1, 1, 1), (2, 2, 2), (N, N, 3), (3, 4, 4), (4, N, N)],
+}
+
+
+@pytest.mark.parametrize("join_type", ["Inner", "Left", "Right", "Full"])
+def test_slt_join_employee_department(lib, join_type):
+    """tests/slt/join.slt:1-40 — a NULL department_id never finds a partner (its hash 0 matches no department)"""
+    emp, dep = employee_numeric(), department_numeric()
+    schema = _join_schema(emp, "employee", dep, "department", "Full")
+    cond = ex.JoinCondition([(InputRef(2, I64), InputRef(0, I64))])
+    out = ex.try_collect(ex.HashJoinExecutor([emp], [dep], join_type, cond, schema, lib=lib).execute())
+    assert [(r[0], r[2], r[3]) for r in rows_of(out)] == SLT_EMP_DEPT[join_type]
+
+
+def test_empty_build_side_yields_nothing(lib):
+    """hash_join.rs:183-185: no left batch -> empty stream for every join type"""
+    right = t2()
+    schema = _join_schema(t1(), "t1", right, "t2", "Full")
+    cond = ex.JoinCondition([(InputRef(0, I64), InputRef(1, I64))])
+    for jt in ("Inner", "Left", "Right", "Full"):
+        assert ex.try_collect(ex.HashJoinExecutor([], [right], jt, cond, schema, lib=lib).execute()) == []
+
+
+# ---------------------------------------------------------------- evaluator
+def test_evaluator_input_ref_and_cast(lib):
+    """evaluator.rs:93-120"""
+    b = batch(["a", "b"], [1, 2, 3], [4, 5, 6], types=[pa.int32(), pa.int32()], nullable=False)
+    assert ex.eval_column(InputRef(1, I32), b, lib=lib).to_pylist() == [4, 5, 6]
+    from sqlrs_b200.host.expr import TypeCast
+
+    out = ex.eval_column(TypeCast(InputRef(0, I32), I64), b, lib=lib)
+    assert out.type == pa.int64() and out.to_pylist() == [1, 2, 3]
+
+
+# ---------------------------------------------------------------- oracle-only: Utf8 cases of the SLT files
+def test_slt_utf8_cases_oracle_only(oracle):
+    """aggregation.slt:13-17,28-34 (max(last_name); group by state with an empty-string key)"""
+    emp = pa.RecordBatch.from_arrays(
+        [pa.array([1, 2, 3, 4], pa.int64()), pa.array(["Hopkins", "Langford", "Travis", "Mill"]), pa.array(["CA", "CO", "CO", ""]),
+         pa.array([12000, 10000, 11500, None], pa.int64())], names=["id", "last_name", "state", "salary"])
+    U8 = ffi.DT_UTF8
+    out = ex.try_collect(ex.SimpleAggExecutor([AggFunc("Max", [InputRef(3, I64)]), AggFunc("Min", [InputRef(0, I64)]), AggFunc("Max", [InputRef(1, U8)])],
+                                              [emp], lib=oracle).execute())
+    assert rows_of(out) == [(12000, 1, "Travis")]
+    st, sal = InputRef(2, U8), InputRef(3, I64)
+    out = ex.try_collect(ex.HashAggExecutor([AggFunc("Count", [st]), AggFunc("Sum", [sal]), AggFunc("Max", [sal]), AggFunc("Min", [sal])], [st], [emp],
+                                            lib=oracle).execute())
+    assert rows_of(out) == [("CA", 1, 12000, 12000, 12000), ("CO", 2, 21500, 11500, 10000), ("", 1, N, N, N)]
