@@ -1,0 +1,79 @@
+"""The N>1 path on CPU: two gloo ranks, each aggregating its row shard with the CPU
+checker behind the same C ABI, partial groups exchanged all-to-all by key hash, merged by their owner,
+finalised on rank 0 — must equal the single-process result (first-appearance order included).
+The same host code (sqlrs_b200/host/distributed.py) runs over NCCL with the CUDA library in bench.py."""
+import os
+import sys
+
+import pyarrow as pa
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, plan_name, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+
+    from sqlrs_b200.host import distributed as sqdist
+    from sqlrs_b200.host import ffi, tpch
+    from sqlrs_b200.host.plan import ExecutorBuilder
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lib = ffi.Library(os.path.join(ROOT, "oracle", "liboracle.so"), "sqlrs_oracle_")
+    d = tpch.dims(0.02)
+    plan, schemas = tpch.q1_plan()
+    opts = lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    n = tpch.num_rows(lib, d, tpch.LINEITEM)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    shard = tpch.host_table(lib, d, tpch.LINEITEM, lo, hi, columns=tpch.Q1_COLUMNS)
+    p = ExecutorBuilder(lib, opts).build(plan, schemas)
+    p.push_table(0, shard.slice(0, shard.num_rows // 2))
+    p.push_table(0, shard.slice(shard.num_rows // 2))
+    group = sqdist.TorchGroup(dist, torch.device("cpu"))
+    result = sqdist.sharded_aggregate(p, group, lo)
+    if rank == 0:
+        whole = ExecutorBuilder(lib, opts).build(plan, schemas)
+        whole.push_table(0, tpch.host_table(lib, d, tpch.LINEITEM, columns=tpch.Q1_COLUMNS))
+        expect = whole.run()
+        from util import assert_batches_match
+
+        assert_batches_match(result, expect, rtol=1e-9)
+        assert result[0].num_rows == 8
+        open(os.path.join(out_dir, "ok"), "w").write("ok")
+    else:
+        assert result == []
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_two_rank_group_by_matches_single_process(tmp_path, oracle):
+    mp.spawn(_worker, args=(2, _free_port(), "q1", str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").read_text() == "ok"
+
+
+def test_partition_by_owner_is_a_partition():
+    sys.path.insert(0, ROOT)
+    import numpy as np
+
+    from sqlrs_b200.host import distributed as sqdist
+
+    h = np.array([0, 1, 2, 3, -1, -2, 2**63 - 1, -2**63], dtype=np.int64)
+    b = pa.RecordBatch.from_arrays([pa.array(h), pa.array(np.arange(len(h)))], names=["hash", "x"])
+    parts = sqdist.partition_by_owner(b, 3)
+    assert sum(p.num_rows for p in parts) == len(h)
+    for r, p in enumerate(parts):
+        assert all((int(v) % 2**64) % 3 == r for v in p.column(0).to_pylist())
