@@ -284,6 +284,15 @@ int SQLRS_API(plan_export_partials)(sqlrs_plan* p, struct ArrowArray* out, struc
 int SQLRS_API(plan_clear_partials)(sqlrs_plan* p);
 int SQLRS_API(plan_merge_partials)(sqlrs_plan* p, struct ArrowArray* partials, const struct ArrowSchema* schema);
 int SQLRS_API(plan_finish_partial)(sqlrs_plan* p);
+/* the same exchange without leaving HBM (what the NCCL path uses): partial groups packed row-major into
+ * caller-provided DEVICE memory on the plan's stream — (cap_rows + 1) rows of *n_words u64 each, row 0 =
+ * header {number of groups (may exceed cap_rows: then rows are missing and the caller must fall back to the
+ * host path)}, row 1+i = [hash, min_row, null mask, key bits..., accumulator words...] — and the merge of
+ * n_buffers such buffers laid out back to back (e.g. the output of an all-gather).  The oracle build returns
+ * SQLRS_ERR_UNSUPPORTED for the two _device calls. */
+int SQLRS_API(plan_partials_row_words)(sqlrs_plan* p, int32_t* n_words);
+int SQLRS_API(plan_export_partials_device)(sqlrs_plan* p, void* dst, int64_t cap_rows);
+int SQLRS_API(plan_merge_partials_device)(sqlrs_plan* p, const void* src, int32_t n_buffers, int64_t cap_rows);
 /* SQLRS_FLAG_TIMING: device time (ms, CUDA events on the plan's stream) the dominant scan kernel(s) of the
  * last plan_execute took, and how many launches that covers — bench.py's roofline numerator/denominator */
 double SQLRS_API(plan_scan_kernel_ms)(sqlrs_plan* p, int64_t* n_launches);

@@ -360,6 +360,18 @@ int sqlrs_oracle_plan_finish_partial(sqlrs_plan* p) {
     p->partial.reset();
   });
 }
+int sqlrs_oracle_plan_partials_row_words(sqlrs_plan*, int32_t*) {
+  g_last_error = "the oracle exchanges partials as host batches only";
+  return SQLRS_ERR_UNSUPPORTED;
+}
+int sqlrs_oracle_plan_export_partials_device(sqlrs_plan*, void*, int64_t) {
+  g_last_error = "the oracle exchanges partials as host batches only";
+  return SQLRS_ERR_UNSUPPORTED;
+}
+int sqlrs_oracle_plan_merge_partials_device(sqlrs_plan*, const void*, int32_t, int64_t) {
+  g_last_error = "the oracle exchanges partials as host batches only";
+  return SQLRS_ERR_UNSUPPORTED;
+}
 double sqlrs_oracle_plan_scan_kernel_ms(sqlrs_plan*, int64_t* n_launches) {
   if (n_launches) *n_launches = 0;
   return 0.0;

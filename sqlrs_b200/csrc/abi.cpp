@@ -287,6 +287,26 @@ int sqlrs_plan_merge_partials(sqlrs_plan* p, ArrowArray* partials, const ArrowSc
     p->impl.merge_partials(import_batch_host(p->impl.ctx(), partials, schema));
   });
 }
+int sqlrs_plan_partials_row_words(sqlrs_plan* p, int32_t* n_words) {
+  return guarded([&] {
+    if (!p || !n_words) fail(SQLRS_ERR_INVALID_ARG, "plan / n_words is NULL");
+    *n_words = p->impl.partial_row_words();
+  });
+}
+int sqlrs_plan_export_partials_device(sqlrs_plan* p, void* dst, int64_t cap_rows) {
+  return guarded([&] {
+    if (!p || !dst) fail(SQLRS_ERR_INVALID_ARG, "plan / dst is NULL");
+    p->impl.ctx().activate();
+    p->impl.export_partials_device((uint64_t*)dst, cap_rows);
+  });
+}
+int sqlrs_plan_merge_partials_device(sqlrs_plan* p, const void* src, int32_t n_buffers, int64_t cap_rows) {
+  return guarded([&] {
+    if (!p || !src) fail(SQLRS_ERR_INVALID_ARG, "plan / src is NULL");
+    p->impl.ctx().activate();
+    p->impl.merge_partials_device((const uint64_t*)src, n_buffers, cap_rows);
+  });
+}
 int sqlrs_plan_finish_partial(sqlrs_plan* p) {
   return guarded([&] {
     if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");

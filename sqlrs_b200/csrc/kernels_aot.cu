@@ -213,19 +213,22 @@ __global__ void __launch_bounds__(kBlock) k_idx_valid(const int64_t* __restrict_
 }
 
 // ------------------------------------------------------------------ group table maintenance
-__global__ void __launch_bounds__(kBlock) k_table_compact(TableView t, int n_keys, int n_acc, uint64_t* out_hash, uint64_t* out_min_row,
-                                                           uint64_t* out_keys, uint32_t* out_knull, uint64_t* out_acc, uint32_t max_out,
-                                                           uint32_t* out_count) {
+// Packed (row-major) form of a group table, used for finalisation and for the partial/final exchange:
+// row 0 = header {number of groups, words per row, 0...}; row 1+i = [hash, min_row, knull, key bits x K,
+// accumulator words x W].  Rows land in arbitrary order (the consumer orders by min_row).
+__global__ void __launch_bounds__(kBlock) k_table_pack(TableView t, int n_keys, int n_acc, uint64_t* __restrict__ dst, unsigned long long cap_rows) {
   const uint32_t stride = gridDim.x * blockDim.x;
+  const int words = 3 + n_keys + n_acc;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
     if (t.state[s] != 2u) continue;
-    const uint32_t o = atomicAdd(out_count, 1u);
-    if (o >= max_out) continue;
-    out_hash[o] = t.hash[s];
-    out_min_row[o] = t.min_row[s];
-    out_knull[o] = t.knull[s];
-    for (int k = 0; k < n_keys; k++) out_keys[(size_t)k * max_out + o] = t.keys[(size_t)k * t.capacity + s];
-    for (int w = 0; w < n_acc; w++) out_acc[(size_t)w * max_out + o] = t.acc[(size_t)w * t.capacity + s];
+    const unsigned long long o = atomicAdd((unsigned long long*)dst, 1ULL);
+    if (o >= cap_rows) continue;  // header keeps counting: the consumer sees count > capacity
+    uint64_t* row = dst + (size_t)(1 + o) * words;
+    row[0] = t.hash[s];
+    row[1] = t.min_row[s];
+    row[2] = t.knull[s];
+    for (int k = 0; k < n_keys; k++) row[3 + k] = t.keys[(size_t)k * t.capacity + s];
+    for (int w = 0; w < n_acc; w++) row[3 + n_keys + w] = t.acc[(size_t)w * t.capacity + s];
   }
 }
 
@@ -253,18 +256,24 @@ __global__ void __launch_bounds__(kBlock) k_table_rehash(TableView from, TableVi
   }
 }
 
-// partial -> final merge (multi-GPU group-by): every partial row is a distinct group of
-// its producer; find-or-insert it here and fold its accumulator words in with the word's operator.
-// ops[w]: 0 add u64, 1 add f64, 2 min i64, 3 max i64.
-__global__ void __launch_bounds__(kBlock) k_table_merge(TableView t, int n_keys, int n_acc, const int* __restrict__ ops, int match_keys,
-                                                         const uint64_t* __restrict__ hash, const uint64_t* __restrict__ min_row,
-                                                         const uint32_t* __restrict__ knull, const uint64_t* __restrict__ keys,
-                                                         const uint64_t* __restrict__ acc, int64_t n) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+// partial -> final merge (multi-GPU group-by; also batches of host partials): n_bufs packed
+// buffers of (cap_rows + 1) rows each; every row is a distinct group of its producer — find-or-insert it
+// and fold its accumulator words in with the word's operator.  ops[w]: 0 add u64, 1 add f64, 2 min i64, 3 max i64.
+__global__ void __launch_bounds__(kBlock) k_table_merge_packed(TableView t, int n_keys, int n_acc, const int* __restrict__ ops, int match_keys,
+                                                                const uint64_t* __restrict__ src, int n_bufs, unsigned long long cap_rows) {
+  const int words = 3 + n_keys + n_acc;
   const uint32_t mask = t.capacity - 1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint64_t h = hash[i];
-    const uint32_t kn = knull[i];
+  const int64_t per_buf = (int64_t)cap_rows;
+  const int64_t total = per_buf * n_bufs;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+    const int b = (int)(j / per_buf);
+    const int64_t i = j % per_buf;
+    const uint64_t* buf = src + (size_t)b * (size_t)(cap_rows + 1) * words;
+    if ((unsigned long long)i >= buf[0]) continue;
+    const uint64_t* row = buf + (size_t)(1 + i) * words;
+    const uint64_t h = row[0];
+    const uint32_t kn = (uint32_t)row[2];
     uint32_t s = mix32(h) & mask;
     int slot = -1;
     for (uint32_t probes = 0; probes <= mask;) {
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(kBlock) k_table_merge(TableView t, int n_keys,
       if (st == 0u) {
         if (atomicCAS(&t.state[s], 0u, 1u) == 0u) {
           t.hash[s] = h;
-          for (int k = 0; k < n_keys; k++) t.keys[(size_t)k * t.capacity + s] = keys[(size_t)k * n + i];
+          for (int k = 0; k < n_keys; k++) t.keys[(size_t)k * t.capacity + s] = row[3 + k];
           t.knull[s] = kn;
           __threadfence();
           atomicExch(&t.state[s], 2u);
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(kBlock) k_table_merge(TableView t, int n_keys,
         bool same = true;
         if (match_keys) {
           same = *((volatile uint32_t*)&t.knull[s]) == kn;
-          for (int k = 0; same && k < n_keys; k++) same = *((volatile uint64_t*)&t.keys[(size_t)k * t.capacity + s]) == keys[(size_t)k * n + i];
+          for (int k = 0; same && k < n_keys; k++) same = *((volatile uint64_t*)&t.keys[(size_t)k * t.capacity + s]) == row[3 + k];
         }
         if (same) {
           slot = (int)s;
@@ -303,16 +312,16 @@ __global__ void __launch_bounds__(kBlock) k_table_merge(TableView t, int n_keys,
       continue;
     }
     // first-appearance order: the smaller global row id wins; with hash-only identity its keys win too
-    const unsigned long long old = atomicMin((unsigned long long*)&t.min_row[slot], (unsigned long long)min_row[i]);
-    if (!match_keys && min_row[i] < old) {
-      for (int k = 0; k < n_keys; k++) t.keys[(size_t)k * t.capacity + slot] = keys[(size_t)k * n + i];
+    const unsigned long long old = atomicMin((unsigned long long*)&t.min_row[slot], (unsigned long long)row[1]);
+    if (!match_keys && row[1] < old) {
+      for (int k = 0; k < n_keys; k++) t.keys[(size_t)k * t.capacity + slot] = row[3 + k];
       t.knull[slot] = kn;
     }
     for (int w = 0; w < n_acc; w++) {
-      const uint64_t x = acc[(size_t)w * n + i];
+      const uint64_t x = row[3 + n_keys + w];
       uint64_t* p = &t.acc[(size_t)w * t.capacity + slot];
       switch (ops[w]) {
-        case 0: atomicAdd((unsigned long long*)p, (unsigned long long)x); break;
+        case 0: if (x) atomicAdd((unsigned long long*)p, (unsigned long long)x); break;
         case 1: atomicAdd((double*)p, __longlong_as_double((long long)x)); break;
         case 2: atomicMin((long long*)p, (long long)x); break;
         case 3: atomicMax((long long*)p, (long long)x); break;
@@ -323,11 +332,10 @@ __global__ void __launch_bounds__(kBlock) k_table_merge(TableView t, int n_keys,
 
 }  // namespace
 
-void launch_table_merge(const TableView& t, int n_keys, int n_acc, const int* ops, int match_keys, const uint64_t* hash,
-                        const uint64_t* min_row, const uint32_t* knull, const uint64_t* keys, const uint64_t* acc, int64_t n,
-                        cudaStream_t stream) {
-  if (n <= 0) return;
-  k_table_merge<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, ops, match_keys, hash, min_row, knull, keys, acc, n);
+void launch_table_merge_packed(const TableView& t, int n_keys, int n_acc, const int* ops, int match_keys, const uint64_t* src, int n_bufs,
+                               uint64_t cap_rows, cudaStream_t stream) {
+  if (n_bufs <= 0 || cap_rows == 0) return;
+  k_table_merge_packed<<<grid_for((int64_t)cap_rows * n_bufs, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, ops, match_keys, src, n_bufs, cap_rows);
   count_launch();
   SQ_CUDA(cudaGetLastError());
 }
@@ -401,10 +409,8 @@ void launch_iota_filter_valid(const int64_t* idx, int64_t m, uint32_t* valid_out
   SQ_CUDA(cudaGetLastError());
 }
 
-void launch_table_compact(const TableView& t, int n_keys, int n_acc, uint64_t* out_hash, uint64_t* out_min_row, uint64_t* out_keys,
-                          uint32_t* out_knull, uint64_t* out_acc, uint32_t max_out, uint32_t* out_count, cudaStream_t stream) {
-  k_table_compact<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, out_hash, out_min_row, out_keys, out_knull,
-                                                                                 out_acc, max_out, out_count);
+void launch_table_pack(const TableView& t, int n_keys, int n_acc, uint64_t* dst, uint64_t cap_rows, cudaStream_t stream) {
+  k_table_pack<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, dst, cap_rows);
   count_launch();
   SQ_CUDA(cudaGetLastError());
 }

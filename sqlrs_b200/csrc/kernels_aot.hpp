@@ -45,14 +45,14 @@ struct TableView {
   uint32_t* counters;
   uint32_t capacity;
 };
-// dense copy of the occupied slots: out arrays sized by the group count; *out_count (device u32, zeroed)
-void launch_table_compact(const TableView& t, int n_keys, int n_acc, uint64_t* out_hash, uint64_t* out_min_row, uint64_t* out_keys,
-                          uint32_t* out_knull, uint64_t* out_acc, uint32_t max_out, uint32_t* out_count, cudaStream_t stream);
-// partial -> final merge: n partial groups (SoA: keys [K][n], acc [W][n]) folded into `t`; ops[w] (device):
+// Packed row-major form of a group table: row 0 = header {group count, ...}, row 1+i =
+// [hash, min_row, knull, key bits x K, accumulator words x W] (3+K+W u64 words per row).
+// dst must hold (cap_rows + 1) rows and have its header zeroed; groups beyond cap_rows are counted, not written.
+void launch_table_pack(const TableView& t, int n_keys, int n_acc, uint64_t* dst, uint64_t cap_rows, cudaStream_t stream);
+// partial -> final merge of n_bufs packed buffers ((cap_rows + 1) rows each) into `t`; ops[w] (device):
 // 0 add u64, 1 add f64, 2 min i64, 3 max i64
-void launch_table_merge(const TableView& t, int n_keys, int n_acc, const int* ops, int match_keys, const uint64_t* hash,
-                        const uint64_t* min_row, const uint32_t* knull, const uint64_t* keys, const uint64_t* acc, int64_t n,
-                        cudaStream_t stream);
+void launch_table_merge_packed(const TableView& t, int n_keys, int n_acc, const int* ops, int match_keys, const uint64_t* src, int n_bufs,
+                               uint64_t cap_rows, cudaStream_t stream);
 // re-insert every occupied slot of `from` into the (empty, initialised) table `to`
 void launch_table_rehash(const TableView& from, const TableView& to, int n_keys, int n_acc, cudaStream_t stream);
 

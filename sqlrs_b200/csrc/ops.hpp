@@ -100,6 +100,10 @@ class AggOp {
   void export_partials(ArrowArray* out, ArrowSchema* out_schema);
   void clear_partials();
   void merge_partials(const DBatch& partials);
+  int partial_row_words() const;  // u64 words per packed partial row: 3 + keys + accumulator words
+  void export_partials_device(uint64_t* dst, int64_t cap_rows);
+  void merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows);
+  void reset();  // forget all groups, keep compiled kernels and buffers
   void set_row_base(int64_t first_global_row) { rows_seen_ = first_global_row; }
 
  private:
@@ -107,6 +111,10 @@ class AggOp {
   struct Table;
   Compiled& compiled_for(const DBatch& batch);
   std::string generate(const std::vector<ColInfo>& cols, Compiled& comp);
+  void init_table_contents(Table& t);
+  void read_counters(uint32_t* out4);
+  void check_partial_supported() const;
+  const int* device_word_ops();
   void ensure_table(uint32_t min_capacity);
   void grow_table(uint32_t min_capacity);
   void build_output(std::vector<Field>* fields, struct HostGroups* groups);
@@ -123,6 +131,10 @@ class AggOp {
   int64_t rows_seen_ = 0, batches_seen_ = 0;
   bool seen_batch_ = false;
   bool use_global_ = false;
+  uint32_t groups_known_ = 0;   // exact group count at the last counter read
+  uint64_t groups_bound_ = 0;   // host-side upper bound since then
+  size_t part_entries_ = 0;     // CTA-partial scratch of sq_agg_small
+  BufPtr p_state_, p_hash_, p_min_, p_keys_, p_knull_, p_acc_, d_ops_;
   std::vector<int> key_dtypes_;
   std::string last_path_;
   double scan_kernel_ms_ = 0;      // SQLRS_FLAG_TIMING: device time of the scan kernels (CUDA events on ctx_.stream)

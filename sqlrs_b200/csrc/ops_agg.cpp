@@ -354,6 +354,20 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
 std::string AggOp::describe() const { return last_path_; }
 
 // ------------------------------------------------------------------ table
+// counters: [0] groups, [1] new-slot list length, [2] status bits, [3] error flag (divide by zero)
+void AggOp::init_table_contents(Table& t) {
+  const Compiled& c = *cache_.begin()->second;
+  const size_t cap = t.capacity;
+  SQ_CUDA(cudaMemsetAsync(t.state->p, 0, cap * 4, ctx_.stream));
+  SQ_CUDA(cudaMemsetAsync(t.min_row->p, 0xff, cap * 8, ctx_.stream));
+  SQ_CUDA(cudaMemsetAsync(t.counters->p, 0, 16, ctx_.stream));
+  for (int w = 0; w < t.n_acc; w++) {
+    uint64_t ident = word_identity(c.words[w].op);
+    if (ident == 0) SQ_CUDA(cudaMemsetAsync((uint64_t*)t.acc->p + (size_t)w * cap, 0, cap * 8, ctx_.stream));
+    else launch_fill_u64((uint64_t*)t.acc->p + (size_t)w * cap, (int64_t)cap, ident, ctx_.stream);
+  }
+}
+
 void AggOp::ensure_table(uint32_t min_capacity) {
   if (table_ && table_->capacity >= min_capacity) return;
   grow_table(min_capacity);
@@ -366,27 +380,49 @@ void AggOp::grow_table(uint32_t min_capacity) {
   t->n_keys = (int)c.key_dtypes.size();
   t->n_acc = (int)c.words.size();
   const size_t cap = t->capacity;
-  t->state = dev_alloc_zero(ctx_, cap * 4);
+  t->state = dev_alloc(ctx_, cap * 4);
   t->hash = dev_alloc(ctx_, cap * 8);
   t->min_row = dev_alloc(ctx_, cap * 8);
   t->keys = dev_alloc_zero(ctx_, cap * 8 * std::max(t->n_keys, 1));
   t->knull = dev_alloc_zero(ctx_, cap * 4);
   t->acc = dev_alloc(ctx_, cap * 8 * std::max(t->n_acc, 1));
   t->new_slots = dev_alloc(ctx_, cap * 4);
-  t->counters = dev_alloc_zero(ctx_, 16);
-  SQ_CUDA(cudaMemsetAsync(t->min_row->p, 0xff, cap * 8, ctx_.stream));
-  for (int w = 0; w < t->n_acc; w++) {
-    uint64_t ident = word_identity(c.words[w].op);
-    if (ident == 0) SQ_CUDA(cudaMemsetAsync((uint64_t*)t->acc->p + (size_t)w * cap, 0, cap * 8, ctx_.stream));
-    else launch_fill_u64((uint64_t*)t->acc->p + (size_t)w * cap, (int64_t)cap, ident, ctx_.stream);
-  }
+  t->counters = dev_alloc(ctx_, 16);
+  init_table_contents(*t);
   if (table_) {
     launch_table_rehash(table_->view(), t->view(), t->n_keys, t->n_acc, ctx_.stream);
-    // carry the counters: groups, pending new-slot list is dropped (fix-up ran before any growth), status
+    // carry the counters (the pending new-slot list is flushed before any growth)
     SQ_CUDA(cudaMemcpyAsync(t->counters->p, table_->counters->p, 4, cudaMemcpyDeviceToDevice, ctx_.stream));
-    SQ_CUDA(cudaMemcpyAsync((uint32_t*)t->counters->p + 2, (uint32_t*)table_->counters->p + 2, 4, cudaMemcpyDeviceToDevice, ctx_.stream));
+    SQ_CUDA(cudaMemcpyAsync((uint32_t*)t->counters->p + 2, (uint32_t*)table_->counters->p + 2, 8, cudaMemcpyDeviceToDevice, ctx_.stream));
   }
   table_ = std::move(t);
+}
+
+// forget all groups but keep the compiled kernels and the device buffers (repeated plan runs)
+void AggOp::reset() {
+  ctx_.activate();
+  if (table_) init_table_contents(*table_);
+  rows_seen_ = 0;
+  batches_seen_ = 0;
+  seen_batch_ = false;
+  use_global_ = false;
+  groups_known_ = 0;
+  groups_bound_ = 0;
+  scan_kernel_ms_ = 0;
+  scan_kernel_launches_ = 0;
+}
+
+// one D2H of the 4 counters; raises what the kernels flagged
+void AggOp::read_counters(uint32_t* out4) {
+  SQ_CUDA(cudaMemcpyAsync(out4, table_->counters->p, 16, cudaMemcpyDeviceToHost, ctx_.stream));
+  SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+  groups_known_ = out4[0];
+  groups_bound_ = out4[0];
+  if (out4[2] & 2u) fail(SQLRS_ERR_INTERNAL, "group table overflow (internal sizing error)");
+  if (out4[3] & 1u) {
+    SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 3, 0, 4, ctx_.stream));
+    fail(SQLRS_ERR_ARROW, "Divide by zero error (aggregate argument)");
+  }
 }
 
 // ------------------------------------------------------------------ push
@@ -403,19 +439,13 @@ void AggOp::push(const DBatch& batch) {
   if (n == 0) return;
   if (n >= (1LL << 32)) fail(SQLRS_ERR_INVALID_ARG, "a batch may hold fewer than 2^32 rows (reference index width, hash_agg.rs:109)");
   const int K = (int)c.key_dtypes.size();
-  BufPtr err = dev_alloc_zero(ctx_, 4);
-  void* errp = err->p;
-  uint32_t host_counters[4] = {0, 0, 0, 0};
-  auto read_counters = [&]() {
-    SQ_CUDA(cudaMemcpyAsync(host_counters, table_->counters->p, 12, cudaMemcpyDeviceToHost, ctx_.stream));
-    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
-    if (host_counters[2] & 2u) fail(SQLRS_ERR_INTERNAL, "group table overflow (internal sizing error)");
-  };
+  const size_t W = c.words.size();
+  uint32_t hc[4] = {0, 0, 0, 0};
   // key fix-up for the groups that appeared since the last flush (hash-only identity: the reference
   // reports the keys of a group's FIRST row), then reset the list.  Must run before the table is
   // re-hashed (slot numbers change) and at the end of every batch (the rows are gone afterwards).
   auto flush_new_slots = [&]() {
-    const uint32_t n_new = host_counters[1];
+    const uint32_t n_new = hc[1];
     if (n_new == 0 || !table_) return;
     if (K > 0 && opt_.match_mode == SQLRS_MATCH_HASH_ONLY) {
       SqInBlob in_all(batch, 0);
@@ -426,28 +456,41 @@ void AggOp::push(const DBatch& batch) {
       jit_launch(c.fixkeys, (unsigned)div_up(n_new, 128), 128, 0, ctx_.stream, fargs);
     }
     SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 1, 0, 4, ctx_.stream));
-    host_counters[1] = 0;
+    hc[1] = 0;
   };
-  uint32_t groups_before = 0;
-  if (table_) {
-    read_counters();
-    groups_before = host_counters[0];
-  }
+  // capacity for `extra` more groups; only syncs when the host-side bound says the table might not hold them
+  auto reserve = [&](uint64_t extra) {
+    if (!table_) {
+      ensure_table((uint32_t)std::min<uint64_t>(2ULL * extra + 1024, 1ULL << 31));
+    } else if (2ULL * (groups_bound_ + extra) + 1024 > table_->capacity) {
+      read_counters(hc);  // exact count instead of the bound
+      flush_new_slots();
+      ensure_table((uint32_t)std::min<uint64_t>(2ULL * (groups_known_ + extra) + 1024, 1ULL << 31));
+    }
+    groups_bound_ += extra;
+  };
 
   bool done = false;
   if (!use_global_ && c.small_ok) {
     const int grid = (int)std::min<int64_t>(c.small_grid, std::max<int64_t>(1, div_up(n, (int64_t)c.block * c.unroll)));
     const size_t entries = (size_t)grid * c.slots;
-    ensure_table((uint32_t)std::min<uint64_t>(2ULL * (groups_before + entries) + 1024, 1ULL << 31));
-    BufPtr p_state = dev_alloc(ctx_, entries * 4), p_hash = dev_alloc(ctx_, entries * 8), p_min = dev_alloc(ctx_, entries * 8);
-    BufPtr p_keys = dev_alloc(ctx_, entries * 8 * std::max(K, 1)), p_knull = dev_alloc(ctx_, entries * 4);
-    BufPtr p_acc = dev_alloc(ctx_, entries * 8 * std::max<size_t>(c.words.size(), 1));
+    reserve(entries);
+    if (part_entries_ < entries) {  // CTA-partial scratch, kept across batches
+      p_state_ = dev_alloc(ctx_, entries * 4);
+      p_hash_ = dev_alloc(ctx_, entries * 8);
+      p_min_ = dev_alloc(ctx_, entries * 8);
+      p_keys_ = dev_alloc(ctx_, entries * 8 * std::max(K, 1));
+      p_knull_ = dev_alloc(ctx_, entries * 4);
+      p_acc_ = dev_alloc(ctx_, entries * 8 * std::max<size_t>(W, 1));
+      part_entries_ = entries;
+    }
     struct {
       void *state, *hash, *min_row, *keys, *knull, *acc;
-    } part = {p_state->p, p_hash->p, p_min->p, p_keys->p, p_knull->p, p_acc->p};
+    } part = {p_state_->p, p_hash_->p, p_min_->p, p_keys_->p, p_knull_->p, p_acc_->p};
     SqInBlob in(batch, 0);
     int64_t n_arg = n, rb = row_base, bn = batch_no;
     void* status = (uint32_t*)table_->counters->p + 2;
+    void* errp = (uint32_t*)table_->counters->p + 3;
     TableView tv = table_->view();
     int n_entries = (int)entries;
     void* args_small[] = {in.ptr(), &n_arg, &rb, &part, &status, &errp};
@@ -456,14 +499,12 @@ void AggOp::push(const DBatch& batch) {
     timer.stop();
     void* args_merge[] = {&part, &n_entries, &tv, &bn, &status};
     jit_launch(c.merge, (unsigned)div_up(n_entries, 128), 128, 0, ctx_.stream, args_merge);
-    read_counters();
+    read_counters(hc);
     scan_kernel_ms_ += timer.elapsed_ms();
     scan_kernel_launches_ += timer.enabled ? 1 : 0;
-    if (host_counters[2] & 1u) {
+    if (hc[2] & 1u) {
       use_global_ = true;  // more groups than the shared-memory path holds: this and later batches use the HBM table
-      uint32_t zero = 0;
-      SQ_CUDA(cudaMemcpyAsync((uint32_t*)table_->counters->p + 2, &zero, 4, cudaMemcpyHostToDevice, ctx_.stream));
-      SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+      SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 2, 0, 4, ctx_.stream));
     } else {
       done = true;
       last_path_ = "sq_agg_small (private shared-memory accumulators, " + std::to_string(c.slots) + " slots x " + std::to_string(c.block) +
@@ -475,16 +516,11 @@ void AggOp::push(const DBatch& batch) {
     const int64_t chunk = 1LL << 22;
     for (int64_t start = 0; start < n; start += chunk) {
       const int64_t len = std::min(chunk, n - start);
-      uint32_t groups_now = 0;
-      if (table_) {
-        read_counters();
-        groups_now = host_counters[0];
-        flush_new_slots();
-      }
-      ensure_table((uint32_t)std::min<uint64_t>(2ULL * ((uint64_t)groups_now + (uint64_t)len) + 1024, 1ULL << 31));
+      reserve((uint64_t)len);
       SqInBlob in(batch, start);
       int64_t n_arg = len, rb = row_base + start, bn = batch_no;
       void* status = (uint32_t*)table_->counters->p + 2;
+      void* errp = (uint32_t*)table_->counters->p + 3;
       TableView tv = table_->view();
       void* args[] = {in.ptr(), &n_arg, &rb, &tv, &bn, &status, &errp};
       const int sms = device_sm_count(ctx_.device);
@@ -498,44 +534,43 @@ void AggOp::push(const DBatch& batch) {
         scan_kernel_launches_++;
       }
     }
-    read_counters();
+    read_counters(hc);
     last_path_ = "sq_agg_global (open-addressed table in HBM, capacity " + std::to_string(table_->capacity) + ")";
   }
-  read_counters();
   flush_new_slots();
-  check_error_flag(ctx_, err, "aggregate argument");
 }
 
 // ------------------------------------------------------------------ finish
+// the group table -> host, through ONE packed buffer and one synchronisation
 void AggOp::build_output(std::vector<Field>* fields, HostGroups* g) {
   if (!seen_batch_) fail(SQLRS_ERR_INTERNAL, "called `Option::unwrap()` on a `None` value (no input batch)");
   ctx_.activate();
   const Compiled& c = *cache_.begin()->second;
   const int K = (int)c.key_dtypes.size(), W = (int)c.words.size();
   g->n = 0;
-  if (table_) {
-    uint32_t counters[4] = {0, 0, 0, 0};
-    SQ_CUDA(cudaMemcpyAsync(counters, table_->counters->p, 12, cudaMemcpyDeviceToHost, ctx_.stream));
-    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
-    const uint32_t n = counters[0];
-    if (n > 0) {
-      BufPtr d_hash = dev_alloc(ctx_, (size_t)n * 8), d_min = dev_alloc(ctx_, (size_t)n * 8);
-      BufPtr d_keys = dev_alloc(ctx_, (size_t)n * 8 * std::max(K, 1)), d_knull = dev_alloc(ctx_, (size_t)n * 4);
-      BufPtr d_acc = dev_alloc(ctx_, (size_t)n * 8 * std::max(W, 1)), d_cnt = dev_alloc_zero(ctx_, 4);
-      launch_table_compact(table_->view(), K, W, (uint64_t*)d_hash->p, (uint64_t*)d_min->p, (uint64_t*)d_keys->p, (uint32_t*)d_knull->p,
-                           (uint64_t*)d_acc->p, n, (uint32_t*)d_cnt->p, ctx_.stream);
-      g->n = n;
-      g->hash.resize(n);
-      g->min_row.resize(n);
-      g->keys.resize((size_t)n * std::max(K, 1));
-      g->knull.resize(n);
-      g->acc.resize((size_t)n * std::max(W, 1));
-      SQ_CUDA(cudaMemcpyAsync(g->hash.data(), d_hash->p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx_.stream));
-      SQ_CUDA(cudaMemcpyAsync(g->min_row.data(), d_min->p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx_.stream));
-      if (K) SQ_CUDA(cudaMemcpyAsync(g->keys.data(), d_keys->p, (size_t)n * 8 * K, cudaMemcpyDeviceToHost, ctx_.stream));
-      SQ_CUDA(cudaMemcpyAsync(g->knull.data(), d_knull->p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx_.stream));
-      if (W) SQ_CUDA(cudaMemcpyAsync(g->acc.data(), d_acc->p, (size_t)n * 8 * W, cudaMemcpyDeviceToHost, ctx_.stream));
-      ctx_.sync();
+  if (table_ && groups_known_ > 0) {
+    const uint32_t n = groups_known_;  // exact: every push / merge ends with a counter read
+    const int words = 3 + K + W;
+    BufPtr packed = dev_alloc(ctx_, (size_t)(n + 1) * words * 8);
+    SQ_CUDA(cudaMemsetAsync(packed->p, 0, (size_t)words * 8, ctx_.stream));
+    launch_table_pack(table_->view(), K, W, (uint64_t*)packed->p, n, ctx_.stream);
+    std::vector<uint64_t> host((size_t)(n + 1) * words);
+    SQ_CUDA(cudaMemcpyAsync(host.data(), packed->p, host.size() * 8, cudaMemcpyDeviceToHost, ctx_.stream));
+    ctx_.sync();
+    if (host[0] != n) fail(SQLRS_ERR_INTERNAL, "group count changed under finalisation");
+    g->n = n;
+    g->hash.resize(n);
+    g->min_row.resize(n);
+    g->keys.resize((size_t)n * std::max(K, 1));
+    g->knull.resize(n);
+    g->acc.resize((size_t)n * std::max(W, 1));
+    for (uint32_t i = 0; i < n; i++) {
+      const uint64_t* row = host.data() + (size_t)(1 + i) * words;
+      g->hash[i] = row[0];
+      g->min_row[i] = row[1];
+      g->knull[i] = (uint32_t)row[2];
+      for (int k = 0; k < K; k++) g->keys[(size_t)k * n + i] = row[3 + k];
+      for (int w = 0; w < W; w++) g->acc[(size_t)w * n + i] = row[3 + K + w];
     }
   }
   fields->clear();
@@ -636,13 +671,23 @@ void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
 DBatch AggOp::finish_device() { fail(SQLRS_ERR_UNSUPPORTED, "aggregate results are produced on the host"); }
 
 // ------------------------------------------------------------------ partial / final (multi-GPU)
-// The un-finalised group table as a host batch: [hash i64, min_row i64, knull i32, key bits i64 x K,
-// accumulator words i64 x W].  Column 0 is the group identity the exchange radix-partitions on.
-void AggOp::export_partials(ArrowArray* out, ArrowSchema* out_schema) {
+void AggOp::check_partial_supported() const {
   if (opt_.count_mode == SQLRS_COUNT_REFERENCE_OVERWRITE)
     for (const AggSpec& a : aggs_)
       if (a.func == SQLRS_AGG_COUNT)
         fail(SQLRS_ERR_UNSUPPORTED, "partial/final COUNT needs SQLRS_COUNT_SQL_ACCUMULATE (the overwrite quirk K1 is defined on one batch stream)");
+}
+
+int AggOp::partial_row_words() const {
+  if (cache_.empty()) fail(SQLRS_ERR_INVALID_ARG, "no batch aggregated yet (accumulator layout unknown)");
+  const Compiled& c = *cache_.begin()->second;
+  return 3 + (int)c.key_dtypes.size() + (int)c.words.size();
+}
+
+// The un-finalised group table as a host batch: [hash i64, min_row i64, knull i32, key bits i64 x K,
+// accumulator words i64 x W].  Column 0 is the group identity the exchange radix-partitions on.
+void AggOp::export_partials(ArrowArray* out, ArrowSchema* out_schema) {
+  check_partial_supported();
   std::vector<Field> fields;
   HostGroups g;
   build_output(&fields, &g);
@@ -672,31 +717,28 @@ void AggOp::export_partials(ArrowArray* out, ArrowSchema* out_schema) {
   export_host_columns(pf, cols, n, out, out_schema);
 }
 
-void AggOp::clear_partials() {
+// the same, packed row-major, written into caller-provided DEVICE memory on the operator's stream
+// (no host round trip): (cap_rows + 1) rows of partial_row_words() u64; row 0 = header {group count}
+void AggOp::export_partials_device(uint64_t* dst, int64_t cap_rows) {
+  check_partial_supported();
+  if (!seen_batch_) fail(SQLRS_ERR_INTERNAL, "called `Option::unwrap()` on a `None` value (no input batch)");
   ctx_.activate();
-  table_.reset();
-  use_global_ = false;
+  const int words = partial_row_words();
+  SQ_CUDA(cudaMemsetAsync(dst, 0, (size_t)words * 8, ctx_.stream));
+  if (table_ && cap_rows > 0) launch_table_pack(table_->view(), table_->n_keys, table_->n_acc, dst, (uint64_t)cap_rows, ctx_.stream);
 }
 
-// folds a batch of partial groups (layout of export_partials, device resident) into the table
-void AggOp::merge_partials(const DBatch& p) {
+void AggOp::clear_partials() {
   ctx_.activate();
-  if (cache_.empty()) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before any batch was aggregated (accumulator layout unknown)");
+  if (table_) init_table_contents(*table_);
+  use_global_ = false;
+  groups_known_ = 0;
+  groups_bound_ = 0;
+}
+
+const int* AggOp::device_word_ops() {
+  if (d_ops_) return (const int*)d_ops_->p;
   const Compiled& c = *cache_.begin()->second;
-  const int K = (int)c.key_dtypes.size(), W = (int)c.words.size();
-  if ((int)p.cols.size() != 3 + K + W) fail(SQLRS_ERR_INVALID_ARG, "partials batch has the wrong number of columns");
-  for (size_t k = 0; k < p.cols.size(); k++)
-    if (p.cols[k].dtype != (k == 2 ? SQLRS_DT_INT32 : SQLRS_DT_INT64) || p.cols[k].valid)
-      fail(SQLRS_ERR_INVALID_ARG, "partials batch has the wrong column types");
-  const int64_t n = p.n;
-  seen_batch_ = true;
-  if (n == 0) return;
-  uint32_t groups_now = 0;
-  if (table_) {
-    SQ_CUDA(cudaMemcpyAsync(&groups_now, table_->counters->p, 4, cudaMemcpyDeviceToHost, ctx_.stream));
-    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
-  }
-  ensure_table((uint32_t)std::min<uint64_t>(2ULL * ((uint64_t)groups_now + (uint64_t)n) + 1024, 1ULL << 31));
   std::vector<int> ops;
   for (const WordPlan& w : c.words) {
     switch (w.op) {
@@ -707,19 +749,57 @@ void AggOp::merge_partials(const DBatch& p) {
       default: fail(SQLRS_ERR_UNSUPPORTED, "partial/final COUNT needs SQLRS_COUNT_SQL_ACCUMULATE");
     }
   }
-  BufPtr d_ops = dev_alloc(ctx_, std::max<size_t>(ops.size(), 1) * 4);
-  if (!ops.empty()) SQ_CUDA(cudaMemcpyAsync(d_ops->p, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice, ctx_.stream));
-  // gather the K key columns / W word columns into [K][n] / [W][n] blocks
-  BufPtr d_keys = dev_alloc(ctx_, (size_t)std::max(K, 1) * n * 8), d_acc = dev_alloc(ctx_, (size_t)std::max(W, 1) * n * 8);
-  for (int k = 0; k < K; k++)
-    SQ_CUDA(cudaMemcpyAsync((uint64_t*)d_keys->p + (size_t)k * n, p.cols[3 + k].data, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx_.stream));
-  for (int w = 0; w < W; w++)
-    SQ_CUDA(cudaMemcpyAsync((uint64_t*)d_acc->p + (size_t)w * n, p.cols[3 + K + w].data, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx_.stream));
-  launch_table_merge(table_->view(), K, W, (const int*)d_ops->p, opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY ? 1 : 0,
-                     (const uint64_t*)p.cols[0].data, (const uint64_t*)p.cols[1].data, (const uint32_t*)p.cols[2].data,
-                     (const uint64_t*)d_keys->p, (const uint64_t*)d_acc->p, n, ctx_.stream);
-  SQ_CUDA(cudaStreamSynchronize(ctx_.stream));  // `ops` (pageable) and the staging buffers stay alive until here
-  SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 1, 0, 4, ctx_.stream));
+  d_ops_ = dev_alloc(ctx_, std::max<size_t>(ops.size(), 1) * 4);
+  if (!ops.empty()) {
+    SQ_CUDA(cudaMemcpyAsync(d_ops_->p, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));  // `ops` is a stack vector
+  }
+  return (const int*)d_ops_->p;
+}
+
+// folds n_bufs packed partial buffers (device memory, layout of export_partials_device) into the table
+void AggOp::merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows) {
+  ctx_.activate();
+  if (cache_.empty()) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before any batch was aggregated (accumulator layout unknown)");
+  seen_batch_ = true;
+  if (n_bufs <= 0 || cap_rows <= 0) return;
+  const int* ops = device_word_ops();
+  const uint64_t extra = (uint64_t)n_bufs * (uint64_t)cap_rows;
+  if (!table_) {
+    ensure_table((uint32_t)std::min<uint64_t>(2ULL * extra + 1024, 1ULL << 31));
+  } else if (2ULL * (groups_bound_ + extra) + 1024 > table_->capacity) {
+    uint32_t hc[4];
+    read_counters(hc);
+    ensure_table((uint32_t)std::min<uint64_t>(2ULL * (groups_known_ + extra) + 1024, 1ULL << 31));
+  }
+  launch_table_merge_packed(table_->view(), table_->n_keys, table_->n_acc, ops, opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY ? 1 : 0, src, n_bufs,
+                            (uint64_t)cap_rows, ctx_.stream);
+  uint32_t hc[4];
+  read_counters(hc);
+}
+
+// folds a batch of partial groups (layout of export_partials, device resident columns) into the table
+void AggOp::merge_partials(const DBatch& p) {
+  ctx_.activate();
+  if (cache_.empty()) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before any batch was aggregated (accumulator layout unknown)");
+  const int words = partial_row_words();
+  if ((int)p.cols.size() != words) fail(SQLRS_ERR_INVALID_ARG, "partials batch has the wrong number of columns");
+  for (size_t k = 0; k < p.cols.size(); k++)
+    if (p.cols[k].dtype != (k == 2 ? SQLRS_DT_INT32 : SQLRS_DT_INT64) || p.cols[k].valid)
+      fail(SQLRS_ERR_INVALID_ARG, "partials batch has the wrong column types");
+  const int64_t n = p.n;
+  seen_batch_ = true;
+  if (n == 0) return;
+  // columns -> one packed buffer (strided copies), header = n
+  BufPtr packed = dev_alloc_zero(ctx_, (size_t)(n + 1) * words * 8);
+  uint64_t header = (uint64_t)n;
+  SQ_CUDA(cudaMemcpyAsync(packed->p, &header, 8, cudaMemcpyHostToDevice, ctx_.stream));
+  for (int k = 0; k < words; k++) {
+    const size_t w = k == 2 ? 4 : 8;
+    SQ_CUDA(cudaMemcpy2DAsync((uint64_t*)packed->p + words + k, (size_t)words * 8, p.cols[k].data, w, w, (size_t)n, cudaMemcpyDeviceToDevice,
+                              ctx_.stream));
+  }
+  merge_partials_device((const uint64_t*)packed->p, 1, n);  // ends with a synchronising counter read: `header` stays valid
 }
 
 }  // namespace sq

@@ -58,7 +58,7 @@ void Plan::reset() {
   }
   results_.clear();
   tables_.clear();
-  partial_op_.reset();
+  partial_active_ = false;
 }
 
 // aggregate at `idx` -> host Arrow.  A Filter directly below is fused into the aggregate's row
@@ -75,7 +75,10 @@ void Plan::run_agg_to_host(int idx, Result* res) {
   } else {
     description_ += std::string(simple ? "[SimpleAgg] " : "[HashAgg] ");
   }
-  AggOp op(n.aggs, n.group_by, n.group_names, simple, fused, opt_);
+  // the operator (compiled kernels, group table, scratch) is kept across execute() calls
+  if (!agg_op_) agg_op_ = std::make_unique<AggOp>(n.aggs, n.group_by, n.group_names, simple, fused, opt_);
+  else agg_op_->reset();
+  AggOp& op = *agg_op_;
   for (const DBatch& b : run(child)) op.push(b);
   op.finish_host(&res->arr, &res->sch);
   res->on_host = true;
@@ -100,31 +103,45 @@ void Plan::execute_partial(int64_t row_base) {
     child = nodes_[child].child0;
     description_ += "[Filter+" + std::string(simple ? "SimpleAgg" : "HashAgg") + " fused, partial] ";
   }
-  partial_op_ = std::make_unique<AggOp>(n.aggs, n.group_by, n.group_names, simple, fused, opt_);
+  if (!partial_op_) partial_op_ = std::make_unique<AggOp>(n.aggs, n.group_by, n.group_names, simple, fused, opt_);
+  else partial_op_->reset();
+  partial_active_ = true;
   partial_op_->set_row_base(row_base);
   for (const DBatch& b : run(child)) partial_op_->push(b);
   description_ += partial_op_->describe() + "; ";
   scan_kernel_ms_ = partial_op_->scan_kernel_ms();
   scan_kernel_launches_ = partial_op_->scan_kernel_launches();
 }
+int Plan::partial_row_words() const {
+  if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "partial_row_words before execute_partial");
+  return partial_op_->partial_row_words();
+}
+void Plan::export_partials_device(uint64_t* dst, int64_t cap_rows) {
+  if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
+  partial_op_->export_partials_device(dst, cap_rows);
+}
+void Plan::merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows) {
+  if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
+  partial_op_->merge_partials_device(src, n_bufs, cap_rows);
+}
 void Plan::export_partials(ArrowArray* out, ArrowSchema* out_schema) {
-  if (!partial_op_) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
+  if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
   partial_op_->export_partials(out, out_schema);
 }
 void Plan::clear_partials() {
-  if (!partial_op_) fail(SQLRS_ERR_INVALID_ARG, "clear_partials before execute_partial");
+  if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "clear_partials before execute_partial");
   partial_op_->clear_partials();
 }
 void Plan::merge_partials(const DBatch& partials) {
-  if (!partial_op_) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
+  if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
   partial_op_->merge_partials(partials);
 }
 void Plan::finish_partial() {
-  if (!partial_op_) fail(SQLRS_ERR_INVALID_ARG, "finish before execute_partial");
+  if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "finish before execute_partial");
   results_.emplace_back();
   partial_op_->finish_host(&results_.back().arr, &results_.back().sch);
   results_.back().on_host = true;
-  partial_op_.reset();
+  partial_active_ = false;
 }
 
 std::vector<DBatch> Plan::run(int idx) {

@@ -24,6 +24,9 @@ class Plan {
   void clear_partials();
   void merge_partials(const DBatch& partials);
   void finish_partial();
+  int partial_row_words() const;
+  void export_partials_device(uint64_t* dst, int64_t cap_rows);
+  void merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows);
   const char* describe() const { return description_.c_str(); }
   double scan_kernel_ms() const { return scan_kernel_ms_; }
   int64_t scan_kernel_launches() const { return scan_kernel_launches_; }
@@ -55,7 +58,9 @@ class Plan {
   int root_ = 0;
   std::map<int, std::vector<DBatch>> tables_;
   std::deque<Result> results_;
-  std::unique_ptr<AggOp> partial_op_;  // execute_partial .. finish_partial
+  std::unique_ptr<AggOp> agg_op_;      // root aggregate of execute(), kept across runs
+  std::unique_ptr<AggOp> partial_op_;  // root aggregate of execute_partial(), kept across runs
+  bool partial_active_ = false;        // between execute_partial and finish_partial
   std::string description_;
   double scan_kernel_ms_ = 0;
   int64_t scan_kernel_launches_ = 0;

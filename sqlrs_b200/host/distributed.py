@@ -4,6 +4,8 @@ One process per GPU (torch.distributed; NCCL over NVLink on the GPU box, gloo in
 Scan, filter and the partial aggregation stay GPU-local; the only exchange is the group-by's:
 
   1. every rank aggregates its contiguous row shard           sqlrs_plan_execute_partial
+  (few groups, NCCL: the packed partial tables are all-gathered device-to-device and rank 0 folds them —
+   sqlrs_plan_export_partials_device / sqlrs_plan_merge_partials_device; otherwise:)
   2. partial groups are radix-partitioned by their identity hash (owner = hash mod world) and
      exchanged all-to-all; the owner folds them               sqlrs_plan_merge_partials
   3. the (now disjoint) owner-merged groups are gathered on rank 0, which finalises them in the
@@ -123,10 +125,41 @@ def partition_by_owner(partials: pa.RecordBatch, world: int) -> List[pa.RecordBa
     return [partials.filter(pa.array(owner == r)) for r in range(world)]
 
 
-def sharded_aggregate(plan, group: TorchGroup, row_base: int = 0) -> List[pa.RecordBatch]:
+def _device_exchange(plan, group: TorchGroup, cap_rows: int):
+    """Fast path for few groups (NCCL): partial groups never leave HBM.  Every rank packs its groups into a
+    fixed-size device buffer, ONE all-gather over NVLink hands all of them to every rank, rank 0 folds them.
+    Returns None when some rank has more than `cap_rows` groups (the caller takes the radix all-to-all path)."""
+    torch, lib = group.torch, plan.lib
+    words = C.c_int32(0)
+    lib.check(lib.plan_partials_row_words(plan.handle, C.byref(words)))
+    key = (words.value, cap_rows)
+    bufs = getattr(group, "_bufs", {})
+    if key not in bufs:
+        n = (cap_rows + 1) * words.value
+        bufs[key] = (torch.empty(n, dtype=torch.int64, device=group.device), torch.empty(n * group.world, dtype=torch.int64, device=group.device))
+        group._bufs = bufs
+    send, recv = bufs[key]
+    lib.check(lib.plan_export_partials_device(plan.handle, C.c_void_p(send.data_ptr()), cap_rows))
+    group.dist.all_gather_into_tensor(recv, send)
+    counts = recv.view(group.world, cap_rows + 1, words.value)[:, 0, 0]
+    if int(counts.max().item()) > cap_rows:
+        return None
+    lib.check(lib.plan_clear_partials(plan.handle))
+    if group.rank == 0:
+        lib.check(lib.plan_merge_partials_device(plan.handle, C.c_void_p(recv.data_ptr()), group.world, cap_rows))
+    lib.check(lib.plan_finish_partial(plan.handle))
+    result = plan.collect()
+    return result if group.rank == 0 else []
+
+
+def sharded_aggregate(plan, group: TorchGroup, row_base: int = 0, device_cap_rows: int = 1024) -> List[pa.RecordBatch]:
     """Runs `plan` (root = aggregate) over the shard pushed on this rank; rank 0 returns the final batches."""
     lib = plan.lib
     lib.check(lib.plan_execute_partial(plan.handle, row_base))
+    if group.native_a2a and device_cap_rows > 0 and lib.prefix == "sqlrs_":
+        result = _device_exchange(plan, group, device_cap_rows)
+        if result is not None:
+            return result
     local = _export_partials(plan)
     received = group.all_to_all_bytes([_to_bytes(p) for p in partition_by_owner(local, group.world)])
     lib.check(lib.plan_clear_partials(plan.handle))

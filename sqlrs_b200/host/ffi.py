@@ -206,6 +206,9 @@ _SIGNATURES = {
     "plan_clear_partials": (C.c_int, [C.c_void_p]),
     "plan_merge_partials": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema)]),
     "plan_finish_partial": (C.c_int, [C.c_void_p]),
+    "plan_partials_row_words": (C.c_int, [C.c_void_p, P(C.c_int32)]),
+    "plan_export_partials_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "plan_merge_partials_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64]),
     "plan_scan_kernel_ms": (C.c_double, [C.c_void_p, P(C.c_int64)]),
     "tpch_num_columns": (C.c_int32, [C.c_int32]),
     "tpch_num_rows": (C.c_int64, [P(TpchDims), C.c_int32]),

@@ -362,3 +362,71 @@ def test_q1_full_size_properties(cuda_lib):
         assert v[4] == a[k][4] + b[k][4] and v[5] == a[k][5] + b[k][5]
         for j in range(4):
             assert abs(v[j] - (a[k][j] + b[k][j])) <= 1e-9 * abs(v[j])
+
+
+def test_device_resident_partial_exchange(cuda_lib, oracle):
+    """The NCCL fast path's building blocks on one GPU: two shards aggregated separately, their packed partial
+    tables (device memory) concatenated like an all-gather would, folded and finalised == whole-table result."""
+    import torch
+
+    d = tpch.dims(0.05)
+    plan, schemas = tpch.q1_plan()
+    opts = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    whole = tpch.host_table(oracle, d, tpch.LINEITEM, columns=tpch.Q1_COLUMNS)
+    n = whole.num_rows
+    cut = n // 3
+    cap = 64
+    bufs, plans = [], []
+    for lo, hi in ((0, cut), (cut, n)):
+        p = ExecutorBuilder(cuda_lib, cuda_lib.options(**opts)).build(plan, schemas)
+        p.push_table(0, whole.slice(lo, hi - lo))
+        cuda_lib.check(cuda_lib.plan_execute_partial(p.handle, lo))
+        words = C.c_int32(0)
+        cuda_lib.check(cuda_lib.plan_partials_row_words(p.handle, C.byref(words)))
+        buf = torch.empty((cap + 1) * words.value, dtype=torch.int64, device="cuda")
+        cuda_lib.check(cuda_lib.plan_export_partials_device(p.handle, C.c_void_p(buf.data_ptr()), cap))
+        torch.cuda.synchronize()
+        assert int(buf[0].item()) == 8
+        bufs.append(buf)
+        plans.append(p)
+    gathered = torch.cat(bufs)
+    p = plans[0]
+    cuda_lib.check(cuda_lib.plan_clear_partials(p.handle))
+    cuda_lib.check(cuda_lib.plan_merge_partials_device(p.handle, C.c_void_p(gathered.data_ptr()), 2, cap))
+    cuda_lib.check(cuda_lib.plan_finish_partial(p.handle))
+    got = p.collect()
+    exp, _ = _run_plan(oracle, plan, schemas, {0: whole}, None, **opts)
+    assert_batches_match(got, exp, rtol=FTOL)
+    # the host (Arrow) form of the same exchange
+    from sqlrs_b200.host import distributed as sqdist
+
+    q = plans[1]
+    part = sqdist._export_partials(q)
+    assert part.num_rows == 8 and part.schema.names[:3] == ["hash", "min_row", "knull"]
+    cuda_lib.check(cuda_lib.plan_clear_partials(q.handle))
+    for piece in sqdist.partition_by_owner(part, 3):
+        sqdist._merge_partials(q, piece)
+    cuda_lib.check(cuda_lib.plan_finish_partial(q.handle))
+    shard_only, _ = _run_plan(oracle, plan, schemas, {0: whole.slice(cut)}, None, **opts)
+    assert_batches_match(q.collect(), shard_only, rtol=FTOL)
+    for x in plans:
+        x.close()
+
+
+def test_plan_can_be_executed_repeatedly(cuda_lib, oracle):
+    """bench.py reuses one plan: operator state must reset between runs (and survive a different table)"""
+    plan, schemas = tpch.q1_plan()
+    opts = dict(count_mode=ffi.COUNT_REFERENCE_OVERWRITE, match_mode=ffi.MATCH_HASH_ONLY)
+    p = ExecutorBuilder(cuda_lib, cuda_lib.options(**opts)).build(plan, schemas)
+    for sf, mode in ((0.01, ffi.TPCH_FLAGS_8GROUP), (0.02, ffi.TPCH_FLAGS_SPEC), (0.01, ffi.TPCH_FLAGS_8GROUP)):
+        t = tpch.host_table(oracle, tpch.dims(sf, mode), tpch.LINEITEM, columns=tpch.Q1_COLUMNS)
+        p.push_table(0, t.slice(0, 5000))
+        p.push_table(0, t.slice(5000))
+        got = p.run()
+        p.reset()
+        exp, _ = _run_plan(oracle, plan, schemas, {0: t}, None, **opts)
+        q = ExecutorBuilder(oracle, oracle.options(**opts)).build(plan, schemas)
+        q.push_table(0, t.slice(0, 5000))
+        q.push_table(0, t.slice(5000))
+        assert_batches_match(got, q.run(), rtol=FTOL)
+    p.close()
