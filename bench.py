@@ -283,6 +283,14 @@ def run_gpu(args, rank, world, local_rank):
     if rank != 0:
         return
     peak, peak_src = measured_peak()
+    traffic = None
+    try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture of this workload (per launch)
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f).get(f"tpch_q1_sf{args.sf:g}")
+        if t and world == 1:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
     ms_per_step = elapsed_ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
     k_ms = kernel_ms[0] / max(kernel_launches[0], 1)
@@ -298,7 +306,7 @@ def run_gpu(args, rank, world, local_rank):
         "hbm_gbs_whole_step": n_total * bytes_per_row / (ms_per_step * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "kernel": "sq_agg_small", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if achieved else None, "frac_of_8TBs": achieved / 8000.0 if achieved else None, "peak_source": peak_src,
-                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": n_local * bytes_per_row, "traffic": None},
+                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": n_local * bytes_per_row, "traffic": traffic},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     if world == 1 and args.cpu_rows > 0:

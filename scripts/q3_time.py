@@ -1,0 +1,44 @@
+"""Times the Q3' plan (customer ⋈ orders ⋈ lineitem -> group-by) on one GPU with device-resident tables."""
+import ctypes as C
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pyarrow as pa
+import torch
+from sqlrs_b200.host import ffi, tpch
+from sqlrs_b200.host.plan import ExecutorBuilder
+
+sf = float(sys.argv[1]) if len(sys.argv) > 1 else 10
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+lib = ffi.load()
+d = tpch.dims(sf)
+tabs = {0: tpch.device_table(lib, d, tpch.CUSTOMER, columns=tpch.Q3_CUSTOMER_COLUMNS),
+        1: tpch.device_table(lib, d, tpch.ORDERS, columns=tpch.Q3_ORDERS_COLUMNS),
+        2: tpch.device_table(lib, d, tpch.LINEITEM, columns=tpch.Q3_LINEITEM_COLUMNS)}
+rows = {k: t.n_rows for k, t in tabs.items()}
+alg = tpch.q3_algorithmic_bytes(rows[0], rows[1], rows[2])
+plan, schemas = tpch.q3_plan()
+stream = torch.cuda.Stream()
+with torch.cuda.stream(stream):
+    opts = lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY, stream=C.c_void_p(stream.cuda_stream))
+    p = ExecutorBuilder(lib, opts).build(plan, schemas)
+    best = 1e9
+    for it in range(reps):
+        for k, t in tabs.items():
+            p.push_table_device(k, t)
+        torch.cuda.synchronize()
+        l0 = lib.kernel_launches()
+        t0 = time.perf_counter()
+        p.execute()
+        out = p.collect()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        launches = lib.kernel_launches() - l0
+        p.reset()
+        if it:
+            best = min(best, dt)
+    res = pa.Table.from_batches(out)
+    print(f"Q3' SF{sf:g}: rows c/o/l = {rows[0]}/{rows[1]}/{rows[2]}  groups={res.num_rows}  best {best*1e3:.2f} ms  "
+          f"{sum(rows.values())/best/1e9:.2f} Grows/s  alg {alg/1e9:.2f} GB -> {alg/best/1e9:.0f} GB/s  launches/run={launches}")
+    print(p.describe()[:600])
+    top = res.sort_by([(res.schema.names[3], "descending"), (res.schema.names[1], "ascending")]).slice(0, 3)
+    print(top.to_pydict())

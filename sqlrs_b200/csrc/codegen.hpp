@@ -61,6 +61,11 @@ class RowProgram {
   const std::vector<ColInfo>& cols() const { return cols_; }
   bool uses_error_flag(int cls) const { return err_used_[cls]; }
   std::string signature() const;  // schema part of the JIT cache key
+  int n_loaded_columns() const {   // distinct input columns the program reads
+    int n = 0;
+    for (const auto& kv : cse_) n += kv.first.rfind("col", 0) == 0;
+    return n;
+  }
 
  private:
   Val load_column(int index);
