@@ -3,7 +3,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <time.h>
+
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -31,6 +35,35 @@ struct Error : std::runtime_error {
 
 extern std::atomic<int64_t> g_kernel_launches;
 inline void count_launch(int64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// SQLRS_B200_TRACE=1: wall-clock phase timings on stderr (each phase end synchronises the stream, so the
+// numbers attribute device work to the phase that enqueued it; tracing slows the run down)
+struct Trace {
+  const char* name;
+  cudaStream_t stream;
+  bool on;
+  double t0 = 0;
+  static bool enabled() {
+    static int e = -1;
+    if (e < 0) e = getenv("SQLRS_B200_TRACE") ? 1 : 0;
+    return e == 1;
+  }
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+  Trace(const char* n, cudaStream_t s) : name(n), stream(s), on(enabled()) {
+    if (on) t0 = now();
+  }
+  ~Trace() {
+    if (!on) return;
+    const double t1 = now();
+    cudaStreamSynchronize(stream);
+    const double t2 = now();
+    fprintf(stderr, "[sqlrs trace] %-28s host %8.3f ms  +drain %8.3f ms\n", name, t1 - t0, t2 - t1);
+  }
+};
 
 inline const char* dtype_name(int dt) {
   switch (dt) {

@@ -15,6 +15,10 @@ class JoinOp {
   void build_push(const DBatch& batch);
   bool probe(const DBatch& right, DBatch* out);  // false where the reference yields nothing (empty build side)
   bool finish(DBatch* out);                      // Left/Full tail
+  // plan executor only: Filters directly below the join evaluated inside the key kernels (rows keep their
+  // original ids, results are identical), and output columns nobody above reads left out of the gathers
+  void set_side_predicates(ExprCopy build_pred, ExprCopy probe_pred);
+  void set_needed_columns(std::vector<bool> needed);
   Ctx& ctx() { return ctx_; }
 
  private:

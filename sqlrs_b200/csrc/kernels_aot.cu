@@ -2,6 +2,8 @@
 // bitmap utilities, warp-ballot stream compaction, gathers (arrow `take`), group-table maintenance.
 // All of it is HBM-bound integer / byte work: coalesced 4/8-byte lanes, whole-word bitmap stores
 // through __ballot_sync, grids sized in multiples of the SM count.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "kernels_aot.hpp"
 
 #include "../../include/sqlrs_tpch_spec.h"
@@ -232,6 +234,36 @@ __global__ void __launch_bounds__(kBlock) k_table_pack(TableView t, int n_keys, 
   }
 }
 
+// occupied slots and their first-row ids, in table order (input of the ordering sort)
+__global__ void __launch_bounds__(kBlock) k_table_list(TableView t, uint64_t* __restrict__ min_rows, uint32_t* __restrict__ slots,
+                                                        uint32_t max_out, uint32_t* __restrict__ count) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
+    if (t.state[s] != 2u) continue;
+    const uint32_t o = atomicAdd(count, 1u);
+    if (o >= max_out) continue;
+    min_rows[o] = t.min_row[s];
+    slots[o] = s;
+  }
+}
+
+// packed rows in the given slot order (first-appearance order after the sort); header written by thread 0
+__global__ void __launch_bounds__(kBlock) k_table_pack_ordered(TableView t, int n_keys, int n_acc, const uint32_t* __restrict__ slots, uint32_t n,
+                                                                uint64_t* __restrict__ dst) {
+  const int words = 3 + n_keys + n_acc;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) dst[0] = n;
+  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += stride) {
+    const uint32_t s = slots[o];
+    uint64_t* row = dst + (size_t)(1 + o) * words;
+    row[0] = t.hash[s];
+    row[1] = t.min_row[s];
+    row[2] = t.knull[s];
+    for (int k = 0; k < n_keys; k++) row[3 + k] = t.keys[(size_t)k * t.capacity + s];
+    for (int w = 0; w < n_acc; w++) row[3 + n_keys + w] = t.acc[(size_t)w * t.capacity + s];
+  }
+}
+
 __device__ __forceinline__ uint32_t mix32(uint64_t h) {  // same spreader as sq_mix32 (csrc/jit/prelude.cuh)
   h ^= h >> 33;
   h *= 0xff51afd7ed558ccdULL;
@@ -413,6 +445,37 @@ void launch_table_pack(const TableView& t, int n_keys, int n_acc, uint64_t* dst,
   k_table_pack<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, dst, cap_rows);
   count_launch();
   SQ_CUDA(cudaGetLastError());
+}
+
+// the n groups of `t` packed in ascending first-row order (= the reference's first-appearance order):
+// list occupied slots -> radix sort by min_row (CUB, a library sort of n small keys) -> ordered pack
+void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, uint64_t* dst, cudaStream_t stream) {
+  if (n == 0) return;
+  uint64_t *k_in = nullptr, *k_out = nullptr;
+  uint32_t *v_in = nullptr, *v_out = nullptr, *count = nullptr;
+  SQ_CUDA(cudaMallocAsync(&k_in, (size_t)n * 8, stream));
+  SQ_CUDA(cudaMallocAsync(&k_out, (size_t)n * 8, stream));
+  SQ_CUDA(cudaMallocAsync(&v_in, (size_t)n * 4, stream));
+  SQ_CUDA(cudaMallocAsync(&v_out, (size_t)n * 4, stream));
+  SQ_CUDA(cudaMallocAsync(&count, 4, stream));
+  SQ_CUDA(cudaMemsetAsync(count, 0, 4, stream));
+  k_table_list<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, k_in, v_in, n, count);
+  count_launch();
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, 64, stream);
+  void* tmp = nullptr;
+  SQ_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, stream));
+  SQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, 64, stream));
+  count_launch(8);
+  k_table_pack_ordered<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, v_out, n, dst);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+  cudaFreeAsync(tmp, stream);
+  cudaFreeAsync(k_in, stream);
+  cudaFreeAsync(k_out, stream);
+  cudaFreeAsync(v_in, stream);
+  cudaFreeAsync(v_out, stream);
+  cudaFreeAsync(count, stream);
 }
 
 void launch_table_rehash(const TableView& from, const TableView& to, int n_keys, int n_acc, cudaStream_t stream) {

@@ -49,6 +49,8 @@ struct TableView {
 // [hash, min_row, knull, key bits x K, accumulator words x W] (3+K+W u64 words per row).
 // dst must hold (cap_rows + 1) rows and have its header zeroed; groups beyond cap_rows are counted, not written.
 void launch_table_pack(const TableView& t, int n_keys, int n_acc, uint64_t* dst, uint64_t cap_rows, cudaStream_t stream);
+// the n groups packed in ascending first-row order (dst: (n + 1) rows; header written)
+void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, uint64_t* dst, cudaStream_t stream);
 // partial -> final merge of n_bufs packed buffers ((cap_rows + 1) rows each) into `t`; ops[w] (device):
 // 0 add u64, 1 add f64, 2 min i64, 3 max i64
 void launch_table_merge_packed(const TableView& t, int n_keys, int n_acc, const int* ops, int match_keys, const uint64_t* src, int n_bufs,
@@ -75,6 +77,7 @@ struct JoinTableView {
   int64_t n_build;
   int n_keys;
   int match_keys;         // SQLRS_MATCH_HASH_AND_KEY: compare key tuples, NULL never joins
+  const uint32_t* build_keep;  // optional bitmap: build rows that pass the Filter fused below the join (nullptr = all)
 };
 
 void launch_scan_u32_large(const uint32_t* counts, int64_t m, unsigned long long* offsets, unsigned long long* total,
@@ -86,14 +89,16 @@ void launch_join_fill(const JoinTableView& t, const int32_t* row_slot, uint32_t*
 void launch_join_sort_ranges(const JoinTableView& t, cudaStream_t stream);
 // stable fallback for heavily duplicated keys: rows = build row ids sorted by (slot, row id)
 void join_fill_sorted(const JoinTableView& t, const int32_t* row_slot, cudaStream_t stream);
-void launch_join_probe_count(const JoinTableView& t, const uint64_t* ph, const uint64_t* pkeys, const uint32_t* pknull, int64_t n_probe,
-                             int keep_unmatched, int32_t* slot_of, uint32_t* out_count, cudaStream_t stream);
+// probe_keep: optional bitmap of probe rows that pass the Filter fused below the join (others produce nothing)
+void launch_join_probe_count(const JoinTableView& t, const uint64_t* ph, const uint64_t* pkeys, const uint32_t* pknull, const uint32_t* probe_keep,
+                             int64_t n_probe, int keep_unmatched, int32_t* slot_of, uint32_t* out_count, cudaStream_t stream);
 void launch_join_probe_write(const JoinTableView& t, const int32_t* slot_of, const unsigned long long* offsets, int64_t n_probe,
                              int keep_unmatched, int64_t* li, uint32_t* ri, cudaStream_t stream);
 // bitmap[idx[k]] = 1 for every k (idx < 0 skipped)
 void launch_mark_bits_i64(const int64_t* idx, int64_t m, uint32_t* bitmap, cudaStream_t stream);
 void launch_mark_bits_u32(const uint32_t* idx, int64_t m, uint32_t* bitmap, cudaStream_t stream);
 // dst = ~src over the first n bits (bits past n cleared)
-void launch_bitmap_not(const uint32_t* src, int64_t n, uint32_t* dst, cudaStream_t stream);
+// (and_mask != nullptr: dst = and_mask & ~src)
+void launch_bitmap_not(const uint32_t* src, int64_t n, uint32_t* dst, cudaStream_t stream, const uint32_t* and_mask = nullptr);
 
 }  // namespace sq

@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(kBlock) k_join_insert(JoinTableView t, int32_t
   const uint32_t mask = t.capacity - 1;
   uint32_t local_max = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.n_build; i += stride) {
-    if (t.match_keys && t.knull[i] != 0u) {  // SQL semantics: a NULL key never joins
+    const bool dropped = t.build_keep && !((t.build_keep[i >> 5] >> (i & 31)) & 1u);  // fails the fused Filter
+    if (dropped || (t.match_keys && t.knull[i] != 0u)) {  // SQL semantics: a NULL key never joins
       row_slot[i] = -1;
       continue;
     }
@@ -96,13 +97,15 @@ __global__ void __launch_bounds__(kBlock) k_join_sort_ranges(JoinTableView t) {
 }
 
 __global__ void __launch_bounds__(kBlock) k_join_probe_count(JoinTableView t, const uint64_t* __restrict__ ph, const uint64_t* __restrict__ pkeys,
-                                                              const uint32_t* __restrict__ pknull, int64_t n_probe, int keep_unmatched,
+                                                              const uint32_t* __restrict__ pknull, const uint32_t* __restrict__ probe_keep,
+                                                              int64_t n_probe, int keep_unmatched,
                                                               int32_t* __restrict__ slot_of, uint32_t* __restrict__ out_count) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const uint32_t mask = t.capacity - 1;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_probe; r += stride) {
     int32_t found = -1;
-    if (!(t.match_keys && pknull[r] != 0u)) {
+    const bool kept = !probe_keep || ((probe_keep[r >> 5] >> (r & 31)) & 1u);
+    if (kept && !(t.match_keys && pknull[r] != 0u)) {
       const uint64_t h = ph[r];
       uint32_t s = mix32(h) & mask;
       for (uint32_t probes = 0; probes <= mask; probes++) {
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(kBlock) k_join_probe_count(JoinTableView t, co
     }
     slot_of[r] = found;
     const uint32_t c = found >= 0 ? t.slot_count[found] : 0u;
-    out_count[r] = c ? c : (keep_unmatched ? 1u : 0u);
+    out_count[r] = c ? c : ((keep_unmatched && kept) ? 1u : 0u);
   }
 }
 
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kBlock) k_join_probe_write(JoinTableView t, co
         li[o + j] = src[j];
         ri[o + j] = (uint32_t)r;
       }
-    } else if (keep_unmatched) {  // Right/Full: (NULL, row), hash_join.rs:242-246
+    } else if (keep_unmatched && offsets[r + 1] > o) {  // Right/Full: (NULL, row), hash_join.rs:242-246 (rows dropped by a fused Filter emit nothing)
       li[o] = -1;
       ri[o] = (uint32_t)r;
     }
@@ -152,11 +155,13 @@ __global__ void __launch_bounds__(kBlock) k_mark_bits(const Idx* __restrict__ id
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_bitmap_not(const uint32_t* __restrict__ src, int64_t n, uint32_t* __restrict__ dst) {
+__global__ void __launch_bounds__(kBlock) k_bitmap_not(const uint32_t* __restrict__ src, int64_t n, uint32_t* __restrict__ dst,
+                                                        const uint32_t* __restrict__ and_mask) {
   const int64_t words = (n + 31) >> 5;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += stride) {
     uint32_t v = ~src[w];
+    if (and_mask) v &= and_mask[w];
     if (w == words - 1 && (n & 31)) v &= (1u << (n & 31)) - 1u;
     dst[w] = v;
   }
@@ -326,10 +331,10 @@ void join_fill_sorted(const JoinTableView& t, const int32_t* row_slot, cudaStrea
   cudaFreeAsync(v_out, stream);
 }
 
-void launch_join_probe_count(const JoinTableView& t, const uint64_t* ph, const uint64_t* pkeys, const uint32_t* pknull, int64_t n_probe,
-                             int keep_unmatched, int32_t* slot_of, uint32_t* out_count, cudaStream_t stream) {
+void launch_join_probe_count(const JoinTableView& t, const uint64_t* ph, const uint64_t* pkeys, const uint32_t* pknull, const uint32_t* probe_keep,
+                             int64_t n_probe, int keep_unmatched, int32_t* slot_of, uint32_t* out_count, cudaStream_t stream) {
   if (n_probe <= 0) return;
-  k_join_probe_count<<<grid_for(n_probe, kBlock), kBlock, 0, stream>>>(t, ph, pkeys, pknull, n_probe, keep_unmatched, slot_of, out_count);
+  k_join_probe_count<<<grid_for(n_probe, kBlock), kBlock, 0, stream>>>(t, ph, pkeys, pknull, probe_keep, n_probe, keep_unmatched, slot_of, out_count);
   SQ_LAUNCH_CHECK();
 }
 void launch_join_probe_write(const JoinTableView& t, const int32_t* slot_of, const unsigned long long* offsets, int64_t n_probe,
@@ -348,9 +353,9 @@ void launch_mark_bits_u32(const uint32_t* idx, int64_t m, uint32_t* bitmap, cuda
   k_mark_bits<uint32_t><<<grid_for(m, kBlock), kBlock, 0, stream>>>(idx, m, bitmap);
   SQ_LAUNCH_CHECK();
 }
-void launch_bitmap_not(const uint32_t* src, int64_t n, uint32_t* dst, cudaStream_t stream) {
+void launch_bitmap_not(const uint32_t* src, int64_t n, uint32_t* dst, cudaStream_t stream, const uint32_t* and_mask) {
   if (n <= 0) return;
-  k_bitmap_not<<<grid_for(div_up(n, 32), kBlock), kBlock, 0, stream>>>(src, n, dst);
+  k_bitmap_not<<<grid_for(div_up(n, 32), kBlock), kBlock, 0, stream>>>(src, n, dst, and_mask);
   SQ_LAUNCH_CHECK();
 }
 

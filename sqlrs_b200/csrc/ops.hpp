@@ -73,7 +73,8 @@ class FilterOp {
   Ctx ctx_;
   EvalProgram prog_;
 };
-DBatch filter_batch(Ctx& ctx, EvalProgram& prog, const DBatch& in);
+// `needed` (optional): gather only these columns, the others become Null-typed placeholders
+DBatch filter_batch(Ctx& ctx, EvalProgram& prog, const DBatch& in, const std::vector<bool>* needed = nullptr);
 
 // ---- aggregates ------------------------------------------------------------------------------------
 struct AggSpec {
@@ -133,6 +134,8 @@ class AggOp {
   bool use_global_ = false;
   uint32_t groups_known_ = 0;   // exact group count at the last counter read
   uint64_t groups_bound_ = 0;   // host-side upper bound since then
+  uint64_t* pinned_ = nullptr;  // pinned host staging of the packed result
+  size_t pinned_words_ = 0;
   size_t part_entries_ = 0;     // CTA-partial scratch of sq_agg_small
   BufPtr p_state_, p_hash_, p_min_, p_keys_, p_knull_, p_acc_, d_ops_;
   std::vector<int> key_dtypes_;

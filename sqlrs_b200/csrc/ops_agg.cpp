@@ -149,7 +149,9 @@ AggOp::AggOp(std::vector<AggSpec> aggs, std::vector<ExprCopy> group_by, std::vec
       fail(SQLRS_ERR_UNSUPPORTED, "DISTINCT aggregates are not supported by the CUDA backend yet (SURVEY §8f rank 4)");
   }
 }
-AggOp::~AggOp() = default;
+AggOp::~AggOp() {
+  if (pinned_) cudaFreeHost(pinned_);
+}
 
 // ------------------------------------------------------------------ code generation
 AggOp::Compiled& AggOp::compiled_for(const DBatch& batch) {
@@ -434,6 +436,7 @@ void AggOp::read_counters(uint32_t* out4) {
 
 // ------------------------------------------------------------------ push
 void AggOp::push(const DBatch& batch) {
+  Trace tr("agg.push", ctx_.stream);
   ctx_.activate();
   ctx_.reap();
   Compiled& c = compiled_for(batch);
@@ -560,9 +563,18 @@ void AggOp::build_output(std::vector<Field>* fields, HostGroups* g) {
     const int words = 3 + K + W;
     BufPtr packed = dev_alloc(ctx_, (size_t)(n + 1) * words * 8);
     SQ_CUDA(cudaMemsetAsync(packed->p, 0, (size_t)words * 8, ctx_.stream));
-    launch_table_pack(table_->view(), K, W, (uint64_t*)packed->p, n, ctx_.stream);
-    std::vector<uint64_t> host((size_t)(n + 1) * words);
-    SQ_CUDA(cudaMemcpyAsync(host.data(), packed->p, host.size() * 8, cudaMemcpyDeviceToHost, ctx_.stream));
+    if (n > 256) table_pack_sorted(table_->view(), K, W, n, (uint64_t*)packed->p, ctx_.stream);  // ordered on the device
+    else launch_table_pack(table_->view(), K, W, (uint64_t*)packed->p, n, ctx_.stream);          // few groups: the host sorts
+    const size_t host_words = (size_t)(n + 1) * words;
+    if (pinned_words_ < host_words) {  // pinned staging, kept across runs: the D2H runs at PCIe speed
+      if (pinned_) cudaFreeHost(pinned_);
+      pinned_ = nullptr;
+      pinned_words_ = 0;
+      SQ_CUDA(cudaHostAlloc((void**)&pinned_, host_words * 8, cudaHostAllocDefault));
+      pinned_words_ = host_words;
+    }
+    uint64_t* host = pinned_;
+    SQ_CUDA(cudaMemcpyAsync(host, packed->p, host_words * 8, cudaMemcpyDeviceToHost, ctx_.stream));
     ctx_.sync();
     if (host[0] != n) fail(SQLRS_ERR_INTERNAL, "group count changed under finalisation");
     g->n = n;
@@ -572,7 +584,7 @@ void AggOp::build_output(std::vector<Field>* fields, HostGroups* g) {
     g->knull.resize(n);
     g->acc.resize((size_t)n * std::max(W, 1));
     for (uint32_t i = 0; i < n; i++) {
-      const uint64_t* row = host.data() + (size_t)(1 + i) * words;
+      const uint64_t* row = host + (size_t)(1 + i) * words;
       g->hash[i] = row[0];
       g->min_row[i] = row[1];
       g->knull[i] = (uint32_t)row[2];
@@ -593,6 +605,7 @@ static double sortable_to_f64(int64_t s) {
 }
 
 void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
+  Trace tr("agg.finish_host", ctx_.stream);
   std::vector<Field> fields;
   HostGroups g;
   build_output(&fields, &g);
@@ -602,7 +615,8 @@ void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
   // first-appearance order (hash_agg.rs:98,134) = ascending first global row id
   std::vector<uint32_t> order(n);
   for (uint32_t i = 0; i < n; i++) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return g.min_row[a] < g.min_row[b]; });
+  if (!std::is_sorted(g.min_row.begin(), g.min_row.end()))  // large tables arrive ordered from the device (table_pack_sorted)
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return g.min_row[a] < g.min_row[b]; });
   const bool synth_row = simple_ && n == 0;  // SimpleAgg over batches without a surviving row: one row of initial values
   const int64_t rows = synth_row ? 1 : n;
   std::vector<HostCol> cols(fields.size());

@@ -153,6 +153,7 @@ std::string EvalProgram::source_for(const std::vector<ColInfo>& cols, std::vecto
 }
 
 EvalResult EvalProgram::run(Ctx& ctx, const DBatch& batch, const char* what) {
+  Trace tr("eval.run", ctx.stream);
   std::vector<ColInfo> cols = col_infos(batch);
   std::string sig = RowProgram(cols).signature();
   auto it = cache_.find(sig);
@@ -256,17 +257,23 @@ static EvalRequest keep_request(const ExprCopy& predicate) {
 }
 
 // filter.rs:16-25 — mask = eval; keep rows whose mask is valid and true; row order preserved
-DBatch filter_batch(Ctx& ctx, EvalProgram& prog, const DBatch& in) {
+DBatch filter_batch(Ctx& ctx, EvalProgram& prog, const DBatch& in, const std::vector<bool>* needed) {
   EvalResult mask = prog.run(ctx, in, "filter predicate");
   DBatch out;
   out.fields = in.fields;
   int64_t kept = 0;
   BufPtr idx = compact_indices(ctx, (const uint32_t*)mask.cols[0].data, in.n, &kept);
   out.n = kept;
-  for (const DCol& c : in.cols) {
-    DCol g = gather_col_u32(ctx, c, (const uint32_t*)idx->p, kept);
-    g.keep_data = std::shared_ptr<void>(g.keep_data);  // (no-op; documents ownership)
-    out.cols.push_back(g);
+  for (size_t k = 0; k < in.cols.size(); k++) {
+    if (needed && !needed->empty() && !(k < needed->size() && (*needed)[k])) {
+      DCol ph;  // nobody above reads this column
+      ph.dtype = SQLRS_DT_NULL;
+      ph.n = kept;
+      ph.null_count = kept;
+      out.cols.push_back(ph);
+      continue;
+    }
+    out.cols.push_back(gather_col_u32(ctx, in.cols[k], (const uint32_t*)idx->p, kept));
   }
   // the index list must outlive the enqueued gathers
   ctx.defer([idx]() {});

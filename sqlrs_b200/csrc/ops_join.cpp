@@ -20,9 +20,16 @@ struct JoinOp::Impl {
   BufPtr visited_left;  // bitmap over build rows (Left/Full)
   std::unique_ptr<EvalProgram> left_prog, right_prog, filter_prog;
   JoinTableView view{};
+  // plan-level fusion (SQLRS plan executor): Filters directly below the join run inside the key evaluation,
+  // and output columns nobody above reads are not gathered
+  ExprCopy build_pred, probe_pred;
+  std::vector<DCol> left_keep_parts;
+  DCol keep_all;
+  std::vector<bool> needed;  // per output field; empty = all
 };
 
-static EvalRequest key_request(const std::vector<ExprCopy>& keys, bool match_keys) {
+// outputs: [hash, (raw bits x K, null mask)?, (keep mask of the fused Filter)?]
+static EvalRequest key_request(const std::vector<ExprCopy>& keys, bool match_keys, const ExprCopy& pred) {
   EvalRequest r;
   for (const ExprCopy& k : keys) {
     r.exprs.push_back(k);
@@ -33,6 +40,11 @@ static EvalRequest key_request(const std::vector<ExprCopy>& keys, bool match_key
     for (size_t k = 0; k < keys.size(); k++) r.outs.push_back({OUT_RAWBITS, (int)k});
     r.outs.push_back({OUT_NULLMASK, 0});
   }
+  if (!pred.empty()) {
+    r.exprs.push_back(pred);
+    r.is_key.push_back(false);
+    r.outs.push_back({OUT_KEEP, (int)r.exprs.size() - 1});
+  }
   return r;
 }
 
@@ -42,9 +54,6 @@ JoinOp::JoinOp(int join_type, std::vector<ExprCopy> left_keys, std::vector<ExprC
       filter_(std::move(filter)), out_fields_(std::move(out_fields)), impl_(new Impl()) {
   if (left_keys_.size() != right_keys_.size() || left_keys_.empty()) fail(SQLRS_ERR_INTERNAL, "HashJoin must has on condition");
   if (left_keys_.size() > 16) fail(SQLRS_ERR_UNSUPPORTED, "more than 16 join keys");
-  const bool mk = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
-  impl_->left_prog = std::make_unique<EvalProgram>(key_request(left_keys_, mk));
-  impl_->right_prog = std::make_unique<EvalProgram>(key_request(right_keys_, mk));
   if (!filter_.empty()) {
     EvalRequest r;
     r.exprs.push_back(filter_);
@@ -55,11 +64,24 @@ JoinOp::JoinOp(int join_type, std::vector<ExprCopy> left_keys, std::vector<ExprC
 }
 JoinOp::~JoinOp() = default;
 
+void JoinOp::set_side_predicates(ExprCopy build_pred, ExprCopy probe_pred) {
+  impl_->build_pred = std::move(build_pred);
+  impl_->probe_pred = std::move(probe_pred);
+}
+void JoinOp::set_needed_columns(std::vector<bool> needed) { impl_->needed = std::move(needed); }
+
 // hash_join.rs:161-181
 void JoinOp::build_push(const DBatch& batch) {
+  Trace tr("join.build_push", ctx_.stream);
   if (impl_->sealed) fail(SQLRS_ERR_INVALID_ARG, "hash_join: build_push after probe");
   ctx_.reap();
+  const bool mk = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
+  if (!impl_->left_prog) impl_->left_prog = std::make_unique<EvalProgram>(key_request(left_keys_, mk, impl_->build_pred));
   EvalResult keys = impl_->left_prog->run(ctx_, batch, "join key");
+  if (!impl_->build_pred.empty()) {
+    impl_->left_keep_parts.push_back(keys.cols.back());
+    keys.cols.pop_back();
+  }
   impl_->left_key_parts.push_back(keys.cols);
   impl_->left_batches.push_back(batch);
   impl_->left_rows += batch.n;
@@ -69,6 +91,7 @@ void JoinOp::build_push(const DBatch& batch) {
 void JoinOp::seal() {
   Impl& im = *impl_;
   if (im.sealed) return;
+  Trace tr("join.seal", ctx_.stream);
   im.sealed = true;
   if (im.left_batches.empty()) return;
   const int64_t n = im.left_rows;
@@ -104,8 +127,10 @@ void JoinOp::seal() {
     for (auto& p : im.left_key_parts) parts.push_back(p[1 + K]);
     im.knull_all = concat_cols(ctx_, parts, SQLRS_DT_INT32);
   }
+  if (!im.build_pred.empty()) im.keep_all = concat_cols(ctx_, im.left_keep_parts, SQLRS_DT_BOOL);
   im.left_batches.clear();
   im.left_key_parts.clear();
+  im.left_keep_parts.clear();
 
   // table: capacity >= 2 x build rows
   uint64_t cap = 1024;
@@ -129,6 +154,7 @@ void JoinOp::seal() {
   v.n_build = n;
   v.n_keys = K;
   v.match_keys = mk ? 1 : 0;
+  v.build_keep = im.build_pred.empty() ? nullptr : (const uint32_t*)im.keep_all.data;
   if (n > 0) {
     BufPtr row_slot = dev_alloc(ctx_, (size_t)n * 4);
     BufPtr misc = dev_alloc_zero(ctx_, 16);  // [0] max count, [8] total
@@ -155,8 +181,21 @@ DBatch JoinOp::build_batch(const DBatch& right, const int64_t* li, bool li_nulla
   DBatch out;
   out.fields = out_fields_;
   out.n = m;
-  for (const DCol& c : impl_->left_single.cols) out.cols.push_back(gather_col_i64(ctx_, c, li, m, li_nullable));
-  for (const DCol& c : right.cols) out.cols.push_back(gather_col_u32(ctx_, c, ri, m));
+  const std::vector<bool>& needed = impl_->needed;
+  auto pruned = [&](size_t k) {  // nobody above reads this column: a Null-typed placeholder keeps the positions
+    if (needed.empty() || k >= needed.size() || needed[k]) return false;
+    DCol c;
+    c.dtype = SQLRS_DT_NULL;
+    c.n = m;
+    c.null_count = m;
+    out.cols.push_back(c);
+    return true;
+  };
+  size_t k = 0;
+  for (const DCol& c : impl_->left_single.cols)
+    if (!pruned(k++)) out.cols.push_back(gather_col_i64(ctx_, c, li, m, li_nullable));
+  for (const DCol& c : right.cols)
+    if (!pruned(k++)) out.cols.push_back(gather_col_u32(ctx_, c, ri, m));
   check_schema(out);
   return out;
 }
@@ -165,6 +204,7 @@ DBatch JoinOp::build_batch(const DBatch& right, const int64_t* li, bool li_nulla
 void JoinOp::check_schema(DBatch& b) {
   if (b.cols.size() != out_fields_.size()) fail(SQLRS_ERR_ARROW, "number of columns must match number of fields in schema");
   for (size_t c = 0; c < b.cols.size(); c++) {
+    if (!impl_->needed.empty() && c < impl_->needed.size() && !impl_->needed[c]) continue;  // pruned placeholder
     if (b.cols[c].dtype != out_fields_[c].dtype)
       fail(SQLRS_ERR_ARROW, std::string("column types must match schema types, expected ") + dtype_name(out_fields_[c].dtype) +
                                 " but found " + dtype_name(b.cols[c].dtype));
@@ -178,13 +218,22 @@ bool JoinOp::probe(const DBatch& right, DBatch* result) {
   seal();
   Impl& im = *impl_;
   if (im.capacity == 0) return false;  // empty build side: no left batch at all (:183-185)
+  Trace tr("join.probe", ctx_.stream);
   ctx_.reap();
   const int K = (int)right_keys_.size();
   const bool mk = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
   const bool keep_right = join_type_ == SQLRS_JOIN_RIGHT || join_type_ == SQLRS_JOIN_FULL;
   const int64_t n = right.n;
   if (n >= (1LL << 32)) fail(SQLRS_ERR_INVALID_ARG, "a probe batch may hold fewer than 2^32 rows (hash_join.rs:219)");
+  if (!im.right_prog) im.right_prog = std::make_unique<EvalProgram>(key_request(right_keys_, mk, im.probe_pred));
   EvalResult rk = im.right_prog->run(ctx_, right, "join key");
+  const uint32_t* probe_keep = nullptr;
+  DCol probe_keep_col;
+  if (!im.probe_pred.empty()) {
+    probe_keep_col = rk.cols.back();
+    rk.cols.pop_back();
+    probe_keep = (const uint32_t*)probe_keep_col.data;
+  }
   BufPtr pkeys;
   if (mk && n > 0) {
     pkeys = dev_alloc(ctx_, (size_t)n * 8 * K);
@@ -198,7 +247,7 @@ bool JoinOp::probe(const DBatch& right, DBatch* result) {
     BufPtr offsets = dev_alloc(ctx_, (size_t)n * 8 + 8);
     BufPtr scratch = dev_alloc(ctx_, scan_scratch_entries(n) * 8);
     launch_join_probe_count(im.view, (const uint64_t*)rk.cols[0].data, mk ? (const uint64_t*)pkeys->p : nullptr,
-                            mk ? (const uint32_t*)rk.cols[1 + K].data : nullptr, n, keep_right ? 1 : 0, (int32_t*)slot_of->p,
+                            mk ? (const uint32_t*)rk.cols[1 + K].data : nullptr, probe_keep, n, keep_right ? 1 : 0, (int32_t*)slot_of->p,
                             (uint32_t*)counts->p, ctx_.stream);
     unsigned long long* total_d = (unsigned long long*)offsets->p + n;
     launch_scan_u32_large((const uint32_t*)counts->p, n, (unsigned long long*)offsets->p, total_d, (unsigned long long*)scratch->p, ctx_.stream);
@@ -229,7 +278,7 @@ bool JoinOp::probe(const DBatch& right, DBatch* result) {
       BufPtr visited = dev_alloc_zero(ctx_, (size_t)bitmap_words(n) * 4);
       launch_mark_bits_u32((const uint32_t*)fr->p, kept, (uint32_t*)visited->p, ctx_.stream);
       BufPtr inv = dev_alloc(ctx_, (size_t)bitmap_words(n) * 4);
-      launch_bitmap_not((const uint32_t*)visited->p, n, (uint32_t*)inv->p, ctx_.stream);
+      launch_bitmap_not((const uint32_t*)visited->p, n, (uint32_t*)inv->p, ctx_.stream, probe_keep);
       unvisited = compact_indices(ctx_, (const uint32_t*)inv->p, n, &extra);
     }
     const int64_t m = kept + extra;
@@ -260,7 +309,7 @@ bool JoinOp::finish(DBatch* result) {
   BufPtr idx;
   if (n > 0) {
     BufPtr inv = dev_alloc(ctx_, (size_t)bitmap_words(n) * 4);
-    launch_bitmap_not((const uint32_t*)im.visited_left->p, n, (uint32_t*)inv->p, ctx_.stream);
+    launch_bitmap_not((const uint32_t*)im.visited_left->p, n, (uint32_t*)inv->p, ctx_.stream, im.view.build_keep);
     idx = compact_indices(ctx_, (const uint32_t*)inv->p, n, &m);
   } else {
     idx = dev_alloc(ctx_, 4);
@@ -268,7 +317,17 @@ bool JoinOp::finish(DBatch* result) {
   DBatch out;
   out.fields = out_fields_;
   out.n = m;
-  for (const DCol& c : im.left_single.cols) out.cols.push_back(gather_col_u32(ctx_, c, (const uint32_t*)idx->p, m));
+  for (size_t c = 0; c < im.left_single.cols.size(); c++) {
+    if (!im.needed.empty() && c < im.needed.size() && !im.needed[c]) {
+      DCol ph;
+      ph.dtype = SQLRS_DT_NULL;
+      ph.n = m;
+      ph.null_count = m;
+      out.cols.push_back(ph);
+    } else {
+      out.cols.push_back(gather_col_u32(ctx_, im.left_single.cols[c], (const uint32_t*)idx->p, m));
+    }
+  }
   for (size_t c = im.left_single.cols.size(); c < out_fields_.size(); c++) out.cols.push_back(null_col(ctx_, out_fields_[c].dtype, m));
   check_schema(out);
   *result = out;

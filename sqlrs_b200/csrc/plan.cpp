@@ -79,7 +79,8 @@ void Plan::run_agg_to_host(int idx, Result* res) {
   if (!agg_op_) agg_op_ = std::make_unique<AggOp>(n.aggs, n.group_by, n.group_names, simple, fused, opt_);
   else agg_op_->reset();
   AggOp& op = *agg_op_;
-  for (const DBatch& b : run(child)) op.push(b);
+  const Needed need = fusion() ? agg_child_needs(n, fused, width_of(child)) : Needed();
+  for (const DBatch& b : run(child, need)) op.push(b);
   op.finish_host(&res->arr, &res->sch);
   res->on_host = true;
   description_ += op.describe() + "; ";
@@ -107,7 +108,8 @@ void Plan::execute_partial(int64_t row_base) {
   else partial_op_->reset();
   partial_active_ = true;
   partial_op_->set_row_base(row_base);
-  for (const DBatch& b : run(child)) partial_op_->push(b);
+  const Needed need = fusion() ? agg_child_needs(n, fused, width_of(child)) : Needed();
+  for (const DBatch& b : run(child, need)) partial_op_->push(b);
   description_ += partial_op_->describe() + "; ";
   scan_kernel_ms_ = partial_op_->scan_kernel_ms();
   scan_kernel_launches_ = partial_op_->scan_kernel_launches();
@@ -144,8 +146,45 @@ void Plan::finish_partial() {
   partial_active_ = false;
 }
 
-std::vector<DBatch> Plan::run(int idx) {
+// ---- which input columns does an expression read?
+static void mark_refs(const ExprCopy& e, std::vector<bool>& needed, int offset = 0, int lo = 0, int hi = 1 << 30) {
+  for (const ExprNodeCopy& n : e)
+    if (n.op == SQLRS_OP_INPUT_REF && n.index >= lo && n.index < hi) {
+      const int k = n.index - offset;
+      if (k >= 0) {
+        if (k >= (int)needed.size()) needed.resize(k + 1, false);
+        needed[k] = true;
+      }
+    }
+}
+
+int Plan::width_of(int idx) {
+  const Node& n = nodes_[idx];
+  switch (n.kind) {
+    case SQLRS_NODE_SCAN: {
+      auto it = tables_.find(n.table_slot);
+      return it == tables_.end() || it->second.empty() ? 0 : (int)it->second[0].cols.size();
+    }
+    case SQLRS_NODE_FILTER: return width_of(n.child0);
+    case SQLRS_NODE_HASH_JOIN: return (int)n.join_fields.size();
+    default: return (int)(n.group_by.size() + n.aggs.size());
+  }
+}
+
+Plan::Needed Plan::agg_child_needs(const Node& agg, const ExprCopy& fused_pred, int child_width) const {
+  Needed need((size_t)std::max(child_width, 0), false);
+  for (const AggSpec& a : agg.aggs) mark_refs(a.arg, need);
+  for (const ExprCopy& g : agg.group_by) mark_refs(g, need);
+  mark_refs(fused_pred, need);
+  return need;
+}
+
+// Pull-based like the reference's stream tree, but a whole child result at a time and entirely in HBM.
+// `needed` prunes the columns materialising operators (Filter, HashJoin) gather: positions are kept, a
+// pruned column is a Null-typed placeholder that nothing above references.
+std::vector<DBatch> Plan::run(int idx, const Needed& needed) {
   Node& n = nodes_[idx];
+  auto is_needed = [&](size_t k) { return needed.empty() || (k < needed.size() && needed[k]); };
   switch (n.kind) {
     case SQLRS_NODE_SCAN: return tables_[n.table_slot];
     case SQLRS_NODE_FILTER: {
@@ -157,19 +196,61 @@ std::vector<DBatch> Plan::run(int idx) {
         n.filter_prog = std::make_unique<EvalProgram>(std::move(r));
       }
       description_ += "[Filter: sq_eval_kernel keep-mask + ballot compaction + gather] ";
+      Needed child_need = needed;
+      if (!child_need.empty()) mark_refs(n.predicate, child_need);
       std::vector<DBatch> out;
-      for (const DBatch& b : run(n.child0)) out.push_back(filter_batch(ctx_, *n.filter_prog, b));
+      for (const DBatch& b : run(n.child0, child_need)) {
+        if (needed.empty()) {
+          out.push_back(filter_batch(ctx_, *n.filter_prog, b));
+        } else {  // gather only what is read above
+          DBatch pruned = b;
+          DBatch res = filter_batch(ctx_, *n.filter_prog, b, &needed);
+          out.push_back(res);
+        }
+      }
       return out;
     }
     case SQLRS_NODE_SIMPLE_AGG:
     case SQLRS_NODE_HASH_AGG:
       fail(SQLRS_ERR_UNSUPPORTED, "an aggregate below another operator is not supported by the CUDA plan executor yet");
     case SQLRS_NODE_HASH_JOIN: {
-      description_ += "[HashJoin: hash build (CSR) + probe count/scan/write + gathers] ";
       JoinOp j(n.join_type, n.left_keys, n.right_keys, n.predicate, n.join_fields, opt_);
-      for (const DBatch& b : run(n.child0)) j.build_push(b);
+      int left = n.child0, right = n.child1;
+      ExprCopy build_pred, probe_pred;
+      if (fusion()) {  // Filters directly below the join run inside the join's key kernels
+        if (nodes_[left].kind == SQLRS_NODE_FILTER) {
+          build_pred = nodes_[left].predicate;
+          left = nodes_[left].child0;
+        }
+        if (nodes_[right].kind == SQLRS_NODE_FILTER) {
+          probe_pred = nodes_[right].predicate;
+          right = nodes_[right].child0;
+        }
+      }
+      const int nleft = width_of(left);
+      Needed left_need, right_need;
+      if (fusion() && nleft > 0) {
+        const int total = (int)n.join_fields.size();
+        left_need.assign((size_t)nleft, false);
+        right_need.assign((size_t)std::max(total - nleft, 0), false);
+        for (int k = 0; k < total; k++)
+          if (is_needed((size_t)k)) (k < nleft ? left_need[(size_t)k] : right_need[(size_t)(k - nleft)]) = true;
+        mark_refs(n.predicate, left_need, 0, 0, nleft);            // non-equi filter over the joined row
+        mark_refs(n.predicate, right_need, nleft, nleft, 1 << 30);
+        Needed out_need((size_t)total, false);                        // what the join itself must gather
+        for (int k = 0; k < total; k++) out_need[(size_t)k] = k < nleft ? left_need[(size_t)k] : right_need[(size_t)(k - nleft)];
+        j.set_needed_columns(out_need);
+        for (const ExprCopy& e : n.left_keys) mark_refs(e, left_need);   // the children must still deliver key / predicate inputs
+        for (const ExprCopy& e : n.right_keys) mark_refs(e, right_need);
+        mark_refs(build_pred, left_need);
+        mark_refs(probe_pred, right_need);
+      }
+      j.set_side_predicates(build_pred, probe_pred);
+      description_ += std::string("[HashJoin") + (build_pred.empty() && probe_pred.empty() ? "" : " + fused side Filter") +
+                      ": CSR hash build, probe count/scan/write, pruned gathers] ";
+      for (const DBatch& b : run(left, left_need)) j.build_push(b);
       std::vector<DBatch> out;
-      for (const DBatch& b : run(n.child1)) {
+      for (const DBatch& b : run(right, right_need)) {
         DBatch r;
         if (j.probe(b, &r)) out.push_back(r);
       }
@@ -197,7 +278,7 @@ void Plan::execute() {
     run_agg_to_host(root_, &results_.back());
     return;
   }
-  for (DBatch& b : run(root_)) {
+  for (DBatch& b : run(root_, Needed())) {
     results_.emplace_back();
     results_.back().dev = std::move(b);
   }
