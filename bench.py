@@ -46,57 +46,59 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+        "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+while True:
+    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+    print("s", time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), ",".join(k for k, b in bits.items() if r & b), flush=True)
+    time.sleep(0.02)
+"""
+
+
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region (NVML, every ~2 ms; nvidia-smi as fallback)."""
+    """SM clock + throttle reasons sampled DURING the timed region by a separate process (NVML every 20 ms), so
+    that the sampling neither holds this process's GIL nor sits between its CUDA calls."""
 
     def __init__(self, index):
-        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
-        self.max_mhz = None
-
-    def _run_nvml(self):
-        import pynvml as nv
-
-        nv.nvmlInit()
-        h = nv.nvmlDeviceGetHandleByIndex(self.index)
-        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
-                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
-        while not self.stop_flag:
-            mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-            self.samples.append((mhz, [k for k, b in bits.items() if r & b]))
-            time.sleep(0.002)
-
-    def _run_smi(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.max_mhz = float(out[1])
-                self.samples.append((float(out[0]), [n for n, v in zip(names, out[2:]) if v.strip().lower().startswith("active")]))
-            except Exception:
-                pass
-
-    def _run(self):
-        try:
-            self._run_nvml()
-        except Exception:
-            self._run_smi()
+        self.index, self.proc = index, None
 
     def start(self):
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
-        time.sleep(0.02)
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc.stdout.readline()  # "max ..." = the sampler is up
+        except Exception:
+            self.proc = None
 
-    def stop(self):
-        self.stop_flag = True
-        if self.thread:
-            self.thread.join(timeout=6)
-        sm = sorted(s[0] for s in self.samples)
-        reasons = sorted({r for s in self.samples for r in s[1]})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
+    def stop(self, t_begin=0.0, t_end=1e300):
+        """Summary of the samples taken in [t_begin, t_end] (time.time() of the timed region)."""
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.03)
+        self.proc.terminate()
+        out = self.proc.stdout.read()
+        sm, reasons = [], set()
+        for line in out.splitlines():
+            parts = line.split()
+            if len(parts) >= 3 and parts[0] == "s" and t_begin <= float(parts[1]) <= t_end:
+                sm.append(float(parts[2]))
+                if len(parts) > 3:
+                    reasons.update(x for x in parts[3].split(",") if x)
+        mx = None
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(nv.nvmlDeviceGetHandleByIndex(self.index), nv.NVML_CLOCK_SM))
+        except Exception:
+            pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def q1_on_host_batches(lib, plan_root, schemas, table, batch_rows, opts):
@@ -191,8 +193,9 @@ def run_gpu(args, rank, world, local_rank):
         kernel_ms, kernel_launches = [0.0], [0]
         group = sqdist.TorchGroup(dist, dev) if world > 1 else None
 
+        plan.push_table_device(0, table)  # zero-copy: the plan scans the table where it lies in HBM
+
         def step(timed):
-            plan.push_table_device(0, table)
             if world > 1:
                 res = sqdist.sharded_aggregate(plan, group, lo)
             else:
@@ -202,7 +205,6 @@ def run_gpu(args, rank, world, local_rank):
                 ms, nl = plan.scan_kernel_ms()
                 kernel_ms[0] += ms
                 kernel_launches[0] += nl
-            plan.reset()
             return res
 
         def barrier():
@@ -210,22 +212,29 @@ def run_gpu(args, rank, world, local_rank):
                 dist.barrier()
             torch.cuda.synchronize(dev)
 
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()  # before the warm-up: NVML start-up stays out of the timed region
         for _ in range(args.warmup):
             result = step(False)
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         launches0 = lib.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin = time.time()
         e0.record(stream)
+        step_wall = []
         for _ in range(args.steps):
+            t_s = time.perf_counter()
             result = step(True)
+            step_wall.append((time.perf_counter() - t_s) * 1e3)
         e1.record(stream)
         barrier()
+        t_end = time.time()
         launches = lib.kernel_launches() - launches0
         elapsed_ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+        step_wall.sort()
+        log(f"rank {rank}: step wall ms min/median/max = {step_wall[0]:.3f}/{step_wall[len(step_wall) // 2]:.3f}/{step_wall[-1]:.3f}")
         if world > 1:
             t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -248,6 +257,8 @@ def run_gpu(args, rank, world, local_rank):
                     a = a.view("float64")
                 arrays.append(pa.array(a))
             host_batch = pa.RecordBatch.from_arrays(arrays, schema=table.schema)
+
+            plan.reset()
 
             def e2e_step():
                 plan.push_table(0, host_batch)

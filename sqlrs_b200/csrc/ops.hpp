@@ -103,7 +103,7 @@ class AggOp {
   void merge_partials(const DBatch& partials);
   int partial_row_words() const;  // u64 words per packed partial row: 3 + keys + accumulator words
   void export_partials_device(uint64_t* dst, int64_t cap_rows);
-  void merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows);
+  void merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows, bool sync_after = false);
   void reset();  // forget all groups, keep compiled kernels and buffers
   void set_row_base(int64_t first_global_row) { rows_seen_ = first_global_row; }
 
@@ -134,6 +134,7 @@ class AggOp {
   bool use_global_ = false;
   uint32_t groups_known_ = 0;   // exact group count at the last counter read
   uint64_t groups_bound_ = 0;   // host-side upper bound since then
+  bool counters_stale_ = false; // device work since the last counter read may have added groups
   uint64_t* pinned_ = nullptr;  // pinned host staging of the packed result
   size_t pinned_words_ = 0;
   size_t part_entries_ = 0;     // CTA-partial scratch of sq_agg_small

@@ -417,6 +417,7 @@ void AggOp::reset() {
   use_global_ = false;
   groups_known_ = 0;
   groups_bound_ = 0;
+  counters_stale_ = false;
   scan_kernel_ms_ = 0;
   scan_kernel_launches_ = 0;
 }
@@ -427,6 +428,7 @@ void AggOp::read_counters(uint32_t* out4) {
   SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
   groups_known_ = out4[0];
   groups_bound_ = out4[0];
+  counters_stale_ = false;
   if (out4[2] & 2u) fail(SQLRS_ERR_INTERNAL, "group table overflow (internal sizing error)");
   if (out4[3] & 1u) {
     SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 3, 0, 4, ctx_.stream));
@@ -558,13 +560,19 @@ void AggOp::build_output(std::vector<Field>* fields, HostGroups* g) {
   const Compiled& c = *cache_.begin()->second;
   const int K = (int)c.key_dtypes.size(), W = (int)c.words.size();
   g->n = 0;
-  if (table_ && groups_known_ > 0) {
-    const uint32_t n = groups_known_;  // exact: every push / merge ends with a counter read
+  if (table_ && counters_stale_ && groups_bound_ > 4096) {  // a device-side merge skipped its counter read
+    uint32_t hc[4];
+    read_counters(hc);
+  }
+  if (table_ && (counters_stale_ ? groups_bound_ > 0 : groups_known_ > 0)) {
+    // exact count when the last push / merge ended with a counter read; else a (small) upper bound: the
+    // packed header then carries the exact count and this stays ONE synchronisation
+    uint32_t n = counters_stale_ ? (uint32_t)std::min<uint64_t>(groups_bound_, table_->capacity) : groups_known_;
     const int words = 3 + K + W;
     BufPtr packed = dev_alloc(ctx_, (size_t)(n + 1) * words * 8);
     SQ_CUDA(cudaMemsetAsync(packed->p, 0, (size_t)words * 8, ctx_.stream));
-    if (n > 256) table_pack_sorted(table_->view(), K, W, n, (uint64_t*)packed->p, ctx_.stream);  // ordered on the device
-    else launch_table_pack(table_->view(), K, W, (uint64_t*)packed->p, n, ctx_.stream);          // few groups: the host sorts
+    if (n > 256 && !counters_stale_) table_pack_sorted(table_->view(), K, W, n, (uint64_t*)packed->p, ctx_.stream);  // ordered on the device
+    else launch_table_pack(table_->view(), K, W, (uint64_t*)packed->p, n, ctx_.stream);                              // few groups: the host sorts
     const size_t host_words = (size_t)(n + 1) * words;
     if (pinned_words_ < host_words) {  // pinned staging, kept across runs: the D2H runs at PCIe speed
       if (pinned_) cudaFreeHost(pinned_);
@@ -576,7 +584,15 @@ void AggOp::build_output(std::vector<Field>* fields, HostGroups* g) {
     uint64_t* host = pinned_;
     SQ_CUDA(cudaMemcpyAsync(host, packed->p, host_words * 8, cudaMemcpyDeviceToHost, ctx_.stream));
     ctx_.sync();
-    if (host[0] != n) fail(SQLRS_ERR_INTERNAL, "group count changed under finalisation");
+    if (counters_stale_) {
+      if (host[0] > n) fail(SQLRS_ERR_INTERNAL, "group count exceeds its bound under finalisation");
+      n = (uint32_t)host[0];
+      groups_known_ = n;
+      groups_bound_ = n;
+      counters_stale_ = false;
+    } else if (host[0] != n) {
+      fail(SQLRS_ERR_INTERNAL, "group count changed under finalisation");
+    }
     g->n = n;
     g->hash.resize(n);
     g->min_row.resize(n);
@@ -755,6 +771,7 @@ void AggOp::clear_partials() {
   use_global_ = false;
   groups_known_ = 0;
   groups_bound_ = 0;
+  counters_stale_ = false;
 }
 
 const int* AggOp::device_word_ops() {
@@ -779,7 +796,7 @@ const int* AggOp::device_word_ops() {
 }
 
 // folds n_bufs packed partial buffers (device memory, layout of export_partials_device) into the table
-void AggOp::merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows) {
+void AggOp::merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows, bool sync_after) {
   ctx_.activate();
   if (cache_.empty()) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before any batch was aggregated (accumulator layout unknown)");
   seen_batch_ = true;
@@ -795,8 +812,13 @@ void AggOp::merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_r
   }
   launch_table_merge_packed(table_->view(), table_->n_keys, table_->n_acc, ops, opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY ? 1 : 0, src, n_bufs,
                             (uint64_t)cap_rows, ctx_.stream);
-  uint32_t hc[4];
-  read_counters(hc);
+  groups_bound_ += extra;
+  if (sync_after) {
+    uint32_t hc[4];
+    read_counters(hc);
+  } else {
+    counters_stale_ = true;  // the next reader of the group count fetches it (build_output: with the packed result)
+  }
 }
 
 // folds a batch of partial groups (layout of export_partials, device resident columns) into the table
@@ -820,7 +842,7 @@ void AggOp::merge_partials(const DBatch& p) {
     SQ_CUDA(cudaMemcpy2DAsync((uint64_t*)packed->p + words + k, (size_t)words * 8, p.cols[k].data, w, w, (size_t)n, cudaMemcpyDeviceToDevice,
                               ctx_.stream));
   }
-  merge_partials_device((const uint64_t*)packed->p, 1, n);  // ends with a synchronising counter read: `header` stays valid
+  merge_partials_device((const uint64_t*)packed->p, 1, n, true);  // ends with a synchronising counter read: `header` stays valid
 }
 
 }  // namespace sq

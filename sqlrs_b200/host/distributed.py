@@ -152,7 +152,7 @@ def _device_exchange(plan, group: TorchGroup, cap_rows: int):
     return result if group.rank == 0 else []
 
 
-def sharded_aggregate(plan, group: TorchGroup, row_base: int = 0, device_cap_rows: int = 1024) -> List[pa.RecordBatch]:
+def sharded_aggregate(plan, group: TorchGroup, row_base: int = 0, device_cap_rows: int = 256) -> List[pa.RecordBatch]:
     """Runs `plan` (root = aggregate) over the shard pushed on this rank; rank 0 returns the final batches."""
     lib = plan.lib
     lib.check(lib.plan_execute_partial(plan.handle, row_base))
