@@ -23,6 +23,9 @@ variants = {
     "simple_same_aggs": PhysicalSimpleAgg(plan.agg_funcs, PhysicalFilter(pred, PhysicalTableScan(0))),
     "one_key": PhysicalHashAgg(plan.agg_funcs, [col["l_returnflag"]], PhysicalFilter(pred, PhysicalTableScan(0))),
     "count_only": PhysicalHashAgg([AggFunc("Count", [col["l_quantity"]])], plan.group_by, PhysicalFilter(pred, PhysicalTableScan(0))),
+    "by_qty_50g": PhysicalHashAgg(plan.agg_funcs, [col["l_quantity_i64"]], PhysicalFilter(pred, PhysicalTableScan(0))),
+    "by_shipdate_2500g": PhysicalHashAgg(plan.agg_funcs, [col["l_shipdate"]], PhysicalFilter(pred, PhysicalTableScan(0))),
+    "by_qty_ship_125kg": PhysicalHashAgg(plan.agg_funcs, [col["l_quantity_i64"], col["l_shipdate"]], PhysicalFilter(pred, PhysicalTableScan(0))),
     "sum1": PhysicalHashAgg([AggFunc("Sum", [col["l_quantity"]])], plan.group_by, PhysicalFilter(pred, PhysicalTableScan(0))),
 }
 stream = torch.cuda.Stream()

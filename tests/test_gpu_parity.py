@@ -430,3 +430,93 @@ def test_plan_can_be_executed_repeatedly(cuda_lib, oracle):
         q.push_table(0, t.slice(5000))
         assert_batches_match(got, q.run(), rtol=FTOL)
     p.close()
+
+
+# ------------------------------------------------------------------ plan executor: fused side Filters, column pruning
+def _random_join_plan(rng, join_type, with_join_filter, root_agg):
+    """HashAgg?(HashJoin(Filter(scan 0), Filter(scan 1))) over two random tables."""
+    from sqlrs_b200.host.plan import PhysicalFilter, PhysicalHashAgg, PhysicalHashJoin, PhysicalTableScan
+
+    dtypes = [I64, I32, F64, I64]
+    left = random_batch(rng, 400, dtypes, null_frac=0.1, small_ints=True, names=["la", "lb", "lc", "ld"])
+    right = random_batch(rng, 700, dtypes, null_frac=0.1, small_ints=True, names=["ra", "rb", "rc", "rd"])
+    schema = pa.schema([pa.field("l." + f.name, f.type, True) for f in left.schema] + [pa.field("r." + f.name, f.type, True) for f in right.schema])
+    lpred = bind_binary_op(InputRef(3, I64), ">", Constant(-4))
+    rpred = BinaryOp("OR", bind_binary_op(InputRef(3, I64), "<", Constant(5)), BinaryOp(">", InputRef(2, F64), Constant(50.0), BOOL), BOOL)
+    cond = ex.JoinCondition([(InputRef(0, I64), InputRef(0, I64))], BinaryOp("<", InputRef(2, F64), InputRef(6, F64), BOOL) if with_join_filter else None)
+    join = PhysicalHashJoin(PhysicalFilter(lpred, PhysicalTableScan(0)), PhysicalFilter(rpred, PhysicalTableScan(1)), join_type, cond, schema)
+    root = join
+    if root_agg:
+        root = PhysicalHashAgg([AggFunc("Sum", [InputRef(6, F64)]), AggFunc("Count", [InputRef(1, I32)]), AggFunc("Max", [InputRef(7, I64)])],
+                               [InputRef(4, I64), InputRef(1, I32)], join)
+    return root, {0: left.schema, 1: right.schema}, {0: left, 1: right}
+
+
+@pytest.mark.parametrize("join_type", ["Inner", "Left", "Right", "Full"])
+@pytest.mark.parametrize("with_join_filter", [False, True])
+@pytest.mark.parametrize("root_agg", [False, True])
+def test_plan_join_with_side_filters(cuda_lib, oracle, join_type, with_join_filter, root_agg):
+    """Filters below a join run inside the join's key kernels and unread columns are not gathered when the plan is
+    fused; the result must equal operator-at-a-time execution and the oracle, row order included."""
+    rng = np.random.default_rng(hash((join_type, with_join_filter, root_agg)) % 2**31)
+    root, schemas, tables = _random_join_plan(rng, join_type, with_join_filter, root_agg)
+    opts = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    exp, _ = _run_plan(oracle, root, schemas, tables, None, **opts)
+    for flags in (0, ffi.FLAG_NO_FUSION):
+        for batch_rows in (None, 150):
+            got, desc = _run_plan(cuda_lib, root, schemas, tables, batch_rows, flags=flags, **opts)
+            if batch_rows is None:
+                assert_batches_match(got, exp, rtol=FTOL)
+            else:
+                exp_b, _ = _run_plan(oracle, root, schemas, tables, batch_rows, **opts)
+                assert_batches_match(got, exp_b, rtol=FTOL)
+            assert ("fused side Filter" in desc) == (flags == 0)
+
+
+@pytest.mark.parametrize("key_type", [I32, F64, BOOL])
+def test_group_by_and_join_on_other_key_types(cuda_lib, oracle, key_type):
+    """Int32 / Float64 (incl. -0.0, NaN, inf) / Boolean keys: hash_one of the reference's other primitive types"""
+    rng = np.random.default_rng(int(key_type) + 40)
+    n = 3000
+    if key_type == F64:
+        pool = np.array([0.0, -0.0, 1.5, -1.5, np.inf, -np.inf, np.nan, 1e300, 2.5, 3.5])
+        keys = pa.array(pool[rng.integers(0, len(pool), n)], mask=rng.random(n) < 0.05)
+    elif key_type == BOOL:
+        keys = pa.array(rng.integers(0, 2, n).astype(bool), mask=rng.random(n) < 0.1)
+    else:
+        keys = pa.array(rng.integers(-3, 4, n).astype(np.int32), mask=rng.random(n) < 0.1)
+    vals = pa.array(rng.integers(-100, 100, n).astype(np.int64))
+    b = pa.RecordBatch.from_arrays([keys, vals], names=["k", "v"])
+    aggs, groups = [AggFunc("Sum", [InputRef(1, I64)]), AggFunc("Count", [InputRef(0, key_type)])], [InputRef(0, key_type)]
+    for mm in (ffi.MATCH_HASH_ONLY, ffi.MATCH_HASH_AND_KEY):
+        got, exp = both(lambda l: ex.try_collect(ex.HashAggExecutor(aggs, groups, [b.slice(0, 1000), b.slice(1000)], lib=l,
+                                                                    options=l.options(match_mode=mm, count_mode=ffi.COUNT_SQL_ACCUMULATE)).execute()), cuda_lib, oracle)
+        g, e = rows_of(got), rows_of(exp)
+        assert len(g) == len(e)
+        for x, y in zip(g, e):
+            same_key = (x[0] == y[0]) or (x[0] is not None and y[0] is not None and x[0] != x[0] and y[0] != y[0])
+            assert same_key and x[1:] == y[1:], (x, y)
+        small = b.slice(0, 60)
+        schema = pa.schema([pa.field("l.k", keys.type), pa.field("l.v", pa.int64()), pa.field("r.k", keys.type), pa.field("r.v", pa.int64())])
+        cond = ex.JoinCondition([(InputRef(0, key_type), InputRef(0, key_type))])
+        gj, ej = both(lambda l: ex.try_collect(ex.HashJoinExecutor([small], [b.slice(60, 200)], "Full", cond, schema, lib=l,
+                                                                   options=l.options(match_mode=mm)).execute()), cuda_lib, oracle)
+        assert [(r[1], r[3]) for r in rows_of(gj)] == [(r[1], r[3]) for r in rows_of(ej)]
+
+
+def test_many_groups_with_growth_across_batches(cuda_lib, oracle):
+    """cardinality climbs batch by batch: the HBM table is re-hashed several times while hash-only key fix-ups are pending"""
+    rng = np.random.default_rng(321)
+    batches = []
+    for i, n in enumerate((500, 5000, 60000, 250000)):
+        k = pa.array(rng.integers(0, 40 * (i + 1) ** 4, n).astype(np.int64))
+        k2 = pa.array(rng.integers(0, 3, n).astype(np.int64))
+        v = pa.array(rng.integers(-1000, 1000, n).astype(np.int64))
+        f = pa.array(np.round(rng.normal(0, 10, n), 3), mask=rng.random(n) < 0.2)
+        batches.append(pa.RecordBatch.from_arrays([k, k2, v, f], names=["k", "k2", "v", "f"]))
+    aggs = [AggFunc("Sum", [InputRef(2, I64)]), AggFunc("Count", [InputRef(3, F64)]), AggFunc("Min", [InputRef(3, F64)]), AggFunc("Sum", [InputRef(3, F64)])]
+    groups = [InputRef(0, I64), InputRef(1, I64)]
+    for mm in (ffi.MATCH_HASH_ONLY, ffi.MATCH_HASH_AND_KEY):
+        got, exp = both(lambda l: ex.try_collect(ex.HashAggExecutor(aggs, groups, batches, lib=l, options=l.options(match_mode=mm)).execute()), cuda_lib, oracle)
+        assert got[0].num_rows > 10000
+        assert_batches_match(got, exp, rtol=FTOL)

@@ -22,7 +22,9 @@ def rows_of(batches):
     return [tuple(r) for r in out]
 
 
-def assert_rows_equal(got, want, rtol=0.0, ordered=True):
+def assert_rows_equal(got, want, rtol=0.0, ordered=True, atol=1e-9):
+    """Floats: |a-b| <= rtol*max(|a|,|b|) + atol when rtol > 0 (atol covers sums that cancel to ~0, where a
+    relative bound is meaningless: summation order differs between the CPU batches and the GPU atomics)."""
     if not ordered:
         key = lambda r: tuple((x is None, 0 if x is None else x) for x in r)
         got, want = sorted(got, key=key), sorted(want, key=key)
@@ -33,7 +35,7 @@ def assert_rows_equal(got, want, rtol=0.0, ordered=True):
             if isinstance(b, float) and isinstance(a, float) and rtol > 0:
                 if math.isnan(a) and math.isnan(b):
                     continue
-                assert abs(a - b) <= rtol * max(abs(a), abs(b)), f"row {i}: {g} != {w}"
+                assert abs(a - b) <= rtol * max(abs(a), abs(b)) + atol, f"row {i}: {g} != {w}"
             else:
                 assert a == b or (isinstance(a, float) and isinstance(b, float) and math.isnan(a) and math.isnan(b)), f"row {i}: {g} != {w}"
 
