@@ -88,6 +88,19 @@ class TorchGroup:
             out.append(bufs[src][off:off + matrix[src][self.rank]].cpu().numpy().tobytes())
         return out
 
+    def all_gather_bytes(self, payload: bytes) -> List[bytes]:
+        torch, dist, W = self.torch, self.dist, self.world
+        size = torch.tensor([len(payload)], dtype=torch.int64, device=self.device)
+        sizes = [torch.empty(1, dtype=torch.int64, device=self.device) for _ in range(W)]
+        dist.all_gather(sizes, size)
+        sz = [int(s.item()) for s in sizes]
+        send = torch.zeros(max(max(sz), 1), dtype=torch.uint8, device=self.device)
+        if payload:
+            send[:len(payload)] = self._tensor(payload)
+        bufs = [torch.empty_like(send) for _ in range(W)]
+        dist.all_gather(bufs, send)
+        return [bufs[r][:sz[r]].cpu().numpy().tobytes() for r in range(W)]
+
     def gather_bytes(self, payload: bytes, dst: int = 0) -> Optional[List[bytes]]:
         torch, dist, W = self.torch, self.dist, self.world
         size = torch.tensor([len(payload)], dtype=torch.int64, device=self.device)
@@ -102,6 +115,18 @@ class TorchGroup:
         if self.rank != dst:
             return None
         return [bufs[r][:sz[r]].cpu().numpy().tobytes() for r in range(W)]
+
+
+def all_gather_batches(group: "TorchGroup", batches: List[pa.RecordBatch], schema: pa.Schema) -> List[pa.RecordBatch]:
+    """Every rank receives every rank's batches, in rank order (the build-side broadcast of a join)."""
+    table = pa.Table.from_batches(batches, schema=schema).combine_chunks()
+    payload = _to_bytes(table.to_batches()[0]) if table.num_rows else _to_bytes(pa.RecordBatch.from_pylist([], schema=schema))
+    out = []
+    for data in group.all_gather_bytes(payload):
+        b = _from_bytes(data)
+        if b.num_rows:
+            out.append(b)
+    return out
 
 
 def _export_partials(plan) -> pa.RecordBatch:
@@ -174,3 +199,37 @@ def sharded_aggregate(plan, group: TorchGroup, row_base: int = 0, device_cap_row
     lib.check(lib.plan_finish_partial(plan.handle))
     result = plan.collect()
     return result if group.rank == 0 else []
+
+
+def broadcast_build_join_aggregate(builder, group: TorchGroup, stage1, stage1_schemas, stage1_tables, stage2, stage2_schemas, stage2_tables,
+                                   build_slot: int) -> List[pa.RecordBatch]:
+    """Broadcast-build / partitioned-probe execution of a left-deep join tree under an aggregate (SURVEY.md §8e, Q3').
+
+    stage1: a plan whose root is a join probed by this rank's shard (its build side is small and present in full on
+    every rank); the join output of all ranks — all-gathered in rank order, which is the single-process output
+    order because shards are contiguous — becomes table `build_slot` of stage2 on every rank.
+    stage2: root = aggregate over a join whose build side is that table and whose probe side is this rank's shard;
+    it runs through `sharded_aggregate` (partial aggregation + exchange of the groups).
+    `stage*_tables`: {slot: RecordBatch | tpch.DeviceTable}."""
+    def push(plan, tables):
+        for slot, t in tables.items():
+            if isinstance(t, pa.RecordBatch):
+                plan.push_table(slot, t)
+            else:
+                plan.push_table_device(slot, t)
+
+    p1 = builder.build(stage1, stage1_schemas)
+    push(p1, stage1_tables)
+    local = p1.run()
+    p1.close()
+    build_side = all_gather_batches(group, local, stage1.output_schema(stage1_schemas))
+    p2 = builder.build(stage2, stage2_schemas)
+    for b in build_side:
+        p2.push_table(build_slot, b)
+    if not build_side:
+        p2.push_table(build_slot, pa.RecordBatch.from_pylist([], schema=stage2_schemas[build_slot]))
+    push(p2, stage2_tables)
+    # rank-major first-appearance order: join output rows of rank r come after those of rank r-1
+    result = sharded_aggregate(p2, group, row_base=group.rank << 40)
+    p2.close()
+    return result

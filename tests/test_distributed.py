@@ -77,3 +77,49 @@ def test_partition_by_owner_is_a_partition():
     assert sum(p.num_rows for p in parts) == len(h)
     for r, p in enumerate(parts):
         assert all((int(v) % 2**64) % 3 == r for v in p.column(0).to_pylist())
+
+
+def _q3_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+
+    from sqlrs_b200.host import distributed as sqdist
+    from sqlrs_b200.host import ffi, tpch
+    from sqlrs_b200.host.plan import ExecutorBuilder
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lib = ffi.Library(os.path.join(ROOT, "oracle", "liboracle.so"), "sqlrs_oracle_")
+    d = tpch.dims(0.02)
+    opts = lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    builder = ExecutorBuilder(lib, opts)
+    (s1, s1_schemas), (s2, s2_schemas) = tpch.q3_stage_plans()
+
+    def shard(table, cols):
+        n = tpch.num_rows(lib, d, table)
+        return tpch.host_table(lib, d, table, n * rank // world, n * (rank + 1) // world, columns=cols)
+
+    customer = tpch.host_table(lib, d, tpch.CUSTOMER, columns=tpch.Q3_CUSTOMER_COLUMNS)  # the small build side: everywhere
+    group = sqdist.TorchGroup(dist, torch.device("cpu"))
+    result = sqdist.broadcast_build_join_aggregate(builder, group, s1, s1_schemas, {0: customer, 1: shard(tpch.ORDERS, tpch.Q3_ORDERS_COLUMNS)},
+                                                   s2, s2_schemas, {1: shard(tpch.LINEITEM, tpch.Q3_LINEITEM_COLUMNS)}, build_slot=0)
+    if rank == 0:
+        plan, schemas = tpch.q3_plan()
+        whole = builder.build(plan, schemas)
+        whole.push_table(0, customer)
+        whole.push_table(1, tpch.host_table(lib, d, tpch.ORDERS, columns=tpch.Q3_ORDERS_COLUMNS))
+        whole.push_table(2, tpch.host_table(lib, d, tpch.LINEITEM, columns=tpch.Q3_LINEITEM_COLUMNS))
+        expect = whole.run()
+        from util import assert_batches_match
+
+        assert expect[0].num_rows > 50
+        assert_batches_match(result, expect, rtol=1e-9)
+        open(os.path.join(out_dir, "ok"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_broadcast_build_join_matches_single_process(tmp_path, oracle):
+    """Q3' with the join build sides broadcast and the probe sides sharded over 2 ranks == single-process Q3'"""
+    mp.spawn(_q3_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").read_text() == "ok"
