@@ -34,6 +34,7 @@ struct SqTable {      // the operator's persistent group table in HBM (SoA, capa
 };
 #define SQ_STATUS_OVERFLOW 1u   /* sq_agg_small: more groups than SQ_SLOTS in some CTA */
 #define SQ_STATUS_FULL 2u       /* table ran out of slots (host sized it wrongly) */
+#define SQ_STATUS_OVERFLOW2 4u  /* sq_agg_medium: more groups than SQ_MSLOTS in some CTA */
 
 struct SqPartial {    // CTA partials of sq_agg_small: [cta][slot]
   u32* state;
@@ -190,6 +191,7 @@ extern "C" __global__ void __launch_bounds__(SQ_BLOCK) sq_agg_small(SqIn in, i64
   bool overflow = false;
   const i64 tile = (i64)SQ_BLOCK * SQ_UNROLL;
   for (i64 base = (i64)blockIdx.x * tile; base < n; base += (i64)gridDim.x * tile) {
+    if (*((volatile u32*)flags) != 0u || (*((volatile u32*)status) & SQ_STATUS_OVERFLOW) != 0u) break;  // some CTA overflowed: the batch is re-run anyway
     // all loads of the tile are issued before the first use: SQ_UNROLL x columns requests in flight per thread
     SqRow o[SQ_UNROLL];
     bool live[SQ_UNROLL];
@@ -207,7 +209,11 @@ extern "C" __global__ void __launch_bounds__(SQ_BLOCK) sq_agg_small(SqIn in, i64
       int g = -1;
       if (live[u]) {
         g = sq_small_lookup(tab, o[u]);
-        overflow |= g < 0;
+        if (g < 0) {
+          overflow = true;
+          *((volatile u32*)flags) = 1u;
+          atomicOr(status, SQ_STATUS_OVERFLOW);  // lets the other CTAs stop early
+        }
       }
       // the lookup is the only divergent code: reconverge before the (uniform, predicated) accumulate —
       // without this the warp stays split per group and every later load is replayed per fragment
@@ -277,7 +283,7 @@ extern "C" __global__ void __launch_bounds__(SQ_BLOCK) sq_agg_small(SqIn in, i64
 // folds the CTA partials of one batch into the operator's table; one thread per (cta, slot)
 extern "C" __global__ void __launch_bounds__(128) sq_agg_merge(SqPartial part, int n_entries, SqTable table, i64 batch_no,
                                                                 u32* __restrict__ status) {
-  if ((*((volatile u32*)status) & SQ_STATUS_OVERFLOW) != 0u) return;
+  if ((*((volatile u32*)status) & (SQ_STATUS_OVERFLOW | SQ_STATUS_OVERFLOW2)) != 0u) return;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_entries) return;
   if (part.state[e] != 2u) return;
@@ -295,6 +301,143 @@ extern "C" __global__ void __launch_bounds__(128) sq_agg_merge(SqPartial part, i
 #pragma unroll
   for (int w = 0; w < SQ_NACC; w++)
     sq_acc_merge_global(&table.acc[(size_t)w * table.capacity + slot], w, part.acc[(size_t)e * SQ_NACC + w], batch_no);
+}
+
+// ------------------------------------------------------------------------------------------
+// sq_agg_medium — up to SQ_MSLOTS groups per CTA (hundreds): ONE copy of the accumulators per CTA in shared
+// memory, updated with shared-memory atomics (contention is spread over many groups here, unlike the
+// few-group case that needs private copies), then flushed into the HBM table once per CTA.
+//   u64 macc[(W+1)][M]; slot table with 2*M entries: thash, tkeys[K], tknull, tstate, tgroup; ngroups; flags
+#define SQ_MTSLOTS (2 * SQ_MSLOTS)
+
+__device__ __forceinline__ int sq_medium_lookup(u64* thash, u64* tkeys, u32* tknull, u32* tstate, u32* tgroup, u32* ngroups, const SqRow& o) {
+  u32 s = sq_mix32(o.h) & (SQ_MTSLOTS - 1);
+  for (int probes = 0; probes < SQ_MTSLOTS;) {
+    if (*((volatile u32*)ngroups) > SQ_MSLOTS) return -1;  // already overflowed: do not walk a full table
+    const u32 st = *((volatile u32*)&tstate[s]);
+    if (st == 2u) {
+      if (*((volatile u64*)&thash[s]) == o.h) {
+#if SQ_MATCH_KEYS
+        bool same = *((volatile u32*)&tknull[s]) == o.knull;
+#pragma unroll
+        for (int k = 0; k < SQ_NKEYS; k++) same = same && (*((volatile u64*)&tkeys[s * (SQ_NKEYS > 0 ? SQ_NKEYS : 1) + k]) == o.kb[k]);
+        if (same) return (int)*((volatile u32*)&tgroup[s]);
+#else
+        return (int)*((volatile u32*)&tgroup[s]);
+#endif
+      }
+      s = (s + 1) & (SQ_MTSLOTS - 1);
+      probes++;
+      continue;
+    }
+    if (st == 0u && atomicCAS(&tstate[s], 0u, 1u) == 0u) {
+      const u32 g = atomicAdd(ngroups, 1u);
+      thash[s] = o.h;
+      if (g < SQ_MSLOTS) {
+#pragma unroll
+        for (int k = 0; k < SQ_NKEYS; k++) tkeys[s * (SQ_NKEYS > 0 ? SQ_NKEYS : 1) + k] = o.kb[k];
+        tknull[s] = o.knull;
+        tgroup[s] = g;
+      } else {
+        tgroup[s] = 0xffffffffu;
+      }
+      __threadfence_block();
+      atomicExch(&tstate[s], 2u);
+      return g >= SQ_MSLOTS ? -1 : (int)g;
+    }
+  }
+  return -1;
+}
+
+extern "C" __global__ void __launch_bounds__(256) sq_agg_medium(SqIn in, i64 n, i64 row_base, SqPartial part,
+                                                                 u32* __restrict__ status, u32* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char sq_smem[];
+  u64* macc = (u64*)sq_smem;
+  u64* thash = macc + (size_t)SQ_ACC_WORDS * SQ_MSLOTS;
+  u64* tkeys = thash + SQ_MTSLOTS;
+  u32* tknull = (u32*)(tkeys + SQ_MTSLOTS * (SQ_NKEYS > 0 ? SQ_NKEYS : 1));
+  u32* tstate = tknull + SQ_MTSLOTS;
+  u32* tgroup = tstate + SQ_MTSLOTS;
+  u32* ngroups = tgroup + SQ_MTSLOTS;
+  u32* flags = ngroups + 1;
+  const int tid = threadIdx.x;
+  if ((*((volatile u32*)status) & SQ_STATUS_OVERFLOW2) != 0u) return;
+
+  for (int i = tid; i < SQ_ACC_WORDS * SQ_MSLOTS; i += 256) {
+    const int w = i / SQ_MSLOTS;
+    macc[i] = (w == SQ_NACC) ? SQ_EMPTY_ROW : sq_acc_identity(w);
+  }
+  for (int s = tid; s < SQ_MTSLOTS; s += 256) tstate[s] = 0u;
+  if (tid == 0) {
+    *ngroups = 0u;
+    *flags = 0u;
+  }
+  __syncthreads();
+
+  bool any_err = false, overflow = false;
+  const i64 tile = (i64)256 * SQ_MUNROLL;
+  for (i64 base = (i64)blockIdx.x * tile; base < n; base += (i64)gridDim.x * tile) {
+    if (*((volatile u32*)flags) != 0u || (*((volatile u32*)status) & SQ_STATUS_OVERFLOW2) != 0u) break;  // some CTA overflowed: the batch is re-run anyway
+    SqRow o[SQ_MUNROLL];
+    bool live[SQ_MUNROLL];
+#pragma unroll
+    for (int u = 0; u < SQ_MUNROLL; u++) {
+      const i64 r = base + (i64)u * 256 + tid;
+      const bool inb = r < n;
+      bool e0 = false, e1 = false;
+      sq_row(in, inb ? r : n - 1, o[u], e0, e1);
+      live[u] = inb && o[u].pass;
+      any_err |= (inb && e0) || (live[u] && e1);
+    }
+#pragma unroll
+    for (int u = 0; u < SQ_MUNROLL; u++) {
+      int g = -1;
+      if (live[u]) {
+        g = sq_medium_lookup(thash, tkeys, tknull, tstate, tgroup, ngroups, o[u]);
+        if (g < 0) {
+          overflow = true;
+          *((volatile u32*)flags) = 1u;
+        }
+      }
+      __syncwarp();
+      if (g >= 0) {
+        u64 local[SQ_NACC > 0 ? SQ_NACC : 1];
+#pragma unroll
+        for (int w = 0; w < SQ_NACC; w++) local[w] = sq_acc_identity(w);
+        sq_acc_update(local, 1, o[u]);
+#pragma unroll
+        for (int w = 0; w < SQ_NACC; w++) sq_acc_merge_shared(&macc[(size_t)w * SQ_MSLOTS + g], w, local[w]);
+        atomicMin(&macc[(size_t)SQ_NACC * SQ_MSLOTS + g], (u64)(row_base + base + (i64)u * 256 + tid));
+      }
+      __syncwarp();
+    }
+  }
+  if (any_err) atomicOr(err, 1u);
+  if (overflow) *((volatile u32*)flags) = 1u;
+  __syncthreads();
+  if (*((volatile u32*)flags) != 0u) {  // more than SQ_MSLOTS groups in this CTA: the host reruns the batch on sq_agg_global
+    if (tid == 0) atomicOr(status, SQ_STATUS_OVERFLOW2);
+    return;
+  }
+  if ((*((volatile u32*)status) & SQ_STATUS_OVERFLOW2) != 0u) return;  // another CTA overflowed: nothing of this batch counts
+  // flush: the CTA's groups go to the scratch area; sq_agg_merge folds them into the HBM table only if NO
+  // CTA overflowed (a flush straight into the table could not be undone before the re-run)
+  for (int g = tid; g < SQ_MSLOTS; g += 256) part.state[(size_t)blockIdx.x * SQ_MSLOTS + g] = 0u;
+  __syncthreads();
+  for (int s = tid; s < SQ_MTSLOTS; s += 256) {
+    if (tstate[s] != 2u) continue;
+    const u32 g = tgroup[s];
+    if (g >= SQ_MSLOTS) continue;
+    const size_t e = (size_t)blockIdx.x * SQ_MSLOTS + g;
+    part.state[e] = 2u;
+    part.hash[e] = thash[s];
+    part.knull[e] = tknull[s];
+    part.min_row[e] = macc[(size_t)SQ_NACC * SQ_MSLOTS + g];
+#pragma unroll
+    for (int k = 0; k < SQ_NKEYS; k++) part.keys[e * SQ_NKEYS + k] = tkeys[s * (SQ_NKEYS > 0 ? SQ_NKEYS : 1) + k];
+#pragma unroll
+    for (int w = 0; w < SQ_NACC; w++) part.acc[e * SQ_NACC + w] = macc[(size_t)w * SQ_MSLOTS + g];
+  }
 }
 
 // many groups: straight into the HBM table

@@ -113,6 +113,7 @@ class AggOp {
   Compiled& compiled_for(const DBatch& batch);
   std::string generate(const std::vector<ColInfo>& cols, Compiled& comp);
   void init_table_contents(Table& t);
+  void ensure_partial_scratch(size_t entries, int K, size_t W);
   void read_counters(uint32_t* out4);
   void check_partial_supported() const;
   const int* device_word_ops();
@@ -131,7 +132,7 @@ class AggOp {
   std::unique_ptr<Table> table_;
   int64_t rows_seen_ = 0, batches_seen_ = 0;
   bool seen_batch_ = false;
-  bool use_global_ = false;
+  int level_ = 0;  // sticky per operator: 0 sq_agg_small, 1 sq_agg_medium, 2 sq_agg_global
   uint32_t groups_known_ = 0;   // exact group count at the last counter read
   uint64_t groups_bound_ = 0;   // host-side upper bound since then
   bool counters_stale_ = false; // device work since the last counter read may have added groups

@@ -108,7 +108,10 @@ struct HostGroups {
 };
 
 struct AggOp::Compiled {
-  JitKernel *small = nullptr, *merge = nullptr, *global = nullptr, *fixkeys = nullptr;
+  JitKernel *small = nullptr, *merge = nullptr, *global = nullptr, *fixkeys = nullptr, *medium = nullptr;
+  int mslots = 0, munroll = 4, medium_grid = 0;  // sq_agg_medium: groups per CTA, rows per thread per trip
+  size_t medium_smem = 0;
+  bool medium_ok = false;
   std::vector<AggPlan> aggs;
   std::vector<WordPlan> words;
   std::vector<int> key_dtypes;
@@ -166,6 +169,12 @@ AggOp::Compiled& AggOp::compiled_for(const DBatch& batch) {
   comp->merge = jit_get("agg", src, "sq_agg_merge");
   comp->global = jit_get("agg", src, "sq_agg_global");
   comp->fixkeys = jit_get("agg", src, "sq_agg_fixkeys");
+  if (comp->medium_ok) {
+    comp->medium = jit_get("agg", src, "sq_agg_medium");
+    int per_sm = jit_max_blocks_per_sm(comp->medium, 256, comp->medium_smem);
+    if (per_sm < 1) comp->medium_ok = false;
+    comp->medium_grid = device_sm_count(ctx_.device) * std::max(per_sm, 1);
+  }
   if (comp->small_ok) {
     int per_sm = jit_max_blocks_per_sm(comp->small, comp->block, comp->small_smem);
     if (per_sm < 1) comp->small_ok = false;
@@ -299,11 +308,24 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
   while (comp->block > 32 && smem_for(comp->block) > 200 * 1024) comp->block /= 2;
   comp->small_ok = smem_for(comp->block) <= 200 * 1024;
   comp->small_smem = smem_for(comp->block);
+  // sq_agg_medium: one accumulator copy per CTA for up to M groups; M = the largest power of two whose shared
+  // memory (accumulators + 2M-entry slot table) stays <= 72 KB, i.e. three 256-thread CTAs per SM
+  auto medium_smem_for = [&](int M) { return (size_t)(W + 1) * M * 8 + (size_t)2 * M * (8 + 8 * std::max(K, 1) + 12) + 16; };
+  comp->mslots = 0;
+  for (int M = 2048; M >= 64; M /= 2)
+    if (medium_smem_for(M) <= 72 * 1024) {
+      comp->mslots = M;
+      break;
+    }
+  comp->medium_ok = K > 0 && comp->mslots > comp->slots;
+  comp->medium_smem = comp->medium_ok ? medium_smem_for(comp->mslots) : 0;
+  comp->munroll = prog.n_loaded_columns() <= 8 ? 4 : 2;
 
   std::ostringstream s;
   s << gen_input_decls(cols);
   s << "#define SQ_NKEYS " << K << "\n#define SQ_NACC " << W << "\n";
   s << "#define SQ_MATCH_KEYS " << (opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY ? 1 : 0) << "\n";
+  s << "#define SQ_MSLOTS " << std::max(comp->mslots, 64) << "\n#define SQ_MUNROLL " << comp->munroll << "\n";
   s << "#define SQ_BLOCK " << comp->block << "\n#define SQ_SLOTS " << comp->slots << "\n#define SQ_UNROLL " << comp->unroll << "\n";
   s << "struct SqRow {\n  bool pass; u64 h; u64 kb[" << std::max(K, 1) << "]; u32 knull;\n";
   for (size_t j = 0; j < aggs_.size(); j++) s << "  " << ctype_of(args[j].dtype) << " a" << j << "; bool an" << j << ";\n";
@@ -338,6 +360,19 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
     }
   }
   s << "  }\n  return x;\n}\n";
+  // the same fold into a CTA-shared copy (sq_agg_medium): plain atomics, the batch epoch is applied at the flush
+  s << "__device__ __forceinline__ void sq_acc_merge_shared(u64* p, int w, u64 x) {\n  switch (w) {\n";
+  for (int w = 0; w < W; w++) {
+    s << "    case " << w << ": ";
+    switch (comp->words[w].op) {
+      case W_ADD_U64:
+      case W_COUNT_EPOCH: s << "if (x) atomicAdd(p, x); break;\n"; break;
+      case W_ADD_F64: s << "atomicAdd((double*)p, __longlong_as_double((i64)x)); break;\n"; break;
+      case W_MIN_I64: s << "atomicMin((i64*)p, (i64)x); break;\n"; break;
+      case W_MAX_I64: s << "atomicMax((i64*)p, (i64)x); break;\n"; break;
+    }
+  }
+  s << "  }\n}\n";
   s << "__device__ __forceinline__ void sq_acc_merge_global(u64* p, int w, u64 x, i64 batch_no) {\n  switch (w) {\n";
   for (int w = 0; w < W; w++) {
     s << "    case " << w << ": ";
@@ -414,7 +449,7 @@ void AggOp::reset() {
   rows_seen_ = 0;
   batches_seen_ = 0;
   seen_batch_ = false;
-  use_global_ = false;
+  level_ = 0;
   groups_known_ = 0;
   groups_bound_ = 0;
   counters_stale_ = false;
@@ -434,6 +469,18 @@ void AggOp::read_counters(uint32_t* out4) {
     SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 3, 0, 4, ctx_.stream));
     fail(SQLRS_ERR_ARROW, "Divide by zero error (aggregate argument)");
   }
+}
+
+// CTA-partial scratch of sq_agg_small / sq_agg_medium, kept across batches
+void AggOp::ensure_partial_scratch(size_t entries, int K, size_t W) {
+  if (part_entries_ >= entries) return;
+  p_state_ = dev_alloc(ctx_, entries * 4);
+  p_hash_ = dev_alloc(ctx_, entries * 8);
+  p_min_ = dev_alloc(ctx_, entries * 8);
+  p_keys_ = dev_alloc(ctx_, entries * 8 * std::max(K, 1));
+  p_knull_ = dev_alloc(ctx_, entries * 4);
+  p_acc_ = dev_alloc(ctx_, entries * 8 * std::max<size_t>(W, 1));
+  part_entries_ = entries;
 }
 
 // ------------------------------------------------------------------ push
@@ -483,19 +530,12 @@ void AggOp::push(const DBatch& batch) {
   };
 
   bool done = false;
-  if (!use_global_ && c.small_ok) {
+  if (level_ == 0 && !c.small_ok) level_ = 1;
+  if (level_ == 0) {
     const int grid = (int)std::min<int64_t>(c.small_grid, std::max<int64_t>(1, div_up(n, (int64_t)c.block * c.unroll)));
     const size_t entries = (size_t)grid * c.slots;
     reserve(entries);
-    if (part_entries_ < entries) {  // CTA-partial scratch, kept across batches
-      p_state_ = dev_alloc(ctx_, entries * 4);
-      p_hash_ = dev_alloc(ctx_, entries * 8);
-      p_min_ = dev_alloc(ctx_, entries * 8);
-      p_keys_ = dev_alloc(ctx_, entries * 8 * std::max(K, 1));
-      p_knull_ = dev_alloc(ctx_, entries * 4);
-      p_acc_ = dev_alloc(ctx_, entries * 8 * std::max<size_t>(W, 1));
-      part_entries_ = entries;
-    }
+    ensure_partial_scratch(entries, K, W);
     struct {
       void *state, *hash, *min_row, *keys, *knull, *acc;
     } part = {p_state_->p, p_hash_->p, p_min_->p, p_keys_->p, p_knull_->p, p_acc_->p};
@@ -515,7 +555,7 @@ void AggOp::push(const DBatch& batch) {
     scan_kernel_ms_ += timer.elapsed_ms();
     scan_kernel_launches_ += timer.enabled ? 1 : 0;
     if (hc[2] & 1u) {
-      use_global_ = true;  // more groups than the shared-memory path holds: this and later batches use the HBM table
+      level_ = 1;  // more groups than the private-accumulator path holds: this and later batches go one level up
       SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 2, 0, 4, ctx_.stream));
     } else {
       done = true;
@@ -523,8 +563,40 @@ void AggOp::push(const DBatch& batch) {
                    " threads, grid " + std::to_string(grid) + ") + sq_agg_merge";
     }
   }
+  if (!done && level_ == 1 && !c.medium_ok) level_ = 2;
+  if (!done && level_ == 1) {
+    const int grid = (int)std::min<int64_t>(c.medium_grid, std::max<int64_t>(1, div_up(n, (int64_t)256 * c.munroll)));
+    const size_t entries = (size_t)grid * c.mslots;
+    reserve(entries);
+    ensure_partial_scratch(entries, K, W);
+    struct {
+      void *state, *hash, *min_row, *keys, *knull, *acc;
+    } part = {p_state_->p, p_hash_->p, p_min_->p, p_keys_->p, p_knull_->p, p_acc_->p};
+    SqInBlob in(batch, 0);
+    int64_t n_arg = n, rb = row_base, bn = batch_no;
+    void* status = (uint32_t*)table_->counters->p + 2;
+    void* errp = (uint32_t*)table_->counters->p + 3;
+    TableView tv = table_->view();
+    int n_entries = (int)entries;
+    void* args[] = {in.ptr(), &n_arg, &rb, &part, &status, &errp};
+    ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
+    jit_launch(c.medium, (unsigned)grid, 256, c.medium_smem, ctx_.stream, args);
+    timer.stop();
+    void* args_merge[] = {&part, &n_entries, &tv, &bn, &status};
+    jit_launch(c.merge, (unsigned)div_up(n_entries, 128), 128, 0, ctx_.stream, args_merge);
+    read_counters(hc);
+    scan_kernel_ms_ += timer.elapsed_ms();
+    scan_kernel_launches_ += timer.enabled ? 1 : 0;
+    if (hc[2] & 4u) {
+      level_ = 2;  // more groups than one CTA's shared-memory table holds
+      SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 2, 0, 4, ctx_.stream));
+    } else {
+      done = true;
+      last_path_ = "sq_agg_medium (shared-memory atomics, " + std::to_string(c.mslots) + " groups per CTA, grid " + std::to_string(grid) + ")";
+    }
+  }
   if (!done) {
-    use_global_ = true;
+    level_ = 2;
     const int64_t chunk = 1LL << 22;
     for (int64_t start = 0; start < n; start += chunk) {
       const int64_t len = std::min(chunk, n - start);
@@ -768,7 +840,7 @@ void AggOp::export_partials_device(uint64_t* dst, int64_t cap_rows) {
 void AggOp::clear_partials() {
   ctx_.activate();
   if (table_) init_table_contents(*table_);
-  use_global_ = false;
+  level_ = 0;
   groups_known_ = 0;
   groups_bound_ = 0;
   counters_stale_ = false;
