@@ -327,6 +327,90 @@ def run_gpu(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def q3_tables(lib, d, make, cols=None):
+    from sqlrs_b200.host import tpch
+
+    return {0: make(lib, d, tpch.CUSTOMER, columns=tpch.Q3_CUSTOMER_COLUMNS), 1: make(lib, d, tpch.ORDERS, columns=tpch.Q3_ORDERS_COLUMNS),
+            2: make(lib, d, tpch.LINEITEM, columns=tpch.Q3_LINEITEM_COLUMNS)}
+
+
+def run_gpu_q3(args):
+    """Secondary line (not the driver's default): Q3' = customer ⋈ orders ⋈ lineitem -> group-by, one GPU, tables in HBM."""
+    import pyarrow as pa
+    import torch
+
+    from sqlrs_b200.host import ffi, tpch
+    from sqlrs_b200.host.plan import ExecutorBuilder
+
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    lib = ffi.load()
+    d = tpch.dims(args.sf)
+    stream = torch.cuda.Stream(device=dev)
+    plan_root, schemas = tpch.q3_plan()
+    mode = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    with torch.cuda.stream(stream):
+        tabs = q3_tables(lib, d, lambda l, dd, t, columns: tpch.device_table(l, dd, t, columns=columns, device=dev))
+        rows = {k: t.n_rows for k, t in tabs.items()}
+        alg = tpch.q3_algorithmic_bytes(rows[0], rows[1], rows[2])
+        plan = ExecutorBuilder(lib, lib.options(device_id=0, stream=C.c_void_p(stream.cuda_stream), **mode)).build(plan_root, schemas)
+        for k, t in tabs.items():
+            plan.push_table_device(k, t)
+
+        def step():
+            plan.execute()
+            return plan.collect()
+
+        sampler = ClockSampler(0)
+        sampler.start()
+        for _ in range(args.warmup):
+            result = step()
+        torch.cuda.synchronize(dev)
+        l0 = lib.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin = time.time()
+        e0.record(stream)
+        for _ in range(args.steps):
+            result = step()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        t_end = time.time()
+        ms = e0.elapsed_time(e1) / args.steps
+        launches = lib.kernel_launches() - l0
+        clocks = sampler.stop(t_begin, t_end)
+        describe = plan.describe()
+        groups = sum(b.num_rows for b in result)
+        plan.close()
+    peak, peak_src = measured_peak()
+    n_in = sum(rows.values())
+    line = {
+        "metric": "tpch_q3_rows_per_sec", "value": n_in / (ms * 1e-3), "unit": "rows/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i64+f64", "data": "synthetic",
+        "config": {"workload": f"tpch_q3_sf{args.sf:g}", "rows": rows, "groups": groups, "count_mode": "sql_accumulate", "match_mode": "hash_and_key",
+                   "l2": "lineitem columns (%.1f GB) are larger than the 126 MB L2" % (rows[2] * 32 / 1e9), "pipeline": describe},
+        "roofline": {"bound": "hbm", "kernel": "whole pipeline (2 x join build/probe + aggregate; no single dominant kernel)", "achieved": alg / (ms * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg, "traffic": None},
+        "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if args.cpu_rows > 0:  # CPU port on a bounded sample: the same plan at a smaller scale factor
+        oracle = load_oracle()
+        dc = tpch.dims(args.cpu_sf)
+        host = q3_tables(oracle, dc, lambda l, dd, t, columns: tpch.host_table(l, dd, t, columns=columns))
+        p = ExecutorBuilder(oracle, oracle.options(**mode)).build(plan_root, schemas)
+        t0 = time.perf_counter()
+        for slot, t in host.items():
+            for off in range(0, t.num_rows, 1024):
+                p.push_table(slot, t.slice(off, 1024))
+        p.run()
+        dt = time.perf_counter() - t0
+        p.close()
+        n_cpu = sum(t.num_rows for t in host.values())
+        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+                                "sample": f"Q3' at SF{args.cpu_sf:g} ({n_cpu} input rows), one pass, batch 1024 rows, C++ restatement of the sqlrs v1 executor"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -337,6 +421,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-rows", type=int, default=48_000_000, help="rows of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--ref-rows", type=int, default=12_000_000, help="rows per step of --impl reference")
+    ap.add_argument("--query", default="q1", choices=["q1", "q3"], help="q1 = the driver's workload; q3 = secondary line (1 GPU)")
+    ap.add_argument("--cpu-sf", type=float, default=1.0, help="scale factor of the q3 cpu_baseline sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -346,6 +432,12 @@ def main():
         return
     if world != args.gpus:
         log(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    if args.query == "q3":
+        if rank == 0:
+            if args.sf == 100.0:
+                args.sf = 10.0  # BASELINE.json configs[2]: Q3 SF10 on one GPU
+            run_gpu_q3(args)
+        return
     run_gpu(args, rank, world, local_rank)
 
 

@@ -331,6 +331,13 @@ int SQLRS_API(debug_compile_agg)(const sqlrs_agg_desc* aggs, int32_t n_aggs, con
                                  int32_t n_group_by, const sqlrs_expr* fused_predicate,
                                  const struct ArrowSchema* input_schema, const sqlrs_options* options,
                                  int32_t compile, char** source_out);
+/* the fused probe -> aggregate kernel (csrc/jit/joinagg.cuh) for an inner join with `right_keys` over `probe_schema`
+ * batches, build side `build_schema`; group_by / aggregate arguments index the joined row (build columns first) */
+int SQLRS_API(debug_compile_joinagg)(const sqlrs_agg_desc* aggs, int32_t n_aggs, const sqlrs_expr* group_by,
+                                     int32_t n_group_by, const sqlrs_expr* right_keys, int32_t n_keys,
+                                     const sqlrs_expr* probe_predicate, const sqlrs_expr* join_filter,
+                                     const struct ArrowSchema* build_schema, const struct ArrowSchema* probe_schema,
+                                     const sqlrs_options* options, int32_t compile, char** source_out);
 int SQLRS_API(debug_compile_eval)(const sqlrs_expr* exprs, int32_t n_exprs, int32_t as_keep_mask,
                                   const struct ArrowSchema* input_schema, int32_t compile, char** source_out);
 void SQLRS_API(free)(void* p);

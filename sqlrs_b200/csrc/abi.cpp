@@ -377,8 +377,26 @@ int sqlrs_debug_compile_agg(const sqlrs_agg_desc* aggs, int32_t n_aggs, const sq
     std::vector<std::string> names((size_t)n_group_by);
     AggOp op(copy_aggs(aggs, n_aggs), copy_exprs(group_by, n_group_by), names, n_group_by == 0, pred, opt);
     std::string gen = op.debug_source(cols_of_schema(input_schema));
-    if (compile) jit_compile_to_cubin("agg", gen, nullptr);
-    if (source_out) *source_out = dup_string(jit_full_source("agg", gen));
+    if (compile) jit_compile_to_cubin("agg_table+agg", gen, nullptr);
+    if (source_out) *source_out = dup_string(jit_full_source("agg_table+agg", gen));
+  });
+}
+
+int sqlrs_debug_compile_joinagg(const sqlrs_agg_desc* aggs, int32_t n_aggs, const sqlrs_expr* group_by, int32_t n_group_by,
+                                const sqlrs_expr* right_keys, int32_t n_keys, const sqlrs_expr* probe_predicate, const sqlrs_expr* join_filter,
+                                const ArrowSchema* build_schema, const ArrowSchema* probe_schema, const sqlrs_options* options, int32_t compile,
+                                char** source_out) {
+  return guarded([&] {
+    Options opt = copy_options(options);
+    opt.device_id = -2;
+    std::vector<std::string> names((size_t)n_group_by);
+    AggOp op(copy_aggs(aggs, n_aggs), copy_exprs(group_by, n_group_by), names, n_group_by == 0, {}, opt);
+    ExprCopy pp, jf;
+    if (probe_predicate && probe_predicate->n_nodes > 0) pp = copy_expr(probe_predicate);
+    if (join_filter && join_filter->n_nodes > 0) jf = copy_expr(join_filter);
+    std::string gen = op.debug_join_source(cols_of_schema(build_schema), cols_of_schema(probe_schema), copy_exprs(right_keys, n_keys), pp, jf);
+    if (compile) jit_compile_to_cubin("agg_table+joinagg", gen, nullptr);
+    if (source_out) *source_out = dup_string(jit_full_source("agg_table+joinagg", gen));
   });
 }
 

@@ -54,6 +54,14 @@ std::string RowProgram::signature() const {
     s += c.has_valid ? 'v' : '-';
     s += c.nullable ? 'n' : '-';
   }
+  if (joined_) {
+    s += '|';
+    for (const ColInfo& c : build_cols_) {
+      s += (char)('0' + c.dtype);
+      s += c.has_valid ? 'v' : '-';
+      s += c.nullable ? 'n' : '-';
+    }
+  }
   return s;
 }
 
@@ -75,7 +83,29 @@ Val RowProgram::define(int dtype, const std::string& value_expr, const std::stri
 }
 
 Val RowProgram::load_column(int index) {
-  if (index < 0 || index >= (int)cols_.size()) fail(SQLRS_ERR_INTERNAL, "InputRef index out of bounds");
+  const int nb = joined_ ? (int)build_cols_.size() : 0;
+  if (index < 0 || index >= nb + (int)cols_.size()) fail(SQLRS_ERR_INTERNAL, "InputRef index out of bounds");
+  if (index < nb) {  // build side of the joined row: gathered at the matched build row
+    const ColInfo& c = build_cols_[index];
+    std::string key = "colB" + std::to_string(index);
+    auto it = cse_.find(key);
+    if (it != cse_.end()) return it->second;
+    std::string ci = std::to_string(index);
+    switch (c.dtype) {
+      case SQLRS_DT_NULL: {
+        Val v = define(SQLRS_DT_NULL, "0", "false", true, true, key);
+        v.always_null = true;
+        cse_[key] = v;
+        return v;
+      }
+      case SQLRS_DT_BOOL: return define(c.dtype, "SQ_LDB_BOOL(" + ci + ", b)", "SQ_VALIDB(" + ci + ", b)", c.has_valid, c.nullable, key);
+      case SQLRS_DT_INT32: return define(c.dtype, "SQ_LDB_I32(" + ci + ", b)", "SQ_VALIDB(" + ci + ", b)", c.has_valid, c.nullable, key);
+      case SQLRS_DT_INT64: return define(c.dtype, "SQ_LDB_I64(" + ci + ", b)", "SQ_VALIDB(" + ci + ", b)", c.has_valid, c.nullable, key);
+      case SQLRS_DT_FLOAT64: return define(c.dtype, "SQ_LDB_F64(" + ci + ", b)", "SQ_VALIDB(" + ci + ", b)", c.has_valid, c.nullable, key);
+      default: fail(SQLRS_ERR_UNSUPPORTED, "Utf8 columns are not supported by the CUDA backend yet (SURVEY §8f rank 4)");
+    }
+  }
+  index -= nb;
   const ColInfo& c = cols_[index];
   std::string key = "col" + std::to_string(index);
   auto it = cse_.find(key);

@@ -44,6 +44,11 @@ const char* ctype_of(int dtype);  // C type used for a value of that dtype in ge
 class RowProgram {
  public:
   explicit RowProgram(std::vector<ColInfo> cols) : cols_(std::move(cols)) {}
+  // joined mode (fused probe -> consumer pipelines): InputRef k addresses the joined row of a hash join —
+  // k < build_cols.size() loads build-side column k at the matched build row `b` (SQ_LDB_* macros), the rest
+  // loads probe-side column k - build_cols.size() at the scan row `r`
+  RowProgram(std::vector<ColInfo> build_cols, std::vector<ColInfo> probe_cols)
+      : cols_(std::move(probe_cols)), build_cols_(std::move(build_cols)), joined_(true) {}
   // compiles one expression; statements are appended to the body.  `err_class` selects the
   // error flag a runtime failure (divide by zero) of this expression raises: 0 = applies to every
   // row, 1 = only to rows that pass the predicate (expressions above a fused Filter).
@@ -77,6 +82,8 @@ class RowProgram {
              const std::string& cse_key);
 
   std::vector<ColInfo> cols_;
+  std::vector<ColInfo> build_cols_;
+  bool joined_ = false;
   std::ostringstream body_;
   std::map<std::string, Val> cse_;
   int next_id_ = 0;

@@ -106,7 +106,15 @@ std::string jit_full_source(const std::string& skeleton, const std::string& gene
   src += "\n// ---- skeleton: ";
   src += skeleton;
   src += " -------------------------------------------------------\n";
-  src += embedded_source(skeleton);
+  // "a+b": building blocks concatenated in order
+  size_t pos = 0;
+  while (pos <= skeleton.size()) {
+    size_t plus = skeleton.find('+', pos);
+    if (plus == std::string::npos) plus = skeleton.size();
+    src += embedded_source(skeleton.substr(pos, plus - pos));
+    src += "\n";
+    pos = plus + 1;
+  }
   return src;
 }
 

@@ -12,6 +12,10 @@ typedef unsigned int u32;
 __device__ __forceinline__ i64 sq_ld_i64(const void* p, i64 r) { return __ldcs(((const i64*)p) + r); }
 __device__ __forceinline__ int sq_ld_i32(const void* p, i64 r) { return __ldcs(((const int*)p) + r); }
 __device__ __forceinline__ double sq_ld_f64(const void* p, i64 r) { return __ldcs(((const double*)p) + r); }
+// gathers (build side of a join): random access, keep them in L1/L2
+__device__ __forceinline__ i64 sq_ldg_i64(const void* p, i64 r) { return __ldg(((const i64*)p) + r); }
+__device__ __forceinline__ int sq_ldg_i32(const void* p, i64 r) { return __ldg(((const int*)p) + r); }
+__device__ __forceinline__ double sq_ldg_f64(const void* p, i64 r) { return __ldg(((const double*)p) + r); }
 __device__ __forceinline__ bool sq_ld_bit(const void* p, i64 r) { return (__ldg(((const u32*)p) + (r >> 5)) >> (r & 31)) & 1u; }
 
 // ---- ahash 0.8.0 fallback hasher with RandomState::with_seeds(0,0,0,0), as the reference uses it

@@ -3,6 +3,7 @@
 // reference's row order (probe-row order, per probe row the build rows in insertion order); Left/Full
 // tail of unmatched build rows at finish.
 #pragma once
+#include "kernels_aot.hpp"
 #include "ops.hpp"
 
 namespace sq {
@@ -20,10 +21,18 @@ class JoinOp {
   void set_side_predicates(ExprCopy build_pred, ExprCopy probe_pred);
   void set_needed_columns(std::vector<bool> needed);
   Ctx& ctx() { return ctx_; }
+  // for consumers fused onto the probe (AggOp::push_join): the sealed build side
+  void seal();
+  bool empty_build() const;                 // no build batch at all: the reference yields nothing (hash_join.rs:183-185)
+  const struct JoinTableView& table_view() const;
+  const DBatch& build_side() const;
+  int join_type() const { return join_type_; }
+  const std::vector<ExprCopy>& right_keys() const { return right_keys_; }
+  const ExprCopy& join_filter() const { return filter_; }
+  bool match_keys() const { return opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY; }
 
  private:
   struct Impl;
-  void seal();
   DBatch build_batch(const DBatch& right, const int64_t* li, bool li_nullable, const uint32_t* ri, int64_t m);
   void check_schema(DBatch& b);
 

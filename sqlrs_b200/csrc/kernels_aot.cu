@@ -357,6 +357,18 @@ __global__ void __launch_bounds__(kBlock) k_table_merge_packed(TableView t, int 
         case 1: atomicAdd((double*)p, __longlong_as_double((long long)x)); break;
         case 2: atomicMin((long long*)p, (long long)x); break;
         case 3: atomicMax((long long*)p, (long long)x); break;
+        case 4: {  // COUNT under the overwrite quirk: (batch epoch << 40 | count) — the later batch wins, equal epochs add
+          unsigned long long old = *p;
+          for (;;) {
+            const unsigned long long eo = old >> 40, ex = x >> 40;
+            const unsigned long long nv = eo == ex ? old + (x & ((1ULL << 40) - 1)) : (ex > eo ? x : old);
+            if (nv == old) break;
+            const unsigned long long prev = atomicCAS((unsigned long long*)p, old, nv);
+            if (prev == old) break;
+            old = prev;
+          }
+          break;
+        }
       }
     }
   }

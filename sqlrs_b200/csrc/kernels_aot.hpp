@@ -52,7 +52,7 @@ void launch_table_pack(const TableView& t, int n_keys, int n_acc, uint64_t* dst,
 // the n groups packed in ascending first-row order (dst: (n + 1) rows; header written)
 void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, uint64_t* dst, cudaStream_t stream);
 // partial -> final merge of n_bufs packed buffers ((cap_rows + 1) rows each) into `t`; ops[w] (device):
-// 0 add u64, 1 add f64, 2 min i64, 3 max i64
+// 0 add u64, 1 add f64, 2 min i64, 3 max i64, 4 (epoch << 40 | count): later epoch wins, equal epochs add
 void launch_table_merge_packed(const TableView& t, int n_keys, int n_acc, const int* ops, int match_keys, const uint64_t* src, int n_bufs,
                                uint64_t cap_rows, cudaStream_t stream);
 // re-insert every occupied slot of `from` into the (empty, initialised) table `to`

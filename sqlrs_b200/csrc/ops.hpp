@@ -96,6 +96,8 @@ class AggOp {
   Ctx& ctx() { return ctx_; }
   std::string describe() const;
   std::string debug_source(const std::vector<ColInfo>& cols);  // generated CUDA for batches of that schema (no GPU needed)
+  std::string debug_join_source(const std::vector<ColInfo>& build_cols, const std::vector<ColInfo>& probe_cols,
+                                const std::vector<ExprCopy>& right_keys, const ExprCopy& probe_pred, const ExprCopy& join_filter);
   // partial/final split for multi-GPU execution: the raw group table as a batch
   // [hash, min_row, knull, key bits..., accumulator words...] and its merge into another operator
   void export_partials(ArrowArray* out, ArrowSchema* out_schema);
@@ -105,13 +107,23 @@ class AggOp {
   void export_partials_device(uint64_t* dst, int64_t cap_rows);
   void merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows, bool sync_after = false);
   void reset();  // forget all groups, keep compiled kernels and buffers
+  // fused probe -> aggregate over an INNER hash join whose build side is sealed in `join` (csrc/jit/joinagg.cuh):
+  // `probe` is a batch of the join's right child, `probe_pred` a Filter fused below the join on that side
+  void push_join(const DBatch& probe, class JoinOp& join, const ExprCopy& probe_pred);
   void set_row_base(int64_t first_global_row) { rows_seen_ = first_global_row; }
 
  private:
   struct Compiled;
   struct Table;
   Compiled& compiled_for(const DBatch& batch);
-  std::string generate(const std::vector<ColInfo>& cols, Compiled& comp);
+  struct JoinGen {  // what the fused probe->aggregate program needs to know about the join below
+    std::vector<ColInfo> build_cols;
+    std::vector<ExprCopy> right_keys;
+    ExprCopy probe_pred, join_filter;
+    bool jmatch = false;
+  };
+  std::string generate(const std::vector<ColInfo>& cols, Compiled& comp, const JoinGen* jg = nullptr);
+  std::unique_ptr<Table> new_table(uint32_t capacity);
   void init_table_contents(Table& t);
   void ensure_partial_scratch(size_t entries, int K, size_t W);
   void read_counters(uint32_t* out4);
@@ -129,6 +141,7 @@ class AggOp {
   bool simple_;
   ExprCopy predicate_;
   std::map<std::string, std::unique_ptr<Compiled>> cache_;
+  std::map<std::string, JitKernel*> join_kernels_;  // fused probe->aggregate kernels by (probe, build) schema signature
   std::unique_ptr<Table> table_;
   int64_t rows_seen_ = 0, batches_seen_ = 0;
   bool seen_batch_ = false;

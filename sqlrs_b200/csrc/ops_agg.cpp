@@ -3,6 +3,7 @@
 // sum.rs:16-97, count.rs:10-29, min_max.rs:47-157}; kernels: csrc/jit/agg.cuh.
 #include <algorithm>
 
+#include "join.hpp"
 #include "kernels_aot.hpp"
 #include "ops.hpp"
 
@@ -165,12 +166,12 @@ AggOp::Compiled& AggOp::compiled_for(const DBatch& batch) {
 
   auto comp = std::make_unique<Compiled>();
   std::string src = generate(cols, *comp);
-  comp->small = comp->small_ok ? jit_get("agg", src, "sq_agg_small") : nullptr;
-  comp->merge = jit_get("agg", src, "sq_agg_merge");
-  comp->global = jit_get("agg", src, "sq_agg_global");
-  comp->fixkeys = jit_get("agg", src, "sq_agg_fixkeys");
+  comp->small = comp->small_ok ? jit_get("agg_table+agg", src, "sq_agg_small") : nullptr;
+  comp->merge = jit_get("agg_table+agg", src, "sq_agg_merge");
+  comp->global = jit_get("agg_table+agg", src, "sq_agg_global");
+  comp->fixkeys = jit_get("agg_table+agg", src, "sq_agg_fixkeys");
   if (comp->medium_ok) {
-    comp->medium = jit_get("agg", src, "sq_agg_medium");
+    comp->medium = jit_get("agg_table+agg", src, "sq_agg_medium");
     int per_sm = jit_max_blocks_per_sm(comp->medium, 256, comp->medium_smem);
     if (per_sm < 1) comp->medium_ok = false;
     comp->medium_grid = device_sm_count(ctx_.device) * std::max(per_sm, 1);
@@ -197,14 +198,31 @@ std::string AggOp::debug_source(const std::vector<ColInfo>& cols) {
   return generate(cols, c);
 }
 
+std::string AggOp::debug_join_source(const std::vector<ColInfo>& build_cols, const std::vector<ColInfo>& probe_cols,
+                                     const std::vector<ExprCopy>& right_keys, const ExprCopy& probe_pred, const ExprCopy& join_filter) {
+  JoinGen jg;
+  jg.build_cols = build_cols;
+  jg.right_keys = right_keys;
+  jg.probe_pred = probe_pred;
+  jg.join_filter = join_filter;
+  jg.jmatch = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
+  Compiled c;
+  return generate(probe_cols, c, &jg);
+}
+
 // the row program + accumulator glue for csrc/jit/agg.cuh (pure: no device access)
-std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref) {
+std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref, const JoinGen* jg) {
   Compiled* comp = &comp_ref;
-  RowProgram prog(cols);
-  const bool fused = !predicate_.empty();
+  // plain: one program over the batch row.  joined (jg): the program addresses the joined row of an inner hash
+  // join — build columns gathered at the matched build row, probe columns at the scan row; its "fused predicate"
+  // is the join's non-equi filter (the probe-side Filter and the join keys live in the stage-1 program below)
+  std::unique_ptr<RowProgram> prog_holder(jg ? new RowProgram(jg->build_cols, cols) : new RowProgram(cols));
+  RowProgram& prog = *prog_holder;
+  const ExprCopy& stage_pred = jg ? jg->join_filter : predicate_;
+  const bool fused = !stage_pred.empty() || jg != nullptr;
   std::string pass = "true";
-  if (fused) {
-    Val p = prog.compile(predicate_, 0);
+  if (!stage_pred.empty()) {
+    Val p = prog.compile(stage_pred, jg ? 1 : 0);
     if (p.dtype != SQLRS_DT_BOOL) fail(SQLRS_ERR_INTERNAL, "filter executor expected evaluate boolean array");
     pass = "(n" + std::to_string(p.id) + " && v" + std::to_string(p.id) + ")";
   }
@@ -323,6 +341,38 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
 
   std::ostringstream s;
   s << gen_input_decls(cols);
+  if (jg) {
+    // build-side inputs + the stage-1 program: fused probe-side Filter, join keys, their row hash (the same
+    // create_hashes the build side was hashed with)
+    const size_t nb = jg->build_cols.size() ? jg->build_cols.size() : 1;
+    s << "struct SqInB { const void* col[" << nb << "]; const u32* val[" << nb << "]; };\n";
+    s << "#define SQ_LDB_I64(c, b) sq_ldg_i64(inb.col[c], b)\n#define SQ_LDB_I32(c, b) sq_ldg_i32(inb.col[c], b)\n";
+    s << "#define SQ_LDB_F64(c, b) sq_ldg_f64(inb.col[c], b)\n#define SQ_LDB_BOOL(c, b) sq_ld_bit(inb.col[c], b)\n";
+    s << "#define SQ_VALIDB(c, b) sq_ld_bit(inb.val[c], b)\n";
+    RowProgram p1(cols);
+    std::string p1_pass = "true";
+    if (!jg->probe_pred.empty()) {
+      Val pp = p1.compile(jg->probe_pred, 0);
+      if (pp.dtype != SQLRS_DT_BOOL) fail(SQLRS_ERR_INTERNAL, "filter executor expected evaluate boolean array");
+      p1_pass = "(n" + std::to_string(pp.id) + " && v" + std::to_string(pp.id) + ")";
+    }
+    std::vector<Val> jkeys;
+    for (const ExprCopy& e : jg->right_keys) jkeys.push_back(p1.compile(e, jg->probe_pred.empty() ? 0 : 1));
+    const int jh = p1.emit_row_hash(jkeys);
+    std::vector<int> jraw;
+    for (const Val& k : jkeys) jraw.push_back(p1.emit_raw_bits(k));
+    const int JK = (int)jkeys.size();
+    s << "#define SQ_JKEYS " << JK << "\n#define SQ_JMATCH " << (jg->jmatch ? 1 : 0) << "\n";
+    s << "struct SqProbe { bool pass; u64 h; u64 kb[" << std::max(JK, 1) << "]; u32 knull; };\n";
+    s << "__device__ __forceinline__ void sq_probe_row(const SqIn& in, i64 r, SqProbe& p, bool& e0, bool& e1) {\n" << p1.body_str();
+    s << "  p.pass = " << p1_pass << ";\n  p.h = v" << jh << ";\n";
+    std::string jknull = "0u";
+    for (int k = 0; k < JK; k++) {
+      s << "  p.kb[" << k << "] = v" << jraw[k] << ";\n";
+      jknull += " | (n" + std::to_string(jkeys[k].id) + " ? 0u : " + std::to_string(1u << k) + "u)";
+    }
+    s << "  p.knull = " << jknull << ";\n}\n";
+  }
   s << "#define SQ_NKEYS " << K << "\n#define SQ_NACC " << W << "\n";
   s << "#define SQ_MATCH_KEYS " << (opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY ? 1 : 0) << "\n";
   s << "#define SQ_MSLOTS " << std::max(comp->mslots, 64) << "\n#define SQ_MUNROLL " << comp->munroll << "\n";
@@ -330,8 +380,10 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
   s << "struct SqRow {\n  bool pass; u64 h; u64 kb[" << std::max(K, 1) << "]; u32 knull;\n";
   for (size_t j = 0; j < aggs_.size(); j++) s << "  " << ctype_of(args[j].dtype) << " a" << j << "; bool an" << j << ";\n";
   s << "};\n";
-  s << "__device__ __forceinline__ void sq_row(const SqIn& in, i64 r, SqRow& o, bool& e0, bool& e1) {\n";
+  if (jg) s << "__device__ __forceinline__ void sq_row(const SqIn& in, const SqInB& inb, i64 r, i64 b, SqRow& o, bool& e1) {\n  bool e0 = false;\n";
+  else s << "__device__ __forceinline__ void sq_row(const SqIn& in, i64 r, SqRow& o, bool& e0, bool& e1) {\n";
   s << prog.body_str();
+  if (jg) s << "  e1 |= e0;\n";
   s << "  o.pass = " << pass << ";\n  o.h = v" << hash_id << ";\n";
   if (K == 0) s << "  o.kb[0] = 0ULL;\n";
   std::string knull = "0u";
@@ -415,6 +467,25 @@ void AggOp::init_table_contents(Table& t) {
 void AggOp::ensure_table(uint32_t min_capacity) {
   if (table_ && table_->capacity >= min_capacity) return;
   grow_table(min_capacity);
+}
+
+std::unique_ptr<AggOp::Table> AggOp::new_table(uint32_t capacity) {
+  const Compiled& c = *cache_.begin()->second;
+  auto t = std::make_unique<Table>();
+  t->capacity = next_pow2(capacity);
+  t->n_keys = (int)c.key_dtypes.size();
+  t->n_acc = (int)c.words.size();
+  const size_t cap = t->capacity;
+  t->state = dev_alloc(ctx_, cap * 4);
+  t->hash = dev_alloc(ctx_, cap * 8);
+  t->min_row = dev_alloc(ctx_, cap * 8);
+  t->keys = dev_alloc_zero(ctx_, cap * 8 * std::max(t->n_keys, 1));
+  t->knull = dev_alloc_zero(ctx_, cap * 4);
+  t->acc = dev_alloc(ctx_, cap * 8 * std::max(t->n_acc, 1));
+  t->new_slots = dev_alloc(ctx_, cap * 4);
+  t->counters = dev_alloc(ctx_, 16);
+  init_table_contents(*t);
+  return t;
 }
 
 void AggOp::grow_table(uint32_t min_capacity) {
@@ -622,6 +693,97 @@ void AggOp::push(const DBatch& batch) {
     last_path_ = "sq_agg_global (open-addressed table in HBM, capacity " + std::to_string(table_->capacity) + ")";
   }
   flush_new_slots();
+}
+
+// ------------------------------------------------------------------ fused probe -> aggregate
+void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_pred) {
+  Trace tr("agg.push_join", ctx_.stream);
+  ctx_.activate();
+  ctx_.reap();
+  if (join.join_type() != SQLRS_JOIN_INNER || opt_.match_mode != SQLRS_MATCH_HASH_AND_KEY)
+    fail(SQLRS_ERR_INTERNAL, "push_join: only inner joins with key comparison are fused");
+  join.seal();
+  if (join.empty_build()) return;  // the join yields no batch at all
+  const DBatch& build = join.build_side();
+  std::vector<ColInfo> pcols = col_infos(probe), bcols = col_infos(build);
+  const std::string sig = RowProgram(bcols, pcols).signature();
+  JoinGen jg;
+  jg.build_cols = bcols;
+  jg.right_keys = join.right_keys();
+  jg.probe_pred = probe_pred;
+  jg.join_filter = join.join_filter();
+  jg.jmatch = join.match_keys();
+  auto kit = join_kernels_.find(sig);
+  if (kit == join_kernels_.end()) {
+    auto comp = std::make_unique<Compiled>();
+    std::string src = generate(pcols, *comp, &jg);
+    JitKernel* k = jit_get("agg_table+joinagg", src, "sq_joinagg_kernel");
+    if (!cache_.empty()) {
+      const Compiled& first = *cache_.begin()->second;
+      bool same = first.words.size() == comp->words.size() && first.key_dtypes == comp->key_dtypes;
+      for (size_t w = 0; same && w < first.words.size(); w++) same = first.words[w].op == comp->words[w].op;
+      if (!same) fail(SQLRS_ERR_ARROW, "batch schema changed between batches (a column declared non-nullable contains nulls?)");
+    } else {
+      cache_["join|" + sig] = std::move(comp);  // the accumulator layout of this operator
+    }
+    kit = join_kernels_.emplace(sig, k).first;
+  }
+  const Compiled& c = *cache_.begin()->second;
+  if (key_dtypes_.empty()) key_dtypes_ = c.key_dtypes;
+  seen_batch_ = true;
+  const int64_t n = probe.n;
+  const int64_t batch_no = batches_seen_++;
+  const int64_t row_base = rows_seen_;
+  rows_seen_ += n;
+  if (n == 0) return;
+  if (n >= (1LL << 32)) fail(SQLRS_ERR_INVALID_ARG, "a probe batch may hold fewer than 2^32 rows (hash_join.rs:219)");
+
+  // The number of joined rows (and groups) is unknown before the probe: aggregate into a batch-local table sized
+  // optimistically; a full table discards it and retries 4x larger, so a batch counts all-or-nothing.
+  const JoinTableView& jt = join.table_view();
+  uint64_t cap = std::max<uint64_t>(4ULL * (uint64_t)jt.n_build, 1ULL << 16);
+  std::unique_ptr<Table> local;
+  uint32_t hc[4] = {0, 0, 0, 0};
+  for (;;) {
+    if (cap > (1ULL << 31)) fail(SQLRS_ERR_INTERNAL, "group table would exceed 2^31 slots");
+    local = new_table((uint32_t)cap);
+    SqInBlob in(probe, 0), inb(build, 0);
+    int64_t n_arg = n, rb = row_base, bn = batch_no;
+    void* status = (uint32_t*)local->counters->p + 2;
+    void* errp = (uint32_t*)local->counters->p + 3;
+    TableView tv = local->view();
+    JoinTableView jv = jt;
+    void* args[] = {in.ptr(), inb.ptr(), &n_arg, &rb, &jv, &tv, &bn, &status, &errp};
+    const int sms = device_sm_count(ctx_.device);
+    unsigned grid = (unsigned)std::min<int64_t>(div_up(n, 512), (int64_t)sms * 8);
+    ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
+    jit_launch(kit->second, grid, 256, 0, ctx_.stream, args);
+    timer.stop();
+    SQ_CUDA(cudaMemcpyAsync(hc, local->counters->p, 16, cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    scan_kernel_ms_ += timer.elapsed_ms();
+    scan_kernel_launches_ += timer.enabled ? 1 : 0;
+    if (hc[3] & 1u) fail(SQLRS_ERR_ARROW, "Divide by zero error (aggregate argument)");
+    if (!(hc[2] & 2u)) break;
+    cap *= 4;
+  }
+  last_path_ = "sq_joinagg_kernel (fused probe + aggregate, batch-local table capacity " + std::to_string(local->capacity) + ")";
+  const bool main_empty = !table_ || (groups_known_ == 0 && !counters_stale_ && groups_bound_ == 0);
+  if (main_empty) {
+    table_ = std::move(local);  // first batch: its table IS the operator's table
+    SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 1, 0, 4, ctx_.stream));
+    groups_known_ = hc[0];
+    groups_bound_ = hc[0];
+    counters_stale_ = false;
+    return;
+  }
+  if (hc[0] == 0) return;
+  // later batches: fold the batch-local groups into the operator's table (packed rows, device to device)
+  const int words = 3 + local->n_keys + local->n_acc;
+  BufPtr packed = dev_alloc(ctx_, (size_t)(hc[0] + 1) * words * 8);
+  SQ_CUDA(cudaMemsetAsync(packed->p, 0, (size_t)words * 8, ctx_.stream));
+  launch_table_pack(local->view(), local->n_keys, local->n_acc, (uint64_t*)packed->p, hc[0], ctx_.stream);
+  merge_partials_device((const uint64_t*)packed->p, 1, hc[0], true);
 }
 
 // ------------------------------------------------------------------ finish
@@ -856,7 +1018,8 @@ const int* AggOp::device_word_ops() {
       case W_ADD_F64: ops.push_back(1); break;
       case W_MIN_I64: ops.push_back(2); break;
       case W_MAX_I64: ops.push_back(3); break;
-      default: fail(SQLRS_ERR_UNSUPPORTED, "partial/final COUNT needs SQLRS_COUNT_SQL_ACCUMULATE");
+      case W_COUNT_EPOCH: ops.push_back(4); break;  // batch-local tables of push_join; the multi-GPU export refuses this mode
+      default: fail(SQLRS_ERR_INTERNAL, "unknown accumulator word");
     }
   }
   d_ops_ = dev_alloc(ctx_, std::max<size_t>(ops.size(), 1) * 4);

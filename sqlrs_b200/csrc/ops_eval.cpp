@@ -169,11 +169,14 @@ EvalResult EvalProgram::run(Ctx& ctx, const DBatch& batch, const char* what) {
   const int64_t n = batch.n;
   size_t m = c.out_dtypes.size() ? c.out_dtypes.size() : 1;
   std::vector<void*> out_blob(2 * m, nullptr);
-  for (size_t j = 0; j < c.out_dtypes.size(); j++) {
-    DCol col = make_col(ctx, c.out_dtypes[j], n, c.out_nullable[j]);
-    out_blob[j] = col_data(col);
-    out_blob[m + j] = col_valid(col);
-    res.cols.push_back(col);
+  {
+    Trace tr_alloc("  eval.alloc", ctx.stream);
+    for (size_t j = 0; j < c.out_dtypes.size(); j++) {
+      DCol col = make_col(ctx, c.out_dtypes[j], n, c.out_nullable[j]);
+      out_blob[j] = col_data(col);
+      out_blob[m + j] = col_valid(col);
+      res.cols.push_back(col);
+    }
   }
   if (n == 0) return res;
   BufPtr err = dev_alloc_zero(ctx, 4);

@@ -176,6 +176,10 @@ void JoinOp::seal() {
   if (join_type_ == SQLRS_JOIN_LEFT || join_type_ == SQLRS_JOIN_FULL) im.visited_left = dev_alloc_zero(ctx_, (size_t)bitmap_words(n) * 4 + 4);
 }
 
+bool JoinOp::empty_build() const { return impl_->capacity == 0; }
+const JoinTableView& JoinOp::table_view() const { return impl_->view; }
+const DBatch& JoinOp::build_side() const { return impl_->left_single; }
+
 // build_batch, hash_join.rs:25-45: all left columns by (nullable) build index, all right columns by probe index
 DBatch JoinOp::build_batch(const DBatch& right, const int64_t* li, bool li_nullable, const uint32_t* ri, int64_t m) {
   DBatch out;
@@ -243,6 +247,7 @@ bool JoinOp::probe(const DBatch& right, DBatch* result) {
   int64_t total = 0;
   BufPtr li, ri;
   if (n > 0) {
+    Trace tr_a("  probe.count+scan+write", ctx_.stream);
     BufPtr slot_of = dev_alloc(ctx_, (size_t)n * 4), counts = dev_alloc(ctx_, (size_t)n * 4);
     BufPtr offsets = dev_alloc(ctx_, (size_t)n * 8 + 8);
     BufPtr scratch = dev_alloc(ctx_, scan_scratch_entries(n) * 8);

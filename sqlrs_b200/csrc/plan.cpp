@@ -3,6 +3,19 @@
 
 namespace sq {
 
+// ---- which input columns does an expression read?
+static void mark_refs(const ExprCopy& e, std::vector<bool>& needed, int offset = 0, int lo = 0, int hi = 1 << 30) {
+  for (const ExprNodeCopy& n : e)
+    if (n.op == SQLRS_OP_INPUT_REF && n.index >= lo && n.index < hi) {
+      const int k = n.index - offset;
+      if (k >= 0) {
+        if (k >= (int)needed.size()) needed.resize(k + 1, false);
+        needed[k] = true;
+      }
+    }
+}
+
+
 Plan::Plan(const sqlrs_plan_node* nodes, int32_t n_nodes, int32_t root, const Options& opt) : ctx_(opt), opt_(opt), root_(root) {
   opt_.stream = ctx_.stream;  // every operator of the plan works on the plan's stream
   opt_.device_id = ctx_.device;
@@ -80,12 +93,49 @@ void Plan::run_agg_to_host(int idx, Result* res) {
   else agg_op_->reset();
   AggOp& op = *agg_op_;
   const Needed need = fusion() ? agg_child_needs(n, fused, width_of(child)) : Needed();
-  for (const DBatch& b : run(child, need)) op.push(b);
+  if (!feed_fused_join(op, child, fused, need))
+    for (const DBatch& b : run(child, need)) op.push(b);
   op.finish_host(&res->arr, &res->sch);
   res->on_host = true;
   description_ += op.describe() + "; ";
   scan_kernel_ms_ = op.scan_kernel_ms();
   scan_kernel_launches_ = op.scan_kernel_launches();
+}
+
+// An INNER HashJoin directly below the aggregate (no Filter in between, SQL key comparison): build the join's left
+// side as usual, then probe and aggregate in ONE kernel per probe batch (csrc/jit/joinagg.cuh) — the joined rows
+// are never materialised.  Returns false when the shape does not apply (the caller runs operator at a time).
+bool Plan::feed_fused_join(AggOp& op, int child, const ExprCopy& agg_fused_pred, const Needed& need) {
+  if (!fusion() || !agg_fused_pred.empty()) return false;
+  Node& jn = nodes_[child];
+  if (jn.kind != SQLRS_NODE_HASH_JOIN || jn.join_type != SQLRS_JOIN_INNER || opt_.match_mode != SQLRS_MATCH_HASH_AND_KEY) return false;
+  int left = jn.child0, right = jn.child1;
+  ExprCopy build_pred, probe_pred;
+  if (nodes_[left].kind == SQLRS_NODE_FILTER) {
+    build_pred = nodes_[left].predicate;
+    left = nodes_[left].child0;
+  }
+  if (nodes_[right].kind == SQLRS_NODE_FILTER) {
+    probe_pred = nodes_[right].predicate;
+    right = nodes_[right].child0;
+  }
+  const int nleft = width_of(left), total = (int)jn.join_fields.size();
+  if (nleft <= 0 || nleft > total) return false;
+  Needed left_need((size_t)nleft, false), right_need((size_t)(total - nleft), false);
+  for (int k = 0; k < total; k++)
+    if (need.empty() || ((size_t)k < need.size() && need[(size_t)k])) (k < nleft ? left_need[(size_t)k] : right_need[(size_t)(k - nleft)]) = true;
+  mark_refs(jn.predicate, left_need, 0, 0, nleft);
+  mark_refs(jn.predicate, right_need, nleft, nleft, 1 << 30);
+  for (const ExprCopy& e : jn.left_keys) mark_refs(e, left_need);
+  for (const ExprCopy& e : jn.right_keys) mark_refs(e, right_need);
+  mark_refs(build_pred, left_need);
+  mark_refs(probe_pred, right_need);
+  JoinOp j(jn.join_type, jn.left_keys, jn.right_keys, jn.predicate, jn.join_fields, opt_);
+  j.set_side_predicates(build_pred, ExprCopy());
+  description_ += "[HashJoin build (CSR) | probe fused into the aggregate: sq_joinagg_kernel] ";
+  for (const DBatch& b : run(left, left_need)) j.build_push(b);
+  for (const DBatch& b : run(right, right_need)) op.push_join(b, j, probe_pred);
+  return true;
 }
 
 // ---- partial / final split for multi-GPU group-by: run everything below the root
@@ -109,7 +159,8 @@ void Plan::execute_partial(int64_t row_base) {
   partial_active_ = true;
   partial_op_->set_row_base(row_base);
   const Needed need = fusion() ? agg_child_needs(n, fused, width_of(child)) : Needed();
-  for (const DBatch& b : run(child, need)) partial_op_->push(b);
+  if (!feed_fused_join(*partial_op_, child, fused, need))
+    for (const DBatch& b : run(child, need)) partial_op_->push(b);
   description_ += partial_op_->describe() + "; ";
   scan_kernel_ms_ = partial_op_->scan_kernel_ms();
   scan_kernel_launches_ = partial_op_->scan_kernel_launches();
@@ -144,18 +195,6 @@ void Plan::finish_partial() {
   partial_op_->finish_host(&results_.back().arr, &results_.back().sch);
   results_.back().on_host = true;
   partial_active_ = false;
-}
-
-// ---- which input columns does an expression read?
-static void mark_refs(const ExprCopy& e, std::vector<bool>& needed, int offset = 0, int lo = 0, int hi = 1 << 30) {
-  for (const ExprNodeCopy& n : e)
-    if (n.op == SQLRS_OP_INPUT_REF && n.index >= lo && n.index < hi) {
-      const int k = n.index - offset;
-      if (k >= 0) {
-        if (k >= (int)needed.size()) needed.resize(k + 1, false);
-        needed[k] = true;
-      }
-    }
 }
 
 int Plan::width_of(int idx) {

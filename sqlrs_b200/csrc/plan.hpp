@@ -52,6 +52,7 @@ class Plan {
   using Needed = std::vector<bool>;  // per output column of a node: does anything above read it?  empty = all
   std::vector<DBatch> run(int idx, const Needed& needed);
   void run_agg_to_host(int idx, Result* res);
+  bool feed_fused_join(AggOp& op, int child, const ExprCopy& agg_fused_pred, const Needed& need);
   int width_of(int idx);              // number of output columns of a node (needs its scans pushed)
   Needed agg_child_needs(const Node& agg, const ExprCopy& fused_pred, int child_width) const;
   bool fusion() const { return !(opt_.flags & SQLRS_FLAG_NO_FUSION); }

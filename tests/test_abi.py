@@ -117,3 +117,27 @@ def test_generator_spec_row_counts(oracle):
     assert t.num_rows == n and 3.9 < n / 15000 < 4.1
     ok = t.column("l_orderkey").to_numpy()
     assert (ok[1:] >= ok[:-1]).all() and ok[0] == 1 and ok[-1] == 15000   # clustered on orderkey like dbgen
+
+
+def test_q3_fused_probe_aggregate_kernel_compiles(cuda_lib):
+    """the fused scan -> filter -> probe -> group-by kernel of Q3's last stage specialises and compiles for sm_100a"""
+    from sqlrs_b200.host.expr import EMPTY_EXPR
+
+    (_, _), (s2, s2s) = tpch.q3_stage_plans()
+    join = s2.child
+    aggs, groups = AggArray(s2.agg_funcs, join.join_output_schema), ExprArray(s2.group_by)
+    rk = ExprArray([r for _, r in join.join_condition.on])
+    pp = join.right.expr.flatten()
+    bs, ps = ffi.export_schema(s2s[0]), ffi.export_schema(s2s[1])
+    src = C.c_void_p()
+    opt = cuda_lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    try:
+        cuda_lib.check(cuda_lib.debug_compile_joinagg(aggs.ptr, aggs.n, groups.ptr, groups.n, rk.ptr, rk.n, C.byref(pp.c), C.byref(EMPTY_EXPR.c),
+                                                      C.byref(bs), C.byref(ps), C.byref(opt), 1, C.byref(src)))
+        text = C.string_at(src.value).decode()
+    finally:
+        ffi.release_schema(bs)
+        ffi.release_schema(ps)
+        if src.value:
+            cuda_lib.free(src)
+    assert "sq_joinagg_kernel" in text and "sq_probe_row" in text and "SQ_LDB_I64(4, b)" in text
