@@ -41,54 +41,151 @@ struct SqSlotTable {
   u32* ngroups;
 };
 
-// group index of the row's key in the CTA-shared table, inserting it if new; -1 = more than
-// SQ_SLOTS groups.  Claim (CAS 0->1), write identity + group index, publish (2): a reader that meets a
-// slot being written spins — independent thread scheduling lets the writer lane progress.
-__device__ __forceinline__ int sq_small_lookup(const SqSlotTable& t, const SqRow& o) {
+// ---- CTA-shared slot table, two-level protocol.
+// Hot path: sq_small_find — read-only probe, no waiting: the dense group index, or -1 when the key is not
+// (yet) published.  Cold path (each CTA meets each group once): sq_small_insert — blocking find-or-insert run by
+// ONE elected lane per warp at a time (see the warp-uniform loop in the kernel), so a lane never spins on a slot
+// that a sibling lane of its own warp is still writing; the writer it may wait for is always in another warp.
+struct SqKey {  // identity of a row's group, passed BY VALUE to the out-of-line cold path
+  u64 h;
+  u64 kb[SQ_NKEYS > 0 ? SQ_NKEYS : 1];
+  u32 knull;
+};
+template <typename R>
+__device__ __forceinline__ bool sq_small_same(const SqSlotTable& t, u32 s, const R& o) {
+  if (*((volatile u64*)&t.thash[s]) != o.h) return false;
+#if SQ_MATCH_KEYS
+  bool same = *((volatile u32*)&t.tknull[s]) == o.knull;
+#pragma unroll
+  for (int k = 0; k < SQ_NKEYS; k++) same = same && (*((volatile u64*)&t.tkeys[s * (SQ_NKEYS > 0 ? SQ_NKEYS : 1) + k]) == o.kb[k]);
+  return same;
+#else
+  return true;
+#endif
+}
+
+template <int TS, typename R>
+__device__ __forceinline__ int sq_small_find(const SqSlotTable& t, const R& o) {
 #if SQ_NKEYS == 0
   return 0;
 #else
-  u32 s = sq_mix32(o.h) & (SQ_TSLOTS - 1);
-  for (int probes = 0; probes < SQ_TSLOTS;) {
-    const u32 st = *((volatile u32*)&t.tstate[s]);
-    if (st == 2u) {
-      if (*((volatile u64*)&t.thash[s]) == o.h) {
-#if SQ_MATCH_KEYS
-        bool same = *((volatile u32*)&t.tknull[s]) == o.knull;
-#pragma unroll
-        for (int k = 0; k < SQ_NKEYS; k++) same = same && (*((volatile u64*)&t.tkeys[s * SQ_NKEYS + k]) == o.kb[k]);
-        if (same) return (int)*((volatile u32*)&t.tgroup[s]);
-#else
-        return (int)*((volatile u32*)&t.tgroup[s]);
-#endif
-      }
-      s = (s + 1) & (SQ_TSLOTS - 1);
-      probes++;
-      continue;
-    }
-    if (st == 0u && atomicCAS(&t.tstate[s], 0u, 1u) == 0u) {
-      const u32 g = atomicAdd(t.ngroups, 1u);
-      if (g >= SQ_SLOTS) {       // too many groups for the private accumulators: leave the slot unusable
-        t.thash[s] = o.h;
-        t.tgroup[s] = 0xffffffffu;
-      } else {
-        t.thash[s] = o.h;
-#pragma unroll
-        for (int k = 0; k < SQ_NKEYS; k++) t.tkeys[s * SQ_NKEYS + k] = o.kb[k];
-        t.tknull[s] = o.knull;
-        t.tgroup[s] = g;
-      }
-      __threadfence_block();
-      atomicExch(&t.tstate[s], 2u);
-      return g >= SQ_SLOTS ? -1 : (int)g;
-    }
-    // st == 1 (or lost the claim): look again
+  u32 s = sq_mix32(o.h) & (TS - 1);
+  for (int probes = 0; probes < TS; probes++) {
+    if (*((volatile u32*)&t.tstate[s]) != 2u) return -1;  // empty or being written: not published (yet)
+    if (sq_small_same(t, s, o)) return (int)*((volatile u32*)&t.tgroup[s]);
+    s = (s + 1) & (TS - 1);
   }
   return -1;
 #endif
 }
 
-extern "C" __global__ void __launch_bounds__(SQ_BLOCK) sq_agg_small(SqIn in, i64 n, i64 row_base, SqPartial part,
+// blocking find-or-insert; -1 = more than SQ_SLOTS groups (the slot is published as unusable)
+template <int TS, int NG>
+__device__ __forceinline__ int sq_small_insert(const SqSlotTable& t, const SqKey& o) {
+#if SQ_NKEYS == 0
+  return 0;
+#else
+  u32 s = sq_mix32(o.h) & (TS - 1);
+  for (int probes = 0; probes < TS;) {
+    const u32 st = *((volatile u32*)&t.tstate[s]);
+    if (st == 2u) {
+      if (sq_small_same(t, s, o)) {
+        const u32 g = *((volatile u32*)&t.tgroup[s]);
+        return g < NG ? (int)g : -1;
+      }
+      s = (s + 1) & (TS - 1);
+      probes++;
+      continue;
+    }
+    if (st == 0u && atomicCAS(&t.tstate[s], 0u, 1u) == 0u) {
+      const u32 g = atomicAdd(t.ngroups, 1u);
+      t.thash[s] = o.h;
+#pragma unroll
+      for (int k = 0; k < SQ_NKEYS; k++) t.tkeys[s * SQ_NKEYS + k] = o.kb[k];
+      t.tknull[s] = o.knull;
+      t.tgroup[s] = g < NG ? g : 0xffffffffu;
+      __threadfence_block();
+      atomicExch(&t.tstate[s], 2u);
+      return g < NG ? (int)g : -1;
+    }
+    // st == 1 (a lane of ANOTHER warp is publishing this slot) or the claim was lost: look again
+  }
+  return -1;
+#endif
+}
+
+// group index for every live lane of the warp (call with the whole warp converged)
+// cold path of sq_small_group: some lane of the (converged) warp met an unpublished key
+template <int TS, int NG>
+__device__ __noinline__ int sq_small_resolve(const SqSlotTable t, const SqKey o, int g, bool need) {  // -2 = overflow
+  bool overflow = false;
+  while (__any_sync(SQ_FULL, need)) {
+    const int leader = __ffs(__ballot_sync(SQ_FULL, need)) - 1;
+    if ((int)(threadIdx.x & 31) == leader) {
+      g = sq_small_insert<TS, NG>(t, o);
+      if (g < 0) overflow = true;
+      need = false;
+    }
+    __syncwarp();
+    if (need) {  // the leader may just have published this lane's key
+      g = sq_small_find<TS>(t, o);
+      need = g < 0;
+    }
+  }
+  return overflow ? -2 : g;
+}
+
+// group index for every live lane of the warp (call with the whole warp converged)
+template <int TS, int NG>
+__device__ __forceinline__ int sq_small_group(const SqSlotTable& t, const SqRow& o, bool live, bool& overflow) {
+  int g = live ? sq_small_find<TS>(t, o) : 0;
+  const bool need = live && g < 0;  // not published yet (or an overflowed slot, which reads back as -1)
+  if (__any_sync(SQ_FULL, need)) {
+    SqKey key;
+    key.h = o.h;
+    key.knull = o.knull;
+#pragma unroll
+    for (int k = 0; k < (SQ_NKEYS > 0 ? SQ_NKEYS : 1); k++) key.kb[k] = o.kb[k];
+    g = sq_small_resolve<TS, NG>(t, key, g, need);
+    if (g == -2) {
+      overflow = true;
+      g = -1;
+    }
+  }
+  return live ? g : -1;
+}
+
+// One tile processed with the blocking protocol: called (out of line, by the whole converged warp) only when some
+// lane met a key that is not published yet — a handful of tiles per CTA.  Re-evaluates the tile's rows so that
+// nothing of the hot loop has to stay live across the call.  Returns bit 0 = error flag, bit 1 = overflow.
+__device__ __noinline__ u32 sq_small_tile_slow(const SqIn in, i64 n, i64 row_base, i64 base, u64* acc, const SqSlotTable tab) {
+  const int tid = threadIdx.x;
+  u32 ret = 0;
+  for (int u = 0; u < SQ_UNROLL; u++) {
+    const i64 r = base + (i64)u * SQ_BLOCK + tid;
+    const bool inb = r < n;
+    SqRow o;
+    bool e0 = false, e1 = false;
+    sq_row(in, inb ? r : n - 1, o, e0, e1);
+    const bool live = inb && o.pass;
+    if ((inb && e0) || (live && e1)) ret |= 1u;
+    bool ovf = false;
+    const int g = sq_small_group<SQ_TSLOTS, SQ_SLOTS>(tab, o, live, ovf);
+    if (ovf) ret |= 2u;
+    __syncwarp();
+    if (g >= 0) {
+      u64* a = acc + (size_t)g * SQ_BLOCK + tid;
+      sq_acc_update(a, SQ_SLOTS * SQ_BLOCK, o);
+      u64* mr = a + (size_t)SQ_NACC * SQ_SLOTS * SQ_BLOCK;
+      const u64 gr = (u64)(row_base + r);
+      if (gr < *mr) *mr = gr;
+    }
+    __syncwarp();
+  }
+  return ret;
+}
+
+extern "C" __global__ void __launch_bounds__(SQ_BLOCK, SQ_MINCTAS) sq_agg_small(SqIn in, i64 n, i64 row_base, SqPartial part,
                                                                      u32* __restrict__ status, u32* __restrict__ err) {
   extern __shared__ __align__(16) unsigned char sq_smem[];
   u64* acc = (u64*)sq_smem;
@@ -134,29 +231,37 @@ extern "C" __global__ void __launch_bounds__(SQ_BLOCK) sq_agg_small(SqIn in, i64
       live[u] = inb && o[u].pass;
       any_err |= (inb && e0) || (live[u] && e1);
     }
+    // group lookup, hot path: read-only probes of the CTA-shared slot table, no waiting, no calls
+    int g[SQ_UNROLL];
+    bool miss = false;
 #pragma unroll
     for (int u = 0; u < SQ_UNROLL; u++) {
-      int g = -1;
-      if (live[u]) {
-        g = sq_small_lookup(tab, o[u]);
-        if (g < 0) {
-          overflow = true;
-          *((volatile u32*)flags) = 1u;
-          atomicOr(status, SQ_STATUS_OVERFLOW);  // lets the other CTAs stop early
-        }
+      g[u] = live[u] ? sq_small_find<SQ_TSLOTS>(tab, o[u]) : -1;
+      miss |= live[u] && g[u] < 0;
+    }
+    // the probes are the only divergent code: reconverge (without this the warp stays split per group and every
+    // later load is replayed per fragment), then decide warp-uniformly
+    if (__any_sync(SQ_FULL, miss)) {  // an unpublished key: start-up tiles only
+      const u32 ret = sq_small_tile_slow(in, n, row_base, base, acc, tab);
+      any_err |= (ret & 1u) != 0u;
+      if (ret & 2u) {
+        overflow = true;
+        *((volatile u32*)flags) = 1u;
+        atomicOr(status, SQ_STATUS_OVERFLOW);  // lets the other CTAs stop early
       }
-      // the lookup is the only divergent code: reconverge before the (uniform, predicated) accumulate —
-      // without this the warp stays split per group and every later load is replayed per fragment
-      __syncwarp();
-      if (g >= 0) {
-        u64* a = acc + (size_t)g * SQ_BLOCK + tid;
+      continue;
+    }
+#pragma unroll
+    for (int u = 0; u < SQ_UNROLL; u++) {
+      if (g[u] >= 0) {
+        u64* a = acc + (size_t)g[u] * SQ_BLOCK + tid;
         sq_acc_update(a, SQ_SLOTS * SQ_BLOCK, o[u]);
         u64* mr = a + (size_t)SQ_NACC * SQ_SLOTS * SQ_BLOCK;
         const u64 gr = (u64)(row_base + base + (i64)u * SQ_BLOCK + tid);
         if (gr < *mr) *mr = gr;
       }
-      __syncwarp();
     }
+    __syncwarp();
   }
   if (any_err) atomicOr(err, 1u);
   if (overflow) *((volatile u32*)flags) = 1u;
@@ -240,56 +345,54 @@ extern "C" __global__ void __launch_bounds__(128) sq_agg_merge(SqPartial part, i
 //   u64 macc[(W+1)][M]; slot table with 2*M entries: thash, tkeys[K], tknull, tstate, tgroup; ngroups; flags
 #define SQ_MTSLOTS (2 * SQ_MSLOTS)
 
-__device__ __forceinline__ int sq_medium_lookup(u64* thash, u64* tkeys, u32* tknull, u32* tstate, u32* tgroup, u32* ngroups, const SqRow& o) {
-  u32 s = sq_mix32(o.h) & (SQ_MTSLOTS - 1);
-  for (int probes = 0; probes < SQ_MTSLOTS;) {
-    if (*((volatile u32*)ngroups) > SQ_MSLOTS) return -1;  // already overflowed: do not walk a full table
-    const u32 st = *((volatile u32*)&tstate[s]);
-    if (st == 2u) {
-      if (*((volatile u64*)&thash[s]) == o.h) {
-#if SQ_MATCH_KEYS
-        bool same = *((volatile u32*)&tknull[s]) == o.knull;
+// the medium kernel's slow tile (see sq_small_tile_slow): blocking protocol + shared-memory atomics
+__device__ __noinline__ u32 sq_medium_tile_slow(const SqIn in, i64 n, i64 row_base, i64 base, u64* macc, const SqSlotTable tab) {
+  const int tid = threadIdx.x;
+  u32 ret = 0;
+  for (int u = 0; u < SQ_MUNROLL; u++) {
+    const i64 r = base + (i64)u * 256 + tid;
+    const bool inb = r < n;
+    SqRow o;
+    bool e0 = false, e1 = false;
+    sq_row(in, inb ? r : n - 1, o, e0, e1);
+    const bool live = inb && o.pass;
+    if ((inb && e0) || (live && e1)) ret |= 1u;
+    bool ovf = false;
+    const int g = sq_small_group<SQ_MTSLOTS, SQ_MSLOTS>(tab, o, live, ovf);
+    if (ovf) ret |= 2u;
+    __syncwarp();
+    if (g >= 0) {
+      u64 local[SQ_NACC > 0 ? SQ_NACC : 1];
 #pragma unroll
-        for (int k = 0; k < SQ_NKEYS; k++) same = same && (*((volatile u64*)&tkeys[s * (SQ_NKEYS > 0 ? SQ_NKEYS : 1) + k]) == o.kb[k]);
-        if (same) return (int)*((volatile u32*)&tgroup[s]);
-#else
-        return (int)*((volatile u32*)&tgroup[s]);
-#endif
-      }
-      s = (s + 1) & (SQ_MTSLOTS - 1);
-      probes++;
-      continue;
-    }
-    if (st == 0u && atomicCAS(&tstate[s], 0u, 1u) == 0u) {
-      const u32 g = atomicAdd(ngroups, 1u);
-      thash[s] = o.h;
-      if (g < SQ_MSLOTS) {
+      for (int w = 0; w < SQ_NACC; w++) local[w] = sq_acc_identity(w);
+      sq_acc_update(local, 1, o);
 #pragma unroll
-        for (int k = 0; k < SQ_NKEYS; k++) tkeys[s * (SQ_NKEYS > 0 ? SQ_NKEYS : 1) + k] = o.kb[k];
-        tknull[s] = o.knull;
-        tgroup[s] = g;
-      } else {
-        tgroup[s] = 0xffffffffu;
-      }
-      __threadfence_block();
-      atomicExch(&tstate[s], 2u);
-      return g >= SQ_MSLOTS ? -1 : (int)g;
+      for (int w = 0; w < SQ_NACC; w++) sq_acc_merge_shared(&macc[(size_t)w * SQ_MSLOTS + g], w, local[w]);
+      atomicMin(&macc[(size_t)SQ_NACC * SQ_MSLOTS + g], (u64)(row_base + r));
     }
+    __syncwarp();
   }
-  return -1;
+  return ret;
 }
 
 extern "C" __global__ void __launch_bounds__(256) sq_agg_medium(SqIn in, i64 n, i64 row_base, SqPartial part,
                                                                  u32* __restrict__ status, u32* __restrict__ err) {
   extern __shared__ __align__(16) unsigned char sq_smem[];
   u64* macc = (u64*)sq_smem;
-  u64* thash = macc + (size_t)SQ_ACC_WORDS * SQ_MSLOTS;
-  u64* tkeys = thash + SQ_MTSLOTS;
-  u32* tknull = (u32*)(tkeys + SQ_MTSLOTS * (SQ_NKEYS > 0 ? SQ_NKEYS : 1));
-  u32* tstate = tknull + SQ_MTSLOTS;
-  u32* tgroup = tstate + SQ_MTSLOTS;
-  u32* ngroups = tgroup + SQ_MTSLOTS;
-  u32* flags = ngroups + 1;
+  SqSlotTable tab;
+  tab.thash = macc + (size_t)SQ_ACC_WORDS * SQ_MSLOTS;
+  tab.tkeys = tab.thash + SQ_MTSLOTS;
+  tab.tknull = (u32*)(tab.tkeys + SQ_MTSLOTS * (SQ_NKEYS > 0 ? SQ_NKEYS : 1));
+  tab.tstate = tab.tknull + SQ_MTSLOTS;
+  tab.tgroup = tab.tstate + SQ_MTSLOTS;
+  tab.ngroups = tab.tgroup + SQ_MTSLOTS;
+  u32* flags = tab.ngroups + 1;
+  u64* thash = tab.thash;
+  u64* tkeys = tab.tkeys;
+  u32* tknull = tab.tknull;
+  u32* tstate = tab.tstate;
+  u32* tgroup = tab.tgroup;
+  u32* ngroups = tab.ngroups;
   const int tid = threadIdx.x;
   if ((*((volatile u32*)status) & SQ_STATUS_OVERFLOW2) != 0u) return;
 
@@ -319,28 +422,35 @@ extern "C" __global__ void __launch_bounds__(256) sq_agg_medium(SqIn in, i64 n, 
       live[u] = inb && o[u].pass;
       any_err |= (inb && e0) || (live[u] && e1);
     }
+    int g[SQ_MUNROLL];
+    bool miss = false;
 #pragma unroll
     for (int u = 0; u < SQ_MUNROLL; u++) {
-      int g = -1;
-      if (live[u]) {
-        g = sq_medium_lookup(thash, tkeys, tknull, tstate, tgroup, ngroups, o[u]);
-        if (g < 0) {
-          overflow = true;
-          *((volatile u32*)flags) = 1u;
-        }
+      g[u] = live[u] ? sq_small_find<SQ_MTSLOTS>(tab, o[u]) : -1;
+      miss |= live[u] && g[u] < 0;
+    }
+    if (__any_sync(SQ_FULL, miss)) {  // an unpublished key: out-of-line blocking protocol for this tile
+      const u32 ret = sq_medium_tile_slow(in, n, row_base, base, macc, tab);
+      any_err |= (ret & 1u) != 0u;
+      if (ret & 2u) {
+        overflow = true;
+        *((volatile u32*)flags) = 1u;
       }
-      __syncwarp();
-      if (g >= 0) {
+      continue;
+    }
+#pragma unroll
+    for (int u = 0; u < SQ_MUNROLL; u++) {
+      if (g[u] >= 0) {
         u64 local[SQ_NACC > 0 ? SQ_NACC : 1];
 #pragma unroll
         for (int w = 0; w < SQ_NACC; w++) local[w] = sq_acc_identity(w);
         sq_acc_update(local, 1, o[u]);
 #pragma unroll
-        for (int w = 0; w < SQ_NACC; w++) sq_acc_merge_shared(&macc[(size_t)w * SQ_MSLOTS + g], w, local[w]);
-        atomicMin(&macc[(size_t)SQ_NACC * SQ_MSLOTS + g], (u64)(row_base + base + (i64)u * 256 + tid));
+        for (int w = 0; w < SQ_NACC; w++) sq_acc_merge_shared(&macc[(size_t)w * SQ_MSLOTS + g[u]], w, local[w]);
+        atomicMin(&macc[(size_t)SQ_NACC * SQ_MSLOTS + g[u]], (u64)(row_base + base + (i64)u * 256 + tid));
       }
-      __syncwarp();
     }
+    __syncwarp();
   }
   if (any_err) atomicOr(err, 1u);
   if (overflow) *((volatile u32*)flags) = 1u;

@@ -53,29 +53,83 @@ __device__ __forceinline__ int sq_join_find(const SqJoin& t, const SqProbe& p) {
   return -1;
 }
 
+// continue a probe sequence at slot `s` (the slow path behind the batched first probe below)
+__device__ __forceinline__ int sq_join_find_from(const SqJoin& t, const SqProbe& p, u32 s) {
+  const u32 mask = t.capacity - 1;
+  for (u32 probes = 0; probes <= mask; probes++) {
+    const i64 rep = __ldg(&t.slot_rep[s]);
+    if (rep < 0) return -1;
+    if (__ldg(&t.h[rep]) == p.h) {
+#if SQ_JMATCH
+      bool same = true;
+#pragma unroll
+      for (int k = 0; k < SQ_JKEYS; k++) same = same && (__ldg(&t.keys[(size_t)k * t.n_build + rep]) == p.kb[k]);
+      if (same) return (int)s;
+#else
+      return (int)s;
+#endif
+    }
+    s = (s + 1) & mask;
+  }
+  return -1;
+}
+
+#ifndef SQ_JUNROLL
+#define SQ_JUNROLL 4
+#endif
+
 extern "C" __global__ void __launch_bounds__(256) sq_joinagg_kernel(SqIn in, SqInB inb, i64 n, i64 row_base, SqJoin jt, SqTable table, i64 batch_no,
                                                                      u32* __restrict__ status, u32* __restrict__ err) {
   bool any_err = false;
   const int lane = threadIdx.x & 31;
   const i64 stride = (i64)gridDim.x * blockDim.x;
-  // warp-uniform trips, two rows per lane per trip so that the probe-side loads of both are in flight together
-  for (i64 base = ((i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * 2; base < n; base += stride * 2) {
-    SqProbe p[2];
-    i64 r[2];
-    bool live[2];
+  const u32 jmask = jt.capacity - 1;
+  // warp-uniform trips, SQ_JUNROLL rows per lane per trip.  The probe is a chain of dependent random reads
+  // (slot -> representative row -> its hash / key), so the first probe of all SQ_JUNROLL rows is issued level by
+  // level: SQ_JUNROLL independent reads in flight per thread instead of one chain at a time.
+  for (i64 base = ((i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * SQ_JUNROLL; base < n; base += stride * SQ_JUNROLL) {
+    SqProbe p[SQ_JUNROLL];
+    i64 r[SQ_JUNROLL];
+    bool live[SQ_JUNROLL];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < SQ_JUNROLL; u++) {
       r[u] = base + u * 32 + lane;
       const bool inb_row = r[u] < n;
       bool e0 = false, e1 = false;
       sq_probe_row(in, inb_row ? r[u] : n - 1, p[u], e0, e1);
       live[u] = inb_row && p[u].pass;
-      any_err |= (inb_row && e0) || (live[u] && e1);
+#if SQ_JMATCH
+      live[u] = live[u] && p[u].knull == 0u;  // SQL semantics: a NULL key never joins
+#endif
+      any_err |= (inb_row && e0) || (inb_row && p[u].pass && e1);
+    }
+    u32 s0[SQ_JUNROLL];
+    i64 rep[SQ_JUNROLL];
+    u64 hh[SQ_JUNROLL];
+#pragma unroll
+    for (int u = 0; u < SQ_JUNROLL; u++) {
+      s0[u] = sq_mix32(p[u].h) & jmask;
+      rep[u] = live[u] ? __ldg(&jt.slot_rep[s0[u]]) : -1;
     }
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < SQ_JUNROLL; u++) hh[u] = rep[u] >= 0 ? __ldg(&jt.h[rep[u]]) : 0ULL;
+#if SQ_JMATCH
+    u64 k0[SQ_JUNROLL];
+#pragma unroll
+    for (int u = 0; u < SQ_JUNROLL; u++) k0[u] = rep[u] >= 0 ? __ldg(&jt.keys[rep[u]]) : 0ULL;
+#endif
+#pragma unroll
+    for (int u = 0; u < SQ_JUNROLL; u++) {
       int slot = -1;
-      if (live[u]) slot = sq_join_find(jt, p[u]);
+      if (rep[u] >= 0) {
+        bool hit = hh[u] == p[u].h;
+#if SQ_JMATCH
+        hit = hit && k0[u] == p[u].kb[0];
+#pragma unroll
+        for (int k = 1; k < SQ_JKEYS; k++) hit = hit && (__ldg(&jt.keys[(size_t)k * jt.n_build + rep[u]]) == p[u].kb[k]);
+#endif
+        slot = hit ? (int)s0[u] : sq_join_find_from(jt, p[u], (s0[u] + 1) & jmask);
+      }
       __syncwarp();
       if (slot >= 0) {
         const u32 cnt = __ldg(&jt.slot_count[slot]);

@@ -116,7 +116,7 @@ struct AggOp::Compiled {
   std::vector<AggPlan> aggs;
   std::vector<WordPlan> words;
   std::vector<int> key_dtypes;
-  int block = 128, slots = 8, unroll = 4;
+  int block = 128, slots = 8, unroll = 4, min_ctas = 1;
   size_t small_smem = 0;
   int small_grid = 0;
   bool small_ok = true;
@@ -312,7 +312,7 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
   comp->slots = K == 0 ? 1 : 8;
   // rows per thread per trip: 8 keeps ~64 8-byte loads in flight per thread for narrow scans (Q1': +4 % over 4);
   // wide scans stay at 4 to bound registers
-  comp->unroll = prog.n_loaded_columns() <= 8 ? 8 : 4;
+  comp->unroll = 4;
   comp->block = 128;
   auto smem_for = [&](int T) {
     return (size_t)(W + 1) * comp->slots * T * 8 + (size_t)4 * comp->slots * (8 + 8 * std::max(K, 1) + 4 + 4 + 4) + 16;
@@ -326,6 +326,15 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
   while (comp->block > 32 && smem_for(comp->block) > 200 * 1024) comp->block /= 2;
   comp->small_ok = smem_for(comp->block) <= 200 * 1024;
   comp->small_smem = smem_for(comp->block);
+  // rows per thread per trip (measured on Q1' SF10, profiles/): 6 keeps ~48 8-byte loads in flight per thread and is
+  // the best for narrow scans with the cheap placement hash (0.673 ms vs 0.710 at 4, 0.811 at 8); with the
+  // reference's ahash identity the longer program is fastest at 4.  The register budget is handed to the compiler
+  // as __launch_bounds__(block, min CTAs) so that a wider program cannot silently drop a resident CTA.
+  if (!std::getenv("SQLRS_B200_AGG_UNROLL"))
+    comp->unroll = (comp->block == 128 && prog.n_loaded_columns() <= 8 && opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY) ? 6 : 4;
+  const int smem_ctas = (int)std::max<size_t>(1, (200 * 1024) / std::max<size_t>(comp->small_smem, 1));
+  const int reg_ctas = 65536 / (comp->block * (comp->unroll >= 6 ? 170 : 128));
+  comp->min_ctas = std::max(1, std::min(smem_ctas, reg_ctas));
   // sq_agg_medium: one accumulator copy per CTA for up to M groups; M = the largest power of two whose shared
   // memory (accumulators + 2M-entry slot table) stays <= 72 KB, i.e. three 256-thread CTAs per SM
   auto medium_smem_for = [&](int M) { return (size_t)(W + 1) * M * 8 + (size_t)2 * M * (8 + 8 * std::max(K, 1) + 12) + 16; };
@@ -376,6 +385,7 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
   s << "#define SQ_NKEYS " << K << "\n#define SQ_NACC " << W << "\n";
   s << "#define SQ_MATCH_KEYS " << (opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY ? 1 : 0) << "\n";
   s << "#define SQ_MSLOTS " << std::max(comp->mslots, 64) << "\n#define SQ_MUNROLL " << comp->munroll << "\n";
+  s << "#define SQ_MINCTAS " << comp->min_ctas << "\n";
   s << "#define SQ_BLOCK " << comp->block << "\n#define SQ_SLOTS " << comp->slots << "\n#define SQ_UNROLL " << comp->unroll << "\n";
   s << "struct SqRow {\n  bool pass; u64 h; u64 kb[" << std::max(K, 1) << "]; u32 knull;\n";
   for (size_t j = 0; j < aggs_.size(); j++) s << "  " << ctype_of(args[j].dtype) << " a" << j << "; bool an" << j << ";\n";
@@ -741,7 +751,8 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
   // The number of joined rows (and groups) is unknown before the probe: aggregate into a batch-local table sized
   // optimistically; a full table discards it and retries 4x larger, so a batch counts all-or-nothing.
   const JoinTableView& jt = join.table_view();
-  uint64_t cap = std::max<uint64_t>(4ULL * (uint64_t)jt.n_build, 1ULL << 16);
+  // guess: about as many groups as build rows (x2 head-room in the open-addressed table)
+  uint64_t cap = std::max<uint64_t>(2ULL * (uint64_t)jt.n_build, 1ULL << 16);
   std::unique_ptr<Table> local;
   uint32_t hc[4] = {0, 0, 0, 0};
   for (;;) {
@@ -755,7 +766,7 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
     JoinTableView jv = jt;
     void* args[] = {in.ptr(), inb.ptr(), &n_arg, &rb, &jv, &tv, &bn, &status, &errp};
     const int sms = device_sm_count(ctx_.device);
-    unsigned grid = (unsigned)std::min<int64_t>(div_up(n, 512), (int64_t)sms * 8);
+    unsigned grid = (unsigned)std::min<int64_t>(div_up(n, 1024), (int64_t)sms * 8);  // 256 threads x SQ_JUNROLL (4) rows per trip
     ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
     jit_launch(kit->second, grid, 256, 0, ctx_.stream, args);
     timer.stop();
@@ -858,7 +869,11 @@ void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
   Trace tr("agg.finish_host", ctx_.stream);
   std::vector<Field> fields;
   HostGroups g;
-  build_output(&fields, &g);
+  {
+    Trace t1("  finish.build_output", ctx_.stream);
+    build_output(&fields, &g);
+  }
+  Trace t2("  finish.convert+export", ctx_.stream);
   const Compiled& c = *cache_.begin()->second;
   const int K = (int)c.key_dtypes.size(), W = (int)c.words.size();
   const uint32_t n = g.n;
@@ -878,6 +893,7 @@ void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
     bool any_null = false;
     for (uint32_t i = 0; i < n; i++) any_null |= (g.knull[order[i]] >> k) & 1u;
     if (any_null) col.valid.assign(n, 1);
+    (col.dtype == SQLRS_DT_FLOAT64) ? col.f.reserve(n) : col.i.reserve(n);
     for (uint32_t i = 0; i < n; i++) {
       const uint32_t e = order[i];
       const uint64_t bits = g.keys[(size_t)k * n + e];
@@ -898,6 +914,7 @@ void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
     col.dtype = p.out_dtype;
     std::vector<uint8_t> valid(rows, 1);
     bool any_null = false;
+    (col.dtype == SQLRS_DT_FLOAT64) ? col.f.reserve(rows) : col.i.reserve(rows);
     for (int64_t i = 0; i < rows; i++) {
       uint64_t word = 0, nvalid = 1;
       if (!synth_row) {
