@@ -33,6 +33,12 @@ struct Error : std::runtime_error {
       ::sq::fail(SQLRS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));             \
   } while (0)
 
+#ifdef __CUDACC__
+#define SQ_HD __host__ __device__
+#else
+#define SQ_HD
+#endif
+
 extern std::atomic<int64_t> g_kernel_launches;
 inline void count_launch(int64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 

@@ -12,7 +12,17 @@
 //   struct SqRow {pass, h, kb[K], knull, args...};  sq_row(in, inb, r, b, o, e1)   — join filter + group keys + arguments
 //   sq_acc_identity / sq_acc_update / sq_acc_merge_global as in agg.cuh
 // HBM-bound on the probe-side scan: algorithmic bytes = 8 B x referenced probe columns per probe row (+ the build
-// side once); the table probes are random 8-byte reads that mostly hit L2.
+// side once).
+//
+// Two phases per warp trip (SQ_JUNROLL x 32 rows):
+//   A. streaming: every lane evaluates the fused Filter + join-key hash of SQ_JUNROLL rows (coalesced 8-byte loads,
+//      all issued before the first use) and tests the hash against the build side's blocked Bloom filter — ONE
+//      8-byte read of an L2-resident table per surviving row.  Rows that may match are appended to a per-warp
+//      queue in shared memory with ballot/popc (warp-aggregated, no atomics).
+//   B. compacted: whenever the queue holds >= 32 candidates a FULL warp probes the hash table (dependent random
+//      reads: slot -> representative row -> hash/key), walks the CSR match list, gathers the build columns and
+//      upserts into the group table.  So the divergent, latency-bound part runs with all lanes busy however
+//      selective the join is, and phase A never waits on it.
 
 struct SqJoin {           // mirrors sq::JoinTableView (kernels_aot.hpp)
   const i64* slot_rep;    // representative build row per slot, -1 = empty
@@ -27,7 +37,15 @@ struct SqJoin {           // mirrors sq::JoinTableView (kernels_aot.hpp)
   int n_keys;
   int match_keys;
   const u32* build_keep;
+  const u64* bloom;       // blocked Bloom filter over the build hashes (3 bits in one 64-bit word per key)
+  u32 bloom_mask;
 };
+
+__device__ __forceinline__ u32 sq_bloom_word(u64 h, u32 mask) { return (u32)((h * 0x9E3779B97F4A7C15ULL) >> 40) & mask; }
+__device__ __forceinline__ u64 sq_bloom_bits(u64 h) {
+  const u64 g = h * 0x9E3779B97F4A7C15ULL;
+  return (1ULL << ((g >> 34) & 63)) | (1ULL << ((g >> 28) & 63)) | (1ULL << ((g >> 22) & 63));
+}
 
 __device__ __forceinline__ int sq_join_find(const SqJoin& t, const SqProbe& p) {
 #if SQ_JMATCH
@@ -53,112 +71,92 @@ __device__ __forceinline__ int sq_join_find(const SqJoin& t, const SqProbe& p) {
   return -1;
 }
 
-// continue a probe sequence at slot `s` (the slow path behind the batched first probe below)
-__device__ __forceinline__ int sq_join_find_from(const SqJoin& t, const SqProbe& p, u32 s) {
-  const u32 mask = t.capacity - 1;
-  for (u32 probes = 0; probes <= mask; probes++) {
-    const i64 rep = __ldg(&t.slot_rep[s]);
-    if (rep < 0) return -1;
-    if (__ldg(&t.h[rep]) == p.h) {
-#if SQ_JMATCH
-      bool same = true;
-#pragma unroll
-      for (int k = 0; k < SQ_JKEYS; k++) same = same && (__ldg(&t.keys[(size_t)k * t.n_build + rep]) == p.kb[k]);
-      if (same) return (int)s;
-#else
-      return (int)s;
+#ifndef SQ_JUNROLL
+#define SQ_JUNROLL 8
 #endif
+#define SQ_JBLOCK 256
+#define SQ_JQUEUE (SQ_JUNROLL * 32 + 32)
+
+// phase B for one candidate row: exact probe, matches in build insertion order, aggregate
+__device__ __forceinline__ void sq_joinagg_candidate(const SqIn& in, const SqInB& inb, i64 r, i64 row_base, const SqJoin& jt, const SqTable& table,
+                                                     i64 batch_no, u32* status, bool& any_err) {
+  SqProbe p;
+  bool e0 = false, e1 = false;
+  sq_probe_row(in, r, p, e0, e1);  // re-evaluated (L1/L2 hits): cheaper than queueing hash + key tuple
+  const int slot = sq_join_find(jt, p);
+  if (slot < 0) return;
+  const u32 cnt = __ldg(&jt.slot_count[slot]);
+  const i64* brow = jt.rows + __ldg(&jt.slot_start[slot]);
+  for (u32 j = 0; j < cnt; j++) {  // per probe row: build rows in insertion order (hash_join.rs:225-235)
+    const i64 b = __ldg(&brow[j]);
+    SqRow o;
+    bool e2 = false;
+    sq_row(in, inb, r, b, o, e2);
+    any_err |= o.pass && e2;
+    if (!o.pass) continue;  // non-equi join filter (apply_join_filter, :47-71)
+    const int g = sq_table_upsert(table, o.h, o.kb, o.knull);
+    if (g < 0) {
+      atomicOr(status, SQ_STATUS_FULL);
+      continue;
     }
-    s = (s + 1) & mask;
+    // first-appearance order of the joined stream = (probe row, match ordinal)
+    const u64 ord = ((u64)(row_base + r) << 20) | (u64)(j < 0xfffffu ? j : 0xfffffu);
+    if (ord < table.min_row[g]) atomicMin(&table.min_row[g], ord);
+    u64 local[SQ_NACC > 0 ? SQ_NACC : 1];
+#pragma unroll
+    for (int w = 0; w < SQ_NACC; w++) local[w] = sq_acc_identity(w);
+    sq_acc_update(local, 1, o);
+#pragma unroll
+    for (int w = 0; w < SQ_NACC; w++) sq_acc_merge_global(&table.acc[(size_t)w * table.capacity + g], w, local[w], batch_no);
   }
-  return -1;
 }
 
-#ifndef SQ_JUNROLL
-#define SQ_JUNROLL 4
-#endif
-
-extern "C" __global__ void __launch_bounds__(256) sq_joinagg_kernel(SqIn in, SqInB inb, i64 n, i64 row_base, SqJoin jt, SqTable table, i64 batch_no,
-                                                                     u32* __restrict__ status, u32* __restrict__ err) {
+extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_kernel(SqIn in, SqInB inb, i64 n, i64 row_base, SqJoin jt, SqTable table, i64 batch_no,
+                                                                           u32* __restrict__ status, u32* __restrict__ err) {
+  __shared__ u32 queue_s[SQ_JBLOCK / 32][SQ_JQUEUE];
   bool any_err = false;
   const int lane = threadIdx.x & 31;
+  u32* queue = queue_s[threadIdx.x >> 5];
+  const u32 lanes_below = (1u << lane) - 1u;
+  u32 queued = 0;  // warp-uniform
   const i64 stride = (i64)gridDim.x * blockDim.x;
-  const u32 jmask = jt.capacity - 1;
-  // warp-uniform trips, SQ_JUNROLL rows per lane per trip.  The probe is a chain of dependent random reads
-  // (slot -> representative row -> its hash / key), so the first probe of all SQ_JUNROLL rows is issued level by
-  // level: SQ_JUNROLL independent reads in flight per thread instead of one chain at a time.
   for (i64 base = ((i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * SQ_JUNROLL; base < n; base += stride * SQ_JUNROLL) {
-    SqProbe p[SQ_JUNROLL];
-    i64 r[SQ_JUNROLL];
+    // ---- phase A
+    u64 hh[SQ_JUNROLL];
     bool live[SQ_JUNROLL];
 #pragma unroll
     for (int u = 0; u < SQ_JUNROLL; u++) {
-      r[u] = base + u * 32 + lane;
-      const bool inb_row = r[u] < n;
+      const i64 r = base + u * 32 + lane;
+      const bool inb_row = r < n;
+      SqProbe p;
       bool e0 = false, e1 = false;
-      sq_probe_row(in, inb_row ? r[u] : n - 1, p[u], e0, e1);
-      live[u] = inb_row && p[u].pass;
+      sq_probe_row(in, inb_row ? r : n - 1, p, e0, e1);
+      live[u] = inb_row && p.pass;
 #if SQ_JMATCH
-      live[u] = live[u] && p[u].knull == 0u;  // SQL semantics: a NULL key never joins
+      live[u] = live[u] && p.knull == 0u;  // SQL semantics: a NULL key never joins
 #endif
-      any_err |= (inb_row && e0) || (inb_row && p[u].pass && e1);
+      any_err |= (inb_row && e0) || (inb_row && p.pass && e1);
+      hh[u] = p.h;
     }
-    u32 s0[SQ_JUNROLL];
-    i64 rep[SQ_JUNROLL];
-    u64 hh[SQ_JUNROLL];
+    u64 bw[SQ_JUNROLL];
+#pragma unroll
+    for (int u = 0; u < SQ_JUNROLL; u++) bw[u] = live[u] ? __ldg(&jt.bloom[sq_bloom_word(hh[u], jt.bloom_mask)]) : 0ULL;
 #pragma unroll
     for (int u = 0; u < SQ_JUNROLL; u++) {
-      s0[u] = sq_mix32(p[u].h) & jmask;
-      rep[u] = live[u] ? __ldg(&jt.slot_rep[s0[u]]) : -1;
+      const u64 bits = sq_bloom_bits(hh[u]);
+      const bool cand = live[u] && (bw[u] & bits) == bits;
+      const u32 m = __ballot_sync(0xffffffffu, cand);
+      if (cand) queue[queued + __popc(m & lanes_below)] = (u32)(base + u * 32 + lane);  // n < 2^32 (checked by the host)
+      queued += __popc(m);
     }
-#pragma unroll
-    for (int u = 0; u < SQ_JUNROLL; u++) hh[u] = rep[u] >= 0 ? __ldg(&jt.h[rep[u]]) : 0ULL;
-#if SQ_JMATCH
-    u64 k0[SQ_JUNROLL];
-#pragma unroll
-    for (int u = 0; u < SQ_JUNROLL; u++) k0[u] = rep[u] >= 0 ? __ldg(&jt.keys[rep[u]]) : 0ULL;
-#endif
-#pragma unroll
-    for (int u = 0; u < SQ_JUNROLL; u++) {
-      int slot = -1;
-      if (rep[u] >= 0) {
-        bool hit = hh[u] == p[u].h;
-#if SQ_JMATCH
-        hit = hit && k0[u] == p[u].kb[0];
-#pragma unroll
-        for (int k = 1; k < SQ_JKEYS; k++) hit = hit && (__ldg(&jt.keys[(size_t)k * jt.n_build + rep[u]]) == p[u].kb[k]);
-#endif
-        slot = hit ? (int)s0[u] : sq_join_find_from(jt, p[u], (s0[u] + 1) & jmask);
-      }
-      __syncwarp();
-      if (slot >= 0) {
-        const u32 cnt = __ldg(&jt.slot_count[slot]);
-        const i64* brow = jt.rows + __ldg(&jt.slot_start[slot]);
-        for (u32 j = 0; j < cnt; j++) {  // per probe row: build rows in insertion order (hash_join.rs:225-235)
-          const i64 b = __ldg(&brow[j]);
-          SqRow o;
-          bool e1 = false;
-          sq_row(in, inb, r[u], b, o, e1);
-          any_err |= o.pass && e1;
-          if (!o.pass) continue;  // non-equi join filter (apply_join_filter, :47-71)
-          const int g = sq_table_upsert(table, o.h, o.kb, o.knull);
-          if (g < 0) {
-            atomicOr(status, SQ_STATUS_FULL);
-            continue;
-          }
-          // first-appearance order of the joined stream = (probe row, match ordinal)
-          const u64 ord = ((u64)(row_base + r[u]) << 20) | (u64)(j < 0xfffffu ? j : 0xfffffu);
-          if (ord < table.min_row[g]) atomicMin(&table.min_row[g], ord);
-          u64 local[SQ_NACC > 0 ? SQ_NACC : 1];
-#pragma unroll
-          for (int w = 0; w < SQ_NACC; w++) local[w] = sq_acc_identity(w);
-          sq_acc_update(local, 1, o);
-#pragma unroll
-          for (int w = 0; w < SQ_NACC; w++) sq_acc_merge_global(&table.acc[(size_t)w * table.capacity + g], w, local[w], batch_no);
-        }
-      }
+    __syncwarp();
+    // ---- phase B: full warps only
+    while (queued >= 32) {
+      queued -= 32;
+      sq_joinagg_candidate(in, inb, (i64)queue[queued + lane], row_base, jt, table, batch_no, status, any_err);
       __syncwarp();
     }
   }
+  if ((u32)lane < queued) sq_joinagg_candidate(in, inb, (i64)queue[lane], row_base, jt, table, batch_no, status, any_err);
   if (any_err) atomicOr(err, 1u);
 }

@@ -78,7 +78,19 @@ struct JoinTableView {
   int n_keys;
   int match_keys;         // SQLRS_MATCH_HASH_AND_KEY: compare key tuples, NULL never joins
   const uint32_t* build_keep;  // optional bitmap: build rows that pass the Filter fused below the join (nullptr = all)
+  // blocked Bloom filter over the row hashes of the inserted build rows: 3 bits in ONE 64-bit word per key
+  // (join_bloom_word / join_bloom_bits below).  A few MB, so it stays L2-resident under a streaming probe scan
+  // and turns a probe miss — the common case of a selective join — into one 8-byte L2 read.
+  uint64_t* bloom;
+  uint32_t bloom_mask;    // number of words - 1 (power of two)
 };
+
+SQ_HD inline uint32_t join_bloom_word(uint64_t h, uint32_t mask) { return (uint32_t)((h * 0x9E3779B97F4A7C15ULL) >> 40) & mask; }
+SQ_HD inline uint64_t join_bloom_bits(uint64_t h) {
+  const uint64_t g = h * 0x9E3779B97F4A7C15ULL;
+  return (1ULL << ((g >> 34) & 63)) | (1ULL << ((g >> 28) & 63)) | (1ULL << ((g >> 22) & 63));
+}
+uint32_t join_bloom_words(int64_t n_build);  // sizing rule: power of two >= n_build / 4, within [1024, 2^24]
 
 void launch_scan_u32_large(const uint32_t* counts, int64_t m, unsigned long long* offsets, unsigned long long* total,
                            unsigned long long* scratch /* >= ceil(m/4096)+1 */, cudaStream_t stream);

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kBlock) k_join_insert(JoinTableView t, int32_t
       s = (s + 1) & mask;
     }
     row_slot[i] = (int32_t)s;
+    if (t.bloom) atomicOr((unsigned long long*)&t.bloom[join_bloom_word(h, t.bloom_mask)], (unsigned long long)join_bloom_bits(h));
     const uint32_t c = atomicAdd(&t.slot_count[s], 1u) + 1u;
     local_max = c > local_max ? c : local_max;
   }
@@ -108,7 +109,12 @@ __global__ void __launch_bounds__(kBlock) k_join_probe_count(JoinTableView t, co
     if (kept && !(t.match_keys && pknull[r] != 0u)) {
       const uint64_t h = ph[r];
       uint32_t s = mix32(h) & mask;
-      for (uint32_t probes = 0; probes <= mask; probes++) {
+      uint32_t probes = 0;
+      if (t.bloom) {  // a clear bit proves the key absent: most misses end here, on an L2-resident word
+        const uint64_t bits = join_bloom_bits(h);
+        if ((__ldg(&t.bloom[join_bloom_word(h, t.bloom_mask)]) & bits) != bits) probes = mask + 1;
+      }
+      for (; probes <= mask; probes++) {
         const int64_t rep = t.slot_rep[s];
         if (rep < 0) break;
         if (same_key(t, rep, h, pkeys, n_probe, r)) {
@@ -267,6 +273,12 @@ __global__ void __launch_bounds__(kBlock) k_slot_keys(const int32_t* __restrict_
   } while (0)
 
 }  // namespace
+
+uint32_t join_bloom_words(int64_t n_build) {
+  uint64_t w = 1024;
+  while (w < (uint64_t)n_build / 4 && w < (1ULL << 24)) w <<= 1;
+  return (uint32_t)w;
+}
 
 size_t scan_scratch_entries(int64_t m) { return (size_t)div_up(m, kScanChunk) + 1; }
 

@@ -766,7 +766,7 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
     JoinTableView jv = jt;
     void* args[] = {in.ptr(), inb.ptr(), &n_arg, &rb, &jv, &tv, &bn, &status, &errp};
     const int sms = device_sm_count(ctx_.device);
-    unsigned grid = (unsigned)std::min<int64_t>(div_up(n, 1024), (int64_t)sms * 8);  // 256 threads x SQ_JUNROLL (4) rows per trip
+    unsigned grid = (unsigned)std::min<int64_t>(div_up(n, 2048), (int64_t)sms * 8);  // 256 threads x SQ_JUNROLL (8) rows per trip
     ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
     jit_launch(kit->second, grid, 256, 0, ctx_.stream, args);
     timer.stop();

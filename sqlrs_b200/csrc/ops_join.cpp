@@ -15,7 +15,7 @@ struct JoinOp::Impl {
   DCol h_all, knull_all;
   BufPtr keys_all;  // [K][n_build]
   // table
-  BufPtr slot_rep, slot_count, slot_start, rows;
+  BufPtr slot_rep, slot_count, slot_start, rows, bloom;
   uint32_t capacity = 0;
   BufPtr visited_left;  // bitmap over build rows (Left/Full)
   std::unique_ptr<EvalProgram> left_prog, right_prog, filter_prog;
@@ -155,6 +155,10 @@ void JoinOp::seal() {
   v.n_keys = K;
   v.match_keys = mk ? 1 : 0;
   v.build_keep = im.build_pred.empty() ? nullptr : (const uint32_t*)im.keep_all.data;
+  const uint32_t bloom_words = join_bloom_words(n);
+  im.bloom = dev_alloc_zero(ctx_, (size_t)bloom_words * 8);
+  v.bloom = (uint64_t*)im.bloom->p;
+  v.bloom_mask = bloom_words - 1;
   if (n > 0) {
     BufPtr row_slot = dev_alloc(ctx_, (size_t)n * 4);
     BufPtr misc = dev_alloc_zero(ctx_, 16);  // [0] max count, [8] total
