@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define SQLRS_ABI_VERSION 1
+#define SQLRS_ABI_VERSION 2
 
 /* ---- status codes: ExecutorError, src/executor/mod.rs:67-85 ------------------- */
 #define SQLRS_OK 0
@@ -222,6 +222,47 @@ int SQLRS_API(hash_join_finish)(sqlrs_hash_join* j, struct ArrowArray* out,
                                 struct ArrowSchema* out_schema, int32_t* has_batch);
 void SQLRS_API(hash_join_destroy)(sqlrs_hash_join* j);
 
+/* ==== the operators that FOLLOW the hot path in a v1 plan; the planner
+ *      stacks them Agg -> Order -> Project -> Limit (src/planner/select.rs:34-45) ================= */
+
+/* ---- ProjectExecutor{exprs, child}, src/executor/project.rs:6-29 ------------------
+ * one output batch per input batch, columns = eval_column of each expression.  Output fields as
+ * eval_field (evaluator.rs:30-64): names[k] == NULL (only for a bare InputRef) keeps the input field,
+ * name and nullability; otherwise the field is (names[k], result type, nullable) — the host computes
+ * the name (binary-op / cast / alias naming rules). */
+typedef struct sqlrs_project sqlrs_project;
+int SQLRS_API(project_create)(const sqlrs_expr* exprs, const char* const* names, int32_t n_exprs,
+                              const sqlrs_options* options, sqlrs_project** out);
+int SQLRS_API(project_execute)(sqlrs_project* p, struct ArrowArray* batch,
+                               const struct ArrowSchema* schema, struct ArrowArray* out,
+                               struct ArrowSchema* out_schema);
+void SQLRS_API(project_destroy)(sqlrs_project* p);
+
+/* ---- OrderExecutor{order_by, child}, src/executor/order.rs:8-67 -------------------
+ * push every child batch, then finish -> ONE batch: all rows (concat_batches :28) taken in the order of
+ * lexsort_to_indices over the evaluated sort expressions (:30-45).  asc[k] = BoundOrderBy::asc;
+ * NULLs sort first whatever the direction (SortOptions::default().nulls_first).  Rows equal on every key:
+ * the reference sorts unstably (order undefined); this ABI keeps them in input order.  finish with zero
+ * pushed batches is an error (order.rs:27 unwraps None). */
+typedef struct sqlrs_order sqlrs_order;
+int SQLRS_API(order_create)(const sqlrs_expr* order_by, const int32_t* asc, int32_t n_order_by,
+                            const sqlrs_options* options, sqlrs_order** out);
+int SQLRS_API(order_push)(sqlrs_order* o, struct ArrowArray* batch, const struct ArrowSchema* schema);
+int SQLRS_API(order_finish)(sqlrs_order* o, struct ArrowArray* out, struct ArrowSchema* out_schema);
+void SQLRS_API(order_destroy)(sqlrs_order* o);
+
+/* ---- LimitExecutor{limit, offset, child}, src/executor/limit.rs:6-80 ---------------
+ * limit / offset = the bound constants, -1 = None.  Push the child's batches in order: *has_batch = 1
+ * when the call yields an output batch (the input itself or a slice of it), *done = 1 once the reference
+ * would stop pulling from its child (limit.rs:31-33 limit 0, :76-78 break).  Reproduces the reference's
+ * per-batch arithmetic, including `limit: None` meaning "the current batch's row count" (:40). */
+typedef struct sqlrs_limit sqlrs_limit;
+int SQLRS_API(limit_create)(int64_t limit, int64_t offset, const sqlrs_options* options, sqlrs_limit** out);
+int SQLRS_API(limit_push)(sqlrs_limit* l, struct ArrowArray* batch, const struct ArrowSchema* schema,
+                          struct ArrowArray* out, struct ArrowSchema* out_schema, int32_t* has_batch,
+                          int32_t* done);
+void SQLRS_API(limit_destroy)(sqlrs_limit* l);
+
 /* ---- whole physical sub-plan: what ExecutorBuilder::build(plan) (src/executor/mod.rs:45-47,
  *      visit_* :87-200) wires together.  Handing the GPU the subtree instead of one
  *      operator lets it keep intermediates in HBM and pick a fused pipeline
@@ -233,6 +274,9 @@ void SQLRS_API(hash_join_destroy)(sqlrs_hash_join* j);
 #define SQLRS_NODE_SIMPLE_AGG 3 /* PhysicalSimpleAgg  mod.rs:151-161 */
 #define SQLRS_NODE_HASH_AGG 4   /* PhysicalHashAgg    mod.rs:163-174 */
 #define SQLRS_NODE_HASH_JOIN 5  /* PhysicalHashJoin   mod.rs:103-114 (child0 = left = build) */
+#define SQLRS_NODE_PROJECT 6    /* PhysicalProject    mod.rs:127-137 */
+#define SQLRS_NODE_ORDER 7      /* PhysicalOrder      mod.rs:189-199 */
+#define SQLRS_NODE_LIMIT 8      /* PhysicalLimit      mod.rs:176-187 */
 
 typedef struct sqlrs_plan_node {
   int32_t kind;   /* SQLRS_NODE_* */
@@ -250,6 +294,14 @@ typedef struct sqlrs_plan_node {
   const sqlrs_expr* left_keys;
   const sqlrs_expr* right_keys;
   const struct ArrowSchema* join_output_schema;
+  /* ABI version 2 */
+  const sqlrs_expr* exprs;        /* PROJECT: select list; ORDER: sort expressions */
+  const char* const* expr_names;  /* PROJECT: output field names (host-computed eval_field names) */
+  const int32_t* order_asc;       /* ORDER: BoundOrderBy::asc per sort expression */
+  int32_t n_exprs;
+  int32_t reserved;
+  int64_t limit;  /* LIMIT: -1 = None */
+  int64_t offset; /* LIMIT: -1 = None */
 } sqlrs_plan_node;
 
 typedef struct sqlrs_plan sqlrs_plan;

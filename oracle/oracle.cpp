@@ -20,6 +20,7 @@
 #include "../include/sqlrs_tpch_spec.h"
 #include "arrow_io.hpp"
 #include "ops.hpp"
+#include "tail_ops.hpp"
 
 using namespace oracle;
 
@@ -82,6 +83,25 @@ struct sqlrs_hash_agg {
 struct sqlrs_hash_join {
   HashJoin impl;
 };
+struct sqlrs_project {
+  Project impl;
+};
+struct sqlrs_order {
+  Order impl;
+};
+struct sqlrs_limit {
+  Limit impl;
+};
+static std::vector<uint8_t> null_names(const char* const* names, int32_t n) {
+  std::vector<uint8_t> out;
+  for (int32_t k = 0; k < n; k++) out.push_back(!(names && names[k]));
+  return out;
+}
+static std::vector<uint8_t> copy_asc(const int32_t* asc, int32_t n) {
+  std::vector<uint8_t> out;
+  for (int32_t k = 0; k < n; k++) out.push_back(asc ? (asc[k] != 0) : 1);
+  return out;
+}
 
 static HashJoin make_join(int32_t join_type, const sqlrs_expr* lk, const sqlrs_expr* rk, int32_t n_keys,
                           const sqlrs_expr* filter, const ArrowSchema* out_schema, const sqlrs_options* options) {
@@ -105,6 +125,9 @@ struct PlanNode {
   std::vector<Expr> group_by, left_keys, right_keys;
   std::vector<std::string> group_names;
   std::vector<Field> join_fields;
+  std::vector<Expr> exprs;
+  std::vector<std::string> expr_names;
+  std::vector<uint8_t> asc, keep_field;
 };
 struct sqlrs_plan {
   std::vector<PlanNode> nodes;
@@ -152,6 +175,30 @@ struct sqlrs_plan {
         }
         Batch tail;
         if (j.finish(&tail)) out.push_back(tail);
+        return out;
+      }
+      case SQLRS_NODE_PROJECT: {
+        Project p{n.exprs, n.expr_names, n.keep_field};
+        std::vector<Batch> out;
+        for (const Batch& b : run(n.raw.child0)) out.push_back(p.execute(b));
+        return out;
+      }
+      case SQLRS_NODE_ORDER: {
+        Order o{n.exprs, n.asc, {}};
+        for (const Batch& b : run(n.raw.child0)) o.push(b);
+        return {o.finish()};
+      }
+      case SQLRS_NODE_LIMIT: {
+        Limit l;
+        l.limit = n.raw.limit;
+        l.offset = n.raw.offset;
+        std::vector<Batch> out;
+        if (l.limit == 0) return out;  // limit.rs:31-33: the child is never polled
+        for (const Batch& b : run(n.raw.child0)) {
+          Batch r;
+          if (l.push(b, &r)) out.push_back(r);
+          if (l.done) break;
+        }
         return out;
       }
     }
@@ -268,6 +315,55 @@ int sqlrs_oracle_hash_join_finish(sqlrs_hash_join* j, ArrowArray* out, ArrowSche
 }
 void sqlrs_oracle_hash_join_destroy(sqlrs_hash_join* j) { delete j; }
 
+int sqlrs_oracle_project_create(const sqlrs_expr* exprs, const char* const* names, int32_t n_exprs, const sqlrs_options*,
+                                sqlrs_project** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_project{Project{copy_exprs(exprs, n_exprs), copy_names(names, n_exprs), null_names(names, n_exprs)}};
+  });
+}
+int sqlrs_oracle_project_execute(sqlrs_project* p, ArrowArray* batch, const ArrowSchema* schema, ArrowArray* out,
+                                 ArrowSchema* out_schema) {
+  return guarded([&] { export_batch(p->impl.execute(consume_batch(batch, schema)), out, out_schema); });
+}
+void sqlrs_oracle_project_destroy(sqlrs_project* p) { delete p; }
+
+int sqlrs_oracle_order_create(const sqlrs_expr* order_by, const int32_t* asc, int32_t n, const sqlrs_options*, sqlrs_order** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_order{Order{copy_exprs(order_by, n), copy_asc(asc, n), {}}};
+  });
+}
+int sqlrs_oracle_order_push(sqlrs_order* o, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] { o->impl.push(consume_batch(batch, schema)); });
+}
+int sqlrs_oracle_order_finish(sqlrs_order* o, ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] { export_batch(o->impl.finish(), out, out_schema); });
+}
+void sqlrs_oracle_order_destroy(sqlrs_order* o) { delete o; }
+
+int sqlrs_oracle_limit_create(int64_t limit, int64_t offset, const sqlrs_options*, sqlrs_limit** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    auto* l = new sqlrs_limit();
+    l->impl.limit = limit < 0 ? -1 : limit;
+    l->impl.offset = offset < 0 ? -1 : offset;
+    *out = l;
+  });
+}
+int sqlrs_oracle_limit_push(sqlrs_limit* l, ArrowArray* batch, const ArrowSchema* schema, ArrowArray* out, ArrowSchema* out_schema,
+                            int32_t* has_batch, int32_t* done) {
+  return guarded([&] {
+    Batch b = consume_batch(batch, schema);
+    Batch r;
+    const bool has = l->impl.push(b, &r);
+    if (has_batch) *has_batch = has;
+    if (done) *done = l->impl.done;
+    if (has) export_batch(r, out, out_schema);
+  });
+}
+void sqlrs_oracle_limit_destroy(sqlrs_limit* l) { delete l; }
+
 int sqlrs_oracle_plan_create(const sqlrs_plan_node* nodes, int32_t n_nodes, int32_t root, const sqlrs_options* options,
                              sqlrs_plan** out) {
   return guarded([&] {
@@ -287,6 +383,12 @@ int sqlrs_oracle_plan_create(const sqlrs_plan_node* nodes, int32_t n_nodes, int3
         n.left_keys = copy_exprs(nodes[k].left_keys, nodes[k].n_keys);
         n.right_keys = copy_exprs(nodes[k].right_keys, nodes[k].n_keys);
         n.join_fields = import_fields(nodes[k].join_output_schema);
+      }
+      if (nodes[k].kind == SQLRS_NODE_PROJECT || nodes[k].kind == SQLRS_NODE_ORDER) {
+        n.exprs = copy_exprs(nodes[k].exprs, nodes[k].n_exprs);
+        n.expr_names = copy_names(nodes[k].expr_names, nodes[k].n_exprs);
+        n.asc = copy_asc(nodes[k].order_asc, nodes[k].n_exprs);
+        n.keep_field = null_names(nodes[k].expr_names, nodes[k].n_exprs);
       }
       p->nodes.push_back(std::move(n));
     }

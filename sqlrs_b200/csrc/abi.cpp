@@ -6,6 +6,7 @@
 #include "kernels_aot.hpp"
 #include "ops.hpp"
 #include "plan.hpp"
+#include "tail.hpp"
 
 using namespace sq;
 
@@ -34,6 +35,11 @@ static std::vector<ExprCopy> copy_exprs(const sqlrs_expr* e, int32_t n) {
   for (int32_t k = 0; k < n; k++) out.push_back(copy_expr(&e[k]));
   return out;
 }
+static std::vector<bool> null_names(const char* const* names, int32_t n) {
+  std::vector<bool> out;
+  for (int32_t k = 0; k < n; k++) out.push_back(!(names && names[k]));
+  return out;
+}
 static std::vector<std::string> copy_names(const char* const* names, int32_t n) {
   std::vector<std::string> out;
   for (int32_t k = 0; k < n; k++) out.push_back(names && names[k] ? names[k] : "");
@@ -58,6 +64,19 @@ struct sqlrs_hash_join {
   sqlrs_hash_join(int type, std::vector<ExprCopy> lk, std::vector<ExprCopy> rk, ExprCopy filter, std::vector<Field> fields,
                   const Options& o)
       : op(type, std::move(lk), std::move(rk), std::move(filter), std::move(fields), o) {}
+};
+struct sqlrs_project {
+  ProjectOp op;
+  sqlrs_project(std::vector<ExprCopy> e, std::vector<std::string> names, std::vector<bool> keep, const Options& o)
+      : op(std::move(e), std::move(names), std::move(keep), o) {}
+};
+struct sqlrs_order {
+  OrderOp op;
+  sqlrs_order(std::vector<ExprCopy> e, std::vector<bool> asc, const Options& o) : op(std::move(e), std::move(asc), o) {}
+};
+struct sqlrs_limit {
+  LimitOp op;
+  sqlrs_limit(int64_t limit, int64_t offset, const Options& o) : op(limit, offset, o) {}
 };
 struct sqlrs_plan {
   Plan impl;
@@ -216,6 +235,71 @@ int sqlrs_hash_join_finish(sqlrs_hash_join* j, ArrowArray* out, ArrowSchema* out
   });
 }
 void sqlrs_hash_join_destroy(sqlrs_hash_join* j) { delete j; }
+
+int sqlrs_project_create(const sqlrs_expr* exprs, const char* const* names, int32_t n_exprs, const sqlrs_options* options,
+                         sqlrs_project** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_project(copy_exprs(exprs, n_exprs), copy_names(names, n_exprs), null_names(names, n_exprs), copy_options(options));
+  });
+}
+int sqlrs_project_execute(sqlrs_project* p, ArrowArray* batch, const ArrowSchema* schema, ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    p->op.ctx().activate();
+    DBatch b = import_batch_host(p->op.ctx(), batch, schema);
+    DBatch r = p->op.execute(b);
+    export_batch_host(p->op.ctx(), r, out, out_schema);
+  });
+}
+void sqlrs_project_destroy(sqlrs_project* p) { delete p; }
+
+int sqlrs_order_create(const sqlrs_expr* order_by, const int32_t* asc, int32_t n, const sqlrs_options* options, sqlrs_order** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    std::vector<bool> dirs;
+    for (int32_t k = 0; k < n; k++) dirs.push_back(asc ? asc[k] != 0 : true);
+    *out = new sqlrs_order(copy_exprs(order_by, n), dirs, copy_options(options));
+  });
+}
+int sqlrs_order_push(sqlrs_order* o, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!o) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    o->op.ctx().activate();
+    o->op.push(import_batch_host(o->op.ctx(), batch, schema));
+  });
+}
+int sqlrs_order_finish(sqlrs_order* o, ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] {
+    if (!o) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    o->op.ctx().activate();
+    DBatch r = o->op.finish();
+    export_batch_host(o->op.ctx(), r, out, out_schema);
+  });
+}
+void sqlrs_order_destroy(sqlrs_order* o) { delete o; }
+
+int sqlrs_limit_create(int64_t limit, int64_t offset, const sqlrs_options* options, sqlrs_limit** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_limit(limit, offset, copy_options(options));
+  });
+}
+int sqlrs_limit_push(sqlrs_limit* l, ArrowArray* batch, const ArrowSchema* schema, ArrowArray* out, ArrowSchema* out_schema,
+                     int32_t* has_batch, int32_t* done) {
+  return guarded([&] {
+    if (!l) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    l->op.ctx().activate();
+    DBatch b = import_batch_host(l->op.ctx(), batch, schema);
+    DBatch r;
+    const bool has = l->op.push(b, &r);
+    if (has_batch) *has_batch = has;
+    if (done) *done = l->op.done();
+    if (has) export_batch_host(l->op.ctx(), r, out, out_schema);
+    else l->op.ctx().sync();
+  });
+}
+void sqlrs_limit_destroy(sqlrs_limit* l) { delete l; }
 
 int sqlrs_plan_create(const sqlrs_plan_node* nodes, int32_t n_nodes, int32_t root, const sqlrs_options* options, sqlrs_plan** out) {
   return guarded([&] {

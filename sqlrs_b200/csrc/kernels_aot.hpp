@@ -114,3 +114,30 @@ void launch_mark_bits_u32(const uint32_t* idx, int64_t m, uint32_t* bitmap, cuda
 void launch_bitmap_not(const uint32_t* src, int64_t n, uint32_t* dst, cudaStream_t stream, const uint32_t* and_mask = nullptr);
 
 }  // namespace sq
+
+// =================================================================== order / limit / finalisation (kernels_sort.cu)
+namespace sq {
+
+void launch_iota_u32(uint32_t* dst, int64_t n, uint32_t first, cudaStream_t stream);
+// One STABLE pass of an LSD lexicographic sort: re-orders perm (u32[n] row ids) by one sort column — order-preserving
+// 64-bit image of the value (complemented when descending), NULLs first.  Call for the LAST sort expression first.
+// reverse_nulls: the run of NULL rows comes out in reverse row order (arrow's single-column descending sort).
+void sort_pass(int dtype, const void* data, const uint32_t* valid, int64_t n, bool descending, bool reverse_nulls, uint32_t* perm,
+               cudaStream_t stream);
+
+// One output column of an aggregate's result, read from the packed group rows
+// [hash, min_row, knull, key bits x K, accumulator words x W] (launch_table_pack / table_pack_sorted).
+struct FinalizeCol {
+  void* data;           // device: int64/float64 8 B, int32 4 B per row, Boolean bit-packed
+  uint32_t* valid;      // device validity bitmap or nullptr
+  int dtype;
+  int word;             // value word within the packed row
+  int null_bit;         // >= 0: group key k, NULL when bit k of the row's null mask is set
+  int nvalid_word;      // >= 0: NULL when that word (number of non-NULL inputs) is 0
+  int f64_sortable;     // value is the total-order integer image of a double (MIN/MAX over Float64)
+  int count_epoch;      // COUNT under the overwrite quirk K1: (batch epoch << 40) | count
+  uint64_t simple_epoch;  // SimpleAgg + K1: only the last batch counts (0 = not applicable)
+};
+void launch_finalize_groups(const uint64_t* packed, int words, int64_t n, int n_cols, const FinalizeCol* cols_dev, cudaStream_t stream);
+
+}  // namespace sq

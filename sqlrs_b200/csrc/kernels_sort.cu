@@ -1,0 +1,177 @@
+// sqlrs_b200 — kernels of the operators that follow the hot path (Order + Limit on the device)
+// and the device-side finalisation of a group table into Arrow columns.
+//   OrderExecutor   reference src/executor/order.rs:26-66 (concat -> lexsort_to_indices -> take)
+//   LimitExecutor   reference src/executor/limit.rs:36-79 (batch.slice)
+//   HashAgg output  reference src/executor/aggregate/hash_agg.rs:126-148 (builders -> one batch)
+// The sort is an LSD sequence of STABLE radix sorts (CUB DeviceRadixSort::SortPairs) over order-preserving 64-bit
+// images of the sort columns, least significant sort expression first; NULLs-first is one more stable 1-bit pass.
+// All of it is small next to the scans (the input is an aggregate's output); HBM-bound on 8 B keys + 4 B row ids.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels_aot.hpp"
+
+namespace sq {
+namespace {
+
+constexpr int kBlock = 256;
+inline unsigned grid_for(int64_t items, int64_t cap = 148 * 8) {
+  int64_t g = div_up(items, kBlock);
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (unsigned)g;
+}
+
+__device__ __forceinline__ bool bit_at(const uint32_t* bm, uint64_t i) { return (bm[i >> 5] >> (i & 31)) & 1u; }
+
+// order-preserving u64 image of a cell: unsigned comparison of the images == the reference's comparison of the
+// values (arrow sort: integers by Ord, Boolean false < true, Float64 by f64::total_cmp)
+__device__ __forceinline__ uint64_t sort_image(int dtype, const void* data, uint64_t r) {
+  switch (dtype) {
+    case SQLRS_DT_INT64: return ((const uint64_t*)data)[r] ^ 0x8000000000000000ULL;
+    case SQLRS_DT_INT32: return (uint64_t)(int64_t)((const int32_t*)data)[r] ^ 0x8000000000000000ULL;
+    case SQLRS_DT_BOOL: return bit_at((const uint32_t*)data, r) ? 1ULL : 0ULL;
+    case SQLRS_DT_FLOAT64: {
+      const uint64_t b = ((const uint64_t*)data)[r];
+      return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+    }
+  }
+  return 0ULL;
+}
+
+// keys[i] = image of column cell at row perm[i]; descending = complemented image.  NULL cells: 0, or — for the
+// reference's single-column descending sort, which reverses the run of NULL rows (arrow sort_to_indices) —
+// n-1-row so that the later stable NULL-flag pass leaves them in reverse input order.
+__global__ void __launch_bounds__(kBlock) k_sort_keys(int dtype, const void* __restrict__ data, const uint32_t* __restrict__ valid,
+                                                      const uint32_t* __restrict__ perm, int64_t n, int descending, int reverse_nulls,
+                                                      uint64_t* __restrict__ keys) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t r = perm[i];
+    uint64_t k;
+    if (dtype == SQLRS_DT_NULL || (valid && !bit_at(valid, r))) {
+      k = reverse_nulls ? (uint64_t)(n - 1) - r : 0ULL;
+    } else {
+      k = sort_image(dtype, data, r);
+      if (descending) k = ~k;
+    }
+    keys[i] = k;
+  }
+}
+
+// flags[i] = 1 for a valid cell at row perm[i], 0 for NULL (NULLs first)
+__global__ void __launch_bounds__(kBlock) k_valid_flags(const uint32_t* __restrict__ valid, const uint32_t* __restrict__ perm, int64_t n,
+                                                        uint32_t* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) flags[i] = bit_at(valid, perm[i]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(kBlock) k_iota_u32(uint32_t* __restrict__ dst, int64_t n, uint32_t first) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = first + (uint32_t)i;
+}
+
+// packed, ordered group rows -> typed Arrow columns (+ validity words by warp ballot)
+__global__ void __launch_bounds__(kBlock) k_finalize_groups(const uint64_t* __restrict__ packed, int words, int64_t n, int n_cols,
+                                                            const FinalizeCol* __restrict__ cols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_up = (n + 31) & ~(int64_t)31;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_up; i += stride) {
+    const bool inb = i < n;
+    const uint64_t* row = packed + (size_t)(1 + (inb ? i : 0)) * words;
+    for (int c = 0; c < n_cols; c++) {
+      const FinalizeCol d = cols[c];
+      uint64_t w = row[d.word];
+      bool valid = true;
+      if (d.null_bit >= 0) valid = !((row[2] >> d.null_bit) & 1ULL);   // group key: bit of the tuple's null mask
+      if (d.nvalid_word >= 0) valid = row[d.nvalid_word] != 0ULL;      // SUM/MIN/MAX over no non-NULL input is NULL
+      if (d.count_epoch) {                                             // quirk K1 word: (batch epoch << 40) | count
+        const uint64_t epoch = w >> 40;
+        w &= (1ULL << 40) - 1;
+        if (d.simple_epoch && epoch != d.simple_epoch) w = 0;
+      }
+      if (d.f64_sortable) {  // MIN/MAX(Float64) accumulate in the total-order integer image
+        const int64_t s = (int64_t)w;
+        w = (uint64_t)(s ^ ((s >> 63) & 0x7fffffffffffffffLL));
+      }
+      if (!valid) w = 0;
+      if (inb) {
+        if (d.dtype == SQLRS_DT_INT32) ((uint32_t*)d.data)[i] = (uint32_t)w;
+        else if (d.dtype != SQLRS_DT_BOOL) ((uint64_t*)d.data)[i] = w;
+      }
+      if (d.dtype == SQLRS_DT_BOOL) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, inb && valid && (w & 1ULL));
+        if (lane == 0) ((uint32_t*)d.data)[i >> 5] = bits;
+      }
+      if (d.valid) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, inb && valid);
+        if (lane == 0) d.valid[i >> 5] = bits;
+      }
+    }
+  }
+}
+
+template <typename K>
+void stable_sort_pairs(K* k_in, K* k_out, uint32_t* v_in, uint32_t* v_out, int64_t n, int end_bit, cudaStream_t stream) {
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, stream);
+  void* tmp = nullptr;
+  SQ_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, stream));
+  SQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, stream));
+  count_launch(end_bit > 8 ? 10 : 3);
+  cudaFreeAsync(tmp, stream);
+}
+
+}  // namespace
+
+void launch_iota_u32(uint32_t* dst, int64_t n, uint32_t first, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_iota_u32<<<grid_for(n), kBlock, 0, stream>>>(dst, n, first);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+// perm (u32[n], initialised by the caller to the identity or to a previous pass's result) is re-ordered by ONE sort
+// column, stably: ties keep their current relative order.  Call for the LAST sort expression first.
+void sort_pass(int dtype, const void* data, const uint32_t* valid, int64_t n, bool descending, bool reverse_nulls, uint32_t* perm,
+               cudaStream_t stream) {
+  if (n <= 1) return;
+  if (n >= (1LL << 31)) fail(SQLRS_ERR_UNSUPPORTED, "Order: more than 2^31 rows in one sort");
+  uint64_t *k_in = nullptr, *k_out = nullptr;
+  uint32_t *p_out = nullptr;
+  SQ_CUDA(cudaMallocAsync(&k_in, (size_t)n * 8, stream));
+  SQ_CUDA(cudaMallocAsync(&k_out, (size_t)n * 8, stream));
+  SQ_CUDA(cudaMallocAsync(&p_out, (size_t)n * 4, stream));
+  k_sort_keys<<<grid_for(n), kBlock, 0, stream>>>(dtype, data, valid, perm, n, descending ? 1 : 0, reverse_nulls ? 1 : 0, k_in);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+  stable_sort_pairs<uint64_t>(k_in, k_out, perm, p_out, n, 64, stream);
+  if (valid || dtype == SQLRS_DT_NULL) {
+    // NULLs first, whatever the direction (SortOptions::default().nulls_first); an all-NULL column only needs the
+    // value pass above (every key equal, or the reversed row ids)
+    if (valid) {
+      uint32_t* f_in = (uint32_t*)k_in;  // reuse: n * 4 <= n * 8
+      uint32_t* f_out = (uint32_t*)k_out;
+      k_valid_flags<<<grid_for(n), kBlock, 0, stream>>>(valid, p_out, n, f_in);
+      count_launch();
+      SQ_CUDA(cudaGetLastError());
+      stable_sort_pairs<uint32_t>(f_in, f_out, p_out, perm, n, 1, stream);
+    } else {
+      SQ_CUDA(cudaMemcpyAsync(perm, p_out, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+  } else {
+    SQ_CUDA(cudaMemcpyAsync(perm, p_out, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  cudaFreeAsync(k_in, stream);
+  cudaFreeAsync(k_out, stream);
+  cudaFreeAsync(p_out, stream);
+}
+
+void launch_finalize_groups(const uint64_t* packed, int words, int64_t n, int n_cols, const FinalizeCol* cols_dev, cudaStream_t stream) {
+  if (n <= 0 || n_cols <= 0) return;
+  k_finalize_groups<<<grid_for(n), kBlock, 0, stream>>>(packed, words, n, n_cols, cols_dev);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
+}  // namespace sq

@@ -42,6 +42,19 @@ Plan::Plan(const sqlrs_plan_node* nodes, int32_t n_nodes, int32_t root, const Op
       }
       n.join_fields = import_fields(s.join_output_schema);
     }
+    if (s.kind == SQLRS_NODE_PROJECT || s.kind == SQLRS_NODE_ORDER) {
+      if (s.n_exprs < 1 || !s.exprs) fail(SQLRS_ERR_INVALID_ARG, "plan: Project / Order need at least one expression");
+      for (int32_t q = 0; q < s.n_exprs; q++) {
+        n.exprs.push_back(copy_expr(&s.exprs[q]));
+        n.expr_names.push_back(s.expr_names && s.expr_names[q] ? s.expr_names[q] : "");
+        n.asc.push_back(s.order_asc ? s.order_asc[q] != 0 : true);
+        n.keep_field.push_back(!(s.expr_names && s.expr_names[q]));
+      }
+    }
+    if (s.kind == SQLRS_NODE_LIMIT) {
+      n.limit = s.limit < 0 ? -1 : s.limit;
+      n.offset = s.offset < 0 ? -1 : s.offset;
+    }
     auto check_child = [&](int c) {
       if (c < 0 || c >= n_nodes) fail(SQLRS_ERR_INVALID_ARG, "plan: child index out of range");
     };
@@ -49,7 +62,10 @@ Plan::Plan(const sqlrs_plan_node* nodes, int32_t n_nodes, int32_t root, const Op
       case SQLRS_NODE_SCAN: break;
       case SQLRS_NODE_FILTER:
       case SQLRS_NODE_SIMPLE_AGG:
-      case SQLRS_NODE_HASH_AGG: check_child(s.child0); break;
+      case SQLRS_NODE_HASH_AGG:
+      case SQLRS_NODE_PROJECT:
+      case SQLRS_NODE_ORDER:
+      case SQLRS_NODE_LIMIT: check_child(s.child0); break;
       case SQLRS_NODE_HASH_JOIN:
         check_child(s.child0);
         check_child(s.child1);
@@ -74,9 +90,9 @@ void Plan::reset() {
   partial_active_ = false;
 }
 
-// aggregate at `idx` -> host Arrow.  A Filter directly below is fused into the aggregate's row
+// aggregate at `idx`, up to (excluding) finalisation.  A Filter directly below is fused into the aggregate's row
 // program unless SQLRS_FLAG_NO_FUSION asks for operator-at-a-time execution.
-void Plan::run_agg_to_host(int idx, Result* res) {
+AggOp& Plan::run_agg(int idx) {
   Node& n = nodes_[idx];
   const bool simple = n.kind == SQLRS_NODE_SIMPLE_AGG;
   int child = n.child0;
@@ -89,17 +105,21 @@ void Plan::run_agg_to_host(int idx, Result* res) {
     description_ += std::string(simple ? "[SimpleAgg] " : "[HashAgg] ");
   }
   // the operator (compiled kernels, group table, scratch) is kept across execute() calls
-  if (!agg_op_) agg_op_ = std::make_unique<AggOp>(n.aggs, n.group_by, n.group_names, simple, fused, opt_);
-  else agg_op_->reset();
-  AggOp& op = *agg_op_;
+  if (!n.agg_op) n.agg_op = std::make_unique<AggOp>(n.aggs, n.group_by, n.group_names, simple, fused, opt_);
+  else n.agg_op->reset();
+  AggOp& op = *n.agg_op;
   const Needed need = fusion() ? agg_child_needs(n, fused, width_of(child)) : Needed();
   if (!feed_fused_join(op, child, fused, need))
     for (const DBatch& b : run(child, need)) op.push(b);
-  op.finish_host(&res->arr, &res->sch);
-  res->on_host = true;
   description_ += op.describe() + "; ";
   scan_kernel_ms_ = op.scan_kernel_ms();
   scan_kernel_launches_ = op.scan_kernel_launches();
+  return op;
+}
+
+void Plan::run_agg_to_host(int idx, Result* res) {
+  run_agg(idx).finish_host(&res->arr, &res->sch);
+  res->on_host = true;
 }
 
 // An INNER HashJoin directly below the aggregate (no Filter in between, SQL key comparison): build the join's left
@@ -204,7 +224,10 @@ int Plan::width_of(int idx) {
       auto it = tables_.find(n.table_slot);
       return it == tables_.end() || it->second.empty() ? 0 : (int)it->second[0].cols.size();
     }
-    case SQLRS_NODE_FILTER: return width_of(n.child0);
+    case SQLRS_NODE_FILTER:
+    case SQLRS_NODE_ORDER:
+    case SQLRS_NODE_LIMIT: return width_of(n.child0);
+    case SQLRS_NODE_PROJECT: return (int)n.exprs.size();
     case SQLRS_NODE_HASH_JOIN: return (int)n.join_fields.size();
     default: return (int)(n.group_by.size() + n.aggs.size());
   }
@@ -250,8 +273,59 @@ std::vector<DBatch> Plan::run(int idx, const Needed& needed) {
       return out;
     }
     case SQLRS_NODE_SIMPLE_AGG:
-    case SQLRS_NODE_HASH_AGG:
-      fail(SQLRS_ERR_UNSUPPORTED, "an aggregate below another operator is not supported by the CUDA plan executor yet");
+    case SQLRS_NODE_HASH_AGG: {
+      // an aggregate below another operator: its result stays in HBM (finalised by one kernel)
+      DBatch r = run_agg(idx).finish_device();
+      description_ += "[aggregate finalised on the device] ";
+      return {r};
+    }
+    case SQLRS_NODE_PROJECT: {
+      if (!n.project_op) n.project_op = std::make_unique<ProjectOp>(n.exprs, n.expr_names, n.keep_field, opt_);
+      Needed child_need;
+      if (fusion()) {
+        const int w = width_of(n.child0);
+        if (w > 0) {
+          child_need.assign((size_t)w, false);
+          for (size_t k = 0; k < n.exprs.size(); k++)
+            if (is_needed(k)) mark_refs(n.exprs[k], child_need);
+        }
+      }
+      description_ += "[Project: sq_eval_kernel] ";
+      std::vector<DBatch> out;
+      for (const DBatch& b : run(n.child0, child_need)) out.push_back(n.project_op->execute(ctx_, b));
+      return out;
+    }
+    case SQLRS_NODE_ORDER: {
+      if (!n.order_op) n.order_op = std::make_unique<OrderOp>(n.exprs, n.asc, opt_);
+      else n.order_op->reset();
+      Needed child_need = needed;
+      if (!child_need.empty())
+        for (const ExprCopy& e : n.exprs) mark_refs(e, child_need);
+      n.order_op->set_row_limit(fusion() ? n.row_limit_hint : -1);
+      description_ += n.row_limit_hint >= 0 && fusion() ? "[Order + Limit: stable LSD radix sort of row ids, top-" + std::to_string(n.row_limit_hint) + " rows gathered] "
+                                                        : "[Order: stable LSD radix sort of row ids + gather] ";
+      for (const DBatch& b : run(n.child0, child_need)) n.order_op->push(b);
+      return {n.order_op->finish(ctx_)};
+    }
+    case SQLRS_NODE_LIMIT: {
+      std::vector<DBatch> out;
+      LimitOp l(n.limit, n.offset, opt_);
+      if (l.done()) return out;  // limit 0: the child is never polled (limit.rs:31-33)
+      // top-k: an Order below (possibly under Projects, which are row-wise) yields ONE batch, of which only the
+      // first offset + limit rows can reach the output
+      int below = n.child0;
+      while (nodes_[below].kind == SQLRS_NODE_PROJECT) below = nodes_[below].child0;
+      if (nodes_[below].kind == SQLRS_NODE_ORDER) nodes_[below].row_limit_hint = l.rows_needed();
+      std::vector<DBatch> in = run(n.child0, needed);
+      if (nodes_[below].kind == SQLRS_NODE_ORDER) nodes_[below].row_limit_hint = -1;
+      description_ += "[Limit] ";
+      for (const DBatch& b : in) {
+        DBatch r;
+        if (l.push(ctx_, b, &r)) out.push_back(r);
+        if (l.done()) break;
+      }
+      return out;
+    }
     case SQLRS_NODE_HASH_JOIN: {
       JoinOp j(n.join_type, n.left_keys, n.right_keys, n.predicate, n.join_fields, opt_);
       int left = n.child0, right = n.child1;

@@ -8,6 +8,7 @@
 
 #include "join.hpp"
 #include "ops.hpp"
+#include "tail.hpp"
 
 namespace sq {
 
@@ -42,6 +43,15 @@ class Plan {
     std::vector<Field> join_fields;
     // operators kept across execute() calls so that repeated runs reuse compiled kernels
     std::unique_ptr<EvalProgram> filter_prog;
+    std::unique_ptr<AggOp> agg_op;
+    std::unique_ptr<ProjectOp> project_op;
+    std::unique_ptr<OrderOp> order_op;
+    // PROJECT: select list + field names; ORDER: sort expressions + directions; LIMIT: the bound constants (-1 = None)
+    std::vector<ExprCopy> exprs;
+    std::vector<std::string> expr_names;
+    std::vector<bool> asc, keep_field;
+    int64_t limit = -1, offset = -1;
+    int64_t row_limit_hint = -1;  // ORDER: set by a Limit above for the current run (top-k: gather only these rows)
   };
   struct Result {
     bool on_host = false;
@@ -52,6 +62,7 @@ class Plan {
   using Needed = std::vector<bool>;  // per output column of a node: does anything above read it?  empty = all
   std::vector<DBatch> run(int idx, const Needed& needed);
   void run_agg_to_host(int idx, Result* res);
+  AggOp& run_agg(int idx);  // everything of an aggregate node up to (excluding) finalisation
   bool feed_fused_join(AggOp& op, int child, const ExprCopy& agg_fused_pred, const Needed& need);
   int width_of(int idx);              // number of output columns of a node (needs its scans pushed)
   Needed agg_child_needs(const Node& agg, const ExprCopy& fused_pred, int child_width) const;
@@ -63,7 +74,6 @@ class Plan {
   int root_ = 0;
   std::map<int, std::vector<DBatch>> tables_;
   std::deque<Result> results_;
-  std::unique_ptr<AggOp> agg_op_;      // root aggregate of execute(), kept across runs
   std::unique_ptr<AggOp> partial_op_;  // root aggregate of execute_partial(), kept across runs
   bool partial_active_ = false;        // between execute_partial and finish_partial
   std::string description_;

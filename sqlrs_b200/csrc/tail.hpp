@@ -1,0 +1,74 @@
+// sqlrs_b200 — the operators that follow the hot path in a v1 plan, on device batches:
+//   ProjectOp  ProjectExecutor  reference src/executor/project.rs:6-29
+//   OrderOp    OrderExecutor    reference src/executor/order.rs:8-67
+//   LimitOp    LimitExecutor    reference src/executor/limit.rs:6-80
+// The planner stacks them Agg -> Order -> Project -> Limit (src/planner/select.rs:34-45); keeping them on the device
+// means only the final rows (Q3': 10) cross PCIe instead of the whole aggregate output.
+#pragma once
+#include "ops.hpp"
+
+namespace sq {
+
+class ProjectOp {
+ public:
+  // keep_field[k]: names[k] was NULL at the ABI — a bare InputRef keeps the input field (evaluator.rs:31)
+  ProjectOp(std::vector<ExprCopy> exprs, std::vector<std::string> names, std::vector<bool> keep_field, const Options& opt);
+  DBatch execute(const DBatch& in);
+  DBatch execute(Ctx& ctx, const DBatch& in);  // on another operator's / the plan's context
+  Ctx& ctx() { return ctx_; }
+
+ private:
+  Ctx ctx_;
+  std::vector<ExprCopy> exprs_;
+  std::vector<std::string> names_;
+  std::vector<bool> keep_field_;
+  std::unique_ptr<EvalProgram> prog_;  // the non-trivial expressions, one fused kernel
+  std::vector<int> slot_;              // per expression: index into prog_'s outputs, or -1 = bare InputRef (column passed through)
+};
+
+class OrderOp {
+ public:
+  OrderOp(std::vector<ExprCopy> order_by, std::vector<bool> asc, const Options& opt);
+  void push(const DBatch& b) { batches_.push_back(b); }
+  // plan-level fusion with a Limit above (top-k): only the first `rows` sorted rows are gathered; < 0 = all
+  void set_row_limit(int64_t rows) { row_limit_ = rows; }
+  DBatch finish();
+  DBatch finish(Ctx& ctx);
+  void reset() { batches_.clear(); }
+  Ctx& ctx() { return ctx_; }
+
+ private:
+  Ctx ctx_;
+  std::vector<ExprCopy> order_by_;
+  std::vector<bool> asc_;
+  std::vector<DBatch> batches_;
+  std::unique_ptr<EvalProgram> prog_;
+  std::vector<int> slot_;
+  int64_t row_limit_ = -1;
+};
+
+class LimitOp {
+ public:
+  LimitOp(int64_t limit, int64_t offset, const Options& opt);  // -1 = None
+  bool push(const DBatch& in, DBatch* out);                     // true: *out is yielded
+  bool push(Ctx& ctx, const DBatch& in, DBatch* out);
+  bool done() const { return done_; }
+  void reset() {
+    returned_count_ = 0;
+    done_ = limit_ == 0;
+  }
+  // rows of the child's stream that can reach the output when the child yields ONE batch (Order below): offset + limit
+  int64_t rows_needed() const { return limit_ < 0 ? -1 : (offset_ < 0 ? 0 : offset_) + limit_; }
+  Ctx& ctx() { return ctx_; }
+
+ private:
+  Ctx ctx_;
+  int64_t limit_, offset_, returned_count_ = 0;
+  bool done_ = false;
+};
+
+// rows [start, start + len) of a batch as a new batch (RecordBatch::slice materialised)
+DBatch slice_batch(Ctx& ctx, const DBatch& in, int64_t start, int64_t len);
+DBatch concat_batches(Ctx& ctx, const std::vector<DBatch>& batches);
+
+}  // namespace sq

@@ -4,7 +4,9 @@ The reference's boundary is "a struct of plan parameters + child stream(s) with
 `execute() -> BoxStream<Result<RecordBatch, ExecutorError>>`".  The classes below have the
 same names and fields (`FilterExecutor{expr, child}`, `SimpleAggExecutor{agg_funcs, child}`,
 `HashAggExecutor{agg_funcs, group_by, child}`, `HashJoinExecutor{left_child, right_child,
-join_type, join_condition, join_output_schema}`); `child` is any iterable of
+join_type, join_condition, join_output_schema}`, and the operators that follow them in a plan:
+`ProjectExecutor{exprs, child}`, `OrderExecutor{order_by, child}`, `LimitExecutor{limit, offset,
+child}`); `child` is any iterable of
 `pyarrow.RecordBatch`, `execute()` is a generator of `RecordBatch`, errors surface as
 `ExecutorError`.  Every batch crosses the C ABI of include/sqlrs_b200.h through the Arrow C
 Data Interface — this file contains no compute.
@@ -18,7 +20,7 @@ from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
 import pyarrow as pa
 
 from . import ffi
-from .expr import AggArray, BoundExpr, ExprArray, FlatExpr, NameArray, EMPTY_EXPR
+from .expr import AggArray, BoundExpr, ExprArray, FlatExpr, NameArray, EMPTY_EXPR, project_field_names
 
 BoxedExecutor = Iterable[pa.RecordBatch]
 
@@ -186,6 +188,102 @@ class HashJoinExecutor:
                 yield _import(out, out_sch)
         finally:
             lib.hash_join_destroy(h)
+
+
+class ProjectExecutor:
+    """src/executor/project.rs:6-29"""
+
+    def __init__(self, exprs: Sequence[BoundExpr], child: BoxedExecutor, lib=None, options=None):
+        self.exprs, self.child, self.lib = list(exprs), child, _lib(lib)
+        self.options = options if options is not None else self.lib.options()
+
+    def execute(self) -> Iterator[pa.RecordBatch]:
+        lib = self.lib
+        h = None
+        keep = None
+        try:
+            for batch in self.child:
+                if h is None:
+                    exprs = ExprArray(self.exprs)
+                    names = NameArray(project_field_names(self.exprs, batch.schema))
+                    keep = (exprs, names)
+                    h = C.c_void_p()
+                    lib.check(lib.project_create(exprs.ptr, names.ptr, exprs.n, C.byref(self.options), C.byref(h)))
+                arr, sch = ffi.export_batch(batch)
+                out, out_sch = ffi.ArrowArray(), ffi.ArrowSchema()
+                try:
+                    lib.check(lib.project_execute(h, C.byref(arr), C.byref(sch), C.byref(out), C.byref(out_sch)))
+                finally:
+                    ffi.release_schema(sch)
+                yield _import(out, out_sch)
+        finally:
+            if h is not None:
+                lib.project_destroy(h)
+
+
+@dataclass
+class BoundOrderBy:
+    """BoundOrderBy{expr, asc} (src/binder/statement/select.rs)"""
+    expr: BoundExpr
+    asc: bool = True
+
+
+class OrderExecutor:
+    """src/executor/order.rs:8-67"""
+
+    def __init__(self, order_by: Sequence[BoundOrderBy], child: BoxedExecutor, lib=None, options=None):
+        self.order_by, self.child, self.lib = list(order_by), child, _lib(lib)
+        self.options = options if options is not None else self.lib.options()
+
+    def execute(self) -> Iterator[pa.RecordBatch]:
+        lib = self.lib
+        exprs = ExprArray([o.expr for o in self.order_by])
+        asc = (C.c_int32 * max(1, len(self.order_by)))(*[int(o.asc) for o in self.order_by])
+        h = C.c_void_p()
+        lib.check(lib.order_create(exprs.ptr, asc, exprs.n, C.byref(self.options), C.byref(h)))
+        try:
+            for batch in self.child:
+                arr, sch = ffi.export_batch(batch)
+                try:
+                    lib.check(lib.order_push(h, C.byref(arr), C.byref(sch)))
+                finally:
+                    ffi.release_schema(sch)
+            out, out_sch = ffi.ArrowArray(), ffi.ArrowSchema()
+            lib.check(lib.order_finish(h, C.byref(out), C.byref(out_sch)))  # zero batches: order.rs:27 unwraps None
+            yield _import(out, out_sch)
+        finally:
+            lib.order_destroy(h)
+
+
+class LimitExecutor:
+    """src/executor/limit.rs:6-80; `limit` / `offset` are the bound constants or None"""
+
+    def __init__(self, limit: Optional[int], offset: Optional[int], child: BoxedExecutor, lib=None, options=None):
+        self.limit, self.offset, self.child, self.lib = limit, offset, child, _lib(lib)
+        self.options = options if options is not None else self.lib.options()
+
+    def execute(self) -> Iterator[pa.RecordBatch]:
+        lib = self.lib
+        if self.limit is not None and self.limit == 0:  # limit.rs:31-33: returns before polling the child
+            return
+        h = C.c_void_p()
+        lib.check(lib.limit_create(-1 if self.limit is None else self.limit, -1 if self.offset is None else self.offset,
+                                   C.byref(self.options), C.byref(h)))
+        try:
+            has, done = C.c_int32(0), C.c_int32(0)
+            for batch in self.child:
+                arr, sch = ffi.export_batch(batch)
+                out, out_sch = ffi.ArrowArray(), ffi.ArrowSchema()
+                try:
+                    lib.check(lib.limit_push(h, C.byref(arr), C.byref(sch), C.byref(out), C.byref(out_sch), C.byref(has), C.byref(done)))
+                finally:
+                    ffi.release_schema(sch)
+                if has.value:
+                    yield _import(out, out_sch)
+                if done.value:
+                    break
+        finally:
+            lib.limit_destroy(h)
 
 
 def eval_column(expr: BoundExpr, batch: pa.RecordBatch, lib=None, options=None) -> pa.Array:

@@ -225,6 +225,12 @@ class FlatExpr:
 EMPTY_EXPR = FlatExpr([])
 
 
+def project_field_names(exprs: Sequence[BoundExpr], schema: pa.Schema) -> List[Optional[str]]:
+    """ProjectExecutor's output field names at the ABI: None = a bare InputRef keeps the input field
+    (evaluator.rs:31); everything else (Alias included) is a new nullable field named by eval_field."""
+    return [None if isinstance(e, InputRef) else e.eval_field(schema).name for e in exprs]
+
+
 class ExprArray:
     def __init__(self, exprs: Sequence[BoundExpr]):
         self.flat = [e.flatten() for e in exprs]
@@ -256,7 +262,7 @@ class AggArray:
 
 
 class NameArray:
-    def __init__(self, names: Sequence[str]):
-        self._b = [n.encode() for n in names]
+    def __init__(self, names: Sequence[Optional[str]]):
+        self._b = [None if n is None else n.encode() for n in names]
         self._arr = (C.c_char_p * max(1, len(self._b)))(*self._b)
         self.ptr = C.cast(self._arr, C.POINTER(C.c_char_p))

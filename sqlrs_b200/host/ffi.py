@@ -27,7 +27,8 @@ COUNT_REFERENCE_OVERWRITE, COUNT_SQL_ACCUMULATE = 0, 1
 MATCH_HASH_ONLY, MATCH_HASH_AND_KEY = 0, 1
 FLAG_NO_FUSION = 1
 FLAG_TIMING = 4
-NODE_SCAN, NODE_FILTER, NODE_SIMPLE_AGG, NODE_HASH_AGG, NODE_HASH_JOIN = 1, 2, 3, 4, 5
+NODE_SCAN, NODE_FILTER, NODE_SIMPLE_AGG, NODE_HASH_AGG, NODE_HASH_JOIN, NODE_PROJECT, NODE_ORDER, NODE_LIMIT = 1, 2, 3, 4, 5, 6, 7, 8
+ABI_VERSION = 2
 TPCH_CUSTOMER, TPCH_ORDERS, TPCH_LINEITEM = 0, 1, 2
 TPCH_FLAGS_8GROUP, TPCH_FLAGS_SPEC = 0, 1
 
@@ -163,6 +164,13 @@ class PlanNode(C.Structure):
         ("left_keys", C.POINTER(Expr)),
         ("right_keys", C.POINTER(Expr)),
         ("join_output_schema", C.POINTER(ArrowSchema)),
+        ("exprs", C.POINTER(Expr)),
+        ("expr_names", C.POINTER(C.c_char_p)),
+        ("order_asc", C.POINTER(C.c_int32)),
+        ("n_exprs", C.c_int32),
+        ("reserved", C.c_int32),
+        ("limit", C.c_int64),
+        ("offset", C.c_int64),
     ]
 
 
@@ -193,6 +201,16 @@ _SIGNATURES = {
     "hash_join_probe": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema), P(ArrowArray), P(ArrowSchema), P(C.c_int32)]),
     "hash_join_finish": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema), P(C.c_int32)]),
     "hash_join_destroy": (None, [C.c_void_p]),
+    "project_create": (C.c_int, [P(Expr), P(C.c_char_p), C.c_int32, P(Options), P(C.c_void_p)]),
+    "project_execute": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema), P(ArrowArray), P(ArrowSchema)]),
+    "project_destroy": (None, [C.c_void_p]),
+    "order_create": (C.c_int, [P(Expr), P(C.c_int32), C.c_int32, P(Options), P(C.c_void_p)]),
+    "order_push": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema)]),
+    "order_finish": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema)]),
+    "order_destroy": (None, [C.c_void_p]),
+    "limit_create": (C.c_int, [C.c_int64, C.c_int64, P(Options), P(C.c_void_p)]),
+    "limit_push": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema), P(ArrowArray), P(ArrowSchema), P(C.c_int32), P(C.c_int32)]),
+    "limit_destroy": (None, [C.c_void_p]),
     "plan_create": (C.c_int, [P(PlanNode), C.c_int32, C.c_int32, P(Options), P(C.c_void_p)]),
     "plan_push_table": (C.c_int, [C.c_void_p, C.c_int32, P(ArrowArray), P(ArrowSchema)]),
     "plan_push_table_device": (C.c_int, [C.c_void_p, C.c_int32, P(ArrowDeviceArray), P(ArrowSchema)]),
@@ -234,8 +252,8 @@ class Library:
             fn.restype = res
             fn.argtypes = args
             setattr(self, name, fn)
-        if self.abi_version() != 1:
-            raise RuntimeError(f"{path}: ABI version {self.abi_version()} != 1")
+        if self.abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{path}: ABI version {self.abi_version()} != {ABI_VERSION}")
 
     def check(self, status: int):
         if status != OK:

@@ -1,7 +1,8 @@
 """Host-side mirror of the reference's physical plan nodes and ExecutorBuilder.
 
 Reference: `PhysicalTableScan`, `PhysicalFilter`, `PhysicalSimpleAgg`, `PhysicalHashAgg`,
-`PhysicalHashJoin` (src/optimizer/plan_node/physical_*.rs) and
+`PhysicalHashJoin`, `PhysicalOrder`, `PhysicalProject`, `PhysicalLimit`
+(src/optimizer/plan_node/physical_*.rs) and
 `ExecutorBuilder::build(plan) -> BoxedExecutor` (src/executor/mod.rs:36-56, visit_* :87-200).
 Handing the library the whole sub-plan (sqlrs_plan_* of include/sqlrs_b200.h) keeps tables and
 intermediates in HBM and lets it fuse Filter into the aggregate above it.  This file contains no
@@ -16,8 +17,8 @@ from typing import Dict, List, Optional, Sequence
 import pyarrow as pa
 
 from . import ffi
-from .executor import JOIN_TYPES, JoinCondition
-from .expr import AggArray, BoundExpr, ExprArray, NameArray
+from .executor import JOIN_TYPES, BoundOrderBy, JoinCondition
+from .expr import AggArray, BoundExpr, ExprArray, NameArray, project_field_names
 
 
 class PlanNode:
@@ -80,6 +81,38 @@ class PhysicalHashJoin(PlanNode):
         return self.join_output_schema
 
 
+@dataclass
+class PhysicalProject(PlanNode):
+    """PhysicalProject{exprs, input} (physical_project.rs)"""
+    exprs: Sequence[BoundExpr]
+    child: PlanNode
+
+    def output_schema(self, tables):
+        s = self.child.output_schema(tables)
+        return pa.schema([e.eval_field(s) for e in self.exprs])
+
+
+@dataclass
+class PhysicalOrder(PlanNode):
+    """PhysicalOrder{order_by, input} (physical_order.rs)"""
+    order_by: Sequence[BoundOrderBy]
+    child: PlanNode
+
+    def output_schema(self, tables):
+        return self.child.output_schema(tables)
+
+
+@dataclass
+class PhysicalLimit(PlanNode):
+    """PhysicalLimit{limit, offset, input} (physical_limit.rs); None = not given"""
+    limit: Optional[int]
+    offset: Optional[int]
+    child: PlanNode
+
+    def output_schema(self, tables):
+        return self.child.output_schema(tables)
+
+
 class GpuPlan:
     """A built plan: push tables, execute, collect (try_collect, src/executor/mod.rs:58-64)."""
 
@@ -92,6 +125,7 @@ class GpuPlan:
         def add(node: PlanNode) -> int:
             rec = ffi.PlanNode()
             rec.child0 = rec.child1 = -1
+            rec.limit = rec.offset = -1
             if isinstance(node, PhysicalTableScan):
                 rec.kind, rec.table_slot = ffi.NODE_SCAN, node.table_slot
             elif isinstance(node, PhysicalFilter):
@@ -132,6 +166,27 @@ class GpuPlan:
                 sch = ffi.export_schema(node.join_output_schema)
                 self._keep.append(sch)
                 rec.join_output_schema = C.pointer(sch)
+            elif isinstance(node, PhysicalProject):
+                child_schema = node.child.output_schema(table_schemas)
+                rec.kind = ffi.NODE_PROJECT
+                rec.child0 = add(node.child)
+                exprs = ExprArray(node.exprs)
+                names = NameArray(project_field_names(node.exprs, child_schema))
+                self._keep += [exprs, names]
+                rec.exprs, rec.expr_names, rec.n_exprs = exprs.ptr, names.ptr, exprs.n
+            elif isinstance(node, PhysicalOrder):
+                rec.kind = ffi.NODE_ORDER
+                rec.child0 = add(node.child)
+                exprs = ExprArray([o.expr for o in node.order_by])
+                asc = (C.c_int32 * max(1, len(node.order_by)))(*[int(o.asc) for o in node.order_by])
+                self._keep += [exprs, asc]
+                rec.exprs, rec.n_exprs = exprs.ptr, exprs.n
+                rec.order_asc = C.cast(asc, C.POINTER(C.c_int32))
+            elif isinstance(node, PhysicalLimit):
+                rec.kind = ffi.NODE_LIMIT
+                rec.child0 = add(node.child)
+                rec.limit = -1 if node.limit is None else int(node.limit)
+                rec.offset = -1 if node.offset is None else int(node.offset)
             else:
                 raise TypeError(f"unknown plan node {node!r}")
             nodes.append(rec)

@@ -26,7 +26,7 @@ def test_header_and_binding_agree():
 def test_cuda_library_exports_every_declared_symbol(cuda_lib):
     for name in header_symbols():
         assert hasattr(cuda_lib.cdll, "sqlrs_" + name), name
-    assert cuda_lib.abi_version() == 1
+    assert cuda_lib.abi_version() == ffi.ABI_VERSION == 2
     assert cuda_lib.kernel_launches() == 0 or cuda_lib.kernel_launches() > 0
 
 

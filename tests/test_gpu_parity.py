@@ -520,3 +520,145 @@ def test_many_groups_with_growth_across_batches(cuda_lib, oracle):
         got, exp = both(lambda l: ex.try_collect(ex.HashAggExecutor(aggs, groups, batches, lib=l, options=l.options(match_mode=mm)).execute()), cuda_lib, oracle)
         assert got[0].num_rows > 10000
         assert_batches_match(got, exp, rtol=FTOL)
+
+
+# ------------------------------------------------------------------ Order / Limit / Project
+def _special_floats(rng, n):
+    v = np.round(rng.normal(0, 3, n), 0)  # many ties
+    for k, x in enumerate((np.nan, -np.nan, np.inf, -np.inf, 0.0, -0.0, 5e-324, -1e308)):
+        v[rng.integers(0, n, 3)] = x
+    return v
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_order_random(cuda_lib, oracle, seed):
+    """ties, NULLs, NaN / -0.0 / inf, every key type, 1..3 sort keys in both directions, several input batches: the
+    output row order must equal the oracle's exactly (both keep ties in input order)"""
+    rng = np.random.default_rng(1000 + seed)
+    dtypes = [I64, F64, I32, BOOL, I64]
+    batches = []
+    for n in (0, 700, 1, 3000)[: 2 + seed % 3]:
+        b = random_batch(rng, n, dtypes, null_frac=0.2 if seed % 2 else 0.0, small_ints=True)
+        if n:
+            mask = None if seed % 2 == 0 else rng.random(n) < 0.2
+            b = b.set_column(1, "c1", pa.array(_special_floats(rng, n), mask=mask))
+        batches.append(b)
+    n_keys = 1 + seed % 3
+    cols = rng.permutation(4)[:n_keys]
+    order_by = [ex.BoundOrderBy(InputRef(int(c), dtypes[int(c)]), asc=bool(rng.integers(0, 2))) for c in cols]
+    if seed == 5:  # an expression as the sort key
+        order_by = [ex.BoundOrderBy(bind_binary_op(InputRef(0, I64), "*", InputRef(4, I64)), asc=False)]
+    got, exp = both(lambda l: ex.try_collect(ex.OrderExecutor(order_by, batches, lib=l).execute()), cuda_lib, oracle)
+    assert len(got) == len(exp) == 1 and got[0].num_rows == sum(b.num_rows for b in batches)
+    assert_batches_match(got, exp)
+
+
+def test_order_single_key_descending_reverses_null_run(cuda_lib, oracle):
+    """arrow's single-column sort_to_indices reverses the run of NULL rows when descending"""
+    b = pa.RecordBatch.from_arrays([pa.array([3, None, 1, None, 2, None], pa.int64()), pa.array([0, 1, 2, 3, 4, 5], pa.int64())], names=["k", "row"])
+    for lib_ in (cuda_lib, oracle):
+        out = ex.try_collect(ex.OrderExecutor([ex.BoundOrderBy(InputRef(0, I64), asc=False)], [b], lib=lib_).execute())
+        assert [r[1] for r in rows_of(out)] == [5, 3, 1, 0, 4, 2]
+        out = ex.try_collect(ex.OrderExecutor([ex.BoundOrderBy(InputRef(0, I64), asc=True)], [b], lib=lib_).execute())
+        assert [r[1] for r in rows_of(out)] == [1, 3, 5, 2, 4, 0]
+
+
+@pytest.mark.parametrize("limit,offset", [(5, None), (None, 7), (1000, 3), (10, 995), (0, 0), (4000, 0), (300, 700), (1, 2999)])
+def test_limit_random_batches(cuda_lib, oracle, limit, offset):
+    rng = np.random.default_rng(7)
+    batches = [random_batch(rng, n, [I64, F64, BOOL, I32]) for n in (400, 0, 600, 33, 2000)]
+    def run(l):
+        try:
+            return ex.try_collect(ex.LimitExecutor(limit, offset, batches, lib=l).execute())
+        except ffi.ExecutorError as e:  # OFFSET without LIMIT over several batches underflows at limit.rs:58 (the reference panics)
+            return e.code
+
+    got, exp = both(run, cuda_lib, oracle)
+    if isinstance(exp, int):
+        assert got == exp == ffi.ERR_INTERNAL and limit is None
+        return
+    assert [b.num_rows for b in got] == [b.num_rows for b in exp]
+    assert_batches_match(got, exp)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_project_random(cuda_lib, oracle, seed):
+    rng = np.random.default_rng(50 + seed)
+    dtypes = [I64, F64, I32, BOOL, I64, F64]
+    batches = [random_batch(rng, n, dtypes, small_ints=True) for n in (257, 0, 4000)]
+    exprs = [InputRef(3, BOOL), random_expr(rng, dtypes, I64, 3), random_expr(rng, dtypes, F64, 2), InputRef(1, F64), random_expr(rng, dtypes, BOOL, 3)]
+    got, exp = both(lambda l: ex.try_collect(ex.ProjectExecutor(exprs, batches, lib=l).execute()), cuda_lib, oracle)
+    assert_batches_match(got, exp, rtol=FTOL)
+
+
+def test_aggregate_finalised_on_device(cuda_lib, oracle):
+    """> 1024 groups take the device finalisation path (packed rows -> typed columns + validity by one kernel): every
+    accumulator kind, nullable arguments, a nullable key, Float64 MIN/MAX, both COUNT modes, first-appearance order"""
+    rng = np.random.default_rng(99)
+    n = 120_000
+    k = pa.array(rng.integers(0, 5000, n).astype(np.int64), mask=rng.random(n) < 0.01)
+    k2 = pa.array(rng.integers(0, 2, n).astype(bool))
+    v = pa.array(rng.integers(-1000, 1000, n).astype(np.int64), mask=rng.random(n) < 0.5)
+    f = pa.array(np.round(rng.normal(0, 10, n), 3), mask=rng.random(n) < 0.5)
+    w = pa.array(rng.integers(-100, 100, n).astype(np.int32))
+    b = pa.RecordBatch.from_arrays([k, k2, v, f, w], names=["k", "k2", "v", "f", "w"])
+    batches = [b.slice(0, 50_000), b.slice(50_000)]
+    aggs = [AggFunc("Sum", [InputRef(2, I64)]), AggFunc("Count", [InputRef(3, F64)]), AggFunc("Min", [InputRef(3, F64)]), AggFunc("Max", [InputRef(3, F64)]),
+            AggFunc("Sum", [InputRef(3, F64)]), AggFunc("Max", [InputRef(4, I32)]), AggFunc("Count", [InputRef(0, I64)])]
+    groups = [InputRef(0, I64), InputRef(1, BOOL)]
+    for cm in (ffi.COUNT_REFERENCE_OVERWRITE, ffi.COUNT_SQL_ACCUMULATE):
+        opts = dict(count_mode=cm, match_mode=ffi.MATCH_HASH_AND_KEY)
+        got, exp = both(lambda l: ex.try_collect(ex.HashAggExecutor(aggs, groups, batches, lib=l, options=l.options(**opts)).execute()), cuda_lib, oracle)
+        assert got[0].num_rows > 5000
+        assert_batches_match(got, exp, rtol=FTOL)
+
+
+def test_q3_full_plan_with_tail_on_device(cuda_lib, oracle):
+    """Q3' including ORDER BY revenue desc, o_orderdate LIMIT 10 and the select list: fused (top-k gather), operator at a
+    time, and the oracle agree row for row"""
+    d = tpch.dims(0.05)
+    plan, schemas = tpch.q3_full_plan()
+    tables = _tables(oracle, d)
+    mode = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    exp, _ = _run_plan(oracle, plan, schemas, tables, None, **mode)
+    assert exp[0].num_rows == 10 and exp[0].schema.names == ["lineitem.l_orderkey", "revenue", "orders.o_orderdate", "orders.o_shippriority"]
+    for fl in (0, ffi.FLAG_NO_FUSION):
+        for batch_rows in (None, 100_000):
+            got, desc = _run_plan(cuda_lib, plan, schemas, tables, batch_rows, flags=fl, **mode)
+            expb, _ = _run_plan(oracle, plan, schemas, tables, batch_rows, **mode)
+            assert_batches_match(got, expb, rtol=FTOL)
+            assert "Order" in desc and "Limit" in desc
+
+
+def test_q1_full_plan_with_tail_on_device(cuda_lib, oracle):
+    d = tpch.dims(0.05)
+    plan, schemas = tpch.q1_full_plan()
+    table = {0: tpch.host_table(oracle, d, tpch.LINEITEM, columns=tpch.Q1_COLUMNS)}
+    mode = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    got, _ = _run_plan(cuda_lib, plan, schemas, table, 65536, **mode)
+    exp, _ = _run_plan(oracle, plan, schemas, table, 65536, **mode)
+    assert [r[:2] for r in rows_of(got)] == sorted(r[:2] for r in rows_of(got)) and got[0].num_rows == 8
+    assert_batches_match(got, exp, rtol=FTOL)
+
+
+def test_plan_order_limit_over_join_and_filter(cuda_lib, oracle):
+    """tail operators over non-aggregate children: Limit(Order(Filter(scan))) and Limit(Project(HashJoin)), several batches"""
+    from sqlrs_b200.host.plan import PhysicalFilter, PhysicalHashJoin, PhysicalLimit, PhysicalOrder, PhysicalProject, PhysicalTableScan
+
+    rng = np.random.default_rng(4242)
+    t = random_batch(rng, 5000, [I64, F64, I64], small_ints=True, names=["a", "b", "c"])
+    u = random_batch(rng, 300, [I64, I64], small_ints=True, names=["x", "y"])
+    schemas = {0: t.schema, 1: u.schema}
+    tables = {0: t, 1: u}
+    filt = PhysicalFilter(bind_binary_op(InputRef(0, I64), ">", Constant(-3)), PhysicalTableScan(0))
+    p1 = PhysicalLimit(40, 10, PhysicalOrder([ex.BoundOrderBy(InputRef(1, F64), False), ex.BoundOrderBy(InputRef(2, I64), True)], filt))
+    jschema = pa.schema([pa.field("u.x", pa.int64()), pa.field("u.y", pa.int64()), pa.field("t.a", pa.int64()), pa.field("t.b", pa.float64()), pa.field("t.c", pa.int64())])
+    join = PhysicalHashJoin(PhysicalTableScan(1), PhysicalTableScan(0), "Inner", ex.JoinCondition([(InputRef(0, I64), InputRef(0, I64))]), jschema)
+    p2 = PhysicalLimit(500, 100, PhysicalProject([bind_binary_op(InputRef(1, I64), "+", InputRef(4, I64)), InputRef(3, F64)], join))
+    for plan in (p1, p2):
+        for batch_rows in (None, 1000):
+            for fl in (0, ffi.FLAG_NO_FUSION):
+                got, _ = _run_plan(cuda_lib, plan, schemas, tables, batch_rows, flags=fl, match_mode=ffi.MATCH_HASH_AND_KEY)
+                exp, _ = _run_plan(oracle, plan, schemas, tables, batch_rows, match_mode=ffi.MATCH_HASH_AND_KEY)
+                assert sum(b.num_rows for b in got) > 0
+                assert_batches_match(got, exp, rtol=FTOL)

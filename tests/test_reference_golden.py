@@ -252,3 +252,92 @@ def test_slt_utf8_cases_oracle_only(oracle):
     out = ex.try_collect(ex.HashAggExecutor([AggFunc("Count", [st]), AggFunc("Sum", [sal]), AggFunc("Max", [sal]), AggFunc("Min", [sal])], [st], [emp],
                                             lib=oracle).execute())
     assert rows_of(out) == [("CA", 1, 12000, 12000, 12000), ("CO", 2, 21500, 11500, 10000), ("", 1, N, N, N)]
+
+
+# ---------------------------------------------------------------- Limit / Order / Project
+def _range_chunk(lo, hi):
+    """limit.rs:121-125 range_to_chunk: one non-nullable Int32 column `a`"""
+    return batch(["a"], list(range(lo, hi)), types=[pa.int32()], nullable=False)
+
+
+@pytest.mark.parametrize("inputs,offset,limit,outputs", [  # limit.rs:96-101
+    ([(0, 6)], 1, 4, [(1, 5)]),
+    ([(0, 6)], 0, 10, [(0, 6)]),
+    ([(0, 6)], 10, 0, []),
+    ([(0, 2), (2, 4), (4, 6)], 1, 4, [(1, 2), (2, 4), (4, 5)]),
+    ([(0, 2), (2, 4), (4, 6)], 1, 2, [(1, 2), (2, 3)]),
+    ([(0, 2), (2, 4), (4, 6)], 3, 0, []),
+])
+def test_limit_executor_cases(lib, inputs, offset, limit, outputs):
+    out = ex.try_collect(ex.LimitExecutor(limit, offset, [_range_chunk(*r) for r in inputs], lib=lib).execute())
+    assert [b.column(0).to_pylist() for b in out] == [list(range(*r)) for r in outputs]
+    for b in out:
+        assert b.schema.field(0).name == "a" and b.schema.field(0).type == pa.int32()
+
+
+def test_executor_limit_and_order(lib):
+    """mod.rs:353-396: `select id from employee offset 2 limit 1` -> [3];
+    `select id from employee order by id desc offset 2 limit 1` -> [2] (plan: Order -> Project -> Limit, select.rs:34-45)"""
+    emp = mem_employee()
+    idc = InputRef(0, I64)
+    out = ex.try_collect(ex.LimitExecutor(1, 2, ex.ProjectExecutor([idc], [emp], lib=lib).execute(), lib=lib).execute())
+    assert len(out) == 1 and out[0].schema.names == ["id"] and rows_of(out) == [(3,)]
+    ordered = ex.OrderExecutor([ex.BoundOrderBy(idc, asc=False)], [emp], lib=lib).execute()
+    out = ex.try_collect(ex.LimitExecutor(1, 2, ex.ProjectExecutor([idc], ordered, lib=lib).execute(), lib=lib).execute())
+    assert len(out) == 1 and rows_of(out) == [(2,)]
+
+
+def test_slt_limit(lib):
+    """limit.slt:1-29 over employee ids 1..4"""
+    emp = employee_numeric()
+    ids = lambda limit, offset: [r[0] for r in rows_of(ex.try_collect(
+        ex.LimitExecutor(limit, offset, ex.ProjectExecutor([InputRef(0, I64)], [emp], lib=lib).execute(), lib=lib).execute()))]
+    assert ids(2, 1) == [2, 3]
+    assert ids(1, 10) == []
+    assert ids(0, 0) == []
+    assert ids(None, 2) == [3, 4]
+    assert ids(2, None) == [1, 2]
+
+
+def test_slt_order_numeric(lib):
+    """order.slt:1-6: order by id desc offset 2 limit 1 -> 2; two sort keys with directions over numeric columns:
+    `order by department_id, id desc` — the NULL department sorts first (SortOptions::default().nulls_first)"""
+    emp = employee_numeric()
+    idc, dep = InputRef(0, I64), InputRef(2, I64)
+    ordered = ex.OrderExecutor([ex.BoundOrderBy(idc, asc=False)], [emp], lib=lib).execute()
+    assert rows_of(ex.try_collect(ex.LimitExecutor(1, 2, ex.ProjectExecutor([idc], ordered, lib=lib).execute(), lib=lib).execute())) == [(2,)]
+    out = ex.try_collect(ex.OrderExecutor([ex.BoundOrderBy(dep, True), ex.BoundOrderBy(idc, False)], [emp], lib=lib).execute())
+    assert len(out) == 1 and out[0].schema.names == ["id", "salary", "department_id"]
+    assert [(r[0], r[2]) for r in rows_of(out)] == [(4, N), (1, 1), (2, 2), (3, 4)]
+    # descending keeps NULLs first
+    out = ex.try_collect(ex.OrderExecutor([ex.BoundOrderBy(dep, False)], [emp], lib=lib).execute())
+    assert [(r[0], r[2]) for r in rows_of(out)] == [(4, N), (3, 4), (2, 2), (1, 1)]
+
+
+def test_order_needs_a_batch(lib):
+    """order.rs:27 unwraps the schema of the first batch: an empty child stream is an error"""
+    with pytest.raises(ffi.ExecutorError) as err:
+        ex.try_collect(ex.OrderExecutor([ex.BoundOrderBy(InputRef(0, I64))], [], lib=lib).execute())
+    assert err.value.code == ffi.ERR_INTERNAL
+
+
+def test_project_field_names(lib):
+    """project.rs:20-27 + evaluator.rs:30-64: an InputRef keeps its field, other expressions are named l{op}r / cast names"""
+    emp = mem_employee()
+    exprs = [InputRef(1, I64), bind_binary_op(InputRef(0, I64), "+", Constant(1)), bind_binary_op(InputRef(1, I64), ">", InputRef(0, I64))]
+    out = ex.try_collect(ex.ProjectExecutor(exprs, [emp], lib=lib).execute())
+    assert out[0].schema.names == ["salary", "id+Int64(1)", "salary>id"]
+    assert not out[0].schema.field(0).nullable and out[0].schema.field(1).nullable
+    assert rows_of(out) == [(100, 2, True), (100, 3, True), (200, 4, True), (400, 5, True)]
+
+
+def test_slt_order_utf8_oracle_only(oracle):
+    """order.slt:8-22: `order by state, id desc` -> 4 (empty) / 1 CA / 3 CO / 2 CO; `order by first_name desc offset 2 limit 1` -> 2"""
+    emp = pa.RecordBatch.from_arrays(
+        [pa.array([1, 2, 3, 4], pa.int64()), pa.array(["Bill", "Gregg", "John", "Von"]), pa.array(["CA", "CO", "CO", ""])], names=["id", "first_name", "state"])
+    U8 = ffi.DT_UTF8
+    out = ex.try_collect(ex.OrderExecutor([ex.BoundOrderBy(InputRef(2, U8), True), ex.BoundOrderBy(InputRef(0, I64), False)], [emp], lib=oracle).execute())
+    assert [(r[0], r[2]) for r in rows_of(out)] == [(4, ""), (1, "CA"), (3, "CO"), (2, "CO")]
+    ordered = ex.OrderExecutor([ex.BoundOrderBy(InputRef(1, U8), False)], [emp], lib=oracle).execute()
+    out = ex.try_collect(ex.LimitExecutor(1, 2, ex.ProjectExecutor([InputRef(0, I64)], ordered, lib=oracle).execute(), lib=oracle).execute())
+    assert rows_of(out) == [(2,)]
