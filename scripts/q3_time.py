@@ -16,7 +16,8 @@ tabs = {0: tpch.device_table(lib, d, tpch.CUSTOMER, columns=tpch.Q3_CUSTOMER_COL
         2: tpch.device_table(lib, d, tpch.LINEITEM, columns=tpch.Q3_LINEITEM_COLUMNS)}
 rows = {k: t.n_rows for k, t in tabs.items()}
 alg = tpch.q3_algorithmic_bytes(rows[0], rows[1], rows[2])
-plan, schemas = tpch.q3_plan()
+full = len(sys.argv) > 3 and sys.argv[3] == "full"  # + Order / Project / Limit on the device
+plan, schemas = tpch.q3_full_plan() if full else tpch.q3_plan()
 stream = torch.cuda.Stream()
 with torch.cuda.stream(stream):
     opts = lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY, stream=C.c_void_p(stream.cuda_stream))
@@ -40,5 +41,8 @@ with torch.cuda.stream(stream):
     print(f"Q3' SF{sf:g}: rows c/o/l = {rows[0]}/{rows[1]}/{rows[2]}  groups={res.num_rows}  best {best*1e3:.2f} ms  "
           f"{sum(rows.values())/best/1e9:.2f} Grows/s  alg {alg/1e9:.2f} GB -> {alg/best/1e9:.0f} GB/s  launches/run={launches}")
     print(p.describe()[:600])
+    if full:
+        print(res.to_pydict())
+        sys.exit(0)
     top = res.sort_by([(res.schema.names[3], "descending"), (res.schema.names[1], "ascending")]).slice(0, 3)
     print(top.to_pydict())
