@@ -390,6 +390,11 @@ int SQLRS_API(debug_compile_joinagg)(const sqlrs_agg_desc* aggs, int32_t n_aggs,
                                      const sqlrs_expr* probe_predicate, const sqlrs_expr* join_filter,
                                      const struct ArrowSchema* build_schema, const struct ArrowSchema* probe_schema,
                                      const sqlrs_options* options, int32_t compile, char** source_out);
+/* the fused probe kernel (csrc/jit/joinprobe.cuh) of a hash join with `right_keys` over `probe_schema` batches and an
+ * optional Filter fused below the join on the probe side */
+int SQLRS_API(debug_compile_joinprobe)(const sqlrs_expr* right_keys, int32_t n_keys, const sqlrs_expr* probe_predicate,
+                                       const struct ArrowSchema* probe_schema, const sqlrs_options* options,
+                                       int32_t compile, char** source_out);
 int SQLRS_API(debug_compile_eval)(const sqlrs_expr* exprs, int32_t n_exprs, int32_t as_keep_mask,
                                   const struct ArrowSchema* input_schema, int32_t compile, char** source_out);
 void SQLRS_API(free)(void* p);

@@ -479,8 +479,22 @@ int sqlrs_debug_compile_joinagg(const sqlrs_agg_desc* aggs, int32_t n_aggs, cons
     if (probe_predicate && probe_predicate->n_nodes > 0) pp = copy_expr(probe_predicate);
     if (join_filter && join_filter->n_nodes > 0) jf = copy_expr(join_filter);
     std::string gen = op.debug_join_source(cols_of_schema(build_schema), cols_of_schema(probe_schema), copy_exprs(right_keys, n_keys), pp, jf);
-    if (compile) jit_compile_to_cubin("agg_table+joinagg", gen, nullptr);
-    if (source_out) *source_out = dup_string(jit_full_source("agg_table+joinagg", gen));
+    if (compile) jit_compile_to_cubin("agg_table+join_table+joinagg", gen, nullptr);
+    if (source_out) *source_out = dup_string(jit_full_source("agg_table+join_table+joinagg", gen));
+  });
+}
+
+int sqlrs_debug_compile_joinprobe(const sqlrs_expr* right_keys, int32_t n_keys, const sqlrs_expr* probe_predicate, const ArrowSchema* probe_schema,
+                                  const sqlrs_options* options, int32_t compile, char** source_out) {
+  return guarded([&] {
+    Options opt = copy_options(options);
+    opt.device_id = -2;
+    ExprCopy pp;
+    if (probe_predicate && probe_predicate->n_nodes > 0) pp = copy_expr(probe_predicate);
+    JoinOp op(SQLRS_JOIN_INNER, copy_exprs(right_keys, n_keys), copy_exprs(right_keys, n_keys), {}, {}, opt);
+    std::string gen = op.debug_probe_source(cols_of_schema(probe_schema), pp);
+    if (compile) jit_compile_to_cubin("join_table+joinprobe", gen, nullptr);
+    if (source_out) *source_out = dup_string(jit_full_source("join_table+joinprobe", gen));
   });
 }
 

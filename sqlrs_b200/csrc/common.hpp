@@ -39,6 +39,11 @@ struct Error : std::runtime_error {
 #define SQ_HD
 #endif
 
+// stream-ordered scratch memory from the library's block cache (device.cpp): freed blocks are reused by later
+// allocations of the same size class on the same stream without a driver call
+void* scratch_alloc(size_t bytes, cudaStream_t stream);
+void scratch_free(void* p, cudaStream_t stream);
+
 extern std::atomic<int64_t> g_kernel_launches;
 inline void count_launch(int64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 

@@ -2,13 +2,18 @@
 #include "device.hpp"
 
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <tuple>
+#include <unordered_map>
 
 #include "kernels_aot.hpp"
 
 namespace sq {
 
 std::atomic<int64_t> g_kernel_launches{0};
+
+static void flush_stream_cache(int device, cudaStream_t stream);  // block cache below
 
 // ------------------------------------------------------------------ Ctx
 static void tune_pool(int device) {
@@ -50,7 +55,11 @@ Ctx::~Ctx() {
     cudaEventDestroy(p.ev);
   }
   pending.clear();
-  if (own_stream) cudaStreamDestroy(stream);
+  if (own_stream) {
+    flush_stream_cache(device, stream);  // cached blocks are keyed by the stream that is about to disappear
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+  }
 }
 
 void Ctx::defer(std::function<void()> fn) {
@@ -82,12 +91,170 @@ void Ctx::sync() {
   pending.clear();
 }
 
-// ------------------------------------------------------------------ buffers
-DevBuf::~DevBuf() {
-  if (p) {
-    cudaSetDevice(device);
+// ------------------------------------------------------------------ block caches
+// A plan re-allocates the same buffer sizes on the same stream every run.  Going to the driver's stream-ordered pool
+// for each of them costs 2-5 us per call and — measured on Q3' SF100 — sporadic 0.5 s stalls when the pool has to
+// re-map physical memory to satisfy a multi-GB request (profiles/r01e_q3_sf100_trace.txt).  Freed blocks are therefore
+// kept per (device, stream, size class) and handed out again in stream order: a block's next user is enqueued on the
+// same stream after its previous user, so no synchronisation is needed.  Size classes: powers of two up to 1 MiB,
+// then 16 steps per octave (<= 12.5 % slack).
+namespace {
+
+size_t size_class(size_t bytes) {
+  if (bytes <= 512) return 512;
+  size_t p = 512;
+  while (p < bytes) p <<= 1;
+  if (p <= (1u << 20)) return p;
+  const size_t step = p >> 4;
+  return (bytes + step - 1) / step * step;
+}
+
+struct DeviceCache {
+  std::mutex mu;
+  std::map<std::tuple<int, cudaStream_t, size_t>, std::vector<void*>> free_blocks;
+  std::unordered_map<void*, size_t> live;  // blocks handed out through scratch_alloc: their class
+  size_t cached = 0;
+  size_t cap = 64ULL << 30;
+  DeviceCache() {
+    if (const char* e = std::getenv("SQLRS_B200_CACHE_GB")) cap = (size_t)std::max(0, atoi(e)) << 30;
+  }
+  void* get(int device, cudaStream_t stream, size_t cls) {
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      auto it = free_blocks.find(std::make_tuple(device, stream, cls));
+      if (it != free_blocks.end() && !it->second.empty()) {
+        void* p = it->second.back();
+        it->second.pop_back();
+        cached -= cls;
+        return p;
+      }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, cls, stream);
+    if (e == cudaErrorMemoryAllocation) {  // give everything cached back to the driver and retry once
+      cudaGetLastError();
+      flush(-1, nullptr, true);
+      e = cudaMallocAsync(&p, cls, stream);
+    }
+    if (e != cudaSuccess) fail(SQLRS_ERR_CUDA, std::string("cudaMallocAsync(") + std::to_string(cls) + " bytes): " + cudaGetErrorString(e));
+    return p;
+  }
+  void put(int device, cudaStream_t stream, void* p, size_t cls) {
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      if (cached + cls <= cap) {
+        free_blocks[std::make_tuple(device, stream, cls)].push_back(p);
+        cached += cls;
+        return;
+      }
+    }
     cudaFreeAsync(p, stream);
   }
+  // returns cached blocks to the driver: those of one (device, stream), or all of them
+  void flush(int device, cudaStream_t stream, bool all) {
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto it = free_blocks.begin(); it != free_blocks.end();) {
+      if (all || (std::get<0>(it->first) == device && std::get<1>(it->first) == stream)) {
+        for (void* p : it->second) {
+          cudaFreeAsync(p, std::get<1>(it->first));
+          cached -= std::get<2>(it->first);
+        }
+        it = free_blocks.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+};
+DeviceCache& device_cache() {
+  static DeviceCache* c = new DeviceCache();  // never destroyed: release callbacks may run during process exit
+  return *c;
+}
+
+// pinned host blocks for results leaving the device: D2H at PCIe speed straight into the exported Arrow buffers
+// (measured: 36 MB of Q3' SF100 groups took 17 ms into pageable memory)
+struct PinnedCache {
+  std::mutex mu;
+  std::map<size_t, std::vector<void*>> free_blocks;
+  std::unordered_map<void*, size_t> live;
+  size_t cached = 0;
+  size_t cap = 8ULL << 30;
+  void* get(size_t bytes) {
+    const size_t cls = size_class(bytes);
+    void* p = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      auto it = free_blocks.find(cls);
+      if (it != free_blocks.end() && !it->second.empty()) {
+        p = it->second.back();
+        it->second.pop_back();
+        cached -= cls;
+      }
+    }
+    if (!p && cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;  // the caller falls back to pageable memory
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    live[p] = cls;
+    return p;
+  }
+  bool put(void* p) {  // false: not one of ours
+    size_t cls = 0;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      auto it = live.find(p);
+      if (it == live.end()) return false;
+      cls = it->second;
+      live.erase(it);
+      if (cached + cls <= cap) {
+        free_blocks[cls].push_back(p);
+        cached += cls;
+        return true;
+      }
+    }
+    cudaFreeHost(p);
+    return true;
+  }
+};
+PinnedCache& pinned_cache() {
+  static PinnedCache* c = new PinnedCache();
+  return *c;
+}
+
+}  // namespace
+
+static void flush_stream_cache(int device, cudaStream_t stream) { device_cache().flush(device, stream, false); }
+
+void* scratch_alloc(size_t bytes, cudaStream_t stream) {
+  int device = 0;
+  SQ_CUDA(cudaGetDevice(&device));
+  DeviceCache& c = device_cache();
+  const size_t cls = size_class(bytes);
+  void* p = c.get(device, stream, cls);
+  std::lock_guard<std::mutex> lock(c.mu);
+  c.live[p] = cls;
+  return p;
+}
+void scratch_free(void* p, cudaStream_t stream) {
+  if (!p) return;
+  int device = 0;
+  cudaGetDevice(&device);
+  DeviceCache& c = device_cache();
+  size_t cls = 0;
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) return;
+    cls = it->second;
+    c.live.erase(it);
+  }
+  c.put(device, stream, p, cls);
+}
+
+// ------------------------------------------------------------------ buffers
+DevBuf::~DevBuf() {
+  if (p) device_cache().put(device, stream, p, size_class(bytes ? bytes : 16));
 }
 
 BufPtr dev_alloc(Ctx& ctx, size_t bytes) {
@@ -95,8 +262,7 @@ BufPtr dev_alloc(Ctx& ctx, size_t bytes) {
   b->bytes = bytes;
   b->stream = ctx.stream;
   b->device = ctx.device;
-  if (bytes == 0) bytes = 16;
-  SQ_CUDA(cudaMallocAsync(&b->p, bytes, ctx.stream));
+  b->p = device_cache().get(ctx.device, ctx.stream, size_class(bytes ? bytes : 16));
   return b;
 }
 BufPtr dev_alloc_zero(Ctx& ctx, size_t bytes) {
@@ -356,7 +522,8 @@ void release_array(ArrowArray* a) {
   for (int64_t c = 0; c < a->n_children; c++)
     if (a->children[c] && a->children[c]->release) a->children[c]->release(a->children[c]);
   auto* p = (ExportPriv*)a->private_data;
-  for (void* m : p->owned) std::free(m);
+  for (void* m : p->owned)
+    if (!pinned_cache().put(m)) std::free(m);
   delete p;
   a->release = nullptr;
 }
@@ -371,6 +538,13 @@ void* xmalloc(size_t bytes) {
   void* p = std::malloc(bytes ? bytes : 1);
   if (!p) fail(SQLRS_ERR_INTERNAL, "out of host memory");
   return p;
+}
+// destination of a D2H copy: pinned (recycled through the release callback) when it is large enough to matter
+void* result_alloc(size_t bytes) {
+  if (bytes >= (64u << 10)) {
+    if (void* p = pinned_cache().get(bytes)) return p;
+  }
+  return xmalloc(bytes);
 }
 void export_field(const Field& f, ArrowSchema* out) {
   auto* p = new SchemaPriv();
@@ -434,13 +608,13 @@ void export_batch_host(Ctx& ctx, const DBatch& b, ArrowArray* out, ArrowSchema* 
     }
     if (col.valid && col.n > 0) {
       size_t nb = (size_t)bitmap_words(col.n) * 4;
-      validity_host[c] = (uint8_t*)xmalloc(nb);
+      validity_host[c] = (uint8_t*)result_alloc(nb);
       cp->owned.push_back(validity_host[c]);
       SQ_CUDA(cudaMemcpyAsync(validity_host[c], col.valid, nb, cudaMemcpyDeviceToHost, ctx.stream));
     }
     cp->buffers.push_back(nullptr);
     size_t vb = col_value_bytes(col.dtype, col.n);
-    void* v = xmalloc(vb);
+    void* v = result_alloc(vb);
     cp->owned.push_back(v);
     if (vb) SQ_CUDA(cudaMemcpyAsync(v, col.data, vb, cudaMemcpyDeviceToHost, ctx.stream));
     cp->buffers.push_back(v);

@@ -1,0 +1,53 @@
+// sqlrs_b200 JIT building block "join_table": the probe side's view of a sealed hash-join build table
+// (kernels_join.cu: open-addressed slots over the distinct keys + CSR row lists + blocked Bloom filter) and its exact
+// lookup, shared by the fused probe kernels (joinprobe.cuh, joinagg.cuh).  Needs SqProbe / SQ_JKEYS / SQ_JMATCH from
+// the generated part.  Reference: the HashMap<u64, Vec<usize>> lookup of src/executor/join/hash_join.rs:225-235.
+
+struct SqJoin {           // mirrors sq::JoinTableView (kernels_aot.hpp)
+  const i64* slot_rep;    // representative build row per slot, -1 = empty
+  const u32* slot_count;
+  const u64* slot_start;
+  const i64* rows;        // build row ids grouped by slot, ascending
+  u32 capacity;
+  const u64* h;           // build-side row hashes
+  const u64* keys;        // [SQ_JKEYS][n_build] raw key bits (SQ_JMATCH)
+  const u32* knull;
+  i64 n_build;
+  int n_keys;
+  int match_keys;
+  const u32* build_keep;
+  const u64* bloom;       // blocked Bloom filter over the build hashes (3 bits in one 64-bit word per key)
+  u32 bloom_mask;
+  int unique;             // every build key occurs once: the match list of a slot is its representative row
+};
+
+__device__ __forceinline__ u32 sq_bloom_word(u64 h, u32 mask) { return (u32)((h * 0x9E3779B97F4A7C15ULL) >> 40) & mask; }
+__device__ __forceinline__ u64 sq_bloom_bits(u64 h) {
+  const u64 g = h * 0x9E3779B97F4A7C15ULL;
+  return (1ULL << ((g >> 34) & 63)) | (1ULL << ((g >> 28) & 63)) | (1ULL << ((g >> 22) & 63));
+}
+
+__device__ __forceinline__ int sq_join_find(const SqJoin& t, const SqProbe& p) {
+#if SQ_JMATCH
+  if (p.knull != 0u) return -1;  // SQL semantics: a NULL key never joins
+#endif
+  const u32 mask = t.capacity - 1;
+  u32 s = sq_mix32(p.h) & mask;
+  for (u32 probes = 0; probes <= mask; probes++) {
+    const i64 rep = __ldg(&t.slot_rep[s]);
+    if (rep < 0) return -1;
+    if (__ldg(&t.h[rep]) == p.h) {
+#if SQ_JMATCH
+      bool same = true;
+#pragma unroll
+      for (int k = 0; k < SQ_JKEYS; k++) same = same && (__ldg(&t.keys[(size_t)k * t.n_build + rep]) == p.kb[k]);
+      if (same) return (int)s;
+#else
+      return (int)s;
+#endif
+    }
+    s = (s + 1) & mask;
+  }
+  return -1;
+}
+

@@ -5,7 +5,7 @@
 // table (kernels_join.cu layout, resident in HBM / L2), build-side columns are gathered only for matching rows, and
 // every joined row goes straight into the group table — no (build row, probe row) pairs, no joined batch.
 //
-// Generated in front of this file (after agg_table.cuh):
+// Generated in front of this file (after agg_table.cuh; join_table.cuh follows the generated part):
 //   SQ_NKEYS / SQ_NACC / SQ_MATCH_KEYS (aggregate), SQ_JKEYS (join keys), SQ_JMATCH (compare join key tuples),
 //   struct SqIn (probe side), struct SqInB (build side),
 //   struct SqProbe {pass, h, kb[SQ_JKEYS], knull}; sq_probe_row(in, r, p, e0, e1)   — fused probe-side Filter + join keys
@@ -24,53 +24,6 @@
 //      upserts into the group table.  So the divergent, latency-bound part runs with all lanes busy however
 //      selective the join is, and phase A never waits on it.
 
-struct SqJoin {           // mirrors sq::JoinTableView (kernels_aot.hpp)
-  const i64* slot_rep;    // representative build row per slot, -1 = empty
-  const u32* slot_count;
-  const u64* slot_start;
-  const i64* rows;        // build row ids grouped by slot, ascending
-  u32 capacity;
-  const u64* h;           // build-side row hashes
-  const u64* keys;        // [SQ_JKEYS][n_build] raw key bits (SQ_JMATCH)
-  const u32* knull;
-  i64 n_build;
-  int n_keys;
-  int match_keys;
-  const u32* build_keep;
-  const u64* bloom;       // blocked Bloom filter over the build hashes (3 bits in one 64-bit word per key)
-  u32 bloom_mask;
-};
-
-__device__ __forceinline__ u32 sq_bloom_word(u64 h, u32 mask) { return (u32)((h * 0x9E3779B97F4A7C15ULL) >> 40) & mask; }
-__device__ __forceinline__ u64 sq_bloom_bits(u64 h) {
-  const u64 g = h * 0x9E3779B97F4A7C15ULL;
-  return (1ULL << ((g >> 34) & 63)) | (1ULL << ((g >> 28) & 63)) | (1ULL << ((g >> 22) & 63));
-}
-
-__device__ __forceinline__ int sq_join_find(const SqJoin& t, const SqProbe& p) {
-#if SQ_JMATCH
-  if (p.knull != 0u) return -1;  // SQL semantics: a NULL key never joins
-#endif
-  const u32 mask = t.capacity - 1;
-  u32 s = sq_mix32(p.h) & mask;
-  for (u32 probes = 0; probes <= mask; probes++) {
-    const i64 rep = __ldg(&t.slot_rep[s]);
-    if (rep < 0) return -1;
-    if (__ldg(&t.h[rep]) == p.h) {
-#if SQ_JMATCH
-      bool same = true;
-#pragma unroll
-      for (int k = 0; k < SQ_JKEYS; k++) same = same && (__ldg(&t.keys[(size_t)k * t.n_build + rep]) == p.kb[k]);
-      if (same) return (int)s;
-#else
-      return (int)s;
-#endif
-    }
-    s = (s + 1) & mask;
-  }
-  return -1;
-}
-
 #ifndef SQ_JUNROLL
 #define SQ_JUNROLL 8
 #endif
@@ -85,8 +38,10 @@ __device__ __forceinline__ void sq_joinagg_candidate(const SqIn& in, const SqInB
   sq_probe_row(in, r, p, e0, e1);  // re-evaluated (L1/L2 hits): cheaper than queueing hash + key tuple
   const int slot = sq_join_find(jt, p);
   if (slot < 0) return;
-  const u32 cnt = __ldg(&jt.slot_count[slot]);
-  const i64* brow = jt.rows + __ldg(&jt.slot_start[slot]);
+  // unique build keys (a primary-key side): the slot's representative row IS its match list — three dependent
+  // random reads (count, range start, row id) less per match
+  const u32 cnt = jt.unique ? 1u : __ldg(&jt.slot_count[slot]);
+  const i64* brow = jt.unique ? jt.slot_rep + slot : jt.rows + __ldg(&jt.slot_start[slot]);
   for (u32 j = 0; j < cnt; j++) {  // per probe row: build rows in insertion order (hash_join.rs:225-235)
     const i64 b = __ldg(&brow[j]);
     SqRow o;

@@ -8,6 +8,11 @@
 
 namespace sq {
 
+// generated CUDA of the probe side's row program (after gen_input_decls): SQ_JKEYS, SQ_JMATCH, struct SqProbe and
+// sq_probe_row(in, r, p, e0, e1) = Filter fused below the join on the probe side (optional) + the join key
+// expressions, their create_hashes row hash, raw key bits and null mask.  Shared by csrc/jit/joinprobe.cuh and joinagg.cuh.
+std::string gen_probe_program(const std::vector<ColInfo>& cols, const std::vector<ExprCopy>& right_keys, const ExprCopy& probe_pred, bool jmatch);
+
 class JoinOp {
  public:
   JoinOp(int join_type, std::vector<ExprCopy> left_keys, std::vector<ExprCopy> right_keys, ExprCopy filter,
@@ -30,6 +35,8 @@ class JoinOp {
   const std::vector<ExprCopy>& right_keys() const { return right_keys_; }
   const ExprCopy& join_filter() const { return filter_; }
   bool match_keys() const { return opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY; }
+  // generated CUDA of the fused probe kernel for probe batches of that schema (diagnostics / build check, no GPU)
+  std::string debug_probe_source(const std::vector<ColInfo>& probe_cols, const ExprCopy& probe_pred) const;
 
  private:
   struct Impl;

@@ -465,29 +465,29 @@ void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, ui
   if (n == 0) return;
   uint64_t *k_in = nullptr, *k_out = nullptr;
   uint32_t *v_in = nullptr, *v_out = nullptr, *count = nullptr;
-  SQ_CUDA(cudaMallocAsync(&k_in, (size_t)n * 8, stream));
-  SQ_CUDA(cudaMallocAsync(&k_out, (size_t)n * 8, stream));
-  SQ_CUDA(cudaMallocAsync(&v_in, (size_t)n * 4, stream));
-  SQ_CUDA(cudaMallocAsync(&v_out, (size_t)n * 4, stream));
-  SQ_CUDA(cudaMallocAsync(&count, 4, stream));
+  k_in = (decltype(k_in))scratch_alloc((size_t)n * 8, stream);
+  k_out = (decltype(k_out))scratch_alloc((size_t)n * 8, stream);
+  v_in = (decltype(v_in))scratch_alloc((size_t)n * 4, stream);
+  v_out = (decltype(v_out))scratch_alloc((size_t)n * 4, stream);
+  count = (decltype(count))scratch_alloc(4, stream);
   SQ_CUDA(cudaMemsetAsync(count, 0, 4, stream));
   k_table_list<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, k_in, v_in, n, count);
   count_launch();
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, 64, stream);
   void* tmp = nullptr;
-  SQ_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, stream));
+  tmp = (decltype(tmp))scratch_alloc(tmp_bytes ? tmp_bytes : 16, stream);
   SQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, 64, stream));
   count_launch(8);
   k_table_pack_ordered<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, v_out, n, dst);
   count_launch();
   SQ_CUDA(cudaGetLastError());
-  cudaFreeAsync(tmp, stream);
-  cudaFreeAsync(k_in, stream);
-  cudaFreeAsync(k_out, stream);
-  cudaFreeAsync(v_in, stream);
-  cudaFreeAsync(v_out, stream);
-  cudaFreeAsync(count, stream);
+  scratch_free(tmp, stream);
+  scratch_free(k_in, stream);
+  scratch_free(k_out, stream);
+  scratch_free(v_in, stream);
+  scratch_free(v_out, stream);
+  scratch_free(count, stream);
 }
 
 void launch_table_rehash(const TableView& from, const TableView& to, int n_keys, int n_acc, cudaStream_t stream) {

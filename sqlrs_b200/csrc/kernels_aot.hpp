@@ -83,6 +83,8 @@ struct JoinTableView {
   // and turns a probe miss — the common case of a selective join — into one 8-byte L2 read.
   uint64_t* bloom;
   uint32_t bloom_mask;    // number of words - 1 (power of two)
+  int unique;             // every build key occurs once (primary-key side): slot_rep is the whole match list,
+                          // slot_start / rows are not built
 };
 
 SQ_HD inline uint32_t join_bloom_word(uint64_t h, uint32_t mask) { return (uint32_t)((h * 0x9E3779B97F4A7C15ULL) >> 40) & mask; }
@@ -106,6 +108,13 @@ void launch_join_probe_count(const JoinTableView& t, const uint64_t* ph, const u
                              int64_t n_probe, int keep_unmatched, int32_t* slot_of, uint32_t* out_count, cudaStream_t stream);
 void launch_join_probe_write(const JoinTableView& t, const int32_t* slot_of, const unsigned long long* offsets, int64_t n_probe,
                              int keep_unmatched, int64_t* li, uint32_t* ri, cudaStream_t stream);
+// fused probe path (csrc/jit/joinprobe.cuh): slot_of[r] (>= 0 slot, -1 kept but unmatched, -2 dropped by the fused Filter)
+// + exclusive offsets of the 2048-row chunks -> (build row, probe row) pairs in the reference's order
+constexpr int kProbeChunk = 2048;
+void launch_join_probe_emit(const JoinTableView& t, const int32_t* slot_of, const unsigned long long* chunk_offsets, int64_t n_probe,
+                            int keep_unmatched, int64_t* li, uint32_t* ri, cudaStream_t stream);
+// bitmap of the probe rows the fused Filter kept: bit r = slot_of[r] != -2
+void launch_slot_keep_bitmap(const int32_t* slot_of, int64_t n, uint32_t* bitmap, cudaStream_t stream);
 // bitmap[idx[k]] = 1 for every k (idx < 0 skipped)
 void launch_mark_bits_i64(const int64_t* idx, int64_t m, uint32_t* bitmap, cudaStream_t stream);
 void launch_mark_bits_u32(const uint32_t* idx, int64_t m, uint32_t* bitmap, cudaStream_t stream);

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kBlock) k_join_probe_count(JoinTableView t, co
       }
     }
     slot_of[r] = found;
-    const uint32_t c = found >= 0 ? t.slot_count[found] : 0u;
+    const uint32_t c = found >= 0 ? (t.unique ? 1u : t.slot_count[found]) : 0u;
     out_count[r] = c ? c : ((keep_unmatched && kept) ? 1u : 0u);
   }
 }
@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(kBlock) k_join_probe_write(JoinTableView t, co
     const int32_t s = slot_of[r];
     unsigned long long o = offsets[r];
     if (s >= 0) {
-      const uint32_t c = t.slot_count[s];
-      const int64_t* src = t.rows + t.slot_start[s];
+      const uint32_t c = t.unique ? 1u : t.slot_count[s];
+      const int64_t* src = t.unique ? t.slot_rep + s : t.rows + t.slot_start[s];
       for (uint32_t j = 0; j < c; j++) {
         li[o + j] = src[j];
         ri[o + j] = (uint32_t)r;
@@ -148,6 +148,69 @@ __global__ void __launch_bounds__(kBlock) k_join_probe_write(JoinTableView t, co
       li[o] = -1;
       ri[o] = (uint32_t)r;
     }
+  }
+}
+
+// one CTA per 2048-row chunk, 8 consecutive probe rows per thread: CTA-wide exclusive prefix of the per-row output
+// counts, then the pairs — positions ascend with the probe row, per probe row with the build insertion order
+__global__ void __launch_bounds__(kBlock) k_join_probe_emit(JoinTableView t, const int32_t* __restrict__ slot_of,
+                                                             const unsigned long long* __restrict__ chunk_offsets, int64_t n_probe, int keep_unmatched,
+                                                             int64_t* __restrict__ li, uint32_t* __restrict__ ri) {
+  constexpr int kPer = kProbeChunk / kBlock;  // 8
+  __shared__ uint32_t warp_sums[kBlock / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t n_chunks = (n_probe + kProbeChunk - 1) / kProbeChunk;
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int64_t r0 = chunk * kProbeChunk + (int64_t)threadIdx.x * kPer;
+    int32_t slot[kPer];
+    uint32_t cnt[kPer];
+    uint32_t local = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+      slot[j] = r0 + j < n_probe ? slot_of[r0 + j] : -2;
+      cnt[j] = slot[j] >= 0 ? (t.unique ? 1u : t.slot_count[slot[j]]) : ((slot[j] == -1 && keep_unmatched) ? 1u : 0u);
+      local += cnt[j];
+    }
+    uint32_t x = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    unsigned long long o = chunk_offsets[chunk] + (x - local);
+    for (int w = 0; w < wid; w++) o += warp_sums[w];
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+      if (slot[j] >= 0) {
+        if (t.unique) {
+          li[o] = t.slot_rep[slot[j]];
+          ri[o] = (uint32_t)(r0 + j);
+        } else {
+          const int64_t* src = t.rows + t.slot_start[slot[j]];
+          for (uint32_t q = 0; q < cnt[j]; q++) {
+            li[o + q] = src[q];
+            ri[o + q] = (uint32_t)(r0 + j);
+          }
+        }
+      } else if (cnt[j]) {  // Right/Full: (NULL, row), hash_join.rs:242-246
+        li[o] = -1;
+        ri[o] = (uint32_t)(r0 + j);
+      }
+      o += cnt[j];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_slot_keep_bitmap(const int32_t* __restrict__ slot_of, int64_t n, uint32_t* __restrict__ bitmap) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_up = (n + 31) & ~(int64_t)31;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_up; r += stride) {
+    const uint32_t w = __ballot_sync(0xffffffffu, r < n && slot_of[r] != -2);
+    if (lane == 0) bitmap[r >> 5] = w;
   }
 }
 
@@ -318,10 +381,10 @@ void join_fill_sorted(const JoinTableView& t, const int32_t* row_slot, cudaStrea
   if (n <= 0) return;
   uint32_t *k_in = nullptr, *k_out = nullptr;
   int64_t *v_in = nullptr, *v_out = nullptr;
-  SQ_CUDA(cudaMallocAsync(&k_in, (size_t)n * 4, stream));
-  SQ_CUDA(cudaMallocAsync(&k_out, (size_t)n * 4, stream));
-  SQ_CUDA(cudaMallocAsync(&v_in, (size_t)n * 8, stream));
-  SQ_CUDA(cudaMallocAsync(&v_out, (size_t)n * 8, stream));
+  k_in = (decltype(k_in))scratch_alloc((size_t)n * 4, stream);
+  k_out = (decltype(k_out))scratch_alloc((size_t)n * 4, stream);
+  v_in = (decltype(v_in))scratch_alloc((size_t)n * 8, stream);
+  v_out = (decltype(v_out))scratch_alloc((size_t)n * 8, stream);
   k_slot_keys<<<grid_for(n, kBlock), kBlock, 0, stream>>>(row_slot, n, t.capacity, k_in);
   SQ_LAUNCH_CHECK();
   k_iota_i64<<<grid_for(n, kBlock), kBlock, 0, stream>>>(v_in, n);
@@ -331,16 +394,16 @@ void join_fill_sorted(const JoinTableView& t, const int32_t* row_slot, cudaStrea
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, bits, stream);
   void* tmp = nullptr;
-  SQ_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, stream));
+  tmp = (decltype(tmp))scratch_alloc(tmp_bytes ? tmp_bytes : 16, stream);
   SQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, bits, stream));
   count_launch(4);
   // rows of NULL-key build rows (slot = capacity) sort last and are never referenced by a slot range
   SQ_CUDA(cudaMemcpyAsync(t.rows, v_out, (size_t)n * 8, cudaMemcpyDeviceToDevice, stream));
-  cudaFreeAsync(tmp, stream);
-  cudaFreeAsync(k_in, stream);
-  cudaFreeAsync(k_out, stream);
-  cudaFreeAsync(v_in, stream);
-  cudaFreeAsync(v_out, stream);
+  scratch_free(tmp, stream);
+  scratch_free(k_in, stream);
+  scratch_free(k_out, stream);
+  scratch_free(v_in, stream);
+  scratch_free(v_out, stream);
 }
 
 void launch_join_probe_count(const JoinTableView& t, const uint64_t* ph, const uint64_t* pkeys, const uint32_t* pknull, const uint32_t* probe_keep,
@@ -353,6 +416,17 @@ void launch_join_probe_write(const JoinTableView& t, const int32_t* slot_of, con
                              int keep_unmatched, int64_t* li, uint32_t* ri, cudaStream_t stream) {
   if (n_probe <= 0) return;
   k_join_probe_write<<<grid_for(n_probe, kBlock), kBlock, 0, stream>>>(t, slot_of, offsets, n_probe, keep_unmatched, li, ri);
+  SQ_LAUNCH_CHECK();
+}
+void launch_join_probe_emit(const JoinTableView& t, const int32_t* slot_of, const unsigned long long* chunk_offsets, int64_t n_probe,
+                            int keep_unmatched, int64_t* li, uint32_t* ri, cudaStream_t stream) {
+  if (n_probe <= 0) return;
+  k_join_probe_emit<<<grid_for(div_up(n_probe, kProbeChunk), 1, 148 * 8), kBlock, 0, stream>>>(t, slot_of, chunk_offsets, n_probe, keep_unmatched, li, ri);
+  SQ_LAUNCH_CHECK();
+}
+void launch_slot_keep_bitmap(const int32_t* slot_of, int64_t n, uint32_t* bitmap, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_slot_keep_bitmap<<<grid_for(n, kBlock), kBlock, 0, stream>>>(slot_of, n, bitmap);
   SQ_LAUNCH_CHECK();
 }
 void launch_mark_bits_i64(const int64_t* idx, int64_t m, uint32_t* bitmap, cudaStream_t stream) {

@@ -116,10 +116,10 @@ void stable_sort_pairs(K* k_in, K* k_out, uint32_t* v_in, uint32_t* v_out, int64
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, stream);
   void* tmp = nullptr;
-  SQ_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, stream));
+  tmp = (decltype(tmp))scratch_alloc(tmp_bytes ? tmp_bytes : 16, stream);
   SQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, stream));
   count_launch(end_bit > 8 ? 10 : 3);
-  cudaFreeAsync(tmp, stream);
+  scratch_free(tmp, stream);
 }
 
 }  // namespace
@@ -139,9 +139,9 @@ void sort_pass(int dtype, const void* data, const uint32_t* valid, int64_t n, bo
   if (n >= (1LL << 31)) fail(SQLRS_ERR_UNSUPPORTED, "Order: more than 2^31 rows in one sort");
   uint64_t *k_in = nullptr, *k_out = nullptr;
   uint32_t *p_out = nullptr;
-  SQ_CUDA(cudaMallocAsync(&k_in, (size_t)n * 8, stream));
-  SQ_CUDA(cudaMallocAsync(&k_out, (size_t)n * 8, stream));
-  SQ_CUDA(cudaMallocAsync(&p_out, (size_t)n * 4, stream));
+  k_in = (decltype(k_in))scratch_alloc((size_t)n * 8, stream);
+  k_out = (decltype(k_out))scratch_alloc((size_t)n * 8, stream);
+  p_out = (decltype(p_out))scratch_alloc((size_t)n * 4, stream);
   k_sort_keys<<<grid_for(n), kBlock, 0, stream>>>(dtype, data, valid, perm, n, descending ? 1 : 0, reverse_nulls ? 1 : 0, k_in);
   count_launch();
   SQ_CUDA(cudaGetLastError());
@@ -162,9 +162,9 @@ void sort_pass(int dtype, const void* data, const uint32_t* valid, int64_t n, bo
   } else {
     SQ_CUDA(cudaMemcpyAsync(perm, p_out, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
   }
-  cudaFreeAsync(k_in, stream);
-  cudaFreeAsync(k_out, stream);
-  cudaFreeAsync(p_out, stream);
+  scratch_free(k_in, stream);
+  scratch_free(k_out, stream);
+  scratch_free(p_out, stream);
 }
 
 void launch_finalize_groups(const uint64_t* packed, int words, int64_t n, int n_cols, const FinalizeCol* cols_dev, cudaStream_t stream) {

@@ -362,29 +362,7 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
     s << "#define SQ_LDB_I64(c, b) sq_ldg_i64(inb.col[c], b)\n#define SQ_LDB_I32(c, b) sq_ldg_i32(inb.col[c], b)\n";
     s << "#define SQ_LDB_F64(c, b) sq_ldg_f64(inb.col[c], b)\n#define SQ_LDB_BOOL(c, b) sq_ld_bit(inb.col[c], b)\n";
     s << "#define SQ_VALIDB(c, b) sq_ld_bit(inb.val[c], b)\n";
-    RowProgram p1(cols);
-    std::string p1_pass = "true";
-    if (!jg->probe_pred.empty()) {
-      Val pp = p1.compile(jg->probe_pred, 0);
-      if (pp.dtype != SQLRS_DT_BOOL) fail(SQLRS_ERR_INTERNAL, "filter executor expected evaluate boolean array");
-      p1_pass = "(n" + std::to_string(pp.id) + " && v" + std::to_string(pp.id) + ")";
-    }
-    std::vector<Val> jkeys;
-    for (const ExprCopy& e : jg->right_keys) jkeys.push_back(p1.compile(e, jg->probe_pred.empty() ? 0 : 1));
-    const int jh = p1.emit_row_hash(jkeys);
-    std::vector<int> jraw;
-    for (const Val& k : jkeys) jraw.push_back(p1.emit_raw_bits(k));
-    const int JK = (int)jkeys.size();
-    s << "#define SQ_JKEYS " << JK << "\n#define SQ_JMATCH " << (jg->jmatch ? 1 : 0) << "\n";
-    s << "struct SqProbe { bool pass; u64 h; u64 kb[" << std::max(JK, 1) << "]; u32 knull; };\n";
-    s << "__device__ __forceinline__ void sq_probe_row(const SqIn& in, i64 r, SqProbe& p, bool& e0, bool& e1) {\n" << p1.body_str();
-    s << "  p.pass = " << p1_pass << ";\n  p.h = v" << jh << ";\n";
-    std::string jknull = "0u";
-    for (int k = 0; k < JK; k++) {
-      s << "  p.kb[" << k << "] = v" << jraw[k] << ";\n";
-      jknull += " | (n" + std::to_string(jkeys[k].id) + " ? 0u : " + std::to_string(1u << k) + "u)";
-    }
-    s << "  p.knull = " << jknull << ";\n}\n";
+    s << gen_probe_program(cols, jg->right_keys, jg->probe_pred, jg->jmatch);
   }
   s << "#define SQ_NKEYS " << K << "\n#define SQ_NACC " << W << "\n";
   s << "#define SQ_MATCH_KEYS " << (opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY ? 1 : 0) << "\n";
@@ -731,7 +709,7 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
   if (kit == join_kernels_.end()) {
     auto comp = std::make_unique<Compiled>();
     std::string src = generate(pcols, *comp, &jg);
-    JitKernel* k = jit_get("agg_table+joinagg", src, "sq_joinagg_kernel");
+    JitKernel* k = jit_get("agg_table+join_table+joinagg", src, "sq_joinagg_kernel");
     if (!cache_.empty()) {
       const Compiled& first = *cache_.begin()->second;
       bool same = first.words.size() == comp->words.size() && first.key_dtypes == comp->key_dtypes;
@@ -759,9 +737,18 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
   uint64_t cap = std::max<uint64_t>(2ULL * (uint64_t)jt.n_build, 1ULL << 16);
   std::unique_ptr<Table> local;
   uint32_t hc[4] = {0, 0, 0, 0};
+  bool first_try = true;
   for (;;) {
     if (cap > (1ULL << 31)) fail(SQLRS_ERR_INTERNAL, "group table would exceed 2^31 slots");
-    local = new_table((uint32_t)cap);
+    {
+      Trace tr_t("  joinagg.new_table", ctx_.stream);
+      // repeated plan runs: the operator's (re-initialised, still empty) table of the previous run is the batch-local table
+      const bool reuse = table_ && groups_known_ == 0 && !counters_stale_ && groups_bound_ == 0 && table_->capacity >= next_pow2(cap) && first_try;
+      if (reuse) local = std::move(table_);
+      else local = new_table((uint32_t)cap);
+      first_try = false;
+    }
+    Trace tr_k("  joinagg.kernel", ctx_.stream);
     SqInBlob in(probe, 0), inb(build, 0);
     int64_t n_arg = n, rb = row_base, bn = batch_no;
     void* status = (uint32_t*)local->counters->p + 2;

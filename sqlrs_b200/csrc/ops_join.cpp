@@ -5,6 +5,35 @@
 
 namespace sq {
 
+std::string gen_probe_program(const std::vector<ColInfo>& cols, const std::vector<ExprCopy>& right_keys, const ExprCopy& probe_pred, bool jmatch) {
+  std::ostringstream s;
+  RowProgram p1(cols);
+  std::string p1_pass = "true";
+  if (!probe_pred.empty()) {
+    Val pp = p1.compile(probe_pred, 0);
+    if (pp.dtype != SQLRS_DT_BOOL) fail(SQLRS_ERR_INTERNAL, "filter executor expected evaluate boolean array");
+    p1_pass = "(n" + std::to_string(pp.id) + " && v" + std::to_string(pp.id) + ")";
+  }
+  // the reference evaluates the keys on the rows the Filter kept: a failing key expression only counts there
+  std::vector<Val> jkeys;
+  for (const ExprCopy& e : right_keys) jkeys.push_back(p1.compile(e, probe_pred.empty() ? 0 : 1));
+  const int jh = p1.emit_row_hash(jkeys);
+  std::vector<int> jraw;
+  for (const Val& k : jkeys) jraw.push_back(p1.emit_raw_bits(k));
+  const int JK = (int)jkeys.size();
+  s << "#define SQ_JKEYS " << JK << "\n#define SQ_JMATCH " << (jmatch ? 1 : 0) << "\n";
+  s << "struct SqProbe { bool pass; u64 h; u64 kb[" << std::max(JK, 1) << "]; u32 knull; };\n";
+  s << "__device__ __forceinline__ void sq_probe_row(const SqIn& in, i64 r, SqProbe& p, bool& e0, bool& e1) {\n" << p1.body_str();
+  s << "  p.pass = " << p1_pass << ";\n  p.h = v" << jh << ";\n";
+  std::string jknull = "0u";
+  for (int k = 0; k < JK; k++) {
+    s << "  p.kb[" << k << "] = v" << jraw[k] << ";\n";
+    jknull += " | (n" + std::to_string(jkeys[k].id) + " ? 0u : " + std::to_string(1u << k) + "u)";
+  }
+  s << "  p.knull = " << jknull << ";\n}\n";
+  return s.str();
+}
+
 struct JoinOp::Impl {
   // build side
   std::vector<DBatch> left_batches;
@@ -19,6 +48,8 @@ struct JoinOp::Impl {
   uint32_t capacity = 0;
   BufPtr visited_left;  // bitmap over build rows (Left/Full)
   std::unique_ptr<EvalProgram> left_prog, right_prog, filter_prog;
+  std::map<std::string, JitKernel*> probe_kernels;  // fused probe kernels by probe-batch schema signature
+  uint32_t max_count = 0;                           // largest number of build rows sharing one key
   JoinTableView view{};
   // plan-level fusion (SQLRS plan executor): Filters directly below the join run inside the key evaluation,
   // and output columns nobody above reads are not gathered
@@ -140,13 +171,12 @@ void JoinOp::seal() {
   im.slot_rep = dev_alloc(ctx_, cap * 8);
   SQ_CUDA(cudaMemsetAsync(im.slot_rep->p, 0xff, cap * 8, ctx_.stream));
   im.slot_count = dev_alloc_zero(ctx_, cap * 4);
-  im.slot_start = dev_alloc(ctx_, cap * 8);
-  im.rows = dev_alloc(ctx_, (size_t)std::max<int64_t>(n, 1) * 8);
   JoinTableView& v = im.view;
   v.slot_rep = (int64_t*)im.slot_rep->p;
   v.slot_count = (uint32_t*)im.slot_count->p;
-  v.slot_start = (uint64_t*)im.slot_start->p;
-  v.rows = (int64_t*)im.rows->p;
+  v.slot_start = nullptr;  // the CSR row lists are only built when some key repeats (below)
+  v.rows = nullptr;
+  v.unique = 1;
   v.capacity = im.capacity;
   v.h = (const uint64_t*)im.h_all.data;
   v.keys = mk ? (const uint64_t*)im.keys_all->p : nullptr;
@@ -163,13 +193,26 @@ void JoinOp::seal() {
     BufPtr row_slot = dev_alloc(ctx_, (size_t)n * 4);
     BufPtr misc = dev_alloc_zero(ctx_, 16);  // [0] max count, [8] total
     launch_join_insert(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
-    BufPtr scratch = dev_alloc(ctx_, scan_scratch_entries((int64_t)cap) * 8);
-    launch_scan_u32_large(v.slot_count, (int64_t)cap, (unsigned long long*)v.slot_start, (unsigned long long*)misc->p + 1,
-                          (unsigned long long*)scratch->p, ctx_.stream);
     uint32_t max_count = 0;
     SQ_CUDA(cudaMemcpyAsync(&max_count, misc->p, 4, cudaMemcpyDeviceToHost, ctx_.stream));
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
-    if (max_count <= 64) {
+    im.max_count = max_count;
+    if (max_count <= 1) {
+      // unique build keys (a primary-key side, e.g. both Q3' joins): the slot's representative row is its whole
+      // match list — no per-slot ranges, no scan over the table, no fill pass
+    } else {
+      v.unique = 0;
+      im.slot_start = dev_alloc(ctx_, cap * 8);
+      im.rows = dev_alloc(ctx_, (size_t)n * 8);
+      v.slot_start = (uint64_t*)im.slot_start->p;
+      v.rows = (int64_t*)im.rows->p;
+      BufPtr scratch = dev_alloc(ctx_, scan_scratch_entries((int64_t)cap) * 8);
+      launch_scan_u32_large(v.slot_count, (int64_t)cap, (unsigned long long*)v.slot_start, (unsigned long long*)misc->p + 1,
+                            (unsigned long long*)scratch->p, ctx_.stream);
+    }
+    if (max_count <= 1) {
+      // nothing to fill
+    } else if (max_count <= 64) {
       BufPtr fill = dev_alloc_zero(ctx_, cap * 4);
       launch_join_fill(v, (const int32_t*)row_slot->p, (uint32_t*)fill->p, ctx_.stream);
       if (max_count > 1) launch_join_sort_ranges(v, ctx_.stream);
@@ -178,6 +221,10 @@ void JoinOp::seal() {
     }
   }
   if (join_type_ == SQLRS_JOIN_LEFT || join_type_ == SQLRS_JOIN_FULL) im.visited_left = dev_alloc_zero(ctx_, (size_t)bitmap_words(n) * 4 + 4);
+}
+
+std::string JoinOp::debug_probe_source(const std::vector<ColInfo>& probe_cols, const ExprCopy& probe_pred) const {
+  return gen_input_decls(probe_cols) + gen_probe_program(probe_cols, right_keys_, probe_pred, match_keys());
 }
 
 bool JoinOp::empty_build() const { return impl_->capacity == 0; }
@@ -228,47 +275,74 @@ bool JoinOp::probe(const DBatch& right, DBatch* result) {
   if (im.capacity == 0) return false;  // empty build side: no left batch at all (:183-185)
   Trace tr("join.probe", ctx_.stream);
   ctx_.reap();
-  const int K = (int)right_keys_.size();
   const bool mk = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
   const bool keep_right = join_type_ == SQLRS_JOIN_RIGHT || join_type_ == SQLRS_JOIN_FULL;
   const int64_t n = right.n;
   if (n >= (1LL << 32)) fail(SQLRS_ERR_INVALID_ARG, "a probe batch may hold fewer than 2^32 rows (hash_join.rs:219)");
-  if (!im.right_prog) im.right_prog = std::make_unique<EvalProgram>(key_request(right_keys_, mk, im.probe_pred));
-  EvalResult rk = im.right_prog->run(ctx_, right, "join key");
-  const uint32_t* probe_keep = nullptr;
-  DCol probe_keep_col;
-  if (!im.probe_pred.empty()) {
-    probe_keep_col = rk.cols.back();
-    rk.cols.pop_back();
-    probe_keep = (const uint32_t*)probe_keep_col.data;
-  }
-  BufPtr pkeys;
-  if (mk && n > 0) {
-    pkeys = dev_alloc(ctx_, (size_t)n * 8 * K);
-    for (int k = 0; k < K; k++)
-      SQ_CUDA(cudaMemcpyAsync((uint64_t*)pkeys->p + (size_t)k * n, rk.cols[1 + k].data, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx_.stream));
-  }
+  // Fused probe (csrc/jit/joinprobe.cuh): ONE pass over the probe batch evaluates the Filter fused below the join and
+  // the key expressions, tests the build side's Bloom filter and probes the table; it leaves the matched slot per row
+  // and the output-row count per 2048-row chunk.  A scan over the chunk counts + k_join_probe_emit then produce the
+  // (build row, probe row) pairs in the reference's order.
+  const uint32_t* probe_keep = nullptr;  // Right/Full + non-equi filter: which probe rows passed the fused Filter
+  BufPtr probe_keep_buf;
   int64_t total = 0;
   BufPtr li, ri;
   if (n > 0) {
-    Trace tr_a("  probe.count+scan+write", ctx_.stream);
-    BufPtr slot_of = dev_alloc(ctx_, (size_t)n * 4), counts = dev_alloc(ctx_, (size_t)n * 4);
-    BufPtr offsets = dev_alloc(ctx_, (size_t)n * 8 + 8);
-    BufPtr scratch = dev_alloc(ctx_, scan_scratch_entries(n) * 8);
-    launch_join_probe_count(im.view, (const uint64_t*)rk.cols[0].data, mk ? (const uint64_t*)pkeys->p : nullptr,
-                            mk ? (const uint32_t*)rk.cols[1 + K].data : nullptr, probe_keep, n, keep_right ? 1 : 0, (int32_t*)slot_of->p,
-                            (uint32_t*)counts->p, ctx_.stream);
-    unsigned long long* total_d = (unsigned long long*)offsets->p + n;
-    launch_scan_u32_large((const uint32_t*)counts->p, n, (unsigned long long*)offsets->p, total_d, (unsigned long long*)scratch->p, ctx_.stream);
-    unsigned long long t = 0;
-    SQ_CUDA(cudaMemcpyAsync(&t, total_d, 8, cudaMemcpyDeviceToHost, ctx_.stream));
+    if (im.max_count >= (1u << 20)) fail(SQLRS_ERR_UNSUPPORTED, "join: more than 2^20 build rows share one key");
+    Trace tr_a("  probe.fused count+scan+emit", ctx_.stream);
+    std::vector<ColInfo> pcols = col_infos(right);
+    const std::string sig = RowProgram(pcols).signature();
+    auto kit = im.probe_kernels.find(sig);
+    if (kit == im.probe_kernels.end()) {
+      const std::string src = gen_input_decls(pcols) + gen_probe_program(pcols, right_keys_, im.probe_pred, mk);
+      kit = im.probe_kernels.emplace(sig, jit_get("join_table+joinprobe", src, "sq_joinprobe_kernel")).first;
+    }
+    const int64_t chunks = div_up(n, kProbeChunk);
+    BufPtr slot_of = dev_alloc(ctx_, (size_t)n * 4);
+    BufPtr counts = dev_alloc(ctx_, (size_t)chunks * 4);
+    BufPtr offsets = dev_alloc(ctx_, (size_t)chunks * 8 + 8);
+    BufPtr err = dev_alloc_zero(ctx_, 8);
+    {
+      std::vector<const void*> in_blob(2 * std::max<size_t>(right.cols.size(), 1), nullptr);
+      const size_t nc = std::max<size_t>(right.cols.size(), 1);
+      for (size_t c = 0; c < right.cols.size(); c++) {
+        in_blob[c] = right.cols[c].data;
+        in_blob[nc + c] = right.cols[c].valid;
+      }
+      int64_t n_arg = n;
+      JoinTableView jv = im.view;
+      int keep = keep_right ? 1 : 0;
+      void* slot_p = slot_of->p;
+      void* counts_p = counts->p;
+      void* err_p = err->p;
+      void* args[] = {in_blob.data(), &n_arg, &jv, &keep, &slot_p, &counts_p, &err_p};
+      const int sms = device_sm_count(ctx_.device);
+      const unsigned grid = (unsigned)std::min<int64_t>(chunks, (int64_t)sms * 8);
+      jit_launch(kit->second, grid, 256, 0, ctx_.stream, args);
+    }
+    unsigned long long* total_d = (unsigned long long*)offsets->p + chunks;
+    launch_scan_u32((const uint32_t*)counts->p, chunks, (unsigned long long*)offsets->p, total_d, ctx_.stream);
+    struct {
+      unsigned long long total;
+      uint32_t err;
+    } host = {0, 0};
+    SQ_CUDA(cudaMemcpyAsync(&host.total, total_d, 8, cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaMemcpyAsync(&host.err, err->p, 4, cudaMemcpyDeviceToHost, ctx_.stream));
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
-    total = (int64_t)t;
+    if (host.err & 1u) fail(SQLRS_ERR_ARROW, "Divide by zero error (join key)");
+    total = (int64_t)host.total;
     if (total >= (1LL << 32)) fail(SQLRS_ERR_UNSUPPORTED, "join output of one probe batch exceeds 2^32 rows");
     li = dev_alloc(ctx_, (size_t)std::max<int64_t>(total, 1) * 8);
     ri = dev_alloc(ctx_, (size_t)std::max<int64_t>(total, 1) * 4);
-    launch_join_probe_write(im.view, (const int32_t*)slot_of->p, (const unsigned long long*)offsets->p, n, keep_right ? 1 : 0,
-                            (int64_t*)li->p, (uint32_t*)ri->p, ctx_.stream);
+    launch_join_probe_emit(im.view, (const int32_t*)slot_of->p, (const unsigned long long*)offsets->p, n, keep_right ? 1 : 0, (int64_t*)li->p,
+                           (uint32_t*)ri->p, ctx_.stream);
+    if (keep_right && !filter_.empty() && !im.probe_pred.empty()) {
+      // apply_join_filter re-appends probe rows that lost all their matches — but only rows the fused Filter kept
+      probe_keep_buf = dev_alloc(ctx_, (size_t)bitmap_words(n) * 4);
+      launch_slot_keep_bitmap((const int32_t*)slot_of->p, n, (uint32_t*)probe_keep_buf->p, ctx_.stream);
+      probe_keep = (const uint32_t*)probe_keep_buf->p;
+    }
+    ctx_.defer([slot_of, counts, offsets, err]() {});
   } else {
     li = dev_alloc(ctx_, 8);
     ri = dev_alloc(ctx_, 4);

@@ -141,3 +141,23 @@ def test_q3_fused_probe_aggregate_kernel_compiles(cuda_lib):
         if src.value:
             cuda_lib.free(src)
     assert "sq_joinagg_kernel" in text and "sq_probe_row" in text and "SQ_LDB_I64(4, b)" in text
+
+
+def test_q3_fused_probe_kernel_compiles(cuda_lib):
+    """the fused scan -> filter -> key hash -> Bloom -> probe kernel of Q3's first join (orders probing customer)
+    specialises and compiles for sm_100a, in both identity modes"""
+    plan, schemas = tpch.q3_plan()
+    j1 = plan.child.left
+    rk = ExprArray([r for _, r in j1.join_condition.on])
+    pp = j1.right.expr.flatten()
+    ps = ffi.export_schema(schemas[1])
+    try:
+        for mm in (ffi.MATCH_HASH_AND_KEY, ffi.MATCH_HASH_ONLY):
+            src = C.c_void_p()
+            opt = cuda_lib.options(match_mode=mm)
+            cuda_lib.check(cuda_lib.debug_compile_joinprobe(rk.ptr, rk.n, C.byref(pp.c), C.byref(ps), C.byref(opt), 1, C.byref(src)))
+            text = C.string_at(src.value).decode()
+            cuda_lib.free(src)
+            assert "sq_joinprobe_kernel" in text and "sq_probe_row" in text and f"#define SQ_JMATCH {mm}" in text
+    finally:
+        ffi.release_schema(ps)
