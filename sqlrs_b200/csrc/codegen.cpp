@@ -318,8 +318,9 @@ int RowProgram::emit_mix_hash(const std::vector<int>& raw_ids, const std::vector
   int id = fresh();
   body_ << "  unsigned long long " << vname(id) << " = 0x9e3779b97f4a7c15ULL;\n";
   for (size_t k = 0; k < raw_ids.size(); k++) {
-    body_ << "  " << vname(id) << " = (" << vname(id) << " ^ " << vname(raw_ids[k]) << (keys[k].maybe_null ? " ^ (" + nname(keys[k].id) + " ? 0ULL : 0x5bd1e995ULL)" : std::string(""))
-          << ") * 0xff51afd7ed558ccdULL;\n";
+    // the key's type is part of the identity (the reference's hash_one differs between Int32 and Int64 too)
+    body_ << "  " << vname(id) << " = (" << vname(id) << " ^ " << vname(raw_ids[k]) << " ^ 0x" << std::hex << (0x1000193ULL * (unsigned)(keys[k].dtype + 1)) << std::dec << "ULL"
+          << (keys[k].maybe_null ? " ^ (" + nname(keys[k].id) + " ? 0ULL : 0x5bd1e995ULL)" : std::string("")) << ") * 0xff51afd7ed558ccdULL;\n";
     body_ << "  " << vname(id) << " ^= " << vname(id) << " >> 32;\n";
   }
   return id;

@@ -35,31 +35,55 @@ __device__ __forceinline__ bool same_key(const JoinTableView& t, int64_t b, uint
   return true;
 }
 
+// Every insert is a chain of dependent random accesses (slot -> CAS -> count); a thread therefore works on kInsertBatch
+// rows at a time and issues each level of the chain for all of them before it waits (measured with one row at a
+// time: 88 long-scoreboard stall cycles per issued instruction, 10 % issue utilisation).
+constexpr int kInsertBatch = 4;
 __global__ void __launch_bounds__(kBlock) k_join_insert(JoinTableView t, int32_t* __restrict__ row_slot, uint32_t* __restrict__ max_count) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const uint32_t mask = t.capacity - 1;
   uint32_t local_max = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.n_build; i += stride) {
-    const bool dropped = t.build_keep && !((t.build_keep[i >> 5] >> (i & 31)) & 1u);  // fails the fused Filter
-    if (dropped || (t.match_keys && t.knull[i] != 0u)) {  // SQL semantics: a NULL key never joins
-      row_slot[i] = -1;
-      continue;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < t.n_build; base += stride * kInsertBatch) {
+    int64_t i[kInsertBatch];
+    bool live[kInsertBatch];
+    uint64_t h[kInsertBatch];
+    uint32_t s[kInsertBatch];
+    long long rep[kInsertBatch];
+#pragma unroll
+    for (int u = 0; u < kInsertBatch; u++) {
+      i[u] = base + u * stride;
+      const bool inb = i[u] < t.n_build;
+      const int64_t r = inb ? i[u] : 0;
+      const bool kept = !t.build_keep || ((t.build_keep[r >> 5] >> (r & 31)) & 1u);            // passes the fused Filter
+      const bool null_key = t.match_keys && t.knull[r] != 0u;                                  // SQL semantics: a NULL key never joins
+      h[u] = t.h[r];
+      live[u] = inb && kept && !null_key;
+      s[u] = mix32(h[u]) & mask;
     }
-    const uint64_t h = t.h[i];
-    uint32_t s = mix32(h) & mask;
-    for (;;) {
-      long long rep = *((volatile long long*)&t.slot_rep[s]);
-      if (rep < 0) {
-        const long long old = (long long)atomicCAS((unsigned long long*)&t.slot_rep[s], (unsigned long long)-1LL, (unsigned long long)i);
-        rep = old < 0 ? i : old;
+#pragma unroll
+    for (int u = 0; u < kInsertBatch; u++) rep[u] = live[u] ? *((volatile long long*)&t.slot_rep[s[u]]) : -1;
+#pragma unroll
+    for (int u = 0; u < kInsertBatch; u++) {
+      if (!live[u]) {
+        if (i[u] < t.n_build) row_slot[i[u]] = -1;
+        continue;
       }
-      if (rep == i || same_key(t, rep, h, t.keys, t.n_build, i)) break;
-      s = (s + 1) & mask;
+      uint32_t slot = s[u];
+      long long r = rep[u];
+      for (;;) {
+        if (r < 0) {
+          const long long old = (long long)atomicCAS((unsigned long long*)&t.slot_rep[slot], (unsigned long long)-1LL, (unsigned long long)i[u]);
+          r = old < 0 ? i[u] : old;
+        }
+        if (r == i[u] || same_key(t, r, h[u], t.keys, t.n_build, i[u])) break;
+        slot = (slot + 1) & mask;
+        r = *((volatile long long*)&t.slot_rep[slot]);
+      }
+      row_slot[i[u]] = (int32_t)slot;
+      if (t.bloom) atomicOr((unsigned long long*)&t.bloom[join_bloom_word(h[u], t.bloom_mask)], (unsigned long long)join_bloom_bits(h[u]));
+      const uint32_t c = atomicAdd(&t.slot_count[slot], 1u) + 1u;
+      local_max = c > local_max ? c : local_max;
     }
-    row_slot[i] = (int32_t)s;
-    if (t.bloom) atomicOr((unsigned long long*)&t.bloom[join_bloom_word(h, t.bloom_mask)], (unsigned long long)join_bloom_bits(h));
-    const uint32_t c = atomicAdd(&t.slot_count[s], 1u) + 1u;
-    local_max = c > local_max ? c : local_max;
   }
   for (int d = 16; d > 0; d >>= 1) {
     const uint32_t o = __shfl_xor_sync(0xffffffffu, local_max, d);
@@ -362,7 +386,7 @@ void launch_scan_u32_large(const uint32_t* counts, int64_t m, unsigned long long
 
 void launch_join_insert(const JoinTableView& t, int32_t* row_slot, uint32_t* max_count, cudaStream_t stream) {
   if (t.n_build <= 0) return;
-  k_join_insert<<<grid_for(t.n_build, kBlock), kBlock, 0, stream>>>(t, row_slot, max_count);
+  k_join_insert<<<grid_for(div_up(t.n_build, kInsertBatch), kBlock, 148 * 32), kBlock, 0, stream>>>(t, row_slot, max_count);
   SQ_LAUNCH_CHECK();
 }
 void launch_join_fill(const JoinTableView& t, const int32_t* row_slot, uint32_t* slot_fill, cudaStream_t stream) {

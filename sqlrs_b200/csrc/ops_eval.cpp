@@ -99,6 +99,16 @@ std::string EvalProgram::source_for(const std::vector<ColInfo>& cols, std::vecto
         g.valid = "true";
         break;
       }
+      case OUT_MIXHASH: {
+        std::vector<int> raw;
+        for (const Val& k : keys) raw.push_back(prog.emit_raw_bits(k));
+        int id = prog.emit_mix_hash(raw, keys);
+        g.dtype = SQLRS_DT_INT64;
+        g.ctype = "u64";
+        g.value = "v" + std::to_string(id);
+        g.valid = "true";
+        break;
+      }
       case OUT_RAWBITS: {
         int id = prog.emit_raw_bits(vals.at(o.expr));
         g.dtype = SQLRS_DT_INT64;

@@ -17,9 +17,9 @@ std::string gen_probe_program(const std::vector<ColInfo>& cols, const std::vecto
   // the reference evaluates the keys on the rows the Filter kept: a failing key expression only counts there
   std::vector<Val> jkeys;
   for (const ExprCopy& e : right_keys) jkeys.push_back(p1.compile(e, probe_pred.empty() ? 0 : 1));
-  const int jh = p1.emit_row_hash(jkeys);
   std::vector<int> jraw;
   for (const Val& k : jkeys) jraw.push_back(p1.emit_raw_bits(k));
+  const int jh = jmatch ? p1.emit_mix_hash(jraw, jkeys) : p1.emit_row_hash(jkeys);  // as the build side (key_request)
   const int JK = (int)jkeys.size();
   s << "#define SQ_JKEYS " << JK << "\n#define SQ_JMATCH " << (jmatch ? 1 : 0) << "\n";
   s << "struct SqProbe { bool pass; u64 h; u64 kb[" << std::max(JK, 1) << "]; u32 knull; };\n";
@@ -66,7 +66,8 @@ static EvalRequest key_request(const std::vector<ExprCopy>& keys, bool match_key
     r.exprs.push_back(k);
     r.is_key.push_back(true);
   }
-  r.outs.push_back({OUT_HASH, 0});
+  // hash-only identity needs the reference's row hash; with key comparison any placement hash does
+  r.outs.push_back({match_keys ? OUT_MIXHASH : OUT_HASH, 0});
   if (match_keys) {
     for (size_t k = 0; k < keys.size(); k++) r.outs.push_back({OUT_RAWBITS, (int)k});
     r.outs.push_back({OUT_NULLMASK, 0});
@@ -316,8 +317,9 @@ bool JoinOp::probe(const DBatch& right, DBatch* result) {
       void* counts_p = counts->p;
       void* err_p = err->p;
       void* args[] = {in_blob.data(), &n_arg, &jv, &keep, &slot_p, &counts_p, &err_p};
-      const int sms = device_sm_count(ctx_.device);
-      const unsigned grid = (unsigned)std::min<int64_t>(chunks, (int64_t)sms * 8);
+      // persistent grid: exactly the CTAs that are resident at once, so the chunk-stride loop has no ragged second wave
+      const int per_sm = std::max(1, jit_max_blocks_per_sm(kit->second, 256, 0));
+      const unsigned grid = (unsigned)std::min<int64_t>(chunks, (int64_t)device_sm_count(ctx_.device) * per_sm);
       jit_launch(kit->second, grid, 256, 0, ctx_.stream, args);
     }
     unsigned long long* total_d = (unsigned long long*)offsets->p + chunks;
