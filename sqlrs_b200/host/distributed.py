@@ -11,6 +11,11 @@ Scan, filter and the partial aggregation stay GPU-local; the only exchange is th
   3. the (now disjoint) owner-merged groups are gathered on rank 0, which finalises them in the
      reference's first-appearance order (minimum global row id) sqlrs_plan_finish_partial
 
+Joins (Q3'): `broadcast_build_join_aggregate` (any sharding of the probe sides, build sides exchanged) and
+`copartitioned_topk` (fact tables range-partitioned on the join key that is also a group key, dimension table
+replicated: every rank runs the WHOLE query on its shards, no data-path collective at all, only the final
+LIMIT rows are gathered).
+
 The reference has no distributed execution; results equal the single-process ones (integers
 bit-exact, float sums up to summation order).  This module contains no compute — partial groups
 cross the C ABI as opaque Arrow batches whose column 0 is the partitioning hash.
@@ -233,3 +238,41 @@ def broadcast_build_join_aggregate(builder, group: TorchGroup, stage1, stage1_sc
     result = sharded_aggregate(p2, group, row_base=group.rank << 40)
     p2.close()
     return result
+
+
+def copartitioned_shard(n_orders: int, rank: int, world: int):
+    """Row ranges of rank `rank` for the synthetic orders / lineitem tables range-partitioned on orderkey: the generator
+    lays out the lines of orders [7b, 7b+7) in lineitem rows [28b, 28b+28) (include/sqlrs_tpch_spec.h), so cutting
+    orders at multiples of 7 and lineitem at the matching multiples of 28 puts every order next to all its lines.
+    Returns ((orders_lo, orders_hi), (lineitem_lo, lineitem_hi or None = to the end))."""
+    blocks = n_orders // 7
+    b_lo, b_hi = blocks * rank // world, blocks * (rank + 1) // world
+    if rank == world - 1:
+        return (7 * b_lo, n_orders), (28 * b_lo, None)
+    return (7 * b_lo, 7 * b_hi), (28 * b_lo, 28 * b_hi)
+
+
+def copartitioned_topk(plan, group: "TorchGroup", order_by, limit: int, offset: Optional[int] = None) -> List[pa.RecordBatch]:
+    """Multi-GPU execution of  Limit(Project(Order(Aggregate(joins...))))  over tables that are co-partitioned on a
+    join key which is also a group-by key ("scan stays GPU-local").
+
+    Every rank has pushed its shards of the partitioned tables and the whole of the replicated (dimension) tables
+    into `plan` — the full query plan, tail included.  Because the partition key is a group key, the groups of
+    different ranks are disjoint, so the global top rows are among the per-rank top rows: each rank runs the plan
+    locally (no collective on the data path), the <= offset+limit local rows are gathered on rank 0, which orders
+    them again with the library's own Order / Limit operators.  `order_by`: BoundOrderBy list over the plan's OUTPUT
+    columns.  Ties between ranks resolve in rank order = global row order, as in the single-process run."""
+    from . import executor as ex
+
+    local = plan.run()
+    schema = local[0].schema if local else None
+    table = pa.Table.from_batches(local).combine_chunks() if local else None
+    payload = _to_bytes(table.to_batches()[0]) if table is not None and table.num_rows else b""
+    gathered = group.gather_bytes(payload, dst=0)
+    if gathered is None:
+        return []
+    batches = [_from_bytes(data) for data in gathered if data]
+    if not batches:
+        return [pa.RecordBatch.from_pylist([], schema=schema)] if schema is not None else []
+    ordered = ex.OrderExecutor(order_by, batches, lib=plan.lib, options=plan.options).execute()
+    return ex.try_collect(ex.LimitExecutor(limit, offset, ordered, lib=plan.lib, options=plan.options).execute())

@@ -123,3 +123,71 @@ def test_two_rank_broadcast_build_join_matches_single_process(tmp_path, oracle):
     """Q3' with the join build sides broadcast and the probe sides sharded over 2 ranks == single-process Q3'"""
     mp.spawn(_q3_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").read_text() == "ok"
+
+
+def _q3_copart_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+
+    from sqlrs_b200.host import distributed as sqdist
+    from sqlrs_b200.host import ffi, tpch
+    from sqlrs_b200.host.plan import ExecutorBuilder
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lib = ffi.Library(os.path.join(ROOT, "oracle", "liboracle.so"), "sqlrs_oracle_")
+    d = tpch.dims(0.02)
+    opts = lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    builder = ExecutorBuilder(lib, opts)
+    plan, schemas = tpch.q3_full_plan()
+    (o_lo, o_hi), (l_lo, l_hi) = sqdist.copartitioned_shard(int(d.n_orders), rank, world)
+    customer = tpch.host_table(lib, d, tpch.CUSTOMER, columns=tpch.Q3_CUSTOMER_COLUMNS)  # dimension table: replicated
+    orders = tpch.host_table(lib, d, tpch.ORDERS, o_lo, o_hi, columns=tpch.Q3_ORDERS_COLUMNS)
+    lineitem = tpch.host_table(lib, d, tpch.LINEITEM, l_lo, l_hi, columns=tpch.Q3_LINEITEM_COLUMNS)
+    # co-partitioned: every line of this rank belongs to one of this rank's orders
+    ok, lk = orders.column(0).to_numpy(), lineitem.column(0).to_numpy()
+    assert lk.min() >= ok.min() and lk.max() <= ok.max()
+    p = builder.build(plan, schemas)
+    p.push_table(0, customer)
+    p.push_table(1, orders)
+    p.push_table(2, lineitem)
+    group = sqdist.TorchGroup(dist, torch.device("cpu"))
+    result = sqdist.copartitioned_topk(p, group, tpch.q3_tail_order_by(), 10)
+    p.close()
+    if rank == 0:
+        whole = builder.build(plan, schemas)
+        whole.push_table(0, customer)
+        whole.push_table(1, tpch.host_table(lib, d, tpch.ORDERS, columns=tpch.Q3_ORDERS_COLUMNS))
+        whole.push_table(2, tpch.host_table(lib, d, tpch.LINEITEM, columns=tpch.Q3_LINEITEM_COLUMNS))
+        expect = whole.run()
+        from util import assert_batches_match
+
+        assert sum(b.num_rows for b in expect) == 10
+        assert_batches_match(result, expect, rtol=1e-9)
+        open(os.path.join(out_dir, "ok"), "w").write("ok")
+    else:
+        assert result == []
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_copartitioned_q3_full_query_matches_single_process(tmp_path, oracle, world):
+    """Q3' incl. ORDER BY / LIMIT with orders and lineitem range-partitioned on orderkey over the ranks and customer
+    replicated: every rank runs the whole query locally, rank 0 merges the per-rank top-10 — equals the single-process result"""
+    mp.spawn(_q3_copart_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok").read_text() == "ok"
+
+
+def test_copartitioned_shard_covers_everything():
+    sys.path.insert(0, ROOT)
+    from sqlrs_b200.host import distributed as sqdist
+
+    for n_orders in (7, 100, 30000, 1500001):
+        for world in (1, 2, 3, 8):
+            o_prev, l_prev = 0, 0
+            for r in range(world):
+                (o_lo, o_hi), (l_lo, l_hi) = sqdist.copartitioned_shard(n_orders, r, world)
+                assert o_lo == o_prev and l_lo == l_prev and o_lo % 7 == 0 and l_lo == 4 * o_lo
+                o_prev, l_prev = o_hi, l_hi
+            assert o_prev == n_orders and l_prev is None
