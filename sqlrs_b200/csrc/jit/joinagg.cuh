@@ -115,3 +115,114 @@ extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_kernel(SqIn i
   if ((u32)lane < queued) sq_joinagg_candidate(in, inb, (i64)queue[lane], row_base, jt, table, batch_no, status, any_err);
   if (any_err) atomicOr(err, 1u);
 }
+
+#if SQ_TMA
+// ---------------------------------------------------------------------------------------------------------------
+// TMA variant: "bulk-async staging of probe-side batches into shared memory".  One elected thread per CTA issues
+// cp.async.bulk copies of whole 2048-row slices (16 KB each) of the columns the probe program reads — Filter column(s)
+// and join key(s) — into a two-stage shared-memory ring and arms an mbarrier with the byte count; the copy of tile
+// i+1 is in flight while the CTA evaluates tile i out of shared memory.  Versus the register-staged kernel above, the
+// DRAM latency of phase A is taken off the warps' critical path and no registers are spent on loads in flight.
+// Phase B (the compacted candidates) is unchanged: it re-evaluates the few candidate rows from global memory (L2 hits:
+// the slice has just passed through L2) and gathers the remaining probe columns only for matches.
+// Requirements checked by the host (ops_agg.cpp): every staged column is 8 bytes wide and 16-byte aligned; the rows
+// behind the last full tile go through sq_joinagg_kernel.
+__device__ __forceinline__ u32 sq_smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sq_mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sq_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sq_mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sq_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sq_bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sq_smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(sq_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void sq_mbar_wait(u64* bar, u32 parity) {
+  u32 done = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(sq_smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
+extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_tma_kernel(SqIn in, SqInB inb, i64 n_tiles, i64 row_base, SqJoin jt, SqTable table,
+                                                                               i64 batch_no, u32* __restrict__ status, u32* __restrict__ err) {
+  extern __shared__ __align__(128) u64 sq_tiles[];  // [2 stages][SQ_TILE_NCOLS][SQ_TROWS]
+  __shared__ __align__(8) u64 mbar[2];
+  __shared__ u32 queue_s[SQ_JBLOCK / 32][SQ_JQUEUE];
+  bool any_err = false;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32* queue = queue_s[warp];
+  const u32 lanes_below = (1u << lane) - 1u;
+  u32 queued = 0;  // warp-uniform
+  const int tile_cols[SQ_TILE_NCOLS] = SQ_TILE_COLS;
+  if (threadIdx.x == 0) {
+    sq_mbar_init(&mbar[0], 1);
+    sq_mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  i64 tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < n_tiles) {
+    sq_mbar_expect_tx(&mbar[0], SQ_TILE_NCOLS * SQ_TROWS * 8);
+#pragma unroll
+    for (int k = 0; k < SQ_TILE_NCOLS; k++)
+      sq_bulk_g2s(sq_tiles + (size_t)k * SQ_TROWS, (const u64*)in.col[tile_cols[k]] + tile * SQ_TROWS, SQ_TROWS * 8, &mbar[0]);
+  }
+  for (u32 it = 0; tile < n_tiles; it++, tile += gridDim.x) {
+    const u32 stage = it & 1u;
+    const i64 next = tile + gridDim.x;
+    if (threadIdx.x == 0 && next < n_tiles) {  // the other stage was released by the __syncthreads() that ended the previous trip
+      sq_mbar_expect_tx(&mbar[stage ^ 1u], SQ_TILE_NCOLS * SQ_TROWS * 8);
+#pragma unroll
+      for (int k = 0; k < SQ_TILE_NCOLS; k++)
+        sq_bulk_g2s(sq_tiles + ((size_t)(stage ^ 1u) * SQ_TILE_NCOLS + k) * SQ_TROWS, (const u64*)in.col[tile_cols[k]] + next * SQ_TROWS, SQ_TROWS * 8,
+                    &mbar[stage ^ 1u]);
+    }
+    sq_mbar_wait(&mbar[stage], (it >> 1) & 1u);
+    const u64* tl = sq_tiles + (size_t)stage * SQ_TILE_NCOLS * SQ_TROWS;
+    const i64 base = tile * SQ_TROWS + (i64)warp * (SQ_JUNROLL * 32);
+    // ---- phase A out of shared memory
+    u64 hh[SQ_JUNROLL];
+    bool live[SQ_JUNROLL];
+#pragma unroll
+    for (int u = 0; u < SQ_JUNROLL; u++) {
+      const int t = warp * (SQ_JUNROLL * 32) + u * 32 + lane;
+      SqProbe p;
+      bool e0 = false, e1 = false;
+      sq_probe_row_tile(in, tl, t, base + u * 32 + lane, p, e0, e1);
+      live[u] = p.pass;
+#if SQ_JMATCH
+      live[u] = live[u] && p.knull == 0u;
+#endif
+      any_err |= e0 || (p.pass && e1);
+      hh[u] = p.h;
+    }
+    u64 bw[SQ_JUNROLL];
+#pragma unroll
+    for (int u = 0; u < SQ_JUNROLL; u++) bw[u] = live[u] ? __ldg(&jt.bloom[sq_bloom_word(hh[u], jt.bloom_mask)]) : 0ULL;
+#pragma unroll
+    for (int u = 0; u < SQ_JUNROLL; u++) {
+      const u64 bits = sq_bloom_bits(hh[u]);
+      const bool cand = live[u] && (bw[u] & bits) == bits;
+      const u32 m = __ballot_sync(0xffffffffu, cand);
+      if (cand) queue[queued + __popc(m & lanes_below)] = (u32)(base + u * 32 + lane);
+      queued += __popc(m);
+    }
+    __syncwarp();
+    // ---- phase B: full warps only
+    while (queued >= 32) {
+      queued -= 32;
+      sq_joinagg_candidate(in, inb, (i64)queue[queued + lane], row_base, jt, table, batch_no, status, any_err);
+      __syncwarp();
+    }
+    __syncthreads();  // every warp is done with this stage before it is refilled
+  }
+  if ((u32)lane < queued) sq_joinagg_candidate(in, inb, (i64)queue[lane], row_base, jt, table, batch_no, status, any_err);
+  if (any_err) atomicOr(err, 1u);
+}
+#endif  // SQ_TMA

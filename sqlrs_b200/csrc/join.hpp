@@ -11,7 +11,14 @@ namespace sq {
 // generated CUDA of the probe side's row program (after gen_input_decls): SQ_JKEYS, SQ_JMATCH, struct SqProbe and
 // sq_probe_row(in, r, p, e0, e1) = Filter fused below the join on the probe side (optional) + the join key
 // expressions, their create_hashes row hash, raw key bits and null mask.  Shared by csrc/jit/joinprobe.cuh and joinagg.cuh.
-std::string gen_probe_program(const std::vector<ColInfo>& cols, const std::vector<ExprCopy>& right_keys, const ExprCopy& probe_pred, bool jmatch);
+// When every column that program reads is an 8-byte column (at most 3 of them), `tile_cols` lists them and the source
+// also contains sq_probe_row_tile(in, tile, t, r, ...): the same program reading those columns from a shared-memory
+// tile staged by TMA bulk copies (SQ_TMA 1, SQ_TILE_NCOLS, SQ_TILE_COLS) — csrc/jit/joinagg.cuh: sq_joinagg_tma_kernel.
+struct ProbeProgram {
+  std::string src;
+  std::vector<int> tile_cols;
+};
+ProbeProgram gen_probe_program(const std::vector<ColInfo>& cols, const std::vector<ExprCopy>& right_keys, const ExprCopy& probe_pred, bool jmatch);
 
 class JoinOp {
  public:

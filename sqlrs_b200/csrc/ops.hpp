@@ -144,7 +144,12 @@ class AggOp {
   bool simple_;
   ExprCopy predicate_;
   std::map<std::string, std::unique_ptr<Compiled>> cache_;
-  std::map<std::string, JitKernel*> join_kernels_;  // fused probe->aggregate kernels by (probe, build) schema signature
+  struct JoinKernels {
+    JitKernel* generic = nullptr;
+    JitKernel* tma = nullptr;      // sq_joinagg_tma_kernel, when the probe program's columns can be staged by TMA
+    std::vector<int> tile_cols;    // the staged probe columns
+  };
+  std::map<std::string, JoinKernels> join_kernels_;  // fused probe->aggregate kernels by (probe, build) schema signature
   std::unique_ptr<Table> table_;
   int64_t rows_seen_ = 0, batches_seen_ = 0;
   bool seen_batch_ = false;

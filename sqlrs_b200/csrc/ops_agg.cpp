@@ -117,6 +117,7 @@ struct AggOp::Compiled {
   std::vector<WordPlan> words;
   std::vector<int> key_dtypes;
   std::vector<bool> key_decl_null;  // may the key be NULL in some batch of this schema?
+  std::vector<int> tile_cols;       // fused probe->aggregate: probe columns the TMA variant stages in shared memory
   int block = 128, slots = 8, unroll = 4, min_ctas = 1;
   size_t small_smem = 0;
   int small_grid = 0;
@@ -362,7 +363,9 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
     s << "#define SQ_LDB_I64(c, b) sq_ldg_i64(inb.col[c], b)\n#define SQ_LDB_I32(c, b) sq_ldg_i32(inb.col[c], b)\n";
     s << "#define SQ_LDB_F64(c, b) sq_ldg_f64(inb.col[c], b)\n#define SQ_LDB_BOOL(c, b) sq_ld_bit(inb.col[c], b)\n";
     s << "#define SQ_VALIDB(c, b) sq_ld_bit(inb.val[c], b)\n";
-    s << gen_probe_program(cols, jg->right_keys, jg->probe_pred, jg->jmatch);
+    ProbeProgram pp = gen_probe_program(cols, jg->right_keys, jg->probe_pred, jg->jmatch);
+    s << pp.src;
+    comp->tile_cols = pp.tile_cols;
   }
   s << "#define SQ_NKEYS " << K << "\n#define SQ_NACC " << W << "\n";
   s << "#define SQ_MATCH_KEYS " << (opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY ? 1 : 0) << "\n";
@@ -709,7 +712,14 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
   if (kit == join_kernels_.end()) {
     auto comp = std::make_unique<Compiled>();
     std::string src = generate(pcols, *comp, &jg);
-    JitKernel* k = jit_get("agg_table+join_table+joinagg", src, "sq_joinagg_kernel");
+    JoinKernels k;
+    k.generic = jit_get("agg_table+join_table+joinagg", src, "sq_joinagg_kernel");
+    k.tile_cols = comp->tile_cols;
+    // opt-in (SQLRS_B200_TMA=1): measured 2.1x SLOWER than the register-staged kernel on Q3' (profiles/r01j_*: 632 vs 300 us
+    // at SF10, 7.2 vs 2.6 ms at SF100) — 64 KB of tile ring per CTA cuts the resident warps from 40 to 24 per SM and the
+    // per-tile CTA barrier couples every warp to the slowest phase-B warp, while the register-staged loads of 40 warps
+    // already cover the DRAM latency
+    if (!k.tile_cols.empty() && std::getenv("SQLRS_B200_TMA")) k.tma = jit_get("agg_table+join_table+joinagg", src, "sq_joinagg_tma_kernel");
     if (!cache_.empty()) {
       const Compiled& first = *cache_.begin()->second;
       bool same = first.words.size() == comp->words.size() && first.key_dtypes == comp->key_dtypes;
@@ -737,7 +747,7 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
   uint64_t cap = std::max<uint64_t>(2ULL * (uint64_t)jt.n_build, 1ULL << 16);
   std::unique_ptr<Table> local;
   uint32_t hc[4] = {0, 0, 0, 0};
-  bool first_try = true;
+  bool first_try = true, tma_used = false;
   for (;;) {
     if (cap > (1ULL << 31)) fail(SQLRS_ERR_INTERNAL, "group table would exceed 2^31 slots");
     {
@@ -750,18 +760,40 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
     }
     Trace tr_k("  joinagg.kernel", ctx_.stream);
     SqInBlob in(probe, 0), inb(build, 0);
-    int64_t n_arg = n, rb = row_base, bn = batch_no;
+    int64_t rb = row_base, bn = batch_no;
     void* status = (uint32_t*)local->counters->p + 2;
     void* errp = (uint32_t*)local->counters->p + 3;
     TableView tv = local->view();
     JoinTableView jv = jt;
-    void* args[] = {in.ptr(), inb.ptr(), &n_arg, &rb, &jv, &tv, &bn, &status, &errp};
-    // persistent grid: exactly the CTAs that are resident at once (a ragged second wave cost ~25 % at 5 CTAs / SM)
-    const int per_sm = std::max(1, jit_max_blocks_per_sm(kit->second, 256, 0));
-    unsigned grid = (unsigned)std::min<int64_t>(div_up(n, 2048), (int64_t)device_sm_count(ctx_.device) * per_sm);  // 256 threads x SQ_JUNROLL (8) rows per trip
+    const int sms = device_sm_count(ctx_.device);
+    const JoinKernels& jk = kit->second;
+    // TMA variant: whole 2048-row slices of the probe program's columns are staged in shared memory by bulk-async
+    // copies, double buffered — needs 16-byte aligned column buffers (sliced Arrow arrays may not be)
+    bool use_tma = jk.tma != nullptr && n >= 2048;
+    for (int c : jk.tile_cols)
+      use_tma = use_tma && c < (int)probe.cols.size() && probe.cols[(size_t)c].data && ((uintptr_t)probe.cols[(size_t)c].data % 16 == 0);
     ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
-    jit_launch(kit->second, grid, 256, 0, ctx_.stream, args);
+    int64_t done_rows = 0;
+    if (use_tma) {
+      int64_t n_tiles = n / 2048;
+      const size_t smem = (size_t)2 * jk.tile_cols.size() * 2048 * 8;
+      const int per_sm = std::max(1, jit_max_blocks_per_sm(jk.tma, 256, smem));
+      unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * per_sm);
+      void* args[] = {in.ptr(), inb.ptr(), &n_tiles, &rb, &jv, &tv, &bn, &status, &errp};
+      jit_launch(jk.tma, grid, 256, smem, ctx_.stream, args);
+      done_rows = n_tiles * 2048;
+    }
+    if (done_rows < n) {  // everything, or the ragged tail behind the last full tile
+      SqInBlob in_tail(probe, done_rows);
+      int64_t n_arg = n - done_rows, rb_tail = row_base + done_rows;
+      // persistent grid: exactly the CTAs that are resident at once (a ragged second wave cost ~25 % at 5 CTAs / SM)
+      const int per_sm = std::max(1, jit_max_blocks_per_sm(jk.generic, 256, 0));
+      unsigned grid = (unsigned)std::min<int64_t>(div_up(n_arg, 2048), (int64_t)sms * per_sm);  // 256 threads x SQ_JUNROLL (8) rows per trip
+      void* args[] = {in_tail.ptr(), inb.ptr(), &n_arg, &rb_tail, &jv, &tv, &bn, &status, &errp};
+      jit_launch(jk.generic, grid, 256, 0, ctx_.stream, args);
+    }
     timer.stop();
+    tma_used = use_tma;
     SQ_CUDA(cudaMemcpyAsync(hc, local->counters->p, 16, cudaMemcpyDeviceToHost, ctx_.stream));
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
     scan_kernel_ms_ += timer.elapsed_ms();
@@ -770,7 +802,8 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
     if (!(hc[2] & 2u)) break;
     cap *= 4;
   }
-  last_path_ = "sq_joinagg_kernel (fused probe + aggregate, batch-local table capacity " + std::to_string(local->capacity) + ")";
+  last_path_ = std::string(tma_used ? "sq_joinagg_tma_kernel (TMA-staged probe tiles, " : "sq_joinagg_kernel (") +
+               "fused probe + aggregate, batch-local table capacity " + std::to_string(local->capacity) + ")";
   const bool main_empty = !table_ || (groups_known_ == 0 && !counters_stale_ && groups_bound_ == 0);
   if (main_empty) {
     table_ = std::move(local);  // first batch: its table IS the operator's table

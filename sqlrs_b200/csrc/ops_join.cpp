@@ -1,11 +1,14 @@
 // sqlrs_b200 — HashJoinExecutor on the GPU (see join.hpp; kernels: kernels_join.cu, csrc/jit/eval.cuh).
 #include "join.hpp"
 
+#include <algorithm>
+#include <cstring>
+
 #include "kernels_aot.hpp"
 
 namespace sq {
 
-std::string gen_probe_program(const std::vector<ColInfo>& cols, const std::vector<ExprCopy>& right_keys, const ExprCopy& probe_pred, bool jmatch) {
+ProbeProgram gen_probe_program(const std::vector<ColInfo>& cols, const std::vector<ExprCopy>& right_keys, const ExprCopy& probe_pred, bool jmatch) {
   std::ostringstream s;
   RowProgram p1(cols);
   std::string p1_pass = "true";
@@ -31,7 +34,41 @@ std::string gen_probe_program(const std::vector<ColInfo>& cols, const std::vecto
     jknull += " | (n" + std::to_string(jkeys[k].id) + " ? 0u : " + std::to_string(1u << k) + "u)";
   }
   s << "  p.knull = " << jknull << ";\n}\n";
-  return s.str();
+  ProbeProgram out;
+  // TMA variant: the same statements with the streaming column loads redirected to a shared-memory tile.  Only when
+  // every loaded column is 8 bytes wide (bulk copies of whole 2048-row column slices) and at most 3 are read.
+  const std::string body = p1.body_str();
+  std::vector<int> tile_cols;
+  bool ok = body.find("SQ_LD_I32(") == std::string::npos && body.find("SQ_LD_BOOL(") == std::string::npos;
+  for (const char* macro : {"SQ_LD_I64(", "SQ_LD_F64("}) {
+    for (size_t pos = body.find(macro); ok && pos != std::string::npos; pos = body.find(macro, pos + 1)) {
+      const int c = atoi(body.c_str() + pos + strlen(macro));
+      if (std::find(tile_cols.begin(), tile_cols.end(), c) == tile_cols.end()) tile_cols.push_back(c);
+    }
+  }
+  if (ok && !tile_cols.empty() && tile_cols.size() <= 3) {
+    std::string tb = body;
+    auto replace_all = [&](const std::string& from, const std::string& to) {
+      for (size_t pos = tb.find(from); pos != std::string::npos; pos = tb.find(from, pos + to.size())) tb.replace(pos, from.size(), to);
+    };
+    for (size_t k = 0; k < tile_cols.size(); k++) {
+      const std::string c = std::to_string(tile_cols[k]), at = "tile[" + std::to_string(k) + " * SQ_TROWS + t]";
+      replace_all("SQ_LD_I64(" + c + ", r)", "((long long)" + at + ")");
+      replace_all("SQ_LD_F64(" + c + ", r)", "__longlong_as_double((long long)" + at + ")");
+    }
+    s << "#define SQ_TMA 1\n#define SQ_TROWS 2048\n#define SQ_TILE_NCOLS " << tile_cols.size() << "\n#define SQ_TILE_COLS {";
+    for (size_t k = 0; k < tile_cols.size(); k++) s << (k ? ", " : "") << tile_cols[k];
+    s << "}\n";
+    s << "__device__ __forceinline__ void sq_probe_row_tile(const SqIn& in, const u64* __restrict__ tile, int t, i64 r, SqProbe& p, bool& e0, bool& e1) {\n" << tb;
+    s << "  p.pass = " << p1_pass << ";\n  p.h = v" << jh << ";\n";
+    for (int k = 0; k < JK; k++) s << "  p.kb[" << k << "] = v" << jraw[k] << ";\n";
+    s << "  p.knull = " << jknull << ";\n}\n";
+    out.tile_cols = tile_cols;
+  } else {
+    s << "#define SQ_TMA 0\n";
+  }
+  out.src = s.str();
+  return out;
 }
 
 struct JoinOp::Impl {
@@ -225,7 +262,7 @@ void JoinOp::seal() {
 }
 
 std::string JoinOp::debug_probe_source(const std::vector<ColInfo>& probe_cols, const ExprCopy& probe_pred) const {
-  return gen_input_decls(probe_cols) + gen_probe_program(probe_cols, right_keys_, probe_pred, match_keys());
+  return gen_input_decls(probe_cols) + gen_probe_program(probe_cols, right_keys_, probe_pred, match_keys()).src;
 }
 
 bool JoinOp::empty_build() const { return impl_->capacity == 0; }
@@ -295,7 +332,7 @@ bool JoinOp::probe(const DBatch& right, DBatch* result) {
     const std::string sig = RowProgram(pcols).signature();
     auto kit = im.probe_kernels.find(sig);
     if (kit == im.probe_kernels.end()) {
-      const std::string src = gen_input_decls(pcols) + gen_probe_program(pcols, right_keys_, im.probe_pred, mk);
+      const std::string src = gen_input_decls(pcols) + gen_probe_program(pcols, right_keys_, im.probe_pred, mk).src;
       kit = im.probe_kernels.emplace(sig, jit_get("join_table+joinprobe", src, "sq_joinprobe_kernel")).first;
     }
     const int64_t chunks = div_up(n, kProbeChunk);

@@ -106,6 +106,30 @@ class TorchGroup:
         dist.all_gather(bufs, send)
         return [bufs[r][:sz[r]].cpu().numpy().tobytes() for r in range(W)]
 
+    def gather_small(self, payload: bytes, dst: int = 0, cap: int = 8192) -> Optional[List[bytes]]:
+        """gather_bytes for payloads known to be small (a LIMIT's worth of rows): ONE fixed-size all-gather
+        [u32 length | payload | padding] instead of a size exchange + a data exchange."""
+        import struct
+
+        torch, dist, W = self.torch, self.dist, self.world
+        if len(payload) + 4 > cap:
+            # rare: tell every rank to take the two-phase path (length prefix 0xffffffff)
+            framed = struct.pack("<I", 0xFFFFFFFF)
+        else:
+            framed = struct.pack("<I", len(payload)) + payload
+        send = torch.zeros(cap, dtype=torch.uint8)
+        send[:len(framed)] = torch.frombuffer(bytearray(framed), dtype=torch.uint8)
+        send = send.to(self.device, non_blocking=True)
+        recv = torch.empty(cap * W, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(recv, send) if self.native_a2a else dist.all_gather(list(recv.view(W, cap).unbind(0)), send)
+        data = recv.cpu().numpy().tobytes()
+        lens = [struct.unpack_from("<I", data, r * cap)[0] for r in range(W)]
+        if any(n == 0xFFFFFFFF for n in lens):
+            return self.gather_bytes(payload, dst)
+        if self.rank != dst:
+            return None
+        return [data[r * cap + 4:r * cap + 4 + lens[r]] for r in range(W)]
+
     def gather_bytes(self, payload: bytes, dst: int = 0) -> Optional[List[bytes]]:
         torch, dist, W = self.torch, self.dist, self.world
         size = torch.tensor([len(payload)], dtype=torch.int64, device=self.device)
@@ -262,17 +286,30 @@ def copartitioned_topk(plan, group: "TorchGroup", order_by, limit: int, offset: 
     locally (no collective on the data path), the <= offset+limit local rows are gathered on rank 0, which orders
     them again with the library's own Order / Limit operators.  `order_by`: BoundOrderBy list over the plan's OUTPUT
     columns.  Ties between ranks resolve in rank order = global row order, as in the single-process run."""
+    import os
+    import time
+
     from . import executor as ex
 
+    trace = os.environ.get("SQLRS_B200_DIST_TRACE") == "1"
+    t0 = time.perf_counter()
     local = plan.run()
+    t1 = time.perf_counter()
     schema = local[0].schema if local else None
     table = pa.Table.from_batches(local).combine_chunks() if local else None
     payload = _to_bytes(table.to_batches()[0]) if table is not None and table.num_rows else b""
-    gathered = group.gather_bytes(payload, dst=0)
+    gathered = group.gather_small(payload, dst=0)
+    t2 = time.perf_counter()
     if gathered is None:
+        if trace:
+            print(f"[dist trace] rank {group.rank}: local plan {1e3 * (t1 - t0):.3f} ms, gather {1e3 * (t2 - t1):.3f} ms", flush=True)
         return []
     batches = [_from_bytes(data) for data in gathered if data]
     if not batches:
         return [pa.RecordBatch.from_pylist([], schema=schema)] if schema is not None else []
     ordered = ex.OrderExecutor(order_by, batches, lib=plan.lib, options=plan.options).execute()
-    return ex.try_collect(ex.LimitExecutor(limit, offset, ordered, lib=plan.lib, options=plan.options).execute())
+    out = ex.try_collect(ex.LimitExecutor(limit, offset, ordered, lib=plan.lib, options=plan.options).execute())
+    if trace:
+        print(f"[dist trace] rank {group.rank}: local plan {1e3 * (t1 - t0):.3f} ms, gather {1e3 * (t2 - t1):.3f} ms, merge {1e3 * (time.perf_counter() - t2):.3f} ms",
+              flush=True)
+    return out

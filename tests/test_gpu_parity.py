@@ -662,3 +662,22 @@ def test_plan_order_limit_over_join_and_filter(cuda_lib, oracle):
                 exp, _ = _run_plan(oracle, plan, schemas, tables, batch_rows, match_mode=ffi.MATCH_HASH_AND_KEY)
                 assert sum(b.num_rows for b in got) > 0
                 assert_batches_match(got, exp, rtol=FTOL)
+
+
+def test_q3_tma_staged_probe_variant(cuda_lib, oracle, monkeypatch):
+    """the opt-in TMA variant of the fused probe + aggregate kernel (cp.async.bulk tiles + mbarrier ring, SQLRS_B200_TMA=1)
+    gives the same groups; a sliced (16-byte misaligned) probe table silently takes the register-staged kernel"""
+    monkeypatch.setenv("SQLRS_B200_TMA", "1")
+    d = tpch.dims(0.05)
+    plan, schemas = tpch.q3_plan()
+    tables = _tables(oracle, d)
+    mode = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    exp, _ = _run_plan(oracle, plan, schemas, tables, None, **mode)
+    got, desc = _run_plan(cuda_lib, plan, schemas, tables, None, **mode)
+    assert_batches_match(got, exp, rtol=FTOL)
+    assert "sq_joinagg_tma_kernel" in desc or desc.startswith("oracle")
+    sliced = dict(tables)
+    sliced[2] = tables[2].slice(1)  # 8-byte offset into every column buffer
+    exp2, _ = _run_plan(oracle, plan, schemas, sliced, None, **mode)
+    got2, desc2 = _run_plan(cuda_lib, plan, schemas, sliced, None, **mode)
+    assert_batches_match(got2, exp2, rtol=FTOL)
