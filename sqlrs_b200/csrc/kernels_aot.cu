@@ -247,6 +247,18 @@ __global__ void __launch_bounds__(kBlock) k_table_list(TableView t, uint64_t* __
   }
 }
 
+// the same from a complete list of the occupied slots (tables filled by one fused probe+aggregate kernel keep one):
+// n entries instead of a scan over the whole capacity
+__global__ void __launch_bounds__(kBlock) k_table_list_from_slots(TableView t, const uint32_t* __restrict__ slot_list, uint32_t n,
+                                                                   uint64_t* __restrict__ min_rows, uint32_t* __restrict__ slots) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t s = slot_list[i];
+    min_rows[i] = t.min_row[s];
+    slots[i] = s;
+  }
+}
+
 // packed rows in the given slot order (first-appearance order after the sort); header written by thread 0
 __global__ void __launch_bounds__(kBlock) k_table_pack_ordered(TableView t, int n_keys, int n_acc, const uint32_t* __restrict__ slots, uint32_t n,
                                                                 uint64_t* __restrict__ dst) {
@@ -461,7 +473,8 @@ void launch_table_pack(const TableView& t, int n_keys, int n_acc, uint64_t* dst,
 
 // the n groups of `t` packed in ascending first-row order (= the reference's first-appearance order):
 // list occupied slots -> radix sort by min_row (CUB, a library sort of n small keys) -> ordered pack
-void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, uint64_t* dst, cudaStream_t stream) {
+void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, uint64_t* dst, cudaStream_t stream, const uint32_t* slot_list,
+                       int key_bits) {
   if (n == 0) return;
   uint64_t *k_in = nullptr, *k_out = nullptr;
   uint32_t *v_in = nullptr, *v_out = nullptr, *count = nullptr;
@@ -471,14 +484,16 @@ void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, ui
   v_out = (decltype(v_out))scratch_alloc((size_t)n * 4, stream);
   count = (decltype(count))scratch_alloc(4, stream);
   SQ_CUDA(cudaMemsetAsync(count, 0, 4, stream));
-  k_table_list<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, k_in, v_in, n, count);
+  if (slot_list) k_table_list_from_slots<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(t, slot_list, n, k_in, v_in);
+  else k_table_list<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, k_in, v_in, n, count);
   count_launch();
+  if (key_bits < 1 || key_bits > 64) key_bits = 64;
   size_t tmp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, 64, stream);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, key_bits, stream);
   void* tmp = nullptr;
   tmp = (decltype(tmp))scratch_alloc(tmp_bytes ? tmp_bytes : 16, stream);
-  SQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, 64, stream));
-  count_launch(8);
+  SQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, key_bits, stream));
+  count_launch(2 + (key_bits + 7) / 8);
   k_table_pack_ordered<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, v_out, n, dst);
   count_launch();
   SQ_CUDA(cudaGetLastError());

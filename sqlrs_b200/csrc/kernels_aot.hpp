@@ -50,7 +50,10 @@ struct TableView {
 // dst must hold (cap_rows + 1) rows and have its header zeroed; groups beyond cap_rows are counted, not written.
 void launch_table_pack(const TableView& t, int n_keys, int n_acc, uint64_t* dst, uint64_t cap_rows, cudaStream_t stream);
 // the n groups packed in ascending first-row order (dst: (n + 1) rows; header written)
-void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, uint64_t* dst, cudaStream_t stream);
+// slot_list (optional): a complete device list of the n occupied slots — skips the scan over the capacity;
+// key_bits: number of significant bits of the min_row keys (fewer radix passes)
+void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, uint64_t* dst, cudaStream_t stream,
+                       const uint32_t* slot_list = nullptr, int key_bits = 64);
 // partial -> final merge of n_bufs packed buffers ((cap_rows + 1) rows each) into `t`; ops[w] (device):
 // 0 add u64, 1 add f64, 2 min i64, 3 max i64, 4 (epoch << 40 | count): later epoch wins, equal epochs add
 void launch_table_merge_packed(const TableView& t, int n_keys, int n_acc, const int* ops, int match_keys, const uint64_t* src, int n_bufs,
@@ -98,7 +101,10 @@ void launch_scan_u32_large(const uint32_t* counts, int64_t m, unsigned long long
                            unsigned long long* scratch /* >= ceil(m/4096)+1 */, cudaStream_t stream);
 size_t scan_scratch_entries(int64_t m);
 
-void launch_join_insert(const JoinTableView& t, int32_t* row_slot, uint32_t* max_count, cudaStream_t stream);
+// inserts the distinct keys (slot_rep, Bloom filter, row_slot); *has_dups = 1 when some key occurred more than once
+void launch_join_insert(const JoinTableView& t, int32_t* row_slot, uint32_t* has_dups, cudaStream_t stream);
+// (only then) rows per slot into t.slot_count (zero-initialised) and the largest count into *max_count
+void launch_join_count(const JoinTableView& t, const int32_t* row_slot, uint32_t* max_count, cudaStream_t stream);
 void launch_join_fill(const JoinTableView& t, const int32_t* row_slot, uint32_t* slot_fill, cudaStream_t stream);
 void launch_join_sort_ranges(const JoinTableView& t, cudaStream_t stream);
 // stable fallback for heavily duplicated keys: rows = build row ids sorted by (slot, row id)

@@ -39,10 +39,12 @@ __device__ __forceinline__ bool same_key(const JoinTableView& t, int64_t b, uint
 // rows at a time and issues each level of the chain for all of them before it waits (measured with one row at a
 // time: 88 long-scoreboard stall cycles per issued instruction, 10 % issue utilisation).
 constexpr int kInsertBatch = 4;
-__global__ void __launch_bounds__(kBlock) k_join_insert(JoinTableView t, int32_t* __restrict__ row_slot, uint32_t* __restrict__ max_count) {
+// Inserts do not count rows per key: they only flag (*has_dups) that some key occurred twice — the common build side is a
+// primary key, for which neither per-slot counts nor the CSR row lists are ever needed (k_join_count runs otherwise).
+__global__ void __launch_bounds__(kBlock) k_join_insert(JoinTableView t, int32_t* __restrict__ row_slot, uint32_t* __restrict__ has_dups) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const uint32_t mask = t.capacity - 1;
-  uint32_t local_max = 0;
+  bool dup = false;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < t.n_build; base += stride * kInsertBatch) {
     int64_t i[kInsertBatch];
     bool live[kInsertBatch];
@@ -75,15 +77,30 @@ __global__ void __launch_bounds__(kBlock) k_join_insert(JoinTableView t, int32_t
           const long long old = (long long)atomicCAS((unsigned long long*)&t.slot_rep[slot], (unsigned long long)-1LL, (unsigned long long)i[u]);
           r = old < 0 ? i[u] : old;
         }
-        if (r == i[u] || same_key(t, r, h[u], t.keys, t.n_build, i[u])) break;
+        if (r == i[u]) break;
+        if (same_key(t, r, h[u], t.keys, t.n_build, i[u])) {
+          dup = true;
+          break;
+        }
         slot = (slot + 1) & mask;
         r = *((volatile long long*)&t.slot_rep[slot]);
       }
       row_slot[i[u]] = (int32_t)slot;
       if (t.bloom) atomicOr((unsigned long long*)&t.bloom[join_bloom_word(h[u], t.bloom_mask)], (unsigned long long)join_bloom_bits(h[u]));
-      const uint32_t c = atomicAdd(&t.slot_count[slot], 1u) + 1u;
-      local_max = c > local_max ? c : local_max;
     }
+  }
+  if (__any_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) *has_dups = 1u;
+}
+
+// only when some key repeats: rows per slot and the largest such count
+__global__ void __launch_bounds__(kBlock) k_join_count(JoinTableView t, const int32_t* __restrict__ row_slot, uint32_t* __restrict__ max_count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  uint32_t local_max = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.n_build; i += stride) {
+    const int32_t s = row_slot[i];
+    if (s < 0) continue;
+    const uint32_t c = atomicAdd(&t.slot_count[s], 1u) + 1u;
+    local_max = c > local_max ? c : local_max;
   }
   for (int d = 16; d > 0; d >>= 1) {
     const uint32_t o = __shfl_xor_sync(0xffffffffu, local_max, d);
@@ -384,9 +401,14 @@ void launch_scan_u32_large(const uint32_t* counts, int64_t m, unsigned long long
   SQ_LAUNCH_CHECK();
 }
 
-void launch_join_insert(const JoinTableView& t, int32_t* row_slot, uint32_t* max_count, cudaStream_t stream) {
+void launch_join_insert(const JoinTableView& t, int32_t* row_slot, uint32_t* has_dups, cudaStream_t stream) {
   if (t.n_build <= 0) return;
-  k_join_insert<<<grid_for(div_up(t.n_build, kInsertBatch), kBlock, 148 * 32), kBlock, 0, stream>>>(t, row_slot, max_count);
+  k_join_insert<<<grid_for(div_up(t.n_build, kInsertBatch), kBlock, 148 * 32), kBlock, 0, stream>>>(t, row_slot, has_dups);
+  SQ_LAUNCH_CHECK();
+}
+void launch_join_count(const JoinTableView& t, const int32_t* row_slot, uint32_t* max_count, cudaStream_t stream) {
+  if (t.n_build <= 0) return;
+  k_join_count<<<grid_for(t.n_build, kBlock), kBlock, 0, stream>>>(t, row_slot, max_count);
   SQ_LAUNCH_CHECK();
 }
 void launch_join_fill(const JoinTableView& t, const int32_t* row_slot, uint32_t* slot_fill, cudaStream_t stream) {

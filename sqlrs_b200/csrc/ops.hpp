@@ -135,6 +135,7 @@ class AggOp {
   void ensure_table(uint32_t min_capacity);
   void grow_table(uint32_t min_capacity);
   void build_output(std::vector<Field>* fields, struct HostGroups* groups);
+  void pack_sorted(int K, int W, uint32_t n, uint64_t* dst);
 
   Ctx ctx_;
   Options opt_;
@@ -157,6 +158,8 @@ class AggOp {
   uint32_t groups_known_ = 0;   // exact group count at the last counter read
   uint64_t groups_bound_ = 0;   // host-side upper bound since then
   bool counters_stale_ = false; // device work since the last counter read may have added groups
+  bool slot_list_complete_ = false;  // table_->new_slots[0 .. groups_known_) lists every occupied slot (table adopted from one
+                                     // fused probe+aggregate launch, untouched since): finalisation need not scan the capacity
   uint64_t* pinned_ = nullptr;  // pinned host staging of the packed result
   size_t pinned_words_ = 0;
   size_t part_entries_ = 0;     // CTA-partial scratch of sq_agg_small

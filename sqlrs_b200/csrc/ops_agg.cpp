@@ -484,6 +484,7 @@ std::unique_ptr<AggOp::Table> AggOp::new_table(uint32_t capacity) {
 }
 
 void AggOp::grow_table(uint32_t min_capacity) {
+  slot_list_complete_ = false;
   const Compiled& c = *cache_.begin()->second;
   auto t = std::make_unique<Table>();
   t->capacity = next_pow2(min_capacity);
@@ -511,6 +512,7 @@ void AggOp::grow_table(uint32_t min_capacity) {
 // forget all groups but keep the compiled kernels and the device buffers (repeated plan runs)
 void AggOp::reset() {
   ctx_.activate();
+  slot_list_complete_ = false;
   if (table_) init_table_contents(*table_);
   rows_seen_ = 0;
   batches_seen_ = 0;
@@ -552,6 +554,7 @@ void AggOp::ensure_partial_scratch(size_t entries, int K, size_t W) {
 // ------------------------------------------------------------------ push
 void AggOp::push(const DBatch& batch) {
   Trace tr("agg.push", ctx_.stream);
+  slot_list_complete_ = false;
   ctx_.activate();
   ctx_.reap();
   Compiled& c = compiled_for(batch);
@@ -811,6 +814,7 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
     groups_known_ = hc[0];
     groups_bound_ = hc[0];
     counters_stale_ = false;
+    slot_list_complete_ = hc[1] == hc[0];  // every group of this launch was appended to new_slots (the list itself stays in place)
     return;
   }
   if (hc[0] == 0) return;
@@ -823,6 +827,18 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
 }
 
 // ------------------------------------------------------------------ finish
+// the n groups packed in first-appearance order; a table straight out of one fused probe+aggregate launch still has the
+// complete list of its slots, and its order keys are (probe row << 20 | match ordinal) < rows_seen_ << 20
+void AggOp::pack_sorted(int K, int W, uint32_t n, uint64_t* dst) {
+  if (slot_list_complete_) {
+    int bits = 21;
+    for (int64_t r = rows_seen_; r > 0; r >>= 1) bits++;
+    table_pack_sorted(table_->view(), K, W, n, dst, ctx_.stream, (const uint32_t*)table_->new_slots->p, std::min(bits, 64));
+  } else {
+    table_pack_sorted(table_->view(), K, W, n, dst, ctx_.stream);
+  }
+}
+
 // the group table -> host, through ONE packed buffer and one synchronisation
 void AggOp::build_output(std::vector<Field>* fields, HostGroups* g) {
   if (!seen_batch_) fail(SQLRS_ERR_INTERNAL, "called `Option::unwrap()` on a `None` value (no input batch)");
@@ -841,7 +857,7 @@ void AggOp::build_output(std::vector<Field>* fields, HostGroups* g) {
     const int words = 3 + K + W;
     BufPtr packed = dev_alloc(ctx_, (size_t)(n + 1) * words * 8);
     SQ_CUDA(cudaMemsetAsync(packed->p, 0, (size_t)words * 8, ctx_.stream));
-    if (n > 256 && !counters_stale_) table_pack_sorted(table_->view(), K, W, n, (uint64_t*)packed->p, ctx_.stream);  // ordered on the device
+    if (n > 256 && !counters_stale_) pack_sorted(K, W, n, (uint64_t*)packed->p);  // ordered on the device
     else launch_table_pack(table_->view(), K, W, (uint64_t*)packed->p, n, ctx_.stream);                              // few groups: the host sorts
     const size_t host_words = (size_t)(n + 1) * words;
     if (pinned_words_ < host_words) {  // pinned staging, kept across runs: the D2H runs at PCIe speed
@@ -1013,7 +1029,8 @@ DBatch AggOp::finish_device() {
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));  // `host` is a stack vector
   } else if (n > 0) {
     SQ_CUDA(cudaMemsetAsync(packed->p, 0, (size_t)words * 8, ctx_.stream));
-    table_pack_sorted(table_->view(), K, W, n, (uint64_t*)packed->p, ctx_.stream);  // first-appearance order (hash_agg.rs:98,134)
+    // first-appearance order (hash_agg.rs:98,134)
+    pack_sorted(K, W, n, (uint64_t*)packed->p);
   }
   DBatch out;
   out.n = rows;
@@ -1125,6 +1142,7 @@ void AggOp::export_partials_device(uint64_t* dst, int64_t cap_rows) {
 
 void AggOp::clear_partials() {
   ctx_.activate();
+  slot_list_complete_ = false;
   if (table_) init_table_contents(*table_);
   level_ = 0;
   groups_known_ = 0;
@@ -1157,6 +1175,7 @@ const int* AggOp::device_word_ops() {
 // folds n_bufs packed partial buffers (device memory, layout of export_partials_device) into the table
 void AggOp::merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows, bool sync_after) {
   ctx_.activate();
+  slot_list_complete_ = false;
   if (cache_.empty()) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before any batch was aggregated (accumulator layout unknown)");
   seen_batch_ = true;
   if (n_bufs <= 0 || cap_rows <= 0) return;

@@ -201,18 +201,28 @@ void JoinOp::seal() {
   im.left_key_parts.clear();
   im.left_keep_parts.clear();
 
-  // table: capacity >= 2 x build rows
+  // table: capacity >= 2 x the build rows that can be inserted.  With a Filter fused below the build side that is the
+  // number of kept rows (one bit count + sync): Q3's customer table shrinks 5x, which is what keeps it L2-resident
+  // under the probe scan
+  int64_t n_insert = n;
+  if (!im.build_pred.empty() && n > 0) {
+    BufPtr cnt = dev_alloc_zero(ctx_, 8);
+    launch_count_bits((const uint32_t*)im.keep_all.data, n, (unsigned long long*)cnt->p, ctx_.stream);
+    unsigned long long kept = 0;
+    SQ_CUDA(cudaMemcpyAsync(&kept, cnt->p, 8, cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    n_insert = (int64_t)kept;
+  }
   uint64_t cap = 1024;
-  while (cap < 2ULL * (uint64_t)n) cap <<= 1;
+  while (cap < 2ULL * (uint64_t)n_insert) cap <<= 1;
   if (cap > (1ULL << 30)) fail(SQLRS_ERR_UNSUPPORTED, "join build side too large for one table (> 2^29 rows)");
   im.capacity = (uint32_t)cap;
   im.slot_rep = dev_alloc(ctx_, cap * 8);
   SQ_CUDA(cudaMemsetAsync(im.slot_rep->p, 0xff, cap * 8, ctx_.stream));
-  im.slot_count = dev_alloc_zero(ctx_, cap * 4);
   JoinTableView& v = im.view;
   v.slot_rep = (int64_t*)im.slot_rep->p;
-  v.slot_count = (uint32_t*)im.slot_count->p;
-  v.slot_start = nullptr;  // the CSR row lists are only built when some key repeats (below)
+  v.slot_count = nullptr;  // per-slot counts and the CSR row lists are only built when some key repeats (below)
+  v.slot_start = nullptr;
   v.rows = nullptr;
   v.unique = 1;
   v.capacity = im.capacity;
@@ -223,39 +233,42 @@ void JoinOp::seal() {
   v.n_keys = K;
   v.match_keys = mk ? 1 : 0;
   v.build_keep = im.build_pred.empty() ? nullptr : (const uint32_t*)im.keep_all.data;
-  const uint32_t bloom_words = join_bloom_words(n);
+  const uint32_t bloom_words = join_bloom_words(n_insert);
   im.bloom = dev_alloc_zero(ctx_, (size_t)bloom_words * 8);
   v.bloom = (uint64_t*)im.bloom->p;
   v.bloom_mask = bloom_words - 1;
+  im.max_count = n_insert > 0 ? 1 : 0;
   if (n > 0) {
     BufPtr row_slot = dev_alloc(ctx_, (size_t)n * 4);
-    BufPtr misc = dev_alloc_zero(ctx_, 16);  // [0] max count, [8] total
+    BufPtr misc = dev_alloc_zero(ctx_, 16);  // [0] has duplicates, [4] max count, [8] total
     launch_join_insert(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
-    uint32_t max_count = 0;
-    SQ_CUDA(cudaMemcpyAsync(&max_count, misc->p, 4, cudaMemcpyDeviceToHost, ctx_.stream));
+    uint32_t has_dups = 0;
+    SQ_CUDA(cudaMemcpyAsync(&has_dups, misc->p, 4, cudaMemcpyDeviceToHost, ctx_.stream));
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
-    im.max_count = max_count;
-    if (max_count <= 1) {
-      // unique build keys (a primary-key side, e.g. both Q3' joins): the slot's representative row is its whole
-      // match list — no per-slot ranges, no scan over the table, no fill pass
-    } else {
+    if (has_dups) {
+      // some key repeats: rows per slot, CSR ranges, ascending row ids per range
       v.unique = 0;
+      im.slot_count = dev_alloc_zero(ctx_, cap * 4);
       im.slot_start = dev_alloc(ctx_, cap * 8);
       im.rows = dev_alloc(ctx_, (size_t)n * 8);
+      v.slot_count = (uint32_t*)im.slot_count->p;
       v.slot_start = (uint64_t*)im.slot_start->p;
       v.rows = (int64_t*)im.rows->p;
+      launch_join_count(v, (const int32_t*)row_slot->p, (uint32_t*)misc->p + 1, ctx_.stream);
       BufPtr scratch = dev_alloc(ctx_, scan_scratch_entries((int64_t)cap) * 8);
       launch_scan_u32_large(v.slot_count, (int64_t)cap, (unsigned long long*)v.slot_start, (unsigned long long*)misc->p + 1,
                             (unsigned long long*)scratch->p, ctx_.stream);
-    }
-    if (max_count <= 1) {
-      // nothing to fill
-    } else if (max_count <= 64) {
-      BufPtr fill = dev_alloc_zero(ctx_, cap * 4);
-      launch_join_fill(v, (const int32_t*)row_slot->p, (uint32_t*)fill->p, ctx_.stream);
-      if (max_count > 1) launch_join_sort_ranges(v, ctx_.stream);
-    } else {
-      join_fill_sorted(v, (const int32_t*)row_slot->p, ctx_.stream);
+      uint32_t max_count = 0;
+      SQ_CUDA(cudaMemcpyAsync(&max_count, (uint32_t*)misc->p + 1, 4, cudaMemcpyDeviceToHost, ctx_.stream));
+      SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+      im.max_count = max_count;
+      if (max_count <= 64) {
+        BufPtr fill = dev_alloc_zero(ctx_, cap * 4);
+        launch_join_fill(v, (const int32_t*)row_slot->p, (uint32_t*)fill->p, ctx_.stream);
+        launch_join_sort_ranges(v, ctx_.stream);
+      } else {
+        join_fill_sorted(v, (const int32_t*)row_slot->p, ctx_.stream);
+      }
     }
   }
   if (join_type_ == SQLRS_JOIN_LEFT || join_type_ == SQLRS_JOIN_FULL) im.visited_left = dev_alloc_zero(ctx_, (size_t)bitmap_words(n) * 4 + 4);
