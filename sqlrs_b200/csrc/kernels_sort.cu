@@ -111,6 +111,43 @@ __global__ void __launch_bounds__(kBlock) k_finalize_groups(const uint64_t* __re
   }
 }
 
+// small inputs (an aggregate's few groups, the per-rank rows of a distributed top-k merge): ONE launch instead of a dozen —
+// a single CTA ranks every row against all others, rank = #{j : (flag_j, key_j, j) < (flag_i, key_i, i)}, which is the
+// stable NULLs-first order of the radix path below
+constexpr int kSmallSort = 2048;
+__global__ void __launch_bounds__(1024) k_sort_pass_small(int dtype, const void* __restrict__ data, const uint32_t* __restrict__ valid,
+                                                          uint32_t* __restrict__ perm, int n, int descending, int reverse_nulls) {
+  __shared__ uint64_t key_s[kSmallSort];
+  __shared__ uint32_t row_s[kSmallSort];
+  __shared__ uint8_t flag_s[kSmallSort];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t r = perm[i];
+    const bool is_null = dtype == SQLRS_DT_NULL || (valid && !bit_at(valid, r));
+    uint64_t k;
+    if (is_null) {
+      k = reverse_nulls ? (uint64_t)(n - 1) - r : 0ULL;
+    } else {
+      k = sort_image(dtype, data, r);
+      if (descending) k = ~k;
+    }
+    key_s[i] = k;
+    row_s[i] = (uint32_t)r;
+    flag_s[i] = is_null ? 0 : 1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t k = key_s[i];
+    const uint8_t f = flag_s[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+      const uint64_t kj = key_s[j];
+      const uint8_t fj = flag_s[j];
+      rank += (fj < f) || (fj == f && (kj < k || (kj == k && j < i)));
+    }
+    perm[rank] = row_s[i];
+  }
+}
+
 template <typename K>
 void stable_sort_pairs(K* k_in, K* k_out, uint32_t* v_in, uint32_t* v_out, int64_t n, int end_bit, cudaStream_t stream) {
   size_t tmp_bytes = 0;
@@ -137,6 +174,12 @@ void sort_pass(int dtype, const void* data, const uint32_t* valid, int64_t n, bo
                cudaStream_t stream) {
   if (n <= 1) return;
   if (n >= (1LL << 31)) fail(SQLRS_ERR_UNSUPPORTED, "Order: more than 2^31 rows in one sort");
+  if (n <= kSmallSort) {
+    k_sort_pass_small<<<1, 1024, 0, stream>>>(dtype, data, valid, perm, (int)n, descending ? 1 : 0, reverse_nulls ? 1 : 0);
+    count_launch();
+    SQ_CUDA(cudaGetLastError());
+    return;
+  }
   uint64_t *k_in = nullptr, *k_out = nullptr;
   uint32_t *p_out = nullptr;
   k_in = (decltype(k_in))scratch_alloc((size_t)n * 8, stream);
