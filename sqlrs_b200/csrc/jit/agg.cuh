@@ -26,11 +26,11 @@
 // ------------------------------------------------------------------------------------------
 // shared-memory layout of sq_agg_small
 //   u64 acc[(W+1)][S][T]   private accumulators, word W = min row id
-//   CTA-shared slot table with SQ_TSLOTS = 4*S entries (load factor <= 1/4, so a lookup is almost
-//   always one probe): u64 thash[TS]; u64 tkeys[TS][K]; u32 tknull[TS]; u32 tstate[TS]; u32 tgroup[TS]
+//   CTA-shared slot table with SQ_TSLOTS = 8*S entries (load factor <= 1/8) probed through a branch-free
+//   two-slot window: u64 thash[TS]; u64 tkeys[TS][K]; u32 tknull[TS]; u32 tstate[TS]; u32 tgroup[TS]
 //   u32 ngroups; u32 flags
 #define SQ_ACC_WORDS (SQ_NACC + 1)
-#define SQ_TSLOTS (4 * SQ_SLOTS)
+#define SQ_TSLOTS (8 * SQ_SLOTS)
 
 struct SqSlotTable {
   u64* thash;
@@ -64,13 +64,27 @@ __device__ __forceinline__ bool sq_small_same(const SqSlotTable& t, u32 s, const
 #endif
 }
 
+// The first TWO slots of the probe sequence are examined without a data-dependent branch (state + hash tag of both,
+// then ONE full key comparison at the selected slot), so a key displaced by one position costs exactly what a key in its
+// home slot costs.  Measured reason: with one-slot probing the Q1' kernel swung between 6.4 and 9.1 ms at SF100
+// depending on whether the 8 group keys happened to land in 8 distinct home slots (a change of the placement hash
+// exposed it) — every divergent extra probe is paid by the whole warp.  Longer chains (rare at load <= 1/8) continue
+// in the loop.
 template <int TS, typename R>
 __device__ __forceinline__ int sq_small_find(const SqSlotTable& t, const R& o) {
 #if SQ_NKEYS == 0
   return 0;
 #else
-  u32 s = sq_mix32(o.h) & (TS - 1);
-  for (int probes = 0; probes < TS; probes++) {
+  const u32 s0 = sq_mix32(o.h) & (TS - 1), s1 = (s0 + 1) & (TS - 1);
+  const bool pub0 = *((volatile u32*)&t.tstate[s0]) == 2u, pub1 = *((volatile u32*)&t.tstate[s1]) == 2u;
+  const bool tag0 = pub0 && *((volatile u64*)&t.thash[s0]) == o.h;
+  const bool tag1 = pub0 && pub1 && *((volatile u64*)&t.thash[s1]) == o.h;
+  const u32 sel = tag0 ? s0 : s1;
+  if ((tag0 || tag1) && sq_small_same(t, sel, o)) return (int)*((volatile u32*)&t.tgroup[sel]);
+  if (!pub0 || !pub1) return -1;  // the chain ends inside the window: not published (yet)
+  if (tag0 && tag1 && sq_small_same(t, s1, o)) return (int)*((volatile u32*)&t.tgroup[s1]);  // equal hashes, different keys
+  u32 s = (s1 + 1) & (TS - 1);
+  for (int probes = 2; probes < TS; probes++) {
     if (*((volatile u32*)&t.tstate[s]) != 2u) return -1;  // empty or being written: not published (yet)
     if (sq_small_same(t, s, o)) return (int)*((volatile u32*)&t.tgroup[s]);
     s = (s + 1) & (TS - 1);

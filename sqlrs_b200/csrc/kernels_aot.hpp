@@ -109,11 +109,6 @@ void launch_join_fill(const JoinTableView& t, const int32_t* row_slot, uint32_t*
 void launch_join_sort_ranges(const JoinTableView& t, cudaStream_t stream);
 // stable fallback for heavily duplicated keys: rows = build row ids sorted by (slot, row id)
 void join_fill_sorted(const JoinTableView& t, const int32_t* row_slot, cudaStream_t stream);
-// probe_keep: optional bitmap of probe rows that pass the Filter fused below the join (others produce nothing)
-void launch_join_probe_count(const JoinTableView& t, const uint64_t* ph, const uint64_t* pkeys, const uint32_t* pknull, const uint32_t* probe_keep,
-                             int64_t n_probe, int keep_unmatched, int32_t* slot_of, uint32_t* out_count, cudaStream_t stream);
-void launch_join_probe_write(const JoinTableView& t, const int32_t* slot_of, const unsigned long long* offsets, int64_t n_probe,
-                             int keep_unmatched, int64_t* li, uint32_t* ri, cudaStream_t stream);
 // fused probe path (csrc/jit/joinprobe.cuh): slot_of[r] (>= 0 slot, -1 kept but unmatched, -2 dropped by the fused Filter)
 // + exclusive offsets of the 2048-row chunks -> (build row, probe row) pairs in the reference's order
 constexpr int kProbeChunk = 2048;

@@ -1,9 +1,10 @@
 // sqlrs_b200 — hash join build / probe kernels for sm_100a (reference src/executor/join/hash_join.rs).
 // Build (:161-187): instead of HashMap<u64, Vec<usize>> the distinct keys go into an open-addressed
-// table and the build row ids into a CSR array grouped by key, ascending per key — so the probe
-// (:208-248) emits (build row, probe row) pairs exactly in the reference's order with a
-// count -> scan -> write pass and no per-row allocation.  All kernels are HBM-latency bound
-// (random 8-byte reads of the table); grids are multiples of the SM count.
+// table (+ a blocked Bloom filter) and — only when some key repeats — the build row ids into a CSR
+// array grouped by key, ascending per key.  Probe (:208-248): the fused JIT kernel csrc/jit/joinprobe.cuh
+// finds the slot of every probe row; k_join_probe_emit here turns slots + per-chunk offsets into
+// (build row, probe row) pairs exactly in the reference's order, with no per-row allocation.  All kernels are
+// HBM-latency bound (random 8-byte reads of the table); grids are multiples of the SM count.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "kernels_aot.hpp"
@@ -134,60 +135,6 @@ __global__ void __launch_bounds__(kBlock) k_join_sort_ranges(JoinTableView t) {
         b--;
       }
       r[b] = v;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kBlock) k_join_probe_count(JoinTableView t, const uint64_t* __restrict__ ph, const uint64_t* __restrict__ pkeys,
-                                                              const uint32_t* __restrict__ pknull, const uint32_t* __restrict__ probe_keep,
-                                                              int64_t n_probe, int keep_unmatched,
-                                                              int32_t* __restrict__ slot_of, uint32_t* __restrict__ out_count) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const uint32_t mask = t.capacity - 1;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_probe; r += stride) {
-    int32_t found = -1;
-    const bool kept = !probe_keep || ((probe_keep[r >> 5] >> (r & 31)) & 1u);
-    if (kept && !(t.match_keys && pknull[r] != 0u)) {
-      const uint64_t h = ph[r];
-      uint32_t s = mix32(h) & mask;
-      uint32_t probes = 0;
-      if (t.bloom) {  // a clear bit proves the key absent: most misses end here, on an L2-resident word
-        const uint64_t bits = join_bloom_bits(h);
-        if ((__ldg(&t.bloom[join_bloom_word(h, t.bloom_mask)]) & bits) != bits) probes = mask + 1;
-      }
-      for (; probes <= mask; probes++) {
-        const int64_t rep = t.slot_rep[s];
-        if (rep < 0) break;
-        if (same_key(t, rep, h, pkeys, n_probe, r)) {
-          found = (int32_t)s;
-          break;
-        }
-        s = (s + 1) & mask;
-      }
-    }
-    slot_of[r] = found;
-    const uint32_t c = found >= 0 ? (t.unique ? 1u : t.slot_count[found]) : 0u;
-    out_count[r] = c ? c : ((keep_unmatched && kept) ? 1u : 0u);
-  }
-}
-
-__global__ void __launch_bounds__(kBlock) k_join_probe_write(JoinTableView t, const int32_t* __restrict__ slot_of,
-                                                              const unsigned long long* __restrict__ offsets, int64_t n_probe, int keep_unmatched,
-                                                              int64_t* __restrict__ li, uint32_t* __restrict__ ri) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_probe; r += stride) {
-    const int32_t s = slot_of[r];
-    unsigned long long o = offsets[r];
-    if (s >= 0) {
-      const uint32_t c = t.unique ? 1u : t.slot_count[s];
-      const int64_t* src = t.unique ? t.slot_rep + s : t.rows + t.slot_start[s];
-      for (uint32_t j = 0; j < c; j++) {
-        li[o + j] = src[j];
-        ri[o + j] = (uint32_t)r;
-      }
-    } else if (keep_unmatched && offsets[r + 1] > o) {  // Right/Full: (NULL, row), hash_join.rs:242-246 (rows dropped by a fused Filter emit nothing)
-      li[o] = -1;
-      ri[o] = (uint32_t)r;
     }
   }
 }
@@ -452,18 +399,6 @@ void join_fill_sorted(const JoinTableView& t, const int32_t* row_slot, cudaStrea
   scratch_free(v_out, stream);
 }
 
-void launch_join_probe_count(const JoinTableView& t, const uint64_t* ph, const uint64_t* pkeys, const uint32_t* pknull, const uint32_t* probe_keep,
-                             int64_t n_probe, int keep_unmatched, int32_t* slot_of, uint32_t* out_count, cudaStream_t stream) {
-  if (n_probe <= 0) return;
-  k_join_probe_count<<<grid_for(n_probe, kBlock), kBlock, 0, stream>>>(t, ph, pkeys, pknull, probe_keep, n_probe, keep_unmatched, slot_of, out_count);
-  SQ_LAUNCH_CHECK();
-}
-void launch_join_probe_write(const JoinTableView& t, const int32_t* slot_of, const unsigned long long* offsets, int64_t n_probe,
-                             int keep_unmatched, int64_t* li, uint32_t* ri, cudaStream_t stream) {
-  if (n_probe <= 0) return;
-  k_join_probe_write<<<grid_for(n_probe, kBlock), kBlock, 0, stream>>>(t, slot_of, offsets, n_probe, keep_unmatched, li, ri);
-  SQ_LAUNCH_CHECK();
-}
 void launch_join_probe_emit(const JoinTableView& t, const int32_t* slot_of, const unsigned long long* chunk_offsets, int64_t n_probe,
                             int keep_unmatched, int64_t* li, uint32_t* ri, cudaStream_t stream) {
   if (n_probe <= 0) return;

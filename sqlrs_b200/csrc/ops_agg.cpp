@@ -320,7 +320,7 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
   comp->unroll = 4;
   comp->block = 128;
   auto smem_for = [&](int T) {
-    return (size_t)(W + 1) * comp->slots * T * 8 + (size_t)4 * comp->slots * (8 + 8 * std::max(K, 1) + 4 + 4 + 4) + 16;
+    return (size_t)(W + 1) * comp->slots * T * 8 + (size_t)8 * comp->slots * (8 + 8 * std::max(K, 1) + 4 + 4 + 4) + 16;  // + SQ_TSLOTS = 8 S slot-table entries
   };
   if (smem_for(256) <= 100 * 1024) comp->block = 256;
   // tuning overrides (experiments only): SQLRS_B200_AGG_BLOCK / _UNROLL / _SLOTS

@@ -84,7 +84,7 @@ struct JoinOp::Impl {
   BufPtr slot_rep, slot_count, slot_start, rows, bloom;
   uint32_t capacity = 0;
   BufPtr visited_left;  // bitmap over build rows (Left/Full)
-  std::unique_ptr<EvalProgram> left_prog, right_prog, filter_prog;
+  std::unique_ptr<EvalProgram> left_prog, filter_prog;
   std::map<std::string, JitKernel*> probe_kernels;  // fused probe kernels by probe-batch schema signature
   uint32_t max_count = 0;                           // largest number of build rows sharing one key
   JoinTableView view{};
