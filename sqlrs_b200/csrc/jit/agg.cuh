@@ -27,12 +27,13 @@
 // shared-memory layout of sq_agg_small
 //   u64 acc[(W+1)][S][T]   private accumulators, word W = min row id
 //   CTA-shared slot table with SQ_TSLOTS = 8*S entries (load factor <= 1/8) probed through a branch-free
-//   two-slot window: u64 thash[TS]; u64 tkeys[TS][K]; u32 tknull[TS]; u32 tstate[TS]; u32 tgroup[TS]
+//   two-slot window: u64 ttag[TS]; u64 thash[TS]; u64 tkeys[TS][K]; u32 tknull[TS]; u32 tstate[TS]; u32 tgroup[TS]
 //   u32 ngroups; u32 flags
 #define SQ_ACC_WORDS (SQ_NACC + 1)
 #define SQ_TSLOTS (8 * SQ_SLOTS)
 
 struct SqSlotTable {
+  u64* ttag;    // 0 = not published; else (hash | 1): publication state + 63 hash bits in ONE word for the hot-path window
   u64* thash;
   u64* tkeys;
   u32* tknull;
@@ -64,25 +65,25 @@ __device__ __forceinline__ bool sq_small_same(const SqSlotTable& t, u32 s, const
 #endif
 }
 
-// The first TWO slots of the probe sequence are examined without a data-dependent branch (state + hash tag of both,
-// then ONE full key comparison at the selected slot), so a key displaced by one position costs exactly what a key in its
-// home slot costs.  Measured reason: with one-slot probing the Q1' kernel swung between 6.4 and 9.1 ms at SF100
-// depending on whether the 8 group keys happened to land in 8 distinct home slots (a change of the placement hash
-// exposed it) — every divergent extra probe is paid by the whole warp.  Longer chains (rare at load <= 1/8) continue
-// in the loop.
+// The first TWO slots of the probe sequence are examined without a data-dependent branch: one tag word per slot
+// carries "published" and 63 bits of the hash, then ONE full comparison at the selected slot — so a key displaced by one
+// position costs exactly what a key in its home slot costs.  Measured reason: with one-slot-at-a-time probing the Q1'
+// kernel swung between 6.4 and 9.1 ms at SF100 depending on whether the 8 group keys happened to land in 8 distinct home
+// slots (a change of the placement hash exposed it) — every divergent extra probe is paid by the whole warp.  Longer
+// chains (rare at load <= 1/8) continue in the loop.
 template <int TS, typename R>
 __device__ __forceinline__ int sq_small_find(const SqSlotTable& t, const R& o) {
 #if SQ_NKEYS == 0
   return 0;
 #else
   const u32 s0 = sq_mix32(o.h) & (TS - 1), s1 = (s0 + 1) & (TS - 1);
-  const bool pub0 = *((volatile u32*)&t.tstate[s0]) == 2u, pub1 = *((volatile u32*)&t.tstate[s1]) == 2u;
-  const bool tag0 = pub0 && *((volatile u64*)&t.thash[s0]) == o.h;
-  const bool tag1 = pub0 && pub1 && *((volatile u64*)&t.thash[s1]) == o.h;
+  const u64 want = o.h | 1ULL;
+  const u64 t0 = *((volatile u64*)&t.ttag[s0]), t1 = *((volatile u64*)&t.ttag[s1]);
+  const bool tag0 = t0 == want, tag1 = t0 != 0ULL && t1 == want;
   const u32 sel = tag0 ? s0 : s1;
   if ((tag0 || tag1) && sq_small_same(t, sel, o)) return (int)*((volatile u32*)&t.tgroup[sel]);
-  if (!pub0 || !pub1) return -1;  // the chain ends inside the window: not published (yet)
-  if (tag0 && tag1 && sq_small_same(t, s1, o)) return (int)*((volatile u32*)&t.tgroup[s1]);  // equal hashes, different keys
+  if (t0 == 0ULL || t1 == 0ULL) return -1;  // the chain ends inside the window: not published (yet)
+  if (tag0 && tag1 && sq_small_same(t, s1, o)) return (int)*((volatile u32*)&t.tgroup[s1]);  // equal tags, different keys
   u32 s = (s1 + 1) & (TS - 1);
   for (int probes = 2; probes < TS; probes++) {
     if (*((volatile u32*)&t.tstate[s]) != 2u) return -1;  // empty or being written: not published (yet)
@@ -90,6 +91,26 @@ __device__ __forceinline__ int sq_small_find(const SqSlotTable& t, const R& o) {
     s = (s + 1) & (TS - 1);
   }
   return -1;
+#endif
+}
+
+// The same lookup for a CONVERGED warp (every lane calls it, `live` says whose result counts): when every live lane
+// finds its key's tag in the home slot — the normal state at load <= 1/8 — a warp-uniform vote skips the second slot's
+// loads altogether; otherwise the whole warp takes the two-slot window together.  Either way no lane waits for another
+// lane's longer probe sequence.
+template <int TS, typename R>
+__device__ __forceinline__ int sq_small_find_warp(const SqSlotTable& t, const R& o, bool live) {
+#if SQ_NKEYS == 0
+  return live ? 0 : -1;
+#else
+  const u32 s0 = sq_mix32(o.h) & (TS - 1);
+  const u64 want = o.h | 1ULL;
+  const bool tag0 = *((volatile u64*)&t.ttag[s0]) == want;
+  if (__all_sync(SQ_FULL, !live || tag0)) {
+    if (live && sq_small_same(t, s0, o)) return (int)*((volatile u32*)&t.tgroup[s0]);
+    return live ? sq_small_find<TS>(t, o) : -1;  // equal tag, different key (a 63-bit collision): the general path
+  }
+  return live ? sq_small_find<TS>(t, o) : -1;
 #endif
 }
 
@@ -119,6 +140,7 @@ __device__ __forceinline__ int sq_small_insert(const SqSlotTable& t, const SqKey
       t.tknull[s] = o.knull;
       t.tgroup[s] = g < NG ? g : 0xffffffffu;
       __threadfence_block();
+      *((volatile u64*)&t.ttag[s]) = o.h | 1ULL;
       atomicExch(&t.tstate[s], 2u);
       return g < NG ? (int)g : -1;
     }
@@ -204,7 +226,8 @@ extern "C" __global__ void __launch_bounds__(SQ_BLOCK, SQ_MINCTAS) sq_agg_small(
   extern __shared__ __align__(16) unsigned char sq_smem[];
   u64* acc = (u64*)sq_smem;
   SqSlotTable tab;
-  tab.thash = acc + (size_t)SQ_ACC_WORDS * SQ_SLOTS * SQ_BLOCK;
+  tab.ttag = acc + (size_t)SQ_ACC_WORDS * SQ_SLOTS * SQ_BLOCK;
+  tab.thash = tab.ttag + SQ_TSLOTS;
   tab.tkeys = tab.thash + SQ_TSLOTS;
   tab.tknull = (u32*)(tab.tkeys + SQ_TSLOTS * (SQ_NKEYS > 0 ? SQ_NKEYS : 1));
   tab.tstate = tab.tknull + SQ_TSLOTS;
@@ -221,7 +244,10 @@ extern "C" __global__ void __launch_bounds__(SQ_BLOCK, SQ_MINCTAS) sq_agg_small(
 #pragma unroll
     for (int s = 0; s < SQ_SLOTS; s++) acc[((size_t)w * SQ_SLOTS + s) * SQ_BLOCK + tid] = ident;
   }
-  for (int s = tid; s < SQ_TSLOTS; s += SQ_BLOCK) tab.tstate[s] = 0u;
+  for (int s = tid; s < SQ_TSLOTS; s += SQ_BLOCK) {
+    tab.tstate[s] = 0u;
+    tab.ttag[s] = 0ULL;
+  }
   if (tid == 0) {
     *tab.ngroups = 0u;
     *flags = 0u;
@@ -250,7 +276,7 @@ extern "C" __global__ void __launch_bounds__(SQ_BLOCK, SQ_MINCTAS) sq_agg_small(
     bool miss = false;
 #pragma unroll
     for (int u = 0; u < SQ_UNROLL; u++) {
-      g[u] = live[u] ? sq_small_find<SQ_TSLOTS>(tab, o[u]) : -1;
+      g[u] = sq_small_find_warp<SQ_TSLOTS>(tab, o[u], live[u]);
       miss |= live[u] && g[u] < 0;
     }
     // the probes are the only divergent code: reconverge (without this the warp stays split per group and every
@@ -394,7 +420,8 @@ extern "C" __global__ void __launch_bounds__(256) sq_agg_medium(SqIn in, i64 n, 
   extern __shared__ __align__(16) unsigned char sq_smem[];
   u64* macc = (u64*)sq_smem;
   SqSlotTable tab;
-  tab.thash = macc + (size_t)SQ_ACC_WORDS * SQ_MSLOTS;
+  tab.ttag = macc + (size_t)SQ_ACC_WORDS * SQ_MSLOTS;
+  tab.thash = tab.ttag + SQ_MTSLOTS;
   tab.tkeys = tab.thash + SQ_MTSLOTS;
   tab.tknull = (u32*)(tab.tkeys + SQ_MTSLOTS * (SQ_NKEYS > 0 ? SQ_NKEYS : 1));
   tab.tstate = tab.tknull + SQ_MTSLOTS;
@@ -414,7 +441,10 @@ extern "C" __global__ void __launch_bounds__(256) sq_agg_medium(SqIn in, i64 n, 
     const int w = i / SQ_MSLOTS;
     macc[i] = (w == SQ_NACC) ? SQ_EMPTY_ROW : sq_acc_identity(w);
   }
-  for (int s = tid; s < SQ_MTSLOTS; s += 256) tstate[s] = 0u;
+  for (int s = tid; s < SQ_MTSLOTS; s += 256) {
+    tstate[s] = 0u;
+    tab.ttag[s] = 0ULL;
+  }
   if (tid == 0) {
     *ngroups = 0u;
     *flags = 0u;

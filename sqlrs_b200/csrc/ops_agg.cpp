@@ -320,7 +320,7 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
   comp->unroll = 4;
   comp->block = 128;
   auto smem_for = [&](int T) {
-    return (size_t)(W + 1) * comp->slots * T * 8 + (size_t)8 * comp->slots * (8 + 8 * std::max(K, 1) + 4 + 4 + 4) + 16;  // + SQ_TSLOTS = 8 S slot-table entries
+    return (size_t)(W + 1) * comp->slots * T * 8 + (size_t)8 * comp->slots * (8 + 8 + 8 * std::max(K, 1) + 4 + 4 + 4) + 16;  // + SQ_TSLOTS = 8 S slot-table entries (tag, hash, keys, null mask, state, group)
   };
   if (smem_for(256) <= 100 * 1024) comp->block = 256;
   // tuning overrides (experiments only): SQLRS_B200_AGG_BLOCK / _UNROLL / _SLOTS
@@ -342,7 +342,7 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
   comp->min_ctas = std::max(1, std::min(smem_ctas, reg_ctas));
   // sq_agg_medium: one accumulator copy per CTA for up to M groups; M = the largest power of two whose shared
   // memory (accumulators + 2M-entry slot table) stays <= 72 KB, i.e. three 256-thread CTAs per SM
-  auto medium_smem_for = [&](int M) { return (size_t)(W + 1) * M * 8 + (size_t)2 * M * (8 + 8 * std::max(K, 1) + 12) + 16; };
+  auto medium_smem_for = [&](int M) { return (size_t)(W + 1) * M * 8 + (size_t)2 * M * (8 + 8 + 8 * std::max(K, 1) + 12) + 16; };
   comp->mslots = 0;
   for (int M = 2048; M >= 64; M /= 2)
     if (medium_smem_for(M) <= 72 * 1024) {
