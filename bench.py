@@ -28,6 +28,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Native libraries print there too (NCCL announces its version on fd 1 when
+# the first communicator comes up), so fd 1 is pointed at stderr for the whole run and the line goes to the saved fd.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def load_oracle():
     """CPU restatement of the reference's executor — used ONLY for cpu_baseline / --impl reference."""
     from sqlrs_b200.host import ffi
@@ -157,7 +168,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": r["rows_per_s"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -324,7 +335,7 @@ def run_gpu(args, rank, world, local_rank):
         r = cpu_port_run(args.cpu_rows, 1024, 1, 0, args.sf)
         line["cpu_baseline"] = {"value": r["rows_per_s"], "unit": "rows/s", "cores": 1, "kind": "port",
                                 "sample": f"first {r['rows']} lineitem rows of SF{args.sf:g}, one pass, batch 1024 rows, C++ restatement of the sqlrs v1 executor"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def q3_tables(lib, d, make, cols=None):
@@ -437,7 +448,7 @@ def run_gpu_q3(args):
         n_cpu = sum(t.num_rows for t in host.values())
         line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "rows/s", "cores": 1, "kind": "port",
                                 "sample": f"Q3' at SF{args.cpu_sf:g} ({n_cpu} input rows), one pass, batch 1024 rows, C++ restatement of the sqlrs v1 executor"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_gpu_q3_multi(args, rank, world, local_rank):
@@ -524,7 +535,7 @@ def run_gpu_q3_multi(args, rank, world, local_rank):
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg // world, "traffic": None, "note": "per GPU"},
         "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
