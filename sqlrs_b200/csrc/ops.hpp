@@ -115,9 +115,12 @@ class AggOp {
   void push_join(const DBatch& probe, class JoinOp& join, const ExprCopy& probe_pred);
   void set_row_base(int64_t first_global_row) { rows_seen_ = first_global_row; }
 
+  bool has_distinct() const { return distinct_ != nullptr; }
+
  private:
   struct Compiled;
   struct Table;
+  struct Distinct;  // DISTINCT aggregates: this operator becomes a composition of DISTINCT-free operators (ops_agg.cpp)
   Compiled& compiled_for(const DBatch& batch);
   struct JoinGen {  // what the fused probe->aggregate program needs to know about the join below
     std::vector<ColInfo> build_cols;
@@ -136,6 +139,7 @@ class AggOp {
   void grow_table(uint32_t min_capacity);
   void build_output(std::vector<Field>* fields, struct HostGroups* groups);
   void pack_sorted(int K, int W, uint32_t n, uint64_t* dst);
+  DBatch finish_distinct();
 
   Ctx ctx_;
   Options opt_;
@@ -144,6 +148,7 @@ class AggOp {
   std::vector<std::string> group_names_;
   bool simple_;
   ExprCopy predicate_;
+  std::unique_ptr<Distinct> distinct_;
   std::map<std::string, std::unique_ptr<Compiled>> cache_;
   struct JoinKernels {
     JitKernel* generic = nullptr;

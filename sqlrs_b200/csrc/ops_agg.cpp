@@ -102,6 +102,23 @@ struct ScanTimer {
 
 }  // namespace
 
+// COUNT(DISTINCT x) / SUM(DISTINCT x) (reference: DistinctCountAccumulator count.rs:31-58, DistinctSumAccumulator
+// sum.rs:99-132 — a HashSet<ScalarValue> per group).  On the GPU the set becomes one more level of grouping:
+//   dedup   = GROUP BY (keys..., x) without aggregates            (the set elements, true equality, NULL is a value)
+//   second  = GROUP BY keys over dedup's output: COUNT(1) — the reference's set counts a NULL element too — or SUM(x)
+//   plain   = the operator's non-DISTINCT aggregates, as usual
+// All three emit their groups in first-appearance order of the keys over the same input, so their rows line up and the
+// result is the positional zip [keys, aggregates in declared order].
+struct AggOp::Distinct {
+  std::unique_ptr<AggOp> plain;
+  struct Item {
+    size_t agg_index;
+    std::unique_ptr<AggOp> dedup;
+  };
+  std::vector<Item> items;
+  bool seen_batch = false;
+};
+
 struct HostGroups {
   uint32_t n = 0;
   std::vector<uint64_t> hash, min_row, keys, acc;  // keys [K][n], acc [W][n]
@@ -149,10 +166,37 @@ AggOp::AggOp(std::vector<AggSpec> aggs, std::vector<ExprCopy> group_by, std::vec
     : ctx_(opt), opt_(opt), aggs_(std::move(aggs)), group_by_(std::move(group_by)), group_names_(std::move(group_names)),
       simple_(simple), predicate_(std::move(fused_predicate)) {
   if (group_by_.size() > 16) fail(SQLRS_ERR_UNSUPPORTED, "more than 16 group-by keys");
+  bool any_distinct = false;
   for (const AggSpec& a : aggs_) {
     if (a.func < SQLRS_AGG_COUNT || a.func > SQLRS_AGG_MAX) fail(SQLRS_ERR_INVALID_ARG, "unknown aggregate function");
-    if (a.distinct && (a.func == SQLRS_AGG_COUNT || a.func == SQLRS_AGG_SUM))
-      fail(SQLRS_ERR_UNSUPPORTED, "DISTINCT aggregates are not supported by the CUDA backend yet (SURVEY §8f rank 4)");
+    // create_accumulator (aggregate/mod.rs:27-49): only Count and Sum have DISTINCT accumulators, Min/Max ignore the flag
+    any_distinct |= a.distinct && (a.func == SQLRS_AGG_COUNT || a.func == SQLRS_AGG_SUM);
+  }
+  if (any_distinct) {
+    if (group_by_.size() >= 16) fail(SQLRS_ERR_UNSUPPORTED, "DISTINCT aggregates with 16 group-by keys");
+    distinct_ = std::make_unique<Distinct>();
+    Options sub = opt;
+    sub.stream = ctx_.stream;  // every sub-operator works on this operator's stream
+    sub.device_id = ctx_.device;
+    std::vector<AggSpec> plain_aggs;
+    for (size_t j = 0; j < aggs_.size(); j++) {
+      const AggSpec& a = aggs_[j];
+      if (a.distinct && (a.func == SQLRS_AGG_COUNT || a.func == SQLRS_AGG_SUM)) {
+        Options dopt = sub;
+        dopt.match_mode = SQLRS_MATCH_HASH_AND_KEY;  // HashSet<ScalarValue>: real equality, whatever the group identity mode
+        std::vector<ExprCopy> keys = group_by_;
+        keys.push_back(a.arg);
+        std::vector<std::string> names = group_names_;
+        names.resize(group_by_.size());
+        names.push_back("distinct_arg");
+        distinct_->items.push_back({j, std::make_unique<AggOp>(std::vector<AggSpec>{}, keys, names, false, predicate_, dopt)});
+      } else {
+        plain_aggs.push_back(a);
+      }
+    }
+    // (an ungrouped aggregate whose aggregates are all DISTINCT needs no plain operator: it yields exactly one row)
+    if (!(plain_aggs.empty() && group_by_.empty()))
+      distinct_->plain = std::make_unique<AggOp>(plain_aggs, group_by_, group_names_, simple_, predicate_, sub);
   }
 }
 AggOp::~AggOp() {
@@ -512,6 +556,11 @@ void AggOp::grow_table(uint32_t min_capacity) {
 // forget all groups but keep the compiled kernels and the device buffers (repeated plan runs)
 void AggOp::reset() {
   ctx_.activate();
+  if (distinct_) {
+    if (distinct_->plain) distinct_->plain->reset();
+    for (auto& it : distinct_->items) it.dedup->reset();
+    distinct_->seen_batch = false;
+  }
   slot_list_complete_ = false;
   if (table_) init_table_contents(*table_);
   rows_seen_ = 0;
@@ -553,6 +602,15 @@ void AggOp::ensure_partial_scratch(size_t entries, int K, size_t W) {
 
 // ------------------------------------------------------------------ push
 void AggOp::push(const DBatch& batch) {
+  if (distinct_) {
+    distinct_->seen_batch = true;
+    seen_batch_ = true;
+    if (distinct_->plain) distinct_->plain->push(batch);
+    for (auto& it : distinct_->items) it.dedup->push(batch);
+    last_path_ = "DISTINCT: GROUP BY (keys, argument) dedup + second-level aggregate" +
+                 (distinct_->plain ? "; plain aggregates: " + distinct_->plain->describe() : std::string());
+    return;
+  }
   Trace tr("agg.push", ctx_.stream);
   slot_list_complete_ = false;
   ctx_.activate();
@@ -695,6 +753,7 @@ void AggOp::push(const DBatch& batch) {
 
 // ------------------------------------------------------------------ fused probe -> aggregate
 void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_pred) {
+  if (distinct_) fail(SQLRS_ERR_INTERNAL, "push_join: DISTINCT aggregates take the unfused path");
   Trace tr("agg.push_join", ctx_.stream);
   ctx_.activate();
   ctx_.reap();
@@ -910,7 +969,7 @@ void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
   Trace tr("agg.finish_host", ctx_.stream);
   // many groups: finalise on the device and copy whole columns (the row-at-a-time host loop below cost 2.7 ms for
   // Q3' SF10's 113 k groups); few groups: one packed D2H and a trivial host loop beat the extra launches
-  if (seen_batch_ && table_ && !counters_stale_ && groups_known_ > 1024) {
+  if (distinct_ || (seen_batch_ && table_ && !counters_stale_ && groups_known_ > 1024)) {
     DBatch b = finish_device();
     export_batch_host(ctx_, b, out, out_schema);
     return;
@@ -1011,6 +1070,7 @@ DBatch AggOp::finish_device() {
   Trace tr("agg.finish_device", ctx_.stream);
   if (!seen_batch_) fail(SQLRS_ERR_INTERNAL, "called `Option::unwrap()` on a `None` value (no input batch)");
   ctx_.activate();
+  if (distinct_) return finish_distinct();
   const Compiled& c = *cache_.begin()->second;
   const int K = (int)c.key_dtypes.size(), W = (int)c.words.size();
   const int words = 3 + K + W;
@@ -1082,8 +1142,82 @@ DBatch AggOp::finish_device() {
   return out;
 }
 
+// DISTINCT: zip of the plain aggregates with one second-level aggregate per DISTINCT aggregate (see struct Distinct)
+DBatch AggOp::finish_distinct() {
+  Distinct& d = *distinct_;
+  const size_t K = group_by_.size();
+  Options sub = opt_;
+  sub.stream = ctx_.stream;
+  sub.device_id = ctx_.device;
+  sub.count_mode = SQLRS_COUNT_SQL_ACCUMULATE;  // the second level counts set elements; quirk K1 is about input batches
+  sub.match_mode = SQLRS_MATCH_HASH_AND_KEY;
+  DBatch plain;  // [keys..., plain aggregates...]
+  if (d.plain) plain = d.plain->finish_device();
+  else plain.n = 1;
+  DBatch out;
+  out.n = plain.n;
+  for (size_t k = 0; k < K; k++) {
+    out.fields.push_back(plain.fields[k]);
+    out.cols.push_back(plain.cols[k]);
+  }
+  std::vector<DCol> agg_cols(aggs_.size());
+  std::vector<Field> agg_fields(aggs_.size());
+  std::vector<bool> filled(aggs_.size(), false);
+  for (auto& it : d.items) {
+    const AggSpec& a = aggs_[it.agg_index];
+    DBatch elems = it.dedup->finish_device();  // [keys..., x], one row per distinct (keys, x), first-appearance order
+    std::vector<ExprCopy> keys;
+    for (size_t k = 0; k < K; k++) {
+      ExprNodeCopy n;
+      n.op = SQLRS_OP_INPUT_REF;
+      n.index = (int)k;
+      n.dtype = elems.cols[k].dtype;
+      keys.push_back(ExprCopy{n});
+    }
+    AggSpec second;
+    second.func = a.func;
+    second.distinct = 0;
+    second.name = a.name;
+    ExprNodeCopy arg;
+    if (a.func == SQLRS_AGG_COUNT) {  // the set's size: a NULL element counts (count.rs:44-57)
+      arg.op = SQLRS_OP_CONSTANT;
+      arg.dtype = SQLRS_DT_INT32;
+      arg.imm_bits = 1;
+      second.return_dtype = SQLRS_DT_INT64;
+    } else {
+      arg.op = SQLRS_OP_INPUT_REF;
+      arg.index = (int)K;
+      arg.dtype = elems.cols[K].dtype;
+      second.return_dtype = a.return_dtype;
+    }
+    second.arg = ExprCopy{arg};
+    std::vector<std::string> names(group_names_.begin(), group_names_.end());
+    names.resize(K);
+    AggOp op2(std::vector<AggSpec>{second}, keys, names, simple_, ExprCopy(), sub);
+    op2.push(elems);
+    DBatch r = op2.finish_device();  // [keys..., aggregate]
+    if (r.n != plain.n)
+      fail(SQLRS_ERR_UNSUPPORTED, "DISTINCT aggregate: the hash-only group identity merged groups that differ by key (quirk K2)");
+    agg_cols[it.agg_index] = r.cols[K];
+    agg_fields[it.agg_index] = Field{a.name, r.cols[K].dtype, true};
+    filled[it.agg_index] = true;
+  }
+  size_t p = K;
+  for (size_t j = 0; j < aggs_.size(); j++) {
+    if (!filled[j]) {
+      agg_cols[j] = plain.cols[p];
+      agg_fields[j] = plain.fields[p];
+      p++;
+    }
+    out.fields.push_back(agg_fields[j]);
+    out.cols.push_back(agg_cols[j]);
+  }
+  return out;
+}
+
 // ------------------------------------------------------------------ partial / final (multi-GPU)
 void AggOp::check_partial_supported() const {
+  if (distinct_) fail(SQLRS_ERR_UNSUPPORTED, "partial/final DISTINCT aggregates");
   if (opt_.count_mode == SQLRS_COUNT_REFERENCE_OVERWRITE)
     for (const AggSpec& a : aggs_)
       if (a.func == SQLRS_AGG_COUNT)

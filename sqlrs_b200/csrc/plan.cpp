@@ -126,7 +126,7 @@ void Plan::run_agg_to_host(int idx, Result* res) {
 // side as usual, then probe and aggregate in ONE kernel per probe batch (csrc/jit/joinagg.cuh) — the joined rows
 // are never materialised.  Returns false when the shape does not apply (the caller runs operator at a time).
 bool Plan::feed_fused_join(AggOp& op, int child, const ExprCopy& agg_fused_pred, const Needed& need) {
-  if (!fusion() || !agg_fused_pred.empty()) return false;
+  if (!fusion() || !agg_fused_pred.empty() || op.has_distinct()) return false;
   Node& jn = nodes_[child];
   if (jn.kind != SQLRS_NODE_HASH_JOIN || jn.join_type != SQLRS_JOIN_INNER || opt_.match_mode != SQLRS_MATCH_HASH_AND_KEY) return false;
   int left = jn.child0, right = jn.child1;

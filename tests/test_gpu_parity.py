@@ -681,3 +681,37 @@ def test_q3_tma_staged_probe_variant(cuda_lib, oracle, monkeypatch):
     exp2, _ = _run_plan(oracle, plan, schemas, sliced, None, **mode)
     got2, desc2 = _run_plan(cuda_lib, plan, schemas, sliced, None, **mode)
     assert_batches_match(got2, exp2, rtol=FTOL)
+
+
+@pytest.mark.parametrize("match_mode", [ffi.MATCH_HASH_ONLY, ffi.MATCH_HASH_AND_KEY])
+def test_distinct_aggregates_random(cuda_lib, oracle, match_mode):
+    """COUNT(DISTINCT x) / SUM(DISTINCT x) mixed with plain aggregates, NULLs in arguments and keys, several batches, grouped and
+    ungrouped, Int64 / Int32 / Boolean arguments (integer sums are order-independent, so results are exact); `select distinct`
+    = a group-by without aggregates"""
+    rng = np.random.default_rng(77)
+    batches = [random_batch(rng, n, [I64, I64, I32, BOOL, I64], null_frac=0.2, small_ints=True, names=["k", "x", "y", "b", "v"]) for n in (3000, 0, 5000)]
+    k, x, y, b, v = (InputRef(i, t) for i, t in enumerate([I64, I64, I32, BOOL, I64]))
+    aggs = [AggFunc("Count", [x], distinct=True), AggFunc("Sum", [v]), AggFunc("Sum", [x], distinct=True), AggFunc("Count", [y], distinct=True),
+            AggFunc("Count", [b], distinct=True), AggFunc("Max", [v]), AggFunc("Count", [bind_binary_op(x, "*", v)], distinct=True)]
+    opts = dict(match_mode=match_mode, count_mode=ffi.COUNT_SQL_ACCUMULATE)
+    got, exp = both(lambda l: ex.try_collect(ex.HashAggExecutor(aggs, [k], batches, lib=l, options=l.options(**opts)).execute()), cuda_lib, oracle)
+    assert got[0].num_rows == 14  # 13 key values + the NULL key
+    assert_batches_match(got, exp)
+    got, exp = both(lambda l: ex.try_collect(ex.SimpleAggExecutor(aggs, batches, lib=l, options=l.options(**opts)).execute()), cuda_lib, oracle)
+    assert_batches_match(got, exp)
+    only_distinct = [AggFunc("Sum", [x], distinct=True), AggFunc("Count", [x], distinct=True)]
+    got, exp = both(lambda l: ex.try_collect(ex.SimpleAggExecutor(only_distinct, batches, lib=l, options=l.options(**opts)).execute()), cuda_lib, oracle)
+    assert_batches_match(got, exp)
+    got, exp = both(lambda l: ex.try_collect(ex.HashAggExecutor([], [k, b], batches, lib=l, options=l.options(**opts)).execute()), cuda_lib, oracle)
+    assert_batches_match(got, exp)
+    # below a Filter in a plan (fused predicate reaches every sub-operator), and with an ORDER BY on top
+    from sqlrs_b200.host.plan import PhysicalFilter, PhysicalHashAgg, PhysicalOrder, PhysicalTableScan
+
+    plan = PhysicalOrder([ex.BoundOrderBy(InputRef(1, I64), asc=False), ex.BoundOrderBy(InputRef(0, I64))],
+                         PhysicalHashAgg([AggFunc("Count", [x], distinct=True), AggFunc("Sum", [v])], [k],
+                                         PhysicalFilter(bind_binary_op(v, ">", Constant(-3)), PhysicalTableScan(0))))
+    table = pa.Table.from_batches(batches).combine_chunks().to_batches()[0]
+    for fl in (0, ffi.FLAG_NO_FUSION):
+        g, _ = _run_plan(cuda_lib, plan, {0: table.schema}, {0: table}, 2500, flags=fl, **opts)
+        e, _ = _run_plan(oracle, plan, {0: table.schema}, {0: table}, 2500, **opts)
+        assert_batches_match(g, e)

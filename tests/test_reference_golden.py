@@ -341,3 +341,43 @@ def test_slt_order_utf8_oracle_only(oracle):
     ordered = ex.OrderExecutor([ex.BoundOrderBy(InputRef(1, U8), False)], [emp], lib=oracle).execute()
     out = ex.try_collect(ex.LimitExecutor(1, 2, ex.ProjectExecutor([InputRef(0, I64)], ordered, lib=oracle).execute(), lib=oracle).execute())
     assert rows_of(out) == [(2,)]
+
+
+# ---------------------------------------------------------------- DISTINCT, tests/slt/distinct.slt
+def test_slt_select_distinct_is_a_group_by_without_aggregates(lib):
+    """distinct.slt:9-17: `select distinct a, b from t2` -> HashAgg{group_by: [a, b], agg_funcs: []}, rows in first-appearance order"""
+    out = ex.try_collect(ex.HashAggExecutor([], [InputRef(0, I64), InputRef(1, I64)], [t2()], lib=lib).execute())
+    assert out[0].schema.names == ["a", "b"]
+    assert rows_of(out) == [(10, 2), (20, 2), (30, 3), (40, 4)]
+
+
+def test_slt_distinct_aggregates(lib):
+    """distinct.slt:18-42: sum(distinct b) = 9; sum(distinct b) group by c = 2, 2, 7; count(distinct b) = 3 over t2.b = [2, 2, 3, 4]"""
+    b, c = InputRef(1, I64), InputRef(2, I64)
+    out = ex.try_collect(ex.SimpleAggExecutor([AggFunc("Sum", [b], distinct=True)], [t2()], lib=lib).execute())
+    assert rows_of(out) == [(9,)]
+    out = ex.try_collect(ex.HashAggExecutor([AggFunc("Sum", [b], distinct=True)], [c], [t2()], lib=lib).execute())
+    assert [r[1] for r in rows_of(out)] == [2, 2, 7] and [r[0] for r in rows_of(out)] == [7, 5, 6]
+    out = ex.try_collect(ex.SimpleAggExecutor([AggFunc("Count", [b], distinct=True)], [t2()], lib=lib).execute())
+    assert rows_of(out) == [(3,)]
+
+
+def test_distinct_count_counts_null_as_a_value(lib):
+    """count.rs:44-57: DistinctCountAccumulator inserts every ScalarValue, NULL included, into its HashSet — so the NULL
+    salary of employee 4 is one more distinct value (unpinned by the reference's tests; the restatement is the definition);
+    DistinctSum skips it (sum.rs:125-131 via sum_result), mixed with plain aggregates in one operator"""
+    emp = employee_numeric()
+    sal, dep = InputRef(1, I64), InputRef(2, I64)
+    aggs = [AggFunc("Count", [sal], distinct=True), AggFunc("Count", [sal]), AggFunc("Sum", [sal], distinct=True), AggFunc("Sum", [sal])]
+    out = ex.try_collect(ex.SimpleAggExecutor(aggs, [emp, emp], lib=lib, options=lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE)).execute())
+    assert rows_of(out) == [(4, 6, 33500, 67000)]
+    out = ex.try_collect(ex.HashAggExecutor([AggFunc("Count", [sal], distinct=True), AggFunc("Sum", [sal], distinct=True), AggFunc("Max", [sal])], [dep],
+                                            [emp, emp], lib=lib).execute())
+    assert rows_of(out) == [(1, 1, 12000, 12000), (2, 1, 10000, 10000), (4, 1, 11500, 11500), (N, 1, N, N)]
+
+
+def test_slt_select_distinct_utf8_oracle_only(oracle):
+    """distinct.slt:1-7: select distinct state from employee -> CA, CO, (empty)"""
+    emp = pa.RecordBatch.from_arrays([pa.array(["CA", "CO", "CO", ""])], names=["state"])
+    out = ex.try_collect(ex.HashAggExecutor([], [InputRef(0, ffi.DT_UTF8)], [emp], lib=oracle).execute())
+    assert rows_of(out) == [("CA",), ("CO",), ("",)]
