@@ -113,7 +113,7 @@ typedef struct sqlrs_expr {
 
 typedef struct sqlrs_agg_desc {
   int32_t func;         /* SQLRS_AGG_* */
-  int32_t distinct;     /* BoundAggFunc::distinct (oracle only; CUDA: SQLRS_ERR_UNSUPPORTED) */
+  int32_t distinct;     /* BoundAggFunc::distinct — Count/Sum keep a set of values per group (count.rs:31-58, sum.rs:99-132) */
   int32_t return_dtype; /* BoundAggFunc::return_type */
   int32_t reserved;
   sqlrs_expr arg;       /* exprs[0] — only the first argument is evaluated (hash_agg.rs:65) */
