@@ -7,9 +7,12 @@
 // needs nightly-2022-07-29 + arrow `simd`), so this restatement is pinned by the reference's own
 // golden tests instead — hash KAT (hash_utils.rs:229-247), HashAgg two-chunk test
 // (hash_agg.rs:182-222), the 8 HashJoin tables (hash_join.rs:423-750), the executor e2e tests
-// (executor/mod.rs:271-396) and the v1 .slt files over tests/csv — see tests/test_oracle_golden.py.
+// (executor/mod.rs:271-396) and the v1 .slt files over tests/csv — see tests/test_reference_golden.py.
+// The operators that follow the hot path (Project / Order / Limit, tail_ops.hpp) are pinned by limit.rs:96-101,
+// executor/mod.rs:353-396, tests/slt/{order,limit}.slt; DISTINCT aggregates by tests/slt/distinct.slt.
 // UNPINNED by any reference test: COUNT over >1 batch (K1), float SUM order, 64-bit collisions (K2),
-// NULL-key joins (K3), Int32/Boolean/Utf8 hash_one, multi-batch joins, Float64 min/max NaN.
+// NULL-key joins (K3), Int32/Boolean/Utf8 hash_one, multi-batch joins, Float64 min/max NaN, the order of rows that
+// tie on every sort key, OFFSET without LIMIT over several batches, NULL as an element of a DISTINCT set.
 #define SQLRS_ORACLE_BUILD 1
 #include <chrono>
 #include <deque>
