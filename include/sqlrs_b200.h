@@ -325,6 +325,24 @@ int SQLRS_API(plan_reset)(sqlrs_plan* p);
 /* human-readable: which pipeline (fused / generic) and kernels the plan runs with */
 const char* SQLRS_API(plan_describe)(sqlrs_plan* p);
 void SQLRS_API(plan_destroy)(sqlrs_plan* p);
+/* ---- GPU-resident tables: the InMemoryStorage / InMemoryTable analogue (src/storage/memory.rs:38-47,137-170;
+ *      SURVEY.md §8f rank 2).  `create_mem_table(id, Vec<RecordBatch>)` becomes table_create + one table_append per
+ *      batch: the batch is moved in, copied to HBM once and kept there; any number of plans then scan it with
+ *      plan_push_table_resident without crossing PCIe again (zero copy; the table may be destroyed while plans still
+ *      hold its batches).  table_read mirrors InMemoryTransaction::next_batch (memory.rs:151-170): batch `batch_index`
+ *      back on the host, *has_batch = 0 past the end; `projection` (column indices, NULL = all) is honoured here although
+ *      the reference's in-memory table ignores it (:137-143). ------------------------------------------------------- */
+typedef struct sqlrs_table sqlrs_table;
+int SQLRS_API(table_create)(const sqlrs_options* options, sqlrs_table** out);
+int SQLRS_API(table_append)(sqlrs_table* t, struct ArrowArray* batch, const struct ArrowSchema* schema);
+int64_t SQLRS_API(table_num_rows)(sqlrs_table* t);
+int32_t SQLRS_API(table_num_batches)(sqlrs_table* t);
+int SQLRS_API(table_read)(sqlrs_table* t, int32_t batch_index, const int32_t* projection, int32_t n_projection,
+                          struct ArrowArray* out, struct ArrowSchema* out_schema, int32_t* has_batch);
+void SQLRS_API(table_destroy)(sqlrs_table* t);
+/* every batch of the table, in order, as the batches of `table_slot` (what PhysicalTableScan pulls, table_scan.rs:16-35) */
+int SQLRS_API(plan_push_table_resident)(sqlrs_plan* p, int32_t table_slot, sqlrs_table* t);
+
 /* ---- partial / final aggregation for plans sharded over several GPUs.  The plan
  *      root must be an aggregate.  Each rank: push its shard, execute_partial (row_base = global row
  *      id of the shard's first row, keeps first-appearance order global), export_partials -> a host

@@ -89,6 +89,9 @@ struct sqlrs_hash_join {
 struct sqlrs_project {
   Project impl;
 };
+struct sqlrs_table {  // InMemoryTable (src/storage/memory.rs:62-123): the batches, as given
+  std::vector<Batch> batches;
+};
 struct sqlrs_order {
   Order impl;
 };
@@ -405,6 +408,58 @@ int sqlrs_oracle_plan_push_table(sqlrs_plan* p, int32_t table_slot, ArrowArray* 
 int sqlrs_oracle_plan_push_table_device(sqlrs_plan*, int32_t, ArrowDeviceArray*, const ArrowSchema*) {
   g_last_error = "the oracle takes host batches only";
   return SQLRS_ERR_UNSUPPORTED;
+}
+int sqlrs_oracle_table_create(const sqlrs_options*, sqlrs_table** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_table();
+  });
+}
+int sqlrs_oracle_table_append(sqlrs_table* t, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!t) fail(SQLRS_ERR_INVALID_ARG, "table is NULL");
+    Batch b = consume_batch(batch, schema);
+    if (!t->batches.empty() && t->batches[0].fields.size() != b.fields.size()) fail(SQLRS_ERR_ARROW, "table_append: schema mismatch");
+    t->batches.push_back(std::move(b));
+  });
+}
+int64_t sqlrs_oracle_table_num_rows(sqlrs_table* t) {
+  int64_t n = 0;
+  if (t)
+    for (const Batch& b : t->batches) n += b.n;
+  return n;
+}
+int32_t sqlrs_oracle_table_num_batches(sqlrs_table* t) { return t ? (int32_t)t->batches.size() : 0; }
+int sqlrs_oracle_table_read(sqlrs_table* t, int32_t batch_index, const int32_t* projection, int32_t n_projection, ArrowArray* out,
+                            ArrowSchema* out_schema, int32_t* has_batch) {
+  return guarded([&] {
+    if (!t) fail(SQLRS_ERR_INVALID_ARG, "table is NULL");
+    if (batch_index < 0 || batch_index >= (int32_t)t->batches.size()) {  // next_batch past the end: None (memory.rs:159-168)
+      if (has_batch) *has_batch = 0;
+      return;
+    }
+    const Batch& b = t->batches[(size_t)batch_index];
+    Batch r;
+    r.n = b.n;
+    if (projection) {
+      for (int32_t k = 0; k < n_projection; k++) {
+        if (projection[k] < 0 || projection[k] >= (int32_t)b.cols.size()) fail(SQLRS_ERR_INVALID_ARG, "table_read: projection index out of range");
+        r.fields.push_back(b.fields[(size_t)projection[k]]);
+        r.cols.push_back(b.cols[(size_t)projection[k]]);
+      }
+    } else {
+      r = b;
+    }
+    export_batch(r, out, out_schema);
+    if (has_batch) *has_batch = 1;
+  });
+}
+void sqlrs_oracle_table_destroy(sqlrs_table* t) { delete t; }
+int sqlrs_oracle_plan_push_table_resident(sqlrs_plan* p, int32_t table_slot, sqlrs_table* t) {
+  return guarded([&] {
+    if (!p || !t) fail(SQLRS_ERR_INVALID_ARG, "plan / table is NULL");
+    for (const Batch& b : t->batches) p->tables[table_slot].push_back(b);
+  });
 }
 int sqlrs_oracle_plan_execute(sqlrs_plan* p) {
   return guarded([&] {

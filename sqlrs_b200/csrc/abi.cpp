@@ -78,6 +78,11 @@ struct sqlrs_limit {
   LimitOp op;
   sqlrs_limit(int64_t limit, int64_t offset, const Options& o) : op(limit, offset, o) {}
 };
+struct sqlrs_table {  // batches resident in HBM (columns shared with every plan they were pushed to)
+  Ctx ctx;
+  std::vector<DBatch> batches;
+  explicit sqlrs_table(const Options& o) : ctx(o) {}
+};
 struct sqlrs_plan {
   Plan impl;
   sqlrs_plan(const sqlrs_plan_node* nodes, int32_t n, int32_t root, const Options& o) : impl(nodes, n, root, o) {}
@@ -319,6 +324,67 @@ int sqlrs_plan_push_table_device(sqlrs_plan* p, int32_t table_slot, ArrowDeviceA
     if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
     p->impl.ctx().activate();
     p->impl.push_table(table_slot, import_batch_device(p->impl.ctx(), batch, schema));
+  });
+}
+int sqlrs_table_create(const sqlrs_options* options, sqlrs_table** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_table(copy_options(options));
+  });
+}
+int sqlrs_table_append(sqlrs_table* t, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!t) fail(SQLRS_ERR_INVALID_ARG, "table is NULL");
+    t->ctx.activate();
+    DBatch b = import_batch_host(t->ctx, batch, schema);
+    if (!t->batches.empty()) {
+      const DBatch& first = t->batches[0];
+      bool same = first.cols.size() == b.cols.size();
+      for (size_t c = 0; same && c < b.cols.size(); c++) same = first.cols[c].dtype == b.cols[c].dtype;
+      if (!same) fail(SQLRS_ERR_ARROW, "table_append: schema mismatch");
+    }
+    t->ctx.sync();  // the H2D copies are complete: any stream may read the batch from now on
+    t->batches.push_back(std::move(b));
+  });
+}
+int64_t sqlrs_table_num_rows(sqlrs_table* t) {
+  int64_t n = 0;
+  if (t)
+    for (const DBatch& b : t->batches) n += b.n;
+  return n;
+}
+int32_t sqlrs_table_num_batches(sqlrs_table* t) { return t ? (int32_t)t->batches.size() : 0; }
+int sqlrs_table_read(sqlrs_table* t, int32_t batch_index, const int32_t* projection, int32_t n_projection, ArrowArray* out, ArrowSchema* out_schema,
+                     int32_t* has_batch) {
+  return guarded([&] {
+    if (!t) fail(SQLRS_ERR_INVALID_ARG, "table is NULL");
+    if (batch_index < 0 || batch_index >= (int32_t)t->batches.size()) {
+      if (has_batch) *has_batch = 0;
+      return;
+    }
+    t->ctx.activate();
+    const DBatch& b = t->batches[(size_t)batch_index];
+    DBatch r;
+    r.n = b.n;
+    if (projection) {
+      for (int32_t k = 0; k < n_projection; k++) {
+        if (projection[k] < 0 || projection[k] >= (int32_t)b.cols.size()) fail(SQLRS_ERR_INVALID_ARG, "table_read: projection index out of range");
+        r.fields.push_back(b.fields[(size_t)projection[k]]);
+        r.cols.push_back(b.cols[(size_t)projection[k]]);
+      }
+    } else {
+      r = b;
+    }
+    export_batch_host(t->ctx, r, out, out_schema);
+    if (has_batch) *has_batch = 1;
+  });
+}
+void sqlrs_table_destroy(sqlrs_table* t) { delete t; }
+int sqlrs_plan_push_table_resident(sqlrs_plan* p, int32_t table_slot, sqlrs_table* t) {
+  return guarded([&] {
+    if (!p || !t) fail(SQLRS_ERR_INVALID_ARG, "plan / table is NULL");
+    if (p->impl.ctx().device != t->ctx.device) fail(SQLRS_ERR_INVALID_ARG, "plan and table live on different devices");
+    for (const DBatch& b : t->batches) p->impl.push_table(table_slot, b);  // zero copy: the columns are shared
   });
 }
 int sqlrs_plan_execute(sqlrs_plan* p) {

@@ -214,6 +214,13 @@ _SIGNATURES = {
     "plan_create": (C.c_int, [P(PlanNode), C.c_int32, C.c_int32, P(Options), P(C.c_void_p)]),
     "plan_push_table": (C.c_int, [C.c_void_p, C.c_int32, P(ArrowArray), P(ArrowSchema)]),
     "plan_push_table_device": (C.c_int, [C.c_void_p, C.c_int32, P(ArrowDeviceArray), P(ArrowSchema)]),
+    "table_create": (C.c_int, [P(Options), P(C.c_void_p)]),
+    "table_append": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema)]),
+    "table_num_rows": (C.c_int64, [C.c_void_p]),
+    "table_num_batches": (C.c_int32, [C.c_void_p]),
+    "table_read": (C.c_int, [C.c_void_p, C.c_int32, P(C.c_int32), C.c_int32, P(ArrowArray), P(ArrowSchema), P(C.c_int32)]),
+    "table_destroy": (None, [C.c_void_p]),
+    "plan_push_table_resident": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "plan_execute": (C.c_int, [C.c_void_p]),
     "plan_next": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema), P(C.c_int32)]),
     "plan_reset": (C.c_int, [C.c_void_p]),

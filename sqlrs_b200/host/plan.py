@@ -218,6 +218,10 @@ class GpuPlan:
         finally:
             ffi.release_schema(sch)
 
+    def push_table_resident(self, table_slot: int, table):
+        """`table`: storage.InMemoryTable — its batches already live in HBM (zero copy, no PCIe traffic)."""
+        self.lib.check(self.lib.plan_push_table_resident(self.handle, table_slot, table.handle))
+
     def execute(self):
         self.lib.check(self.lib.plan_execute(self.handle))
 

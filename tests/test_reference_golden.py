@@ -381,3 +381,33 @@ def test_slt_select_distinct_utf8_oracle_only(oracle):
     emp = pa.RecordBatch.from_arrays([pa.array(["CA", "CO", "CO", ""])], names=["state"])
     out = ex.try_collect(ex.HashAggExecutor([], [InputRef(0, ffi.DT_UTF8)], [emp], lib=oracle).execute())
     assert rows_of(out) == [("CA",), ("CO",), ("",)]
+
+
+# ---------------------------------------------------------------- resident tables, src/storage/memory.rs
+def test_in_memory_storage_resident_tables(lib):
+    """memory.rs:38-56,137-170 + its tests :176-214: create_mem_table, get_table, read() returns the batches as given; a plan
+    scans the resident table (twice, and two plans) with the results of pushing host batches (mod.rs:293-350)"""
+    from sqlrs_b200.host.plan import ExecutorBuilder, PhysicalFilter, PhysicalHashAgg, PhysicalTableScan
+    from sqlrs_b200.host.storage import InMemoryStorage, StorageError
+
+    emp = mem_employee()
+    storage = InMemoryStorage(lib)
+    storage.create_mem_table("employee", [emp.slice(0, 3), emp.slice(3)])
+    with pytest.raises(StorageError):
+        storage.get_table("nope")
+    table = storage.get_table("employee")
+    assert table.num_rows == 4 and table.num_batches == 2
+    assert rows_of(list(table.read())) == rows_of([emp])
+    assert rows_of(list(table.read(projection=[1]))) == [(100,), (100,), (200,), (400,)]
+    idc, sal = InputRef(0, I64), InputRef(1, I64)
+    plan = PhysicalHashAgg([AggFunc("Count", [idc]), AggFunc("Sum", [idc]), AggFunc("Max", [idc]), AggFunc("Min", [idc])], [sal],
+                           PhysicalFilter(bind_binary_op(idc, ">", Constant(0)), PhysicalTableScan(0)))
+    opts = lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE)
+    for _ in range(2):  # two plans over the same resident table
+        p = ExecutorBuilder(lib, opts).build(plan, {0: emp.schema})
+        for _ in range(2):  # and the same plan run twice
+            p.push_table_resident(0, table)
+            assert rows_of(p.run()) == [(100, 2, 3, 2, 1), (200, 1, 3, 3, 3), (400, 1, 4, 4, 4)]
+            p.reset()
+        p.close()
+    table.close()
