@@ -191,3 +191,30 @@ def test_copartitioned_shard_covers_everything():
                 assert o_lo == o_prev and l_lo == l_prev and o_lo % 7 == 0 and l_lo == 4 * o_lo
                 o_prev, l_prev = o_hi, l_hi
             assert o_prev == n_orders and l_prev is None
+
+
+def _gather_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+
+    from sqlrs_b200.host import distributed as sqdist
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    group = sqdist.TorchGroup(dist, torch.device("cpu"))
+    small = bytes([rank + 1]) * (10 + rank)
+    got = group.gather_small(small, dst=0, cap=64)
+    assert (got == [bytes([r + 1]) * (10 + r) for r in range(world)]) if rank == 0 else got is None
+    # one rank's payload does not fit the fixed-size frame: every rank falls back to the two-phase gather
+    big = bytes([rank + 1]) * (200 if rank == 1 else 5)
+    got = group.gather_small(big, dst=0, cap=64)
+    assert (got == [bytes([r + 1]) * (200 if r == 1 else 5) for r in range(world)]) if rank == 0 else got is None
+    assert group.gather_small(b"", dst=0, cap=64) == ([b""] * world if rank == 0 else None)
+    if rank == 0:
+        open(os.path.join(out_dir, "ok"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_small_and_its_fallback(tmp_path):
+    mp.spawn(_gather_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+    assert (tmp_path / "ok").read_text() == "ok"
