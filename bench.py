@@ -10,6 +10,10 @@ one B200).  With N GPUs the rows are split into N contiguous shards (strong scal
 each rank aggregates its shard, partial groups are exchanged by key hash (all-to-all) and merged.
 `value` = rows/s with inputs resident in HBM; `e2e` = the same call with HOST (pinned) Arrow buffers,
 H2D copies inside the timed region.  One JSON line on stdout (rank 0).
+
+    python bench.py --query q3 [--q3-sf 100]                  # secondary line: Q3' (2 hash joins + group-by), one GPU:
+                                                              #   `value` = plan up to the aggregate, `full_query` = + ORDER BY / LIMIT on the device
+    torchrun ... bench.py --gpus N --query q3 --q3-sf 100     # Q3' whole query on N GPUs, orders/lineitem co-partitioned on orderkey
 """
 import argparse
 import ctypes as C
