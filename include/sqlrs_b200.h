@@ -222,6 +222,20 @@ int SQLRS_API(hash_join_finish)(sqlrs_hash_join* j, struct ArrowArray* out,
                                 struct ArrowSchema* out_schema, int32_t* has_batch);
 void SQLRS_API(hash_join_destroy)(sqlrs_hash_join* j);
 
+/* ---- CrossJoinExecutor{left_child, right_child, join_output_schema}, src/executor/join/cross_join.rs:8-57 -----------
+ * (what comma joins and `cross join` plan to).  Push every left batch (build_push), then each
+ * right batch through probe: it queues ONE output batch per left row — that row's values repeated to the right batch's
+ * length, then the right batch's columns (cross_join.rs:41-55) — which cross_join_next hands out in order
+ * (*has_batch = 0 when the queue is empty).  An empty left side yields nothing (:33-35). */
+typedef struct sqlrs_cross_join sqlrs_cross_join;
+int SQLRS_API(cross_join_create)(const struct ArrowSchema* join_output_schema, const sqlrs_options* options,
+                                 sqlrs_cross_join** out);
+int SQLRS_API(cross_join_build_push)(sqlrs_cross_join* j, struct ArrowArray* batch, const struct ArrowSchema* schema);
+int SQLRS_API(cross_join_probe)(sqlrs_cross_join* j, struct ArrowArray* batch, const struct ArrowSchema* schema);
+int SQLRS_API(cross_join_next)(sqlrs_cross_join* j, struct ArrowArray* out, struct ArrowSchema* out_schema,
+                               int32_t* has_batch);
+void SQLRS_API(cross_join_destroy)(sqlrs_cross_join* j);
+
 /* ==== the operators that FOLLOW the hot path in a v1 plan; the planner
  *      stacks them Agg -> Order -> Project -> Limit (src/planner/select.rs:34-45) ================= */
 
@@ -277,6 +291,7 @@ void SQLRS_API(limit_destroy)(sqlrs_limit* l);
 #define SQLRS_NODE_PROJECT 6    /* PhysicalProject    mod.rs:127-137 */
 #define SQLRS_NODE_ORDER 7      /* PhysicalOrder      mod.rs:189-199 */
 #define SQLRS_NODE_LIMIT 8      /* PhysicalLimit      mod.rs:176-187 */
+#define SQLRS_NODE_CROSS_JOIN 9 /* PhysicalCrossJoin  mod.rs:116-125 (child0 = left, child1 = right; join_output_schema) */
 
 typedef struct sqlrs_plan_node {
   int32_t kind;   /* SQLRS_NODE_* */

@@ -89,6 +89,10 @@ struct sqlrs_hash_join {
 struct sqlrs_project {
   Project impl;
 };
+struct sqlrs_cross_join {
+  CrossJoin impl;
+  std::deque<Batch> queue;
+};
 struct sqlrs_table {  // InMemoryTable (src/storage/memory.rs:62-123): the batches, as given
   std::vector<Batch> batches;
 };
@@ -181,6 +185,15 @@ struct sqlrs_plan {
         }
         Batch tail;
         if (j.finish(&tail)) out.push_back(tail);
+        return out;
+      }
+      case SQLRS_NODE_CROSS_JOIN: {
+        CrossJoin j;
+        j.out_fields = n.join_fields;
+        for (const Batch& b : run(n.raw.child0)) j.build_push(b);
+        std::vector<Batch> out;
+        for (const Batch& b : run(n.raw.child1))
+          for (Batch& r : j.probe(b)) out.push_back(std::move(r));
         return out;
       }
       case SQLRS_NODE_PROJECT: {
@@ -321,6 +334,36 @@ int sqlrs_oracle_hash_join_finish(sqlrs_hash_join* j, ArrowArray* out, ArrowSche
 }
 void sqlrs_oracle_hash_join_destroy(sqlrs_hash_join* j) { delete j; }
 
+int sqlrs_oracle_cross_join_create(const ArrowSchema* join_output_schema, const sqlrs_options*, sqlrs_cross_join** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    auto* j = new sqlrs_cross_join();
+    std::unique_ptr<sqlrs_cross_join> hold(j);
+    j->impl.out_fields = import_fields(join_output_schema);
+    *out = hold.release();
+  });
+}
+int sqlrs_oracle_cross_join_build_push(sqlrs_cross_join* j, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] { j->impl.build_push(consume_batch(batch, schema)); });
+}
+int sqlrs_oracle_cross_join_probe(sqlrs_cross_join* j, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] {
+    for (Batch& b : j->impl.probe(consume_batch(batch, schema))) j->queue.push_back(std::move(b));
+  });
+}
+int sqlrs_oracle_cross_join_next(sqlrs_cross_join* j, ArrowArray* out, ArrowSchema* out_schema, int32_t* has_batch) {
+  return guarded([&] {
+    if (j->queue.empty()) {
+      if (has_batch) *has_batch = 0;
+      return;
+    }
+    export_batch(j->queue.front(), out, out_schema);
+    j->queue.pop_front();
+    if (has_batch) *has_batch = 1;
+  });
+}
+void sqlrs_oracle_cross_join_destroy(sqlrs_cross_join* j) { delete j; }
+
 int sqlrs_oracle_project_create(const sqlrs_expr* exprs, const char* const* names, int32_t n_exprs, const sqlrs_options*,
                                 sqlrs_project** out) {
   return guarded([&] {
@@ -390,6 +433,7 @@ int sqlrs_oracle_plan_create(const sqlrs_plan_node* nodes, int32_t n_nodes, int3
         n.right_keys = copy_exprs(nodes[k].right_keys, nodes[k].n_keys);
         n.join_fields = import_fields(nodes[k].join_output_schema);
       }
+      if (nodes[k].kind == SQLRS_NODE_CROSS_JOIN) n.join_fields = import_fields(nodes[k].join_output_schema);
       if (nodes[k].kind == SQLRS_NODE_PROJECT || nodes[k].kind == SQLRS_NODE_ORDER) {
         n.exprs = copy_exprs(nodes[k].exprs, nodes[k].n_exprs);
         n.expr_names = copy_names(nodes[k].expr_names, nodes[k].n_exprs);

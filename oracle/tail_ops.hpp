@@ -3,6 +3,7 @@
 //   ProjectExecutor  src/executor/project.rs:6-29
 //   OrderExecutor    src/executor/order.rs:8-67   (arrow 28 lexsort_to_indices / sort_to_indices + take)
 //   LimitExecutor    src/executor/limit.rs:6-80
+//   CrossJoinExecutor src/executor/join/cross_join.rs:8-57 (pinned by tests/slt/join.slt:96-103)
 // Plan position in the reference: Agg -> Order -> Project -> Limit (src/planner/select.rs:34-45).
 //
 // Pinned by the reference's goldens: limit.rs:96-101 (six offset/limit cases over 1 and 3 batches),
@@ -124,6 +125,56 @@ struct Order {
     out.fields = all.fields;
     out.n = all.n;
     for (const ColPtr& c : all.cols) out.cols.push_back(take(*c, idx));
+    return out;
+  }
+};
+
+// ------------------------------------------------------------------ CrossJoin
+// cross_join.rs:26-56: the left side is drained and concatenated; for every right batch and every left row one output
+// batch = that row's scalars materialised to the right batch's length (build_scalar_value_array) + the right columns.
+struct CrossJoin {
+  std::vector<Field> out_fields;
+  std::vector<Batch> left_batches;
+  bool sealed = false;
+  Batch left_single;
+
+  void build_push(const Batch& b) {
+    if (sealed) fail(SQLRS_ERR_INVALID_ARG, "cross_join: build_push after probe");
+    left_batches.push_back(b);
+  }
+  void seal() {
+    if (sealed) return;
+    sealed = true;
+    if (left_batches.empty()) return;
+    left_single.fields = left_batches[0].fields;
+    for (size_t c = 0; c < left_single.fields.size(); c++) {
+      std::vector<ColPtr> parts;
+      for (const Batch& b : left_batches) {
+        if (b.cols.size() != left_single.fields.size()) fail(SQLRS_ERR_ARROW, "concat_batches: schema mismatch");
+        parts.push_back(b.cols[c]);
+      }
+      left_single.cols.push_back(concat_columns(parts));
+    }
+    for (const Batch& b : left_batches) left_single.n += b.n;
+  }
+  std::vector<Batch> probe(const Batch& right) {
+    seal();
+    std::vector<Batch> out;
+    if (left_batches.empty()) return out;  // :33-35
+    if (left_single.cols.size() + right.cols.size() != out_fields.size())
+      fail(SQLRS_ERR_ARROW, "number of columns must match number of fields in schema");
+    for (int64_t r = 0; r < left_single.n; r++) {
+      Batch b;
+      b.fields = out_fields;
+      b.n = right.n;
+      for (const ColPtr& c : left_single.cols) b.cols.push_back(scalar_to_column(Scalar::from_column(*c, r), right.n));
+      for (const ColPtr& c : right.cols) b.cols.push_back(c);
+      for (size_t k = 0; k < b.cols.size(); k++)
+        if (b.cols[k]->dtype != out_fields[k].dtype)
+          fail(SQLRS_ERR_ARROW, std::string("column types must match schema types, expected ") + dtype_name(out_fields[k].dtype) + " but found " +
+                                    dtype_name(b.cols[k]->dtype));
+      out.push_back(std::move(b));
+    }
     return out;
   }
 };

@@ -1,6 +1,8 @@
 // sqlrs_b200 — the extern "C" boundary of include/sqlrs_b200.h (symbols sqlrs_*), CUDA build.
 // Every entry point catches C++ exceptions and maps them to the status codes of the header; the
 // library never aborts the process (the reference panics in several of these places).
+#include <deque>
+
 #include "../../include/sqlrs_tpch_spec.h"
 #include "join.hpp"
 #include "kernels_aot.hpp"
@@ -77,6 +79,11 @@ struct sqlrs_order {
 struct sqlrs_limit {
   LimitOp op;
   sqlrs_limit(int64_t limit, int64_t offset, const Options& o) : op(limit, offset, o) {}
+};
+struct sqlrs_cross_join {
+  CrossJoinOp op;
+  std::deque<DBatch> queue;
+  sqlrs_cross_join(std::vector<Field> f, const Options& o) : op(std::move(f), o) {}
 };
 struct sqlrs_table {  // batches resident in HBM (columns shared with every plan they were pushed to)
   Ctx ctx;
@@ -240,6 +247,42 @@ int sqlrs_hash_join_finish(sqlrs_hash_join* j, ArrowArray* out, ArrowSchema* out
   });
 }
 void sqlrs_hash_join_destroy(sqlrs_hash_join* j) { delete j; }
+
+int sqlrs_cross_join_create(const ArrowSchema* join_output_schema, const sqlrs_options* options, sqlrs_cross_join** out) {
+  return guarded([&] {
+    if (!out) fail(SQLRS_ERR_INVALID_ARG, "out is NULL");
+    *out = new sqlrs_cross_join(import_fields(join_output_schema), copy_options(options));
+  });
+}
+int sqlrs_cross_join_build_push(sqlrs_cross_join* j, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!j) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    j->op.ctx().activate();
+    j->op.build_push(import_batch_host(j->op.ctx(), batch, schema));
+  });
+}
+int sqlrs_cross_join_probe(sqlrs_cross_join* j, ArrowArray* batch, const ArrowSchema* schema) {
+  return guarded([&] {
+    if (!j) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    j->op.ctx().activate();
+    DBatch b = import_batch_host(j->op.ctx(), batch, schema);
+    for (DBatch& r : j->op.probe(b)) j->queue.push_back(std::move(r));
+  });
+}
+int sqlrs_cross_join_next(sqlrs_cross_join* j, ArrowArray* out, ArrowSchema* out_schema, int32_t* has_batch) {
+  return guarded([&] {
+    if (!j) fail(SQLRS_ERR_INVALID_ARG, "handle is NULL");
+    if (j->queue.empty()) {
+      if (has_batch) *has_batch = 0;
+      return;
+    }
+    j->op.ctx().activate();
+    export_batch_host(j->op.ctx(), j->queue.front(), out, out_schema);
+    j->queue.pop_front();
+    if (has_batch) *has_batch = 1;
+  });
+}
+void sqlrs_cross_join_destroy(sqlrs_cross_join* j) { delete j; }
 
 int sqlrs_project_create(const sqlrs_expr* exprs, const char* const* names, int32_t n_exprs, const sqlrs_options* options,
                          sqlrs_project** out) {

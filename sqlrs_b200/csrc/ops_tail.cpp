@@ -90,6 +90,44 @@ DBatch slice_batch(Ctx& ctx, const DBatch& in, int64_t start, int64_t len) {
   return out;
 }
 
+// ------------------------------------------------------------------ CrossJoin, cross_join.rs:26-56
+CrossJoinOp::CrossJoinOp(std::vector<Field> out_fields, const Options& opt) : ctx_(opt), out_fields_(std::move(out_fields)) {}
+void CrossJoinOp::build_push(const DBatch& b) {
+  if (sealed_) fail(SQLRS_ERR_INVALID_ARG, "cross_join: build_push after probe");
+  left_batches_.push_back(b);
+}
+std::vector<DBatch> CrossJoinOp::probe(const DBatch& right) { return probe(ctx_, right); }
+std::vector<DBatch> CrossJoinOp::probe(Ctx& ctx, const DBatch& right) {
+  Trace tr("cross_join.probe", ctx.stream);
+  std::vector<DBatch> out;
+  if (!sealed_) {
+    sealed_ = true;
+    has_left_ = !left_batches_.empty();
+    if (has_left_) left_single_ = concat_batches(ctx, left_batches_);  // :37
+    left_batches_.clear();
+  }
+  if (!has_left_) return out;  // :33-35
+  if (left_single_.cols.size() + right.cols.size() != out_fields_.size())
+    fail(SQLRS_ERR_ARROW, "number of columns must match number of fields in schema");
+  const int64_t m = right.n;
+  for (int64_t r = 0; r < left_single_.n; r++) {  // :44-55: one batch per left row
+    BufPtr idx = dev_alloc(ctx, (size_t)std::max<int64_t>(m, 1) * 8);
+    launch_fill_u64((uint64_t*)idx->p, m, (uint64_t)r, ctx.stream);
+    DBatch b;
+    b.fields = out_fields_;
+    b.n = m;
+    for (const DCol& c : left_single_.cols) b.cols.push_back(gather_col_i64(ctx, c, (const int64_t*)idx->p, m, false));  // build_scalar_value_array
+    for (const DCol& c : right.cols) b.cols.push_back(c);
+    for (size_t k = 0; k < b.cols.size(); k++)
+      if (b.cols[k].dtype != out_fields_[k].dtype)
+        fail(SQLRS_ERR_ARROW, std::string("column types must match schema types, expected ") + dtype_name(out_fields_[k].dtype) + " but found " +
+                                  dtype_name(b.cols[k].dtype));
+    ctx.defer([idx]() {});
+    out.push_back(std::move(b));
+  }
+  return out;
+}
+
 // ------------------------------------------------------------------ Order, order.rs:14-66
 OrderOp::OrderOp(std::vector<ExprCopy> order_by, std::vector<bool> asc, const Options& opt)
     : ctx_(opt), order_by_(std::move(order_by)), asc_(std::move(asc)) {

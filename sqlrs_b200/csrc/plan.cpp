@@ -42,6 +42,7 @@ Plan::Plan(const sqlrs_plan_node* nodes, int32_t n_nodes, int32_t root, const Op
       }
       n.join_fields = import_fields(s.join_output_schema);
     }
+    if (s.kind == SQLRS_NODE_CROSS_JOIN) n.join_fields = import_fields(s.join_output_schema);
     if (s.kind == SQLRS_NODE_PROJECT || s.kind == SQLRS_NODE_ORDER) {
       if (s.n_exprs < 1 || !s.exprs) fail(SQLRS_ERR_INVALID_ARG, "plan: Project / Order need at least one expression");
       for (int32_t q = 0; q < s.n_exprs; q++) {
@@ -67,6 +68,7 @@ Plan::Plan(const sqlrs_plan_node* nodes, int32_t n_nodes, int32_t root, const Op
       case SQLRS_NODE_ORDER:
       case SQLRS_NODE_LIMIT: check_child(s.child0); break;
       case SQLRS_NODE_HASH_JOIN:
+      case SQLRS_NODE_CROSS_JOIN:
         check_child(s.child0);
         check_child(s.child1);
         break;
@@ -228,7 +230,8 @@ int Plan::width_of(int idx) {
     case SQLRS_NODE_ORDER:
     case SQLRS_NODE_LIMIT: return width_of(n.child0);
     case SQLRS_NODE_PROJECT: return (int)n.exprs.size();
-    case SQLRS_NODE_HASH_JOIN: return (int)n.join_fields.size();
+    case SQLRS_NODE_HASH_JOIN:
+    case SQLRS_NODE_CROSS_JOIN: return (int)n.join_fields.size();
     default: return (int)(n.group_by.size() + n.aggs.size());
   }
 }
@@ -278,6 +281,15 @@ std::vector<DBatch> Plan::run(int idx, const Needed& needed) {
       DBatch r = run_agg(idx).finish_device();
       description_ += "[aggregate finalised on the device] ";
       return {r};
+    }
+    case SQLRS_NODE_CROSS_JOIN: {
+      CrossJoinOp j(n.join_fields, opt_);
+      description_ += "[CrossJoin: one batch per left row (fill + gather), right columns shared] ";
+      for (const DBatch& b : run(n.child0, Needed())) j.build_push(b);
+      std::vector<DBatch> out;
+      for (const DBatch& b : run(n.child1, Needed()))
+        for (DBatch& r : j.probe(ctx_, b)) out.push_back(std::move(r));
+      return out;
     }
     case SQLRS_NODE_PROJECT: {
       if (!n.project_op) n.project_op = std::make_unique<ProjectOp>(n.exprs, n.expr_names, n.keep_field, opt_);

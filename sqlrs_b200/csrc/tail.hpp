@@ -67,6 +67,25 @@ class LimitOp {
   bool done_ = false;
 };
 
+// CrossJoinExecutor, reference src/executor/join/cross_join.rs:8-57: the left side is drained and concatenated; every
+// right batch yields ONE output batch per left row (that row repeated to the right batch's length + the right columns,
+// which are shared, not copied).  Built from the take / fill primitives only — a cross join is not on the hot path.
+class CrossJoinOp {
+ public:
+  CrossJoinOp(std::vector<Field> out_fields, const Options& opt);
+  void build_push(const DBatch& b);
+  std::vector<DBatch> probe(const DBatch& right);
+  std::vector<DBatch> probe(Ctx& ctx, const DBatch& right);
+  Ctx& ctx() { return ctx_; }
+
+ private:
+  Ctx ctx_;
+  std::vector<Field> out_fields_;
+  std::vector<DBatch> left_batches_;
+  bool sealed_ = false, has_left_ = false;
+  DBatch left_single_;
+};
+
 // rows [start, start + len) of a batch as a new batch (RecordBatch::slice materialised)
 DBatch slice_batch(Ctx& ctx, const DBatch& in, int64_t start, int64_t len);
 DBatch concat_batches(Ctx& ctx, const std::vector<DBatch>& batches);

@@ -190,6 +190,46 @@ class HashJoinExecutor:
             lib.hash_join_destroy(h)
 
 
+class CrossJoinExecutor:
+    """src/executor/join/cross_join.rs:8-57: one output batch per (right batch, left row)"""
+
+    def __init__(self, left_child, right_child, join_output_schema: pa.Schema, lib=None, options=None):
+        self.left_child, self.right_child, self.join_output_schema = left_child, right_child, join_output_schema
+        self.lib = _lib(lib)
+        self.options = options if options is not None else self.lib.options()
+
+    def execute(self) -> Iterator[pa.RecordBatch]:
+        lib = self.lib
+        out_schema_c = ffi.export_schema(self.join_output_schema)
+        h = C.c_void_p()
+        try:
+            lib.check(lib.cross_join_create(C.byref(out_schema_c), C.byref(self.options), C.byref(h)))
+        finally:
+            ffi.release_schema(out_schema_c)
+        try:
+            for batch in self.left_child:
+                arr, sch = ffi.export_batch(batch)
+                try:
+                    lib.check(lib.cross_join_build_push(h, C.byref(arr), C.byref(sch)))
+                finally:
+                    ffi.release_schema(sch)
+            has = C.c_int32(0)
+            for batch in self.right_child:
+                arr, sch = ffi.export_batch(batch)
+                try:
+                    lib.check(lib.cross_join_probe(h, C.byref(arr), C.byref(sch)))
+                finally:
+                    ffi.release_schema(sch)
+                while True:
+                    out, out_sch = ffi.ArrowArray(), ffi.ArrowSchema()
+                    lib.check(lib.cross_join_next(h, C.byref(out), C.byref(out_sch), C.byref(has)))
+                    if not has.value:
+                        break
+                    yield _import(out, out_sch)
+        finally:
+            lib.cross_join_destroy(h)
+
+
 class ProjectExecutor:
     """src/executor/project.rs:6-29"""
 

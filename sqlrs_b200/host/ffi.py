@@ -27,7 +27,7 @@ COUNT_REFERENCE_OVERWRITE, COUNT_SQL_ACCUMULATE = 0, 1
 MATCH_HASH_ONLY, MATCH_HASH_AND_KEY = 0, 1
 FLAG_NO_FUSION = 1
 FLAG_TIMING = 4
-NODE_SCAN, NODE_FILTER, NODE_SIMPLE_AGG, NODE_HASH_AGG, NODE_HASH_JOIN, NODE_PROJECT, NODE_ORDER, NODE_LIMIT = 1, 2, 3, 4, 5, 6, 7, 8
+NODE_SCAN, NODE_FILTER, NODE_SIMPLE_AGG, NODE_HASH_AGG, NODE_HASH_JOIN, NODE_PROJECT, NODE_ORDER, NODE_LIMIT, NODE_CROSS_JOIN = 1, 2, 3, 4, 5, 6, 7, 8, 9
 ABI_VERSION = 2
 TPCH_CUSTOMER, TPCH_ORDERS, TPCH_LINEITEM = 0, 1, 2
 TPCH_FLAGS_8GROUP, TPCH_FLAGS_SPEC = 0, 1
@@ -201,6 +201,11 @@ _SIGNATURES = {
     "hash_join_probe": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema), P(ArrowArray), P(ArrowSchema), P(C.c_int32)]),
     "hash_join_finish": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema), P(C.c_int32)]),
     "hash_join_destroy": (None, [C.c_void_p]),
+    "cross_join_create": (C.c_int, [P(ArrowSchema), P(Options), P(C.c_void_p)]),
+    "cross_join_build_push": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema)]),
+    "cross_join_probe": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema)]),
+    "cross_join_next": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema), P(C.c_int32)]),
+    "cross_join_destroy": (None, [C.c_void_p]),
     "project_create": (C.c_int, [P(Expr), P(C.c_char_p), C.c_int32, P(Options), P(C.c_void_p)]),
     "project_execute": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema), P(ArrowArray), P(ArrowSchema)]),
     "project_destroy": (None, [C.c_void_p]),

@@ -82,6 +82,17 @@ class PhysicalHashJoin(PlanNode):
 
 
 @dataclass
+class PhysicalCrossJoin(PlanNode):
+    """PhysicalCrossJoin{left, right, join_output_columns} (physical_cross_join.rs)"""
+    left: PlanNode
+    right: PlanNode
+    join_output_schema: pa.Schema
+
+    def output_schema(self, tables):
+        return self.join_output_schema
+
+
+@dataclass
 class PhysicalProject(PlanNode):
     """PhysicalProject{exprs, input} (physical_project.rs)"""
     exprs: Sequence[BoundExpr]
@@ -163,6 +174,13 @@ class GpuPlan:
                     flat = node.join_condition.filter.flatten()
                     self._keep.append(flat)
                     rec.predicate = flat.c
+                sch = ffi.export_schema(node.join_output_schema)
+                self._keep.append(sch)
+                rec.join_output_schema = C.pointer(sch)
+            elif isinstance(node, PhysicalCrossJoin):
+                rec.kind = ffi.NODE_CROSS_JOIN
+                rec.child0 = add(node.left)
+                rec.child1 = add(node.right)
                 sch = ffi.export_schema(node.join_output_schema)
                 self._keep.append(sch)
                 rec.join_output_schema = C.pointer(sch)

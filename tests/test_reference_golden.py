@@ -411,3 +411,41 @@ def test_in_memory_storage_resident_tables(lib):
             p.reset()
         p.close()
     table.close()
+
+
+# ---------------------------------------------------------------- CrossJoin, src/executor/join/cross_join.rs
+def test_slt_cross_join(lib):
+    """join.slt:96-103: `select t1.*, t2.* from t1 cross join t2 where t1.a = 0` -> the t1 row (0,4,7) next to every t2 row.
+    cross_join.rs:41-55 yields ONE batch per (right batch, left row); an empty left side yields nothing (:33-35)"""
+    left = ex.try_collect(ex.FilterExecutor(bind_binary_op(InputRef(0, I64), "=", Constant(0)), [t1()], lib=lib).execute())
+    right = t2()
+    schema = _join_schema(t1(), "t1", right, "t2", "Inner")
+    out = ex.try_collect(ex.CrossJoinExecutor(left, [right], schema, lib=lib).execute())
+    assert len(out) == 1 and out[0].schema.names == ["t1.a", "t1.b", "t1.c", "t2.a", "t2.b", "t2.c"]
+    assert rows_of(out) == [(0, 4, 7, 10, 2, 7), (0, 4, 7, 20, 2, 5), (0, 4, 7, 30, 3, 6), (0, 4, 7, 40, 4, 6)]
+    # all of t1 (two left batches) x t2 in two right batches: 4 left rows x 2 right batches = 8 output batches, left row major
+    # within a right batch
+    out = ex.try_collect(ex.CrossJoinExecutor([t1().slice(0, 1), t1().slice(1)], [right.slice(0, 3), right.slice(3)], schema, lib=lib).execute())
+    assert [b.num_rows for b in out] == [3, 3, 3, 3, 1, 1, 1, 1]
+    assert rows_of(out[:4]) == [l + r for l in rows_of([t1()]) for r in rows_of([right.slice(0, 3)])]
+    assert rows_of(out[4:]) == [l + (40, 4, 6) for l in rows_of([t1()])]
+    assert ex.try_collect(ex.CrossJoinExecutor([], [right], schema, lib=lib).execute()) == []
+    # a NULL left cell is repeated as NULL (build_scalar_value_array of a None scalar)
+    emp, dep = employee_numeric(), department_numeric()
+    es = _join_schema(emp, "employee", dep, "department", "Full")
+    out = ex.try_collect(ex.CrossJoinExecutor([emp.slice(3)], [dep], es, lib=lib).execute())
+    assert rows_of(out) == [(4, N, N, 1), (4, N, N, 2), (4, N, N, 3), (4, N, N, 4)]
+
+
+def test_plan_cross_join_then_filter(lib):
+    """the plan shape of join.slt:96-103 before predicate push-down: Filter(CrossJoin(scan t1, scan t2))"""
+    from sqlrs_b200.host.plan import ExecutorBuilder, PhysicalCrossJoin, PhysicalFilter, PhysicalTableScan
+
+    schema = _join_schema(t1(), "t1", t2(), "t2", "Inner")
+    plan = PhysicalFilter(bind_binary_op(InputRef(0, I64), "=", Constant(0)), PhysicalCrossJoin(PhysicalTableScan(0), PhysicalTableScan(1), schema))
+    p = ExecutorBuilder(lib).build(plan, {0: t1().schema, 1: t2().schema})
+    p.push_table(0, t1())
+    p.push_table(1, t2())
+    out = p.run()
+    p.close()
+    assert rows_of(out) == [(0, 4, 7, 10, 2, 7), (0, 4, 7, 20, 2, 5), (0, 4, 7, 30, 3, 6), (0, 4, 7, 40, 4, 6)]
