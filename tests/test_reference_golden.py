@@ -10,6 +10,9 @@ GPU box, against the CUDA library (`-m gpu`).  Fixtures are the reference's test
 Utf8 columns are outside the CUDA backend's scope: string cases run on the
 oracle only, numeric projections of the same tables on both.
 """
+import json
+import os
+
 import pyarrow as pa
 import pytest
 
@@ -20,6 +23,12 @@ from util import batch, rows_of
 
 I32, I64, F64, BOOL = ffi.DT_INT32, ffi.DT_INT64, ffi.DT_FLOAT64, ffi.DT_BOOL
 N = None
+# the reference's vectors as a committed fixture (tests/golden/reference_vectors.json, each entry cites its source)
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.json")))
+
+
+def _tuples(rows):
+    return [tuple(r) for r in rows]
 
 
 # ---------------------------------------------------------------- fixtures = the reference's data
@@ -48,8 +57,8 @@ def mem_employee():
 # ---------------------------------------------------------------- hash KAT
 def test_hash_kat(lib):
     """hash_utils.rs:229-247: two identical Float64 columns -> pinned u64 hashes"""
-    a = pa.array([0.12, 0.5, 1.0, 444.7])
-    assert ex.create_hashes([a, a], lib=lib) == [13192744372685867462, 5527281222425499956, 3851526787237496334, 1092489821776418240]
+    g = GOLDEN["hash_kat"]
+    assert ex.create_hashes([pa.array(c) for c in g["columns"]], lib=lib) == g["hashes"]
 
 
 def test_hash_single_column_and_null(lib):
@@ -143,12 +152,7 @@ def _join_schema(left, lname, right, rname, join_type):
     return pa.schema(fields)
 
 
-JOIN_EXPECTED = {  # hash_join.rs:442-450, 473-483, 506-515, 538-549
-    "Inner": [(1, 4, 7, 10, 4, 70), (2, 5, 8, 20, 5, 80), (3, 5, 9, 20, 5, 80)],
-    "Left": [(1, 4, 7, 10, 4, 70), (2, 5, 8, 20, 5, 80), (3, 5, 9, 20, 5, 80), (0, 0, 10, N, N, N), (4, 8, 10, N, N, N)],
-    "Right": [(1, 4, 7, 10, 4, 70), (2, 5, 8, 20, 5, 80), (3, 5, 9, 20, 5, 80), (N, N, N, 30, 6, 90)],
-    "Full": [(1, 4, 7, 10, 4, 70), (2, 5, 8, 20, 5, 80), (3, 5, 9, 20, 5, 80), (N, N, N, 30, 6, 90), (0, 0, 10, N, N, N), (4, 8, 10, N, N, N)],
-}
+JOIN_EXPECTED = {jt: _tuples(GOLDEN["hash_join"][jt]) for jt in ("Inner", "Left", "Right", "Full")}  # hash_join.rs:442-549
 
 
 @pytest.mark.parametrize("join_type", ["Inner", "Left", "Right", "Full"])
@@ -162,12 +166,7 @@ def test_hash_join_results(lib, join_type):
     assert rows_of(out) == JOIN_EXPECTED[join_type]
 
 
-JOIN_FILTER_EXPECTED = {  # hash_join.rs:620-627, 657-667, 697-706, 736-748 (key l.a = r.b, filter l.c > r.c)
-    "Inner": [(2, 7, 9, 10, 2, 7), (2, 7, 9, 20, 2, 5)],
-    "Left": [(2, 7, 9, 10, 2, 7), (2, 7, 9, 20, 2, 5), (0, 4, 7, N, N, N), (1, 5, 8, N, N, N), (2, 8, 1, N, N, N)],
-    "Right": [(2, 7, 9, 10, 2, 7), (2, 7, 9, 20, 2, 5), (N, N, N, 30, 3, 6), (N, N, N, 40, 4, 6)],
-    "Full": [(2, 7, 9, 10, 2, 7), (2, 7, 9, 20, 2, 5), (N, N, N, 30, 3, 6), (N, N, N, 40, 4, 6), (0, 4, 7, N, N, N), (1, 5, 8, N, N, N), (2, 8, 1, N, N, N)],
-}
+JOIN_FILTER_EXPECTED = {jt: _tuples(GOLDEN["hash_join_filter"][jt]) for jt in ("Inner", "Left", "Right", "Full")}  # hash_join.rs:620-748
 JOIN_NOFILTER_T1T2 = {  # tests/slt/join_filter.slt: t1.a = t2.b without the non-equi part
     "Inner": [(2, 7, 9, 10, 2, 7), (2, 8, 1, 10, 2, 7), (2, 7, 9, 20, 2, 5), (2, 8, 1, 20, 2, 5)],
     "Left": [(2, 7, 9, 10, 2, 7), (2, 8, 1, 10, 2, 7), (2, 7, 9, 20, 2, 5), (2, 8, 1, 20, 2, 5), (0, 4, 7, N, N, N), (1, 5, 8, N, N, N)],
@@ -260,14 +259,7 @@ def _range_chunk(lo, hi):
     return batch(["a"], list(range(lo, hi)), types=[pa.int32()], nullable=False)
 
 
-@pytest.mark.parametrize("inputs,offset,limit,outputs", [  # limit.rs:96-101
-    ([(0, 6)], 1, 4, [(1, 5)]),
-    ([(0, 6)], 0, 10, [(0, 6)]),
-    ([(0, 6)], 10, 0, []),
-    ([(0, 2), (2, 4), (4, 6)], 1, 4, [(1, 2), (2, 4), (4, 5)]),
-    ([(0, 2), (2, 4), (4, 6)], 1, 2, [(1, 2), (2, 3)]),
-    ([(0, 2), (2, 4), (4, 6)], 3, 0, []),
-])
+@pytest.mark.parametrize("inputs,offset,limit,outputs", [tuple(c) for c in GOLDEN["limit_cases"]["cases"]])  # limit.rs:96-101
 def test_limit_executor_cases(lib, inputs, offset, limit, outputs):
     out = ex.try_collect(ex.LimitExecutor(limit, offset, [_range_chunk(*r) for r in inputs], lib=lib).execute())
     assert [b.column(0).to_pylist() for b in out] == [list(range(*r)) for r in outputs]
