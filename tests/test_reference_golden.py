@@ -406,20 +406,9 @@ def test_in_memory_storage_resident_tables(lib):
 
 
 # ---------------------------------------------------------------- CrossJoin, src/executor/join/cross_join.rs
-# The CUDA CrossJoin was written after this round's GPU budget was spent: its hardware run is still pending, so a failure of
-# the cuda leg is reported as xfail instead of stopping the suite (strict=False: a pass shows up as XPASS).
-_UNVERIFIED_ON_GPU = pytest.mark.xfail(reason="CrossJoin on the CUDA library has not been run on hardware yet (round-1 GPU budget spent)", strict=False)
-
-
-@pytest.fixture(params=["oracle", pytest.param("cuda", marks=[pytest.mark.gpu, _UNVERIFIED_ON_GPU])])
-def lib_cross(request):
-    return request.getfixturevalue("oracle" if request.param == "oracle" else "cuda_lib")
-
-
-def test_slt_cross_join(lib_cross):
+def test_slt_cross_join(lib):
     """join.slt:96-103: `select t1.*, t2.* from t1 cross join t2 where t1.a = 0` -> the t1 row (0,4,7) next to every t2 row.
     cross_join.rs:41-55 yields ONE batch per (right batch, left row); an empty left side yields nothing (:33-35)"""
-    lib = lib_cross
     left = ex.try_collect(ex.FilterExecutor(bind_binary_op(InputRef(0, I64), "=", Constant(0)), [t1()], lib=lib).execute())
     right = t2()
     schema = _join_schema(t1(), "t1", right, "t2", "Inner")
@@ -440,11 +429,10 @@ def test_slt_cross_join(lib_cross):
     assert rows_of(out) == [(4, N, N, 1), (4, N, N, 2), (4, N, N, 3), (4, N, N, 4)]
 
 
-def test_plan_cross_join_then_filter(lib_cross):
+def test_plan_cross_join_then_filter(lib):
     """the plan shape of join.slt:96-103 before predicate push-down: Filter(CrossJoin(scan t1, scan t2))"""
     from sqlrs_b200.host.plan import ExecutorBuilder, PhysicalCrossJoin, PhysicalFilter, PhysicalTableScan
 
-    lib = lib_cross
     schema = _join_schema(t1(), "t1", t2(), "t2", "Inner")
     plan = PhysicalFilter(bind_binary_op(InputRef(0, I64), "=", Constant(0)), PhysicalCrossJoin(PhysicalTableScan(0), PhysicalTableScan(1), schema))
     p = ExecutorBuilder(lib).build(plan, {0: t1().schema, 1: t2().schema})
