@@ -374,7 +374,11 @@ int SQLRS_API(plan_finish_partial)(sqlrs_plan* p);
  * header {number of groups (may exceed cap_rows: then rows are missing and the caller must fall back to the
  * host path)}, row 1+i = [hash, min_row, null mask, key bits..., accumulator words...] — and the merge of
  * n_buffers such buffers laid out back to back (e.g. the output of an all-gather).  The oracle build returns
- * SQLRS_ERR_UNSUPPORTED for the two _device calls. */
+ * SQLRS_ERR_UNSUPPORTED for the two _device calls.
+ * Stream contract: with sqlrs_options.stream set, export writes `dst` and merge reads `src` ON THAT STREAM — enqueue the
+ * collective on the same stream (or order it with events).  With options.stream == NULL the plan owns a private
+ * non-blocking stream: export then synchronises before it returns (dst is complete for any stream), and the caller
+ * must have completed the writes to `src` (synchronise its own stream) before calling merge. */
 int SQLRS_API(plan_partials_row_words)(sqlrs_plan* p, int32_t* n_words);
 int SQLRS_API(plan_export_partials_device)(sqlrs_plan* p, void* dst, int64_t cap_rows);
 int SQLRS_API(plan_merge_partials_device)(sqlrs_plan* p, const void* src, int32_t n_buffers, int64_t cap_rows);

@@ -194,6 +194,9 @@ int Plan::partial_row_words() const {
 void Plan::export_partials_device(uint64_t* dst, int64_t cap_rows) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
   partial_op_->export_partials_device(dst, cap_rows);
+  // a plan that owns its stream (options.stream == NULL) has no stream the caller could order against: the buffer is
+  // complete when the call returns.  With a caller-provided stream the pack is ordered on that stream.
+  if (ctx_.own_stream) SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
 }
 void Plan::merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
@@ -298,8 +301,10 @@ std::vector<DBatch> Plan::run(int idx, const Needed& needed) {
         const int w = width_of(n.child0);
         if (w > 0) {
           child_need.assign((size_t)w, false);
-          for (size_t k = 0; k < n.exprs.size(); k++)
-            if (is_needed(k)) mark_refs(n.exprs[k], child_need);
+          // ProjectOp evaluates EVERY expression, as the reference does (project.rs:20-24: an error in a select item
+          // nobody reads still ends the stream), so every expression's inputs must arrive — not only those of the
+          // columns the parent reads
+          for (size_t k = 0; k < n.exprs.size(); k++) mark_refs(n.exprs[k], child_need);
         }
       }
       description_ += "[Project: sq_eval_kernel] ";

@@ -179,6 +179,10 @@ def partition_by_owner(partials: pa.RecordBatch, world: int) -> List[pa.RecordBa
     return [partials.filter(pa.array(owner == r)) for r in range(world)]
 
 
+def _plan_stream(plan) -> int:
+    return int(getattr(plan.options, "stream", None) or 0)
+
+
 def _device_exchange(plan, group: TorchGroup, cap_rows: int):
     """Fast path for few groups (NCCL): partial groups never leave HBM.  Every rank packs its groups into a
     fixed-size device buffer, ONE all-gather over NVLink hands all of them to every rank, rank 0 folds them.
@@ -193,8 +197,15 @@ def _device_exchange(plan, group: TorchGroup, cap_rows: int):
         bufs[key] = (torch.empty(n, dtype=torch.int64, device=group.device), torch.empty(n * group.world, dtype=torch.int64, device=group.device))
         group._bufs = bufs
     send, recv = bufs[key]
+    # stream contract (include/sqlrs_b200.h): a plan on the caller's stream packs in stream order with the collective;
+    # a plan that owns its stream synchronises inside export, and needs the gathered buffer complete before the merge
+    shared_stream = _plan_stream(plan) == torch.cuda.current_stream(group.device).cuda_stream
+    if _plan_stream(plan) and not shared_stream:
+        raise ValueError("sharded_aggregate: options.stream must be torch's current stream (or NULL)")
     lib.check(lib.plan_export_partials_device(plan.handle, C.c_void_p(send.data_ptr()), cap_rows))
     group.dist.all_gather_into_tensor(recv, send)
+    if not shared_stream:
+        torch.cuda.current_stream(group.device).synchronize()
     counts = recv.view(group.world, cap_rows + 1, words.value)[:, 0, 0]
     if int(counts.max().item()) > cap_rows:
         return None

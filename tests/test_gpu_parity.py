@@ -327,6 +327,55 @@ def test_generator_is_bit_identical_on_device(cuda_lib, oracle):
             assert np.array_equal(t.cpu().numpy(), want.view(np.int64)), (table, c)
 
 
+# ------------------------------------------------------------------ BASELINE.json configs[1] / configs[2] at their full size, vs the oracle
+def _assert_tables_equal(got, exp, rtol):
+    """Vectorised: every integer column and the row order bit-exact, Float64 within rtol (north star: 1e-6)."""
+    got, exp = pa.Table.from_batches(got).combine_chunks(), pa.Table.from_batches(exp).combine_chunks()
+    assert got.schema.names == exp.schema.names and got.num_rows == exp.num_rows, (got.schema, exp.schema, got.num_rows, exp.num_rows)
+    for name in got.schema.names:
+        g, w = got.column(name), exp.column(name)
+        assert g.null_count == w.null_count == 0, name
+        g, w = g.to_numpy(), w.to_numpy()
+        if g.dtype.kind == "f":
+            bad = np.abs(g - w) > rtol * np.abs(w)
+            assert not bad.any(), (name, int(bad.sum()), g[bad][:5], w[bad][:5])
+        else:
+            assert np.array_equal(g, w), (name, int((g != w).sum()))
+
+
+def test_q3_sf10_bit_exact_vs_oracle(cuda_lib, oracle):
+    """BASELINE.json configs[2]: "TPC-H Q3 SF10 ... bit-exact row check" — 76.5 M input rows, ~113 k result groups: keys,
+    group order (first appearance, hash_agg.rs:98,134) exact; SUM(float) <= 1e-6 relative.  The oracle runs the reference's
+    per-batch algorithm on one batch per table (~5 s)."""
+    d = tpch.dims(10)
+    plan, schemas = tpch.q3_plan()
+    tables = _tables(oracle, d)
+    opts = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    got, desc = _run_plan(cuda_lib, plan, schemas, tables, None, **opts)
+    exp, _ = _run_plan(oracle, plan, schemas, tables, None, **opts)
+    assert sum(b.num_rows for b in exp) > 50_000
+    _assert_tables_equal(got, exp, 1e-6)
+    # the whole query (ORDER BY revenue desc, o_orderdate LIMIT 10 on the device) against the oracle's own Order/Limit
+    full, _ = tpch.q3_full_plan()
+    got10, _ = _run_plan(cuda_lib, full, schemas, tables, None, **opts)
+    exp10, _ = _run_plan(oracle, full, schemas, tables, None, **opts)
+    assert sum(b.num_rows for b in got10) == 10
+    _assert_tables_equal(got10, exp10, 1e-6)
+
+
+@pytest.mark.parametrize("batch_rows", [None, 1 << 22])
+def test_q1_sf10_bit_exact_vs_oracle(cuda_lib, oracle, batch_rows):
+    """BASELINE.json configs[1]: Q1' SF10 (60 M rows): 8 groups, COUNT and the int64 SUM exact, Float64 sums <= 1e-6."""
+    d = tpch.dims(10)
+    plan, schemas = tpch.q1_plan()
+    table = {0: tpch.host_table(oracle, d, tpch.LINEITEM, columns=tpch.Q1_COLUMNS)}
+    opts = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    got, _ = _run_plan(cuda_lib, plan, schemas, table, batch_rows, **opts)
+    exp, _ = _run_plan(oracle, plan, schemas, table, 1 << 22, **opts)
+    assert exp[0].num_rows == 8
+    _assert_tables_equal(got, exp, 1e-6)
+
+
 # ------------------------------------------------------------------ full size: properties that need no oracle pass
 def test_q1_full_size_properties(cuda_lib):
     """BASELINE config 2 size (SF10, ~60 M rows, resident in HBM): integer checksums and linearity"""
