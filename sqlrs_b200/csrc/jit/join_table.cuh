@@ -19,7 +19,12 @@ struct SqJoin {           // mirrors sq::JoinTableView (kernels_aot.hpp)
   const u64* bloom;       // blocked Bloom filter over the build hashes (3 bits in one 64-bit word per key)
   u32 bloom_mask;
   int unique;             // every build key occurs once: the match list of a slot is its representative row
+  const u64* kv;          // key-in-slot layout (single key compared by value): kv[2s] = key bits, kv[2s+1] = representative row
+  int kv_dtype;
+  int rep_stride;         // slot_rep[slot * rep_stride] (2 in kv mode, where slot_rep = kv + 1)
+  i64 n_inserted;
 };
+#define SQ_KV_EMPTY 0xffffffffffffffffULL
 
 __device__ __forceinline__ u32 sq_bloom_word(u64 h, u32 mask) { return (u32)((h * 0x9E3779B97F4A7C15ULL) >> 40) & mask; }
 __device__ __forceinline__ u64 sq_bloom_bits(u64 h) {
@@ -27,12 +32,28 @@ __device__ __forceinline__ u64 sq_bloom_bits(u64 h) {
   return (1ULL << ((g >> 34) & 63)) | (1ULL << ((g >> 28) & 63)) | (1ULL << ((g >> 22) & 63));
 }
 
-__device__ __forceinline__ int sq_join_find(const SqJoin& t, const SqProbe& p) {
+// exact lookup: the matched slot (or -1) and its representative build row
+__device__ __forceinline__ int sq_join_find_rep(const SqJoin& t, const SqProbe& p, i64& rep_out) {
 #if SQ_JMATCH
   if (p.knull != 0u) return -1;  // SQL semantics: a NULL key never joins
 #endif
   const u32 mask = t.capacity - 1;
   u32 s = sq_mix32(p.h) & mask;
+#if SQ_JMATCH && SQ_JKEYS == 1
+  if (t.kv) {  // ONE 16-byte read per probe step: {key bits, representative row}
+    if (t.kv_dtype != SQ_JKEY0_DTYPE || p.kb[0] == SQ_KV_EMPTY) return -1;
+    for (u32 probes = 0; probes <= mask; probes++) {
+      const ulonglong2 e = __ldg((const ulonglong2*)t.kv + s);
+      if (e.x == p.kb[0]) {
+        rep_out = (i64)e.y;
+        return (int)s;
+      }
+      if (e.x == SQ_KV_EMPTY) return -1;
+      s = (s + 1) & mask;
+    }
+    return -1;
+  }
+#endif
   for (u32 probes = 0; probes <= mask; probes++) {
     const i64 rep = __ldg(&t.slot_rep[s]);
     if (rep < 0) return -1;
@@ -41,8 +62,12 @@ __device__ __forceinline__ int sq_join_find(const SqJoin& t, const SqProbe& p) {
       bool same = true;
 #pragma unroll
       for (int k = 0; k < SQ_JKEYS; k++) same = same && (__ldg(&t.keys[(size_t)k * t.n_build + rep]) == p.kb[k]);
-      if (same) return (int)s;
+      if (same) {
+        rep_out = rep;
+        return (int)s;
+      }
 #else
+      rep_out = rep;
       return (int)s;
 #endif
     }
@@ -50,4 +75,7 @@ __device__ __forceinline__ int sq_join_find(const SqJoin& t, const SqProbe& p) {
   }
   return -1;
 }
-
+__device__ __forceinline__ int sq_join_find(const SqJoin& t, const SqProbe& p) {
+  i64 rep;
+  return sq_join_find_rep(t, p, rep);
+}

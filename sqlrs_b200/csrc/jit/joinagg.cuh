@@ -36,14 +36,15 @@ __device__ __forceinline__ void sq_joinagg_candidate(const SqIn& in, const SqInB
   SqProbe p;
   bool e0 = false, e1 = false;
   sq_probe_row(in, r, p, e0, e1);  // re-evaluated (L1/L2 hits): cheaper than queueing hash + key tuple
-  const int slot = sq_join_find(jt, p);
+  i64 rep = -1;
+  const int slot = sq_join_find_rep(jt, p, rep);
   if (slot < 0) return;
   // unique build keys (a primary-key side): the slot's representative row IS its match list — three dependent
   // random reads (count, range start, row id) less per match
   const u32 cnt = jt.unique ? 1u : __ldg(&jt.slot_count[slot]);
-  const i64* brow = jt.unique ? jt.slot_rep + slot : jt.rows + __ldg(&jt.slot_start[slot]);
+  const i64* brow = jt.unique ? nullptr : jt.rows + __ldg(&jt.slot_start[slot]);
   for (u32 j = 0; j < cnt; j++) {  // per probe row: build rows in insertion order (hash_join.rs:225-235)
-    const i64 b = __ldg(&brow[j]);
+    const i64 b = jt.unique ? rep : __ldg(&brow[j]);
     SqRow o;
     bool e2 = false;
     sq_row(in, inb, r, b, o, e2);

@@ -19,6 +19,8 @@ struct ProbeProgram {
   std::vector<int> tile_cols;
 };
 ProbeProgram gen_probe_program(const std::vector<ColInfo>& cols, const std::vector<ExprCopy>& right_keys, const ExprCopy& probe_pred, bool jmatch);
+// struct SqInB + the SQ_LDB_* / SQ_VALIDB macros: the build side of a joined-mode row program (RowProgram(build_cols, probe_cols))
+std::string gen_build_decls(const std::vector<ColInfo>& build_cols);
 
 class JoinOp {
  public:
@@ -42,6 +44,10 @@ class JoinOp {
   const std::vector<ExprCopy>& right_keys() const { return right_keys_; }
   const ExprCopy& join_filter() const { return filter_; }
   bool match_keys() const { return opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY; }
+  const std::vector<Field>& out_fields() const { return out_fields_; }
+  // a build side produced elsewhere (JoinChainOp: the previous join's probe built this table directly): `build` is the
+  // (virtual) build batch the table's row ids index, `keep` the buffers the view points into
+  void adopt_build(DBatch build, const struct JoinTableView& view, std::vector<BufPtr> keep);
   // generated CUDA of the fused probe kernel for probe batches of that schema (diagnostics / build check, no GPU)
   std::string debug_probe_source(const std::vector<ColInfo>& probe_cols, const ExprCopy& probe_pred) const;
 
@@ -57,6 +63,40 @@ class JoinOp {
   ExprCopy filter_;
   std::vector<Field> out_fields_;
   std::unique_ptr<Impl> impl_;
+};
+
+// Left-deep join chains: join 1's probe builds join 2's table directly (csrc/jit/joinchain.cuh), nothing of join 1's output
+// is materialised.  Applies to: INNER joins with key comparison, join 1 without non-equi filter and with unique build keys
+// (found at seal), ONE probe batch, join 2 with a single key over join 1's probe-side columns, and no build-1 column read
+// above.  Table 2 is sized from a strided sample count of join 1's matches, or — on repeated runs of the same plan over
+// tables of the same size — from the previous run's exact count; in that case nothing synchronises and the run is
+// validated afterwards (validate()): a table that turned out too small, a repeated or unrepresentable key make the
+// plan fall back to the operator-at-a-time path.
+class JoinChainOp {
+ public:
+  explicit JoinChainOp(const Options& opt);
+  ~JoinChainOp();
+  // false = the chain does not apply (caller builds join 2 the ordinary way)
+  bool run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pred1, const ExprCopy& key2, JoinOp& j2);
+  bool pending() const { return pending_; }
+  bool validate();  // after the stream has been synchronised; false = results of this run must be discarded
+  bool disabled() const { return disabled_; }
+  std::string debug_source(const std::vector<ColInfo>& build_cols, const std::vector<ColInfo>& probe_cols, const std::vector<ExprCopy>& right_keys1,
+                           const ExprCopy& probe_pred1, const ExprCopy& key2, int* key_dtype = nullptr);
+
+ private:
+  bool check_flags();
+  Ctx ctx_;
+  Options opt_;
+  std::map<std::string, std::pair<JitKernel*, int>> kernels_;  // by schema signature: kernel + dtype of the chain key
+  struct Host {  // pinned
+    uint32_t flags[4];
+    unsigned long long inserted;
+  };
+  Host* host_ = nullptr;
+  int64_t hint_inserted_ = -1, hint_probe_rows_ = -1, hint_build_rows_ = -1;
+  uint64_t cap_used_ = 0;
+  bool pending_ = false, disabled_ = false;
 };
 
 }  // namespace sq

@@ -88,7 +88,18 @@ struct JoinTableView {
   uint32_t bloom_mask;    // number of words - 1 (power of two)
   int unique;             // every build key occurs once (primary-key side): slot_rep is the whole match list,
                           // slot_start / rows are not built
+  // Key-in-slot layout ("kv", cuCollections-style static map) for the common single-key join compared by value
+  // (n_keys == 1, match_keys): kv[2*s] = raw key bits (kJoinKvEmpty = empty slot), kv[2*s+1] = representative (smallest)
+  // build row.  A probe step is ONE 16-byte read instead of the dependent chain slot_rep -> h[rep] -> keys[rep], and the
+  // table needs no per-build-row hash / key arrays — which is what lets a probe kernel build the NEXT join's table
+  // directly (csrc/jit/joinchain.cuh).  In this mode slot_rep = kv + 1 and rep_stride = 2.  A build key whose bits
+  // equal kJoinKvEmpty cannot be stored: the insert kernels flag it and the host falls back to the slot_rep layout.
+  uint64_t* kv;
+  int kv_dtype;           // dtype of the key: a probe key of another type never matches (the placement hash is typed too)
+  int rep_stride;         // 1, or 2 in kv mode
+  int64_t n_inserted;     // host-side number (or, while a run is unvalidated, estimate) of build rows in the table
 };
+constexpr uint64_t kJoinKvEmpty = 0xffffffffffffffffULL;
 
 SQ_HD inline uint32_t join_bloom_word(uint64_t h, uint32_t mask) { return (uint32_t)((h * 0x9E3779B97F4A7C15ULL) >> 40) & mask; }
 SQ_HD inline uint64_t join_bloom_bits(uint64_t h) {
@@ -103,6 +114,8 @@ size_t scan_scratch_entries(int64_t m);
 
 // inserts the distinct keys (slot_rep, Bloom filter, row_slot); *has_dups = 1 when some key occurred more than once
 void launch_join_insert(const JoinTableView& t, int32_t* row_slot, uint32_t* has_dups, cudaStream_t stream);
+// the same into the kv layout; misc[0] = 1 when some key repeats, misc[4] = 1 when a key equals kJoinKvEmpty (table unusable)
+void launch_join_insert_kv(const JoinTableView& t, int32_t* row_slot, uint32_t* misc, cudaStream_t stream);
 // (only then) rows per slot into t.slot_count (zero-initialised) and the largest count into *max_count
 void launch_join_count(const JoinTableView& t, const int32_t* row_slot, uint32_t* max_count, cudaStream_t stream);
 void launch_join_fill(const JoinTableView& t, const int32_t* row_slot, uint32_t* slot_fill, cudaStream_t stream);

@@ -93,6 +93,63 @@ __global__ void __launch_bounds__(kBlock) k_join_insert(JoinTableView t, int32_t
   if (__any_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) *has_dups = 1u;
 }
 
+// The kv layout (JoinTableView::kv): the key word of a slot is claimed by CAS against kJoinKvEmpty, the representative row is
+// the smallest build row of the key (atomicMin), so the table is deterministic whatever the thread order.  One atomic on a
+// fresh line per insert, no dependent read of a per-row key array on a collision.
+__global__ void __launch_bounds__(kBlock) k_join_insert_kv(JoinTableView t, int32_t* __restrict__ row_slot, uint32_t* __restrict__ misc) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint32_t mask = t.capacity - 1;
+  bool dup = false, sentinel = false;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < t.n_build; base += stride * kInsertBatch) {
+    int64_t i[kInsertBatch];
+    bool live[kInsertBatch];
+    uint64_t h[kInsertBatch], key[kInsertBatch], seen[kInsertBatch];
+    uint32_t s[kInsertBatch];
+#pragma unroll
+    for (int u = 0; u < kInsertBatch; u++) {
+      i[u] = base + u * stride;
+      const bool inb = i[u] < t.n_build;
+      const int64_t r = inb ? i[u] : 0;
+      const bool kept = !t.build_keep || ((t.build_keep[r >> 5] >> (r & 31)) & 1u);
+      const bool null_key = t.knull[r] != 0u;  // SQL semantics: a NULL key never joins
+      h[u] = t.h[r];
+      key[u] = t.keys[r];
+      live[u] = inb && kept && !null_key;
+      if (live[u] && key[u] == kJoinKvEmpty) {
+        sentinel = true;
+        live[u] = false;
+      }
+      s[u] = mix32(h[u]) & mask;
+    }
+#pragma unroll
+    for (int u = 0; u < kInsertBatch; u++) seen[u] = live[u] ? *((volatile unsigned long long*)&t.kv[2 * (size_t)s[u]]) : 0ULL;
+#pragma unroll
+    for (int u = 0; u < kInsertBatch; u++) {
+      if (!live[u]) {
+        if (i[u] < t.n_build) row_slot[i[u]] = -1;
+        continue;
+      }
+      uint32_t slot = s[u];
+      unsigned long long cur = seen[u];
+      for (;;) {
+        if (cur == kJoinKvEmpty) cur = atomicCAS((unsigned long long*)&t.kv[2 * (size_t)slot], (unsigned long long)kJoinKvEmpty, (unsigned long long)key[u]);
+        if (cur == kJoinKvEmpty) break;  // claimed
+        if (cur == key[u]) {
+          dup = true;
+          break;
+        }
+        slot = (slot + 1) & mask;
+        cur = *((volatile unsigned long long*)&t.kv[2 * (size_t)slot]);
+      }
+      atomicMin((unsigned long long*)&t.kv[2 * (size_t)slot + 1], (unsigned long long)i[u]);
+      row_slot[i[u]] = (int32_t)slot;
+      if (t.bloom) atomicOr((unsigned long long*)&t.bloom[join_bloom_word(h[u], t.bloom_mask)], (unsigned long long)join_bloom_bits(h[u]));
+    }
+  }
+  if (__any_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) misc[0] = 1u;
+  if (__any_sync(0xffffffffu, sentinel) && (threadIdx.x & 31) == 0) misc[4] = 1u;
+}
+
 // only when some key repeats: rows per slot and the largest such count
 __global__ void __launch_bounds__(kBlock) k_join_count(JoinTableView t, const int32_t* __restrict__ row_slot, uint32_t* __restrict__ max_count) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -173,7 +230,7 @@ __global__ void __launch_bounds__(kBlock) k_join_probe_emit(JoinTableView t, con
     for (int j = 0; j < kPer; j++) {
       if (slot[j] >= 0) {
         if (t.unique) {
-          li[o] = t.slot_rep[slot[j]];
+          li[o] = t.slot_rep[(size_t)slot[j] * t.rep_stride];
           ri[o] = (uint32_t)(r0 + j);
         } else {
           const int64_t* src = t.rows + t.slot_start[slot[j]];
@@ -351,6 +408,11 @@ void launch_scan_u32_large(const uint32_t* counts, int64_t m, unsigned long long
 void launch_join_insert(const JoinTableView& t, int32_t* row_slot, uint32_t* has_dups, cudaStream_t stream) {
   if (t.n_build <= 0) return;
   k_join_insert<<<grid_for(div_up(t.n_build, kInsertBatch), kBlock, 148 * 32), kBlock, 0, stream>>>(t, row_slot, has_dups);
+  SQ_LAUNCH_CHECK();
+}
+void launch_join_insert_kv(const JoinTableView& t, int32_t* row_slot, uint32_t* misc, cudaStream_t stream) {
+  if (t.n_build <= 0) return;
+  k_join_insert_kv<<<grid_for(div_up(t.n_build, kInsertBatch), kBlock, 148 * 32), kBlock, 0, stream>>>(t, row_slot, misc);
   SQ_LAUNCH_CHECK();
 }
 void launch_join_count(const JoinTableView& t, const int32_t* row_slot, uint32_t* max_count, cudaStream_t stream) {

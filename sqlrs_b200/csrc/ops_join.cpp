@@ -24,7 +24,7 @@ ProbeProgram gen_probe_program(const std::vector<ColInfo>& cols, const std::vect
   for (const Val& k : jkeys) jraw.push_back(p1.emit_raw_bits(k));
   const int jh = jmatch ? p1.emit_mix_hash(jraw, jkeys) : p1.emit_row_hash(jkeys);  // as the build side (key_request)
   const int JK = (int)jkeys.size();
-  s << "#define SQ_JKEYS " << JK << "\n#define SQ_JMATCH " << (jmatch ? 1 : 0) << "\n";
+  s << "#define SQ_JKEYS " << JK << "\n#define SQ_JMATCH " << (jmatch ? 1 : 0) << "\n#define SQ_JKEY0_DTYPE " << (JK > 0 ? jkeys[0].dtype : 0) << "\n";
   s << "struct SqProbe { bool pass; u64 h; u64 kb[" << std::max(JK, 1) << "]; u32 knull; };\n";
   s << "__device__ __forceinline__ void sq_probe_row(const SqIn& in, i64 r, SqProbe& p, bool& e0, bool& e1) {\n" << p1.body_str();
   s << "  p.pass = " << p1_pass << ";\n  p.h = v" << jh << ";\n";
@@ -71,6 +71,16 @@ ProbeProgram gen_probe_program(const std::vector<ColInfo>& cols, const std::vect
   return out;
 }
 
+std::string gen_build_decls(const std::vector<ColInfo>& build_cols) {
+  std::ostringstream s;
+  const size_t nb = build_cols.size() ? build_cols.size() : 1;
+  s << "struct SqInB { const void* col[" << nb << "]; const u32* val[" << nb << "]; };\n";
+  s << "#define SQ_LDB_I64(c, b) sq_ldg_i64(inb.col[c], b)\n#define SQ_LDB_I32(c, b) sq_ldg_i32(inb.col[c], b)\n";
+  s << "#define SQ_LDB_F64(c, b) sq_ldg_f64(inb.col[c], b)\n#define SQ_LDB_BOOL(c, b) sq_ld_bit(inb.col[c], b)\n";
+  s << "#define SQ_VALIDB(c, b) sq_ld_bit(inb.val[c], b)\n";
+  return s.str();
+}
+
 struct JoinOp::Impl {
   // build side
   std::vector<DBatch> left_batches;
@@ -93,7 +103,9 @@ struct JoinOp::Impl {
   ExprCopy build_pred, probe_pred;
   std::vector<DCol> left_keep_parts;
   DCol keep_all;
+  int key0_dtype = 0;  // static dtype of the first key expression (kv layout)
   std::vector<bool> needed;  // per output field; empty = all
+  std::vector<BufPtr> adopted;  // adopt_build: the buffers the view points into
 };
 
 // outputs: [hash, (raw bits x K, null mask)?, (keep mask of the fused Filter)?]
@@ -147,6 +159,7 @@ void JoinOp::build_push(const DBatch& batch) {
   const bool mk = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
   if (!impl_->left_prog) impl_->left_prog = std::make_unique<EvalProgram>(key_request(left_keys_, mk, impl_->build_pred));
   EvalResult keys = impl_->left_prog->run(ctx_, batch, "join key");
+  if (!keys.expr_dtypes.empty()) impl_->key0_dtype = keys.expr_dtypes[0];
   if (!impl_->build_pred.empty()) {
     impl_->left_keep_parts.push_back(keys.cols.back());
     keys.cols.pop_back();
@@ -217,10 +230,8 @@ void JoinOp::seal() {
   while (cap < 2ULL * (uint64_t)n_insert) cap <<= 1;
   if (cap > (1ULL << 30)) fail(SQLRS_ERR_UNSUPPORTED, "join build side too large for one table (> 2^29 rows)");
   im.capacity = (uint32_t)cap;
-  im.slot_rep = dev_alloc(ctx_, cap * 8);
-  SQ_CUDA(cudaMemsetAsync(im.slot_rep->p, 0xff, cap * 8, ctx_.stream));
   JoinTableView& v = im.view;
-  v.slot_rep = (int64_t*)im.slot_rep->p;
+  v = JoinTableView{};
   v.slot_count = nullptr;  // per-slot counts and the CSR row lists are only built when some key repeats (below)
   v.slot_start = nullptr;
   v.rows = nullptr;
@@ -233,19 +244,44 @@ void JoinOp::seal() {
   v.n_keys = K;
   v.match_keys = mk ? 1 : 0;
   v.build_keep = im.build_pred.empty() ? nullptr : (const uint32_t*)im.keep_all.data;
+  v.n_inserted = n_insert;
   const uint32_t bloom_words = join_bloom_words(n_insert);
   im.bloom = dev_alloc_zero(ctx_, (size_t)bloom_words * 8);
   v.bloom = (uint64_t*)im.bloom->p;
   v.bloom_mask = bloom_words - 1;
   im.max_count = n_insert > 0 ? 1 : 0;
-  if (n > 0) {
+  // single key compared by value: key-in-slot layout (kernels_aot.hpp).  A key whose bits equal the empty marker cannot
+  // be stored there; the insert kernel flags it and the table is rebuilt in the slot_rep layout.
+  bool use_kv = mk && K == 1 && !std::getenv("SQLRS_B200_NO_KV");
+  for (int attempt = 0; attempt < 2; attempt++) {
+    if (use_kv) {
+      im.slot_rep = dev_alloc(ctx_, cap * 16);
+      SQ_CUDA(cudaMemsetAsync(im.slot_rep->p, 0xff, cap * 16, ctx_.stream));
+      v.kv = (uint64_t*)im.slot_rep->p;
+      v.kv_dtype = im.key0_dtype;
+      v.slot_rep = (int64_t*)im.slot_rep->p + 1;
+      v.rep_stride = 2;
+    } else {
+      im.slot_rep = dev_alloc(ctx_, cap * 8);
+      SQ_CUDA(cudaMemsetAsync(im.slot_rep->p, 0xff, cap * 8, ctx_.stream));
+      v.kv = nullptr;
+      v.kv_dtype = 0;
+      v.slot_rep = (int64_t*)im.slot_rep->p;
+      v.rep_stride = 1;
+    }
+    if (n <= 0) break;
     BufPtr row_slot = dev_alloc(ctx_, (size_t)n * 4);
-    BufPtr misc = dev_alloc_zero(ctx_, 16);  // [0] has duplicates, [4] max count, [8] total
-    launch_join_insert(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
-    uint32_t has_dups = 0;
-    SQ_CUDA(cudaMemcpyAsync(&has_dups, misc->p, 4, cudaMemcpyDeviceToHost, ctx_.stream));
+    BufPtr misc = dev_alloc_zero(ctx_, 32);  // u32 [0] has duplicates, [1] max count, [2..3] u64 total, [4] kv: a key equals the empty marker
+    if (use_kv) launch_join_insert_kv(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
+    else launch_join_insert(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
+    uint32_t flags[5] = {0, 0, 0, 0, 0};
+    SQ_CUDA(cudaMemcpyAsync(flags, misc->p, sizeof(flags), cudaMemcpyDeviceToHost, ctx_.stream));
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
-    if (has_dups) {
+    if (use_kv && flags[4]) {  // rare: rebuild in the other layout (the Bloom filter already holds a superset: harmless)
+      use_kv = false;
+      continue;
+    }
+    if (flags[0]) {
       // some key repeats: rows per slot, CSR ranges, ascending row ids per range
       v.unique = 0;
       im.slot_count = dev_alloc_zero(ctx_, cap * 4);
@@ -270,8 +306,21 @@ void JoinOp::seal() {
         join_fill_sorted(v, (const int32_t*)row_slot->p, ctx_.stream);
       }
     }
+    break;
   }
   if (join_type_ == SQLRS_JOIN_LEFT || join_type_ == SQLRS_JOIN_FULL) im.visited_left = dev_alloc_zero(ctx_, (size_t)bitmap_words(n) * 4 + 4);
+}
+
+void JoinOp::adopt_build(DBatch build, const JoinTableView& view, std::vector<BufPtr> keep) {
+  Impl& im = *impl_;
+  if (im.sealed || !im.left_batches.empty()) fail(SQLRS_ERR_INVALID_ARG, "hash_join: adopt_build on a join that already has a build side");
+  im.sealed = true;
+  im.left_rows = build.n;
+  im.left_single = std::move(build);
+  im.view = view;
+  im.capacity = view.capacity;
+  im.max_count = 1;
+  im.adopted = std::move(keep);
 }
 
 std::string JoinOp::debug_probe_source(const std::vector<ColInfo>& probe_cols, const ExprCopy& probe_pred) const {
@@ -466,6 +515,171 @@ bool JoinOp::finish(DBatch* result) {
   for (size_t c = im.left_single.cols.size(); c < out_fields_.size(); c++) out.cols.push_back(null_col(ctx_, out_fields_[c].dtype, m));
   check_schema(out);
   *result = out;
+  return true;
+}
+
+// ------------------------------------------------------------------ join chain (csrc/jit/joinchain.cuh)
+JoinChainOp::JoinChainOp(const Options& opt) : ctx_(opt), opt_(opt) {}
+JoinChainOp::~JoinChainOp() {
+  if (host_) cudaFreeHost(host_);
+}
+
+std::string JoinChainOp::debug_source(const std::vector<ColInfo>& build_cols, const std::vector<ColInfo>& probe_cols, const std::vector<ExprCopy>& right_keys1,
+                                      const ExprCopy& probe_pred1, const ExprCopy& key2, int* key_dtype) {
+  std::ostringstream s;
+  s << gen_input_decls(probe_cols) << gen_build_decls(build_cols);
+  s << gen_probe_program(probe_cols, right_keys1, probe_pred1, true).src;
+  RowProgram prog(build_cols, probe_cols);  // joined mode: join 1's output row
+  Val k = prog.compile(key2, 1);
+  if (k.dtype == SQLRS_DT_NULL || k.dtype == SQLRS_DT_UTF8) fail(SQLRS_ERR_UNSUPPORTED, "join chain: unsupported key type");
+  const int raw = prog.emit_raw_bits(k);
+  const int h = prog.emit_mix_hash({raw}, {k});  // the placement hash gen_probe_program gives join 2's probe side
+  if (key_dtype) *key_dtype = k.dtype;
+  s << "struct SqChainKey { u64 h; u64 kb; u32 knull; };\n";
+  s << "__device__ __forceinline__ void sq_chain_key(const SqIn& in, const SqInB& inb, i64 r, i64 b, SqChainKey& o, bool& e1) {\n  bool e0 = false;\n";
+  s << prog.body_str();
+  s << "  e1 |= e0;\n  o.h = v" << h << ";\n  o.kb = v" << raw << ";\n  o.knull = n" << k.id << " ? 0u : 1u;\n}\n";
+  return s.str();
+}
+
+bool JoinChainOp::check_flags() {
+  const uint32_t* f = host_->flags;
+  if (f[3]) fail(SQLRS_ERR_ARROW, "Divide by zero error (join key)");
+  if (f[0] || f[2]) {  // a repeated key needs the CSR lists, an unrepresentable key the slot_rep layout: not this path
+    disabled_ = true;
+    hint_inserted_ = -1;
+    return false;
+  }
+  if (f[1]) {  // the table was too small for the estimate
+    hint_inserted_ = -1;
+    return false;
+  }
+  return true;
+}
+
+bool JoinChainOp::validate() {
+  if (!pending_) return true;
+  pending_ = false;
+  if (!check_flags()) return false;
+  hint_inserted_ = (int64_t)host_->inserted;
+  return true;
+}
+
+bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pred1, const ExprCopy& key2, JoinOp& j2) {
+  if (disabled_ || std::getenv("SQLRS_B200_NO_CHAIN")) return false;
+  Trace tr("join.chain", ctx_.stream);
+  ctx_.activate();
+  ctx_.reap();
+  j1.seal();
+  if (j1.empty_build()) return false;
+  const JoinTableView& jt = j1.table_view();
+  const int64_t n = probe1.n;
+  if (!jt.unique || jt.capacity == 0 || n <= 0 || n >= (1LL << 32)) return false;
+  const DBatch& build1 = j1.build_side();
+  std::vector<ColInfo> pcols = col_infos(probe1), bcols = col_infos(build1);
+  const std::string sig = RowProgram(bcols, pcols).signature();
+  auto kit = kernels_.find(sig);
+  if (kit == kernels_.end()) {
+    int key_dtype = 0;
+    const std::string src = debug_source(bcols, pcols, j1.right_keys(), probe_pred1, key2, &key_dtype);
+    kit = kernels_.emplace(sig, std::make_pair(jit_get("join_table+joinchain", src, "sq_joinchain_kernel"), key_dtype)).first;
+  }
+  JitKernel* kernel = kit->second.first;
+  if (!host_) SQ_CUDA(cudaHostAlloc((void**)&host_, sizeof(Host), cudaHostAllocDefault));
+
+  const int sms = device_sm_count(ctx_.device);
+  const int per_sm = std::max(1, jit_max_blocks_per_sm(kernel, 256, 0));
+  std::vector<const void*> in_blob(2 * std::max<size_t>(probe1.cols.size(), 1), nullptr), inb_blob(2 * std::max<size_t>(build1.cols.size(), 1), nullptr);
+  for (size_t c = 0; c < probe1.cols.size(); c++) {
+    in_blob[c] = probe1.cols[c].data;
+    in_blob[std::max<size_t>(probe1.cols.size(), 1) + c] = probe1.cols[c].valid;
+  }
+  for (size_t c = 0; c < build1.cols.size(); c++) {
+    inb_blob[c] = build1.cols[c].data;
+    inb_blob[std::max<size_t>(build1.cols.size(), 1) + c] = build1.cols[c].valid;
+  }
+  struct ChainOut {
+    uint64_t* kv;
+    uint64_t* bloom;
+    uint32_t capacity, bloom_mask;
+    uint32_t* flags;
+    unsigned long long* inserted;
+  };
+  BufPtr status = dev_alloc_zero(ctx_, 32);  // u32 flags[4] + u64 inserted
+  auto launch = [&](ChainOut out, int64_t chunk_step) {
+    int64_t n_arg = n, step = chunk_step;
+    JoinTableView jv = jt;
+    void* args[] = {in_blob.data(), inb_blob.data(), &n_arg, &jv, &out, &step};
+    const int64_t trips = div_up(div_up(n, 2048), chunk_step);
+    const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(trips, 1), (int64_t)sms * per_sm);
+    jit_launch(kernel, grid, 256, 0, ctx_.stream, args);
+  };
+
+  // ---- how many rows will join 1 yield?  Exact count of the previous run over tables of the same size, else a strided sample
+  bool optimistic = hint_inserted_ >= 0 && hint_probe_rows_ == n && hint_build_rows_ == jt.n_build && !(opt_.flags & SQLRS_FLAG_TIMING);
+  int64_t est = hint_inserted_;
+  if (!optimistic) {
+    const int64_t chunks = div_up(n, 2048);
+    const int64_t step = std::max<int64_t>(1, chunks / 4096);  // ~8 M sampled rows at most
+    ChainOut cnt{nullptr, nullptr, 0, 0, (uint32_t*)status->p, (unsigned long long*)((uint32_t*)status->p + 4)};
+    launch(cnt, step);
+    SQ_CUDA(cudaMemcpyAsync(host_, status->p, sizeof(Host), cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    if (host_->flags[3]) fail(SQLRS_ERR_ARROW, "Divide by zero error (join key)");
+    est = (int64_t)((double)host_->inserted * (double)step * 1.25) + 4096;
+    SQ_CUDA(cudaMemsetAsync(status->p, 0, 32, ctx_.stream));
+  }
+  uint64_t cap = 1024;
+  while (cap < 2ULL * (uint64_t)est) cap <<= 1;
+  if (cap > (1ULL << 30)) return false;
+  cap_used_ = cap;
+  BufPtr kv = dev_alloc(ctx_, cap * 16);
+  SQ_CUDA(cudaMemsetAsync(kv->p, 0xff, cap * 16, ctx_.stream));
+  const uint32_t bloom_words = join_bloom_words(est);
+  BufPtr bloom = dev_alloc_zero(ctx_, (size_t)bloom_words * 8);
+  ChainOut out{(uint64_t*)kv->p, (uint64_t*)bloom->p, (uint32_t)cap, bloom_words - 1, (uint32_t*)status->p, (unsigned long long*)((uint32_t*)status->p + 4)};
+  launch(out, 1);
+  SQ_CUDA(cudaMemcpyAsync(host_, status->p, sizeof(Host), cudaMemcpyDeviceToHost, ctx_.stream));
+  hint_probe_rows_ = n;
+  hint_build_rows_ = jt.n_build;
+  int64_t inserted = est;
+  if (optimistic) {
+    pending_ = true;  // validated by the plan once the stream has been synchronised
+  } else {
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    if (!check_flags()) return false;
+    inserted = (int64_t)host_->inserted;
+    hint_inserted_ = inserted;
+  }
+  ctx_.defer([status]() {});
+
+  // ---- join 2's build side: a view of join 1's probe batch (row ids = its row numbers); build-1 columns are not available
+  JoinTableView v{};
+  v.capacity = (uint32_t)cap;
+  v.kv = (uint64_t*)kv->p;
+  v.kv_dtype = kit->second.second;
+  v.slot_rep = (int64_t*)kv->p + 1;
+  v.rep_stride = 2;
+  v.n_build = n;
+  v.n_keys = 1;
+  v.match_keys = 1;
+  v.bloom = (uint64_t*)bloom->p;
+  v.bloom_mask = bloom_words - 1;
+  v.unique = 1;
+  v.n_inserted = inserted;
+  DBatch vb;
+  vb.fields = j1.out_fields();
+  vb.n = n;
+  for (size_t c = 0; c < build1.cols.size(); c++) {
+    DCol ph;
+    ph.dtype = SQLRS_DT_NULL;
+    ph.n = n;
+    ph.null_count = n;
+    vb.cols.push_back(ph);
+  }
+  for (const DCol& c : probe1.cols) vb.cols.push_back(c);
+  if (vb.cols.size() != vb.fields.size()) fail(SQLRS_ERR_ARROW, "number of columns must match number of fields in schema");
+  j2.adopt_build(std::move(vb), v, {kv, bloom});
   return true;
 }
 
