@@ -432,6 +432,13 @@ int SQLRS_API(debug_compile_joinagg)(const sqlrs_agg_desc* aggs, int32_t n_aggs,
 int SQLRS_API(debug_compile_joinprobe)(const sqlrs_expr* right_keys, int32_t n_keys, const sqlrs_expr* probe_predicate,
                                        const struct ArrowSchema* probe_schema, const sqlrs_options* options,
                                        int32_t compile, char** source_out);
+/* the fused probe -> build kernel of a join chain (csrc/jit/joinchain.cuh): join 1 (`right_keys1` over `probe_schema` batches,
+ * build side `build_schema`, optional probe-side Filter) inserts `chain_key` — join 2's build key, an expression over join 1's
+ * output row (build columns first) — into join 2's table */
+int SQLRS_API(debug_compile_joinchain)(const sqlrs_expr* right_keys1, int32_t n_keys, const sqlrs_expr* probe_predicate,
+                                       const sqlrs_expr* chain_key, const struct ArrowSchema* build_schema,
+                                       const struct ArrowSchema* probe_schema, const sqlrs_options* options,
+                                       int32_t compile, char** source_out);
 int SQLRS_API(debug_compile_eval)(const sqlrs_expr* exprs, int32_t n_exprs, int32_t as_keep_mask,
                                   const struct ArrowSchema* input_schema, int32_t compile, char** source_out);
 void SQLRS_API(free)(void* p);

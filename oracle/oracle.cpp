@@ -639,6 +639,11 @@ int sqlrs_oracle_debug_compile_joinprobe(const sqlrs_expr*, int32_t, const sqlrs
   g_last_error = "the oracle generates no kernels";
   return SQLRS_ERR_UNSUPPORTED;
 }
+int sqlrs_oracle_debug_compile_joinchain(const sqlrs_expr*, int32_t, const sqlrs_expr*, const sqlrs_expr*, const ArrowSchema*, const ArrowSchema*,
+                                         const sqlrs_options*, int32_t, char**) {
+  g_last_error = "the oracle generates no kernels";
+  return SQLRS_ERR_UNSUPPORTED;
+}
 int sqlrs_oracle_debug_compile_eval(const sqlrs_expr*, int32_t, int32_t, const ArrowSchema*, int32_t, char**) {
   g_last_error = "the oracle generates no kernels";
   return SQLRS_ERR_UNSUPPORTED;

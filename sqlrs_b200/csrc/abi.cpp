@@ -607,6 +607,22 @@ int sqlrs_debug_compile_joinprobe(const sqlrs_expr* right_keys, int32_t n_keys, 
   });
 }
 
+int sqlrs_debug_compile_joinchain(const sqlrs_expr* right_keys1, int32_t n_keys, const sqlrs_expr* probe_predicate, const sqlrs_expr* chain_key,
+                                  const ArrowSchema* build_schema, const ArrowSchema* probe_schema, const sqlrs_options* options, int32_t compile,
+                                  char** source_out) {
+  return guarded([&] {
+    Options opt = copy_options(options);
+    opt.device_id = -2;
+    ExprCopy pp;
+    if (probe_predicate && probe_predicate->n_nodes > 0) pp = copy_expr(probe_predicate);
+    if (!chain_key) fail(SQLRS_ERR_INVALID_ARG, "chain_key is NULL");
+    JoinChainOp op(opt);
+    std::string gen = op.debug_source(cols_of_schema(build_schema), cols_of_schema(probe_schema), copy_exprs(right_keys1, n_keys), pp, copy_expr(chain_key));
+    if (compile) jit_compile_to_cubin("join_table+joinchain", gen, nullptr);
+    if (source_out) *source_out = dup_string(jit_full_source("join_table+joinchain", gen));
+  });
+}
+
 int sqlrs_debug_compile_eval(const sqlrs_expr* exprs, int32_t n_exprs, int32_t as_keep_mask, const ArrowSchema* input_schema,
                              int32_t compile, char** source_out) {
   return guarded([&] {

@@ -100,6 +100,10 @@ inline int dtype_width(int dt) {
 inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t bitmap_words(int64_t n) { return div_up(n, 32); }  // device bitmaps are u32-word granular
 
+// thrown by an operator whose state was sized from a previous run's numbers and turned out too small; the plan re-runs
+// without the hint (Plan::run_validated)
+struct RetrySizingError {};
+
 struct Options {
   int count_mode = SQLRS_COUNT_REFERENCE_OVERWRITE;
   int match_mode = SQLRS_MATCH_HASH_ONLY;

@@ -112,7 +112,11 @@ class AggOp {
   void reset();  // forget all groups, keep compiled kernels and buffers
   // fused probe -> aggregate over an INNER hash join whose build side is sealed in `join` (csrc/jit/joinagg.cuh):
   // `probe` is a batch of the join's right child, `probe_pred` a Filter fused below the join on that side
-  void push_join(const DBatch& probe, class JoinOp& join, const ExprCopy& probe_pred);
+  // `defer`: the caller validates this run afterwards (Plan::run_validated), so when a previous run of this operator left
+  // a group-count hint the table is sized from it and NOTHING synchronises here; the counters are read by the next
+  // consumer (finish / settle), and a table that turned out too small raises RetrySizingError there
+  void push_join(const DBatch& probe, class JoinOp& join, const ExprCopy& probe_pred, bool defer = false);
+  void settle();  // reads the counters of a deferred push_join now (one synchronisation)
   void set_row_base(int64_t first_global_row) { rows_seen_ = first_global_row; }
 
   bool has_distinct() const { return distinct_ != nullptr; }
@@ -163,6 +167,9 @@ class AggOp {
   uint32_t groups_known_ = 0;   // exact group count at the last counter read
   uint64_t groups_bound_ = 0;   // host-side upper bound since then
   bool counters_stale_ = false; // device work since the last counter read may have added groups
+  uint32_t groups_hint_ = 0;    // group count at the end of the previous run (0 = none)
+  bool hint_sized_ = false;     // the current table was sized from groups_hint_ and its overflow flag has not been read yet
+  bool slot_list_pending_ = false;  // a deferred push_join: whether new_slots lists every group is known at the counter read
   bool slot_list_complete_ = false;  // table_->new_slots[0 .. groups_known_) lists every occupied slot (table adopted from one
                                      // fused probe+aggregate launch, untouched since): finalisation need not scan the capacity
   uint64_t* pinned_ = nullptr;  // pinned host staging of the packed result

@@ -562,6 +562,8 @@ void AggOp::reset() {
     distinct_->seen_batch = false;
   }
   slot_list_complete_ = false;
+  slot_list_pending_ = false;
+  hint_sized_ = false;
   if (table_) init_table_contents(*table_);
   rows_seen_ = 0;
   batches_seen_ = 0;
@@ -581,6 +583,19 @@ void AggOp::read_counters(uint32_t* out4) {
   groups_known_ = out4[0];
   groups_bound_ = out4[0];
   counters_stale_ = false;
+  groups_hint_ = out4[0];
+  if (slot_list_pending_) {  // deferred push_join: the launch appended every new group to new_slots
+    slot_list_pending_ = false;
+    slot_list_complete_ = out4[1] == out4[0];
+    SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 1, 0, 4, ctx_.stream));
+  }
+  if (hint_sized_) {
+    hint_sized_ = false;
+    if (out4[2] & 2u) {  // more groups than the previous run's count allowed for: the plan re-runs with exact sizing
+      groups_hint_ = 0;
+      throw RetrySizingError{};
+    }
+  }
   if (out4[2] & 2u) fail(SQLRS_ERR_INTERNAL, "group table overflow (internal sizing error)");
   if (out4[3] & 1u) {
     SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 3, 0, 4, ctx_.stream));
@@ -752,11 +767,19 @@ void AggOp::push(const DBatch& batch) {
 }
 
 // ------------------------------------------------------------------ fused probe -> aggregate
-void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_pred) {
+void AggOp::settle() {
+  if (table_ && counters_stale_) {
+    uint32_t hc[4];
+    read_counters(hc);
+  }
+}
+
+void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_pred, bool defer) {
   if (distinct_) fail(SQLRS_ERR_INTERNAL, "push_join: DISTINCT aggregates take the unfused path");
   Trace tr("agg.push_join", ctx_.stream);
   ctx_.activate();
   ctx_.reap();
+  settle();  // an earlier deferred batch
   if (join.join_type() != SQLRS_JOIN_INNER || opt_.match_mode != SQLRS_MATCH_HASH_AND_KEY)
     fail(SQLRS_ERR_INTERNAL, "push_join: only inner joins with key comparison are fused");
   join.seal();
@@ -805,8 +828,12 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
   // The number of joined rows (and groups) is unknown before the probe: aggregate into a batch-local table sized
   // optimistically; a full table discards it and retries 4x larger, so a batch counts all-or-nothing.
   const JoinTableView& jt = join.table_view();
-  // guess: about as many groups as build rows (x2 head-room in the open-addressed table)
-  uint64_t cap = std::max<uint64_t>(2ULL * (uint64_t)jt.n_build, 1ULL << 16);
+  // guess: about as many groups as build rows in the table (x2 head-room in the open-addressed table); a repeated run
+  // knows better: the previous run's group count (+25 %)
+  const bool main_empty_before = !table_ || (groups_known_ == 0 && !counters_stale_ && groups_bound_ == 0);
+  const bool use_hint = defer && groups_hint_ > 0 && main_empty_before && !(opt_.flags & SQLRS_FLAG_TIMING);
+  uint64_t cap = std::max<uint64_t>(2ULL * (uint64_t)(jt.n_inserted > 0 ? jt.n_inserted : jt.n_build), 1ULL << 16);
+  if (use_hint) cap = std::max<uint64_t>(2ULL * ((uint64_t)groups_hint_ + groups_hint_ / 4), 1ULL << 16);
   std::unique_ptr<Table> local;
   uint32_t hc[4] = {0, 0, 0, 0};
   bool first_try = true, tma_used = false;
@@ -815,7 +842,9 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
     {
       Trace tr_t("  joinagg.new_table", ctx_.stream);
       // repeated plan runs: the operator's (re-initialised, still empty) table of the previous run is the batch-local table
-      const bool reuse = table_ && groups_known_ == 0 && !counters_stale_ && groups_bound_ == 0 && table_->capacity >= next_pow2(cap) && first_try;
+      // (a hint-sized run wants exactly the hinted capacity: a smaller table keeps more of itself in L2)
+      const bool reuse = table_ && groups_known_ == 0 && !counters_stale_ && groups_bound_ == 0 && first_try &&
+                         (use_hint ? table_->capacity == next_pow2(cap) : table_->capacity >= next_pow2(cap));
       if (reuse) local = std::move(table_);
       else local = new_table((uint32_t)cap);
       first_try = false;
@@ -856,6 +885,16 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
     }
     timer.stop();
     tma_used = use_tma;
+    if (use_hint) {  // nothing synchronises: the table becomes the operator's, its counters are read by the next consumer
+      table_ = std::move(local);
+      counters_stale_ = true;
+      hint_sized_ = true;
+      slot_list_pending_ = true;
+      groups_bound_ = table_->capacity;
+      last_path_ = "sq_joinagg_kernel (fused probe + aggregate, table sized by the previous run's group count: capacity " +
+                   std::to_string(table_->capacity) + ", unsynchronised)";
+      return;
+    }
     SQ_CUDA(cudaMemcpyAsync(hc, local->counters->p, 16, cudaMemcpyDeviceToHost, ctx_.stream));
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
     scan_kernel_ms_ += timer.elapsed_ms();
@@ -870,6 +909,7 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
   if (main_empty) {
     table_ = std::move(local);  // first batch: its table IS the operator's table
     SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 1, 0, 4, ctx_.stream));
+    groups_hint_ = hc[0];
     groups_known_ = hc[0];
     groups_bound_ = hc[0];
     counters_stale_ = false;
@@ -967,6 +1007,7 @@ static double sortable_to_f64(int64_t s) {
 
 void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
   Trace tr("agg.finish_host", ctx_.stream);
+  if (hint_sized_) settle();  // a deferred push_join: the group count decides the path below
   // many groups: finalise on the device and copy whole columns (the row-at-a-time host loop below cost 2.7 ms for
   // Q3' SF10's 113 k groups); few groups: one packed D2H and a trivial host loop beat the extra launches
   if (distinct_ || (seen_batch_ && table_ && !counters_stale_ && groups_known_ > 1024)) {

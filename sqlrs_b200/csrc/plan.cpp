@@ -154,10 +154,75 @@ bool Plan::feed_fused_join(AggOp& op, int child, const ExprCopy& agg_fused_pred,
   mark_refs(probe_pred, right_need);
   JoinOp j(jn.join_type, jn.left_keys, jn.right_keys, jn.predicate, jn.join_fields, opt_);
   j.set_side_predicates(build_pred, ExprCopy());
-  description_ += "[HashJoin build (CSR) | probe fused into the aggregate: sq_joinagg_kernel] ";
-  for (const DBatch& b : run(left, left_need)) j.build_push(b);
-  for (const DBatch& b : run(right, right_need)) op.push_join(b, j, probe_pred);
+  bool chained = false;
+  if (build_pred.empty() && nodes_[left].kind == SQLRS_NODE_HASH_JOIN) chained = try_chain(child, left, left_need, j);
+  if (chained) {
+    description_ += "[HashJoin 1 probe builds HashJoin 2's table: sq_joinchain_kernel | probe 2 fused into the aggregate: sq_joinagg_kernel] ";
+  } else {
+    description_ += "[HashJoin build (CSR) | probe fused into the aggregate: sq_joinagg_kernel] ";
+    for (const DBatch& b : run(left, left_need)) j.build_push(b);
+  }
+  const bool defer = chained && nodes_[child].chain_op->pending();
+  for (const DBatch& b : run(right, right_need)) op.push_join(b, j, probe_pred, defer);
   return true;
+}
+
+// (A join B) join C with A join B inner, no non-equi filter, and C's join reading nothing of A: B's probe of A's table
+// inserts (key 2 -> B row) straight into join 2's table; join 1's output is never materialised.
+bool Plan::try_chain(int jidx, int left, const Needed& left_need, JoinOp& j) {
+  Node& j2 = nodes_[jidx];
+  Node& j1 = nodes_[left];
+  if (j1.join_type != SQLRS_JOIN_INNER || !j1.predicate.empty() || j2.left_keys.size() != 1 || j1.left_keys.empty()) return false;
+  int l1 = j1.child0, r1 = j1.child1;
+  ExprCopy build_pred1, probe_pred1;
+  if (nodes_[l1].kind == SQLRS_NODE_FILTER) {
+    build_pred1 = nodes_[l1].predicate;
+    l1 = nodes_[l1].child0;
+  }
+  if (nodes_[r1].kind == SQLRS_NODE_FILTER) {
+    probe_pred1 = nodes_[r1].predicate;
+    r1 = nodes_[r1].child0;
+  }
+  const int nleft1 = width_of(l1), total1 = (int)j1.join_fields.size();
+  if (nleft1 <= 0 || nleft1 > total1) return false;
+  for (int k = 0; k < nleft1; k++)
+    if (left_need.empty() || ((size_t)k < left_need.size() && left_need[(size_t)k])) return false;  // a build-1 column is read above
+  if (nodes_[r1].kind != SQLRS_NODE_SCAN) return false;  // the probe side must be a resident table (ONE batch, checked below)
+  auto it = tables_.find(nodes_[r1].table_slot);
+  if (it == tables_.end() || it->second.size() != 1 || it->second[0].n <= 0) return false;
+  if (!j2.chain_op) j2.chain_op = std::make_unique<JoinChainOp>(opt_);
+  if (j2.chain_op->disabled()) return false;
+  Needed l1_need((size_t)nleft1, false);
+  for (const ExprCopy& e : j1.left_keys) mark_refs(e, l1_need);
+  mark_refs(build_pred1, l1_need);
+  JoinOp jo1(j1.join_type, j1.left_keys, j1.right_keys, j1.predicate, j1.join_fields, opt_);
+  jo1.set_side_predicates(build_pred1, ExprCopy());
+  for (const DBatch& b : run(l1, l1_need)) jo1.build_push(b);
+  if (!j2.chain_op->run(jo1, it->second[0], probe_pred1, j2.left_keys[0], j)) return false;
+  if (j2.chain_op->pending()) pending_chains_.push_back(j2.chain_op.get());
+  return true;
+}
+
+void Plan::run_validated(const std::function<void()>& body) {
+  for (int attempt = 0;; attempt++) {
+    pending_chains_.clear();
+    bool ok = true;
+    try {
+      body();
+    } catch (const RetrySizingError&) {
+      ok = false;
+    }
+    if (ok && !pending_chains_.empty()) {
+      SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+      for (JoinChainOp* c : pending_chains_) ok = c->validate() && ok;
+    } else {
+      for (JoinChainOp* c : pending_chains_) c->validate();  // settles their state (the failed run's numbers are not used)
+    }
+    pending_chains_.clear();
+    if (ok) return;
+    if (attempt >= 3) fail(SQLRS_ERR_INTERNAL, "plan: sizing hints kept failing");
+    description_.clear();
+  }
 }
 
 // ---- partial / final split for multi-GPU group-by: run everything below the root
@@ -177,12 +242,17 @@ void Plan::execute_partial(int64_t row_base) {
     description_ += "[Filter+" + std::string(simple ? "SimpleAgg" : "HashAgg") + " fused, partial] ";
   }
   if (!partial_op_) partial_op_ = std::make_unique<AggOp>(n.aggs, n.group_by, n.group_names, simple, fused, opt_);
-  else partial_op_->reset();
-  partial_active_ = true;
-  partial_op_->set_row_base(row_base);
-  const Needed need = fusion() ? agg_child_needs(n, fused, width_of(child)) : Needed();
-  if (!feed_fused_join(*partial_op_, child, fused, need))
-    for (const DBatch& b : run(child, need)) partial_op_->push(b);
+  const std::string head = description_;
+  run_validated([&]() {
+    description_ = head;
+    partial_op_->reset();
+    partial_active_ = true;
+    partial_op_->set_row_base(row_base);
+    const Needed need = fusion() ? agg_child_needs(n, fused, width_of(child)) : Needed();
+    if (!feed_fused_join(*partial_op_, child, fused, need))
+      for (const DBatch& b : run(child, need)) partial_op_->push(b);
+    partial_op_->settle();  // a hint-sized group table is checked here (one counter read), before anything is exported
+  });
   description_ += partial_op_->describe() + "; ";
   scan_kernel_ms_ = partial_op_->scan_kernel_ms();
   scan_kernel_launches_ = partial_op_->scan_kernel_launches();
@@ -400,18 +470,27 @@ void Plan::execute() {
     }
   }
   results_.clear();
-  description_.clear();
   ctx_.reap();
-  Node& root = nodes_[root_];
-  if (root.kind == SQLRS_NODE_SIMPLE_AGG || root.kind == SQLRS_NODE_HASH_AGG) {
-    results_.emplace_back();
-    run_agg_to_host(root_, &results_.back());
-    return;
-  }
-  for (DBatch& b : run(root_, Needed())) {
-    results_.emplace_back();
-    results_.back().dev = std::move(b);
-  }
+  run_validated([&]() {
+    for (Result& r : results_) {  // a discarded attempt
+      if (r.on_host) {
+        if (r.arr.release) r.arr.release(&r.arr);
+        if (r.sch.release) r.sch.release(&r.sch);
+      }
+    }
+    results_.clear();
+    description_.clear();
+    Node& root = nodes_[root_];
+    if (root.kind == SQLRS_NODE_SIMPLE_AGG || root.kind == SQLRS_NODE_HASH_AGG) {
+      results_.emplace_back();
+      run_agg_to_host(root_, &results_.back());
+      return;
+    }
+    for (DBatch& b : run(root_, Needed())) {
+      results_.emplace_back();
+      results_.back().dev = std::move(b);
+    }
+  });
 }
 
 bool Plan::next(ArrowArray* out, ArrowSchema* out_schema) {

@@ -46,6 +46,7 @@ class Plan {
     std::unique_ptr<AggOp> agg_op;
     std::unique_ptr<ProjectOp> project_op;
     std::unique_ptr<OrderOp> order_op;
+    std::unique_ptr<JoinChainOp> chain_op;  // HASH_JOIN whose build side is another join: fused probe -> build (join.hpp)
     // PROJECT: select list + field names; ORDER: sort expressions + directions; LIMIT: the bound constants (-1 = None)
     std::vector<ExprCopy> exprs;
     std::vector<std::string> expr_names;
@@ -64,6 +65,10 @@ class Plan {
   void run_agg_to_host(int idx, Result* res);
   AggOp& run_agg(int idx);  // everything of an aggregate node up to (excluding) finalisation
   bool feed_fused_join(AggOp& op, int child, const ExprCopy& agg_fused_pred, const Needed& need);
+  // join `jidx`'s build side is the inner join `left`: let that join's probe build j's table (JoinChainOp)
+  bool try_chain(int jidx, int left, const Needed& left_need, JoinOp& j);
+  // runs `body` until the hint-sized (unsynchronised) parts of the run validate; see JoinChainOp / AggOp::push_join
+  void run_validated(const std::function<void()>& body);
   int width_of(int idx);              // number of output columns of a node (needs its scans pushed)
   Needed agg_child_needs(const Node& agg, const ExprCopy& fused_pred, int child_width) const;
   bool fusion() const { return !(opt_.flags & SQLRS_FLAG_NO_FUSION); }
@@ -77,6 +82,7 @@ class Plan {
   std::unique_ptr<AggOp> partial_op_;  // root aggregate of execute_partial(), kept across runs
   bool partial_active_ = false;        // between execute_partial and finish_partial
   std::string description_;
+  std::vector<JoinChainOp*> pending_chains_;  // runs sized by hints, to be validated once the stream has been synchronised
   double scan_kernel_ms_ = 0;
   int64_t scan_kernel_launches_ = 0;
 };

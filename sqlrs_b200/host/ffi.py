@@ -247,6 +247,7 @@ _SIGNATURES = {
     "debug_compile_joinagg": (C.c_int, [P(AggDesc), C.c_int32, P(Expr), C.c_int32, P(Expr), C.c_int32, P(Expr), P(Expr), P(ArrowSchema), P(ArrowSchema),
                               P(Options), C.c_int32, P(C.c_void_p)]),
     "debug_compile_joinprobe": (C.c_int, [P(Expr), C.c_int32, P(Expr), P(ArrowSchema), P(Options), C.c_int32, P(C.c_void_p)]),
+    "debug_compile_joinchain": (C.c_int, [P(Expr), C.c_int32, P(Expr), P(Expr), P(ArrowSchema), P(ArrowSchema), P(Options), C.c_int32, P(C.c_void_p)]),
     "debug_compile_eval": (C.c_int, [P(Expr), C.c_int32, C.c_int32, P(ArrowSchema), C.c_int32, P(C.c_void_p)]),
     "free": (None, [C.c_void_p]),
 }
