@@ -314,6 +314,15 @@ int RowProgram::emit_raw_bits(const Val& v) {
   return id;
 }
 
+std::string RowProgram::mix_hash_of_bits_source(const std::vector<int>& dtypes) {
+  std::ostringstream s;
+  s << "  unsigned long long h = 0x9e3779b97f4a7c15ULL;\n";
+  for (size_t k = 0; k < dtypes.size(); k++)
+    s << "  h = (h ^ kb[" << k << "] ^ 0x" << std::hex << (0x1000193ULL * (unsigned)(dtypes[k] + 1)) << std::dec << "ULL) * 0xff51afd7ed558ccdULL;\n  h ^= h >> 32;\n";
+  s << "  return h;\n";
+  return s.str();
+}
+
 int RowProgram::emit_mix_hash(const std::vector<int>& raw_ids, const std::vector<Val>& keys) {
   int id = fresh();
   body_ << "  unsigned long long " << vname(id) << " = 0x9e3779b97f4a7c15ULL;\n";

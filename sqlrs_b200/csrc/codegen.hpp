@@ -59,6 +59,9 @@ class RowProgram {
   int emit_raw_bits(const Val& v);
   // cheap placement hash over raw key bits + null flags (only valid where key tuples are compared too)
   int emit_mix_hash(const std::vector<int>& raw_ids, const std::vector<Val>& keys);
+  // the same hash as C statements over an array `kb[]` of raw key bits of NON-NULL keys of these dtypes (the fused probe
+  // kernels queue the key bits of a candidate row and re-derive its hash instead of re-reading the row)
+  static std::string mix_hash_of_bits_source(const std::vector<int>& dtypes);
   Val cast(const Val& a, int to);  // arrow compute::cast (also used by SUM: sum.rs:54)
   int fresh() { return next_id_++; }
   std::ostringstream& body() { return body_; }

@@ -16,7 +16,7 @@ struct SqJoin {           // mirrors sq::JoinTableView (kernels_aot.hpp)
   int n_keys;
   int match_keys;
   const u32* build_keep;
-  const u64* bloom;       // blocked Bloom filter over the build hashes (3 bits in one 64-bit word per key)
+  const u32* bloom;       // blocked Bloom filter over the build hashes (3 bits in one 32-bit word per key)
   u32 bloom_mask;
   int unique;             // every build key occurs once: the match list of a slot is its representative row
   const u64* kv;          // key-in-slot layout (single key compared by value): kv[2s] = key bits, kv[2s+1] = representative row
@@ -26,10 +26,11 @@ struct SqJoin {           // mirrors sq::JoinTableView (kernels_aot.hpp)
 };
 #define SQ_KV_EMPTY 0xffffffffffffffffULL
 
-__device__ __forceinline__ u32 sq_bloom_word(u64 h, u32 mask) { return (u32)((h * 0x9E3779B97F4A7C15ULL) >> 40) & mask; }
-__device__ __forceinline__ u64 sq_bloom_bits(u64 h) {
-  const u64 g = h * 0x9E3779B97F4A7C15ULL;
-  return (1ULL << ((g >> 34) & 63)) | (1ULL << ((g >> 28) & 63)) | (1ULL << ((g >> 22) & 63));
+// (mirrors join_bloom_word / join_bloom_bits of kernels_aot.hpp: all 32-bit arithmetic on the two halves of the hash)
+__device__ __forceinline__ u32 sq_bloom_word(u64 h, u32 mask) { return (u32)(h >> 32) & mask; }
+__device__ __forceinline__ u32 sq_bloom_bits(u64 h) {
+  const u32 lo = (u32)h;
+  return (1u << (lo & 31u)) | (1u << ((lo >> 5) & 31u)) | (1u << ((lo >> 10) & 31u));
 }
 
 // exact lookup: the matched slot (or -1) and its representative build row
@@ -79,3 +80,41 @@ __device__ __forceinline__ int sq_join_find(const SqJoin& t, const SqProbe& p) {
   i64 rep;
   return sq_join_find_rep(t, p, rep);
 }
+
+// phase A for SQ_JUNROLL x 32 rows starting at `base` (shared by the register-staged kernels): candidates are appended to
+// the warp's queue (row number + the value phase B needs, see SQ_PQMODE)
+#define SQ_PHASE_A(UNROLL, ROW_EXPR)                                                                          \
+  {                                                                                                           \
+    u64 qv[UNROLL];                                                                                           \
+    u32 bits[UNROLL], bw[UNROLL];                                                                             \
+    bool live[UNROLL];                                                                                        \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                                      \
+      const i64 r = base + u * 32 + lane;                                                                     \
+      const bool inb_row = r < n;                                                                             \
+      SqProbe p;                                                                                              \
+      bool e0 = false, e1 = false;                                                                            \
+      sq_probe_row(in, inb_row ? r : n - 1, p, e0, e1);                                                       \
+      live[u] = inb_row && p.pass;                                                                            \
+      if (SQ_JMATCH) live[u] = live[u] && p.knull == 0u; /* SQL semantics: a NULL key never joins */          \
+      any_err |= (inb_row && e0) || (inb_row && p.pass && e1);                                                \
+      qv[u] = SQ_PQMODE ? sq_probe_qv(p) : 0ULL;                                                              \
+      bits[u] = sq_bloom_bits(p.h);                                                                           \
+      bw[u] = sq_bloom_word(p.h, jt.bloom_mask);                                                              \
+    }                                                                                                         \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) bw[u] = live[u] ? __ldg(&jt.bloom[bw[u]]) : 0u;        \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                                      \
+      const bool cand = live[u] && (bw[u] & bits[u]) == bits[u];                                              \
+      const u32 m = __ballot_sync(0xffffffffu, cand);                                                         \
+      if (cand) {                                                                                             \
+        const u32 pos = queued + __popc(m & lanes_below);                                                     \
+        queue[pos] = (u32)(ROW_EXPR);                                                                         \
+        if (SQ_PQMODE) queue_v[pos] = qv[u];                                                                  \
+      }                                                                                                       \
+      queued += __popc(m);                                                                                    \
+    }                                                                                                         \
+    __syncwarp();                                                                                             \
+  }
+#if !SQ_PQMODE
+__device__ __forceinline__ u64 sq_probe_qv(const SqProbe&) { return 0ULL; }
+#endif
+

@@ -31,11 +31,15 @@
 #define SQ_JQUEUE (SQ_JUNROLL * 32 + 32)
 
 // phase B for one candidate row: exact probe, matches in build insertion order, aggregate
-__device__ __forceinline__ void sq_joinagg_candidate(const SqIn& in, const SqInB& inb, i64 r, i64 row_base, const SqJoin& jt, const SqTable& table,
-                                                     i64 batch_no, u32* status, bool& any_err) {
+__device__ __forceinline__ void sq_joinagg_candidate(const SqIn& in, const SqInB& inb, i64 r, u64 qv, i64 row_base, const SqJoin& jt,
+                                                     const SqTable& table, i64 batch_no, u32* status, bool& any_err) {
   SqProbe p;
+#if SQ_PQMODE
+  sq_probe_unq(qv, p);  // the queued key bits / hash: no second read of the probe row
+#else
   bool e0 = false, e1 = false;
-  sq_probe_row(in, r, p, e0, e1);  // re-evaluated (L1/L2 hits): cheaper than queueing hash + key tuple
+  sq_probe_row(in, r, p, e0, e1);  // several compared keys: re-evaluated (the scan's lines are still in L2)
+#endif
   i64 rep = -1;
   const int slot = sq_join_find_rep(jt, p, rep);
   if (slot < 0) return;
@@ -70,50 +74,24 @@ __device__ __forceinline__ void sq_joinagg_candidate(const SqIn& in, const SqInB
 extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_kernel(SqIn in, SqInB inb, i64 n, i64 row_base, SqJoin jt, SqTable table, i64 batch_no,
                                                                            u32* __restrict__ status, u32* __restrict__ err) {
   __shared__ u32 queue_s[SQ_JBLOCK / 32][SQ_JQUEUE];
+  __shared__ u64 queue_vs[SQ_JBLOCK / 32][SQ_PQMODE ? SQ_JQUEUE : 1];
   bool any_err = false;
   const int lane = threadIdx.x & 31;
   u32* queue = queue_s[threadIdx.x >> 5];
+  u64* queue_v = queue_vs[threadIdx.x >> 5];
   const u32 lanes_below = (1u << lane) - 1u;
   u32 queued = 0;  // warp-uniform
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 base = ((i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * SQ_JUNROLL; base < n; base += stride * SQ_JUNROLL) {
-    // ---- phase A
-    u64 hh[SQ_JUNROLL];
-    bool live[SQ_JUNROLL];
-#pragma unroll
-    for (int u = 0; u < SQ_JUNROLL; u++) {
-      const i64 r = base + u * 32 + lane;
-      const bool inb_row = r < n;
-      SqProbe p;
-      bool e0 = false, e1 = false;
-      sq_probe_row(in, inb_row ? r : n - 1, p, e0, e1);
-      live[u] = inb_row && p.pass;
-#if SQ_JMATCH
-      live[u] = live[u] && p.knull == 0u;  // SQL semantics: a NULL key never joins
-#endif
-      any_err |= (inb_row && e0) || (inb_row && p.pass && e1);
-      hh[u] = p.h;
-    }
-    u64 bw[SQ_JUNROLL];
-#pragma unroll
-    for (int u = 0; u < SQ_JUNROLL; u++) bw[u] = live[u] ? __ldg(&jt.bloom[sq_bloom_word(hh[u], jt.bloom_mask)]) : 0ULL;
-#pragma unroll
-    for (int u = 0; u < SQ_JUNROLL; u++) {
-      const u64 bits = sq_bloom_bits(hh[u]);
-      const bool cand = live[u] && (bw[u] & bits) == bits;
-      const u32 m = __ballot_sync(0xffffffffu, cand);
-      if (cand) queue[queued + __popc(m & lanes_below)] = (u32)(base + u * 32 + lane);  // n < 2^32 (checked by the host)
-      queued += __popc(m);
-    }
-    __syncwarp();
+    SQ_PHASE_A(SQ_JUNROLL, base + u * 32 + lane)  // n < 2^32 (checked by the host)
     // ---- phase B: full warps only
     while (queued >= 32) {
       queued -= 32;
-      sq_joinagg_candidate(in, inb, (i64)queue[queued + lane], row_base, jt, table, batch_no, status, any_err);
+      sq_joinagg_candidate(in, inb, (i64)queue[queued + lane], SQ_PQMODE ? queue_v[queued + lane] : 0ULL, row_base, jt, table, batch_no, status, any_err);
       __syncwarp();
     }
   }
-  if ((u32)lane < queued) sq_joinagg_candidate(in, inb, (i64)queue[lane], row_base, jt, table, batch_no, status, any_err);
+  if ((u32)lane < queued) sq_joinagg_candidate(in, inb, (i64)queue[lane], SQ_PQMODE ? queue_v[lane] : 0ULL, row_base, jt, table, batch_no, status, any_err);
   if (any_err) atomicOr(err, 1u);
 }
 
@@ -155,9 +133,11 @@ extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_tma_kernel(Sq
   extern __shared__ __align__(128) u64 sq_tiles[];  // [2 stages][SQ_TILE_NCOLS][SQ_TROWS]
   __shared__ __align__(8) u64 mbar[2];
   __shared__ u32 queue_s[SQ_JBLOCK / 32][SQ_JQUEUE];
+  __shared__ u64 queue_vs[SQ_JBLOCK / 32][SQ_PQMODE ? SQ_JQUEUE : 1];
   bool any_err = false;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   u32* queue = queue_s[warp];
+  u64* queue_v = queue_vs[warp];
   const u32 lanes_below = (1u << lane) - 1u;
   u32 queued = 0;  // warp-uniform
   const int tile_cols[SQ_TILE_NCOLS] = SQ_TILE_COLS;
@@ -188,7 +168,7 @@ extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_tma_kernel(Sq
     const u64* tl = sq_tiles + (size_t)stage * SQ_TILE_NCOLS * SQ_TROWS;
     const i64 base = tile * SQ_TROWS + (i64)warp * (SQ_JUNROLL * 32);
     // ---- phase A out of shared memory
-    u64 hh[SQ_JUNROLL];
+    u64 hh[SQ_JUNROLL], qvv[SQ_JUNROLL];
     bool live[SQ_JUNROLL];
 #pragma unroll
     for (int u = 0; u < SQ_JUNROLL; u++) {
@@ -202,28 +182,33 @@ extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_tma_kernel(Sq
 #endif
       any_err |= e0 || (p.pass && e1);
       hh[u] = p.h;
+      qvv[u] = SQ_PQMODE ? sq_probe_qv(p) : 0ULL;
     }
-    u64 bw[SQ_JUNROLL];
+    u32 bw[SQ_JUNROLL];
 #pragma unroll
-    for (int u = 0; u < SQ_JUNROLL; u++) bw[u] = live[u] ? __ldg(&jt.bloom[sq_bloom_word(hh[u], jt.bloom_mask)]) : 0ULL;
+    for (int u = 0; u < SQ_JUNROLL; u++) bw[u] = live[u] ? __ldg(&jt.bloom[sq_bloom_word(hh[u], jt.bloom_mask)]) : 0u;
 #pragma unroll
     for (int u = 0; u < SQ_JUNROLL; u++) {
-      const u64 bits = sq_bloom_bits(hh[u]);
+      const u32 bits = sq_bloom_bits(hh[u]);
       const bool cand = live[u] && (bw[u] & bits) == bits;
       const u32 m = __ballot_sync(0xffffffffu, cand);
-      if (cand) queue[queued + __popc(m & lanes_below)] = (u32)(base + u * 32 + lane);
+      if (cand) {
+        const u32 pos = queued + __popc(m & lanes_below);
+        queue[pos] = (u32)(base + u * 32 + lane);
+        if (SQ_PQMODE) queue_v[pos] = qvv[u];
+      }
       queued += __popc(m);
     }
     __syncwarp();
     // ---- phase B: full warps only
     while (queued >= 32) {
       queued -= 32;
-      sq_joinagg_candidate(in, inb, (i64)queue[queued + lane], row_base, jt, table, batch_no, status, any_err);
+      sq_joinagg_candidate(in, inb, (i64)queue[queued + lane], SQ_PQMODE ? queue_v[queued + lane] : 0ULL, row_base, jt, table, batch_no, status, any_err);
       __syncwarp();
     }
     __syncthreads();  // every warp is done with this stage before it is refilled
   }
-  if ((u32)lane < queued) sq_joinagg_candidate(in, inb, (i64)queue[lane], row_base, jt, table, batch_no, status, any_err);
+  if ((u32)lane < queued) sq_joinagg_candidate(in, inb, (i64)queue[lane], SQ_PQMODE ? queue_v[lane] : 0ULL, row_base, jt, table, batch_no, status, any_err);
   if (any_err) atomicOr(err, 1u);
 }
 #endif  // SQ_TMA

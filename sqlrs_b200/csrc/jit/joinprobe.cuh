@@ -17,10 +17,12 @@
 extern "C" __global__ void __launch_bounds__(SQ_PBLOCK) sq_joinprobe_kernel(SqIn in, i64 n, SqJoin jt, int keep_unmatched, int* __restrict__ slot_of,
                                                                              u32* __restrict__ chunk_counts, u32* __restrict__ err) {
   __shared__ u32 queue_s[SQ_PBLOCK / 32][SQ_PUNROLL * 32];
+  __shared__ u64 queue_vs[SQ_PBLOCK / 32][SQ_PQMODE ? SQ_PUNROLL * 32 : 1];
   __shared__ u32 warp_total[SQ_PBLOCK / 32];
   bool any_err = false;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   u32* queue = queue_s[warp];
+  u64* queue_v = queue_vs[warp];
   const u32 lanes_below = (1u << lane) - 1u;
   const i64 n_chunks = (n + SQ_PCHUNK - 1) / SQ_PCHUNK;
   for (i64 chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
@@ -28,7 +30,8 @@ extern "C" __global__ void __launch_bounds__(SQ_PBLOCK) sq_joinprobe_kernel(SqIn
     u32 out_rows = 0;  // per lane
     u32 queued = 0;    // warp-uniform
     // ---- phase A: streaming Filter + hash + Bloom test (see joinagg.cuh)
-    u64 hh[SQ_PUNROLL];
+    u64 qv[SQ_PUNROLL];
+    u32 bits[SQ_PUNROLL], bw[SQ_PUNROLL];
     bool live[SQ_PUNROLL], kept[SQ_PUNROLL];
 #pragma unroll
     for (int u = 0; u < SQ_PUNROLL; u++) {
@@ -43,19 +46,21 @@ extern "C" __global__ void __launch_bounds__(SQ_PBLOCK) sq_joinprobe_kernel(SqIn
       live[u] = live[u] && p.knull == 0u;  // SQL semantics: a NULL key never joins
 #endif
       any_err |= (inb && e0) || (kept[u] && e1);
-      hh[u] = p.h;
+      qv[u] = SQ_PQMODE ? sq_probe_qv(p) : 0ULL;
+      bits[u] = sq_bloom_bits(p.h);
+      bw[u] = sq_bloom_word(p.h, jt.bloom_mask);
     }
-    u64 bw[SQ_PUNROLL];
 #pragma unroll
-    for (int u = 0; u < SQ_PUNROLL; u++) bw[u] = live[u] ? __ldg(&jt.bloom[sq_bloom_word(hh[u], jt.bloom_mask)]) : 0ULL;
+    for (int u = 0; u < SQ_PUNROLL; u++) bw[u] = live[u] ? __ldg(&jt.bloom[bw[u]]) : 0u;
 #pragma unroll
     for (int u = 0; u < SQ_PUNROLL; u++) {
       const i64 r = base + u * 32 + lane;
-      const u64 bits = sq_bloom_bits(hh[u]);
-      const bool cand = live[u] && (bw[u] & bits) == bits;
+      const bool cand = live[u] && (bw[u] & bits[u]) == bits[u];
       const u32 m = __ballot_sync(0xffffffffu, cand);
       if (cand) {
-        queue[queued + __popc(m & lanes_below)] = (u32)(u * 32 + lane);
+        const u32 pos = queued + __popc(m & lanes_below);
+        queue[pos] = (u32)(u * 32 + lane);
+        if (SQ_PQMODE) queue_v[pos] = qv[u];
       } else if (r < n) {
         slot_of[r] = kept[u] ? -1 : -2;
         out_rows += (kept[u] && keep_unmatched) ? 1u : 0u;
@@ -67,8 +72,12 @@ extern "C" __global__ void __launch_bounds__(SQ_PBLOCK) sq_joinprobe_kernel(SqIn
     for (u32 i = lane; i < queued; i += 32) {
       const i64 r = base + queue[i];
       SqProbe p;
+#if SQ_PQMODE
+      sq_probe_unq(queue_v[i], p);
+#else
       bool e0 = false, e1 = false;
       sq_probe_row(in, r, p, e0, e1);
+#endif
       const int slot = sq_join_find(jt, p);
       slot_of[r] = slot;
       out_rows += slot >= 0 ? (jt.unique ? 1u : __ldg(&jt.slot_count[slot])) : (keep_unmatched ? 1u : 0u);

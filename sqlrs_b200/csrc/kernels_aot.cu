@@ -505,6 +505,13 @@ void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, ui
   scratch_free(count, stream);
 }
 
+void launch_table_pack_list(const TableView& t, int n_keys, int n_acc, const uint32_t* slot_list, uint32_t n, uint64_t* dst, cudaStream_t stream) {
+  if (n == 0) return;
+  k_table_pack_ordered<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, slot_list, n, dst);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
 void launch_table_rehash(const TableView& from, const TableView& to, int n_keys, int n_acc, cudaStream_t stream) {
   k_table_rehash<<<grid_for(from.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(from, to, n_keys, n_acc);
   count_launch();

@@ -81,10 +81,12 @@ struct JoinTableView {
   int n_keys;
   int match_keys;         // SQLRS_MATCH_HASH_AND_KEY: compare key tuples, NULL never joins
   const uint32_t* build_keep;  // optional bitmap: build rows that pass the Filter fused below the join (nullptr = all)
-  // blocked Bloom filter over the row hashes of the inserted build rows: 3 bits in ONE 64-bit word per key
-  // (join_bloom_word / join_bloom_bits below).  A few MB, so it stays L2-resident under a streaming probe scan
-  // and turns a probe miss — the common case of a selective join — into one 8-byte L2 read.
-  uint64_t* bloom;
+  // blocked Bloom filter over the row hashes of the inserted build rows: 3 bits in ONE 32-bit word per key, >= 16 bits
+  // of filter per key (join_bloom_word / join_bloom_bits below: the word comes from the hash's high half, the bit positions
+  // from its low 15 bits — a dozen 32-bit instructions per probe row, which matters because the fused probe kernels are
+  // instruction-issue bound).  A few MB, so it stays L2-resident under a streaming probe scan and turns a probe miss —
+  // the common case of a selective join — into one 4-byte L2 read.
+  uint32_t* bloom;
   uint32_t bloom_mask;    // number of words - 1 (power of two)
   int unique;             // every build key occurs once (primary-key side): slot_rep is the whole match list,
                           // slot_start / rows are not built
@@ -101,12 +103,12 @@ struct JoinTableView {
 };
 constexpr uint64_t kJoinKvEmpty = 0xffffffffffffffffULL;
 
-SQ_HD inline uint32_t join_bloom_word(uint64_t h, uint32_t mask) { return (uint32_t)((h * 0x9E3779B97F4A7C15ULL) >> 40) & mask; }
-SQ_HD inline uint64_t join_bloom_bits(uint64_t h) {
-  const uint64_t g = h * 0x9E3779B97F4A7C15ULL;
-  return (1ULL << ((g >> 34) & 63)) | (1ULL << ((g >> 28) & 63)) | (1ULL << ((g >> 22) & 63));
+SQ_HD inline uint32_t join_bloom_word(uint64_t h, uint32_t mask) { return (uint32_t)(h >> 32) & mask; }
+SQ_HD inline uint32_t join_bloom_bits(uint64_t h) {
+  const uint32_t lo = (uint32_t)h;
+  return (1u << (lo & 31u)) | (1u << ((lo >> 5) & 31u)) | (1u << ((lo >> 10) & 31u));
 }
-uint32_t join_bloom_words(int64_t n_build);  // sizing rule: power of two >= n_build / 4, within [1024, 2^24]
+uint32_t join_bloom_words(int64_t n_build);  // sizing rule: 32-bit words, power of two >= n_build / 2, within [1024, 2^25]
 
 void launch_scan_u32_large(const uint32_t* counts, int64_t m, unsigned long long* offsets, unsigned long long* total,
                            unsigned long long* scratch /* >= ceil(m/4096)+1 */, cudaStream_t stream);
@@ -161,6 +163,26 @@ struct FinalizeCol {
   int count_epoch;      // COUNT under the overwrite quirk K1: (batch epoch << 40) | count
   uint64_t simple_epoch;  // SimpleAgg + K1: only the last batch counts (0 = not applicable)
 };
-void launch_finalize_groups(const uint64_t* packed, int words, int64_t n, int n_cols, const FinalizeCol* cols_dev, cudaStream_t stream);
+// (the column descriptors travel as kernel parameters: no H2D copy, nothing for the host to keep alive)
+void launch_finalize_groups(const uint64_t* packed, int words, int64_t n, int n_cols, const FinalizeCol* cols_host, cudaStream_t stream);
+// packed rows in the order of a given slot list (no ordering: the consumer orders by something else anyway)
+void launch_table_pack_list(const TableView& t, int n_keys, int n_acc, const uint32_t* slot_list, uint32_t n, uint64_t* dst, cudaStream_t stream);
+
+// ORDER BY ... LIMIT k without sorting: the k smallest rows under the lexicographic order of up to kTopKMaxKeys sort columns
+// (same order-preserving images as sort_pass: NULLs first, descending = complemented), ties broken by `tiebreak[row]`
+// (unique per row; nullptr = the row number, i.e. the stable order) -> perm_out[0 .. min(k, n)) in sorted order.
+// Two launches: every CTA selects the k smallest rows of its slice by k rounds of "smallest key above the previous
+// winner", one CTA does the same over the candidates.  Reads each sort column k times out of L1/L2, writes k row ids.
+constexpr int kTopKMaxKeys = 4;
+constexpr int kTopKMaxRows = 128;
+struct TopKKeys {
+  int m;
+  int dtype[kTopKMaxKeys];
+  int descending[kTopKMaxKeys];
+  const void* data[kTopKMaxKeys];
+  const uint32_t* valid[kTopKMaxKeys];
+  const uint64_t* tiebreak;
+};
+void launch_topk(const TopKKeys& keys, int64_t n, int k, uint32_t* perm_out, cudaStream_t stream);
 
 }  // namespace sq

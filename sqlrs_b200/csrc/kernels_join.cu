@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kBlock) k_join_insert(JoinTableView t, int32_t
         r = *((volatile long long*)&t.slot_rep[slot]);
       }
       row_slot[i[u]] = (int32_t)slot;
-      if (t.bloom) atomicOr((unsigned long long*)&t.bloom[join_bloom_word(h[u], t.bloom_mask)], (unsigned long long)join_bloom_bits(h[u]));
+      if (t.bloom) atomicOr(&t.bloom[join_bloom_word(h[u], t.bloom_mask)], join_bloom_bits(h[u]));
     }
   }
   if (__any_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) *has_dups = 1u;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kBlock) k_join_insert_kv(JoinTableView t, int3
       }
       atomicMin((unsigned long long*)&t.kv[2 * (size_t)slot + 1], (unsigned long long)i[u]);
       row_slot[i[u]] = (int32_t)slot;
-      if (t.bloom) atomicOr((unsigned long long*)&t.bloom[join_bloom_word(h[u], t.bloom_mask)], (unsigned long long)join_bloom_bits(h[u]));
+      if (t.bloom) atomicOr(&t.bloom[join_bloom_word(h[u], t.bloom_mask)], join_bloom_bits(h[u]));
     }
   }
   if (__any_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) misc[0] = 1u;
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kBlock) k_slot_keys(const int32_t* __restrict_
 
 uint32_t join_bloom_words(int64_t n_build) {
   uint64_t w = 1024;
-  while (w < (uint64_t)n_build / 4 && w < (1ULL << 24)) w <<= 1;
+  while (w < (uint64_t)n_build / 2 && w < (1ULL << 25)) w <<= 1;
   return (uint32_t)w;
 }
 

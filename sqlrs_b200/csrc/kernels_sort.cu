@@ -71,8 +71,13 @@ __global__ void __launch_bounds__(kBlock) k_iota_u32(uint32_t* __restrict__ dst,
 }
 
 // packed, ordered group rows -> typed Arrow columns (+ validity words by warp ballot)
+constexpr int kFinalizeMaxCols = 32;
+struct FinalizeCols {
+  FinalizeCol c[kFinalizeMaxCols];
+};
 __global__ void __launch_bounds__(kBlock) k_finalize_groups(const uint64_t* __restrict__ packed, int words, int64_t n, int n_cols,
-                                                            const FinalizeCol* __restrict__ cols) {
+                                                            const __grid_constant__ FinalizeCols cols_p) {
+  const FinalizeCol* cols = cols_p.c;
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n_up = (n + 31) & ~(int64_t)31;
@@ -210,11 +215,145 @@ void sort_pass(int dtype, const void* data, const uint32_t* valid, int64_t n, bo
   scratch_free(p_out, stream);
 }
 
-void launch_finalize_groups(const uint64_t* packed, int words, int64_t n, int n_cols, const FinalizeCol* cols_dev, cudaStream_t stream) {
+void launch_finalize_groups(const uint64_t* packed, int words, int64_t n, int n_cols, const FinalizeCol* cols_host, cudaStream_t stream) {
   if (n <= 0 || n_cols <= 0) return;
-  k_finalize_groups<<<grid_for(n), kBlock, 0, stream>>>(packed, words, n, n_cols, cols_dev);
+  for (int first = 0; first < n_cols; first += kFinalizeMaxCols) {
+    FinalizeCols p{};
+    const int m = std::min(kFinalizeMaxCols, n_cols - first);
+    for (int c = 0; c < m; c++) p.c[c] = cols_host[first + c];
+    k_finalize_groups<<<grid_for(n), kBlock, 0, stream>>>(packed, words, n, m, p);
+    count_launch();
+    SQ_CUDA(cudaGetLastError());
+  }
+}
+
+// ------------------------------------------------------------------ top-k (ORDER BY ... LIMIT k)
+namespace {
+constexpr int kTopKWords = 2 * kTopKMaxKeys + 1;  // per key: (valid flag, image); then the tie-break word
+struct TopKKey {
+  uint64_t w[kTopKWords];
+};
+__device__ __forceinline__ bool topk_less(const TopKKey& a, const TopKKey& b, int nw) {
+#pragma unroll
+  for (int j = 0; j < kTopKWords; j++) {
+    if (j >= nw) break;
+    if (a.w[j] != b.w[j]) return a.w[j] < b.w[j];
+  }
+  return false;
+}
+__device__ __forceinline__ void topk_load(const TopKKeys& keys, uint64_t row, TopKKey& out) {
+#pragma unroll
+  for (int j = 0; j < kTopKMaxKeys; j++) {
+    if (j >= keys.m) break;
+    const bool is_null = keys.valid[j] && !bit_at(keys.valid[j], row);
+    uint64_t img = 0;
+    if (!is_null) {
+      img = sort_image(keys.dtype[j], keys.data[j], row);
+      if (keys.descending[j]) img = ~img;
+    }
+    out.w[2 * j] = is_null ? 0ULL : 1ULL;  // NULLs first, whatever the direction
+    out.w[2 * j + 1] = img;
+  }
+  out.w[2 * keys.m] = keys.tiebreak ? keys.tiebreak[row] : row;
+}
+// block-wide argmin of (key, row) over the threads that have one; every thread receives the winner.  256 threads.
+__device__ __forceinline__ bool topk_block_min(TopKKey& key, uint32_t& row, bool has, int nw, TopKKey* s_key, uint32_t* s_row, int* s_has) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    TopKKey o;
+#pragma unroll
+    for (int j = 0; j < kTopKWords; j++)
+      if (j < nw) o.w[j] = __shfl_xor_sync(0xffffffffu, key.w[j], d);
+    const uint32_t orow = __shfl_xor_sync(0xffffffffu, row, d);
+    const bool ohas = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, d) != 0;
+    if (ohas && (!has || topk_less(o, key, nw))) {
+      key = o;
+      row = orow;
+      has = true;
+    }
+  }
+  if (lane == 0) {
+    s_key[wid] = key;
+    s_row[wid] = row;
+    s_has[wid] = has ? 1 : 0;
+  }
+  __syncthreads();
+  bool any = false;
+  for (int w = 0; w < kBlock / 32; w++) {
+    if (!s_has[w]) continue;
+    if (!any || topk_less(s_key[w], key, nw)) {
+      key = s_key[w];
+      row = s_row[w];
+      any = true;
+    }
+  }
+  __syncthreads();
+  return any;
+}
+
+// rows: nullptr = the CTA's slice [blockIdx.x * slice, +slice) of 0..n; else the n_rows candidate row ids (one CTA)
+__global__ void __launch_bounds__(kBlock) k_topk_select(const __grid_constant__ TopKKeys keys, int64_t n, int64_t slice, const uint32_t* __restrict__ rows,
+                                                        int k, uint32_t* __restrict__ out, uint32_t* __restrict__ out_count) {
+  __shared__ TopKKey s_key[kBlock / 32];
+  __shared__ uint32_t s_row[kBlock / 32];
+  __shared__ int s_has[kBlock / 32];
+  const int nw = 2 * keys.m + 1;
+  const int64_t lo = rows ? 0 : (int64_t)blockIdx.x * slice;
+  const int64_t hi = rows ? n : (lo + slice < n ? lo + slice : n);
+  TopKKey prev;
+  bool have_prev = false;
+  int produced = 0;
+  for (int round = 0; round < k; round++) {
+    TopKKey best;
+    uint32_t best_row = 0;
+    bool has = false;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += kBlock) {
+      const uint32_t r = rows ? rows[i] : (uint32_t)i;
+      if (rows && r == 0xffffffffu) continue;  // a slice that held fewer than k rows
+      TopKKey cur;
+      topk_load(keys, r, cur);
+      if (have_prev && !topk_less(prev, cur, nw)) continue;  // already selected (keys are unique: the tie-break word)
+      if (!has || topk_less(cur, best, nw)) {
+        best = cur;
+        best_row = r;
+        has = true;
+      }
+    }
+    const bool any = topk_block_min(best, best_row, has, nw, s_key, s_row, s_has);
+    if (!any) break;
+    prev = best;
+    have_prev = true;
+    if (threadIdx.x == 0) out[(size_t)blockIdx.x * k + round] = best_row;
+    produced++;
+  }
+  if (threadIdx.x == 0) {
+    for (int j = produced; j < k; j++) out[(size_t)blockIdx.x * k + j] = 0xffffffffu;
+    if (out_count) *out_count = (uint32_t)produced;
+  }
+}
+}  // namespace
+
+void launch_topk(const TopKKeys& keys, int64_t n, int k, uint32_t* perm_out, cudaStream_t stream) {
+  if (n <= 0 || k <= 0) return;
+  if (keys.m < 1 || keys.m > kTopKMaxKeys || k > kTopKMaxRows || n >= (1LL << 32) - 1) fail(SQLRS_ERR_INTERNAL, "launch_topk: unsupported shape");
+  int64_t slice = 4096;
+  while (div_up(n, slice) > 148 * 8) slice *= 2;
+  const int64_t ctas = div_up(n, slice);
+  if (ctas == 1) {
+    k_topk_select<<<1, kBlock, 0, stream>>>(keys, n, slice, nullptr, k, perm_out, nullptr);
+    count_launch();
+    SQ_CUDA(cudaGetLastError());
+    return;
+  }
+  uint32_t* cand = (uint32_t*)scratch_alloc((size_t)ctas * k * 4, stream);
+  k_topk_select<<<(unsigned)ctas, kBlock, 0, stream>>>(keys, n, slice, nullptr, k, cand, nullptr);
   count_launch();
   SQ_CUDA(cudaGetLastError());
+  k_topk_select<<<1, kBlock, 0, stream>>>(keys, ctas * k, 0, cand, k, perm_out, nullptr);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+  scratch_free(cand, stream);
 }
 
 }  // namespace sq

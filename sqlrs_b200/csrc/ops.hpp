@@ -94,7 +94,9 @@ class AggOp {
         ExprCopy fused_predicate, const Options& opt);
   ~AggOp();
   void push(const DBatch& batch);
-  DBatch finish_device();                                      // result as a (small) device batch
+  // result as a device batch.  first_row != nullptr: the groups in ANY order (no sort by first appearance) plus the
+  // column of their first-appearance ordinals — for a consumer that orders by something else (Order above the aggregate)
+  DBatch finish_device(DCol* first_row = nullptr);
   void finish_host(ArrowArray* out, ArrowSchema* out_schema);  // result straight to host Arrow
   Ctx& ctx() { return ctx_; }
   std::string describe() const;

@@ -1107,11 +1107,14 @@ void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
 // the same result as finish_host, but as a device-resident batch (columns in HBM): what an operator above the
 // aggregate in the same plan consumes (Order / Project / Limit), and the fast path to the host for many groups —
 // one kernel turns the ordered packed rows into typed columns + validity words, the host never touches a row
-DBatch AggOp::finish_device() {
+DBatch AggOp::finish_device(DCol* first_row) {
   Trace tr("agg.finish_device", ctx_.stream);
   if (!seen_batch_) fail(SQLRS_ERR_INTERNAL, "called `Option::unwrap()` on a `None` value (no input batch)");
   ctx_.activate();
-  if (distinct_) return finish_distinct();
+  if (distinct_) {
+    if (first_row) fail(SQLRS_ERR_INTERNAL, "finish_device: DISTINCT aggregates are finalised in order");
+    return finish_distinct();
+  }
   const Compiled& c = *cache_.begin()->second;
   const int K = (int)c.key_dtypes.size(), W = (int)c.words.size();
   const int words = 3 + K + W;
@@ -1130,8 +1133,13 @@ DBatch AggOp::finish_device() {
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));  // `host` is a stack vector
   } else if (n > 0) {
     SQ_CUDA(cudaMemsetAsync(packed->p, 0, (size_t)words * 8, ctx_.stream));
-    // first-appearance order (hash_agg.rs:98,134)
-    pack_sorted(K, W, n, (uint64_t*)packed->p);
+    if (first_row) {  // any order: straight from the slot list / a scan of the table
+      if (slot_list_complete_) launch_table_pack_list(table_->view(), K, W, (const uint32_t*)table_->new_slots->p, n, (uint64_t*)packed->p, ctx_.stream);
+      else launch_table_pack(table_->view(), K, W, (uint64_t*)packed->p, n, ctx_.stream);
+    } else {
+      // first-appearance order (hash_agg.rs:98,134)
+      pack_sorted(K, W, n, (uint64_t*)packed->p);
+    }
   }
   DBatch out;
   out.n = rows;
@@ -1174,11 +1182,20 @@ DBatch AggOp::finish_device() {
     desc.push_back(d);
     out.cols.push_back(col);
   }
+  if (first_row) {  // the groups' first-appearance ordinals (packed word 1) as one more Int64 column
+    *first_row = make_col(ctx_, SQLRS_DT_INT64, rows, false);
+    FinalizeCol d{};
+    d.data = col_data(*first_row);
+    d.valid = nullptr;
+    d.dtype = SQLRS_DT_INT64;
+    d.word = 1;
+    d.null_bit = -1;
+    d.nvalid_word = -1;
+    desc.push_back(d);
+  }
   if (rows > 0 && !desc.empty()) {
-    BufPtr d_desc = dev_alloc(ctx_, desc.size() * sizeof(FinalizeCol));
-    SQ_CUDA(cudaMemcpyAsync(d_desc->p, desc.data(), desc.size() * sizeof(FinalizeCol), cudaMemcpyHostToDevice, ctx_.stream));
-    launch_finalize_groups((const uint64_t*)packed->p, words, rows, (int)desc.size(), (const FinalizeCol*)d_desc->p, ctx_.stream);
-    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));  // `desc` is a stack vector; the columns are ready for any stream
+    launch_finalize_groups((const uint64_t*)packed->p, words, rows, (int)desc.size(), desc.data(), ctx_.stream);
+    ctx_.defer([packed]() {});
   }
   return out;
 }

@@ -34,6 +34,19 @@ ProbeProgram gen_probe_program(const std::vector<ColInfo>& cols, const std::vect
     jknull += " | (n" + std::to_string(jkeys[k].id) + " ? 0u : " + std::to_string(1u << k) + "u)";
   }
   s << "  p.knull = " << jknull << ";\n}\n";
+  // What phase B needs of a candidate row besides its number (csrc/jit/joinagg.cuh): ONE queued u64 — the key bits of a
+  // single compared key (the hash is re-derived from them), or the row hash itself when the hash is the identity.
+  // Several compared keys (SQ_PQMODE 0): phase B re-evaluates the row.
+  const int pqmode = jmatch ? (JK == 1 ? 1 : 0) : 2;
+  s << "#define SQ_PQMODE " << pqmode << "\n";
+  if (pqmode == 1) {
+    s << "__device__ __forceinline__ u64 sq_probe_rehash(const u64* kb) {\n" << RowProgram::mix_hash_of_bits_source({jkeys[0].dtype}) << "}\n";
+    s << "__device__ __forceinline__ u64 sq_probe_qv(const SqProbe& p) { return p.kb[0]; }\n";
+    s << "__device__ __forceinline__ void sq_probe_unq(u64 qv, SqProbe& p) { p.pass = true; p.kb[0] = qv; p.knull = 0u; p.h = sq_probe_rehash(p.kb); }\n";
+  } else if (pqmode == 2) {
+    s << "__device__ __forceinline__ u64 sq_probe_qv(const SqProbe& p) { return p.h; }\n";
+    s << "__device__ __forceinline__ void sq_probe_unq(u64 qv, SqProbe& p) { p.pass = true; p.h = qv; p.knull = 0u; }\n";
+  }
   ProbeProgram out;
   // TMA variant: the same statements with the streaming column loads redirected to a shared-memory tile.  Only when
   // every loaded column is 8 bytes wide (bulk copies of whole 2048-row column slices) and at most 3 are read.
@@ -246,8 +259,8 @@ void JoinOp::seal() {
   v.build_keep = im.build_pred.empty() ? nullptr : (const uint32_t*)im.keep_all.data;
   v.n_inserted = n_insert;
   const uint32_t bloom_words = join_bloom_words(n_insert);
-  im.bloom = dev_alloc_zero(ctx_, (size_t)bloom_words * 8);
-  v.bloom = (uint64_t*)im.bloom->p;
+  im.bloom = dev_alloc_zero(ctx_, (size_t)bloom_words * 4);
+  v.bloom = (uint32_t*)im.bloom->p;
   v.bloom_mask = bloom_words - 1;
   im.max_count = n_insert > 0 ? 1 : 0;
   // single key compared by value: key-in-slot layout (kernels_aot.hpp).  A key whose bits equal the empty marker cannot
@@ -600,7 +613,7 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
   }
   struct ChainOut {
     uint64_t* kv;
-    uint64_t* bloom;
+    uint32_t* bloom;
     uint32_t capacity, bloom_mask;
     uint32_t* flags;
     unsigned long long* inserted;
@@ -636,8 +649,8 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
   BufPtr kv = dev_alloc(ctx_, cap * 16);
   SQ_CUDA(cudaMemsetAsync(kv->p, 0xff, cap * 16, ctx_.stream));
   const uint32_t bloom_words = join_bloom_words(est);
-  BufPtr bloom = dev_alloc_zero(ctx_, (size_t)bloom_words * 8);
-  ChainOut out{(uint64_t*)kv->p, (uint64_t*)bloom->p, (uint32_t)cap, bloom_words - 1, (uint32_t*)status->p, (unsigned long long*)((uint32_t*)status->p + 4)};
+  BufPtr bloom = dev_alloc_zero(ctx_, (size_t)bloom_words * 4);
+  ChainOut out{(uint64_t*)kv->p, (uint32_t*)bloom->p, (uint32_t)cap, bloom_words - 1, (uint32_t*)status->p, (unsigned long long*)((uint32_t*)status->p + 4)};
   launch(out, 1);
   SQ_CUDA(cudaMemcpyAsync(host_, status->p, sizeof(Host), cudaMemcpyDeviceToHost, ctx_.stream));
   hint_probe_rows_ = n;
@@ -663,7 +676,7 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
   v.n_build = n;
   v.n_keys = 1;
   v.match_keys = 1;
-  v.bloom = (uint64_t*)bloom->p;
+  v.bloom = (uint32_t*)bloom->p;
   v.bloom_mask = bloom_words - 1;
   v.unique = 1;
   v.n_inserted = inserted;

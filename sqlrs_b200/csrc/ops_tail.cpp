@@ -1,6 +1,8 @@
 // sqlrs_b200 — Project / Order / Limit on device batches (see tail.hpp; kernels: csrc/jit/eval.cuh, kernels_sort.cu).
 #include "tail.hpp"
 
+#include <cstdlib>
+
 #include "kernels_aot.hpp"
 
 namespace sq {
@@ -134,6 +136,9 @@ OrderOp::OrderOp(std::vector<ExprCopy> order_by, std::vector<bool> asc, const Op
   if (asc_.size() != order_by_.size()) fail(SQLRS_ERR_INVALID_ARG, "order: one direction per sort expression");
   prog_ = value_program(order_by_, &slot_);
 }
+bool OrderOp::topk_applies(int64_t row_limit) const {
+  return row_limit >= 1 && row_limit <= kTopKMaxRows && order_by_.size() <= (size_t)kTopKMaxKeys && !std::getenv("SQLRS_B200_NO_TOPK");
+}
 DBatch OrderOp::finish() { return finish(ctx_); }
 DBatch OrderOp::finish(Ctx& ctx) {
   Trace tr("order.finish", ctx.stream);
@@ -145,8 +150,36 @@ DBatch OrderOp::finish(Ctx& ctx) {
   std::vector<DCol> keys = eval_values(ctx, prog_.get(), order_by_, slot_, all, "order by");  // :30-43
   for (const DCol& k : keys)
     if (k.dtype == SQLRS_DT_UTF8) fail(SQLRS_ERR_UNSUPPORTED, "Utf8 sort keys are not supported by the CUDA backend yet");
+  // ORDER BY ... LIMIT k (the plan passed the Limit down): select the k first rows instead of sorting all n.  Not for arrow's
+  // single-column descending sort over a column with NULLs, which also reverses the run of NULL rows (sort_pass).
+  bool topk = topk_applies(row_limit_);
+  for (size_t c = 0; c < keys.size(); c++)
+    if (keys[c].dtype == SQLRS_DT_NULL || (keys.size() == 1 && !asc_[c] && keys[c].valid)) topk = false;
+  if (topk) {
+    TopKKeys tk{};
+    tk.m = (int)keys.size();
+    for (size_t c = 0; c < keys.size(); c++) {
+      tk.dtype[c] = keys[c].dtype;
+      tk.descending[c] = asc_[c] ? 0 : 1;
+      tk.data[c] = keys[c].data;
+      tk.valid[c] = keys[c].valid;
+    }
+    tk.tiebreak = has_tiebreak_ ? (const uint64_t*)tiebreak_.data : nullptr;
+    const int64_t m = std::min(row_limit_, n);
+    BufPtr perm = dev_alloc(ctx, (size_t)m * 4);
+    launch_topk(tk, n, (int)m, (uint32_t*)perm->p, ctx.stream);
+    DBatch out;
+    out.fields = all.fields;
+    out.n = m;
+    for (const DCol& c : all.cols) out.cols.push_back(gather_col_u32(ctx, c, (const uint32_t*)perm->p, m));
+    DCol tb = tiebreak_;
+    ctx.defer([perm, keys, tb]() {});
+    return out;
+  }
   BufPtr perm = dev_alloc(ctx, (size_t)std::max<int64_t>(n, 1) * 4);
   launch_iota_u32((uint32_t*)perm->p, n, 0u, ctx.stream);
+  // unordered input with first-appearance ordinals: they are the least significant sort key
+  if (has_tiebreak_) sort_pass(SQLRS_DT_INT64, tiebreak_.data, nullptr, n, false, false, (uint32_t*)perm->p, ctx.stream);
   // lexsort_to_indices (:45) as an LSD sequence of stable passes, last sort expression first.  A single descending
   // column goes through arrow's sort_to_indices, which also reverses the run of NULL rows.
   const bool single = keys.size() == 1;

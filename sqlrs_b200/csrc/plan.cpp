@@ -389,8 +389,25 @@ std::vector<DBatch> Plan::run(int idx, const Needed& needed) {
       if (!child_need.empty())
         for (const ExprCopy& e : n.exprs) mark_refs(e, child_need);
       n.order_op->set_row_limit(fusion() ? n.row_limit_hint : -1);
-      description_ += n.row_limit_hint >= 0 && fusion() ? "[Order + Limit: stable LSD radix sort of row ids, top-" + std::to_string(n.row_limit_hint) + " rows gathered] "
-                                                        : "[Order: stable LSD radix sort of row ids + gather] ";
+      const bool topk = fusion() && n.order_op->topk_applies(n.row_limit_hint);
+      description_ += topk ? "[Order + Limit: top-" + std::to_string(n.row_limit_hint) + " selection (k rounds of block-wide argmin), rows gathered] "
+                           : (n.row_limit_hint >= 0 && fusion() ? "[Order + Limit: stable LSD radix sort of row ids, top-" + std::to_string(n.row_limit_hint) + " rows gathered] "
+                                                                 : "[Order: stable LSD radix sort of row ids + gather] ");
+      const int ck = nodes_[n.child0].kind;
+      if (topk && (ck == SQLRS_NODE_SIMPLE_AGG || ck == SQLRS_NODE_HASH_AGG)) {
+        // the aggregate's groups are not sorted by first appearance first: the selection breaks ties by the ordinals
+        AggOp& agg = run_agg(n.child0);
+        if (!agg.has_distinct()) {
+          DCol first_row;
+          DBatch r = agg.finish_device(&first_row);
+          description_ += "[aggregate finalised on the device, unordered] ";
+          n.order_op->set_tiebreak(first_row);
+          n.order_op->push(r);
+          return {n.order_op->finish(ctx_)};
+        }
+        n.order_op->push(agg.finish_device());
+        return {n.order_op->finish(ctx_)};
+      }
       for (const DBatch& b : run(n.child0, child_need)) n.order_op->push(b);
       return {n.order_op->finish(ctx_)};
     }

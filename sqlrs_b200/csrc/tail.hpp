@@ -32,9 +32,20 @@ class OrderOp {
   void push(const DBatch& b) { batches_.push_back(b); }
   // plan-level fusion with a Limit above (top-k): only the first `rows` sorted rows are gathered; < 0 = all
   void set_row_limit(int64_t rows) { row_limit_ = rows; }
+  // Rows that tie on every sort key come out in input order (stable).  An aggregate below may hand its groups over in
+  // ANY order together with this column of their first-appearance ordinals (unique, Int64): ties then resolve by it,
+  // which is the order the sorted hand-over would have produced — without sorting the groups first.
+  void set_tiebreak(DCol first_row) { tiebreak_ = std::move(first_row); has_tiebreak_ = true; }
+  // can finish() use the top-k selection (no full sort) for this row limit?  (what the plan asks before it skips the
+  // aggregate's ordered finalisation)
+  bool topk_applies(int64_t row_limit) const;
   DBatch finish();
   DBatch finish(Ctx& ctx);
-  void reset() { batches_.clear(); }
+  void reset() {
+    batches_.clear();
+    has_tiebreak_ = false;
+    tiebreak_ = DCol();
+  }
   Ctx& ctx() { return ctx_; }
 
  private:
@@ -45,6 +56,8 @@ class OrderOp {
   std::unique_ptr<EvalProgram> prog_;
   std::vector<int> slot_;
   int64_t row_limit_ = -1;
+  DCol tiebreak_;
+  bool has_tiebreak_ = false;
 };
 
 class LimitOp {
