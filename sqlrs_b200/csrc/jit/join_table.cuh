@@ -25,6 +25,7 @@ struct SqJoin {           // mirrors sq::JoinTableView (kernels_aot.hpp)
   i64 n_inserted;
 };
 #define SQ_KV_EMPTY 0xffffffffffffffffULL
+#define SQ_KV_L2_SLOTS (4u << 20)  /* a kv table with more slots (> 64 MB) is not worth L2 space: its probes are single-use */
 
 // (mirrors join_bloom_word / join_bloom_bits of kernels_aot.hpp: all 32-bit arithmetic on the two halves of the hash)
 __device__ __forceinline__ u32 sq_bloom_word(u64 h, u32 mask) { return (u32)(h >> 32) & mask; }
@@ -44,7 +45,7 @@ __device__ __forceinline__ int sq_join_find_rep(const SqJoin& t, const SqProbe& 
   if (t.kv) {  // ONE 16-byte read per probe step: {key bits, representative row}
     if (t.kv_dtype != SQ_JKEY0_DTYPE || p.kb[0] == SQ_KV_EMPTY) return -1;
     for (u32 probes = 0; probes <= mask; probes++) {
-      const ulonglong2 e = __ldg((const ulonglong2*)t.kv + s);
+      const ulonglong2 e = t.capacity > SQ_KV_L2_SLOTS ? sq_ld_u64x2_l2((const ulonglong2*)t.kv + s, sq_l2_evict_first()) : __ldg((const ulonglong2*)t.kv + s);
       if (e.x == p.kb[0]) {
         rep_out = (i64)e.y;
         return (int)s;
@@ -101,7 +102,7 @@ __device__ __forceinline__ int sq_join_find(const SqJoin& t, const SqProbe& p) {
       bits[u] = sq_bloom_bits(p.h);                                                                           \
       bw[u] = sq_bloom_word(p.h, jt.bloom_mask);                                                              \
     }                                                                                                         \
-    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) bw[u] = live[u] ? __ldg(&jt.bloom[bw[u]]) : 0u;        \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) bw[u] = live[u] ? sq_ld_u32_l2(&jt.bloom[bw[u]], pol_keep) : 0u; \
     _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                                      \
       const bool cand = live[u] && (bw[u] & bits[u]) == bits[u];                                              \
       const u32 m = __ballot_sync(0xffffffffu, cand);                                                         \

@@ -81,6 +81,7 @@ extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_kernel(SqIn i
   u64* queue_v = queue_vs[threadIdx.x >> 5];
   const u32 lanes_below = (1u << lane) - 1u;
   u32 queued = 0;  // warp-uniform
+  const u64 pol_keep = sq_l2_evict_last();
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 base = ((i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * SQ_JUNROLL; base < n; base += stride * SQ_JUNROLL) {
     SQ_PHASE_A(SQ_JUNROLL, base + u * 32 + lane)  // n < 2^32 (checked by the host)
@@ -186,7 +187,7 @@ extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_tma_kernel(Sq
     }
     u32 bw[SQ_JUNROLL];
 #pragma unroll
-    for (int u = 0; u < SQ_JUNROLL; u++) bw[u] = live[u] ? __ldg(&jt.bloom[sq_bloom_word(hh[u], jt.bloom_mask)]) : 0u;
+    for (int u = 0; u < SQ_JUNROLL; u++) bw[u] = live[u] ? sq_ld_u32_l2(&jt.bloom[sq_bloom_word(hh[u], jt.bloom_mask)], sq_l2_evict_last()) : 0u;
 #pragma unroll
     for (int u = 0; u < SQ_JUNROLL; u++) {
       const u32 bits = sq_bloom_bits(hh[u]);

@@ -24,6 +24,7 @@ extern "C" __global__ void __launch_bounds__(SQ_PBLOCK) sq_joinprobe_kernel(SqIn
   u32* queue = queue_s[warp];
   u64* queue_v = queue_vs[warp];
   const u32 lanes_below = (1u << lane) - 1u;
+  const u64 pol_keep = sq_l2_evict_last();
   const i64 n_chunks = (n + SQ_PCHUNK - 1) / SQ_PCHUNK;
   for (i64 chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     const i64 base = chunk * SQ_PCHUNK + (i64)warp * (SQ_PUNROLL * 32);
@@ -51,7 +52,7 @@ extern "C" __global__ void __launch_bounds__(SQ_PBLOCK) sq_joinprobe_kernel(SqIn
       bw[u] = sq_bloom_word(p.h, jt.bloom_mask);
     }
 #pragma unroll
-    for (int u = 0; u < SQ_PUNROLL; u++) bw[u] = live[u] ? __ldg(&jt.bloom[bw[u]]) : 0u;
+    for (int u = 0; u < SQ_PUNROLL; u++) bw[u] = live[u] ? sq_ld_u32_l2(&jt.bloom[bw[u]], pol_keep) : 0u;
 #pragma unroll
     for (int u = 0; u < SQ_PUNROLL; u++) {
       const i64 r = base + u * 32 + lane;

@@ -18,6 +18,42 @@ __device__ __forceinline__ int sq_ldg_i32(const void* p, i64 r) { return __ldg((
 __device__ __forceinline__ double sq_ldg_f64(const void* p, i64 r) { return __ldg(((const double*)p) + r); }
 __device__ __forceinline__ bool sq_ld_bit(const void* p, i64 r) { return (__ldg(((const u32*)p) + (r >> 5)) >> (r & 31)) & 1u; }
 
+// ---- L2 residency control.  The fused join kernels mix three kinds of traffic through the 126 MB L2: a column stream (GBs,
+// no reuse: evict-first loads above), random single-use accesses to hash tables far larger than the L2 (hundreds of MB), and
+// small hot structures — the Bloom filters, a few MB to tens of MB — that every probe row reads.  Measured (profiles/
+// r02b_*): with the default policy the table traffic turns the whole L2 over every ~20 us and evicts the Bloom words
+// between touches (90 % of the Bloom atomics and 45 % of the Bloom loads went to DRAM).  So: hot structures are accessed
+// with an evict-last policy, single-use table accesses with evict-first.
+__device__ __forceinline__ u64 sq_l2_evict_last() {
+  u64 p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ u64 sq_l2_evict_first() {
+  u64 p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ u32 sq_ld_u32_l2(const u32* a, u64 pol) {  // read-only data
+  u32 v;
+  asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ ulonglong2 sq_ld_u64x2_l2(const ulonglong2* a, u64 pol) {  // read-only data
+  ulonglong2 v;
+  asm("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(a), "l"(pol));
+  return v;
+}
+// (atom.cas takes no cache hint — ptxas: "Illegal modifier '.L2::cache_hint'" — so a table insert is a plain CAS followed by a
+// hinted store of the payload, which leaves the line marked evict-first)
+__device__ __forceinline__ u64 sq_cas_u64_l2(u64* a, u64 cmp, u64 val, u64) { return atomicCAS(a, cmp, val); }
+__device__ __forceinline__ void sq_st_u64_l2(u64* a, u64 val, u64 pol) {
+  asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(a), "l"(val), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void sq_red_or_u32_l2(u32* a, u32 val, u64 pol) {
+  asm volatile("red.global.or.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(a), "r"(val), "l"(pol) : "memory");
+}
+
 // ---- ahash 0.8.0 fallback hasher with RandomState::with_seeds(0,0,0,0), as the reference uses it
 // (src/executor/aggregate/hash_utils.rs:161-220; constants pinned by its KAT :229-247):
 //   buf = folded_multiply(v ^ k0, MULTIPLE);  h = rotl(folded_multiply(buf, k1), buf & 63)

@@ -48,6 +48,13 @@ class JoinOp {
   // a build side produced elsewhere (JoinChainOp: the previous join's probe built this table directly): `build` is the
   // (virtual) build batch the table's row ids index, `keep` the buffers the view points into
   void adopt_build(DBatch build, const struct JoinTableView& view, std::vector<BufPtr> keep);
+  // A caller that validates the run afterwards (JoinChainOp) may pass what the previous run of the same plan learned: the
+  // number of build rows its fused Filter kept.  seal() then sizes the table from it, assumes unique keys and does NOT
+  // synchronise; it copies {flags u32[6] (kernels_aot.hpp: launch_join_insert_kv), pad, kept rows u64} to `pinned`
+  // (8 x u32 + u64, pinned host memory) on the stream for the caller to check.  Only taken for the kv layout.
+  void set_build_hint(int64_t kept_rows, uint32_t* pinned) { hint_kept_ = kept_rows; hint_pinned_ = pinned; }
+  bool sealed_deferred() const { return sealed_deferred_; }
+  int64_t build_rows() const;
   // generated CUDA of the fused probe kernel for probe batches of that schema (diagnostics / build check, no GPU)
   std::string debug_probe_source(const std::vector<ColInfo>& probe_cols, const ExprCopy& probe_pred) const;
 
@@ -63,6 +70,9 @@ class JoinOp {
   ExprCopy filter_;
   std::vector<Field> out_fields_;
   std::unique_ptr<Impl> impl_;
+  int64_t hint_kept_ = -1;
+  uint32_t* hint_pinned_ = nullptr;
+  bool sealed_deferred_ = false;
 };
 
 // Left-deep join chains: join 1's probe builds join 2's table directly (csrc/jit/joinchain.cuh), nothing of join 1's output
@@ -92,8 +102,12 @@ class JoinChainOp {
   struct Host {  // pinned
     uint32_t flags[4];
     unsigned long long inserted;
+    uint32_t j1_flags[8];          // join 1's deferred seal (JoinOp::set_build_hint)
+    unsigned long long j1_kept;
   };
   Host* host_ = nullptr;
+  int64_t hint_j1_kept_ = -1;
+  bool j1_deferred_ = false;
   int64_t hint_inserted_ = -1, hint_probe_rows_ = -1, hint_build_rows_ = -1;
   uint64_t cap_used_ = 0;
   bool pending_ = false, disabled_ = false;

@@ -116,7 +116,7 @@ size_t scan_scratch_entries(int64_t m);
 
 // inserts the distinct keys (slot_rep, Bloom filter, row_slot); *has_dups = 1 when some key occurred more than once
 void launch_join_insert(const JoinTableView& t, int32_t* row_slot, uint32_t* has_dups, cudaStream_t stream);
-// the same into the kv layout; misc[0] = 1 when some key repeats, misc[4] = 1 when a key equals kJoinKvEmpty (table unusable)
+// the same into the kv layout; misc[0] = 1 when some key repeats, misc[4] = 1 when a key equals kJoinKvEmpty (table unusable), misc[5] = 1 when the table ran full
 void launch_join_insert_kv(const JoinTableView& t, int32_t* row_slot, uint32_t* misc, cudaStream_t stream);
 // (only then) rows per slot into t.slot_count (zero-initialised) and the largest count into *max_count
 void launch_join_count(const JoinTableView& t, const int32_t* row_slot, uint32_t* max_count, cudaStream_t stream);

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kBlock) k_join_insert(JoinTableView t, int32_t
 __global__ void __launch_bounds__(kBlock) k_join_insert_kv(JoinTableView t, int32_t* __restrict__ row_slot, uint32_t* __restrict__ misc) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const uint32_t mask = t.capacity - 1;
-  bool dup = false, sentinel = false;
+  bool dup = false, sentinel = false, full = false;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < t.n_build; base += stride * kInsertBatch) {
     int64_t i[kInsertBatch];
     bool live[kInsertBatch];
@@ -131,15 +131,25 @@ __global__ void __launch_bounds__(kBlock) k_join_insert_kv(JoinTableView t, int3
       }
       uint32_t slot = s[u];
       unsigned long long cur = seen[u];
-      for (;;) {
+      bool placed = true;
+      for (uint32_t probes = 0;; probes++) {
         if (cur == kJoinKvEmpty) cur = atomicCAS((unsigned long long*)&t.kv[2 * (size_t)slot], (unsigned long long)kJoinKvEmpty, (unsigned long long)key[u]);
         if (cur == kJoinKvEmpty) break;  // claimed
         if (cur == key[u]) {
           dup = true;
           break;
         }
+        if (probes >= mask) {  // table full (sized from a stale hint): flagged, the host rebuilds
+          full = true;
+          placed = false;
+          break;
+        }
         slot = (slot + 1) & mask;
         cur = *((volatile unsigned long long*)&t.kv[2 * (size_t)slot]);
+      }
+      if (!placed) {
+        row_slot[i[u]] = -1;
+        continue;
       }
       atomicMin((unsigned long long*)&t.kv[2 * (size_t)slot + 1], (unsigned long long)i[u]);
       row_slot[i[u]] = (int32_t)slot;
@@ -148,6 +158,7 @@ __global__ void __launch_bounds__(kBlock) k_join_insert_kv(JoinTableView t, int3
   }
   if (__any_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) misc[0] = 1u;
   if (__any_sync(0xffffffffu, sentinel) && (threadIdx.x & 31) == 0) misc[4] = 1u;
+  if (__any_sync(0xffffffffu, full) && (threadIdx.x & 31) == 0) misc[5] = 1u;
 }
 
 // only when some key repeats: rows per slot and the largest such count

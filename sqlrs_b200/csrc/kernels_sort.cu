@@ -229,42 +229,55 @@ void launch_finalize_groups(const uint64_t* packed, int words, int64_t n, int n_
 
 // ------------------------------------------------------------------ top-k (ORDER BY ... LIMIT k)
 namespace {
-constexpr int kTopKWords = 2 * kTopKMaxKeys + 1;  // per key: (valid flag, image); then the tie-break word
+constexpr int kTopKWords = 2 * kTopKMaxKeys + 1;
 struct TopKKey {
   uint64_t w[kTopKWords];
 };
+// w[0] = tie-break word (compared LAST), w[1 + 2j] / w[2 + 2j] = (valid flag, image) of sort column j; nw = 1 + 2m words are
+// in use — the others are never touched, and all indices are static so the key lives in registers
 __device__ __forceinline__ bool topk_less(const TopKKey& a, const TopKKey& b, int nw) {
+  bool less = false, decided = false;
 #pragma unroll
-  for (int j = 0; j < kTopKWords; j++) {
-    if (j >= nw) break;
-    if (a.w[j] != b.w[j]) return a.w[j] < b.w[j];
+  for (int j = 1; j < kTopKWords; j++) {
+    if (j < nw) {
+      const bool ne = a.w[j] != b.w[j];
+      if (!decided && ne) less = a.w[j] < b.w[j];
+      decided = decided || ne;
+    }
   }
-  return false;
+  if (!decided) less = a.w[0] < b.w[0];
+  return less;
 }
 __device__ __forceinline__ void topk_load(const TopKKeys& keys, uint64_t row, TopKKey& out) {
 #pragma unroll
   for (int j = 0; j < kTopKMaxKeys; j++) {
-    if (j >= keys.m) break;
-    const bool is_null = keys.valid[j] && !bit_at(keys.valid[j], row);
-    uint64_t img = 0;
-    if (!is_null) {
-      img = sort_image(keys.dtype[j], keys.data[j], row);
-      if (keys.descending[j]) img = ~img;
+    uint64_t flag = 0, img = 0;
+    if (j < keys.m) {
+      const bool is_null = keys.valid[j] && !bit_at(keys.valid[j], row);
+      flag = is_null ? 0ULL : 1ULL;  // NULLs first, whatever the direction
+      if (!is_null) {
+        img = sort_image(keys.dtype[j], keys.data[j], row);
+        if (keys.descending[j]) img = ~img;
+      }
     }
-    out.w[2 * j] = is_null ? 0ULL : 1ULL;  // NULLs first, whatever the direction
-    out.w[2 * j + 1] = img;
+    out.w[1 + 2 * j] = flag;
+    out.w[2 + 2 * j] = img;
   }
-  out.w[2 * keys.m] = keys.tiebreak ? keys.tiebreak[row] : row;
+  out.w[0] = keys.tiebreak ? keys.tiebreak[row] : row;
 }
-// block-wide argmin of (key, row) over the threads that have one; every thread receives the winner.  256 threads.
+__device__ __forceinline__ void topk_shfl(const TopKKey& in, TopKKey& o, int d, int nw) {
+#pragma unroll
+  for (int j = 0; j < kTopKWords; j++)
+    if (j < nw) o.w[j] = __shfl_xor_sync(0xffffffffu, in.w[j], d);
+}
+// block-wide argmin of (key, row) over the threads that have one; every thread receives the winner
+template <int THREADS>
 __device__ __forceinline__ bool topk_block_min(TopKKey& key, uint32_t& row, bool has, int nw, TopKKey* s_key, uint32_t* s_row, int* s_has) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     TopKKey o;
-#pragma unroll
-    for (int j = 0; j < kTopKWords; j++)
-      if (j < nw) o.w[j] = __shfl_xor_sync(0xffffffffu, key.w[j], d);
+    topk_shfl(key, o, d, nw);
     const uint32_t orow = __shfl_xor_sync(0xffffffffu, row, d);
     const bool ohas = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, d) != 0;
     if (ohas && (!has || topk_less(o, key, nw))) {
@@ -279,81 +292,102 @@ __device__ __forceinline__ bool topk_block_min(TopKKey& key, uint32_t& row, bool
     s_has[wid] = has ? 1 : 0;
   }
   __syncthreads();
-  bool any = false;
-  for (int w = 0; w < kBlock / 32; w++) {
-    if (!s_has[w]) continue;
-    if (!any || topk_less(s_key[w], key, nw)) {
-      key = s_key[w];
-      row = s_row[w];
-      any = true;
+  // every warp reduces the per-warp winners again (THREADS / 32 <= 32 entries)
+  const int src = lane < THREADS / 32 ? lane : 0;
+  TopKKey k2 = s_key[src];
+  uint32_t r2 = s_row[src];
+  bool h2 = lane < THREADS / 32 && s_has[src] != 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    TopKKey o;  // (all five steps: every lane ends up with the winner)
+    topk_shfl(k2, o, d, nw);
+    const uint32_t orow = __shfl_xor_sync(0xffffffffu, r2, d);
+    const bool ohas = __shfl_xor_sync(0xffffffffu, h2 ? 1 : 0, d) != 0;
+    if (ohas && (!h2 || topk_less(o, k2, nw))) {
+      k2 = o;
+      r2 = orow;
+      h2 = true;
     }
   }
   __syncthreads();
-  return any;
+  key = k2;
+  row = r2;
+  return h2;
 }
 
-// rows: nullptr = the CTA's slice [blockIdx.x * slice, +slice) of 0..n; else the n_rows candidate row ids (one CTA)
-__global__ void __launch_bounds__(kBlock) k_topk_select(const __grid_constant__ TopKKeys keys, int64_t n, int64_t slice, const uint32_t* __restrict__ rows,
-                                                        int k, uint32_t* __restrict__ out, uint32_t* __restrict__ out_count) {
+// One reduction pass: CTA b takes kTopKPer entries per thread (rows_in[b * kTopKCta ...], or the row numbers themselves when
+// rows_in == nullptr), loads their keys into registers ONCE, and emits its k smallest in order: k rounds of block-wide
+// argmin over registers, no memory traffic in the rounds.  Passes repeat until one CTA is left (launch_topk).
+constexpr int kTopKPer = 4, kTopKCta = kBlock * kTopKPer;
+__global__ void __launch_bounds__(kBlock) k_topk_pass(const __grid_constant__ TopKKeys keys, const uint32_t* __restrict__ rows_in, int64_t n_in, int k,
+                                                      uint32_t* __restrict__ out) {
   __shared__ TopKKey s_key[kBlock / 32];
   __shared__ uint32_t s_row[kBlock / 32];
   __shared__ int s_has[kBlock / 32];
-  const int nw = 2 * keys.m + 1;
-  const int64_t lo = rows ? 0 : (int64_t)blockIdx.x * slice;
-  const int64_t hi = rows ? n : (lo + slice < n ? lo + slice : n);
-  TopKKey prev;
-  bool have_prev = false;
-  int produced = 0;
+  const int nw = 1 + 2 * keys.m;
+  TopKKey ck[kTopKPer];
+  uint32_t crow[kTopKPer];
+  bool live[kTopKPer];
+#pragma unroll
+  for (int c = 0; c < kTopKPer; c++) {
+    const int64_t i = (int64_t)blockIdx.x * kTopKCta + c * kBlock + threadIdx.x;
+    crow[c] = i < n_in ? (rows_in ? rows_in[i] : (uint32_t)i) : 0xffffffffu;
+    live[c] = crow[c] != 0xffffffffu;
+  }
+#pragma unroll
+  for (int c = 0; c < kTopKPer; c++) topk_load(keys, live[c] ? crow[c] : 0, ck[c]);
   for (int round = 0; round < k; round++) {
     TopKKey best;
     uint32_t best_row = 0;
     bool has = false;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += kBlock) {
-      const uint32_t r = rows ? rows[i] : (uint32_t)i;
-      if (rows && r == 0xffffffffu) continue;  // a slice that held fewer than k rows
-      TopKKey cur;
-      topk_load(keys, r, cur);
-      if (have_prev && !topk_less(prev, cur, nw)) continue;  // already selected (keys are unique: the tie-break word)
-      if (!has || topk_less(cur, best, nw)) {
-        best = cur;
-        best_row = r;
+#pragma unroll
+    for (int j = 0; j < kTopKWords; j++) best.w[j] = 0;
+#pragma unroll
+    for (int c = 0; c < kTopKPer; c++)
+      if (live[c] && (!has || topk_less(ck[c], best, nw))) {
+        best = ck[c];
+        best_row = crow[c];
         has = true;
       }
+    const bool any = topk_block_min<kBlock>(best, best_row, has, nw, s_key, s_row, s_has);
+    if (threadIdx.x == 0) out[(size_t)blockIdx.x * k + round] = any ? best_row : 0xffffffffu;
+    if (!any) {
+      if (threadIdx.x == 0)
+        for (int j = round + 1; j < k; j++) out[(size_t)blockIdx.x * k + j] = 0xffffffffu;
+      break;
     }
-    const bool any = topk_block_min(best, best_row, has, nw, s_key, s_row, s_has);
-    if (!any) break;
-    prev = best;
-    have_prev = true;
-    if (threadIdx.x == 0) out[(size_t)blockIdx.x * k + round] = best_row;
-    produced++;
-  }
-  if (threadIdx.x == 0) {
-    for (int j = produced; j < k; j++) out[(size_t)blockIdx.x * k + j] = 0xffffffffu;
-    if (out_count) *out_count = (uint32_t)produced;
+#pragma unroll
+    for (int c = 0; c < kTopKPer; c++)
+      if (live[c] && crow[c] == best_row) live[c] = false;
   }
 }
 }  // namespace
 
 void launch_topk(const TopKKeys& keys, int64_t n, int k, uint32_t* perm_out, cudaStream_t stream) {
   if (n <= 0 || k <= 0) return;
-  if (keys.m < 1 || keys.m > kTopKMaxKeys || k > kTopKMaxRows || n >= (1LL << 32) - 1) fail(SQLRS_ERR_INTERNAL, "launch_topk: unsupported shape");
-  int64_t slice = 4096;
-  while (div_up(n, slice) > 148 * 8) slice *= 2;
-  const int64_t ctas = div_up(n, slice);
-  if (ctas == 1) {
-    k_topk_select<<<1, kBlock, 0, stream>>>(keys, n, slice, nullptr, k, perm_out, nullptr);
+  if (keys.m < 1 || keys.m > kTopKMaxKeys || k > kTopKMaxRows || n >= (1LL << 32) - 2) fail(SQLRS_ERR_INTERNAL, "launch_topk: unsupported shape");
+  // every pass turns kTopKCta entries into k candidates
+  const uint32_t* in = nullptr;
+  int64_t n_in = n;
+  uint32_t* bufs[2] = {nullptr, nullptr};
+  int which = 0;
+  for (;;) {
+    const int64_t ctas = div_up(n_in, kTopKCta);
+    uint32_t* dst = perm_out;
+    if (ctas > 1) {
+      if (!bufs[which]) bufs[which] = (uint32_t*)scratch_alloc((size_t)ctas * k * 4, stream);  // (later passes need less)
+      dst = bufs[which];
+    }
+    k_topk_pass<<<(unsigned)ctas, kBlock, 0, stream>>>(keys, in, n_in, k, dst);
     count_launch();
     SQ_CUDA(cudaGetLastError());
-    return;
+    if (ctas == 1) break;
+    in = dst;
+    n_in = ctas * k;
+    which ^= 1;
   }
-  uint32_t* cand = (uint32_t*)scratch_alloc((size_t)ctas * k * 4, stream);
-  k_topk_select<<<(unsigned)ctas, kBlock, 0, stream>>>(keys, n, slice, nullptr, k, cand, nullptr);
-  count_launch();
-  SQ_CUDA(cudaGetLastError());
-  k_topk_select<<<1, kBlock, 0, stream>>>(keys, ctas * k, 0, cand, k, perm_out, nullptr);
-  count_launch();
-  SQ_CUDA(cudaGetLastError());
-  scratch_free(cand, stream);
+  for (uint32_t* b : bufs)
+    if (b) scratch_free(b, stream);
 }
 
 }  // namespace sq

@@ -231,13 +231,24 @@ void JoinOp::seal() {
   // number of kept rows (one bit count + sync): Q3's customer table shrinks 5x, which is what keeps it L2-resident
   // under the probe scan
   int64_t n_insert = n;
+  bool use_kv = mk && K == 1 && !std::getenv("SQLRS_B200_NO_KV");
+  const bool deferred = use_kv && hint_pinned_ && n > 0 && (im.build_pred.empty() || hint_kept_ >= 0);
   if (!im.build_pred.empty() && n > 0) {
     BufPtr cnt = dev_alloc_zero(ctx_, 8);
     launch_count_bits((const uint32_t*)im.keep_all.data, n, (unsigned long long*)cnt->p, ctx_.stream);
-    unsigned long long kept = 0;
-    SQ_CUDA(cudaMemcpyAsync(&kept, cnt->p, 8, cudaMemcpyDeviceToHost, ctx_.stream));
-    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
-    n_insert = (int64_t)kept;
+    if (deferred) {  // sized from the previous run's count (+12 %); this run's count travels to the caller for the next one
+      SQ_CUDA(cudaMemcpyAsync(hint_pinned_ + 8, cnt->p, 8, cudaMemcpyDeviceToHost, ctx_.stream));
+      n_insert = hint_kept_ + hint_kept_ / 8 + 64;
+      ctx_.defer([cnt]() {});
+    } else {
+      unsigned long long kept = 0;
+      SQ_CUDA(cudaMemcpyAsync(&kept, cnt->p, 8, cudaMemcpyDeviceToHost, ctx_.stream));
+      SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+      n_insert = (int64_t)kept;
+      if (hint_pinned_) *(unsigned long long*)(hint_pinned_ + 8) = kept;
+    }
+  } else if (hint_pinned_) {
+    *(unsigned long long*)(hint_pinned_ + 8) = (unsigned long long)n;
   }
   uint64_t cap = 1024;
   while (cap < 2ULL * (uint64_t)n_insert) cap <<= 1;
@@ -265,7 +276,6 @@ void JoinOp::seal() {
   im.max_count = n_insert > 0 ? 1 : 0;
   // single key compared by value: key-in-slot layout (kernels_aot.hpp).  A key whose bits equal the empty marker cannot
   // be stored there; the insert kernel flags it and the table is rebuilt in the slot_rep layout.
-  bool use_kv = mk && K == 1 && !std::getenv("SQLRS_B200_NO_KV");
   for (int attempt = 0; attempt < 2; attempt++) {
     if (use_kv) {
       im.slot_rep = dev_alloc(ctx_, cap * 16);
@@ -287,9 +297,16 @@ void JoinOp::seal() {
     BufPtr misc = dev_alloc_zero(ctx_, 32);  // u32 [0] has duplicates, [1] max count, [2..3] u64 total, [4] kv: a key equals the empty marker
     if (use_kv) launch_join_insert_kv(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
     else launch_join_insert(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
-    uint32_t flags[5] = {0, 0, 0, 0, 0};
+    if (deferred) {  // unique keys assumed; the caller checks the flags once the stream has been synchronised
+      SQ_CUDA(cudaMemcpyAsync(hint_pinned_, misc->p, 24, cudaMemcpyDeviceToHost, ctx_.stream));
+      ctx_.defer([row_slot, misc]() {});
+      sealed_deferred_ = true;
+      break;
+    }
+    uint32_t flags[6] = {0, 0, 0, 0, 0, 0};
     SQ_CUDA(cudaMemcpyAsync(flags, misc->p, sizeof(flags), cudaMemcpyDeviceToHost, ctx_.stream));
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    if (hint_pinned_) std::memcpy(hint_pinned_, flags, sizeof(flags));
     if (use_kv && flags[4]) {  // rare: rebuild in the other layout (the Bloom filter already holds a superset: harmless)
       use_kv = false;
       continue;
@@ -341,6 +358,7 @@ std::string JoinOp::debug_probe_source(const std::vector<ColInfo>& probe_cols, c
 }
 
 bool JoinOp::empty_build() const { return impl_->capacity == 0; }
+int64_t JoinOp::build_rows() const { return impl_->left_rows; }
 const JoinTableView& JoinOp::table_view() const { return impl_->view; }
 const DBatch& JoinOp::build_side() const { return impl_->left_single; }
 
@@ -548,6 +566,9 @@ std::string JoinChainOp::debug_source(const std::vector<ColInfo>& build_cols, co
   const int raw = prog.emit_raw_bits(k);
   const int h = prog.emit_mix_hash({raw}, {k});  // the placement hash gen_probe_program gives join 2's probe side
   if (key_dtype) *key_dtype = k.dtype;
+  bool uses_build = false;  // does join 2's key read a build-1 column?  (then it cannot be evaluated before join 1's probe resolved)
+  for (const ExprNodeCopy& nd : key2) uses_build |= nd.op == SQLRS_OP_INPUT_REF && nd.index < (int)build_cols.size();
+  s << "#define SQ_CHAIN_KEY_USES_BUILD " << (uses_build ? 1 : 0) << "\n";
   s << "struct SqChainKey { u64 h; u64 kb; u32 knull; };\n";
   s << "__device__ __forceinline__ void sq_chain_key(const SqIn& in, const SqInB& inb, i64 r, i64 b, SqChainKey& o, bool& e1) {\n  bool e0 = false;\n";
   s << prog.body_str();
@@ -556,6 +577,15 @@ std::string JoinChainOp::debug_source(const std::vector<ColInfo>& build_cols, co
 }
 
 bool JoinChainOp::check_flags() {
+  if (j1_deferred_) {  // join 1 was sealed without a synchronisation: repeated key / unrepresentable key / table full?
+    j1_deferred_ = false;
+    const uint32_t* g = host_->j1_flags;
+    if (g[0] || g[4] || g[5]) {
+      hint_inserted_ = -1;  // the next run goes the synchronised way (which handles all of these)
+      hint_j1_kept_ = -1;
+      return false;
+    }
+  }
   const uint32_t* f = host_->flags;
   if (f[3]) fail(SQLRS_ERR_ARROW, "Divide by zero error (join key)");
   if (f[0] || f[2]) {  // a repeated key needs the CSR lists, an unrepresentable key the slot_rep layout: not this path
@@ -575,6 +605,7 @@ bool JoinChainOp::validate() {
   pending_ = false;
   if (!check_flags()) return false;
   hint_inserted_ = (int64_t)host_->inserted;
+  hint_j1_kept_ = (int64_t)host_->j1_kept;
   return true;
 }
 
@@ -583,11 +614,22 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
   Trace tr("join.chain", ctx_.stream);
   ctx_.activate();
   ctx_.reap();
+  const int64_t n = probe1.n;
+  if (n <= 0 || n >= (1LL << 32)) return false;
+  if (!host_) {
+    SQ_CUDA(cudaHostAlloc((void**)&host_, sizeof(Host), cudaHostAllocDefault));
+    std::memset(host_, 0, sizeof(Host));
+  }
+  // repeated run over tables of the same size: everything is sized from the previous run's numbers, nothing synchronises,
+  // and validate() checks the flags afterwards
+  const bool optimistic = hint_inserted_ >= 0 && hint_probe_rows_ == n && hint_build_rows_ == j1.build_rows() && !(opt_.flags & SQLRS_FLAG_TIMING);
+  std::memset(host_->j1_flags, 0, sizeof(host_->j1_flags));
+  j1.set_build_hint(optimistic ? hint_j1_kept_ : -1, host_->j1_flags);
   j1.seal();
+  j1_deferred_ = j1.sealed_deferred();
   if (j1.empty_build()) return false;
   const JoinTableView& jt = j1.table_view();
-  const int64_t n = probe1.n;
-  if (!jt.unique || jt.capacity == 0 || n <= 0 || n >= (1LL << 32)) return false;
+  if (!jt.unique || jt.capacity == 0) return false;
   const DBatch& build1 = j1.build_side();
   std::vector<ColInfo> pcols = col_infos(probe1), bcols = col_infos(build1);
   const std::string sig = RowProgram(bcols, pcols).signature();
@@ -598,7 +640,6 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
     kit = kernels_.emplace(sig, std::make_pair(jit_get("join_table+joinchain", src, "sq_joinchain_kernel"), key_dtype)).first;
   }
   JitKernel* kernel = kit->second.first;
-  if (!host_) SQ_CUDA(cudaHostAlloc((void**)&host_, sizeof(Host), cudaHostAllocDefault));
 
   const int sms = device_sm_count(ctx_.device);
   const int per_sm = std::max(1, jit_max_blocks_per_sm(kernel, 256, 0));
@@ -629,14 +670,13 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
   };
 
   // ---- how many rows will join 1 yield?  Exact count of the previous run over tables of the same size, else a strided sample
-  bool optimistic = hint_inserted_ >= 0 && hint_probe_rows_ == n && hint_build_rows_ == jt.n_build && !(opt_.flags & SQLRS_FLAG_TIMING);
   int64_t est = hint_inserted_;
   if (!optimistic) {
     const int64_t chunks = div_up(n, 2048);
     const int64_t step = std::max<int64_t>(1, chunks / 4096);  // ~8 M sampled rows at most
     ChainOut cnt{nullptr, nullptr, 0, 0, (uint32_t*)status->p, (unsigned long long*)((uint32_t*)status->p + 4)};
     launch(cnt, step);
-    SQ_CUDA(cudaMemcpyAsync(host_, status->p, sizeof(Host), cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaMemcpyAsync(host_, status->p, 24, cudaMemcpyDeviceToHost, ctx_.stream));
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
     if (host_->flags[3]) fail(SQLRS_ERR_ARROW, "Divide by zero error (join key)");
     est = (int64_t)((double)host_->inserted * (double)step * 1.25) + 4096;
@@ -652,9 +692,9 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
   BufPtr bloom = dev_alloc_zero(ctx_, (size_t)bloom_words * 4);
   ChainOut out{(uint64_t*)kv->p, (uint32_t*)bloom->p, (uint32_t)cap, bloom_words - 1, (uint32_t*)status->p, (unsigned long long*)((uint32_t*)status->p + 4)};
   launch(out, 1);
-  SQ_CUDA(cudaMemcpyAsync(host_, status->p, sizeof(Host), cudaMemcpyDeviceToHost, ctx_.stream));
+  SQ_CUDA(cudaMemcpyAsync(host_, status->p, 24, cudaMemcpyDeviceToHost, ctx_.stream));
   hint_probe_rows_ = n;
-  hint_build_rows_ = jt.n_build;
+  hint_build_rows_ = j1.build_rows();
   int64_t inserted = est;
   if (optimistic) {
     pending_ = true;  // validated by the plan once the stream has been synchronised
@@ -663,6 +703,7 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
     if (!check_flags()) return false;
     inserted = (int64_t)host_->inserted;
     hint_inserted_ = inserted;
+    hint_j1_kept_ = (int64_t)host_->j1_kept;
   }
   ctx_.defer([status]() {});
 
