@@ -135,6 +135,7 @@ typedef struct sqlrs_agg_desc {
 #define SQLRS_FLAG_NO_FUSION 1   /* plan API: never pick a fused pipeline, run operator by operator */
 #define SQLRS_FLAG_DEVICE_OUTPUT 2 /* reserved */
 #define SQLRS_FLAG_TIMING 4 /* bracket the dominant scan kernels with CUDA events (sqlrs_plan_scan_kernel_ms) */
+#define SQLRS_FLAG_KERNEL_EVENTS 8 /* record CUDA events around every hot kernel; adds no synchronisation (sqlrs_kernel_events_collect) */
 
 typedef struct sqlrs_options {
   int32_t count_mode; /* default SQLRS_COUNT_REFERENCE_OVERWRITE */
@@ -333,6 +334,16 @@ int SQLRS_API(plan_push_table_device)(sqlrs_plan* p, int32_t table_slot,
  * and complete when the call returns only for host-visible results (plan_next syncs) */
 int SQLRS_API(plan_execute)(sqlrs_plan* p);
 /* pull the result stream (try_collect, src/executor/mod.rs:58-64) */
+/* The next pending result batch WITHOUT leaving the device (the exchange steps of multi-GPU execution): its shape, and a copy
+ * of its columns into caller-provided DEVICE buffers (columns[c] holds >= n_rows values of the column's width; the copy is
+ * enqueued on the plan's stream).  Columns with NULLs are refused with SQLRS_ERR_UNSUPPORTED (take sqlrs_plan_next).
+ * *has_batch = 0 when nothing is pending. */
+int SQLRS_API(plan_result_shape)(sqlrs_plan* p, int64_t* n_rows, int32_t* n_columns, int32_t* has_batch);
+int SQLRS_API(plan_next_to_device)(sqlrs_plan* p, void* const* columns, int32_t n_columns);
+/* sqlrs_plan_push_table of ONE host batch that the plan then scans in slices of batch_rows rows (a multiple of 32), the
+ * way the reference's scan hands its executor 1024-row batches (src/storage/csv.rs:105): one H2D copy, zero-copy slices. */
+int SQLRS_API(plan_push_table_batched)(sqlrs_plan* p, int32_t table_slot, struct ArrowArray* batch,
+                                       const struct ArrowSchema* schema, int64_t batch_rows);
 int SQLRS_API(plan_next)(sqlrs_plan* p, struct ArrowArray* out, struct ArrowSchema* out_schema,
                          int32_t* has_batch);
 /* forget pushed tables / operator state, keep plan + device scratch (repeated runs) */
@@ -380,6 +391,14 @@ int SQLRS_API(plan_finish_partial)(sqlrs_plan* p);
  * non-blocking stream: export then synchronises before it returns (dst is complete for any stream), and the caller
  * must have completed the writes to `src` (synchronise its own stream) before calling merge. */
 int SQLRS_API(plan_partials_row_words)(sqlrs_plan* p, int32_t* n_words);
+/* Radix partitioning of the partial groups for the all-to-all exchange ("radix-partition partial rows by
+ * hash(keys) mod G"): the groups of the un-finalised table are packed into `n_parts` back-to-back regions of `dst` (DEVICE
+ * memory, on the plan's stream), region q = (cap_rows + 1) rows of *n_words u64 in the layout above, holding the groups
+ * whose identity hash (as u64) mod n_parts == q; its row 0 = header {count (may exceed cap_rows: rows missing, retry larger)}.
+ * Equal-sized regions, so ONE all_to_all_single with equal splits moves them and the receive buffer feeds
+ * sqlrs_plan_merge_partials_device(n_buffers = n_parts) directly.  *groups_out = number of groups in the table (this call
+ * synchronises once to learn it; pass cap_rows <= 0 to only learn the count). */
+int SQLRS_API(plan_export_partials_partitioned)(sqlrs_plan* p, void* dst, int32_t n_parts, int64_t cap_rows, int64_t* groups_out);
 int SQLRS_API(plan_export_partials_device)(sqlrs_plan* p, void* dst, int64_t cap_rows);
 int SQLRS_API(plan_merge_partials_device)(sqlrs_plan* p, const void* src, int32_t n_buffers, int64_t cap_rows);
 /* SQLRS_FLAG_TIMING: device time (ms, CUDA events on the plan's stream) the dominant scan kernel(s) of the
@@ -441,6 +460,9 @@ int SQLRS_API(debug_compile_joinchain)(const sqlrs_expr* right_keys1, int32_t n_
                                        int32_t compile, char** source_out);
 int SQLRS_API(debug_compile_eval)(const sqlrs_expr* exprs, int32_t n_exprs, int32_t as_keep_mask,
                                   const struct ArrowSchema* input_schema, int32_t compile, char** source_out);
+/* SQLRS_FLAG_KERNEL_EVENTS: JSON {"kernel": {"ms": total device time, "launches": n}, ...} of the events recorded since the
+ * last call (call after synchronising the stream).  malloc'ed; release with sqlrs_free.  Oracle: "{}". */
+int SQLRS_API(kernel_events_collect)(char** json_out);
 void SQLRS_API(free)(void* p);
 
 #ifdef __cplusplus

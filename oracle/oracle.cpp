@@ -449,6 +449,44 @@ int sqlrs_oracle_plan_create(const sqlrs_plan_node* nodes, int32_t n_nodes, int3
 int sqlrs_oracle_plan_push_table(sqlrs_plan* p, int32_t table_slot, ArrowArray* batch, const ArrowSchema* schema) {
   return guarded([&] { p->tables[table_slot].push_back(consume_batch(batch, schema)); });
 }
+// one host batch handed to the executor in slices of batch_rows rows — what the reference's scan does with its 1024-row
+// batches (src/storage/csv.rs:105, memory.rs:151-170); the slicing happens here, outside any timed executor run
+int sqlrs_oracle_plan_push_table_batched(sqlrs_plan* p, int32_t table_slot, ArrowArray* batch, const ArrowSchema* schema, int64_t batch_rows) {
+  return guarded([&] {
+    if (batch_rows <= 0) fail(SQLRS_ERR_INVALID_ARG, "push_table_batched: batch_rows must be positive");
+    Batch whole = consume_batch(batch, schema);
+    if (whole.n == 0) {
+      p->tables[table_slot].push_back(std::move(whole));
+      return;
+    }
+    for (int64_t off = 0; off < whole.n; off += batch_rows) {
+      Batch b;
+      b.fields = whole.fields;
+      b.n = std::min(batch_rows, whole.n - off);
+      for (const ColPtr& c : whole.cols) b.cols.push_back(slice_column(*c, off, b.n));
+      p->tables[table_slot].push_back(std::move(b));
+    }
+  });
+}
+int sqlrs_oracle_plan_result_shape(sqlrs_plan*, int64_t*, int32_t*, int32_t*) {
+  g_last_error = "the oracle keeps no device results";
+  return SQLRS_ERR_UNSUPPORTED;
+}
+int sqlrs_oracle_plan_next_to_device(sqlrs_plan*, void* const*, int32_t) {
+  g_last_error = "the oracle keeps no device results";
+  return SQLRS_ERR_UNSUPPORTED;
+}
+int sqlrs_oracle_plan_export_partials_partitioned(sqlrs_plan*, void*, int32_t, int64_t, int64_t*) {
+  g_last_error = "the oracle exchanges partials as host batches only";
+  return SQLRS_ERR_UNSUPPORTED;
+}
+int sqlrs_oracle_kernel_events_collect(char** json_out) {
+  if (json_out) {
+    *json_out = (char*)std::malloc(3);
+    if (*json_out) std::memcpy(*json_out, "{}", 3);
+  }
+  return SQLRS_OK;
+}
 int sqlrs_oracle_plan_push_table_device(sqlrs_plan*, int32_t, ArrowDeviceArray*, const ArrowSchema*) {
   g_last_error = "the oracle takes host batches only";
   return SQLRS_ERR_UNSUPPORTED;

@@ -362,6 +362,42 @@ int sqlrs_plan_push_table(sqlrs_plan* p, int32_t table_slot, ArrowArray* batch, 
     p->impl.push_table(table_slot, import_batch_host(p->impl.ctx(), batch, schema));
   });
 }
+static char* dup_string(const std::string& s);
+int sqlrs_plan_push_table_batched(sqlrs_plan* p, int32_t table_slot, ArrowArray* batch, const ArrowSchema* schema, int64_t batch_rows) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.ctx().activate();
+    p->impl.push_table_batched(table_slot, import_batch_host(p->impl.ctx(), batch, schema), batch_rows);
+  });
+}
+int sqlrs_plan_result_shape(sqlrs_plan* p, int64_t* n_rows, int32_t* n_columns, int32_t* has_batch) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    const bool has = p->impl.result_shape(n_rows, n_columns);
+    if (has_batch) *has_batch = has ? 1 : 0;
+  });
+}
+int sqlrs_plan_next_to_device(sqlrs_plan* p, void* const* columns, int32_t n_columns) {
+  return guarded([&] {
+    if (!p || !columns) fail(SQLRS_ERR_INVALID_ARG, "plan / columns is NULL");
+    p->impl.ctx().activate();
+    p->impl.next_to_device(columns, n_columns);
+  });
+}
+int sqlrs_plan_export_partials_partitioned(sqlrs_plan* p, void* dst, int32_t n_parts, int64_t cap_rows, int64_t* groups_out) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.ctx().activate();
+    const int64_t g = p->impl.export_partials_partitioned((uint64_t*)dst, n_parts, cap_rows);
+    if (groups_out) *groups_out = g;
+  });
+}
+int sqlrs_kernel_events_collect(char** json_out) {
+  return guarded([&] {
+    if (!json_out) fail(SQLRS_ERR_INVALID_ARG, "json_out is NULL");
+    *json_out = dup_string(kernel_events_collect_json());
+  });
+}
 int sqlrs_plan_push_table_device(sqlrs_plan* p, int32_t table_slot, ArrowDeviceArray* batch, const ArrowSchema* schema) {
   return guarded([&] {
     if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");

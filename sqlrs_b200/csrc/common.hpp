@@ -76,6 +76,22 @@ struct Trace {
   }
 };
 
+// SQLRS_FLAG_KERNEL_EVENTS: CUDA events around the hot kernels, recorded on the launching stream and resolved later
+// (kernel_events_collect, after the caller synchronised) — no synchronisation is added to the run.  device.cpp.
+void kernel_event_begin(cudaStream_t stream, const char* name);
+void kernel_event_end(cudaStream_t stream);
+std::string kernel_events_collect_json();  // {"name": {"ms": total, "launches": n}, ...}; clears the record
+struct KernelEvent {
+  cudaStream_t stream;
+  bool on;
+  KernelEvent(int flags, cudaStream_t s, const char* name) : stream(s), on((flags & SQLRS_FLAG_KERNEL_EVENTS) != 0) {
+    if (on) kernel_event_begin(stream, name);
+  }
+  ~KernelEvent() {
+    if (on) kernel_event_end(stream);
+  }
+};
+
 inline const char* dtype_name(int dt) {
   switch (dt) {
     case SQLRS_DT_NULL: return "Null";

@@ -15,6 +15,62 @@ std::atomic<int64_t> g_kernel_launches{0};
 
 static void flush_stream_cache(int device, cudaStream_t stream);  // block cache below
 
+// ------------------------------------------------------------------ kernel events (SQLRS_FLAG_KERNEL_EVENTS)
+namespace {
+struct EventRec {
+  std::string name;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool closed = false;
+};
+std::mutex g_events_mu;
+std::vector<EventRec> g_events;
+}  // namespace
+void kernel_event_begin(cudaStream_t stream, const char* name) {
+  EventRec r;
+  r.name = name;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, stream);
+  std::lock_guard<std::mutex> lock(g_events_mu);
+  g_events.push_back(r);
+}
+void kernel_event_end(cudaStream_t stream) {  // closes the innermost open record (scopes nest)
+  std::lock_guard<std::mutex> lock(g_events_mu);
+  for (size_t i = g_events.size(); i-- > 0;) {
+    if (g_events[i].closed) continue;
+    cudaEventRecord(g_events[i].e1, stream);
+    g_events[i].closed = true;
+    break;
+  }
+}
+std::string kernel_events_collect_json() {
+  std::lock_guard<std::mutex> lock(g_events_mu);
+  std::map<std::string, std::pair<double, int64_t>> acc;
+  for (EventRec& r : g_events) {
+    if (r.closed) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+        auto& a = acc[r.name];
+        a.first += ms;
+        a.second += 1;
+      }
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_events.clear();
+  cudaGetLastError();
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : acc) {
+    char buf[256];
+    std::snprintf(buf, sizeof buf, "%s\"%s\": {\"ms\": %.6f, \"launches\": %lld}", first ? "" : ", ", kv.first.c_str(), kv.second.first, (long long)kv.second.second);
+    out += buf;
+    first = false;
+  }
+  return out + "}";
+}
+
 // ------------------------------------------------------------------ Ctx
 static void tune_pool(int device) {
   static std::mutex mu;

@@ -234,6 +234,27 @@ __global__ void __launch_bounds__(kBlock) k_table_pack(TableView t, int n_keys, 
   }
 }
 
+// radix partitioning for the multi-GPU exchange: group rows packed into n_parts regions by identity hash mod n_parts;
+// region q starts at dst + q * (cap_rows + 1) * words, its row 0 is the header {count}
+__global__ void __launch_bounds__(kBlock) k_table_pack_partitioned(TableView t, int n_keys, int n_acc, uint64_t* __restrict__ dst, unsigned n_parts,
+                                                                    unsigned long long cap_rows) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const int words = 3 + n_keys + n_acc;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
+    if (t.state[s] != 2u) continue;
+    const uint64_t h = t.hash[s];
+    uint64_t* region = dst + (size_t)(h % n_parts) * (cap_rows + 1) * words;
+    const unsigned long long o = atomicAdd((unsigned long long*)region, 1ULL);
+    if (o >= cap_rows) continue;  // header keeps counting: the consumer sees count > capacity
+    uint64_t* row = region + (size_t)(1 + o) * words;
+    row[0] = h;
+    row[1] = t.min_row[s];
+    row[2] = t.knull[s];
+    for (int k = 0; k < n_keys; k++) row[3 + k] = t.keys[(size_t)k * t.capacity + s];
+    for (int w = 0; w < n_acc; w++) row[3 + n_keys + w] = t.acc[(size_t)w * t.capacity + s];
+  }
+}
+
 // occupied slots and their first-row ids, in table order (input of the ordering sort)
 __global__ void __launch_bounds__(kBlock) k_table_list(TableView t, uint64_t* __restrict__ min_rows, uint32_t* __restrict__ slots,
                                                         uint32_t max_out, uint32_t* __restrict__ count) {
@@ -505,6 +526,11 @@ void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, ui
   scratch_free(count, stream);
 }
 
+void launch_table_pack_partitioned(const TableView& t, int n_keys, int n_acc, uint64_t* dst, int n_parts, uint64_t cap_rows, cudaStream_t stream) {
+  k_table_pack_partitioned<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, dst, (unsigned)n_parts, cap_rows);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
 void launch_table_pack_list(const TableView& t, int n_keys, int n_acc, const uint32_t* slot_list, uint32_t n, uint64_t* dst, cudaStream_t stream) {
   if (n == 0) return;
   k_table_pack_ordered<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, slot_list, n, dst);

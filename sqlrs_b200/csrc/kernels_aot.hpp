@@ -165,6 +165,8 @@ struct FinalizeCol {
 };
 // (the column descriptors travel as kernel parameters: no H2D copy, nothing for the host to keep alive)
 void launch_finalize_groups(const uint64_t* packed, int words, int64_t n, int n_cols, const FinalizeCol* cols_host, cudaStream_t stream);
+// the same into n_parts regions of (cap_rows + 1) rows each, by identity hash mod n_parts (headers must be zeroed)
+void launch_table_pack_partitioned(const TableView& t, int n_keys, int n_acc, uint64_t* dst, int n_parts, uint64_t cap_rows, cudaStream_t stream);
 // packed rows in the order of a given slot list (no ordering: the consumer orders by something else anyway)
 void launch_table_pack_list(const TableView& t, int n_keys, int n_acc, const uint32_t* slot_list, uint32_t n, uint64_t* dst, cudaStream_t stream);
 

@@ -110,6 +110,7 @@ class AggOp {
   void merge_partials(const DBatch& partials);
   int partial_row_words() const;  // u64 words per packed partial row: 3 + keys + accumulator words
   void export_partials_device(uint64_t* dst, int64_t cap_rows);
+  int64_t export_partials_partitioned(uint64_t* dst, int n_parts, int64_t cap_rows);  // returns the group count (one sync)
   void merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows, bool sync_after = false);
   void reset();  // forget all groups, keep compiled kernels and buffers
   // fused probe -> aggregate over an INNER hash join whose build side is sealed in `join` (csrc/jit/joinagg.cuh):

@@ -689,7 +689,10 @@ void AggOp::push(const DBatch& batch) {
     int n_entries = (int)entries;
     void* args_small[] = {in.ptr(), &n_arg, &rb, &part, &status, &errp};
     ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
-    jit_launch(c.small, (unsigned)grid, (unsigned)c.block, c.small_smem, ctx_.stream, args_small);
+    {
+      KernelEvent ev(opt_.flags, ctx_.stream, "sq_agg_small");
+      jit_launch(c.small, (unsigned)grid, (unsigned)c.block, c.small_smem, ctx_.stream, args_small);
+    }
     timer.stop();
     void* args_merge[] = {&part, &n_entries, &tv, &bn, &status};
     jit_launch(c.merge, (unsigned)div_up(n_entries, 128), 128, 0, ctx_.stream, args_merge);
@@ -722,7 +725,10 @@ void AggOp::push(const DBatch& batch) {
     int n_entries = (int)entries;
     void* args[] = {in.ptr(), &n_arg, &rb, &part, &status, &errp};
     ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
-    jit_launch(c.medium, (unsigned)grid, 256, c.medium_smem, ctx_.stream, args);
+    {
+      KernelEvent ev(opt_.flags, ctx_.stream, "sq_agg_medium");
+      jit_launch(c.medium, (unsigned)grid, 256, c.medium_smem, ctx_.stream, args);
+    }
     timer.stop();
     void* args_merge[] = {&part, &n_entries, &tv, &bn, &status};
     jit_launch(c.merge, (unsigned)div_up(n_entries, 128), 128, 0, ctx_.stream, args_merge);
@@ -752,7 +758,10 @@ void AggOp::push(const DBatch& batch) {
       const int sms = device_sm_count(ctx_.device);
       unsigned grid = (unsigned)std::min<int64_t>(div_up(len, 256), (int64_t)sms * 8);
       ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
-      jit_launch(c.global, grid, 256, 0, ctx_.stream, args);
+      {
+        KernelEvent ev(opt_.flags, ctx_.stream, "sq_agg_global");
+        jit_launch(c.global, grid, 256, 0, ctx_.stream, args);
+      }
       timer.stop();
       if (timer.enabled) {
         SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
@@ -824,6 +833,8 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
   rows_seen_ += n;
   if (n == 0) return;
   if (n >= (1LL << 32)) fail(SQLRS_ERR_INVALID_ARG, "a probe batch may hold fewer than 2^32 rows (hash_join.rs:219)");
+  // first-appearance ordinals of the joined stream are (global probe row << 20 | match ordinal) in one u64
+  if ((uint64_t)(row_base + n) >= (1ULL << 44)) fail(SQLRS_ERR_UNSUPPORTED, "fused probe + aggregate: global probe row numbers must stay below 2^44");
 
   // The number of joined rows (and groups) is unknown before the probe: aggregate into a batch-local table sized
   // optimistically; a full table discards it and retries 4x larger, so a batch counts all-or-nothing.
@@ -881,6 +892,7 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
       const int per_sm = std::max(1, jit_max_blocks_per_sm(jk.generic, 256, 0));
       unsigned grid = (unsigned)std::min<int64_t>(div_up(n_arg, 2048), (int64_t)sms * per_sm);  // 256 threads x SQ_JUNROLL (8) rows per trip
       void* args[] = {in_tail.ptr(), inb.ptr(), &n_arg, &rb_tail, &jv, &tv, &bn, &status, &errp};
+      KernelEvent ev(opt_.flags, ctx_.stream, "sq_joinagg_kernel");
       jit_launch(jk.generic, grid, 256, 0, ctx_.stream, args);
     }
     timer.stop();
@@ -1109,6 +1121,7 @@ void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
 // one kernel turns the ordered packed rows into typed columns + validity words, the host never touches a row
 DBatch AggOp::finish_device(DCol* first_row) {
   Trace tr("agg.finish_device", ctx_.stream);
+  KernelEvent ev(opt_.flags, ctx_.stream, "aggregate finalise (pack + k_finalize_groups)");
   if (!seen_batch_) fail(SQLRS_ERR_INTERNAL, "called `Option::unwrap()` on a `None` value (no input batch)");
   ctx_.activate();
   if (distinct_) {
@@ -1330,6 +1343,21 @@ void AggOp::export_partials_device(uint64_t* dst, int64_t cap_rows) {
   const int words = partial_row_words();
   SQ_CUDA(cudaMemsetAsync(dst, 0, (size_t)words * 8, ctx_.stream));
   if (table_ && cap_rows > 0) launch_table_pack(table_->view(), table_->n_keys, table_->n_acc, dst, (uint64_t)cap_rows, ctx_.stream);
+}
+
+int64_t AggOp::export_partials_partitioned(uint64_t* dst, int n_parts, int64_t cap_rows) {
+  check_partial_supported();
+  if (!seen_batch_) fail(SQLRS_ERR_INTERNAL, "called `Option::unwrap()` on a `None` value (no input batch)");
+  if (n_parts < 1) fail(SQLRS_ERR_INVALID_ARG, "n_parts must be >= 1");
+  ctx_.activate();
+  uint32_t hc[4] = {0, 0, 0, 0};
+  if (table_) read_counters(hc);
+  const int64_t groups = table_ ? (int64_t)groups_known_ : 0;
+  if (cap_rows <= 0 || !dst) return groups;
+  const int words = partial_row_words();
+  for (int q = 0; q < n_parts; q++) SQ_CUDA(cudaMemsetAsync(dst + (size_t)q * (cap_rows + 1) * words, 0, (size_t)words * 8, ctx_.stream));
+  if (table_ && groups > 0) launch_table_pack_partitioned(table_->view(), table_->n_keys, table_->n_acc, dst, n_parts, (uint64_t)cap_rows, ctx_.stream);
+  return groups;
 }
 
 void AggOp::clear_partials() {

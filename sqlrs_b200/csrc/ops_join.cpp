@@ -171,7 +171,11 @@ void JoinOp::build_push(const DBatch& batch) {
   ctx_.reap();
   const bool mk = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
   if (!impl_->left_prog) impl_->left_prog = std::make_unique<EvalProgram>(key_request(left_keys_, mk, impl_->build_pred));
-  EvalResult keys = impl_->left_prog->run(ctx_, batch, "join key");
+  EvalResult keys;
+  {
+    KernelEvent ev(opt_.flags, ctx_.stream, "sq_eval_kernel (join build keys + fused Filter)");
+    keys = impl_->left_prog->run(ctx_, batch, "join key");
+  }
   if (!keys.expr_dtypes.empty()) impl_->key0_dtype = keys.expr_dtypes[0];
   if (!impl_->build_pred.empty()) {
     impl_->left_keep_parts.push_back(keys.cols.back());
@@ -295,8 +299,11 @@ void JoinOp::seal() {
     if (n <= 0) break;
     BufPtr row_slot = dev_alloc(ctx_, (size_t)n * 4);
     BufPtr misc = dev_alloc_zero(ctx_, 32);  // u32 [0] has duplicates, [1] max count, [2..3] u64 total, [4] kv: a key equals the empty marker
-    if (use_kv) launch_join_insert_kv(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
-    else launch_join_insert(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
+    {
+      KernelEvent ev(opt_.flags, ctx_.stream, use_kv ? "k_join_insert_kv" : "k_join_insert");
+      if (use_kv) launch_join_insert_kv(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
+      else launch_join_insert(v, (int32_t*)row_slot->p, (uint32_t*)misc->p, ctx_.stream);
+    }
     if (deferred) {  // unique keys assumed; the caller checks the flags once the stream has been synchronised
       SQ_CUDA(cudaMemcpyAsync(hint_pinned_, misc->p, 24, cudaMemcpyDeviceToHost, ctx_.stream));
       ctx_.defer([row_slot, misc]() {});
@@ -450,6 +457,7 @@ bool JoinOp::probe(const DBatch& right, DBatch* result) {
       // persistent grid: exactly the CTAs that are resident at once, so the chunk-stride loop has no ragged second wave
       const int per_sm = std::max(1, jit_max_blocks_per_sm(kit->second, 256, 0));
       const unsigned grid = (unsigned)std::min<int64_t>(chunks, (int64_t)device_sm_count(ctx_.device) * per_sm);
+      KernelEvent ev(opt_.flags, ctx_.stream, "sq_joinprobe_kernel");
       jit_launch(kit->second, grid, 256, 0, ctx_.stream, args);
     }
     unsigned long long* total_d = (unsigned long long*)offsets->p + chunks;
@@ -666,6 +674,7 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
     void* args[] = {in_blob.data(), inb_blob.data(), &n_arg, &jv, &out, &step};
     const int64_t trips = div_up(div_up(n, 2048), chunk_step);
     const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(trips, 1), (int64_t)sms * per_sm);
+    KernelEvent ev(opt_.flags, ctx_.stream, out.kv ? "sq_joinchain_kernel" : "sq_joinchain_kernel (sample count)");
     jit_launch(kernel, grid, 256, 0, ctx_.stream, args);
   };
 

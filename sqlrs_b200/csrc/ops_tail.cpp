@@ -132,7 +132,7 @@ std::vector<DBatch> CrossJoinOp::probe(Ctx& ctx, const DBatch& right) {
 
 // ------------------------------------------------------------------ Order, order.rs:14-66
 OrderOp::OrderOp(std::vector<ExprCopy> order_by, std::vector<bool> asc, const Options& opt)
-    : ctx_(opt), order_by_(std::move(order_by)), asc_(std::move(asc)) {
+    : ctx_(opt), order_by_(std::move(order_by)), asc_(std::move(asc)), flags_(opt.flags) {
   if (asc_.size() != order_by_.size()) fail(SQLRS_ERR_INVALID_ARG, "order: one direction per sort expression");
   prog_ = value_program(order_by_, &slot_);
 }
@@ -142,6 +142,7 @@ bool OrderOp::topk_applies(int64_t row_limit) const {
 DBatch OrderOp::finish() { return finish(ctx_); }
 DBatch OrderOp::finish(Ctx& ctx) {
   Trace tr("order.finish", ctx.stream);
+  KernelEvent ev(flags_, ctx.stream, "order (sort keys + top-k / radix passes + gather)");
   if (batches_.empty()) fail(SQLRS_ERR_INTERNAL, "called `Option::unwrap()` on a `None` value (no input batch)");  // order.rs:27
   DBatch all = concat_batches(ctx, batches_);  // :28
   batches_.clear();

@@ -268,6 +268,66 @@ void Plan::export_partials_device(uint64_t* dst, int64_t cap_rows) {
   // complete when the call returns.  With a caller-provided stream the pack is ordered on that stream.
   if (ctx_.own_stream) SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
 }
+int64_t Plan::export_partials_partitioned(uint64_t* dst, int n_parts, int64_t cap_rows) {
+  if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
+  const int64_t g = partial_op_->export_partials_partitioned(dst, n_parts, cap_rows);
+  if (ctx_.own_stream) SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+  return g;
+}
+bool Plan::result_shape(int64_t* n_rows, int32_t* n_cols) {
+  if (results_.empty()) return false;
+  Result& r = results_.front();
+  if (r.on_host) fail(SQLRS_ERR_UNSUPPORTED, "plan_result_shape: this result was finalised on the host (take sqlrs_plan_next)");
+  if (n_rows) *n_rows = r.dev.n;
+  if (n_cols) *n_cols = (int32_t)r.dev.cols.size();
+  return true;
+}
+void Plan::next_to_device(void* const* columns, int32_t n_columns) {
+  if (results_.empty()) fail(SQLRS_ERR_INVALID_ARG, "plan_next_to_device: no pending result");
+  Result& r = results_.front();
+  if (r.on_host) fail(SQLRS_ERR_UNSUPPORTED, "plan_next_to_device: this result was finalised on the host (take sqlrs_plan_next)");
+  if (n_columns != (int32_t)r.dev.cols.size()) fail(SQLRS_ERR_INVALID_ARG, "plan_next_to_device: column count mismatch");
+  for (int32_t c = 0; c < n_columns; c++) {
+    DCol& col = r.dev.cols[(size_t)c];
+    if (col.dtype == SQLRS_DT_NULL || col.dtype == SQLRS_DT_BOOL || col.dtype == SQLRS_DT_UTF8)
+      fail(SQLRS_ERR_UNSUPPORTED, "plan_next_to_device: only fixed-width value columns (Int32 / Int64 / Float64)");
+    if (col.valid && null_count_of(ctx_, col) > 0) fail(SQLRS_ERR_UNSUPPORTED, "plan_next_to_device: column with NULLs");
+    if (!columns[c] && col.n > 0) fail(SQLRS_ERR_INVALID_ARG, "plan_next_to_device: NULL destination");
+    if (col.n > 0)
+      SQ_CUDA(cudaMemcpyAsync(columns[c], col.data, (size_t)col.n * dtype_width(col.dtype), cudaMemcpyDeviceToDevice, ctx_.stream));
+  }
+  DBatch keep = std::move(r.dev);
+  results_.pop_front();
+  ctx_.defer([keep]() {});
+  if (ctx_.own_stream) SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+}
+// ONE imported batch scanned as zero-copy slices of batch_rows rows (pointer arithmetic; validity / Boolean words need a
+// 32-row granularity)
+void Plan::push_table_batched(int slot, const DBatch& whole, int64_t batch_rows) {
+  if (batch_rows <= 0 || (batch_rows & 31)) fail(SQLRS_ERR_INVALID_ARG, "push_table_batched: batch_rows must be a positive multiple of 32");
+  if (whole.n == 0) {
+    tables_[slot].push_back(whole);
+    return;
+  }
+  for (int64_t off = 0; off < whole.n; off += batch_rows) {
+    DBatch b;
+    b.fields = whole.fields;
+    b.n = std::min(batch_rows, whole.n - off);
+    for (const DCol& c : whole.cols) {
+      DCol s = c;
+      s.n = b.n;
+      if (c.dtype == SQLRS_DT_NULL) s.null_count = b.n;
+      else if (c.dtype == SQLRS_DT_BOOL) s.data = (const uint32_t*)c.data + (off >> 5);
+      else s.data = (const uint8_t*)c.data + (size_t)off * dtype_width(c.dtype);
+      if (c.valid) {
+        s.valid = c.valid + (off >> 5);
+        s.null_count = -1;
+      }
+      b.cols.push_back(s);
+    }
+    tables_[slot].push_back(std::move(b));
+  }
+}
 void Plan::merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
   partial_op_->merge_partials_device(src, n_bufs, cap_rows);

@@ -27,6 +27,10 @@ class Plan {
   void finish_partial();
   int partial_row_words() const;
   void export_partials_device(uint64_t* dst, int64_t cap_rows);
+  int64_t export_partials_partitioned(uint64_t* dst, int n_parts, int64_t cap_rows);
+  bool result_shape(int64_t* n_rows, int32_t* n_cols);
+  void next_to_device(void* const* columns, int32_t n_columns);
+  void push_table_batched(int slot, const DBatch& whole, int64_t batch_rows);
   void merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows);
   const char* describe() const { return description_.c_str(); }
   double scan_kernel_ms() const { return scan_kernel_ms_; }

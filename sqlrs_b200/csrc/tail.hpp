@@ -56,6 +56,7 @@ class OrderOp {
   std::unique_ptr<EvalProgram> prog_;
   std::vector<int> slot_;
   int64_t row_limit_ = -1;
+  int flags_ = 0;
   DCol tiebreak_;
   bool has_tiebreak_ = false;
 };

@@ -1,24 +1,27 @@
-"""Multi-GPU execution of a plan whose root is an aggregate.
+"""Multi-GPU execution of plans over row-sharded tables.
 
-One process per GPU (torch.distributed; NCCL over NVLink on the GPU box, gloo in the CPU tests).
-Scan, filter and the partial aggregation stay GPU-local; the only exchange is the group-by's:
+One process per GPU (torch.distributed; NCCL over NVLink on the GPU box, gloo in the CPU tests).  Scan, filter, join
+probe and the partial aggregation stay GPU-local; what crosses NVLink are the exchange steps of the stateful operators,
+and with NCCL + the CUDA library they cross it as DEVICE buffers — no Arrow IPC, no host copy of the data plane:
 
-  1. every rank aggregates its contiguous row shard           sqlrs_plan_execute_partial
-  (few groups, NCCL: the packed partial tables are all-gathered device-to-device and rank 0 folds them —
-   sqlrs_plan_export_partials_device / sqlrs_plan_merge_partials_device; otherwise:)
-  2. partial groups are radix-partitioned by their identity hash (owner = hash mod world) and
-     exchanged all-to-all; the owner folds them               sqlrs_plan_merge_partials
-  3. the (now disjoint) owner-merged groups are gathered on rank 0, which finalises them in the
-     reference's first-appearance order (minimum global row id) sqlrs_plan_finish_partial
+  group-by   sqlrs_plan_execute_partial, then
+             few groups : every rank packs its group table into a fixed-size device buffer, ONE all-gather, rank 0 folds
+                          them (sqlrs_plan_export_partials_device / _merge_partials_device); the header counts are read
+                          back asynchronously and checked at the END of the step, not between collective and merge
+             many groups: a partition kernel packs the partial groups by identity hash mod world into per-owner regions
+                          (sqlrs_plan_export_partials_partitioned), ONE all_to_all_single with equal splits, every owner
+                          folds what it received, the owner-merged (disjoint) groups are all-gathered and finalised on
+                          rank 0 in the reference's first-appearance order
+  join       broadcast-build / partitioned-probe: every rank runs the build side's sub-plan on its shard, the surviving
+             rows are all-gathered device-to-device in rank order (= the single-process row order: shards are contiguous)
+             and every rank builds the whole table (`broadcast_rows`); the probe side stays sharded.
+             When the caller's table statistics (min / max of the join key per shard, computed once at load time like a
+             zone map) show that a build shard covers every key its probe shard can hold and the shards' key ranges are
+             disjoint, the join needs no exchange at all (`key_ranges_copartitioned`): `distributed_join_topk`.
 
-Joins (Q3'): `broadcast_build_join_aggregate` (any sharding of the probe sides, build sides exchanged) and
-`copartitioned_topk` (fact tables range-partitioned on the join key that is also a group key, dimension table
-replicated: every rank runs the WHOLE query on its shards, no data-path collective at all, only the final
-LIMIT rows are gathered).
-
-The reference has no distributed execution; results equal the single-process ones (integers
-bit-exact, float sums up to summation order).  This module contains no compute — partial groups
-cross the C ABI as opaque Arrow batches whose column 0 is the partitioning hash.
+The reference has no distributed execution; results equal the single-process ones (integers bit-exact, float sums up to
+summation order).  With gloo or the CPU checker the same steps run through host batches (`_export_partials` etc.).
+This module contains no compute.
 """
 from __future__ import annotations
 
@@ -183,48 +186,133 @@ def _plan_stream(plan) -> int:
     return int(getattr(plan.options, "stream", None) or 0)
 
 
-def _device_exchange(plan, group: TorchGroup, cap_rows: int):
-    """Fast path for few groups (NCCL): partial groups never leave HBM.  Every rank packs its groups into a
-    fixed-size device buffer, ONE all-gather over NVLink hands all of them to every rank, rank 0 folds them.
-    Returns None when some rank has more than `cap_rows` groups (the caller takes the radix all-to-all path)."""
-    torch, lib = group.torch, plan.lib
-    words = C.c_int32(0)
-    lib.check(lib.plan_partials_row_words(plan.handle, C.byref(words)))
-    key = (words.value, cap_rows)
-    bufs = getattr(group, "_bufs", {})
+def _check_stream(plan, group) -> bool:
+    """stream contract of the *_device calls (include/sqlrs_b200.h): a plan on the caller's stream works in stream order with
+    the collectives; a plan that owns its stream synchronises inside its exports, and the caller synchronises before merges"""
+    torch = group.torch
+    shared = _plan_stream(plan) == torch.cuda.current_stream(group.device).cuda_stream
+    if _plan_stream(plan) and not shared:
+        raise ValueError("distributed execution: options.stream must be torch's current stream (or NULL)")
+    return shared
+
+
+def _buffers(group, key, make):
+    bufs = getattr(group, "_bufs", None)
+    if bufs is None:
+        bufs = group._bufs = {}
     if key not in bufs:
-        n = (cap_rows + 1) * words.value
-        bufs[key] = (torch.empty(n, dtype=torch.int64, device=group.device), torch.empty(n * group.world, dtype=torch.int64, device=group.device))
-        group._bufs = bufs
-    send, recv = bufs[key]
-    # stream contract (include/sqlrs_b200.h): a plan on the caller's stream packs in stream order with the collective;
-    # a plan that owns its stream synchronises inside export, and needs the gathered buffer complete before the merge
-    shared_stream = _plan_stream(plan) == torch.cuda.current_stream(group.device).cuda_stream
-    if _plan_stream(plan) and not shared_stream:
-        raise ValueError("sharded_aggregate: options.stream must be torch's current stream (or NULL)")
+        bufs[key] = make()
+    return bufs[key]
+
+
+def _row_words(plan) -> int:
+    words = C.c_int32(0)
+    plan.lib.check(plan.lib.plan_partials_row_words(plan.handle, C.byref(words)))
+    return int(words.value)
+
+
+def _device_exchange(plan, group: TorchGroup, cap_rows: int):
+    """Few groups (NCCL): partial groups never leave HBM.  Every rank packs its groups into a fixed-size device buffer, ONE
+    all-gather over NVLink hands all of them to every rank, rank 0 folds them and finalises.  Nothing synchronises between
+    the collective and the merge: the per-rank group counts (buffer headers) are copied to pinned memory asynchronously and
+    looked at when the step's work has been enqueued.  Returns None when some rank had more than `cap_rows` groups (every
+    rank sees the same headers, so every rank takes the radix path together)."""
+    torch, lib, W = group.torch, plan.lib, group.world
+    words = _row_words(plan)
+
+    def make():
+        n = (cap_rows + 1) * words
+        return (torch.empty(n, dtype=torch.int64, device=group.device), torch.empty(n * W, dtype=torch.int64, device=group.device),
+                torch.empty(W, dtype=torch.int64, pin_memory=True))
+
+    send, recv, counts_host = _buffers(group, ("few", words, cap_rows), make)
+    shared = _check_stream(plan, group)
     lib.check(lib.plan_export_partials_device(plan.handle, C.c_void_p(send.data_ptr()), cap_rows))
     group.dist.all_gather_into_tensor(recv, send)
-    if not shared_stream:
+    counts_host.copy_(recv.view(W, cap_rows + 1, words)[:, 0, 0], non_blocking=True)
+    if not shared:
         torch.cuda.current_stream(group.device).synchronize()
-    counts = recv.view(group.world, cap_rows + 1, words.value)[:, 0, 0]
-    if int(counts.max().item()) > cap_rows:
+    lib.check(lib.plan_clear_partials(plan.handle))
+    result = []
+    if group.rank == 0:
+        lib.check(lib.plan_merge_partials_device(plan.handle, C.c_void_p(recv.data_ptr()), W, cap_rows))
+        lib.check(lib.plan_finish_partial(plan.handle))
+        result = plan.collect()
+    else:
+        lib.check(lib.plan_finish_partial(plan.handle))
+        plan.collect()
+    torch.cuda.current_stream(group.device).synchronize()  # counts_host is complete (rank 0 synchronised for its result anyway)
+    if int(counts_host.max()) > cap_rows:
         return None
+    return result
+
+
+def _radix_exchange(plan, group: TorchGroup):
+    """Many groups (NCCL): radix-partition the partial groups by identity hash mod world into per-owner regions of a device
+    send buffer, exchange them with ONE all_to_all_single (equal splits: every region carries its own count), fold on the
+    owner, then all-gather the owner-merged groups — disjoint across ranks — and finalise on rank 0."""
+    torch, lib, W = group.torch, plan.lib, group.world
+    words = _row_words(plan)
+    shared = _check_stream(plan, group)
+    groups = C.c_int64(0)
+    lib.check(lib.plan_export_partials_partitioned(plan.handle, None, W, 0, C.byref(groups)))  # learn the local group count
+    t = torch.tensor([groups.value], dtype=torch.int64, device=group.device)
+    group.dist.all_reduce(t, op=group.dist.ReduceOp.MAX)
+    most = int(t.item())
+    for attempt in range(3):
+        # a hash partition holds ~1/W of a rank's groups; head-room for skew, then x4 per retry
+        cap = max(256, int(most / W * 1.25 * (4 ** attempt)) + 1024)
+        cap = min(cap, max(most, 1))
+        region = (cap + 1) * words
+        send = torch.empty(region * W, dtype=torch.int64, device=group.device)
+        recv = torch.empty(region * W, dtype=torch.int64, device=group.device)
+        lib.check(lib.plan_export_partials_partitioned(plan.handle, C.c_void_p(send.data_ptr()), W, cap, C.byref(groups)))
+        group.dist.all_to_all_single(recv, send)
+        worst = recv.view(W, cap + 1, words)[:, 0, 0].max().reshape(1).clone()
+        group.dist.all_reduce(worst, op=group.dist.ReduceOp.MAX)
+        if int(worst.item()) <= cap:
+            break
+    else:
+        raise RuntimeError("radix exchange: a hash partition kept overflowing its region")
+    if not shared:
+        torch.cuda.current_stream(group.device).synchronize()
+    lib.check(lib.plan_clear_partials(plan.handle))
+    lib.check(lib.plan_merge_partials_device(plan.handle, C.c_void_p(recv.data_ptr()), W, cap))
+    # the owner-merged groups of all ranks -> rank 0
+    owned = C.c_int64(0)
+    lib.check(lib.plan_export_partials_partitioned(plan.handle, None, 1, 0, C.byref(owned)))
+    t = torch.tensor([owned.value], dtype=torch.int64, device=group.device)
+    group.dist.all_reduce(t, op=group.dist.ReduceOp.MAX)
+    cap2 = max(int(t.item()), 1)
+    send2 = torch.empty((cap2 + 1) * words, dtype=torch.int64, device=group.device)
+    recv2 = torch.empty((cap2 + 1) * words * W, dtype=torch.int64, device=group.device)
+    lib.check(lib.plan_export_partials_device(plan.handle, C.c_void_p(send2.data_ptr()), cap2))
+    group.dist.all_gather_into_tensor(recv2, send2)
+    if not shared:
+        torch.cuda.current_stream(group.device).synchronize()
     lib.check(lib.plan_clear_partials(plan.handle))
     if group.rank == 0:
-        lib.check(lib.plan_merge_partials_device(plan.handle, C.c_void_p(recv.data_ptr()), group.world, cap_rows))
+        lib.check(lib.plan_merge_partials_device(plan.handle, C.c_void_p(recv2.data_ptr()), W, cap2))
     lib.check(lib.plan_finish_partial(plan.handle))
     result = plan.collect()
     return result if group.rank == 0 else []
 
 
 def sharded_aggregate(plan, group: TorchGroup, row_base: int = 0, device_cap_rows: int = 256) -> List[pa.RecordBatch]:
-    """Runs `plan` (root = aggregate) over the shard pushed on this rank; rank 0 returns the final batches."""
+    """Runs `plan` (root = aggregate) over the shard pushed on this rank; rank 0 returns the final batches.
+    `row_base`: global row number of the shard's first row (first-appearance order across ranks)."""
     lib = plan.lib
     lib.check(lib.plan_execute_partial(plan.handle, row_base))
-    if group.native_a2a and device_cap_rows > 0 and lib.prefix == "sqlrs_":
-        result = _device_exchange(plan, group, device_cap_rows)
-        if result is not None:
-            return result
+    if group.native_a2a and lib.prefix == "sqlrs_":  # NCCL + the CUDA library: the exchange stays in HBM
+        if device_cap_rows > 0:
+            if not getattr(plan, "_many_groups", False):
+                result = _device_exchange(plan, group, device_cap_rows)
+                if result is not None:
+                    return result
+                plan._many_groups = True  # remembered: later runs of this plan go straight to the radix exchange
+                lib.check(lib.plan_execute_partial(plan.handle, row_base))  # the few-groups attempt consumed the partial state
+        return _radix_exchange(plan, group)
+    # host path (gloo / the CPU checker): the same steps through Arrow batches
     local = _export_partials(plan)
     received = group.all_to_all_bytes([_to_bytes(p) for p in partition_by_owner(local, group.world)])
     lib.check(lib.plan_clear_partials(plan.handle))
@@ -241,38 +329,156 @@ def sharded_aggregate(plan, group: TorchGroup, row_base: int = 0, device_cap_row
     return result if group.rank == 0 else []
 
 
+# ---------------------------------------------------------------------------------------------- joins
+class DeviceBatch:
+    """Columns resident in HBM as torch tensors (int64 storage; Float64 columns as their bit patterns), exportable as an
+    ArrowDeviceArray for `GpuPlan.push_table_device` (same interface as tpch.DeviceTable)."""
+
+    def __init__(self, schema: pa.Schema, tensors: list, n_rows: int, device_index: int):
+        self._schema, self.tensors, self.n_rows, self.device_index = schema, tensors, n_rows, device_index
+        self._keep: list = []
+
+    @property
+    def schema(self) -> pa.Schema:
+        return self._schema
+
+    def export(self):
+        from .tpch import DeviceTable
+
+        return DeviceTable.export(self)
+
+
+def broadcast_rows(plan, group: TorchGroup, schema: pa.Schema) -> DeviceBatch:
+    """The rows `plan` (already executed on this rank's shard; ONE pending device result of fixed-width, NULL-free columns)
+    produced on every rank, concatenated in rank order, on every rank — all-gathered device to device.  This is the
+    build-side broadcast of a broadcast-build / partitioned-probe join."""
+    torch, W = group.torch, group.world
+    shape = plan.result_shape()
+    n, ncols = shape if shape is not None else (0, len(schema))
+    counts = torch.empty(W, dtype=torch.int64, device=group.device)
+    group.dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device=group.device))
+    counts = counts.tolist()  # sizes of the receive buffers: the one host round trip of this step
+    most = max(max(counts), 1)
+    send = torch.empty((ncols, most), dtype=torch.int64, device=group.device)
+    if shape is not None:
+        plan.next_to_device([send[c].data_ptr() for c in range(ncols)])
+    _check_stream(plan, group)
+    recv = torch.empty((W, ncols, most), dtype=torch.int64, device=group.device)
+    group.dist.all_gather_into_tensor(recv, send)
+    cols = [torch.cat([recv[r, c, :counts[r]] for r in range(W)]) for c in range(ncols)]
+    dev = group.device.index if group.device.index is not None else 0
+    return DeviceBatch(schema, cols, int(sum(counts)), dev)
+
+
+def key_ranges_copartitioned(group: TorchGroup, build_range, probe_range) -> bool:
+    """`build_range` / `probe_range`: (min, max) of the join key in this rank's shard of the build-side / probe-side table
+    (table statistics, computed once at load time).  True on every rank iff on every rank the probe shard's keys lie inside
+    the build shard's range and the build shards' ranges are pairwise disjoint — then every probe row finds all its matches
+    on its own rank and the join needs no exchange."""
+    torch, W = group.torch, group.world
+    mine = torch.tensor([build_range[0], build_range[1], probe_range[0], probe_range[1]], dtype=torch.int64, device=group.device)
+    every = torch.empty(W * 4, dtype=torch.int64, device=group.device)
+    group.dist.all_gather_into_tensor(every, mine) if group.native_a2a else group.dist.all_gather(list(every.view(W, 4).unbind(0)), mine)
+    r = every.view(W, 4).tolist()
+    inside = all(b_lo <= p_lo and p_hi <= b_hi for b_lo, b_hi, p_lo, p_hi in r if p_lo <= p_hi)
+    spans = sorted((b_lo, b_hi) for b_lo, b_hi, _, _ in r if b_lo <= b_hi)
+    disjoint = all(spans[i][1] < spans[i + 1][0] for i in range(len(spans) - 1))
+    return inside and disjoint
+
+
+def merge_topk(plan, group: TorchGroup, local: List[pa.RecordBatch], order_by, limit: int) -> List[pa.RecordBatch]:
+    """Global ORDER BY ... LIMIT over per-rank results whose groups are disjoint across ranks: the <= limit local rows of
+    every rank are gathered on rank 0 (a few hundred bytes per rank) and ordered again with the library's own Order / Limit
+    operators.  Ties between ranks resolve in rank order = global row order, as in the single-process run."""
+    from . import executor as ex
+
+    schema = local[0].schema if local else None
+    table = pa.Table.from_batches(local).combine_chunks() if local else None
+    payload = _to_bytes(table.to_batches()[0]) if table is not None and table.num_rows else b""
+    gathered = group.gather_small(payload, dst=0)
+    if gathered is None:
+        return []
+    batches = [_from_bytes(data) for data in gathered if data]
+    if not batches:
+        return [pa.RecordBatch.from_pylist([], schema=schema)] if schema is not None else []
+    ordered = ex.OrderExecutor(order_by, batches, lib=plan.lib, options=plan.options).execute()
+    return ex.try_collect(ex.LimitExecutor(limit, None, ordered, lib=plan.lib, options=plan.options).execute())
+
+
+def _push(plan, tables):
+    for slot, t in tables.items():
+        if isinstance(t, pa.RecordBatch):
+            plan.push_table(slot, t)
+        else:
+            plan.push_table_device(slot, t)
+
+
 def broadcast_build_join_aggregate(builder, group: TorchGroup, stage1, stage1_schemas, stage1_tables, stage2, stage2_schemas, stage2_tables,
-                                   build_slot: int) -> List[pa.RecordBatch]:
+                                   build_slot: int, row_base: Optional[int] = None) -> List[pa.RecordBatch]:
     """Broadcast-build / partitioned-probe execution of a left-deep join tree under an aggregate (SURVEY.md §8e, Q3').
 
-    stage1: a plan whose root is a join probed by this rank's shard (its build side is small and present in full on
-    every rank); the join output of all ranks — all-gathered in rank order, which is the single-process output
-    order because shards are contiguous — becomes table `build_slot` of stage2 on every rank.
+    stage1: a plan whose root is a join probed by this rank's shard (its build side is present in full on every rank);
+    the join output of all ranks — all-gathered in rank order, which is the single-process output order because shards
+    are contiguous — becomes table `build_slot` of stage2 on every rank.  With NCCL and the CUDA library the rows move
+    device to device (`broadcast_rows`); otherwise as Arrow batches through the host.
     stage2: root = aggregate over a join whose build side is that table and whose probe side is this rank's shard;
     it runs through `sharded_aggregate` (partial aggregation + exchange of the groups).
-    `stage*_tables`: {slot: RecordBatch | tpch.DeviceTable}."""
-    def push(plan, tables):
-        for slot, t in tables.items():
-            if isinstance(t, pa.RecordBatch):
-                plan.push_table(slot, t)
-            else:
-                plan.push_table_device(slot, t)
-
+    `stage*_tables`: {slot: RecordBatch | DeviceBatch | tpch.DeviceTable}.  `row_base`: global row number of the first row
+    of this rank's stage-2 probe shard (default: rank << 40, enough to order ranks; < 16 ranks)."""
+    device_path = group.native_a2a and builder.lib.prefix == "sqlrs_"
     p1 = builder.build(stage1, stage1_schemas)
-    push(p1, stage1_tables)
-    local = p1.run()
-    p1.close()
-    build_side = all_gather_batches(group, local, stage1.output_schema(stage1_schemas))
+    _push(p1, stage1_tables)
     p2 = builder.build(stage2, stage2_schemas)
-    for b in build_side:
-        p2.push_table(build_slot, b)
-    if not build_side:
-        p2.push_table(build_slot, pa.RecordBatch.from_pylist([], schema=stage2_schemas[build_slot]))
-    push(p2, stage2_tables)
-    # rank-major first-appearance order: join output rows of rank r come after those of rank r-1
-    result = sharded_aggregate(p2, group, row_base=group.rank << 40)
+    if device_path:
+        p1.execute()
+        build_side = broadcast_rows(p1, group, stage1.output_schema(stage1_schemas))
+        p1.close()
+        p2.push_table_device(build_slot, build_side)
+    else:
+        local = p1.run()
+        p1.close()
+        build_side = all_gather_batches(group, local, stage1.output_schema(stage1_schemas))
+        for b in build_side:
+            p2.push_table(build_slot, b)
+        if not build_side:
+            p2.push_table(build_slot, pa.RecordBatch.from_pylist([], schema=stage2_schemas[build_slot]))
+    _push(p2, stage2_tables)
+    if row_base is None:
+        if group.world > 16:
+            raise ValueError("broadcast_build_join_aggregate: pass row_base for more than 16 ranks (ordinals are 44 bits)")
+        row_base = group.rank << 40  # rank-major first-appearance order: rows of rank r come after those of rank r-1
+    result = sharded_aggregate(p2, group, row_base=row_base)
     p2.close()
     return result
+
+
+def distributed_join_topk(builder, group: TorchGroup, *, build_plan, build_schemas, build_tables, query_plan, query_schemas, query_tables,
+                          build_slot: int, order_by, limit: int, state: Optional[dict] = None) -> List[pa.RecordBatch]:
+    """ORDER BY ... LIMIT query over a join tree whose fact tables are sharded so that the joins between them need no
+    exchange (the caller established that with `key_ranges_copartitioned`) and whose first build side is small:
+
+      1. `build_plan` (e.g. Filter(Scan) over this rank's shard of the dimension table) runs locally; its surviving rows are
+         all-gathered device to device, so every rank holds the whole filtered build side — never the whole table;
+      2. `query_plan` — the complete query, tail included — runs locally with that table in `build_slot`; the partition key
+         is a group key, so groups of different ranks are disjoint and the global top rows are among the per-rank top rows;
+      3. the <= `limit` rows per rank are gathered on rank 0 and ordered again (`merge_topk`).
+
+    `state`: a dict kept by the caller across calls; the built plans live there so that repeated runs reuse compiled kernels,
+    device buffers and sizing hints."""
+    state = state if state is not None else {}
+    if "p_build" not in state:
+        state["p_build"] = builder.build(build_plan, build_schemas)
+        state["p_query"] = builder.build(query_plan, query_schemas)
+    p_build, p_query = state["p_build"], state["p_query"]
+    p_build.reset()
+    p_query.reset()
+    _push(p_build, build_tables)
+    p_build.execute()
+    build_side = broadcast_rows(p_build, group, build_plan.output_schema(build_schemas))
+    p_query.push_table_device(build_slot, build_side)
+    _push(p_query, query_tables)
+    local = p_query.run()
+    return merge_topk(p_query, group, local, order_by, limit)
 
 
 def copartitioned_shard(n_orders: int, rank: int, world: int):
@@ -288,6 +494,13 @@ def copartitioned_shard(n_orders: int, rank: int, world: int):
 
 
 def copartitioned_topk(plan, group: "TorchGroup", order_by, limit: int, offset: Optional[int] = None) -> List[pa.RecordBatch]:
+    if offset:
+        # every rank's plan carries the query's own Limit: with an OFFSET each rank would drop ITS first rows, not the global ones
+        raise ValueError("copartitioned_topk: build the per-rank plan with Limit(limit + offset) and apply the OFFSET to the merged rows")
+    return _copartitioned_topk(plan, group, order_by, limit)
+
+
+def _copartitioned_topk(plan, group: "TorchGroup", order_by, limit: int, offset: Optional[int] = None) -> List[pa.RecordBatch]:
     """Multi-GPU execution of  Limit(Project(Order(Aggregate(joins...))))  over tables that are co-partitioned on a
     join key which is also a group-by key ("scan stays GPU-local").
 

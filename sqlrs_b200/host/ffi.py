@@ -27,6 +27,7 @@ COUNT_REFERENCE_OVERWRITE, COUNT_SQL_ACCUMULATE = 0, 1
 MATCH_HASH_ONLY, MATCH_HASH_AND_KEY = 0, 1
 FLAG_NO_FUSION = 1
 FLAG_TIMING = 4
+FLAG_KERNEL_EVENTS = 8
 NODE_SCAN, NODE_FILTER, NODE_SIMPLE_AGG, NODE_HASH_AGG, NODE_HASH_JOIN, NODE_PROJECT, NODE_ORDER, NODE_LIMIT, NODE_CROSS_JOIN = 1, 2, 3, 4, 5, 6, 7, 8, 9
 ABI_VERSION = 2
 TPCH_CUSTOMER, TPCH_ORDERS, TPCH_LINEITEM = 0, 1, 2
@@ -240,6 +241,11 @@ _SIGNATURES = {
     "plan_export_partials_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "plan_merge_partials_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64]),
     "plan_scan_kernel_ms": (C.c_double, [C.c_void_p, P(C.c_int64)]),
+    "plan_push_table_batched": (C.c_int, [C.c_void_p, C.c_int32, P(ArrowArray), P(ArrowSchema), C.c_int64]),
+    "plan_result_shape": (C.c_int, [C.c_void_p, P(C.c_int64), P(C.c_int32), P(C.c_int32)]),
+    "plan_next_to_device": (C.c_int, [C.c_void_p, P(C.c_void_p), C.c_int32]),
+    "plan_export_partials_partitioned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, P(C.c_int64)]),
+    "kernel_events_collect": (C.c_int, [P(C.c_void_p)]),
     "tpch_num_columns": (C.c_int32, [C.c_int32]),
     "tpch_num_rows": (C.c_int64, [P(TpchDims), C.c_int32]),
     "tpch_generate": (C.c_int, [P(TpchDims), C.c_int32, C.c_int64, C.c_int64, P(C.c_void_p), C.c_void_p]),

@@ -228,6 +228,37 @@ class GpuPlan:
         finally:
             ffi.release_schema(sch)
 
+    def push_table_batched(self, table_slot: int, batch: pa.RecordBatch, batch_rows: int = 1024):
+        """ONE host batch that the plan scans in `batch_rows`-row slices (the reference's scan batch size, csv.rs:105):
+        the slicing happens inside the library, not in a Python loop."""
+        arr, sch = ffi.export_batch(batch)
+        try:
+            self.lib.check(self.lib.plan_push_table_batched(self.handle, table_slot, C.byref(arr), C.byref(sch), batch_rows))
+        finally:
+            ffi.release_schema(sch)
+
+    def result_shape(self):
+        """(rows, columns) of the next pending DEVICE result, or None."""
+        n, c, has = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        self.lib.check(self.lib.plan_result_shape(self.handle, C.byref(n), C.byref(c), C.byref(has)))
+        return (int(n.value), int(c.value)) if has.value else None
+
+    def next_to_device(self, column_ptrs: Sequence[int]):
+        """copies the next pending result's columns into device buffers (raw pointers), device to device"""
+        arr = (C.c_void_p * max(1, len(column_ptrs)))(*column_ptrs)
+        self.lib.check(self.lib.plan_next_to_device(self.handle, arr, len(column_ptrs)))
+
+    def kernel_events(self) -> dict:
+        """{kernel: {ms, launches}} recorded since the last call (plans built with FLAG_KERNEL_EVENTS)"""
+        import json
+
+        out = C.c_void_p()
+        self.lib.check(self.lib.kernel_events_collect(C.byref(out)))
+        try:
+            return json.loads(C.string_at(out).decode()) if out.value else {}
+        finally:
+            self.lib.free(out)
+
     def push_table_device(self, table_slot: int, device_batch):
         """`device_batch`: tpch.DeviceTable (columns resident in HBM); zero copy."""
         darr, sch = device_batch.export()
