@@ -229,131 +229,92 @@ void launch_finalize_groups(const uint64_t* packed, int words, int64_t n, int n_
 
 // ------------------------------------------------------------------ top-k (ORDER BY ... LIMIT k)
 namespace {
-constexpr int kTopKWords = 2 * kTopKMaxKeys + 1;
+// Composite key of a row under M sort columns: w[0] = tie-break word (compared LAST), w[1 + 2j] / w[2 + 2j] = (valid flag,
+// order-preserving image) of column j.  The kernels are instantiated per M so the keys are exactly 2M + 1 registers wide.
+template <int M>
 struct TopKKey {
-  uint64_t w[kTopKWords];
+  uint64_t w[2 * M + 1];
 };
-// w[0] = tie-break word (compared LAST), w[1 + 2j] / w[2 + 2j] = (valid flag, image) of sort column j; nw = 1 + 2m words are
-// in use — the others are never touched, and all indices are static so the key lives in registers
-__device__ __forceinline__ bool topk_less(const TopKKey& a, const TopKKey& b, int nw) {
+template <int M>
+__device__ __forceinline__ bool topk_less(const TopKKey<M>& a, const TopKKey<M>& b) {
   bool less = false, decided = false;
 #pragma unroll
-  for (int j = 1; j < kTopKWords; j++) {
-    if (j < nw) {
-      const bool ne = a.w[j] != b.w[j];
-      if (!decided && ne) less = a.w[j] < b.w[j];
-      decided = decided || ne;
-    }
+  for (int j = 1; j < 2 * M + 1; j++) {
+    const bool ne = a.w[j] != b.w[j];
+    if (!decided && ne) less = a.w[j] < b.w[j];
+    decided = decided || ne;
   }
   if (!decided) less = a.w[0] < b.w[0];
   return less;
 }
-__device__ __forceinline__ void topk_load(const TopKKeys& keys, uint64_t row, TopKKey& out) {
+template <int M>
+__device__ __forceinline__ void topk_load(const TopKKeys& keys, uint64_t row, TopKKey<M>& out) {
 #pragma unroll
-  for (int j = 0; j < kTopKMaxKeys; j++) {
-    uint64_t flag = 0, img = 0;
-    if (j < keys.m) {
-      const bool is_null = keys.valid[j] && !bit_at(keys.valid[j], row);
-      flag = is_null ? 0ULL : 1ULL;  // NULLs first, whatever the direction
-      if (!is_null) {
-        img = sort_image(keys.dtype[j], keys.data[j], row);
-        if (keys.descending[j]) img = ~img;
-      }
+  for (int j = 0; j < M; j++) {
+    const bool is_null = keys.valid[j] && !bit_at(keys.valid[j], row);
+    uint64_t img = 0;
+    if (!is_null) {
+      img = sort_image(keys.dtype[j], keys.data[j], row);
+      if (keys.descending[j]) img = ~img;
     }
-    out.w[1 + 2 * j] = flag;
+    out.w[1 + 2 * j] = is_null ? 0ULL : 1ULL;  // NULLs first, whatever the direction
     out.w[2 + 2 * j] = img;
   }
   out.w[0] = keys.tiebreak ? keys.tiebreak[row] : row;
 }
-__device__ __forceinline__ void topk_shfl(const TopKKey& in, TopKKey& o, int d, int nw) {
-#pragma unroll
-  for (int j = 0; j < kTopKWords; j++)
-    if (j < nw) o.w[j] = __shfl_xor_sync(0xffffffffu, in.w[j], d);
-}
-// block-wide argmin of (key, row) over the threads that have one; every thread receives the winner
-template <int THREADS>
-__device__ __forceinline__ bool topk_block_min(TopKKey& key, uint32_t& row, bool has, int nw, TopKKey* s_key, uint32_t* s_row, int* s_has) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    TopKKey o;
-    topk_shfl(key, o, d, nw);
-    const uint32_t orow = __shfl_xor_sync(0xffffffffu, row, d);
-    const bool ohas = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, d) != 0;
-    if (ohas && (!has || topk_less(o, key, nw))) {
-      key = o;
-      row = orow;
-      has = true;
-    }
-  }
-  if (lane == 0) {
-    s_key[wid] = key;
-    s_row[wid] = row;
-    s_has[wid] = has ? 1 : 0;
-  }
-  __syncthreads();
-  // every warp reduces the per-warp winners again (THREADS / 32 <= 32 entries)
-  const int src = lane < THREADS / 32 ? lane : 0;
-  TopKKey k2 = s_key[src];
-  uint32_t r2 = s_row[src];
-  bool h2 = lane < THREADS / 32 && s_has[src] != 0;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    TopKKey o;  // (all five steps: every lane ends up with the winner)
-    topk_shfl(k2, o, d, nw);
-    const uint32_t orow = __shfl_xor_sync(0xffffffffu, r2, d);
-    const bool ohas = __shfl_xor_sync(0xffffffffu, h2 ? 1 : 0, d) != 0;
-    if (ohas && (!h2 || topk_less(o, k2, nw))) {
-      k2 = o;
-      r2 = orow;
-      h2 = true;
-    }
-  }
-  __syncthreads();
-  key = k2;
-  row = r2;
-  return h2;
-}
 
-// One reduction pass: CTA b takes kTopKPer entries per thread (rows_in[b * kTopKCta ...], or the row numbers themselves when
-// rows_in == nullptr), loads their keys into registers ONCE, and emits its k smallest in order: k rounds of block-wide
-// argmin over registers, no memory traffic in the rounds.  Passes repeat until one CTA is left (launch_topk).
-constexpr int kTopKPer = 4, kTopKCta = kBlock * kTopKPer;
+// One reduction pass, one WARP per slice of kTopKWarpRows entries (rows_in[...], or the row numbers themselves when rows_in ==
+// nullptr): every lane loads the keys of its kTopKPer entries into registers ONCE, then the warp emits its k smallest in
+// order — k rounds of a shuffle argmin over registers; no shared memory, no barrier, no memory traffic in the rounds.
+// Passes repeat until one warp is left (launch_topk): every pass shrinks the candidates kTopKWarpRows / k-fold.
+constexpr int kTopKPer = 8, kTopKWarpRows = 32 * kTopKPer;
+template <int M>
 __global__ void __launch_bounds__(kBlock) k_topk_pass(const __grid_constant__ TopKKeys keys, const uint32_t* __restrict__ rows_in, int64_t n_in, int k,
                                                       uint32_t* __restrict__ out) {
-  __shared__ TopKKey s_key[kBlock / 32];
-  __shared__ uint32_t s_row[kBlock / 32];
-  __shared__ int s_has[kBlock / 32];
-  const int nw = 1 + 2 * keys.m;
-  TopKKey ck[kTopKPer];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  const int64_t base = warp * kTopKWarpRows;
+  if (base >= n_in) return;
+  TopKKey<M> ck[kTopKPer];
   uint32_t crow[kTopKPer];
   bool live[kTopKPer];
 #pragma unroll
   for (int c = 0; c < kTopKPer; c++) {
-    const int64_t i = (int64_t)blockIdx.x * kTopKCta + c * kBlock + threadIdx.x;
+    const int64_t i = base + c * 32 + lane;
     crow[c] = i < n_in ? (rows_in ? rows_in[i] : (uint32_t)i) : 0xffffffffu;
     live[c] = crow[c] != 0xffffffffu;
   }
 #pragma unroll
-  for (int c = 0; c < kTopKPer; c++) topk_load(keys, live[c] ? crow[c] : 0, ck[c]);
+  for (int c = 0; c < kTopKPer; c++) topk_load<M>(keys, live[c] ? crow[c] : 0, ck[c]);
+  uint32_t* dst = out + warp * k;
   for (int round = 0; round < k; round++) {
-    TopKKey best;
-    uint32_t best_row = 0;
-    bool has = false;
+    TopKKey<M> best = ck[0];
+    uint32_t best_row = crow[0];
+    bool has = live[0];
 #pragma unroll
-    for (int j = 0; j < kTopKWords; j++) best.w[j] = 0;
-#pragma unroll
-    for (int c = 0; c < kTopKPer; c++)
-      if (live[c] && (!has || topk_less(ck[c], best, nw))) {
+    for (int c = 1; c < kTopKPer; c++)
+      if (live[c] && (!has || topk_less<M>(ck[c], best))) {
         best = ck[c];
         best_row = crow[c];
         has = true;
       }
-    const bool any = topk_block_min<kBlock>(best, best_row, has, nw, s_key, s_row, s_has);
-    if (threadIdx.x == 0) out[(size_t)blockIdx.x * k + round] = any ? best_row : 0xffffffffu;
-    if (!any) {
-      if (threadIdx.x == 0)
-        for (int j = round + 1; j < k; j++) out[(size_t)blockIdx.x * k + j] = 0xffffffffu;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      TopKKey<M> o;
+#pragma unroll
+      for (int j = 0; j < 2 * M + 1; j++) o.w[j] = __shfl_xor_sync(0xffffffffu, best.w[j], d);
+      const uint32_t orow = __shfl_xor_sync(0xffffffffu, best_row, d);
+      const bool ohas = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, d) != 0;
+      if (ohas && (!has || topk_less<M>(o, best))) {
+        best = o;
+        best_row = orow;
+        has = true;
+      }
+    }
+    if (lane == 0) dst[round] = has ? best_row : 0xffffffffu;
+    if (!has) {
+      if (lane == 0)
+        for (int j = round + 1; j < k; j++) dst[j] = 0xffffffffu;
       break;
     }
 #pragma unroll
@@ -366,24 +327,29 @@ __global__ void __launch_bounds__(kBlock) k_topk_pass(const __grid_constant__ To
 void launch_topk(const TopKKeys& keys, int64_t n, int k, uint32_t* perm_out, cudaStream_t stream) {
   if (n <= 0 || k <= 0) return;
   if (keys.m < 1 || keys.m > kTopKMaxKeys || k > kTopKMaxRows || n >= (1LL << 32) - 2) fail(SQLRS_ERR_INTERNAL, "launch_topk: unsupported shape");
-  // every pass turns kTopKCta entries into k candidates
   const uint32_t* in = nullptr;
   int64_t n_in = n;
   uint32_t* bufs[2] = {nullptr, nullptr};
   int which = 0;
   for (;;) {
-    const int64_t ctas = div_up(n_in, kTopKCta);
+    const int64_t warps = div_up(n_in, kTopKWarpRows);
     uint32_t* dst = perm_out;
-    if (ctas > 1) {
-      if (!bufs[which]) bufs[which] = (uint32_t*)scratch_alloc((size_t)ctas * k * 4, stream);  // (later passes need less)
+    if (warps > 1) {
+      if (!bufs[which]) bufs[which] = (uint32_t*)scratch_alloc((size_t)warps * k * 4, stream);  // (later passes need less)
       dst = bufs[which];
     }
-    k_topk_pass<<<(unsigned)ctas, kBlock, 0, stream>>>(keys, in, n_in, k, dst);
+    const unsigned grid = (unsigned)div_up(warps, kBlock / 32);
+    switch (keys.m) {
+      case 1: k_topk_pass<1><<<grid, kBlock, 0, stream>>>(keys, in, n_in, k, dst); break;
+      case 2: k_topk_pass<2><<<grid, kBlock, 0, stream>>>(keys, in, n_in, k, dst); break;
+      case 3: k_topk_pass<3><<<grid, kBlock, 0, stream>>>(keys, in, n_in, k, dst); break;
+      default: k_topk_pass<4><<<grid, kBlock, 0, stream>>>(keys, in, n_in, k, dst); break;
+    }
     count_launch();
     SQ_CUDA(cudaGetLastError());
-    if (ctas == 1) break;
+    if (warps == 1) break;
     in = dst;
-    n_in = ctas * k;
+    n_in = warps * k;
     which ^= 1;
   }
   for (uint32_t* b : bufs)
