@@ -146,11 +146,22 @@ class ClockSampler:
 MODE = None  # filled in main(): dict(count_mode=SQL_ACCUMULATE, match_mode=HASH_AND_KEY)
 
 
-def pin_core():
-    try:
-        os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[0]})
-    except Exception:
-        pass
+class pin_core:
+    """the CPU port runs on ONE core (the reference's executor is single-threaded per query); the affinity is restored afterwards"""
+
+    def __enter__(self):
+        try:
+            self.prev = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, {sorted(self.prev)[0]})
+        except Exception:
+            self.prev = None
+
+    def __exit__(self, *exc):
+        if self.prev:
+            try:
+                os.sched_setaffinity(0, self.prev)
+            except Exception:
+                pass
 
 
 # ------------------------------------------------------------------------------------------------ CPU port (oracle)
@@ -166,16 +177,16 @@ def cpu_port_q1(oracle, sf, sample_rows, batch_rows, repeats=1):
     n = min(sample_rows, tpch.num_rows(oracle, d, tpch.LINEITEM))
     table = tpch.host_table(oracle, d, tpch.LINEITEM, 0, n, columns=tpch.Q1_COLUMNS)
     plan_root, schemas = tpch.q1_plan()
-    pin_core()
     best, res = None, None
-    for _ in range(repeats):
-        p = ExecutorBuilder(oracle, oracle.options(**MODE)).build(plan_root, schemas)
-        p.push_table_batched(0, table, batch_rows)
-        t0 = time.perf_counter()
-        res = pa.Table.from_batches(p.run())
-        dt = time.perf_counter() - t0
-        p.close()
-        best = dt if best is None else min(best, dt)
+    with pin_core():
+        for _ in range(repeats):
+            p = ExecutorBuilder(oracle, oracle.options(**MODE)).build(plan_root, schemas)
+            p.push_table_batched(0, table, batch_rows)
+            t0 = time.perf_counter()
+            res = pa.Table.from_batches(p.run())
+            dt = time.perf_counter() - t0
+            p.close()
+            best = dt if best is None else min(best, dt)
     return {"rows_per_s": n / best, "seconds": best, "rows": n, "batch_rows": batch_rows}, res
 
 
@@ -189,14 +200,14 @@ def cpu_port_q3(oracle, sf, batch_rows=1024):
     host = {0: tpch.host_table(oracle, d, tpch.CUSTOMER, columns=tpch.Q3_CUSTOMER_COLUMNS), 1: tpch.host_table(oracle, d, tpch.ORDERS, columns=tpch.Q3_ORDERS_COLUMNS),
             2: tpch.host_table(oracle, d, tpch.LINEITEM, columns=tpch.Q3_LINEITEM_COLUMNS)}
     plan_root, schemas = tpch.q3_full_plan()
-    pin_core()
-    p = ExecutorBuilder(oracle, oracle.options(**MODE)).build(plan_root, schemas)
-    for slot, t in host.items():
-        p.push_table_batched(slot, t, batch_rows)
-    t0 = time.perf_counter()
-    res = pa.Table.from_batches(p.run())
-    dt = time.perf_counter() - t0
-    p.close()
+    with pin_core():
+        p = ExecutorBuilder(oracle, oracle.options(**MODE)).build(plan_root, schemas)
+        for slot, t in host.items():
+            p.push_table_batched(slot, t, batch_rows)
+        t0 = time.perf_counter()
+        res = pa.Table.from_batches(p.run())
+        dt = time.perf_counter() - t0
+        p.close()
     n = sum(t.num_rows for t in host.values())
     return {"rows_per_s": n / dt, "seconds": dt, "rows": n, "batch_rows": batch_rows, "sf": sf}, res
 
@@ -378,42 +389,45 @@ def run_gpu_q1(args, ctx):
         parity["ok"] = parity["count_sum"] == count_expected and parity["sum_qty_i64"] == qty_expected and parity["groups"] == 8
     del keep
 
-    # ---- e2e: the same call with HOST (pinned) Arrow buffers; H2D inside the timed region
-    e2e = None
-    if args.e2e_steps > 0:
-        host_batch, keep_alive = pinned_batch(ctx, table)
-        plan.reset()
-
-        def e2e_step():
-            plan.push_table(0, host_batch)
-            if world > 1:
-                res = sqdist.sharded_aggregate(plan, ctx.group, lo)
-            else:
-                plan.execute()
-                res = plan.collect()
+    # ---- e2e: the same call with HOST (pinned) Arrow buffers; H2D inside the timed region.  Runs AFTER every resident timing of
+    # the process (main): pinning / unpinning tens of GB of host memory must not overlap another query's timed region.
+    def run_e2e():
+        e2e = None
+        if args.e2e_steps > 0:
+            host_batch, keep_alive = pinned_batch(ctx, table)
             plan.reset()
-            return res
 
-        e2e_step()
-        barrier(ctx)
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_result = e2e_step()
-        barrier(ctx)
-        e2e_s = max_over_ranks(ctx, time.perf_counter() - t0)
-        out_bytes = sum(b.nbytes for b in e2e_result) if e2e_result else 0
-        e2e_ok = None
-        if rank == 0:
-            e2e_ok = tables_equal(pa.Table.from_batches(e2e_result), pa.Table.from_batches(result))
-        e2e = {"value": n_total * args.e2e_steps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": n_local * bytes_per_row, "d2h_bytes_per_step": int(out_bytes),
-               "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "result_equals_resident_run": e2e_ok,
-               "note": "pinned host Arrow buffers -> sqlrs_plan_push_table (H2D) -> execute -> result to host, per rank shard"}
-        del host_batch, keep_alive
-    plan.close()
-    del table
-    torch.cuda.empty_cache()
+            def e2e_step():
+                plan.push_table(0, host_batch)
+                if world > 1:
+                    res = sqdist.sharded_aggregate(plan, ctx.group, lo)
+                else:
+                    plan.execute()
+                    res = plan.collect()
+                plan.reset()
+                return res
+
+            e2e_step()
+            barrier(ctx)
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e_result = e2e_step()
+            barrier(ctx)
+            e2e_s = max_over_ranks(ctx, time.perf_counter() - t0)
+            out_bytes = sum(b.nbytes for b in e2e_result) if e2e_result else 0
+            e2e_ok = None
+            if rank == 0:
+                e2e_ok = tables_equal(pa.Table.from_batches(e2e_result), pa.Table.from_batches(result))
+            e2e = {"value": n_total * args.e2e_steps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": n_local * bytes_per_row, "d2h_bytes_per_step": int(out_bytes),
+                   "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "result_equals_resident_run": e2e_ok,
+                   "note": "pinned host Arrow buffers -> sqlrs_plan_push_table (H2D) -> execute -> result to host, per rank shard"}
+            del host_batch, keep_alive
+        plan.close()
+        torch.cuda.empty_cache()
+        return e2e
+
     if rank != 0:
-        return None
+        return None, None, run_e2e
     peak, peak_src = measured_peak()
     k_ms = kernel_ms[0] / max(kernel_launches[0], 1)
     achieved = (n_local * bytes_per_row) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
@@ -429,9 +443,9 @@ def run_gpu_q1(args, ctx):
                      "algorithmic_bytes_per_launch": n_local * bytes_per_row,
                      "traffic": ncu_traffic(f"tpch_q1_sf{args.sf:g}", "sq_agg_small") if world == 1 else None,
                      "traffic_source": "profiles/r02_traffic.json (ncu --set full of this kernel source; null when the sources changed since, or N > 1)"},
-        "e2e": e2e, "gpu_launches": int(launches), "parity_check": parity,
+        "e2e": None, "gpu_launches": int(launches), "parity_check": parity,
     }
-    return line, window
+    return line, window, run_e2e
 
 
 def q3_device_tables(ctx, d, shards=None):
@@ -576,8 +590,10 @@ def run_gpu_q3(args, ctx, sf, cpu=None):
                                     "d2h_bytes_per_step": int(sum(b.nbytes for b in agg_res))}
         agg_plan.close()
         parity = {"top10_equals_top10_of_the_aggregate_output": bool(top_ok), "result_rows": top.num_rows}
-        # ---- e2e: host (pinned) Arrow buffers -> push_table (H2D) -> whole query -> 10 rows to the host
-        if args.e2e_steps > 0:
+        # ---- e2e: host (pinned) Arrow buffers -> push_table (H2D) -> whole query -> 10 rows to the host (deferred: see main)
+        def run_e2e():
+            if args.e2e_steps <= 0:
+                return
             host = {}
             keep_alive = []
             for k, t in tabs.items():
@@ -604,8 +620,10 @@ def run_gpu_q3(args, ctx, sf, cpu=None):
                           "d2h_bytes_per_step": int(sum(b.nbytes for b in e_res)), "steps": args.e2e_steps,
                           "result_equals_resident_run": tables_equal(pa.Table.from_batches(e_res), top),
                           "note": "pinned host Arrow buffers -> sqlrs_plan_push_table x3 (H2D) -> execute -> 10 rows to host"}
+            out["parity_check"]["ok"] = bool(out["parity_check"]["ok"] and out["e2e"]["result_equals_resident_run"])
             e_plan.close()
             del host, keep_alive
+
         # ---- CPU port beside it, and the oracle as checker: the same plan at the CPU sample's scale factor on both
         if cpu is not None:
             cpu_stats, cpu_res = cpu
@@ -621,7 +639,7 @@ def run_gpu_q3(args, ctx, sf, cpu=None):
             out["cpu_baseline"] = {"value": cpu_stats["rows_per_s"], "unit": "rows/s", "cores": 1, "kind": "port",
                                    "sample": f"Q3' whole query at SF{cpu_stats['sf']:g} ({cpu_stats['rows']} input rows), one pass, 1024-row batches sliced inside the library, "
                                              "C++ restatement of the sqlrs v1 executor"}
-        parity["ok"] = bool(top_ok) and parity.get("equals_oracle_on_sample", True) and out.get("e2e", {}).get("result_equals_resident_run", True)
+        parity["ok"] = bool(top_ok) and parity.get("equals_oracle_on_sample", True)
         out["parity_check"] = parity
     else:
         out["pipeline"] = state["p_query"].describe()
@@ -638,38 +656,40 @@ def run_gpu_q3(args, ctx, sf, cpu=None):
             parity = {"equals_single_gpu_result": tables_equal(top, single), "result_rows": top.num_rows}
             parity["ok"] = parity["equals_single_gpu_result"]
         out["parity_check"] = parity
-        # ---- e2e: every rank's shards in pinned host memory
-        if args.e2e_steps > 0:
-            host, keep_alive = {}, []
-            for k, t in tabs.items():
-                host[k], ka = pinned_batch(ctx, t)
-                keep_alive.append(ka)
-            e_state = {}
+        # ---- e2e: every rank's shards in pinned host memory (deferred: see main)
+        def run_e2e():
+            if args.e2e_steps > 0:
+                host, keep_alive = {}, []
+                for k, t in tabs.items():
+                    host[k], ka = pinned_batch(ctx, t)
+                    keep_alive.append(ka)
+                e_state = {}
 
-            def e2e_step():
-                return sqdist.distributed_join_topk(builder, ctx.group, build_plan=cust_plan, build_schemas={0: schemas[0]}, build_tables={0: host[0]},
-                                                    query_plan=full_root, query_schemas=schemas, query_tables={1: host[1], 2: host[2]}, build_slot=0,
-                                                    order_by=tpch.q3_tail_order_by(), limit=10, state=e_state)
+                def e2e_step():
+                    return sqdist.distributed_join_topk(builder, ctx.group, build_plan=cust_plan, build_schemas={0: schemas[0]}, build_tables={0: host[0]},
+                                                        query_plan=full_root, query_schemas=schemas, query_tables={1: host[1], 2: host[2]}, build_slot=0,
+                                                        order_by=tpch.q3_tail_order_by(), limit=10, state=e_state)
 
-            e2e_step()
-            barrier(ctx)
-            t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                e_res = e2e_step()
-            barrier(ctx)
-            e_s = max_over_ranks(ctx, time.perf_counter() - t0)
-            out["e2e"] = {"value": n_in * args.e2e_steps / e_s, "unit": "rows/s", "ms_per_step": 1e3 * e_s / args.e2e_steps,
-                          "h2d_bytes_per_step": int(sum(t.nbytes() for t in tabs.values())), "d2h_bytes_per_step": int(sum(b.nbytes for b in e_res)) if e_res else 0,
-                          "steps": args.e2e_steps, "result_equals_resident_run": tables_equal(pa.Table.from_batches(e_res), top) if rank == 0 else None,
-                          "note": "per rank: pinned host shards -> push_table (H2D) -> filtered customer rows all-gathered -> whole query -> top-10 merged"}
-            for p in e_state.values():
-                p.close()
-            del host, keep_alive
-        for p in state.values():
-            p.close()
-    del tabs
-    torch.cuda.empty_cache()
-    return (out, window) if rank == 0 else (None, window)
+                e2e_step()
+                barrier(ctx)
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    e_res = e2e_step()
+                barrier(ctx)
+                e_s = max_over_ranks(ctx, time.perf_counter() - t0)
+                out["e2e"] = {"value": n_in * args.e2e_steps / e_s, "unit": "rows/s", "ms_per_step": 1e3 * e_s / args.e2e_steps,
+                              "h2d_bytes_per_step": int(sum(t.nbytes() for t in tabs.values())), "d2h_bytes_per_step": int(sum(b.nbytes for b in e_res)) if e_res else 0,
+                              "steps": args.e2e_steps, "result_equals_resident_run": tables_equal(pa.Table.from_batches(e_res), top) if rank == 0 else None,
+                              "note": "per rank: pinned host shards -> push_table (H2D) -> filtered customer rows all-gathered -> whole query -> top-10 merged"}
+                for p in e_state.values():
+                    if hasattr(p, "close"):
+                        p.close()
+                del host, keep_alive
+            for p in state.values():
+                if hasattr(p, "close"):
+                    p.close()
+
+    return (out if rank == 0 else None), window, run_e2e
 
 
 def main():
@@ -719,28 +739,34 @@ def main():
     ctx.lib = ffi.load()
     ctx.stream = torch.cuda.Stream(device=ctx.dev)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("SQLRS_BENCH_NO_SAMPLER"):
         sampler.start()  # before any warm-up: NVML start-up stays out of the timed regions
     windows = []
     line = None
     q3 = {}
     with torch.cuda.stream(ctx.stream):
         ctx.group = sqdist.TorchGroup(ctx.dist, ctx.dev) if world > 1 else None
+        deferred = []  # the e2e legs: after EVERY resident timing
         if args.query == "q1" or args.q3 == "on":
-            res = run_gpu_q1(args, ctx)
-            if res:
-                line, w = res
+            line, w, fin = run_gpu_q1(args, ctx)
+            if w:
                 windows.append(w)
+            deferred.append(("q1", fin))
         if args.q3 == "on" or args.query == "q3":
             cpu = None
             if rank == 0 and world == 1 and args.cpu_rows > 0:
                 cpu = cpu_port_q3(load_oracle(), args.cpu_sf)
             sfs = [args.q3_sf] if args.q3_sf else ([10.0, 100.0] if world == 1 else [100.0])
             for sf in sfs:
-                entry, w = run_gpu_q3(args, ctx, sf, cpu)
+                entry, w, fin = run_gpu_q3(args, ctx, sf, cpu)
                 windows.append(w)
                 if entry:
                     q3[f"sf{sf:g}"] = entry
+                deferred.append((f"q3 sf{sf:g}", fin))
+        for name, fin in deferred:
+            r = fin()
+            if name == "q1" and line is not None:
+                line["e2e"] = r
     if world > 1:
         ctx.dist.barrier()
         ctx.dist.destroy_process_group()

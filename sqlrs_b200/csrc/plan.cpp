@@ -220,6 +220,7 @@ void Plan::run_validated(const std::function<void()>& body) {
     }
     pending_chains_.clear();
     if (ok) return;
+    if (std::getenv("SQLRS_B200_LOG_RETRY")) fprintf(stderr, "[sqlrs] plan run %d discarded: a hint-sized structure did not validate; re-running with exact sizing\n", attempt);
     if (attempt >= 3) fail(SQLRS_ERR_INTERNAL, "plan: sizing hints kept failing");
     description_.clear();
   }

@@ -348,6 +348,49 @@ class DeviceBatch:
         return DeviceTable.export(self)
 
 
+def merge_topk_device(plan, group: TorchGroup, schema: pa.Schema, order_by, limit: int, state: dict, builder) -> List[pa.RecordBatch]:
+    """`merge_topk` without leaving HBM until the final rows: the <= limit rows pending in `plan` (a DEVICE result) are copied
+    into one fixed-size tensor [count | limit x columns], all-gathered, and rank 0 runs Limit(Order(Scan)) over the W x limit
+    candidate rows on the device — rank-major row order, so ties resolve as in the single-process run."""
+    from .plan import PhysicalLimit, PhysicalOrder, PhysicalTableScan
+
+    torch, W = group.torch, group.world
+    ncols = len(schema)
+    shape = plan.result_shape()
+    n = shape[0] if shape is not None else 0
+    if n > limit:
+        raise ValueError("merge_topk_device: the local plan returned more rows than the limit")
+    key = ("topk", ncols, limit)
+    if key not in state:
+        state[key] = (torch.zeros(1 + ncols * limit, dtype=torch.int64, device=group.device),
+                      torch.empty(W * (1 + ncols * limit), dtype=torch.int64, device=group.device))
+    send, recv = state[key]
+    send[0] = n
+    if shape is not None:
+        body = send[1:].view(ncols, limit)
+        plan.next_to_device([body[c].data_ptr() for c in range(ncols)])
+    _check_stream(plan, group)
+    group.dist.all_gather_into_tensor(recv, send)
+    if group.rank != 0:
+        return []
+    every = recv.view(W, 1 + ncols * limit)
+    counts = every[:, 0].tolist()
+    total = int(sum(counts))
+    if total == W * limit:  # the usual case: every rank had at least `limit` rows — one strided copy, rank-major rows
+        body = every[:, 1:].reshape(W, ncols, limit).permute(1, 0, 2).contiguous()
+        cols = [body[c].view(-1) for c in range(ncols)]
+    else:
+        cols = [torch.cat([every[r, 1:].view(ncols, limit)[c, :counts[r]] for r in range(W)]) for c in range(ncols)]
+    if "p_tail" not in state:
+        tail = PhysicalLimit(limit, None, PhysicalOrder(order_by, PhysicalTableScan(0)))
+        state["p_tail"] = builder.build(tail, {0: schema})
+    p_tail = state["p_tail"]
+    p_tail.reset()
+    dev = group.device.index if group.device.index is not None else 0
+    p_tail.push_table_device(0, DeviceBatch(schema, cols, total, dev))
+    return p_tail.run()
+
+
 def broadcast_rows(plan, group: TorchGroup, schema: pa.Schema) -> DeviceBatch:
     """The rows `plan` (already executed on this rank's shard; ONE pending device result of fixed-width, NULL-free columns)
     produced on every rank, concatenated in rank order, on every rank — all-gathered device to device.  This is the
@@ -465,20 +508,45 @@ def distributed_join_topk(builder, group: TorchGroup, *, build_plan, build_schem
 
     `state`: a dict kept by the caller across calls; the built plans live there so that repeated runs reuse compiled kernels,
     device buffers and sizing hints."""
+    import os
+    import time
+
+    trace = os.environ.get("SQLRS_B200_DIST_TRACE") == "1"
+
+    def mark(label, t=[None]):
+        if not trace:
+            return
+        group.torch.cuda.synchronize(group.device)
+        now = time.perf_counter()
+        if t[0] is not None and label:
+            print(f"[dist trace] rank {group.rank}: {label} {1e3 * (now - t[0]):.3f} ms", flush=True)
+        t[0] = now
+
     state = state if state is not None else {}
     if "p_build" not in state:
         state["p_build"] = builder.build(build_plan, build_schemas)
         state["p_query"] = builder.build(query_plan, query_schemas)
     p_build, p_query = state["p_build"], state["p_query"]
+    mark("")
     p_build.reset()
     p_query.reset()
     _push(p_build, build_tables)
     p_build.execute()
+    mark("build-side sub-plan (local shard)")
     build_side = broadcast_rows(p_build, group, build_plan.output_schema(build_schemas))
+    mark("all-gather of its rows")
     p_query.push_table_device(build_slot, build_side)
     _push(p_query, query_tables)
-    local = p_query.run()
-    return merge_topk(p_query, group, local, order_by, limit)
+    if group.native_a2a and builder.lib.prefix == "sqlrs_":
+        p_query.execute()
+        mark("query plan (local shards)")
+        out = merge_topk_device(p_query, group, query_plan.output_schema(query_schemas), order_by, limit, state, builder)
+    else:
+        local = p_query.run()
+        mark("query plan (local shards)")
+        out = merge_topk(p_query, group, local, order_by, limit)
+    mark("top-k merge")
+    return out
 
 
 def copartitioned_shard(n_orders: int, rank: int, world: int):
