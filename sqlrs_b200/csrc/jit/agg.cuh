@@ -524,35 +524,62 @@ extern "C" __global__ void __launch_bounds__(256) sq_agg_medium(SqIn in, i64 n, 
   }
 }
 
-// many groups: straight into the HBM table
-extern "C" __global__ void __launch_bounds__(256) sq_agg_global(SqIn in, i64 n, i64 row_base, SqTable table, i64 batch_no,
-                                                                 u32* __restrict__ status, u32* __restrict__ err) {
+// many groups: straight into the HBM table.  The table is kept DENSE: it starts small and a row whose group is new while the
+// table holds `limit` groups is not inserted but appended to `overflow_rows`; the host grows the table (x4, re-hash) and
+// launches the kernel again over that list (`redo_rows`).  Measured reason (profiles/r02_q1_sf10_variants.txt): sized for the
+// worst case "every row a new group", 125 k groups scattered over 16 M slots x 13 arrays touch ~200 MB of L2 lines and every
+// row pays DRAM latency a dozen times; in a 256 k-slot table the same groups are L2-resident.
+// SQ_GUNROLL rows per thread per trip: their loads and their find-or-insert probes are independent chains, issued back to
+// back; the first-row id only goes through an atomic when it lowers the slot's current value, the accumulator words are
+// fire-and-forget reductions.
+#ifndef SQ_GUNROLL
+#define SQ_GUNROLL 2
+#endif
+extern "C" __global__ void __launch_bounds__(256) sq_agg_global(SqIn in, i64 n, i64 row_base, SqTable table, i64 batch_no, u32* __restrict__ status,
+                                                                 u32* __restrict__ err, const u32* __restrict__ redo_rows, u32 n_redo,
+                                                                 u32* __restrict__ overflow_rows, u32* __restrict__ overflow_count, u32 limit) {
   bool any_err = false;
-  const i64 stride = (i64)gridDim.x * blockDim.x;
+  const i64 total = redo_rows ? (i64)n_redo : n;
+  const i64 stride = (i64)gridDim.x * blockDim.x * SQ_GUNROLL;
   // warp-uniform trip count (the tail is predicated) so that __syncwarp can reconverge the warp
   // after the divergent find-or-insert
-  for (i64 base = (i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
-    const i64 r = base + (threadIdx.x & 31);
-    const bool inb = r < n;
-    SqRow o;
-    bool e0 = false, e1 = false;
-    sq_row(in, inb ? r : n - 1, o, e0, e1);
-    const bool live = inb && o.pass;
-    any_err |= (inb && e0) || (live && e1);
-    int slot = -1;
-    if (live) {
-      slot = sq_table_upsert(table, o.h, o.kb, o.knull);
-      if (slot < 0) atomicOr(status, SQ_STATUS_FULL);
+  for (i64 base = ((i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * SQ_GUNROLL; base < total; base += stride) {
+    SqRow o[SQ_GUNROLL];
+    bool live[SQ_GUNROLL];
+    i64 row[SQ_GUNROLL];
+#pragma unroll
+    for (int u = 0; u < SQ_GUNROLL; u++) {
+      const i64 i = base + u * 32 + (threadIdx.x & 31);
+      const bool inb = i < total;
+      row[u] = inb ? (redo_rows ? (i64)redo_rows[i] : i) : n - 1;
+      bool e0 = false, e1 = false;
+      sq_row(in, row[u], o[u], e0, e1);
+      live[u] = inb && o[u].pass;
+      any_err |= (inb && e0) || (live[u] && e1);
+    }
+    int slot[SQ_GUNROLL];
+#pragma unroll
+    for (int u = 0; u < SQ_GUNROLL; u++) {
+      slot[u] = -1;
+      if (live[u]) {
+        slot[u] = sq_table_upsert(table, o[u].h, o[u].kb, o[u].knull, limit);
+        if (slot[u] == -1) atomicOr(status, SQ_STATUS_FULL);
+        if (slot[u] == -2) overflow_rows[atomicAdd(overflow_count, 1u)] = (u32)row[u];
+      }
     }
     __syncwarp();
-    if (slot >= 0) {
-      atomicMin(&table.min_row[slot], (u64)(row_base + r));
-      u64 local[SQ_NACC > 0 ? SQ_NACC : 1];
 #pragma unroll
-      for (int w = 0; w < SQ_NACC; w++) local[w] = sq_acc_identity(w);
-      sq_acc_update(local, 1, o);
+    for (int u = 0; u < SQ_GUNROLL; u++) {
+      if (slot[u] >= 0) {
+        const u64 gr = (u64)(row_base + row[u]);
+        if (gr < table.min_row[slot[u]]) atomicMin(&table.min_row[slot[u]], gr);
+        u64 local[SQ_NACC > 0 ? SQ_NACC : 1];
 #pragma unroll
-      for (int w = 0; w < SQ_NACC; w++) sq_acc_merge_global(&table.acc[(size_t)w * table.capacity + slot], w, local[w], batch_no);
+        for (int w = 0; w < SQ_NACC; w++) local[w] = sq_acc_identity(w);
+        sq_acc_update(local, 1, o[u]);
+#pragma unroll
+        for (int w = 0; w < SQ_NACC; w++) sq_acc_merge_global(&table.acc[(size_t)w * table.capacity + slot[u]], w, local[w], batch_no);
+      }
     }
     __syncwarp();
   }

@@ -34,20 +34,29 @@ __device__ __forceinline__ bool sq_keys_equal(const u64* a, u32 an, const u64* b
   return true;
 }
 
-// find-or-insert in the HBM table; returns the slot or -1 (table full)
-__device__ __forceinline__ int sq_table_upsert(const SqTable& t, u64 h, const u64* kb, u32 knull) {
+// Publication protocol of a slot: the publisher writes hash / keys / null mask, then stores state = 2 with release semantics.
+// A reader loads the state from L2 (volatile) and — only after it saw 2: the loads are control-dependent — the identity
+// words with ld.global.cg, i.e. from L2 as well, never from a possibly stale L1 line.  No fence and no acquire on the read
+// side: __threadfence() per lookup is a MEMBAR.GPU per row, ld.acquire.gpu compiles to an L1 invalidate (CCTL.IVALL, 20 % of
+// the stall samples of sq_agg_global in profiles/r02f_*).
+__device__ __forceinline__ u32 sq_ld_acquire_u32(const u32* p) { return *((volatile const u32*)p); }
+__device__ __forceinline__ void sq_st_release_u32(u32* p, u32 v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// find-or-insert in the HBM table; returns the slot, -1 (table full), or -2: the key is absent and the table already holds
+// `limit` groups (the caller keeps the table dense: it records the row, grows the table and redoes the row)
+__device__ __forceinline__ int sq_table_upsert(const SqTable& t, u64 h, const u64* kb, u32 knull, u32 limit = 0xffffffffu) {
   const u32 mask = t.capacity - 1;
   u32 s = sq_mix32(h) & mask;
   for (u32 probes = 0; probes <= mask;) {
-    u32 st = *((volatile u32*)&t.state[s]);
+    u32 st = sq_ld_acquire_u32(&t.state[s]);
     if (st == 0) {
+      if (limit != 0xffffffffu && *((volatile u32*)&t.counters[0]) >= limit) return -2;
       if (atomicCAS(&t.state[s], 0u, 1u) == 0u) {
         t.hash[s] = h;
 #pragma unroll
         for (int k = 0; k < SQ_NKEYS; k++) t.keys[(size_t)k * t.capacity + s] = kb[k];
         t.knull[s] = knull;
-        __threadfence();
-        atomicExch(&t.state[s], 2u);
+        sq_st_release_u32(&t.state[s], 2u);
         atomicAdd(&t.counters[0], 1u);
         t.new_slots[atomicAdd(&t.counters[1], 1u)] = s;
         return (int)s;
@@ -55,13 +64,12 @@ __device__ __forceinline__ int sq_table_upsert(const SqTable& t, u64 h, const u6
       continue;  // lost the race: look at the slot again
     }
     if (st == 1) continue;  // another thread is publishing this slot
-    __threadfence();
-    if (*((volatile u64*)&t.hash[s]) == h) {
+    if (__ldcg(&t.hash[s]) == h) {   // published slots never change their identity
 #if SQ_MATCH_KEYS
       u64 other[SQ_NKEYS > 0 ? SQ_NKEYS : 1];
 #pragma unroll
-      for (int k = 0; k < SQ_NKEYS; k++) other[k] = *((volatile u64*)&t.keys[(size_t)k * t.capacity + s]);
-      if (sq_keys_equal(other, *((volatile u32*)&t.knull[s]), kb, knull)) return (int)s;
+      for (int k = 0; k < SQ_NKEYS; k++) other[k] = __ldcg(&t.keys[(size_t)k * t.capacity + s]);
+      if (sq_keys_equal(other, __ldcg(&t.knull[s]), kb, knull)) return (int)s;
 #else
       return (int)s;
 #endif
@@ -71,4 +79,3 @@ __device__ __forceinline__ int sq_table_upsert(const SqTable& t, u64 h, const u6
   }
   return -1;
 }
-

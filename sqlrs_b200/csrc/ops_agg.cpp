@@ -568,7 +568,14 @@ void AggOp::reset() {
   rows_seen_ = 0;
   batches_seen_ = 0;
   seen_batch_ = false;
+  // the tier that fits the previous run's group count (a plan is usually re-run over similar data): the escalation small ->
+  // medium -> global costs two wasted passes over the first batch otherwise
   level_ = 0;
+  if (!cache_.empty() && groups_hint_ > 0) {
+    const Compiled& c = *cache_.begin()->second;
+    if (groups_hint_ > (uint32_t)c.slots) level_ = 1;
+    if (groups_hint_ > (uint32_t)std::max(c.mslots, c.slots)) level_ = 2;
+  }
   groups_known_ = 0;
   groups_bound_ = 0;
   counters_stale_ = false;
@@ -745,32 +752,57 @@ void AggOp::push(const DBatch& batch) {
   }
   if (!done) {
     level_ = 2;
-    const int64_t chunk = 1LL << 22;
+    // The table stays dense (see sq_agg_global): it starts at 64 k slots and accepts new groups up to 3/4 of its capacity; rows
+    // of further new groups come back in an overflow list, the table grows x4 (re-hash) and the kernel runs again over the list.
+    const int64_t chunk = 1LL << 24;
+    const int sms = device_sm_count(ctx_.device);
+    if (!table_) ensure_table(1u << 16);
+    BufPtr lists[2] = {dev_alloc(ctx_, (size_t)std::min(chunk, n) * 4), nullptr};
+    BufPtr ov_count = dev_alloc_zero(ctx_, 4);
+    int grows = 0;
     for (int64_t start = 0; start < n; start += chunk) {
       const int64_t len = std::min(chunk, n - start);
-      reserve((uint64_t)len);
       SqInBlob in(batch, start);
-      int64_t n_arg = len, rb = row_base + start, bn = batch_no;
-      void* status = (uint32_t*)table_->counters->p + 2;
-      void* errp = (uint32_t*)table_->counters->p + 3;
-      TableView tv = table_->view();
-      void* args[] = {in.ptr(), &n_arg, &rb, &tv, &bn, &status, &errp};
-      const int sms = device_sm_count(ctx_.device);
-      unsigned grid = (unsigned)std::min<int64_t>(div_up(len, 256), (int64_t)sms * 8);
-      ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
-      {
-        KernelEvent ev(opt_.flags, ctx_.stream, "sq_agg_global");
-        jit_launch(c.global, grid, 256, 0, ctx_.stream, args);
-      }
-      timer.stop();
-      if (timer.enabled) {
-        SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+      const uint32_t* redo = nullptr;
+      uint32_t n_redo = 0;
+      int cur = 0;
+      for (;;) {
+        int64_t n_arg = len, rb = row_base + start, bn = batch_no;
+        void* status = (uint32_t*)table_->counters->p + 2;
+        void* errp = (uint32_t*)table_->counters->p + 3;
+        TableView tv = table_->view();
+        uint32_t limit = table_->capacity / 4 * 3;
+        void* ov_rows = lists[cur]->p;
+        void* ov_cnt = ov_count->p;
+        void* args[] = {in.ptr(), &n_arg, &rb, &tv, &bn, &status, &errp, &redo, &n_redo, &ov_rows, &ov_cnt, &limit};
+        const int64_t items = redo ? (int64_t)n_redo : len;
+        unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(div_up(items, 256 * 2), 1), (int64_t)sms * 8);  // 256 threads x SQ_GUNROLL (2) rows per trip
+        ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
+        {
+          KernelEvent ev(opt_.flags, ctx_.stream, "sq_agg_global");
+          jit_launch(c.global, grid, 256, 0, ctx_.stream, args);
+        }
+        timer.stop();
+        uint32_t overflowed = 0;
+        SQ_CUDA(cudaMemcpyAsync(&overflowed, ov_count->p, 4, cudaMemcpyDeviceToHost, ctx_.stream));
+        read_counters(hc);  // synchronises: the group count, the status bits and `overflowed`
         scan_kernel_ms_ += timer.elapsed_ms();
-        scan_kernel_launches_++;
+        scan_kernel_launches_ += timer.enabled && !redo ? 1 : 0;
+        if (std::getenv("SQLRS_B200_DEBUG_CHUNKS"))
+          fprintf(stderr, "[sqlrs] sq_agg_global chunk @%lld: %lld items, %.3f ms, groups %u, overflowed %u, capacity %u\n", (long long)start, (long long)items,
+                  timer.elapsed_ms(), hc[0], overflowed, table_->capacity);
+        if (overflowed == 0) break;
+        flush_new_slots();  // slot numbers change under the re-hash
+        grow_table(table_->capacity * 4);
+        grows++;
+        SQ_CUDA(cudaMemsetAsync(ov_count->p, 0, 4, ctx_.stream));
+        redo = (const uint32_t*)lists[cur]->p;
+        n_redo = overflowed;
+        cur ^= 1;
+        if (!lists[cur]) lists[cur] = dev_alloc(ctx_, (size_t)std::min(chunk, n) * 4);
       }
     }
-    read_counters(hc);
-    last_path_ = "sq_agg_global (open-addressed table in HBM, capacity " + std::to_string(table_->capacity) + ")";
+    last_path_ = "sq_agg_global (dense open-addressed table in HBM, capacity " + std::to_string(table_->capacity) + ", grown " + std::to_string(grows) + "x)";
   }
   flush_new_slots();
 }
