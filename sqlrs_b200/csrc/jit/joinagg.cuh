@@ -98,15 +98,29 @@ extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_kernel(SqIn i
 
 #if SQ_TMA
 // ---------------------------------------------------------------------------------------------------------------
-// TMA variant: "bulk-async staging of probe-side batches into shared memory".  One elected thread per CTA issues
-// cp.async.bulk copies of whole 2048-row slices (16 KB each) of the columns the probe program reads — Filter column(s)
-// and join key(s) — into a two-stage shared-memory ring and arms an mbarrier with the byte count; the copy of tile
-// i+1 is in flight while the CTA evaluates tile i out of shared memory.  Versus the register-staged kernel above, the
-// DRAM latency of phase A is taken off the warps' critical path and no registers are spent on loads in flight.
-// Phase B (the compacted candidates) is unchanged: it re-evaluates the few candidate rows from global memory (L2 hits:
-// the slice has just passed through L2) and gathers the remaining probe columns only for matches.
-// Requirements checked by the host (ops_agg.cpp): every staged column is 8 bytes wide and 16-byte aligned; the rows
-// behind the last full tile go through sq_joinagg_kernel.
+// TMA variant (opt-in: SQLRS_B200_TMA=1): "bulk-async staging of probe-side batches into shared memory", warp-specialised.
+//   * ONE producer warp per CTA: its lane 0 issues cp.async.bulk copies of SQ_TROWS-row slices of the columns the probe
+//     program reads (Filter column(s) + join key(s), 8 KB per column) into a SQ_TSTAGES-deep shared-memory ring.  Per stage
+//     a FULL mbarrier (armed with the byte count, completed by the copies) and an EMPTY mbarrier (one arrival per consumer
+//     warp).  The producer only ever waits for a stage to be EMPTY, so up to SQ_TSTAGES tiles are in flight per CTA with no
+//     registers spent on loads.
+//   * SQ_TCONSUMERS consumer warps: each waits for FULL, evaluates its 1/SQ_TCONSUMERS slice of the tile out of shared
+//     memory (phase A), and releases the stage with ONE mbarrier.arrive per warp as soon as its values are in registers —
+//     no __syncthreads(), nobody waits for another warp.  The Bloom test and phase B (exact probe of the queued candidates,
+//     gathers, group upsert) run AFTER the release and touch global memory only, as in the register-staged kernel.
+// Round 1's variant (two stages, issuing thread inside a consumer warp, a CTA barrier per tile) coupled every warp to the
+// slowest phase-B warp; this is the structure the comparison in profiles/r02g_* is made with.
+// Requirements checked by the host (ops_agg.cpp): every staged column is 8 bytes wide and 16-byte aligned; the rows behind
+// the last full tile go through sq_joinagg_kernel.
+#ifndef SQ_TSTAGES
+#define SQ_TSTAGES 4
+#endif
+#ifndef SQ_TCONSUMERS
+#define SQ_TCONSUMERS 8
+#endif
+#define SQ_TBLOCK (32 * (SQ_TCONSUMERS + 1))
+#define SQ_TUNROLL (SQ_TROWS / SQ_TCONSUMERS / 32)
+#define SQ_TQUEUE (SQ_TUNROLL * 32 + 32)
 __device__ __forceinline__ u32 sq_smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sq_mbar_init(u64* bar, u32 count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sq_smem_u32(bar)), "r"(count) : "memory");
@@ -114,6 +128,7 @@ __device__ __forceinline__ void sq_mbar_init(u64* bar, u32 count) {
 __device__ __forceinline__ void sq_mbar_expect_tx(u64* bar, u32 bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sq_smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void sq_mbar_arrive(u64* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sq_smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ void sq_bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sq_smem_u32(dst)), "l"(src), "r"(bytes),
                "r"(sq_smem_u32(bar))
@@ -129,74 +144,82 @@ __device__ __forceinline__ void sq_mbar_wait(u64* bar, u32 parity) {
   } while (!done);
 }
 
-extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_tma_kernel(SqIn in, SqInB inb, i64 n_tiles, i64 row_base, SqJoin jt, SqTable table,
+extern "C" __global__ void __launch_bounds__(SQ_TBLOCK) sq_joinagg_tma_kernel(SqIn in, SqInB inb, i64 n_tiles, i64 row_base, SqJoin jt, SqTable table,
                                                                                i64 batch_no, u32* __restrict__ status, u32* __restrict__ err) {
-  extern __shared__ __align__(128) u64 sq_tiles[];  // [2 stages][SQ_TILE_NCOLS][SQ_TROWS]
-  __shared__ __align__(8) u64 mbar[2];
-  __shared__ u32 queue_s[SQ_JBLOCK / 32][SQ_JQUEUE];
-  __shared__ u64 queue_vs[SQ_JBLOCK / 32][SQ_PQMODE ? SQ_JQUEUE : 1];
-  bool any_err = false;
+  extern __shared__ __align__(128) u64 sq_tiles[];  // [SQ_TSTAGES][SQ_TILE_NCOLS][SQ_TROWS]
+  __shared__ __align__(8) u64 bar_full[SQ_TSTAGES], bar_empty[SQ_TSTAGES];
+  __shared__ u32 queue_s[SQ_TCONSUMERS][SQ_TQUEUE];
+  __shared__ u64 queue_vs[SQ_TCONSUMERS][SQ_PQMODE ? SQ_TQUEUE : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  u32* queue = queue_s[warp];
-  u64* queue_v = queue_vs[warp];
-  const u32 lanes_below = (1u << lane) - 1u;
-  u32 queued = 0;  // warp-uniform
-  const int tile_cols[SQ_TILE_NCOLS] = SQ_TILE_COLS;
   if (threadIdx.x == 0) {
-    sq_mbar_init(&mbar[0], 1);
-    sq_mbar_init(&mbar[1], 1);
+#pragma unroll
+    for (int s = 0; s < SQ_TSTAGES; s++) {
+      sq_mbar_init(&bar_full[s], 1);
+      sq_mbar_init(&bar_empty[s], SQ_TCONSUMERS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  i64 tile = blockIdx.x;
-  if (threadIdx.x == 0 && tile < n_tiles) {
-    sq_mbar_expect_tx(&mbar[0], SQ_TILE_NCOLS * SQ_TROWS * 8);
+  if (warp == SQ_TCONSUMERS) {
+    // ---- producer warp
+    if (lane == 0) {
+      const int tile_cols[SQ_TILE_NCOLS] = SQ_TILE_COLS;
+      u32 k = 0;
+      for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
+        const u32 stage = k % SQ_TSTAGES, use = k / SQ_TSTAGES;
+        sq_mbar_wait(&bar_empty[stage], (use & 1u) ^ 1u);  // a fresh barrier passes: the stage has never been filled
+        sq_mbar_expect_tx(&bar_full[stage], SQ_TILE_NCOLS * SQ_TROWS * 8);
 #pragma unroll
-    for (int k = 0; k < SQ_TILE_NCOLS; k++)
-      sq_bulk_g2s(sq_tiles + (size_t)k * SQ_TROWS, (const u64*)in.col[tile_cols[k]] + tile * SQ_TROWS, SQ_TROWS * 8, &mbar[0]);
-  }
-  for (u32 it = 0; tile < n_tiles; it++, tile += gridDim.x) {
-    const u32 stage = it & 1u;
-    const i64 next = tile + gridDim.x;
-    if (threadIdx.x == 0 && next < n_tiles) {  // the other stage was released by the __syncthreads() that ended the previous trip
-      sq_mbar_expect_tx(&mbar[stage ^ 1u], SQ_TILE_NCOLS * SQ_TROWS * 8);
-#pragma unroll
-      for (int k = 0; k < SQ_TILE_NCOLS; k++)
-        sq_bulk_g2s(sq_tiles + ((size_t)(stage ^ 1u) * SQ_TILE_NCOLS + k) * SQ_TROWS, (const u64*)in.col[tile_cols[k]] + next * SQ_TROWS, SQ_TROWS * 8,
-                    &mbar[stage ^ 1u]);
+        for (int c = 0; c < SQ_TILE_NCOLS; c++)
+          sq_bulk_g2s(sq_tiles + ((size_t)stage * SQ_TILE_NCOLS + c) * SQ_TROWS, (const u64*)in.col[tile_cols[c]] + tile * SQ_TROWS, SQ_TROWS * 8, &bar_full[stage]);
+      }
     }
-    sq_mbar_wait(&mbar[stage], (it >> 1) & 1u);
+    return;
+  }
+  // ---- consumer warps
+  bool any_err = false;
+  u32* queue = queue_s[warp];
+  u64* queue_v = queue_vs[warp];
+  const u32 lanes_below = (1u << lane) - 1u;
+  const u64 pol_keep = sq_l2_evict_last();
+  u32 queued = 0;  // warp-uniform
+  u32 k = 0;
+  for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
+    const u32 stage = k % SQ_TSTAGES, use = k / SQ_TSTAGES;
+    sq_mbar_wait(&bar_full[stage], use & 1u);
     const u64* tl = sq_tiles + (size_t)stage * SQ_TILE_NCOLS * SQ_TROWS;
-    const i64 base = tile * SQ_TROWS + (i64)warp * (SQ_JUNROLL * 32);
+    const int t0 = warp * (SQ_TUNROLL * 32);
+    const i64 base = tile * SQ_TROWS + t0;
     // ---- phase A out of shared memory
-    u64 hh[SQ_JUNROLL], qvv[SQ_JUNROLL];
-    bool live[SQ_JUNROLL];
+    u64 qv[SQ_TUNROLL];
+    u32 bits[SQ_TUNROLL], bw[SQ_TUNROLL];
+    bool live[SQ_TUNROLL];
 #pragma unroll
-    for (int u = 0; u < SQ_JUNROLL; u++) {
-      const int t = warp * (SQ_JUNROLL * 32) + u * 32 + lane;
+    for (int u = 0; u < SQ_TUNROLL; u++) {
       SqProbe p;
       bool e0 = false, e1 = false;
-      sq_probe_row_tile(in, tl, t, base + u * 32 + lane, p, e0, e1);
+      sq_probe_row_tile(in, tl, t0 + u * 32 + lane, base + u * 32 + lane, p, e0, e1);
       live[u] = p.pass;
 #if SQ_JMATCH
       live[u] = live[u] && p.knull == 0u;
 #endif
       any_err |= e0 || (p.pass && e1);
-      hh[u] = p.h;
-      qvv[u] = SQ_PQMODE ? sq_probe_qv(p) : 0ULL;
+      qv[u] = SQ_PQMODE ? sq_probe_qv(p) : 0ULL;
+      bits[u] = sq_bloom_bits(p.h);
+      bw[u] = sq_bloom_word(p.h, jt.bloom_mask);
     }
-    u32 bw[SQ_JUNROLL];
+    __syncwarp();
+    if (lane == 0) sq_mbar_arrive(&bar_empty[stage]);  // this warp is done with the stage: the producer may refill it
 #pragma unroll
-    for (int u = 0; u < SQ_JUNROLL; u++) bw[u] = live[u] ? sq_ld_u32_l2(&jt.bloom[sq_bloom_word(hh[u], jt.bloom_mask)], sq_l2_evict_last()) : 0u;
+    for (int u = 0; u < SQ_TUNROLL; u++) bw[u] = live[u] ? sq_ld_u32_l2(&jt.bloom[bw[u]], pol_keep) : 0u;
 #pragma unroll
-    for (int u = 0; u < SQ_JUNROLL; u++) {
-      const u32 bits = sq_bloom_bits(hh[u]);
-      const bool cand = live[u] && (bw[u] & bits) == bits;
+    for (int u = 0; u < SQ_TUNROLL; u++) {
+      const bool cand = live[u] && (bw[u] & bits[u]) == bits[u];
       const u32 m = __ballot_sync(0xffffffffu, cand);
       if (cand) {
         const u32 pos = queued + __popc(m & lanes_below);
         queue[pos] = (u32)(base + u * 32 + lane);
-        if (SQ_PQMODE) queue_v[pos] = qvv[u];
+        if (SQ_PQMODE) queue_v[pos] = qv[u];
       }
       queued += __popc(m);
     }
@@ -207,7 +230,6 @@ extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_tma_kernel(Sq
       sq_joinagg_candidate(in, inb, (i64)queue[queued + lane], SQ_PQMODE ? queue_v[queued + lane] : 0ULL, row_base, jt, table, batch_no, status, any_err);
       __syncwarp();
     }
-    __syncthreads();  // every warp is done with this stage before it is refilled
   }
   if ((u32)lane < queued) sq_joinagg_candidate(in, inb, (i64)queue[lane], SQ_PQMODE ? queue_v[lane] : 0ULL, row_base, jt, table, batch_no, status, any_err);
   if (any_err) atomicOr(err, 1u);

@@ -14,6 +14,12 @@ namespace sq {
 // When every column that program reads is an 8-byte column (at most 3 of them), `tile_cols` lists them and the source
 // also contains sq_probe_row_tile(in, tile, t, r, ...): the same program reading those columns from a shared-memory
 // tile staged by TMA bulk copies (SQ_TMA 1, SQ_TILE_NCOLS, SQ_TILE_COLS) — csrc/jit/joinagg.cuh: sq_joinagg_tma_kernel.
+// shape of the TMA ring of csrc/jit/joinagg.cuh: sq_joinagg_tma_kernel — rows per tile (8 B x rows per staged column), stages,
+// consumer warps per CTA.  Defaults 1024 / 4 / 8; SQLRS_B200_TMA_TROWS / _STAGES / _CONSUMERS override them (experiments).
+struct TmaShape {
+  int tile_rows, stages, consumers;
+};
+const TmaShape& tma_shape();
 struct ProbeProgram {
   std::string src;
   std::vector<int> tile_cols;

@@ -903,19 +903,22 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
     const JoinKernels& jk = kit->second;
     // TMA variant: whole 2048-row slices of the probe program's columns are staged in shared memory by bulk-async
     // copies, double buffered — needs 16-byte aligned column buffers (sliced Arrow arrays may not be)
-    bool use_tma = jk.tma != nullptr && n >= 2048;
+    const int kTmaTileRows = tma_shape().tile_rows, kTmaStages = tma_shape().stages, kTmaConsumerWarps = tma_shape().consumers;
+    bool use_tma = jk.tma != nullptr && n >= kTmaTileRows;
     for (int c : jk.tile_cols)
       use_tma = use_tma && c < (int)probe.cols.size() && probe.cols[(size_t)c].data && ((uintptr_t)probe.cols[(size_t)c].data % 16 == 0);
     ScanTimer timer(ctx_.stream, (opt_.flags & SQLRS_FLAG_TIMING) != 0);
     int64_t done_rows = 0;
     if (use_tma) {
-      int64_t n_tiles = n / 2048;
-      const size_t smem = (size_t)2 * jk.tile_cols.size() * 2048 * 8;
-      const int per_sm = std::max(1, jit_max_blocks_per_sm(jk.tma, 256, smem));
+      int64_t n_tiles = n / kTmaTileRows;
+      const size_t smem = (size_t)kTmaStages * jk.tile_cols.size() * kTmaTileRows * 8;
+      const int tblock = 32 * (kTmaConsumerWarps + 1);  // one producer warp + the consumer warps
+      const int per_sm = std::max(1, jit_max_blocks_per_sm(jk.tma, tblock, smem));
       unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * per_sm);
       void* args[] = {in.ptr(), inb.ptr(), &n_tiles, &rb, &jv, &tv, &bn, &status, &errp};
-      jit_launch(jk.tma, grid, 256, smem, ctx_.stream, args);
-      done_rows = n_tiles * 2048;
+      KernelEvent ev(opt_.flags, ctx_.stream, "sq_joinagg_tma_kernel");
+      jit_launch(jk.tma, grid, (unsigned)tblock, smem, ctx_.stream, args);
+      done_rows = n_tiles * kTmaTileRows;
     }
     if (done_rows < n) {  // everything, or the ragged tail behind the last full tile
       SqInBlob in_tail(probe, done_rows);

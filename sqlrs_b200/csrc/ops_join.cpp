@@ -69,7 +69,8 @@ ProbeProgram gen_probe_program(const std::vector<ColInfo>& cols, const std::vect
       replace_all("SQ_LD_I64(" + c + ", r)", "((long long)" + at + ")");
       replace_all("SQ_LD_F64(" + c + ", r)", "__longlong_as_double((long long)" + at + ")");
     }
-    s << "#define SQ_TMA 1\n#define SQ_TROWS 2048\n#define SQ_TILE_NCOLS " << tile_cols.size() << "\n#define SQ_TILE_COLS {";
+    s << "#define SQ_TMA 1\n#define SQ_TROWS " << tma_shape().tile_rows << "\n#define SQ_TSTAGES " << tma_shape().stages << "\n#define SQ_TCONSUMERS "
+      << tma_shape().consumers << "\n#define SQ_TILE_NCOLS " << tile_cols.size() << "\n#define SQ_TILE_COLS {";
     for (size_t k = 0; k < tile_cols.size(); k++) s << (k ? ", " : "") << tile_cols[k];
     s << "}\n";
     s << "__device__ __forceinline__ void sq_probe_row_tile(const SqIn& in, const u64* __restrict__ tile, int t, i64 r, SqProbe& p, bool& e0, bool& e1) {\n" << tb;
@@ -82,6 +83,18 @@ ProbeProgram gen_probe_program(const std::vector<ColInfo>& cols, const std::vect
   }
   out.src = s.str();
   return out;
+}
+
+const TmaShape& tma_shape() {
+  static const TmaShape shape = [] {
+    TmaShape s{1024, 4, 8};
+    if (const char* e = std::getenv("SQLRS_B200_TMA_TROWS")) s.tile_rows = std::max(256, atoi(e) / 256 * 256);
+    if (const char* e = std::getenv("SQLRS_B200_TMA_STAGES")) s.stages = std::min(16, std::max(2, atoi(e)));
+    if (const char* e = std::getenv("SQLRS_B200_TMA_CONSUMERS")) s.consumers = std::min(31, std::max(1, atoi(e)));
+    while (s.tile_rows % (32 * s.consumers) != 0 && s.consumers > 1) s.consumers--;  // every consumer warp takes whole 32-row groups
+    return s;
+  }();
+  return shape;
 }
 
 std::string gen_build_decls(const std::vector<ColInfo>& build_cols) {
