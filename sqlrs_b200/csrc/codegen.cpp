@@ -1,6 +1,10 @@
 // sqlrs_b200 — row-program code generator (see codegen.hpp).
 #include "codegen.hpp"
 
+#include <cstring>
+
+#include "device.hpp"
+
 #include <cstdio>
 
 namespace sq {
@@ -17,6 +21,10 @@ ExprCopy copy_expr(const sqlrs_expr* e) {
     n.is_null = e->nodes[k].is_null;
     n.imm_bits = e->nodes[k].imm_bits;
     n.has_str = e->nodes[k].str != nullptr;
+    if (n.op == SQLRS_OP_CONSTANT && n.dtype == SQLRS_DT_UTF8 && !n.is_null) {  // a string literal becomes its id in the string pool
+      const char* str = e->nodes[k].str ? e->nodes[k].str : "";
+      n.imm_bits = StringPool::instance().intern(str, std::strlen(str));
+    }
     out.push_back(n);
   }
   return out;
@@ -102,7 +110,8 @@ Val RowProgram::load_column(int index) {
       case SQLRS_DT_INT32: return define(c.dtype, "SQ_LDB_I32(" + ci + ", b)", "SQ_VALIDB(" + ci + ", b)", c.has_valid, c.nullable, key);
       case SQLRS_DT_INT64: return define(c.dtype, "SQ_LDB_I64(" + ci + ", b)", "SQ_VALIDB(" + ci + ", b)", c.has_valid, c.nullable, key);
       case SQLRS_DT_FLOAT64: return define(c.dtype, "SQ_LDB_F64(" + ci + ", b)", "SQ_VALIDB(" + ci + ", b)", c.has_valid, c.nullable, key);
-      default: fail(SQLRS_ERR_UNSUPPORTED, "Utf8 columns are not supported by the CUDA backend yet (SURVEY §8f rank 4)");
+      case SQLRS_DT_UTF8: return define(c.dtype, "SQ_LDB_I64(" + ci + ", b)", "SQ_VALIDB(" + ci + ", b)", c.has_valid, c.nullable, key);  // string pool id
+      default: fail(SQLRS_ERR_INVALID_ARG, "unknown column dtype");
     }
   }
   index -= nb;
@@ -122,8 +131,7 @@ Val RowProgram::load_column(int index) {
     case SQLRS_DT_INT32: return define(c.dtype, "SQ_LD_I32(" + ci + ", r)", "SQ_VALID(" + ci + ", r)", c.has_valid, c.nullable, key);
     case SQLRS_DT_INT64: return define(c.dtype, "SQ_LD_I64(" + ci + ", r)", "SQ_VALID(" + ci + ", r)", c.has_valid, c.nullable, key);
     case SQLRS_DT_FLOAT64: return define(c.dtype, "SQ_LD_F64(" + ci + ", r)", "SQ_VALID(" + ci + ", r)", c.has_valid, c.nullable, key);
-    case SQLRS_DT_UTF8:
-      fail(SQLRS_ERR_UNSUPPORTED, "Utf8 columns are not supported by the CUDA backend yet (SURVEY §8f rank 4)");
+    case SQLRS_DT_UTF8: return define(c.dtype, "SQ_LD_I64(" + ci + ", r)", "SQ_VALID(" + ci + ", r)", c.has_valid, c.nullable, key);  // string pool id
   }
   fail(SQLRS_ERR_INVALID_ARG, "unknown column dtype");
 }
@@ -138,8 +146,7 @@ Val RowProgram::constant(const ExprNodeCopy& n) {
     case SQLRS_DT_INT32: value = is_null ? "0" : "((int)" + lit_i64((int32_t)n.imm_bits) + ")"; break;
     case SQLRS_DT_INT64: value = is_null ? "0" : lit_i64(n.imm_bits); break;
     case SQLRS_DT_FLOAT64: value = is_null ? "0.0" : lit_f64_bits(n.imm_bits); break;
-    case SQLRS_DT_UTF8:
-      fail(SQLRS_ERR_UNSUPPORTED, "Utf8 constants are not supported by the CUDA backend yet (SURVEY §8f rank 4)");
+    case SQLRS_DT_UTF8: value = is_null ? "0" : lit_i64(n.imm_bits); break;  // copy_expr interned the literal: its pool id
     default: fail(SQLRS_ERR_INVALID_ARG, "unknown constant dtype");
   }
   Val v = define(n.dtype, value, "false", is_null, is_null, key);
@@ -236,6 +243,9 @@ Val RowProgram::comparison(const Val& l, const Val& r, int op) {
   if (l.dtype != r.dtype)
     fail(SQLRS_ERR_ARROW, std::string("Invalid argument error: comparing ") + dtype_name(l.dtype) + " with " + dtype_name(r.dtype));
   if (l.dtype == SQLRS_DT_NULL) fail(SQLRS_ERR_ARROW, "comparison of Null arrays is not supported");
+  // Utf8 values are string-pool ids: equal strings have equal ids; the ORDER of two strings is not the order of their ids
+  if (l.dtype == SQLRS_DT_UTF8 && op != SQLRS_OP_EQ && op != SQLRS_OP_NE)
+    fail(SQLRS_ERR_UNSUPPORTED, "ordering comparisons (<, <=, >, >=) of Utf8 values are not supported by the CUDA backend");
   const char* o = op == SQLRS_OP_GT ? ">" : op == SQLRS_OP_LT ? "<" : op == SQLRS_OP_GE ? ">=" : op == SQLRS_OP_LE ? "<=" : op == SQLRS_OP_EQ ? "==" : "!=";
   std::string key = "cmp" + std::to_string(op) + "_" + std::to_string(l.id) + "_" + std::to_string(r.id);
   std::string a = vname(l.id), b = vname(r.id);
@@ -306,7 +316,8 @@ int RowProgram::emit_raw_bits(const Val& v) {
     case SQLRS_DT_FLOAT64: e = "(unsigned long long)__double_as_longlong(" + vname(v.id) + ")"; break;
     case SQLRS_DT_BOOL: e = "(unsigned long long)(" + vname(v.id) + " ? 1 : 0)"; break;
     case SQLRS_DT_INT32: e = "(unsigned long long)(long long)" + vname(v.id); break;
-    case SQLRS_DT_INT64: e = "(unsigned long long)" + vname(v.id); break;
+    case SQLRS_DT_INT64:
+    case SQLRS_DT_UTF8: e = "(unsigned long long)" + vname(v.id); break;  // Utf8: the string pool id identifies the string
     default: e = "0ULL"; break;
   }
   // NULL cells compare by the null mask alone: force their payload to 0
@@ -350,6 +361,9 @@ int RowProgram::emit_row_hash(const std::vector<Val>& keys) {
         continue;
       case SQLRS_DT_INT32: cell = "(unsigned long long)(unsigned)" + vname(k.id); break;
       case SQLRS_DT_INT64: cell = "(unsigned long long)" + vname(k.id); break;
+      // Utf8: hash_one over the pool id, not over the bytes as the reference does (hash_utils.rs:199-208) — hashes never leave
+      // the operators and ids identify strings, so only the collision pattern of the hash-only identity mode differs (unpinned)
+      case SQLRS_DT_UTF8: cell = "(unsigned long long)" + vname(k.id) + " ^ 0x7574663875746638ULL"; break;
       case SQLRS_DT_BOOL: cell = "(unsigned long long)(" + vname(k.id) + " ? 1 : 0)"; break;
       case SQLRS_DT_FLOAT64: cell = "(unsigned long long)__double_as_longlong(" + vname(k.id) + ")"; break;
       default: fail(SQLRS_ERR_INTERNAL, std::string("Unsupported data type in hasher: ") + dtype_name(k.dtype));

@@ -109,7 +109,8 @@ inline int dtype_width(int dt) {
   switch (dt) {
     case SQLRS_DT_INT32: return 4;
     case SQLRS_DT_INT64:
-    case SQLRS_DT_FLOAT64: return 8;
+    case SQLRS_DT_FLOAT64:
+    case SQLRS_DT_UTF8: return 8;  // Utf8 on the device: the string's id in the library's string pool (device.hpp)
   }
   return 0;
 }

@@ -1,6 +1,7 @@
 // sqlrs_b200 — device memory, device batches and the Arrow C Data bridge (see device.hpp).
 #include "device.hpp"
 
+#include <algorithm>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -14,6 +15,42 @@ namespace sq {
 std::atomic<int64_t> g_kernel_launches{0};
 
 static void flush_stream_cache(int device, cudaStream_t stream);  // block cache below
+
+// ------------------------------------------------------------------ string pool (Utf8 columns are columns of pool ids)
+struct StringPool::Impl {
+  mutable std::mutex mu;
+  std::unordered_map<std::string, int64_t> ids;
+  std::vector<const std::string*> by_id;  // points into `ids` (node-based: stable addresses)
+};
+StringPool::StringPool() : impl_(new Impl()) {}
+StringPool& StringPool::instance() {
+  static StringPool pool;
+  return pool;
+}
+int64_t StringPool::intern(const char* data, size_t len) {
+  std::lock_guard<std::mutex> lock(impl_->mu);
+  auto it = impl_->ids.emplace(std::string(data, len), (int64_t)impl_->by_id.size());
+  if (it.second) impl_->by_id.push_back(&it.first->first);
+  return it.first->second;
+}
+std::string StringPool::get(int64_t id) const {
+  std::lock_guard<std::mutex> lock(impl_->mu);
+  if (id < 0 || id >= (int64_t)impl_->by_id.size()) fail(SQLRS_ERR_INTERNAL, "string pool: id out of range");
+  return *impl_->by_id[(size_t)id];
+}
+int64_t StringPool::size() const {
+  std::lock_guard<std::mutex> lock(impl_->mu);
+  return (int64_t)impl_->by_id.size();
+}
+std::vector<int32_t> StringPool::ranks() const {
+  std::lock_guard<std::mutex> lock(impl_->mu);
+  const size_t n = impl_->by_id.size();
+  std::vector<int32_t> order(n), rank(n);
+  for (size_t i = 0; i < n; i++) order[i] = (int32_t)i;
+  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return *impl_->by_id[(size_t)a] < *impl_->by_id[(size_t)b]; });  // std::string <: byte-wise
+  for (size_t r = 0; r < n; r++) rank[(size_t)order[r]] = (int32_t)r;
+  return rank;
+}
 
 // ------------------------------------------------------------------ kernel events (SQLRS_FLAG_KERNEL_EVENTS)
 namespace {
@@ -467,12 +504,35 @@ DCol import_column_host(Ctx& ctx, const ArrowArray* a, int dtype, int64_t parent
     col.null_count = length;
     return col;
   }
-  if (dtype == SQLRS_DT_UTF8)
-    fail(SQLRS_ERR_UNSUPPORTED, "Utf8 columns are not supported by the CUDA backend yet (SURVEY §8f rank 4)");
   if (a->length < parent_offset + length) fail(SQLRS_ERR_INVALID_ARG, "child array shorter than batch");
   if (a->n_buffers < 2) fail(SQLRS_ERR_INVALID_ARG, "primitive array needs 2 buffers");
   const int64_t off = a->offset + parent_offset;
   const uint8_t* validity = (const uint8_t*)a->buffers[0];
+  if (dtype == SQLRS_DT_UTF8) {  // dictionary-encode on ingest: the column becomes its strings' pool ids
+    if (a->n_buffers < 3) fail(SQLRS_ERR_INVALID_ARG, "utf8 array needs 3 buffers");
+    const int32_t* offsets = (const int32_t*)a->buffers[1];
+    const char* chars = (const char*)a->buffers[2];
+    auto ids = std::make_shared<std::vector<uint8_t>>((size_t)std::max<int64_t>(length, 1) * 8);
+    int64_t* out = (int64_t*)ids->data();
+    StringPool& pool = StringPool::instance();
+    for (int64_t r = 0; r < length; r++) {
+      const bool is_null = validity && a->null_count != 0 && !((validity[(off + r) >> 3] >> ((off + r) & 7)) & 1);
+      const int32_t b = offsets[off + r], e = offsets[off + r + 1];
+      out[r] = is_null ? 0 : pool.intern(chars ? chars + b : "", (size_t)(e - b));
+    }
+    if (validity && a->null_count != 0 && length > 0) {
+      BufPtr v = upload_bits(ctx, validity, off, length, staging);
+      col.valid = (const uint32_t*)v->p;
+      col.keep_valid = v;
+      col.null_count = a->null_count > 0 && parent_offset == 0 && a->length == length ? a->null_count : -1;
+    }
+    BufPtr d = dev_alloc(ctx, (size_t)std::max<int64_t>(length, 1) * 8);
+    if (length) SQ_CUDA(cudaMemcpyAsync(d->p, ids->data(), (size_t)length * 8, cudaMemcpyHostToDevice, ctx.stream));
+    staging.push_back(ids);
+    col.data = d->p;
+    col.keep_data = d;
+    return col;
+  }
   if (validity && a->null_count != 0 && length > 0) {
     BufPtr v = upload_bits(ctx, validity, off, length, staging);
     col.valid = (const uint32_t*)v->p;
@@ -537,7 +597,7 @@ DBatch import_batch_device(Ctx& ctx, ArrowDeviceArray* darray, const ArrowSchema
       b.cols.push_back(col);
       continue;
     }
-    if (dt == SQLRS_DT_UTF8) fail(SQLRS_ERR_UNSUPPORTED, "Utf8 columns are not supported by the CUDA backend yet");
+    if (dt == SQLRS_DT_UTF8) fail(SQLRS_ERR_UNSUPPORTED, "device-resident Utf8 columns are not supported (push host batches: strings are dictionary-encoded on ingest)");
     if (ch->length < a.offset + a.length) fail(SQLRS_ERR_INVALID_ARG, "child array shorter than batch");
     const int64_t off = ch->offset + a.offset;
     if (ch->buffers[0] && ch->null_count != 0) {
@@ -686,6 +746,26 @@ void export_batch_host(Ctx& ctx, const DBatch& b, ArrowArray* out, ArrowSchema* 
     a->null_count = nulls;
     if (nulls > 0) cp->buffers[0] = validity_host[c];
     a->n_buffers = 2;
+    if (col.dtype == SQLRS_DT_UTF8) {  // decode the pool ids: Arrow Utf8 = [validity, int32 offsets, bytes]
+      const int64_t* ids = (const int64_t*)cp->buffers[1];
+      int32_t* offsets = (int32_t*)xmalloc(sizeof(int32_t) * (size_t)(col.n + 1));
+      std::string chars;
+      StringPool& pool = StringPool::instance();
+      offsets[0] = 0;
+      for (int64_t r = 0; r < col.n; r++) {
+        const bool is_null = nulls > 0 && !((validity_host[c][r >> 3] >> (r & 7)) & 1);
+        if (!is_null) chars += pool.get(ids[r]);
+        if (chars.size() > 0x7fffffffu) fail(SQLRS_ERR_UNSUPPORTED, "Utf8 result column exceeds 2 GiB");
+        offsets[r + 1] = (int32_t)chars.size();
+      }
+      char* bytes = (char*)xmalloc(chars.size());
+      if (!chars.empty()) std::memcpy(bytes, chars.data(), chars.size());
+      cp->owned.push_back(offsets);
+      cp->owned.push_back(bytes);
+      cp->buffers[1] = offsets;
+      cp->buffers.push_back(bytes);
+      a->n_buffers = 3;
+    }
     a->buffers = cp->buffers.data();
   }
   p->buffers.push_back(nullptr);

@@ -36,6 +36,26 @@ struct Ctx {
   void sync();                           // cudaStreamSynchronize + run all deferred functions
 };
 
+// Utf8 on the device: every distinct string the library has seen lives once in a process-wide,
+// append-only pool; a Utf8 column in HBM is an 8-byte column of pool ids (dictionary encoding on ingest).  Equal strings
+// have equal ids, so group keys, join keys, DISTINCT and = / <> work on the ids as they stand; what depends on the ORDER
+// of strings (ORDER BY, MIN / MAX, < ... >=) goes through a rank table — the byte-wise rank of every id, as Rust's `str`
+// ordering (min_string / max_string, arrow sort) compares — built on the host when an operator needs it.
+// Result columns are decoded back to Arrow Utf8 on export.
+class StringPool {
+ public:
+  static StringPool& instance();
+  int64_t intern(const char* data, size_t len);
+  std::string get(int64_t id) const;
+  int64_t size() const;
+  std::vector<int32_t> ranks() const;  // ranks()[id] = position of string `id` in byte-wise order
+
+ private:
+  struct Impl;
+  StringPool();
+  Impl* impl_;
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;

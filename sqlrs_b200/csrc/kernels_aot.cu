@@ -526,6 +526,44 @@ void table_pack_sorted(const TableView& t, int n_keys, int n_acc, uint32_t n, ui
   scratch_free(count, stream);
 }
 
+__global__ void __launch_bounds__(kBlock) k_str_rank(const int64_t* __restrict__ ids, int64_t n, const int32_t* __restrict__ rank, int64_t* __restrict__ out,
+                                                      int pack) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t id = ids[i];
+    const int64_t r = (int64_t)rank[id];
+    out[i] = pack ? (int64_t)(((uint64_t)r << 32) | (uint64_t)(uint32_t)id) : r;
+  }
+}
+__global__ void __launch_bounds__(kBlock) k_str_rerank(uint64_t* __restrict__ words, const uint32_t* __restrict__ state, uint32_t capacity,
+                                                        const int32_t* __restrict__ rank, uint64_t identity) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < capacity; s += stride) {
+    if (state[s] != 2u) continue;
+    const uint64_t v = words[s];
+    if (v == identity) continue;
+    const uint64_t id = v & 0xffffffffULL;
+    words[s] = ((uint64_t)rank[id] << 32) | id;
+  }
+}
+void launch_str_rank(const int64_t* ids, int64_t n, const int32_t* rank, int64_t* out, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_str_rank<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(ids, n, rank, out, 0);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+void launch_str_pack(const int64_t* ids, int64_t n, const int32_t* rank, int64_t* out, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_str_rank<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, stream>>>(ids, n, rank, out, 1);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+void launch_str_rerank(uint64_t* words, const uint32_t* state, uint32_t capacity, const int32_t* rank, uint64_t identity, cudaStream_t stream) {
+  k_str_rerank<<<grid_for(capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(words, state, capacity, rank, identity);
+  count_launch();
+  SQ_CUDA(cudaGetLastError());
+}
+
 void launch_table_pack_partitioned(const TableView& t, int n_keys, int n_acc, uint64_t* dst, int n_parts, uint64_t cap_rows, cudaStream_t stream) {
   k_table_pack_partitioned<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, dst, (unsigned)n_parts, cap_rows);
   count_launch();

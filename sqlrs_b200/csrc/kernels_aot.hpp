@@ -29,6 +29,15 @@ void launch_gather_u32idx(int width, const void* src, const uint32_t* src_valid,
 void launch_gather_i64idx(int width, const void* src, const uint32_t* src_valid, const int64_t* idx, int64_t m, void* dst,
                           uint32_t* dst_valid, cudaStream_t stream);
 
+// ---- Utf8 (string pool ids, device.hpp): order-dependent operators go through the pool's rank table (int32 per id)
+// out[i] = rank[ids[i]]                                   (ORDER BY a Utf8 column: sort the ranks)
+void launch_str_rank(const int64_t* ids, int64_t n, const int32_t* rank, int64_t* out, cudaStream_t stream);
+// out[i] = rank[ids[i]] << 32 | ids[i]                    (MIN / MAX over a Utf8 column: an Int64 whose order is the strings')
+void launch_str_pack(const int64_t* ids, int64_t n, const int32_t* rank, int64_t* out, cudaStream_t stream);
+// words[s] = rank[id] << 32 | id with id = low half of words[s], for occupied slots whose word is not `identity`: the
+// accumulated MIN / MAX strings re-expressed in the CURRENT ranks (the pool grew since the last batch)
+void launch_str_rerank(uint64_t* words, const uint32_t* state, uint32_t capacity, const int32_t* rank, uint64_t identity, cudaStream_t stream);
+
 // ---- misc
 void launch_fill_u64(uint64_t* dst, int64_t n, uint64_t value, cudaStream_t stream);
 void launch_iota_filter_valid(const int64_t* idx, int64_t m, uint32_t* valid_out, cudaStream_t stream);
@@ -160,6 +169,7 @@ struct FinalizeCol {
   int null_bit;         // >= 0: group key k, NULL when bit k of the row's null mask is set
   int nvalid_word;      // >= 0: NULL when that word (number of non-NULL inputs) is 0
   int f64_sortable;     // value is the total-order integer image of a double (MIN/MAX over Float64)
+  int utf8_packed;      // MIN / MAX over Utf8: the word is rank << 32 | string pool id; the column receives the id
   int count_epoch;      // COUNT under the overwrite quirk K1: (batch epoch << 40) | count
   uint64_t simple_epoch;  // SimpleAgg + K1: only the last batch counts (0 = not applicable)
 };

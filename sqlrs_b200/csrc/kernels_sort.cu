@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(kBlock) k_finalize_groups(const uint64_t* __re
         const int64_t s = (int64_t)w;
         w = (uint64_t)(s ^ ((s >> 63) & 0x7fffffffffffffffLL));
       }
+      if (d.utf8_packed) w &= 0xffffffffULL;
       if (!valid) w = 0;
       if (inb) {
         if (d.dtype == SQLRS_DT_INT32) ((uint32_t*)d.data)[i] = (uint32_t)w;

@@ -36,6 +36,7 @@ struct AggPlan {
   int value_word = -1;   // main accumulator word
   int nvalid_word = -1;  // number of non-NULL inputs (only when the argument can be NULL)
   bool f64_sortable = false;
+  bool utf8_packed = false;  // MIN / MAX over a Utf8 column: the word holds rank << 32 | string pool id
 };
 
 constexpr uint64_t kEpochShift = 40;
@@ -135,6 +136,7 @@ struct AggOp::Compiled {
   std::vector<int> key_dtypes;
   std::vector<bool> key_decl_null;  // may the key be NULL in some batch of this schema?
   std::vector<int> tile_cols;       // fused probe->aggregate: probe columns the TMA variant stages in shared memory
+  std::vector<int> utf8_minmax_cols;  // input columns under MIN / MAX(Utf8): pushed as rank << 32 | id (AggOp::push)
   int block = 128, slots = 8, unroll = 4, min_ctas = 1;
   size_t small_smem = 0;
   int small_grid = 0;
@@ -328,14 +330,23 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
       }
       case SQLRS_AGG_MIN:
       case SQLRS_AGG_MAX: {
-        if (v.dtype == SQLRS_DT_UTF8) fail(SQLRS_ERR_UNSUPPORTED, "Utf8 min/max is not supported by the CUDA backend yet");
-        if (!is_numeric(v.dtype)) fail(SQLRS_ERR_UNSUPPORTED, std::string("unsupported min/max type: ") + dtype_name(v.dtype));
+        if (v.dtype == SQLRS_DT_UTF8) {
+          // min_string / max_string (min_max.rs:12-19,47-65): the column arrives as rank << 32 | id (AggOp::push re-expresses
+          // ids through the string pool's current byte-wise ranks), so the Int64 order of the words is the strings' order
+          if (jg || a.arg.size() != 1 || a.arg[0].op != SQLRS_OP_INPUT_REF)
+            fail(SQLRS_ERR_UNSUPPORTED, "min/max over a Utf8 EXPRESSION (only a plain column, outside fused joins) is not supported by the CUDA backend");
+          if (std::find(comp->utf8_minmax_cols.begin(), comp->utf8_minmax_cols.end(), a.arg[0].index) == comp->utf8_minmax_cols.end())
+            comp->utf8_minmax_cols.push_back(a.arg[0].index);
+        } else if (!is_numeric(v.dtype)) {
+          fail(SQLRS_ERR_UNSUPPORTED, std::string("unsupported min/max type: ") + dtype_name(v.dtype));
+        }
         if (v.dtype != a.return_dtype)
           fail(SQLRS_ERR_UNSUPPORTED, std::string("unsupported min_max scalar type: ") + dtype_name(a.return_dtype));
         p.out_dtype = v.dtype;
         const bool is_min = a.func == SQLRS_AGG_MIN;
         p.value_word = add_word(is_min ? W_MIN_I64 : W_MAX_I64);
         p.f64_sortable = v.dtype == SQLRS_DT_FLOAT64;
+        p.utf8_packed = v.dtype == SQLRS_DT_UTF8;
         std::string vn = "o.a" + std::to_string(j), nn = "o.an" + std::to_string(j);
         std::string as_i64 = p.f64_sortable ? "sq_f64_sortable(" + vn + ")" : "(i64)" + vn;
         upd << "  if (" << nn << ") { i64* p = (i64*)(a + " << p.value_word << " * stride); const i64 x = " << as_i64 << "; if (x "
@@ -351,6 +362,19 @@ std::string AggOp::generate(const std::vector<ColInfo>& cols, Compiled& comp_ref
   }
   const int K = (int)keys.size(), W = (int)comp->words.size();
   if (W > 48) fail(SQLRS_ERR_UNSUPPORTED, "too many aggregate accumulators for one operator (max 48 words)");
+  // a column under MIN / MAX(Utf8) is pushed in its packed form: nothing else of the operator may read its ids
+  for (int c : comp->utf8_minmax_cols) {
+    auto reads = [&](const ExprCopy& e) {
+      for (const ExprNodeCopy& nd : e)
+        if (nd.op == SQLRS_OP_INPUT_REF && nd.index == c) return true;
+      return false;
+    };
+    bool other = reads(stage_pred);
+    for (const ExprCopy& g : group_by_) other = other || reads(g);
+    for (const AggSpec& a : aggs_)
+      if (!(a.func == SQLRS_AGG_MIN || a.func == SQLRS_AGG_MAX || a.func == SQLRS_AGG_COUNT)) other = other || reads(a.arg);
+    if (other) fail(SQLRS_ERR_UNSUPPORTED, "a Utf8 column under MIN / MAX that is also a group key, predicate input or SUM argument is not supported by the CUDA backend");
+  }
   std::vector<int> raw_ids;
   for (const Val& k : keys) raw_ids.push_back(prog.emit_raw_bits(k));
   // group identity: the reference's row hash when it IS the identity (hash-only, quirk K2); with key
@@ -623,10 +647,11 @@ void AggOp::ensure_partial_scratch(size_t entries, int K, size_t W) {
 }
 
 // ------------------------------------------------------------------ push
-void AggOp::push(const DBatch& batch) {
+void AggOp::push(const DBatch& batch_in) {
   if (distinct_) {
     distinct_->seen_batch = true;
     seen_batch_ = true;
+    const DBatch& batch = batch_in;
     if (distinct_->plain) distinct_->plain->push(batch);
     for (auto& it : distinct_->items) it.dedup->push(batch);
     last_path_ = "DISTINCT: GROUP BY (keys, argument) dedup + second-level aggregate" +
@@ -637,7 +662,36 @@ void AggOp::push(const DBatch& batch) {
   slot_list_complete_ = false;
   ctx_.activate();
   ctx_.reap();
-  Compiled& c = compiled_for(batch);
+  Compiled& c0 = compiled_for(batch_in);
+  // MIN / MAX over Utf8 columns: re-express what has been accumulated so far and this batch's ids in the string pool's
+  // CURRENT byte-wise ranks (the pool may have grown since the last batch), as rank << 32 | id
+  DBatch packed_batch;
+  if (!c0.utf8_minmax_cols.empty()) {
+    const std::vector<int32_t> ranks = StringPool::instance().ranks();
+    BufPtr rank_table = dev_alloc(ctx_, std::max<size_t>(ranks.size(), 1) * 4);
+    if (!ranks.empty()) SQ_CUDA(cudaMemcpyAsync(rank_table->p, ranks.data(), ranks.size() * 4, cudaMemcpyHostToDevice, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));  // `ranks` is a local vector
+    if (table_)
+      for (size_t j = 0; j < c0.aggs.size(); j++)
+        if (c0.aggs[j].utf8_packed)
+          launch_str_rerank((uint64_t*)table_->acc->p + (size_t)c0.aggs[j].value_word * table_->capacity, (const uint32_t*)table_->state->p, table_->capacity,
+                            (const int32_t*)rank_table->p, word_identity(c0.words[c0.aggs[j].value_word].op), ctx_.stream);
+    packed_batch = batch_in;
+    for (int col : c0.utf8_minmax_cols) {
+      if (col < 0 || col >= (int)packed_batch.cols.size()) fail(SQLRS_ERR_INTERNAL, "InputRef index out of bounds");
+      DCol& src = packed_batch.cols[(size_t)col];
+      if (src.dtype != SQLRS_DT_UTF8) continue;
+      DCol dst = make_col(ctx_, SQLRS_DT_UTF8, src.n, false);
+      launch_str_pack((const int64_t*)src.data, src.n, (const int32_t*)rank_table->p, (int64_t*)col_data(dst), ctx_.stream);
+      dst.valid = src.valid;
+      dst.keep_valid = src.keep_valid;
+      dst.null_count = src.null_count;
+      src = dst;
+    }
+    ctx_.defer([rank_table]() {});
+  }
+  const DBatch& batch = c0.utf8_minmax_cols.empty() ? batch_in : packed_batch;
+  Compiled& c = c0;
   if (key_dtypes_.empty()) key_dtypes_ = c.key_dtypes;
   seen_batch_ = true;
   const int64_t n = batch.n;
@@ -1057,7 +1111,14 @@ void AggOp::finish_host(ArrowArray* out, ArrowSchema* out_schema) {
   if (hint_sized_) settle();  // a deferred push_join: the group count decides the path below
   // many groups: finalise on the device and copy whole columns (the row-at-a-time host loop below cost 2.7 ms for
   // Q3' SF10's 113 k groups); few groups: one packed D2H and a trivial host loop beat the extra launches
-  if (distinct_ || (seen_batch_ && table_ && !counters_stale_ && groups_known_ > 1024)) {
+  bool any_utf8 = false;
+  if (!cache_.empty()) {
+    const Compiled& cc = *cache_.begin()->second;
+    for (int dt : cc.key_dtypes) any_utf8 |= dt == SQLRS_DT_UTF8;
+    for (const AggPlan& ap : cc.aggs) any_utf8 |= ap.out_dtype == SQLRS_DT_UTF8;
+  }
+  if (any_utf8 && table_ && counters_stale_) settle();
+  if (distinct_ || any_utf8 || (seen_batch_ && table_ && !counters_stale_ && groups_known_ > 1024)) {
     DBatch b = finish_device();
     export_batch_host(ctx_, b, out, out_schema);
     return;
@@ -1222,6 +1283,7 @@ DBatch AggOp::finish_device(DCol* first_row) {
     d.nvalid_word = (!is_count && p.nvalid_word >= 0) ? 3 + K + p.nvalid_word : -1;
     if (synth_row && !is_count) d.nvalid_word = 0;  // word 0 (hash) of the synthetic row is 0: SUM/MIN/MAX of nothing is NULL
     d.f64_sortable = p.f64_sortable ? 1 : 0;
+    d.utf8_packed = p.utf8_packed ? 1 : 0;
     if (is_count && c.words[p.value_word].op == W_COUNT_EPOCH) {
       d.count_epoch = 1;
       // SimpleAgg updates its single accumulator set with EVERY batch, empty ones included (simple_agg.rs:34-54)
@@ -1324,6 +1386,9 @@ DBatch AggOp::finish_distinct() {
 // ------------------------------------------------------------------ partial / final (multi-GPU)
 void AggOp::check_partial_supported() const {
   if (distinct_) fail(SQLRS_ERR_UNSUPPORTED, "partial/final DISTINCT aggregates");
+  if (!cache_.empty())
+    for (const AggPlan& ap : cache_.begin()->second->aggs)
+      if (ap.utf8_packed) fail(SQLRS_ERR_UNSUPPORTED, "partial/final MIN / MAX over Utf8 (the packed ranks are local to one process's string pool state)");
   if (opt_.count_mode == SQLRS_COUNT_REFERENCE_OVERWRITE)
     for (const AggSpec& a : aggs_)
       if (a.func == SQLRS_AGG_COUNT)

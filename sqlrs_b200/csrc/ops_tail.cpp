@@ -149,8 +149,23 @@ DBatch OrderOp::finish(Ctx& ctx) {
   const int64_t n = all.n;
   if (n >= (1LL << 31)) fail(SQLRS_ERR_UNSUPPORTED, "Order: more than 2^31 rows in one sort");
   std::vector<DCol> keys = eval_values(ctx, prog_.get(), order_by_, slot_, all, "order by");  // :30-43
-  for (const DCol& k : keys)
-    if (k.dtype == SQLRS_DT_UTF8) fail(SQLRS_ERR_UNSUPPORTED, "Utf8 sort keys are not supported by the CUDA backend yet");
+  // Utf8 sort keys: the column holds string pool ids; sort their byte-wise ranks (arrow sorts Utf8 by the strings' bytes)
+  BufPtr rank_table;
+  for (DCol& k : keys) {
+    if (k.dtype != SQLRS_DT_UTF8) continue;
+    if (!rank_table) {
+      const std::vector<int32_t> ranks = StringPool::instance().ranks();
+      rank_table = dev_alloc(ctx, std::max<size_t>(ranks.size(), 1) * 4);
+      if (!ranks.empty()) SQ_CUDA(cudaMemcpyAsync(rank_table->p, ranks.data(), ranks.size() * 4, cudaMemcpyHostToDevice, ctx.stream));
+      SQ_CUDA(cudaStreamSynchronize(ctx.stream));  // `ranks` is a local vector
+    }
+    DCol r = make_col(ctx, SQLRS_DT_INT64, n, false);
+    launch_str_rank((const int64_t*)k.data, n, (const int32_t*)rank_table->p, (int64_t*)col_data(r), ctx.stream);
+    r.valid = k.valid;
+    r.keep_valid = k.keep_valid;
+    r.null_count = k.null_count;
+    k = r;
+  }
   // ORDER BY ... LIMIT k (the plan passed the Limit down): select the k first rows instead of sorting all n.  Not for arrow's
   // single-column descending sort over a column with NULLs, which also reverses the run of NULL rows (sort_pass).
   bool topk = topk_applies(row_limit_);

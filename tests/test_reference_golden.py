@@ -237,9 +237,11 @@ def test_evaluator_input_ref_and_cast(lib):
     assert out.type == pa.int64() and out.to_pylist() == [1, 2, 3]
 
 
-# ---------------------------------------------------------------- oracle-only: Utf8 cases of the SLT files
-def test_slt_utf8_cases_oracle_only(oracle):
+# ---------------------------------------------------------------- Utf8 cases of the SLT files: on the CUDA library strings are
+# dictionary-encoded on ingest (string pool ids), ordered through the pool's byte-wise ranks, decoded on export
+def test_slt_utf8_cases(lib):
     """aggregation.slt:13-17,28-34 (max(last_name); group by state with an empty-string key)"""
+    oracle = lib
     emp = pa.RecordBatch.from_arrays(
         [pa.array([1, 2, 3, 4], pa.int64()), pa.array(["Hopkins", "Langford", "Travis", "Mill"]), pa.array(["CA", "CO", "CO", ""]),
          pa.array([12000, 10000, 11500, None], pa.int64())], names=["id", "last_name", "state", "salary"])
@@ -323,7 +325,8 @@ def test_project_field_names(lib):
     assert rows_of(out) == [(100, 2, True), (100, 3, True), (200, 4, True), (400, 5, True)]
 
 
-def test_slt_order_utf8_oracle_only(oracle):
+def test_slt_order_utf8(lib):
+    oracle = lib
     """order.slt:8-22: `order by state, id desc` -> 4 (empty) / 1 CA / 3 CO / 2 CO; `order by first_name desc offset 2 limit 1` -> 2"""
     emp = pa.RecordBatch.from_arrays(
         [pa.array([1, 2, 3, 4], pa.int64()), pa.array(["Bill", "Gregg", "John", "Von"]), pa.array(["CA", "CO", "CO", ""])], names=["id", "first_name", "state"])
@@ -368,8 +371,9 @@ def test_distinct_count_counts_null_as_a_value(lib):
     assert rows_of(out) == [(1, 1, 12000, 12000), (2, 1, 10000, 10000), (4, 1, 11500, 11500), (N, 1, N, N)]
 
 
-def test_slt_select_distinct_utf8_oracle_only(oracle):
+def test_slt_select_distinct_utf8(lib):
     """distinct.slt:1-7: select distinct state from employee -> CA, CO, (empty)"""
+    oracle = lib
     emp = pa.RecordBatch.from_arrays([pa.array(["CA", "CO", "CO", ""])], names=["state"])
     out = ex.try_collect(ex.HashAggExecutor([], [InputRef(0, ffi.DT_UTF8)], [emp], lib=oracle).execute())
     assert rows_of(out) == [("CA",), ("CO",), ("",)]
