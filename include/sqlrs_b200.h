@@ -60,6 +60,7 @@ extern "C" {
 #define SQLRS_ERR_UNSUPPORTED 3 /* the reference panics here (todo!/unimplemented!) or the GPU path lacks the dtype */
 #define SQLRS_ERR_INVALID_ARG 4
 #define SQLRS_ERR_CUDA 5
+#define SQLRS_ERR_STORAGE 6     /* ExecutorError::Storage(StorageError): io error / table not found (src/storage/mod.rs) */
 
 /* ---- the type universe of the v1 executor: ScalarValue, src/types/mod.rs:23-36 - */
 #define SQLRS_DT_NULL 0
@@ -67,7 +68,8 @@ extern "C" {
 #define SQLRS_DT_INT32 2
 #define SQLRS_DT_INT64 3
 #define SQLRS_DT_FLOAT64 4
-#define SQLRS_DT_UTF8 5 /* oracle: full support; CUDA library: SQLRS_ERR_UNSUPPORTED */
+#define SQLRS_DT_UTF8 5 /* CUDA library: dictionary-encoded on ingest (string pool ids in HBM), decoded on export; ordering comparisons in
+                           expressions (<, <=, >, >=) and MIN / MAX over Utf8 EXPRESSIONS return SQLRS_ERR_UNSUPPORTED */
 
 /* ---- expression bytecode: flattened BoundExpr, src/binder/expression/mod.rs:18-27
  * Postfix order: children first (left then right), then the node.  `Alias` is
@@ -81,6 +83,13 @@ extern "C" {
 #define SQLRS_OP_SUB 11      /* BinaryOperator::Minus     array_compute.rs:77 */
 #define SQLRS_OP_MUL 12      /* BinaryOperator::Multiply  array_compute.rs:78 */
 #define SQLRS_OP_DIV 13      /* BinaryOperator::Divide    array_compute.rs:79 (DivideByZero -> SQLRS_ERR_ARROW) */
+/* the v2 engine's arithmetic (src/function/scalar/arithmetic_function.rs:63-264: add_checked / subtract_checked /
+ * multiply_checked / divide_checked): as above, but an Int32 / Int64 result that does not fit its type ends the stream with
+ * SQLRS_ERR_ARROW ("Overflow happened on ...") instead of wrapping; Float64 is unchanged */
+#define SQLRS_OP_ADD_CHECKED 14
+#define SQLRS_OP_SUB_CHECKED 15
+#define SQLRS_OP_MUL_CHECKED 16
+#define SQLRS_OP_DIV_CHECKED 17
 #define SQLRS_OP_GT 20       /* gt_dyn     array_compute.rs:80 */
 #define SQLRS_OP_LT 21       /* lt_dyn     array_compute.rs:81 */
 #define SQLRS_OP_GE 22       /* gt_eq_dyn  array_compute.rs:82 */
@@ -367,6 +376,14 @@ int SQLRS_API(table_read)(sqlrs_table* t, int32_t batch_index, const int32_t* pr
                           struct ArrowArray* out, struct ArrowSchema* out_schema, int32_t* has_batch);
 void SQLRS_API(table_destroy)(sqlrs_table* t);
 /* every batch of the table, in order, as the batches of `table_slot` (what PhysicalTableScan pulls, table_scan.rs:16-35) */
+/* CsvTable (src/storage/csv.rs:99-235): the file parsed ON THE DEVICE into a resident table of batch_rows-row batches (1024 in
+ * the reference, :105; a multiple of 32 here).  has_header / delimiter as CsvConfig (:99-109); the schema is inferred from the first
+ * 10 records like arrow-csv's (Boolean / Int64 / Float64 / Utf8, every field nullable); bounds_offset / bounds_limit < 0 = no
+ * bounds, else Bounds = (offset, limit) over the whole file (:196-206); projection == NULL = every column.  Scan it with
+ * sqlrs_plan_push_table_resident, read it back with sqlrs_table_read. */
+int SQLRS_API(table_read_csv)(const char* path, int32_t has_header, int32_t delimiter, int64_t batch_rows, int64_t bounds_offset,
+                              int64_t bounds_limit, const int32_t* projection, int32_t n_projection, const sqlrs_options* options,
+                              sqlrs_table** out);
 int SQLRS_API(plan_push_table_resident)(sqlrs_plan* p, int32_t table_slot, sqlrs_table* t);
 
 /* ---- partial / final aggregation for plans sharded over several GPUs.  The plan

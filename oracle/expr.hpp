@@ -67,7 +67,11 @@ inline void merge_validity(Column& out, const Column& l, const Column& r) {
 inline int64_t wrap_int(int dtype, int64_t v) { return dtype == SQLRS_DT_INT32 ? (int64_t)(int32_t)v : v; }
 
 // arithmetic_op!, array_compute.rs:37-46
-inline ColPtr arithmetic(const Column& l, const Column& r, int op) {
+inline ColPtr arithmetic(const Column& l, const Column& r, int op_in) {
+  // the v2 engine's *_checked kernels (src/function/scalar/arithmetic_function.rs:66-71,147-152,219-224,244-249): an integer
+  // result that does not fit its type is ArrowError::ComputeError("Overflow happened on: ..."), Float64 is unchanged
+  const bool checked = op_in >= SQLRS_OP_ADD_CHECKED && op_in <= SQLRS_OP_DIV_CHECKED;
+  const int op = checked ? op_in - (SQLRS_OP_ADD_CHECKED - SQLRS_OP_ADD) : op_in;
   if (!is_numeric(l.dtype)) fail(SQLRS_ERR_UNSUPPORTED, "todo!: unsupported data type");  // :43
   if (r.dtype != l.dtype)
     fail(SQLRS_ERR_INTERNAL, "compute_op failed to downcast array");  // expect() at :23
@@ -102,6 +106,23 @@ inline ColPtr arithmetic(const Column& l, const Column& r, int op) {
           if (r.i[k] == -1) v = (int64_t)(0 - a);  // div_wrapping: MIN / -1 wraps
           else v = l.i[k] / r.i[k];
           break;
+      }
+      if (checked && out->is_valid(k)) {
+        bool ovf = false;
+        const int64_t x = l.i[k], y = r.i[k];
+        if (l.dtype == SQLRS_DT_INT32) {
+          const int64_t w = op == SQLRS_OP_ADD ? x + y : op == SQLRS_OP_SUB ? x - y : op == SQLRS_OP_MUL ? x * y : (y == -1 ? -x : 0);
+          ovf = w != (int64_t)(int32_t)w;
+        } else {
+          int64_t w;
+          switch (op) {
+            case SQLRS_OP_ADD: ovf = __builtin_add_overflow(x, y, &w); break;
+            case SQLRS_OP_SUB: ovf = __builtin_sub_overflow(x, y, &w); break;
+            case SQLRS_OP_MUL: ovf = __builtin_mul_overflow(x, y, &w); break;
+            default: ovf = x == INT64_MIN && y == -1; break;
+          }
+        }
+        if (ovf) fail(SQLRS_ERR_ARROW, "Compute error: Overflow happened on: " + std::to_string(x) + " and " + std::to_string(y));
       }
       out->i[k] = wrap_int(l.dtype, v);
     }
@@ -246,7 +267,7 @@ inline ColPtr eval_expr(const Expr& e, const Batch& batch) {
         stack.pop_back();
         ColPtr l = stack.back();
         stack.pop_back();
-        if (n.op >= SQLRS_OP_ADD && n.op <= SQLRS_OP_DIV) stack.push_back(arithmetic(*l, *r, n.op));
+        if (n.op >= SQLRS_OP_ADD && n.op <= SQLRS_OP_DIV_CHECKED) stack.push_back(arithmetic(*l, *r, n.op));
         else if (n.op >= SQLRS_OP_GT && n.op <= SQLRS_OP_NE) stack.push_back(comparison(*l, *r, n.op));
         else if (n.op == SQLRS_OP_AND || n.op == SQLRS_OP_OR) stack.push_back(kleene(*l, *r, n.op));
         else fail(SQLRS_ERR_UNSUPPORTED, "todo!: unsupported binary operator");  // array_compute.rs:88

@@ -22,6 +22,7 @@
 #include "../include/sqlrs_b200.h"
 #include "../include/sqlrs_tpch_spec.h"
 #include "arrow_io.hpp"
+#include "csv_reader.hpp"
 #include "ops.hpp"
 #include "tail_ops.hpp"
 
@@ -503,6 +504,17 @@ int sqlrs_oracle_table_append(sqlrs_table* t, ArrowArray* batch, const ArrowSche
     Batch b = consume_batch(batch, schema);
     if (!t->batches.empty() && t->batches[0].fields.size() != b.fields.size()) fail(SQLRS_ERR_ARROW, "table_append: schema mismatch");
     t->batches.push_back(std::move(b));
+  });
+}
+int sqlrs_oracle_table_read_csv(const char* path, int32_t has_header, int32_t delimiter, int64_t batch_rows, int64_t bounds_offset, int64_t bounds_limit,
+                                const int32_t* projection, int32_t n_projection, const sqlrs_options*, sqlrs_table** out) {
+  return guarded([&] {
+    if (!out || !path) fail(SQLRS_ERR_INVALID_ARG, "path / out is NULL");
+    std::vector<int> proj;
+    for (int32_t k = 0; projection && k < n_projection; k++) proj.push_back(projection[k]);
+    auto t = std::make_unique<sqlrs_table>();
+    t->batches = read_csv(path, has_header != 0, (char)delimiter, batch_rows > 0 ? batch_rows : 1024, bounds_offset, bounds_limit, proj);
+    *out = t.release();
   });
 }
 int64_t sqlrs_oracle_table_num_rows(sqlrs_table* t) {

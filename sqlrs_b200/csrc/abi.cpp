@@ -7,6 +7,7 @@
 #include "join.hpp"
 #include "kernels_aot.hpp"
 #include "ops.hpp"
+#include "csv.hpp"
 #include "plan.hpp"
 #include "tail.hpp"
 
@@ -424,6 +425,24 @@ int sqlrs_table_append(sqlrs_table* t, ArrowArray* batch, const ArrowSchema* sch
     }
     t->ctx.sync();  // the H2D copies are complete: any stream may read the batch from now on
     t->batches.push_back(std::move(b));
+  });
+}
+int sqlrs_table_read_csv(const char* path, int32_t has_header, int32_t delimiter, int64_t batch_rows, int64_t bounds_offset, int64_t bounds_limit,
+                         const int32_t* projection, int32_t n_projection, const sqlrs_options* options, sqlrs_table** out) {
+  return guarded([&] {
+    if (!out || !path) fail(SQLRS_ERR_INVALID_ARG, "path / out is NULL");
+    auto t = std::make_unique<sqlrs_table>(copy_options(options));
+    t->ctx.activate();
+    CsvOptions o;
+    o.has_header = has_header != 0;
+    o.delimiter = (char)delimiter;
+    o.batch_rows = batch_rows > 0 ? batch_rows : 1024;
+    o.bounds_offset = bounds_offset;
+    o.bounds_limit = bounds_limit;
+    for (int32_t k = 0; projection && k < n_projection; k++) o.projection.push_back(projection[k]);
+    t->batches = read_csv_device(t->ctx, path, o);
+    t->ctx.sync();
+    *out = t.release();
   });
 }
 int64_t sqlrs_table_num_rows(sqlrs_table* t) {

@@ -195,14 +195,41 @@ Val RowProgram::cast(const Val& a, int to) {
 
 // arithmetic_op!, array_compute.rs:37-46 — arrow add/subtract/multiply/divide: integers wrap,
 // NULL in either operand -> NULL, a valid zero divisor -> Err(DivideByZero).
-Val RowProgram::arithmetic(const Val& l, const Val& r, int op, int err_class) {
+bool g_checked_arithmetic_compiled = false;
+
+Val RowProgram::arithmetic(const Val& l, const Val& r, int op_in, int err_class) {
+  // *_checked (the v2 engine, arithmetic_function.rs:66-71,147-152,219-224,244-249): the same value, and an integer result
+  // that does not fit raises the row's error flag (reported as SQLRS_ERR_ARROW like arrow's "Overflow happened on ...")
+  const bool checked = op_in >= SQLRS_OP_ADD_CHECKED;
+  const int op = checked ? op_in - (SQLRS_OP_ADD_CHECKED - SQLRS_OP_ADD) : op_in;
   if (!is_numeric(l.dtype)) fail(SQLRS_ERR_UNSUPPORTED, "todo!: unsupported data type");
   if (r.dtype != l.dtype) fail(SQLRS_ERR_INTERNAL, "compute_op failed to downcast array");
   std::string a = vname(l.id), b = vname(r.id);
   bool mn = l.maybe_null || r.maybe_null;
   std::string valid = "(" + nname(l.id) + " && " + nname(r.id) + ")";
-  std::string key = "ar" + std::to_string(op) + "_" + std::to_string(l.id) + "_" + std::to_string(r.id);
+  std::string key = "ar" + std::to_string(op_in) + "_" + std::to_string(l.id) + "_" + std::to_string(r.id);
   std::string expr;
+  if (checked && l.dtype != SQLRS_DT_FLOAT64 && cse_.find(key) == cse_.end()) {
+    g_checked_arithmetic_compiled = true;
+    std::string ovf;
+    if (l.dtype == SQLRS_DT_INT32) {
+      const char* o = op == SQLRS_OP_ADD ? "+" : op == SQLRS_OP_SUB ? "-" : op == SQLRS_OP_MUL ? "*" : nullptr;
+      if (o) ovf = "((long long)" + a + " " + o + " (long long)" + b + " != (long long)(int)((long long)" + a + " " + o + " (long long)" + b + "))";
+      else ovf = "(" + a + " == (-2147483647 - 1) && " + b + " == -1)";
+    } else {
+      const std::string mx = "9223372036854775807LL", mn64 = "(-9223372036854775807LL - 1)";
+      switch (op) {
+        case SQLRS_OP_ADD: ovf = "((" + b + " > 0 && " + a + " > " + mx + " - " + b + ") || (" + b + " < 0 && " + a + " < " + mn64 + " - " + b + "))"; break;
+        case SQLRS_OP_SUB: ovf = "((" + b + " < 0 && " + a + " > " + mx + " + " + b + ") || (" + b + " > 0 && " + a + " < " + mn64 + " + " + b + "))"; break;
+        case SQLRS_OP_MUL:
+          ovf = "(__mul64hi(" + a + ", " + b + ") != ((long long)((unsigned long long)" + a + " * (unsigned long long)" + b + ") >> 63))";
+          break;
+        default: ovf = "(" + a + " == " + mn64 + " && " + b + " == -1)"; break;
+      }
+    }
+    body_ << "  e" << err_class << " |= (" << valid << " && " << ovf << ");\n";
+    err_used_[err_class] = true;
+  }
   if (l.dtype == SQLRS_DT_FLOAT64) {
     const char* o = op == SQLRS_OP_ADD ? "+" : op == SQLRS_OP_SUB ? "-" : op == SQLRS_OP_MUL ? "*" : "/";
     // __d*_rn: keep the reference's separate multiply/add roundings (no FMA contraction)
@@ -298,7 +325,7 @@ Val RowProgram::compile(const ExprCopy& e, int err_class) {
         stack.pop_back();
         Val l = stack.back();
         stack.pop_back();
-        if (n.op >= SQLRS_OP_ADD && n.op <= SQLRS_OP_DIV) stack.push_back(arithmetic(l, r, n.op, err_class));
+        if (n.op >= SQLRS_OP_ADD && n.op <= SQLRS_OP_DIV_CHECKED) stack.push_back(arithmetic(l, r, n.op, err_class));
         else if (n.op >= SQLRS_OP_GT && n.op <= SQLRS_OP_NE) stack.push_back(comparison(l, r, n.op));
         else if (n.op == SQLRS_OP_AND || n.op == SQLRS_OP_OR) stack.push_back(kleene(l, r, n.op));
         else fail(SQLRS_ERR_UNSUPPORTED, "todo!: unsupported binary operator");

@@ -93,6 +93,12 @@ class RowProgram {
   bool err_used_[2] = {false, false};
 };
 
+// set once a *_checked operator has been compiled: the operators' "row error" flag then also stands for integer overflow
+extern bool g_checked_arithmetic_compiled;
+inline const char* arithmetic_error_text() {
+  return g_checked_arithmetic_compiled ? "Compute error: Overflow happened (checked arithmetic) or Divide by zero error" : "Divide by zero error";
+}
+
 // C literal helpers
 std::string lit_i64(int64_t v);
 std::string lit_f64_bits(int64_t bits);

@@ -630,7 +630,7 @@ void AggOp::read_counters(uint32_t* out4) {
   if (out4[2] & 2u) fail(SQLRS_ERR_INTERNAL, "group table overflow (internal sizing error)");
   if (out4[3] & 1u) {
     SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 3, 0, 4, ctx_.stream));
-    fail(SQLRS_ERR_ARROW, "Divide by zero error (aggregate argument)");
+    fail(SQLRS_ERR_ARROW, std::string(arithmetic_error_text()) + " (aggregate argument)");
   }
 }
 
@@ -1000,7 +1000,7 @@ void AggOp::push_join(const DBatch& probe, JoinOp& join, const ExprCopy& probe_p
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
     scan_kernel_ms_ += timer.elapsed_ms();
     scan_kernel_launches_ += timer.enabled ? 1 : 0;
-    if (hc[3] & 1u) fail(SQLRS_ERR_ARROW, "Divide by zero error (aggregate argument)");
+    if (hc[3] & 1u) fail(SQLRS_ERR_ARROW, std::string(arithmetic_error_text()) + " (aggregate argument)");
     if (!(hc[2] & 2u)) break;
     cap *= 4;
   }

@@ -45,7 +45,7 @@ void check_error_flag(Ctx& ctx, const BufPtr& err, const char* what) {
   uint32_t flag = 0;
   SQ_CUDA(cudaMemcpyAsync(&flag, err->p, 4, cudaMemcpyDeviceToHost, ctx.stream));
   SQ_CUDA(cudaStreamSynchronize(ctx.stream));
-  if (flag & 1u) fail(SQLRS_ERR_ARROW, std::string("Divide by zero error") + (what ? std::string(" (") + what + ")" : ""));
+  if (flag & 1u) fail(SQLRS_ERR_ARROW, std::string(arithmetic_error_text()) + (what ? std::string(" (") + what + ")" : ""));
 }
 
 // ------------------------------------------------------------------ EvalProgram

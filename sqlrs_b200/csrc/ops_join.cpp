@@ -482,7 +482,7 @@ bool JoinOp::probe(const DBatch& right, DBatch* result) {
     SQ_CUDA(cudaMemcpyAsync(&host.total, total_d, 8, cudaMemcpyDeviceToHost, ctx_.stream));
     SQ_CUDA(cudaMemcpyAsync(&host.err, err->p, 4, cudaMemcpyDeviceToHost, ctx_.stream));
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
-    if (host.err & 1u) fail(SQLRS_ERR_ARROW, "Divide by zero error (join key)");
+    if (host.err & 1u) fail(SQLRS_ERR_ARROW, std::string(arithmetic_error_text()) + " (join key)");
     total = (int64_t)host.total;
     if (total >= (1LL << 32)) fail(SQLRS_ERR_UNSUPPORTED, "join output of one probe batch exceeds 2^32 rows");
     li = dev_alloc(ctx_, (size_t)std::max<int64_t>(total, 1) * 8);
@@ -608,7 +608,7 @@ bool JoinChainOp::check_flags() {
     }
   }
   const uint32_t* f = host_->flags;
-  if (f[3]) fail(SQLRS_ERR_ARROW, "Divide by zero error (join key)");
+  if (f[3]) fail(SQLRS_ERR_ARROW, std::string(arithmetic_error_text()) + " (join key)");
   if (f[0] || f[2]) {  // a repeated key needs the CSR lists, an unrepresentable key the slot_rep layout: not this path
     disabled_ = true;
     hint_inserted_ = -1;
@@ -700,7 +700,7 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
     launch(cnt, step);
     SQ_CUDA(cudaMemcpyAsync(host_, status->p, 24, cudaMemcpyDeviceToHost, ctx_.stream));
     SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
-    if (host_->flags[3]) fail(SQLRS_ERR_ARROW, "Divide by zero error (join key)");
+    if (host_->flags[3]) fail(SQLRS_ERR_ARROW, std::string(arithmetic_error_text()) + " (join key)");
     est = (int64_t)((double)host_->inserted * (double)step * 1.25) + 4096;
     SQ_CUDA(cudaMemsetAsync(status->p, 0, 32, ctx_.stream));
   }

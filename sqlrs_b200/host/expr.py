@@ -20,8 +20,22 @@ _OPS = {
     "+": ffi.OP_ADD, "-": ffi.OP_SUB, "*": ffi.OP_MUL, "/": ffi.OP_DIV,
     ">": ffi.OP_GT, "<": ffi.OP_LT, ">=": ffi.OP_GE, "<=": ffi.OP_LE, "=": ffi.OP_EQ, "<>": ffi.OP_NE,
     "AND": ffi.OP_AND, "OR": ffi.OP_OR,
+    # the v2 engine's checked arithmetic (src/function/scalar/arithmetic_function.rs): integer overflow is an error
+    "+checked": ffi.OP_ADD_CHECKED, "-checked": ffi.OP_SUB_CHECKED, "*checked": ffi.OP_MUL_CHECKED, "/checked": ffi.OP_DIV_CHECKED,
 }
-_ARITH = {"+", "-", "*", "/"}
+_ARITH = {"+", "-", "*", "/", "+checked", "-checked", "*checked", "/checked"}
+
+
+def fold_and(predicates):
+    """The v2 Filter's predicate: its expressions folded into one AND conjunction, left to right
+    (BoundConjunctionExpression::try_build_and_conjunction_expression, src/execution/physical_plan/physical_filter.rs:11-16)."""
+    predicates = list(predicates)
+    if not predicates:
+        raise ValueError("fold_and: a Filter has at least one predicate")
+    out = predicates[0]
+    for p in predicates[1:]:
+        out = BinaryOp("AND", out, p, ffi.DT_BOOL)
+    return out
 
 
 class BoundExpr:
@@ -146,7 +160,7 @@ class BinaryOp(BoundExpr):
 
     def eval_field(self, schema):
         l, r = self.left.eval_field(schema), self.right.eval_field(schema)
-        return pa.field(f"{l.name}{self.op}{r.name}", ffi.pa_type_of(self.return_dtype), True)
+        return pa.field(f"{l.name}{self.op.replace('checked', '')}{r.name}", ffi.pa_type_of(self.return_dtype), True)
 
     def _emit(self, out):
         self.left._emit(out)

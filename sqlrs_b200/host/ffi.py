@@ -15,10 +15,11 @@ import struct
 import pyarrow as pa
 
 # ---- constants (mirror include/sqlrs_b200.h) ---------------------------------------------------
-OK, ERR_INTERNAL, ERR_ARROW, ERR_UNSUPPORTED, ERR_INVALID_ARG, ERR_CUDA = range(6)
+OK, ERR_INTERNAL, ERR_ARROW, ERR_UNSUPPORTED, ERR_INVALID_ARG, ERR_CUDA, ERR_STORAGE = range(7)
 DT_NULL, DT_BOOL, DT_INT32, DT_INT64, DT_FLOAT64, DT_UTF8 = range(6)
 OP_INPUT_REF, OP_CONSTANT, OP_CAST = 1, 2, 3
 OP_ADD, OP_SUB, OP_MUL, OP_DIV = 10, 11, 12, 13
+OP_ADD_CHECKED, OP_SUB_CHECKED, OP_MUL_CHECKED, OP_DIV_CHECKED = 14, 15, 16, 17
 OP_GT, OP_LT, OP_GE, OP_LE, OP_EQ, OP_NE = 20, 21, 22, 23, 24, 25
 OP_AND, OP_OR = 30, 31
 AGG_COUNT, AGG_SUM, AGG_MIN, AGG_MAX = 0, 1, 2, 3
@@ -226,6 +227,7 @@ _SIGNATURES = {
     "table_num_batches": (C.c_int32, [C.c_void_p]),
     "table_read": (C.c_int, [C.c_void_p, C.c_int32, P(C.c_int32), C.c_int32, P(ArrowArray), P(ArrowSchema), P(C.c_int32)]),
     "table_destroy": (None, [C.c_void_p]),
+    "table_read_csv": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, P(C.c_int32), C.c_int32, P(Options), P(C.c_void_p)]),
     "plan_push_table_resident": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "plan_execute": (C.c_int, [C.c_void_p]),
     "plan_next": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema), P(C.c_int32)]),

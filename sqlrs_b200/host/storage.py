@@ -66,6 +66,24 @@ class InMemoryTable:
             pass
 
 
+class CsvTable(InMemoryTable):
+    """CsvTable (src/storage/csv.rs:111-170): `CsvStorage::create_csv_table(id, filepath)` infers the schema from the file and
+    scans it in 1024-row batches; here the file is parsed on the device once (sqlrs_table_read_csv) and the table is resident.
+    `bounds` = (offset, limit) over the whole table and `projection` as in `Table::read(bounds, projection)` (:163-170)."""
+
+    def __init__(self, lib: ffi.Library, table_id: str, filepath: str, options=None, has_header: bool = True, delimiter: str = ",", batch_size: int = 1024,
+                 bounds=None, projection: Optional[Sequence[int]] = None):
+        self.lib, self.id, self.filepath = lib, table_id, filepath
+        self.handle = C.c_void_p()
+        opts = options if options is not None else lib.options()
+        proj = (C.c_int32 * len(projection))(*projection) if projection is not None else None
+        off, lim = bounds if bounds is not None else (-1, -1)
+        lib.check(lib.table_read_csv(filepath.encode(), int(has_header), ord(delimiter), batch_size, off, lim, proj, len(projection) if projection is not None else 0,
+                                     C.byref(opts), C.byref(self.handle)))
+        first = next(iter(self.read()), None)
+        self.schema = first.schema if first is not None else None
+
+
 class InMemoryStorage:
     """InMemoryStorage (memory.rs:9-60): id -> table"""
 
@@ -76,6 +94,10 @@ class InMemoryStorage:
 
     def create_mem_table(self, table_id: str, data: Sequence[pa.RecordBatch]) -> None:
         self.tables[table_id] = InMemoryTable(self.lib, table_id, list(data), self.options)
+
+    def create_csv_table(self, table_id: str, filepath: str, **kw) -> None:
+        """CsvStorage::create_csv_table (csv.rs:60-72)"""
+        self.tables[table_id] = CsvTable(self.lib, table_id, filepath, self.options, **kw)
 
     def get_table(self, table_id: str) -> InMemoryTable:
         try:

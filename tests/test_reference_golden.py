@@ -445,3 +445,32 @@ def test_plan_cross_join_then_filter(lib):
     out = p.run()
     p.close()
     assert rows_of(out) == [(0, 4, 7, 10, 2, 7), (0, 4, 7, 20, 2, 5), (0, 4, 7, 30, 3, 6), (0, 4, 7, 40, 4, 6)]
+
+
+# ---------------------------------------------------------------- v2 engine expression surface
+def test_v2_checked_arithmetic_scalar_function_slt(lib):
+    """tests/slt/scalar_function.slt:1-37 (a+a, a-a, a*a, a/a over (1),(2),(3),(NULL)) through the *_checked operators of
+    src/function/scalar/arithmetic_function.rs; integer overflow is an error there (add_checked & co), not a wrap"""
+    from sqlrs_b200.host.expr import fold_and
+
+    b = batch(["a"], [1, 2, 3, None], types=[pa.int32()])
+    a = InputRef(0, I32)
+    for op, want in (("+checked", [2, 4, 6, N]), ("-checked", [0, 0, 0, N]), ("*checked", [1, 4, 9, N]), ("/checked", [1, 1, 1, N])):
+        assert ex.eval_column(BinaryOp(op, a, a, I32), b, lib=lib).to_pylist() == want
+    big = batch(["x", "y"], [2**63 - 1, 5, -2**63], [1, 6, -1])
+    x, y = InputRef(0, I64), InputRef(1, I64)
+    assert ex.eval_column(BinaryOp("+", x, y, I64), big, lib=lib).to_pylist() == [-2**63, 11, 2**63 - 1]  # v1: wrapping (array_compute.rs:76)
+    for op in ("+checked", "*checked", "/checked"):
+        with pytest.raises(ffi.ExecutorError) as e:
+            ex.eval_column(BinaryOp(op, x, y, I64), big, lib=lib)
+        assert e.value.code == ffi.ERR_ARROW
+    ok = batch(["x", "y"], [2**62, 5, -2**62], [2**62 - 1, 6, -2**62])
+    assert ex.eval_column(BinaryOp("+checked", x, y, I64), ok, lib=lib).to_pylist() == [2**63 - 1, 11, -2**63]
+    small = batch(["x", "y"], [2**31 - 1, 7], [1, 1], types=[pa.int32(), pa.int32()])
+    with pytest.raises(ffi.ExecutorError):
+        ex.eval_column(BinaryOp("+checked", InputRef(0, I32), InputRef(1, I32), I32), small, lib=lib)
+    # the v2 Filter folds its predicates into one AND conjunction (physical_filter.rs:11-16)
+    t = batch(["a", "b"], [1, 2, 3, 4, None], [10, 20, 30, None, 50])
+    preds = [bind_binary_op(InputRef(0, I64), ">", Constant(1)), bind_binary_op(InputRef(1, I64), "<", Constant(40))]
+    out = ex.try_collect(ex.FilterExecutor(fold_and(preds), [t], lib=lib).execute())
+    assert rows_of(out) == [(2, 20), (3, 30)]
