@@ -100,9 +100,12 @@ def test_eval_program_compiles_and_type_errors_surface_without_a_gpu(cuda_lib):
             cuda_lib.check(cuda_lib.debug_compile_eval(bad.ptr, bad.n, 0, C.byref(sch), 0, None))
         assert err.value.code == ffi.ERR_INTERNAL
         utf8 = ffi.export_schema(pa.schema([pa.field("s", pa.utf8())]))
-        one = ExprArray([InputRef(0, ffi.DT_UTF8)])
+        # Utf8 columns are string-pool ids on the device: equality compiles, an ORDERING comparison of strings is refused
+        one = ExprArray([BinaryOp("=", InputRef(0, ffi.DT_UTF8), Constant("CO"), ffi.DT_BOOL)])
+        cuda_lib.check(cuda_lib.debug_compile_eval(one.ptr, one.n, 0, C.byref(utf8), 1, None))
+        less = ExprArray([BinaryOp("<", InputRef(0, ffi.DT_UTF8), Constant("CO"), ffi.DT_BOOL)])
         with pytest.raises(ffi.ExecutorError) as err:
-            cuda_lib.check(cuda_lib.debug_compile_eval(one.ptr, one.n, 0, C.byref(utf8), 0, None))
+            cuda_lib.check(cuda_lib.debug_compile_eval(less.ptr, less.n, 0, C.byref(utf8), 0, None))
         assert err.value.code == ffi.ERR_UNSUPPORTED
         ffi.release_schema(utf8)
     finally:
