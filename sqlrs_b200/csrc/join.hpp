@@ -60,6 +60,9 @@ class JoinOp {
   // (8 x u32 + u64, pinned host memory) on the stream for the caller to check.  Only taken for the kv layout.
   void set_build_hint(int64_t kept_rows, uint32_t* pinned) { hint_kept_ = kept_rows; hint_pinned_ = pinned; }
   bool sealed_deferred() const { return sealed_deferred_; }
+  // plan executor: one build batch, one compared key, no Left / Full tail -> scan + Filter + hash + insert in ONE kernel
+  // (csrc/jit/joinbuild.cuh) at seal(); anything else (several batches, repeated keys, ...) takes the materialising path
+  void enable_fused_build();
   int64_t build_rows() const;
   // generated CUDA of the fused probe kernel for probe batches of that schema (diagnostics / build check, no GPU)
   std::string debug_probe_source(const std::vector<ColInfo>& probe_cols, const ExprCopy& probe_pred) const;
@@ -67,6 +70,8 @@ class JoinOp {
  private:
   struct Impl;
   DBatch build_batch(const DBatch& right, const int64_t* li, bool li_nullable, const uint32_t* ri, int64_t m);
+  void eval_push(const DBatch& batch);  // the materialising build: key / hash / keep columns of one batch
+  bool seal_fused();
   void check_schema(DBatch& b);
 
   Ctx ctx_;

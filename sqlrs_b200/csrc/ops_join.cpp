@@ -132,6 +132,9 @@ struct JoinOp::Impl {
   int key0_dtype = 0;  // static dtype of the first key expression (kv layout)
   std::vector<bool> needed;  // per output field; empty = all
   std::vector<BufPtr> adopted;  // adopt_build: the buffers the view points into
+  bool fused_build = false;      // enable_fused_build
+  std::vector<DBatch> stashed;   // build batches not evaluated yet (fused build)
+  JitKernel* build_kernel = nullptr;
 };
 
 // outputs: [hash, (raw bits x K, null mask)?, (keep mask of the fused Filter)?]
@@ -178,10 +181,119 @@ void JoinOp::set_side_predicates(ExprCopy build_pred, ExprCopy probe_pred) {
 void JoinOp::set_needed_columns(std::vector<bool> needed) { impl_->needed = std::move(needed); }
 
 // hash_join.rs:161-181
+void JoinOp::enable_fused_build() {
+  const bool mk = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
+  impl_->fused_build = mk && left_keys_.size() == 1 && (join_type_ == SQLRS_JOIN_INNER || join_type_ == SQLRS_JOIN_RIGHT) && !std::getenv("SQLRS_B200_NO_KV") &&
+                       !std::getenv("SQLRS_B200_NO_FUSED_BUILD");
+}
+
+// scan + Filter + key hash + insert of the ONE stashed build batch in one kernel; false = take the materialising path
+bool JoinOp::seal_fused() {
+  Impl& im = *impl_;
+  if (im.stashed.size() != 1 || im.stashed[0].n <= 0) return false;
+  const DBatch& b = im.stashed[0];
+  const int64_t n = b.n;
+  std::vector<ColInfo> cols = col_infos(b);
+  int key_dtype = 0;
+  {
+    RowProgram p(cols);
+    key_dtype = p.compile(left_keys_[0], im.build_pred.empty() ? 0 : 1).dtype;
+  }
+  if (key_dtype == SQLRS_DT_NULL) return false;
+  if (!im.build_kernel) {
+    const std::string src = gen_input_decls(cols) + gen_probe_program(cols, left_keys_, im.build_pred, true).src;
+    im.build_kernel = jit_get("join_table+joinbuild", src, "sq_joinbuild_kernel");
+  }
+  std::vector<const void*> in_blob(2 * std::max<size_t>(b.cols.size(), 1), nullptr);
+  for (size_t c = 0; c < b.cols.size(); c++) {
+    in_blob[c] = b.cols[c].data;
+    in_blob[std::max<size_t>(b.cols.size(), 1) + c] = b.cols[c].valid;
+  }
+  struct BuildOut {
+    uint64_t* kv;
+    uint32_t* bloom;
+    uint32_t capacity, bloom_mask;
+    uint32_t* flags;
+    unsigned long long* kept;
+  };
+  BufPtr status = dev_alloc_zero(ctx_, 40);  // u32 flags[8] + u64 kept
+  const int sms = device_sm_count(ctx_.device);
+  const int per_sm = std::max(1, jit_max_blocks_per_sm(im.build_kernel, 256, 0));
+  auto launch = [&](BuildOut out) {
+    int64_t n_arg = n;
+    void* args[] = {in_blob.data(), &n_arg, &out};
+    const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(div_up(n, 256 * 4), 1), (int64_t)sms * per_sm);
+    KernelEvent ev(opt_.flags, ctx_.stream, out.kv ? "sq_joinbuild_kernel" : "sq_joinbuild_kernel (count)");
+    jit_launch(im.build_kernel, grid, 256, 0, ctx_.stream, args);
+  };
+  const bool deferred = hint_pinned_ && hint_kept_ >= 0;
+  int64_t n_insert = 0;
+  if (deferred) {
+    n_insert = hint_kept_ + hint_kept_ / 8 + 64;
+  } else {  // how many rows does the Filter keep?  One count-only pass over the Filter / key columns
+    launch(BuildOut{nullptr, nullptr, 0, 0, (uint32_t*)status->p, (unsigned long long*)((uint32_t*)status->p + 8)});
+    unsigned long long kept = 0;
+    SQ_CUDA(cudaMemcpyAsync(&kept, (uint32_t*)status->p + 8, 8, cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    n_insert = (int64_t)kept;
+    SQ_CUDA(cudaMemsetAsync(status->p, 0, 40, ctx_.stream));
+  }
+  uint64_t cap = 1024;
+  while (cap < 2ULL * (uint64_t)n_insert) cap <<= 1;
+  if (cap > (1ULL << 30)) return false;
+  BufPtr kv = dev_alloc(ctx_, cap * 16);
+  SQ_CUDA(cudaMemsetAsync(kv->p, 0xff, cap * 16, ctx_.stream));
+  const uint32_t bloom_words = join_bloom_words(n_insert);
+  BufPtr bloom = dev_alloc_zero(ctx_, (size_t)bloom_words * 4);
+  launch(BuildOut{(uint64_t*)kv->p, (uint32_t*)bloom->p, (uint32_t)cap, bloom_words - 1, (uint32_t*)status->p, (unsigned long long*)((uint32_t*)status->p + 8)});
+  if (deferred) {  // unique keys assumed; the caller checks {flags[0..5], kept} once the stream has been synchronised
+    SQ_CUDA(cudaMemcpyAsync(hint_pinned_, status->p, 40, cudaMemcpyDeviceToHost, ctx_.stream));
+    sealed_deferred_ = true;
+  } else {
+    uint32_t flags[10] = {0};
+    SQ_CUDA(cudaMemcpyAsync(flags, status->p, 40, cudaMemcpyDeviceToHost, ctx_.stream));
+    SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    if (flags[3]) fail(SQLRS_ERR_ARROW, std::string(arithmetic_error_text()) + " (join key)");
+    if (flags[0] || flags[4] || flags[5]) return false;  // repeated key / unrepresentable key: the materialising path handles those
+    if (hint_pinned_) std::memcpy(hint_pinned_, flags, 40);
+  }
+  ctx_.defer([status]() {});
+  im.left_single = b;
+  im.slot_rep = kv;
+  im.bloom = bloom;
+  im.capacity = (uint32_t)cap;
+  im.max_count = 1;
+  JoinTableView& v = im.view;
+  v = JoinTableView{};
+  v.capacity = (uint32_t)cap;
+  v.kv = (uint64_t*)kv->p;
+  v.kv_dtype = key_dtype;
+  v.slot_rep = (int64_t*)kv->p + 1;
+  v.rep_stride = 2;
+  v.n_build = n;
+  v.n_keys = 1;
+  v.match_keys = 1;
+  v.bloom = (uint32_t*)bloom->p;
+  v.bloom_mask = bloom_words - 1;
+  v.unique = 1;
+  v.n_inserted = n_insert;
+  im.stashed.clear();
+  return true;
+}
+
 void JoinOp::build_push(const DBatch& batch) {
   Trace tr("join.build_push", ctx_.stream);
   if (impl_->sealed) fail(SQLRS_ERR_INVALID_ARG, "hash_join: build_push after probe");
   ctx_.reap();
+  if (impl_->fused_build) {
+    impl_->stashed.push_back(batch);
+    impl_->left_rows += batch.n;
+    return;
+  }
+  eval_push(batch);
+}
+
+void JoinOp::eval_push(const DBatch& batch) {
   const bool mk = opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY;
   if (!impl_->left_prog) impl_->left_prog = std::make_unique<EvalProgram>(key_request(left_keys_, mk, impl_->build_pred));
   EvalResult keys;
@@ -205,6 +317,14 @@ void JoinOp::seal() {
   if (im.sealed) return;
   Trace tr("join.seal", ctx_.stream);
   im.sealed = true;
+  if (!im.stashed.empty()) {
+    if (seal_fused()) return;
+    std::vector<DBatch> batches = std::move(im.stashed);  // the materialising path after all
+    im.stashed.clear();
+    im.left_rows = 0;
+    sealed_deferred_ = false;
+    for (const DBatch& b : batches) eval_push(b);
+  }
   if (im.left_batches.empty()) return;
   const int64_t n = im.left_rows;
   const int K = (int)left_keys_.size();
@@ -601,6 +721,7 @@ bool JoinChainOp::check_flags() {
   if (j1_deferred_) {  // join 1 was sealed without a synchronisation: repeated key / unrepresentable key / table full?
     j1_deferred_ = false;
     const uint32_t* g = host_->j1_flags;
+    if (g[3]) fail(SQLRS_ERR_ARROW, std::string(arithmetic_error_text()) + " (join key)");
     if (g[0] || g[4] || g[5]) {
       hint_inserted_ = -1;  // the next run goes the synchronised way (which handles all of these)
       hint_j1_kept_ = -1;

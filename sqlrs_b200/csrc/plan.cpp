@@ -154,6 +154,7 @@ bool Plan::feed_fused_join(AggOp& op, int child, const ExprCopy& agg_fused_pred,
   mark_refs(probe_pred, right_need);
   JoinOp j(jn.join_type, jn.left_keys, jn.right_keys, jn.predicate, jn.join_fields, opt_);
   j.set_side_predicates(build_pred, ExprCopy());
+  j.enable_fused_build();
   bool chained = false;
   if (build_pred.empty() && nodes_[left].kind == SQLRS_NODE_HASH_JOIN) chained = try_chain(child, left, left_need, j);
   if (chained) {
@@ -197,6 +198,7 @@ bool Plan::try_chain(int jidx, int left, const Needed& left_need, JoinOp& j) {
   mark_refs(build_pred1, l1_need);
   JoinOp jo1(j1.join_type, j1.left_keys, j1.right_keys, j1.predicate, j1.join_fields, opt_);
   jo1.set_side_predicates(build_pred1, ExprCopy());
+  jo1.enable_fused_build();
   for (const DBatch& b : run(l1, l1_need)) jo1.build_push(b);
   if (!j2.chain_op->run(jo1, it->second[0], probe_pred1, j2.left_keys[0], j)) return false;
   if (j2.chain_op->pending()) pending_chains_.push_back(j2.chain_op.get());
@@ -524,6 +526,7 @@ std::vector<DBatch> Plan::run(int idx, const Needed& needed) {
         mark_refs(probe_pred, right_need);
       }
       j.set_side_predicates(build_pred, probe_pred);
+      if (fusion()) j.enable_fused_build();
       description_ += std::string("[HashJoin") + (build_pred.empty() && probe_pred.empty() ? "" : " + fused side Filter") +
                       ": CSR hash build, probe count/scan/write, pruned gathers] ";
       for (const DBatch& b : run(left, left_need)) j.build_push(b);

@@ -408,9 +408,15 @@ def broadcast_rows(plan, group: TorchGroup, schema: pa.Schema) -> DeviceBatch:
     _check_stream(plan, group)
     recv = torch.empty((W, ncols, most), dtype=torch.int64, device=group.device)
     group.dist.all_gather_into_tensor(recv, send)
-    cols = [torch.cat([recv[r, c, :counts[r]] for r in range(W)]) for c in range(ncols)]
+    total = int(sum(counts))
+    packed = torch.empty((ncols, max(total, 1)), dtype=torch.int64, device=group.device)
+    off = 0
+    for r in range(W):  # one strided copy per rank (all columns at once), rank order = row order
+        if counts[r]:
+            packed[:, off:off + counts[r]] = recv[r, :, :counts[r]]
+            off += counts[r]
     dev = group.device.index if group.device.index is not None else 0
-    return DeviceBatch(schema, cols, int(sum(counts)), dev)
+    return DeviceBatch(schema, [packed[c, :total] for c in range(ncols)], total, dev)
 
 
 def key_ranges_copartitioned(group: TorchGroup, build_range, probe_range) -> bool:
