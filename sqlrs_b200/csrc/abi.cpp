@@ -658,6 +658,8 @@ int sqlrs_debug_compile_joinprobe(const sqlrs_expr* right_keys, int32_t n_keys, 
     JoinOp op(SQLRS_JOIN_INNER, copy_exprs(right_keys, n_keys), copy_exprs(right_keys, n_keys), {}, {}, opt);
     std::string gen = op.debug_probe_source(cols_of_schema(probe_schema), pp);
     if (compile) jit_compile_to_cubin("join_table+joinprobe", gen, nullptr);
+    // the fused BUILD kernel (csrc/jit/joinbuild.cuh) takes the same generated program for the build side's Filter + key
+    if (compile && n_keys == 1 && opt.match_mode == SQLRS_MATCH_HASH_AND_KEY) jit_compile_to_cubin("join_table+joinbuild", gen, nullptr);
     if (source_out) *source_out = dup_string(jit_full_source("join_table+joinprobe", gen));
   });
 }

@@ -222,7 +222,7 @@ bool JoinOp::seal_fused() {
   auto launch = [&](BuildOut out) {
     int64_t n_arg = n;
     void* args[] = {in_blob.data(), &n_arg, &out};
-    const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(div_up(n, 256 * 4), 1), (int64_t)sms * per_sm);
+    const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(div_up(n, 256 * 8), 1), (int64_t)sms * per_sm);  // 256 threads x 8 rows per trip
     KernelEvent ev(opt_.flags, ctx_.stream, out.kv ? "sq_joinbuild_kernel" : "sq_joinbuild_kernel (count)");
     jit_launch(im.build_kernel, grid, 256, 0, ctx_.stream, args);
   };
