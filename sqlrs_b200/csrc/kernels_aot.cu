@@ -376,12 +376,9 @@ __global__ void __launch_bounds__(kBlock) k_table_merge_packed(TableView t, int 
       atomicOr(&t.counters[2], 2u);
       continue;
     }
-    // first-appearance order: the smaller global row id wins; with hash-only identity its keys win too
-    const unsigned long long old = atomicMin((unsigned long long*)&t.min_row[slot], (unsigned long long)row[1]);
-    if (!match_keys && row[1] < old) {
-      for (int k = 0; k < n_keys; k++) t.keys[(size_t)k * t.capacity + slot] = row[3 + k];
-      t.knull[slot] = kn;
-    }
+    // first-appearance order: the smaller global row id wins; with hash-only identity its keys win too — written by
+    // k_table_merge_fixkeys once every min_row is final (one writer per slot, no interleaving of two key tuples)
+    atomicMin((unsigned long long*)&t.min_row[slot], (unsigned long long)row[1]);
     for (int w = 0; w < n_acc; w++) {
       const uint64_t x = row[3 + n_keys + w];
       uint64_t* p = &t.acc[(size_t)w * t.capacity + slot];
@@ -407,6 +404,35 @@ __global__ void __launch_bounds__(kBlock) k_table_merge_packed(TableView t, int 
   }
 }
 
+// hash-only identity (reference quirk K2): after the merge, the partial group that supplied a slot's final min_row
+// rewrites the slot's key tuple.  Global row ids are unique, so at most one source row matches per slot.
+__global__ void __launch_bounds__(kBlock) k_table_merge_fixkeys(TableView t, int n_keys, int n_acc, const uint64_t* __restrict__ src, int n_bufs,
+                                                                 unsigned long long cap_rows) {
+  const int words = 3 + n_keys + n_acc;
+  const uint32_t mask = t.capacity - 1;
+  const int64_t per_buf = (int64_t)cap_rows;
+  const int64_t total = per_buf * n_bufs;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+    const int b = (int)(j / per_buf);
+    const int64_t i = j % per_buf;
+    const uint64_t* buf = src + (size_t)b * (size_t)(cap_rows + 1) * words;
+    if ((unsigned long long)i >= buf[0]) continue;
+    const uint64_t* row = buf + (size_t)(1 + i) * words;
+    const uint64_t h = row[0];
+    uint32_t s = mix32(h) & mask;
+    for (uint32_t probes = 0; probes <= mask; probes++, s = (s + 1) & mask) {
+      if (t.state[s] == 0u) break;
+      if (t.hash[s] != h) continue;
+      if (t.min_row[s] == row[1]) {
+        for (int k = 0; k < n_keys; k++) t.keys[(size_t)k * t.capacity + s] = row[3 + k];
+        t.knull[s] = (uint32_t)row[2];
+      }
+      break;
+    }
+  }
+}
+
 }  // namespace
 
 void launch_table_merge_packed(const TableView& t, int n_keys, int n_acc, const int* ops, int match_keys, const uint64_t* src, int n_bufs,
@@ -414,6 +440,10 @@ void launch_table_merge_packed(const TableView& t, int n_keys, int n_acc, const 
   if (n_bufs <= 0 || cap_rows == 0) return;
   k_table_merge_packed<<<grid_for((int64_t)cap_rows * n_bufs, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, ops, match_keys, src, n_bufs, cap_rows);
   count_launch();
+  if (!match_keys && n_keys > 0) {
+    k_table_merge_fixkeys<<<grid_for((int64_t)cap_rows * n_bufs, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, src, n_bufs, cap_rows);
+    count_launch();
+  }
   SQ_CUDA(cudaGetLastError());
 }
 

@@ -462,6 +462,49 @@ def test_device_resident_partial_exchange(cuda_lib, oracle):
         x.close()
 
 
+def test_partial_merge_hash_only_first_rows_keys_win(cuda_lib, oracle):
+    """Quirk K2 across partial tables: (i, j) and (j, i) share a row hash; under hash-only identity the merged group
+    reports the keys of the globally FIRST row, whichever partial supplied it and whatever order the merge saw them in."""
+    import torch
+    from sqlrs_b200.host.plan import PhysicalHashAgg, PhysicalTableScan
+
+    m = 3000
+    i = np.arange(m, dtype=np.int64)
+    schema = pa.schema([pa.field("a", pa.int64()), pa.field("b", pa.int64()), pa.field("v", pa.int64())])
+    # shard 0 (global rows 0..m): even groups as (lo, hi), odd groups as (hi, lo); shard 1 the mirror image
+    a0 = pa.array(np.where(i % 2 == 0, i, i + 100_000))
+    b0 = pa.array(np.where(i % 2 == 0, i + 100_000, i))
+    shard0 = pa.RecordBatch.from_arrays([a0, b0, pa.array(i + 1)], schema=schema)
+    shard1 = pa.RecordBatch.from_arrays([b0, a0, pa.array(2 * i + 1)], schema=schema)
+    plan = PhysicalHashAgg([AggFunc("Sum", [InputRef(2, I64)])], [InputRef(0, I64), InputRef(1, I64)], PhysicalTableScan(0))
+    opts = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_ONLY)
+    whole = pa.Table.from_batches([shard0, shard1])
+    exp, _ = _run_plan(oracle, plan, {0: schema}, {0: whole}, None, **opts)
+    assert exp[0].num_rows == m
+    cap = 4096
+    for order in ((0, 1), (1, 0)):
+        bufs, plans = [], []
+        for shard, base in ((shard0, 0), (shard1, m)):
+            p = ExecutorBuilder(cuda_lib, cuda_lib.options(**opts)).build(plan, {0: schema})
+            p.push_table(0, pa.Table.from_batches([shard]))
+            cuda_lib.check(cuda_lib.plan_execute_partial(p.handle, base))
+            words = C.c_int32(0)
+            cuda_lib.check(cuda_lib.plan_partials_row_words(p.handle, C.byref(words)))
+            buf = torch.empty((cap + 1) * words.value, dtype=torch.int64, device="cuda")
+            cuda_lib.check(cuda_lib.plan_export_partials_device(p.handle, C.c_void_p(buf.data_ptr()), cap))
+            torch.cuda.synchronize()
+            bufs.append(buf)
+            plans.append(p)
+        gathered = torch.cat([bufs[order[0]], bufs[order[1]]])
+        p = plans[0]
+        cuda_lib.check(cuda_lib.plan_clear_partials(p.handle))
+        cuda_lib.check(cuda_lib.plan_merge_partials_device(p.handle, C.c_void_p(gathered.data_ptr()), 2, cap))
+        cuda_lib.check(cuda_lib.plan_finish_partial(p.handle))
+        assert_batches_match(p.collect(), exp)
+        for x in plans:
+            x.close()
+
+
 def test_plan_can_be_executed_repeatedly(cuda_lib, oracle):
     """bench.py reuses one plan: operator state must reset between runs (and survive a different table)"""
     plan, schemas = tpch.q1_plan()
