@@ -453,7 +453,7 @@ std::vector<DBatch> Plan::run(int idx, const Needed& needed) {
         for (const ExprCopy& e : n.exprs) mark_refs(e, child_need);
       n.order_op->set_row_limit(fusion() ? n.row_limit_hint : -1);
       const bool topk = fusion() && n.order_op->topk_applies(n.row_limit_hint);
-      description_ += topk ? "[Order + Limit: top-" + std::to_string(n.row_limit_hint) + " selection (k rounds of block-wide argmin), rows gathered] "
+      description_ += topk ? "[Order + Limit: top-" + std::to_string(n.row_limit_hint) + " selection (k_topk_pass: warp-level, keys in registers), rows gathered] "
                            : (n.row_limit_hint >= 0 && fusion() ? "[Order + Limit: stable LSD radix sort of row ids, top-" + std::to_string(n.row_limit_hint) + " rows gathered] "
                                                                  : "[Order: stable LSD radix sort of row ids + gather] ");
       const int ck = nodes_[n.child0].kind;
