@@ -397,6 +397,13 @@ int SQLRS_API(plan_export_partials)(sqlrs_plan* p, struct ArrowArray* out, struc
 int SQLRS_API(plan_clear_partials)(sqlrs_plan* p);
 int SQLRS_API(plan_merge_partials)(sqlrs_plan* p, struct ArrowArray* partials, const struct ArrowSchema* schema);
 int SQLRS_API(plan_finish_partial)(sqlrs_plan* p);
+/* DISTINCT aggregates (reference: a HashSet<ScalarValue> per group, count.rs:31-58 / sum.rs:99-132) keep their set elements in
+ * one more table per DISTINCT aggregate, next to the table of the plain aggregates.  *n_tables = how many tables the partial
+ * state of this plan has (1 without DISTINCT); select_partials_table makes export / clear / merge / row_words (and the
+ * _device forms below) address table `index` (execute_partial selects 0).  Exchange every table the same way, merge table 0
+ * first, then finish_partial once.  Column 0 of every table's rows is the hash to partition on. */
+int SQLRS_API(plan_partials_tables)(sqlrs_plan* p, int32_t* n_tables);
+int SQLRS_API(plan_select_partials_table)(sqlrs_plan* p, int32_t index);
 /* the same exchange without leaving HBM (what the NCCL path uses): partial groups packed row-major into
  * caller-provided DEVICE memory on the plan's stream — (cap_rows + 1) rows of *n_words u64 each, row 0 =
  * header {number of groups (may exceed cap_rows: then rows are missing and the caller must fall back to the

@@ -318,8 +318,24 @@ struct HashAgg {
   }
 
   // ---- partial / final split (multi-process group-by; NOT part of the reference):
-  // un-finalised groups as a batch [hash, min_row, keys..., per aggregate: state value, count]
-  Batch export_partials() const {
+  // table 0: un-finalised groups as a batch [hash, min_row, keys..., per aggregate: state value, count];
+  // table 1 + j (the j-th DISTINCT COUNT / SUM): the elements of the per-group sets, [hash, min_row, keys..., element]
+  static bool is_distinct_agg(const AggDesc& d) { return d.distinct && (d.func == SQLRS_AGG_COUNT || d.func == SQLRS_AGG_SUM); }
+  std::vector<size_t> distinct_aggs() const {
+    std::vector<size_t> out;
+    for (size_t k = 0; k < aggs.size(); k++)
+      if (is_distinct_agg(aggs[k])) out.push_back(k);
+    return out;
+  }
+  int partial_tables() const { return 1 + (int)distinct_aggs().size(); }
+  static Scalar i64_scalar(int64_t v) {
+    Scalar s = Scalar::null_of(SQLRS_DT_INT64);
+    s.is_null = false;
+    s.i = v;
+    return s;
+  }
+
+  Batch export_partials(int table = 0) const {
     if (!seen_batch) fail(SQLRS_ERR_INTERNAL, "called `Option::unwrap()` on a `None` value (no input batch)");
     if (opt.count_mode != SQLRS_COUNT_SQL_ACCUMULATE) fail(SQLRS_ERR_UNSUPPORTED, "partial/final COUNT needs SQLRS_COUNT_SQL_ACCUMULATE");
     Batch out;
@@ -333,60 +349,99 @@ struct HashAgg {
     add("hash", SQLRS_DT_INT64);
     add("min_row", SQLRS_DT_INT64);
     for (size_t k = 0; k < group_by.size(); k++) add("key" + std::to_string(k), key_dtypes[k]);
-    for (size_t k = 0; k < aggs.size(); k++) {
-      if (aggs[k].distinct) fail(SQLRS_ERR_UNSUPPORTED, "partial/final DISTINCT aggregates");
-      add("state" + std::to_string(k), agg_output_dtype(aggs[k]));
-      add("count" + std::to_string(k), SQLRS_DT_INT64);
-    }
-    auto i64 = [](int64_t v) {
-      Scalar s = Scalar::null_of(SQLRS_DT_INT64);
-      s.is_null = false;
-      s.i = v;
-      return s;
-    };
-    for (const Group& g : groups) {
-      size_t c = 0;
-      append_scalar(*cols[c++], i64((int64_t)g.hash));
-      append_scalar(*cols[c++], i64(g.first_row));
-      for (const Scalar& k : g.keys) append_scalar(*cols[c++], k);
-      for (const Accumulator& a : g.accs) {
-        append_scalar(*cols[c++], a.evaluate());
-        append_scalar(*cols[c++], i64(a.count));
+    int64_t n = 0;
+    if (table == 0) {
+      for (size_t k = 0; k < aggs.size(); k++) {
+        add("state" + std::to_string(k), agg_output_dtype(aggs[k]));
+        add("count" + std::to_string(k), SQLRS_DT_INT64);
       }
+      for (const Group& g : groups) {
+        size_t c = 0;
+        append_scalar(*cols[c++], i64_scalar((int64_t)g.hash));
+        append_scalar(*cols[c++], i64_scalar(g.first_row));
+        for (const Scalar& k : g.keys) append_scalar(*cols[c++], k);
+        for (size_t k = 0; k < g.accs.size(); k++) {
+          const Accumulator& a = g.accs[k];
+          // a DISTINCT accumulator's state is its set: table 1 + j carries it
+          append_scalar(*cols[c++], is_distinct_agg(aggs[k]) ? Scalar::null_of(agg_output_dtype(aggs[k])) : a.evaluate());
+          append_scalar(*cols[c++], i64_scalar(is_distinct_agg(aggs[k]) ? 0 : a.count));
+        }
+        n++;
+      }
+    } else {
+      const std::vector<size_t> da = distinct_aggs();
+      if (table < 0 || (size_t)table > da.size()) fail(SQLRS_ERR_INVALID_ARG, "partials table index out of range");
+      const size_t k = da[(size_t)table - 1];
+      int elem_dtype = SQLRS_DT_INT64;  // (no element anywhere: an empty batch of any type)
+      for (const Group& g : groups)
+        if (!g.accs[k].distinct_values.empty()) elem_dtype = g.accs[k].distinct_values[0].dtype;
+      add("element", elem_dtype);
+      for (const Group& g : groups)
+        for (const Scalar& v : g.accs[k].distinct_values) {
+          size_t c = 0;
+          append_scalar(*cols[c++], i64_scalar((int64_t)g.hash));
+          append_scalar(*cols[c++], i64_scalar(g.first_row));
+          for (const Scalar& key : g.keys) append_scalar(*cols[c++], key);
+          append_scalar(*cols[c++], v);
+          n++;
+        }
     }
-    out.n = (int64_t)groups.size();
+    out.n = n;
     for (auto& c : cols) {
       c->normalize();
       out.cols.push_back(c);
     }
     return out;
   }
-  void clear_partials() {
-    groups.clear();
-    by_hash.clear();
+  void clear_partials(int table = 0) {
+    if (table == 0) {
+      groups.clear();
+      by_hash.clear();
+      return;
+    }
+    const std::vector<size_t> da = distinct_aggs();
+    if (table < 0 || (size_t)table > da.size()) fail(SQLRS_ERR_INVALID_ARG, "partials table index out of range");
+    for (Group& g : groups) g.accs[da[(size_t)table - 1]].distinct_values.clear();
   }
-  void merge_partials(const Batch& p) {
+  // the group of partial row r (created if this process has not seen it), first-appearance bookkeeping included
+  Group& merge_group(const Batch& p, const std::vector<ColPtr>& keys, int64_t r) {
     const size_t K = group_by.size();
-    if (p.cols.size() != 2 + K + 2 * aggs.size()) fail(SQLRS_ERR_INVALID_ARG, "partials batch has the wrong number of columns");
+    const int64_t saved = rows_seen;
+    rows_seen = p.cols[1]->i[r];  // find_or_create stamps first_row = rows_seen + row
+    const size_t before = groups.size();
+    int gid = find_or_create((uint64_t)p.cols[0]->i[r], keys, r);
+    if (groups.size() != before) groups[gid].first_row = p.cols[1]->i[r];
+    rows_seen = saved;
+    Group& g = groups[gid];
+    if (p.cols[1]->i[r] < g.first_row) {
+      g.first_row = p.cols[1]->i[r];
+      if (opt.match_mode == SQLRS_MATCH_HASH_ONLY)
+        for (size_t k = 0; k < K; k++) g.keys[k] = Scalar::from_column(*keys[k], r);
+    }
+    return g;
+  }
+  void merge_partials(const Batch& p, int table = 0) {
+    const size_t K = group_by.size();
+    const std::vector<size_t> da = distinct_aggs();
+    if (table < 0 || (size_t)table > da.size()) fail(SQLRS_ERR_INVALID_ARG, "partials table index out of range");
+    if (p.cols.size() != (table == 0 ? 2 + K + 2 * aggs.size() : 2 + K + 1)) fail(SQLRS_ERR_INVALID_ARG, "partials batch has the wrong number of columns");
     if (!seen_batch) {
       for (size_t k = 0; k < K; k++) key_dtypes.push_back(p.cols[2 + k]->dtype);
       seen_batch = true;
     }
     std::vector<ColPtr> keys(p.cols.begin() + 2, p.cols.begin() + 2 + K);
     for (int64_t r = 0; r < p.n; r++) {
-      const int64_t saved = rows_seen;
-      rows_seen = p.cols[1]->i[r];  // find_or_create stamps first_row = rows_seen + row
-      const size_t before = groups.size();
-      int gid = find_or_create((uint64_t)p.cols[0]->i[r], keys, 0 * r + r);
-      if (groups.size() != before) groups[gid].first_row = p.cols[1]->i[r];
-      rows_seen = saved;
-      Group& g = groups[gid];
-      if (p.cols[1]->i[r] < g.first_row) {
-        g.first_row = p.cols[1]->i[r];
-        if (opt.match_mode == SQLRS_MATCH_HASH_ONLY)
-          for (size_t k = 0; k < K; k++) g.keys[k] = Scalar::from_column(*keys[k], r);
+      Group& g = merge_group(p, keys, r);
+      if (table > 0) {  // one set element: insert unless present (count.rs:44-53)
+        Accumulator& a = g.accs[da[(size_t)table - 1]];
+        Scalar v = Scalar::from_column(*p.cols[2 + K], r);
+        bool seen = false;
+        for (const Scalar& o : a.distinct_values) seen = seen || o.equals(v);
+        if (!seen) a.distinct_values.push_back(v);
+        continue;
       }
       for (size_t k = 0; k < aggs.size(); k++) {
+        if (is_distinct_agg(aggs[k])) continue;
         Accumulator& a = g.accs[k];
         Scalar v = Scalar::from_column(*p.cols[2 + K + 2 * k], r);
         a.count += p.cols[2 + K + 2 * k + 1]->i[r];

@@ -149,6 +149,7 @@ struct sqlrs_plan {
   std::deque<Batch> results;
   std::string description;
   std::unique_ptr<HashAgg> partial;
+  int partial_sel = 0;  // table of `partial` the partial-state calls address (DISTINCT: one table per set)
 
   std::vector<Batch> run(int idx) {
     if (idx < 0 || idx >= (int)nodes.size()) fail(SQLRS_ERR_INVALID_ARG, "plan: child index out of range");
@@ -586,25 +587,39 @@ int sqlrs_oracle_plan_execute_partial(sqlrs_plan* p, int64_t row_base) {
     if (n.raw.kind != SQLRS_NODE_HASH_AGG) fail(SQLRS_ERR_UNSUPPORTED, "oracle: execute_partial needs a HashAgg root");
     p->partial.reset(new HashAgg(n.aggs, n.group_by, n.group_names, p->opt));
     p->partial->rows_seen = row_base;
+    p->partial_sel = 0;
     for (const Batch& b : p->run(n.raw.child0)) p->partial->push(b);
+  });
+}
+int sqlrs_oracle_plan_partials_tables(sqlrs_plan* p, int32_t* n_tables) {
+  return guarded([&] {
+    if (!p->partial) fail(SQLRS_ERR_INVALID_ARG, "partials_tables before execute_partial");
+    *n_tables = p->partial->partial_tables();
+  });
+}
+int sqlrs_oracle_plan_select_partials_table(sqlrs_plan* p, int32_t index) {
+  return guarded([&] {
+    if (!p->partial) fail(SQLRS_ERR_INVALID_ARG, "select_partials_table before execute_partial");
+    if (index < 0 || index >= p->partial->partial_tables()) fail(SQLRS_ERR_INVALID_ARG, "partials table index out of range");
+    p->partial_sel = index;
   });
 }
 int sqlrs_oracle_plan_export_partials(sqlrs_plan* p, ArrowArray* out, ArrowSchema* out_schema) {
   return guarded([&] {
     if (!p->partial) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
-    export_batch(p->partial->export_partials(), out, out_schema);
+    export_batch(p->partial->export_partials(p->partial_sel), out, out_schema);
   });
 }
 int sqlrs_oracle_plan_clear_partials(sqlrs_plan* p) {
   return guarded([&] {
     if (!p->partial) fail(SQLRS_ERR_INVALID_ARG, "clear_partials before execute_partial");
-    p->partial->clear_partials();
+    p->partial->clear_partials(p->partial_sel);
   });
 }
 int sqlrs_oracle_plan_merge_partials(sqlrs_plan* p, ArrowArray* partials, const ArrowSchema* schema) {
   return guarded([&] {
     if (!p->partial) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
-    p->partial->merge_partials(consume_batch(partials, schema));
+    p->partial->merge_partials(consume_batch(partials, schema), p->partial_sel);
   });
 }
 int sqlrs_oracle_plan_finish_partial(sqlrs_plan* p) {

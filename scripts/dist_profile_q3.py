@@ -45,9 +45,13 @@ with torch.cuda.stream(stream):
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter(); one(); torch.cuda.synchronize(); walls.append((time.perf_counter() - t0) * 1e3)
     print(f"[dist trace] rank {rank}: single steps after a barrier: {sorted(walls)[0]:.3f} .. {sorted(walls)[-1]:.3f} ms", flush=True)
-    for it in range(6):
+    for it in range(9):
         if it == 4:
             os.environ["SQLRS_B200_DIST_TRACE"] = "1"
+        if it == 6:  # the host's timeline of an undisturbed step: where it waits, what it spends between the waits
+            os.environ["SQLRS_B200_DIST_TRACE"] = "host"
+            if rank == 0:
+                print("[dist trace] ---- host timeline (no added synchronisation)", flush=True)
         dist.barrier()
         sqdist.distributed_join_topk(builder, group, build_plan=cust, build_schemas={0: schemas[0]}, build_tables={0: tabs[0]}, query_plan=full, query_schemas=schemas,
                                      query_tables={1: tabs[1], 2: tabs[2]}, build_slot=0, order_by=tpch.q3_tail_order_by(), limit=10, state=state)

@@ -535,6 +535,18 @@ int sqlrs_plan_merge_partials(sqlrs_plan* p, ArrowArray* partials, const ArrowSc
     p->impl.merge_partials(import_batch_host(p->impl.ctx(), partials, schema));
   });
 }
+int sqlrs_plan_partials_tables(sqlrs_plan* p, int32_t* n_tables) {
+  return guarded([&] {
+    if (!p || !n_tables) fail(SQLRS_ERR_INVALID_ARG, "plan / n_tables is NULL");
+    *n_tables = p->impl.partials_tables();
+  });
+}
+int sqlrs_plan_select_partials_table(sqlrs_plan* p, int32_t index) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.select_partials_table(index);
+  });
+}
 int sqlrs_plan_partials_row_words(sqlrs_plan* p, int32_t* n_words) {
   return guarded([&] {
     if (!p || !n_words) fail(SQLRS_ERR_INVALID_ARG, "plan / n_words is NULL");

@@ -120,9 +120,13 @@ class AggOp {
   // consumer (finish / settle), and a table that turned out too small raises RetrySizingError there
   void push_join(const DBatch& probe, class JoinOp& join, const ExprCopy& probe_pred, bool defer = false);
   void settle();  // reads the counters of a deferred push_join now (one synchronisation)
-  void set_row_base(int64_t first_global_row) { rows_seen_ = first_global_row; }
+  void set_row_base(int64_t first_global_row);
 
   bool has_distinct() const { return distinct_ != nullptr; }
+  // DISTINCT aggregates keep one group table per DISTINCT aggregate (the set elements) next to the table of the plain
+  // aggregates: the partial/final calls above address ONE table, this is how a caller walks all of them
+  int partial_tables() const;
+  AggOp& partial_table(int index);
 
  private:
   struct Compiled;

@@ -1384,8 +1384,31 @@ DBatch AggOp::finish_distinct() {
 }
 
 // ------------------------------------------------------------------ partial / final (multi-GPU)
+void AggOp::set_row_base(int64_t first_global_row) {
+  rows_seen_ = first_global_row;
+  if (distinct_) {
+    if (distinct_->plain) distinct_->plain->set_row_base(first_global_row);
+    for (auto& it : distinct_->items) it.dedup->set_row_base(first_global_row);
+  }
+}
+
+// the tables of a DISTINCT composition: [plain aggregates (if any), one dedup table per DISTINCT aggregate in declared order]
+int AggOp::partial_tables() const {
+  if (!distinct_) return 1;
+  return (distinct_->plain ? 1 : 0) + (int)distinct_->items.size();
+}
+AggOp& AggOp::partial_table(int index) {
+  if (index < 0 || index >= partial_tables()) fail(SQLRS_ERR_INVALID_ARG, "partials table index out of range");
+  if (!distinct_) return *this;
+  if (distinct_->plain) {
+    if (index == 0) return *distinct_->plain;
+    index--;
+  }
+  return *distinct_->items[(size_t)index].dedup;
+}
+
 void AggOp::check_partial_supported() const {
-  if (distinct_) fail(SQLRS_ERR_UNSUPPORTED, "partial/final DISTINCT aggregates");
+  if (distinct_) fail(SQLRS_ERR_INTERNAL, "partial/final DISTINCT aggregates are addressed table by table (partial_table)");
   if (!cache_.empty())
     for (const AggPlan& ap : cache_.begin()->second->aggs)
       if (ap.utf8_packed) fail(SQLRS_ERR_UNSUPPORTED, "partial/final MIN / MAX over Utf8 (the packed ranks are local to one process's string pool state)");

@@ -250,6 +250,7 @@ void Plan::execute_partial(int64_t row_base) {
     description_ = head;
     partial_op_->reset();
     partial_active_ = true;
+    partial_sel_ = 0;
     partial_op_->set_row_base(row_base);
     const Needed need = fusion() ? agg_child_needs(n, fused, width_of(child)) : Needed();
     if (!feed_fused_join(*partial_op_, child, fused, need))
@@ -260,20 +261,29 @@ void Plan::execute_partial(int64_t row_base) {
   scan_kernel_ms_ = partial_op_->scan_kernel_ms();
   scan_kernel_launches_ = partial_op_->scan_kernel_launches();
 }
+int Plan::partials_tables() const {
+  if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "partials_tables before execute_partial");
+  return partial_op_->partial_tables();
+}
+void Plan::select_partials_table(int index) {
+  if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "select_partials_table before execute_partial");
+  if (index < 0 || index >= partial_op_->partial_tables()) fail(SQLRS_ERR_INVALID_ARG, "partials table index out of range");
+  partial_sel_ = index;
+}
 int Plan::partial_row_words() const {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "partial_row_words before execute_partial");
-  return partial_op_->partial_row_words();
+  return partial_op_->partial_table(partial_sel_).partial_row_words();
 }
 void Plan::export_partials_device(uint64_t* dst, int64_t cap_rows) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
-  partial_op_->export_partials_device(dst, cap_rows);
+  partial_op_->partial_table(partial_sel_).export_partials_device(dst, cap_rows);
   // a plan that owns its stream (options.stream == NULL) has no stream the caller could order against: the buffer is
   // complete when the call returns.  With a caller-provided stream the pack is ordered on that stream.
   if (ctx_.own_stream) SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
 }
 int64_t Plan::export_partials_partitioned(uint64_t* dst, int n_parts, int64_t cap_rows) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
-  const int64_t g = partial_op_->export_partials_partitioned(dst, n_parts, cap_rows);
+  const int64_t g = partial_op_->partial_table(partial_sel_).export_partials_partitioned(dst, n_parts, cap_rows);
   if (ctx_.own_stream) SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
   return g;
 }
@@ -333,19 +343,19 @@ void Plan::push_table_batched(int slot, const DBatch& whole, int64_t batch_rows)
 }
 void Plan::merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
-  partial_op_->merge_partials_device(src, n_bufs, cap_rows);
+  partial_op_->partial_table(partial_sel_).merge_partials_device(src, n_bufs, cap_rows);
 }
 void Plan::export_partials(ArrowArray* out, ArrowSchema* out_schema) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
-  partial_op_->export_partials(out, out_schema);
+  partial_op_->partial_table(partial_sel_).export_partials(out, out_schema);
 }
 void Plan::clear_partials() {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "clear_partials before execute_partial");
-  partial_op_->clear_partials();
+  partial_op_->partial_table(partial_sel_).clear_partials();
 }
 void Plan::merge_partials(const DBatch& partials) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
-  partial_op_->merge_partials(partials);
+  partial_op_->partial_table(partial_sel_).merge_partials(partials);
 }
 void Plan::finish_partial() {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "finish before execute_partial");

@@ -26,6 +26,8 @@ class Plan {
   void merge_partials(const DBatch& partials);
   void finish_partial();
   int partial_row_words() const;
+  int partials_tables() const;  // > 1 with DISTINCT aggregates; the partial-state calls address the selected table
+  void select_partials_table(int index);
   void export_partials_device(uint64_t* dst, int64_t cap_rows);
   int64_t export_partials_partitioned(uint64_t* dst, int n_parts, int64_t cap_rows);
   bool result_shape(int64_t* n_rows, int32_t* n_cols);
@@ -85,6 +87,7 @@ class Plan {
   std::deque<Result> results_;
   std::unique_ptr<AggOp> partial_op_;  // root aggregate of execute_partial(), kept across runs
   bool partial_active_ = false;        // between execute_partial and finish_partial
+  int partial_sel_ = 0;                // table of partial_op_ the partial-state calls address
   std::string description_;
   std::vector<JoinChainOp*> pending_chains_;  // runs sized by hints, to be validated once the stream has been synchronised
   double scan_kernel_ms_ = 0;

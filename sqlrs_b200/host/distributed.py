@@ -247,10 +247,11 @@ def _device_exchange(plan, group: TorchGroup, cap_rows: int):
     return result
 
 
-def _radix_exchange(plan, group: TorchGroup):
+def _radix_exchange(plan, group: TorchGroup, finish: bool = True):
     """Many groups (NCCL): radix-partition the partial groups by identity hash mod world into per-owner regions of a device
     send buffer, exchange them with ONE all_to_all_single (equal splits: every region carries its own count), fold on the
-    owner, then all-gather the owner-merged groups — disjoint across ranks — and finalise on rank 0."""
+    owner, then all-gather the owner-merged groups — disjoint across ranks — and finalise on rank 0.
+    `finish=False`: stop once rank 0's selected table holds the merged groups (the caller exchanges further tables)."""
     torch, lib, W = group.torch, plan.lib, group.world
     words = _row_words(plan)
     shared = _check_stream(plan, group)
@@ -293,17 +294,41 @@ def _radix_exchange(plan, group: TorchGroup):
     lib.check(lib.plan_clear_partials(plan.handle))
     if group.rank == 0:
         lib.check(lib.plan_merge_partials_device(plan.handle, C.c_void_p(recv2.data_ptr()), W, cap2))
+    if not finish:
+        return None
     lib.check(lib.plan_finish_partial(plan.handle))
     result = plan.collect()
     return result if group.rank == 0 else []
 
 
+def _partials_tables(plan) -> int:
+    n = C.c_int32(1)
+    plan.lib.check(plan.lib.plan_partials_tables(plan.handle, C.byref(n)))
+    return int(n.value)
+
+
+def _select(plan, table: int):
+    plan.lib.check(plan.lib.plan_select_partials_table(plan.handle, table))
+
+
 def sharded_aggregate(plan, group: TorchGroup, row_base: int = 0, device_cap_rows: int = 256) -> List[pa.RecordBatch]:
     """Runs `plan` (root = aggregate) over the shard pushed on this rank; rank 0 returns the final batches.
-    `row_base`: global row number of the shard's first row (first-appearance order across ranks)."""
+    `row_base`: global row number of the shard's first row (first-appearance order across ranks).
+    DISTINCT aggregates: the partial state is several tables (the plain aggregates' groups + the set elements of every
+    DISTINCT aggregate); each is exchanged like a group table — partitioned by its own identity hash — and rank 0 finalises
+    once all of them are merged."""
     lib = plan.lib
     lib.check(lib.plan_execute_partial(plan.handle, row_base))
+    tables = _partials_tables(plan)
     if group.native_a2a and lib.prefix == "sqlrs_":  # NCCL + the CUDA library: the exchange stays in HBM
+        if tables > 1:
+            for t in range(tables):
+                _select(plan, t)
+                _radix_exchange(plan, group, finish=False)
+            if group.rank != 0:
+                return []  # nothing to finalise here: the merged tables live on rank 0
+            lib.check(lib.plan_finish_partial(plan.handle))
+            return plan.collect()
         if device_cap_rows > 0:
             if not getattr(plan, "_many_groups", False):
                 result = _device_exchange(plan, group, device_cap_rows)
@@ -312,24 +337,59 @@ def sharded_aggregate(plan, group: TorchGroup, row_base: int = 0, device_cap_row
                 plan._many_groups = True  # remembered: later runs of this plan go straight to the radix exchange
                 lib.check(lib.plan_execute_partial(plan.handle, row_base))  # the few-groups attempt consumed the partial state
         return _radix_exchange(plan, group)
-    # host path (gloo / the CPU checker): the same steps through Arrow batches
-    local = _export_partials(plan)
-    received = group.all_to_all_bytes([_to_bytes(p) for p in partition_by_owner(local, group.world)])
-    lib.check(lib.plan_clear_partials(plan.handle))
-    for data in received:
-        _merge_partials(plan, _from_bytes(data))
-    owned = _export_partials(plan)
-    gathered = group.gather_bytes(_to_bytes(owned), dst=0)
-    lib.check(lib.plan_clear_partials(plan.handle))
-    if gathered is not None:
-        for data in gathered:
-            _merge_partials(plan, _from_bytes(data))
+    # host path (gloo / the CPU checker): the same steps through Arrow batches.  Every table is exported before any is
+    # cleared and merged in table order (table 0 = the groups themselves)
+    def export_all():
+        out = []
+        for t in range(tables):
+            _select(plan, t)
+            out.append(_export_partials(plan))
+        return out
+
+    def replace_all(received):  # received[t] = batches to fold into table t
+        for t in reversed(range(tables)):
+            _select(plan, t)
+            lib.check(lib.plan_clear_partials(plan.handle))
+        for t in range(tables):
+            _select(plan, t)
+            for batch in received[t]:
+                _merge_partials(plan, batch)
+
+    local = export_all()
+    received = [[_from_bytes(d) for d in group.all_to_all_bytes([_to_bytes(p) for p in partition_by_owner(local[t], group.world)])]
+                for t in range(tables)]
+    replace_all(received)
+    owned = export_all()
+    gathered = [group.gather_bytes(_to_bytes(owned[t]), dst=0) for t in range(tables)]
+    replace_all([[_from_bytes(d) for d in g] if g is not None else [] for g in gathered])
+    if tables > 1 and group.rank != 0:
+        return []
     lib.check(lib.plan_finish_partial(plan.handle))
     result = plan.collect()
     return result if group.rank == 0 else []
 
 
 # ---------------------------------------------------------------------------------------------- joins
+_MARK_T = [None]
+
+
+def _mark(group, label):
+    """SQLRS_B200_DIST_TRACE=1: wall time per phase with a device synchronisation at every mark (attributes device work to
+    the phase that enqueued it); =host: the host's own timeline, nothing added (shows where the host waits)."""
+    import os
+    import time
+
+    mode = os.environ.get("SQLRS_B200_DIST_TRACE")
+    if mode not in ("1", "host"):
+        return
+    if mode == "1":
+        group.torch.cuda.synchronize(group.device)
+    now = time.perf_counter()
+    if _MARK_T[0] is not None and label:
+        print(f"[dist trace] rank {group.rank}: {label} {1e3 * (now - _MARK_T[0]):.3f} ms", flush=True)
+    _MARK_T[0] = now
+
+
 class DeviceBatch:
     """Columns resident in HBM as torch tensors (int64 storage; Float64 columns as their bit patterns), exportable as an
     ArrowDeviceArray for `GpuPlan.push_table_device` (same interface as tpch.DeviceTable)."""
@@ -375,6 +435,7 @@ def merge_topk_device(plan, group: TorchGroup, schema: pa.Schema, order_by, limi
         return []
     every = recv.view(W, 1 + ncols * limit)
     counts = every[:, 0].tolist()
+    _mark(group, "  top-k: candidates gathered, counts on the host")
     total = int(sum(counts))
     if total == W * limit:  # the usual case: every rank had at least `limit` rows — one strided copy, rank-major rows
         body = every[:, 1:].reshape(W, ncols, limit).permute(1, 0, 2).contiguous()
@@ -401,6 +462,7 @@ def broadcast_rows(plan, group: TorchGroup, schema: pa.Schema) -> DeviceBatch:
     counts = torch.empty(W, dtype=torch.int64, device=group.device)
     group.dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device=group.device))
     counts = counts.tolist()  # sizes of the receive buffers: the one host round trip of this step
+    _mark(group, "  broadcast: row counts known on the host")
     most = max(max(counts), 1)
     send = torch.empty((ncols, most), dtype=torch.int64, device=group.device)
     if shape is not None:
@@ -416,6 +478,7 @@ def broadcast_rows(plan, group: TorchGroup, schema: pa.Schema) -> DeviceBatch:
             packed[:, off:off + counts[r]] = recv[r, :, :counts[r]]
             off += counts[r]
     dev = group.device.index if group.device.index is not None else 0
+    _mark(group, "  broadcast: all-gather + packing enqueued")
     return DeviceBatch(schema, [packed[c, :total] for c in range(ncols)], total, dev)
 
 
@@ -514,19 +577,8 @@ def distributed_join_topk(builder, group: TorchGroup, *, build_plan, build_schem
 
     `state`: a dict kept by the caller across calls; the built plans live there so that repeated runs reuse compiled kernels,
     device buffers and sizing hints."""
-    import os
-    import time
-
-    trace = os.environ.get("SQLRS_B200_DIST_TRACE") == "1"
-
-    def mark(label, t=[None]):
-        if not trace:
-            return
-        group.torch.cuda.synchronize(group.device)
-        now = time.perf_counter()
-        if t[0] is not None and label:
-            print(f"[dist trace] rank {group.rank}: {label} {1e3 * (now - t[0]):.3f} ms", flush=True)
-        t[0] = now
+    def mark(label):
+        _mark(group, label)
 
     state = state if state is not None else {}
     if "p_build" not in state:
@@ -543,6 +595,7 @@ def distributed_join_topk(builder, group: TorchGroup, *, build_plan, build_schem
     mark("all-gather of its rows")
     p_query.push_table_device(build_slot, build_side)
     _push(p_query, query_tables)
+    mark("  query: tables pushed")
     if group.native_a2a and builder.lib.prefix == "sqlrs_":
         p_query.execute()
         mark("query plan (local shards)")

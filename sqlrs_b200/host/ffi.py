@@ -240,6 +240,8 @@ _SIGNATURES = {
     "plan_merge_partials": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema)]),
     "plan_finish_partial": (C.c_int, [C.c_void_p]),
     "plan_partials_row_words": (C.c_int, [C.c_void_p, P(C.c_int32)]),
+    "plan_partials_tables": (C.c_int, [C.c_void_p, P(C.c_int32)]),
+    "plan_select_partials_table": (C.c_int, [C.c_void_p, C.c_int32]),
     "plan_export_partials_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "plan_merge_partials_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64]),
     "plan_scan_kernel_ms": (C.c_double, [C.c_void_p, P(C.c_int64)]),

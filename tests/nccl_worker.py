@@ -3,6 +3,7 @@ checked here against the single-GPU result of the same library on the same table
 Float64 sums within 1e-9 relative):
   1. Q1' (8 groups): device all-gather exchange
   2. a Q1-shaped group-by with thousands of groups: radix-partition kernel + all_to_all_single + owner merge
+  2b. the same with COUNT(DISTINCT) / SUM(DISTINCT): the set elements are exchanged as one more table per DISTINCT aggregate
   3. Q3' general sharding: broadcast-build join (device all-gather of the join-1 output) + group exchange
   4. Q3' co-partitioned shards (decided from key-range statistics): filtered customer rows all-gathered, top-10 merged
 """
@@ -89,6 +90,23 @@ def main():
             assert_batches_match(got, exp, rtol=1e-9)
         p.close()
         done.append("many groups (radix all-to-all)")
+
+        # ---- 2b. DISTINCT aggregates: one table of set elements per DISTINCT aggregate rides the same radix exchange
+        plan2b = PhysicalHashAgg([AggFunc("Count", [InputRef(1, I64)], distinct=True), AggFunc("Sum", [InputRef(1, I64)]),
+                                  AggFunc("Sum", [InputRef(1, I64)], distinct=True), AggFunc("Count", [InputRef(2, F64)], distinct=True)],
+                                 [InputRef(0, I64)], PhysicalTableScan(0))
+        p = builder.build(plan2b, {0: ls})
+        p.push_table_device(0, t)
+        for _ in range(2):
+            got = sqdist.sharded_aggregate(p, group, lo)
+        if rank == 0:
+            exp = single(plan2b, {0: ls}, {0: whole(tpch.LINEITEM, [0, 8, 2])})
+            assert exp[0].num_rows > 10_000, exp[0].num_rows
+            assert_batches_match(got, exp)
+        else:
+            assert got == []
+        p.close()
+        done.append("DISTINCT aggregates (one exchange per table)")
 
         # ---- 3. Q3', arbitrary contiguous shards: broadcast-build / partitioned-probe + group exchange
         (s1, s1_schemas), (s2, s2_schemas) = tpch.q3_stage_plans()

@@ -26,6 +26,14 @@ def _worker(rank, world, port, plan_name, out_dir):
     lib = ffi.Library(os.path.join(ROOT, "oracle", "liboracle.so"), "sqlrs_oracle_")
     d = tpch.dims(0.02)
     plan, schemas = tpch.q1_plan()
+    if plan_name == "distinct":  # DISTINCT aggregates: the sets of every group are one more table of the exchange each
+        from sqlrs_b200.host.expr import AggFunc, InputRef
+        from sqlrs_b200.host.plan import PhysicalHashAgg
+
+        col = {f.name: InputRef(i, ffi.dtype_of(f.type)) for i, f in enumerate(schemas[0])}
+        plan = PhysicalHashAgg([AggFunc("Count", [col["l_quantity_i64"]], distinct=True), AggFunc("Sum", [col["l_quantity_i64"]]),
+                                AggFunc("Sum", [col["l_quantity_i64"]], distinct=True), AggFunc("Count", [col["l_shipdate"]], distinct=True),
+                                AggFunc("Count", [col["l_quantity"]])], [col["l_returnflag"], col["l_linestatus"]], plan.child)
     opts = lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
     n = tpch.num_rows(lib, d, tpch.LINEITEM)
     lo, hi = n * rank // world, n * (rank + 1) // world
@@ -62,6 +70,13 @@ def _free_port():
 
 def test_two_rank_group_by_matches_single_process(tmp_path, oracle):
     mp.spawn(_worker, args=(2, _free_port(), "q1", str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").read_text() == "ok"
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distinct_aggregates_across_ranks_match_single_process(tmp_path, oracle, world):
+    """COUNT(DISTINCT) / SUM(DISTINCT) in the partial/final split: sets merged across ranks == one process over all rows"""
+    mp.spawn(_worker, args=(world, _free_port(), "distinct", str(tmp_path)), nprocs=world, join=True)
     assert (tmp_path / "ok").read_text() == "ok"
 
 

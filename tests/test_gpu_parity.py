@@ -462,6 +462,58 @@ def test_device_resident_partial_exchange(cuda_lib, oracle):
         x.close()
 
 
+@pytest.mark.parametrize("grouped", [True, False])
+def test_distinct_aggregates_in_the_partial_final_split(cuda_lib, oracle, grouped):
+    """DISTINCT aggregates keep one table per set next to the plain aggregates' table: two shards aggregated separately, every
+    table exported (device form for one shard, host Arrow form for the other), merged into a third plan == whole-table result"""
+    import torch
+    from sqlrs_b200.host import distributed as sqdist
+    from sqlrs_b200.host.plan import PhysicalHashAgg, PhysicalSimpleAgg, PhysicalTableScan
+
+    rng = np.random.default_rng(77)
+    n = 20_000
+    schema = pa.schema([pa.field("k", pa.int64()), pa.field("x", pa.int64()), pa.field("v", pa.int64())])
+    k = rng.integers(0, 300, n)
+    x = pa.array(rng.integers(0, 40, n), mask=rng.random(n) < 0.05)
+    whole = pa.RecordBatch.from_arrays([pa.array(k), x, pa.array(rng.integers(-1000, 1000, n))], schema=schema)
+    K, X, V = InputRef(0, I64), InputRef(1, I64), InputRef(2, I64)
+    aggs = [AggFunc("Count", [X], distinct=True), AggFunc("Sum", [V]), AggFunc("Sum", [X], distinct=True), AggFunc("Count", [V])]
+    plan = PhysicalHashAgg(aggs, [K], PhysicalTableScan(0)) if grouped else PhysicalSimpleAgg(aggs, PhysicalTableScan(0))
+    opts = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    exp, _ = _run_plan(oracle, plan, {0: schema}, {0: whole}, None, **opts)
+    cut = n // 3
+    plans = []
+    for lo, hi in ((0, cut), (cut, n), (0, 1)):  # the third plan is the merge target (its own one-row partial state is cleared)
+        p = ExecutorBuilder(cuda_lib, cuda_lib.options(**opts)).build(plan, {0: schema})
+        p.push_table(0, whole.slice(lo, hi - lo))
+        cuda_lib.check(cuda_lib.plan_execute_partial(p.handle, lo))
+        plans.append(p)
+    a, b, target = plans
+    tables = C.c_int32(0)
+    cuda_lib.check(cuda_lib.plan_partials_tables(target.handle, C.byref(tables)))
+    assert tables.value == 3  # plain aggregates + two sets
+    for t in range(tables.value):
+        for p in plans:
+            cuda_lib.check(cuda_lib.plan_select_partials_table(p.handle, t))
+        cuda_lib.check(cuda_lib.plan_clear_partials(target.handle))
+        words = C.c_int32(0)
+        cuda_lib.check(cuda_lib.plan_partials_row_words(a.handle, C.byref(words)))
+        cap = n
+        buf = torch.empty((cap + 1) * words.value, dtype=torch.int64, device="cuda")
+        cuda_lib.check(cuda_lib.plan_export_partials_device(a.handle, C.c_void_p(buf.data_ptr()), cap))
+        torch.cuda.synchronize()
+        cuda_lib.check(cuda_lib.plan_merge_partials_device(target.handle, C.c_void_p(buf.data_ptr()), 1, cap))
+        for piece in sqdist.partition_by_owner(sqdist._export_partials(b), 2):
+            sqdist._merge_partials(target, piece)
+    cuda_lib.check(cuda_lib.plan_finish_partial(target.handle))
+    assert_batches_match(target.collect(), exp)
+    with pytest.raises(ex.ExecutorError):
+        cuda_lib.check(cuda_lib.plan_execute_partial(a.handle, 0))
+        cuda_lib.check(cuda_lib.plan_select_partials_table(a.handle, 3))
+    for p in plans:
+        p.close()
+
+
 def test_partial_merge_hash_only_first_rows_keys_win(cuda_lib, oracle):
     """Quirk K2 across partial tables: (i, j) and (j, i) share a row hash; under hash-only identity the merged group
     reports the keys of the globally FIRST row, whichever partial supplied it and whatever order the merge saw them in."""
@@ -478,7 +530,7 @@ def test_partial_merge_hash_only_first_rows_keys_win(cuda_lib, oracle):
     shard1 = pa.RecordBatch.from_arrays([b0, a0, pa.array(2 * i + 1)], schema=schema)
     plan = PhysicalHashAgg([AggFunc("Sum", [InputRef(2, I64)])], [InputRef(0, I64), InputRef(1, I64)], PhysicalTableScan(0))
     opts = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_ONLY)
-    whole = pa.Table.from_batches([shard0, shard1])
+    whole = pa.Table.from_batches([shard0, shard1]).combine_chunks().to_batches()[0]
     exp, _ = _run_plan(oracle, plan, {0: schema}, {0: whole}, None, **opts)
     assert exp[0].num_rows == m
     cap = 4096
@@ -486,7 +538,7 @@ def test_partial_merge_hash_only_first_rows_keys_win(cuda_lib, oracle):
         bufs, plans = [], []
         for shard, base in ((shard0, 0), (shard1, m)):
             p = ExecutorBuilder(cuda_lib, cuda_lib.options(**opts)).build(plan, {0: schema})
-            p.push_table(0, pa.Table.from_batches([shard]))
+            p.push_table(0, shard)
             cuda_lib.check(cuda_lib.plan_execute_partial(p.handle, base))
             words = C.c_int32(0)
             cuda_lib.check(cuda_lib.plan_partials_row_words(p.handle, C.byref(words)))
