@@ -357,6 +357,8 @@ int SQLRS_API(plan_next)(sqlrs_plan* p, struct ArrowArray* out, struct ArrowSche
                          int32_t* has_batch);
 /* forget pushed tables / operator state, keep plan + device scratch (repeated runs) */
 int SQLRS_API(plan_reset)(sqlrs_plan* p);
+/* forget the batches pushed into ONE table slot (the other slots keep theirs: a plan re-run with one input replaced) */
+int SQLRS_API(plan_clear_table)(sqlrs_plan* p, int32_t table_slot);
 /* human-readable: which pipeline (fused / generic) and kernels the plan runs with */
 const char* SQLRS_API(plan_describe)(sqlrs_plan* p);
 void SQLRS_API(plan_destroy)(sqlrs_plan* p);

@@ -579,6 +579,9 @@ int sqlrs_oracle_plan_reset(sqlrs_plan* p) {
     p->results.clear();
   });
 }
+int sqlrs_oracle_plan_clear_table(sqlrs_plan* p, int32_t table_slot) {
+  return guarded([&] { p->tables.erase(table_slot); });
+}
 const char* sqlrs_oracle_plan_describe(sqlrs_plan* p) { return p->description.c_str(); }
 void sqlrs_oracle_plan_destroy(sqlrs_plan* p) { delete p; }
 int sqlrs_oracle_plan_execute_partial(sqlrs_plan* p, int64_t row_base) {

@@ -506,6 +506,12 @@ int sqlrs_plan_reset(sqlrs_plan* p) {
     p->impl.reset();
   });
 }
+int sqlrs_plan_clear_table(sqlrs_plan* p, int32_t table_slot) {
+  return guarded([&] {
+    if (!p) fail(SQLRS_ERR_INVALID_ARG, "plan is NULL");
+    p->impl.clear_table(table_slot);
+  });
+}
 const char* sqlrs_plan_describe(sqlrs_plan* p) { return p ? p->impl.describe() : ""; }
 void sqlrs_plan_destroy(sqlrs_plan* p) { delete p; }
 int sqlrs_plan_execute_partial(sqlrs_plan* p, int64_t row_base) {

@@ -91,6 +91,7 @@ void Plan::reset() {
   tables_.clear();
   partial_active_ = false;
 }
+void Plan::clear_table(int slot) { tables_.erase(slot); }
 
 // aggregate at `idx`, up to (excluding) finalisation.  A Filter directly below is fused into the aggregate's row
 // program unless SQLRS_FLAG_NO_FUSION asks for operator-at-a-time execution.

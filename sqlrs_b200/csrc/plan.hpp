@@ -20,6 +20,7 @@ class Plan {
   void execute();
   bool next(ArrowArray* out, ArrowSchema* out_schema);
   void reset();
+  void clear_table(int slot);
   void execute_partial(int64_t row_base);
   void export_partials(ArrowArray* out, ArrowSchema* out_schema);
   void clear_partials();

@@ -411,7 +411,10 @@ class DeviceBatch:
 def merge_topk_device(plan, group: TorchGroup, schema: pa.Schema, order_by, limit: int, state: dict, builder) -> List[pa.RecordBatch]:
     """`merge_topk` without leaving HBM until the final rows: the <= limit rows pending in `plan` (a DEVICE result) are copied
     into one fixed-size tensor [count | limit x columns], all-gathered, and rank 0 runs Limit(Order(Scan)) over the W x limit
-    candidate rows on the device — rank-major row order, so ties resolve as in the single-process run."""
+    candidate rows on the device — rank-major row order, so ties resolve as in the single-process run.
+    Rank 0 does not wait for the per-rank counts before it orders: it assumes the usual case (every rank returned `limit` rows),
+    enqueues the tail plan on the W x limit candidates, and looks at the counts — copied to pinned memory ahead of the tail —
+    when the tail's result has arrived; only if some rank had fewer rows is the tail run again over the exact candidates."""
     from .plan import PhysicalLimit, PhysicalOrder, PhysicalTableScan
 
     torch, W = group.torch, group.world
@@ -423,60 +426,90 @@ def merge_topk_device(plan, group: TorchGroup, schema: pa.Schema, order_by, limi
     key = ("topk", ncols, limit)
     if key not in state:
         state[key] = (torch.zeros(1 + ncols * limit, dtype=torch.int64, device=group.device),
-                      torch.empty(W * (1 + ncols * limit), dtype=torch.int64, device=group.device))
-    send, recv = state[key]
-    send[0] = n
+                      torch.empty(W * (1 + ncols * limit), dtype=torch.int64, device=group.device),
+                      torch.empty((ncols, W * limit), dtype=torch.int64, device=group.device),
+                      torch.empty(W, dtype=torch.int64, pin_memory=True))
+    send, recv, cand, counts_host = state[key]
+    send[:1].fill_(n)
     if shape is not None:
         body = send[1:].view(ncols, limit)
         plan.next_to_device([body[c].data_ptr() for c in range(ncols)])
-    _check_stream(plan, group)
+    shared = _check_stream(plan, group)
     group.dist.all_gather_into_tensor(recv, send)
     if group.rank != 0:
         return []
     every = recv.view(W, 1 + ncols * limit)
-    counts = every[:, 0].tolist()
-    _mark(group, "  top-k: candidates gathered, counts on the host")
-    total = int(sum(counts))
-    if total == W * limit:  # the usual case: every rank had at least `limit` rows — one strided copy, rank-major rows
-        body = every[:, 1:].reshape(W, ncols, limit).permute(1, 0, 2).contiguous()
-        cols = [body[c].view(-1) for c in range(ncols)]
-    else:
-        cols = [torch.cat([every[r, 1:].view(ncols, limit)[c, :counts[r]] for r in range(W)]) for c in range(ncols)]
+    counts_host.copy_(every[:, 0], non_blocking=True)
+    cand.view(ncols, W, limit).copy_(every[:, 1:].view(W, ncols, limit).permute(1, 0, 2))  # rank-major rows, one strided copy
     if "p_tail" not in state:
         tail = PhysicalLimit(limit, None, PhysicalOrder(order_by, PhysicalTableScan(0)))
         state["p_tail"] = builder.build(tail, {0: schema})
     p_tail = state["p_tail"]
-    p_tail.reset()
     dev = group.device.index if group.device.index is not None else 0
-    p_tail.push_table_device(0, DeviceBatch(schema, cols, total, dev))
+    if not shared:
+        torch.cuda.current_stream(group.device).synchronize()
+    if not state.get("tail_pushed"):  # the candidate buffer is the same memory every step: the tail plan keeps scanning it
+        p_tail.reset()
+        p_tail.push_table_device(0, DeviceBatch(schema, [cand[c] for c in range(ncols)], W * limit, dev))
+        state["tail_pushed"] = True
+    out = p_tail.run()
+    torch.cuda.current_stream(group.device).synchronize()  # counts_host is complete (a no-op after the tail's own result copy)
+    counts = counts_host.tolist()
+    _mark(group, "  top-k: tail plan over W x limit candidates")
+    if all(c == limit for c in counts):
+        return out
+    # some rank had fewer than `limit` rows: order exactly the rows that exist
+    cols = [torch.cat([every[r, 1:].view(ncols, limit)[c, :counts[r]] for r in range(W)]) for c in range(ncols)]
+    state["tail_pushed"] = False
+    p_tail.reset()
+    p_tail.push_table_device(0, DeviceBatch(schema, cols, int(sum(counts)), dev))
     return p_tail.run()
 
 
-def broadcast_rows(plan, group: TorchGroup, schema: pa.Schema) -> DeviceBatch:
+def broadcast_rows(plan, group: TorchGroup, schema: pa.Schema, state: Optional[dict] = None, while_waiting=None) -> DeviceBatch:
     """The rows `plan` (already executed on this rank's shard; ONE pending device result of fixed-width, NULL-free columns)
     produced on every rank, concatenated in rank order, on every rank — all-gathered device to device.  This is the
-    build-side broadcast of a broadcast-build / partitioned-probe join."""
+    build-side broadcast of a broadcast-build / partitioned-probe join.
+    `state`: a dict the caller keeps across calls (buffers and the packing index are reused while the row counts repeat);
+    `while_waiting`: host work that does not depend on the exchange, done while the row counts travel."""
     torch, W = group.torch, group.world
+    state = state if state is not None else {}
     shape = plan.result_shape()
     n, ncols = shape if shape is not None else (0, len(schema))
-    counts = torch.empty(W, dtype=torch.int64, device=group.device)
-    group.dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device=group.device))
-    counts = counts.tolist()  # sizes of the receive buffers: the one host round trip of this step
+    if "bc_counts" not in state:
+        state["bc_counts"] = (torch.empty(1, dtype=torch.int64, device=group.device), torch.empty(W, dtype=torch.int64, device=group.device),
+                              torch.empty(W, dtype=torch.int64, pin_memory=True))
+    mine, counts_dev, counts_host = state["bc_counts"]
+    mine.fill_(n)
+    group.dist.all_gather_into_tensor(counts_dev, mine)
+    counts_host.copy_(counts_dev, non_blocking=True)
+    arrived = torch.cuda.Event()
+    arrived.record(torch.cuda.current_stream(group.device))
+    if while_waiting is not None:
+        while_waiting()
+    arrived.synchronize()  # sizes of the receive buffers: the one host round trip of this step
+    counts = tuple(counts_host.tolist())
     _mark(group, "  broadcast: row counts known on the host")
-    most = max(max(counts), 1)
-    send = torch.empty((ncols, most), dtype=torch.int64, device=group.device)
+    most, total = max(max(counts), 1), int(sum(counts))
+    key = ("bc_bufs", ncols, counts)
+    if state.get("bc_key") != key:
+        # flat positions in recv [W, ncols, most] of the packed [ncols, total] layout: rank order = row order
+        rank_of = torch.repeat_interleave(torch.arange(W), torch.tensor(counts, dtype=torch.int64))
+        starts = torch.cumsum(torch.tensor((0,) + counts[:-1], dtype=torch.int64), 0)
+        within = torch.arange(total, dtype=torch.int64) - starts[rank_of]
+        flat = (rank_of * (ncols * most) + within).unsqueeze(0) + (torch.arange(ncols, dtype=torch.int64) * most).unsqueeze(1)
+        state["bc_key"] = key
+        state["bc_bufs"] = (torch.empty((ncols, most), dtype=torch.int64, device=group.device),
+                            torch.empty((W, ncols, most), dtype=torch.int64, device=group.device),
+                            torch.empty((ncols, max(total, 1)), dtype=torch.int64, device=group.device),
+                            flat.to(group.device))
+    send, recv, packed, flat = state["bc_bufs"]
     if shape is not None:
         plan.next_to_device([send[c].data_ptr() for c in range(ncols)])
     _check_stream(plan, group)
-    recv = torch.empty((W, ncols, most), dtype=torch.int64, device=group.device)
     group.dist.all_gather_into_tensor(recv, send)
-    total = int(sum(counts))
-    packed = torch.empty((ncols, max(total, 1)), dtype=torch.int64, device=group.device)
-    off = 0
-    for r in range(W):  # one strided copy per rank (all columns at once), rank order = row order
-        if counts[r]:
-            packed[:, off:off + counts[r]] = recv[r, :, :counts[r]]
-            off += counts[r]
+    if total:
+        torch.take(recv, flat, out=packed)  # one gather kernel: packed [ncols, total]
     dev = group.device.index if group.device.index is not None else 0
     _mark(group, "  broadcast: all-gather + packing enqueued")
     return DeviceBatch(schema, [packed[c, :total] for c in range(ncols)], total, dev)
@@ -564,6 +597,11 @@ def broadcast_build_join_aggregate(builder, group: TorchGroup, stage1, stage1_sc
     return result
 
 
+def _same_tables(prev: dict, now: dict) -> bool:
+    """the same DEVICE-resident tables as last time (a host batch is copied to the device on every call: that is the call's input)"""
+    return list(prev) == list(now) and all(prev[k] is now[k] and not isinstance(now[k], pa.RecordBatch) for k in now)
+
+
 def distributed_join_topk(builder, group: TorchGroup, *, build_plan, build_schemas, build_tables, query_plan, query_schemas, query_tables,
                           build_slot: int, order_by, limit: int, state: Optional[dict] = None) -> List[pa.RecordBatch]:
     """ORDER BY ... LIMIT query over a join tree whose fact tables are sharded so that the joins between them need no
@@ -586,15 +624,22 @@ def distributed_join_topk(builder, group: TorchGroup, *, build_plan, build_schem
         state["p_query"] = builder.build(query_plan, query_schemas)
     p_build, p_query = state["p_build"], state["p_query"]
     mark("")
-    p_build.reset()
-    p_query.reset()
-    _push(p_build, build_tables)
+    # tables that are the same objects as in the previous (completed) call stay pushed: only the exchanged build side changes
+    same = state.get("pushed") is not None and all(_same_tables(x, y) for x, y in zip(state["pushed"], (build_tables, query_tables)))
+    state["pushed"] = None  # (set again when this call completes: a failed call leaves the plans to a full reset)
+    if same:
+        p_query.clear_table(build_slot)
+        later = None
+    else:
+        p_build.reset()
+        p_query.reset()
+        _push(p_build, build_tables)
+        later = lambda: _push(p_query, query_tables)  # noqa: E731 — pushed while the row counts of the exchange travel
     p_build.execute()
     mark("build-side sub-plan (local shard)")
-    build_side = broadcast_rows(p_build, group, build_plan.output_schema(build_schemas))
+    build_side = broadcast_rows(p_build, group, build_plan.output_schema(build_schemas), state, while_waiting=later)
     mark("all-gather of its rows")
     p_query.push_table_device(build_slot, build_side)
-    _push(p_query, query_tables)
     mark("  query: tables pushed")
     if group.native_a2a and builder.lib.prefix == "sqlrs_":
         p_query.execute()
@@ -605,6 +650,7 @@ def distributed_join_topk(builder, group: TorchGroup, *, build_plan, build_schem
         mark("query plan (local shards)")
         out = merge_topk(p_query, group, local, order_by, limit)
     mark("top-k merge")
+    state["pushed"] = (dict(build_tables), dict(query_tables))
     return out
 
 

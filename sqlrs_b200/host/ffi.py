@@ -232,6 +232,7 @@ _SIGNATURES = {
     "plan_execute": (C.c_int, [C.c_void_p]),
     "plan_next": (C.c_int, [C.c_void_p, P(ArrowArray), P(ArrowSchema), P(C.c_int32)]),
     "plan_reset": (C.c_int, [C.c_void_p]),
+    "plan_clear_table": (C.c_int, [C.c_void_p, C.c_int32]),
     "plan_describe": (C.c_char_p, [C.c_void_p]),
     "plan_destroy": (None, [C.c_void_p]),
     "plan_execute_partial": (C.c_int, [C.c_void_p, C.c_int64]),

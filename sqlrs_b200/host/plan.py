@@ -291,6 +291,10 @@ class GpuPlan:
     def reset(self):
         self.lib.check(self.lib.plan_reset(self.handle))
 
+    def clear_table(self, table_slot: int):
+        """forget the batches of one table slot; the other slots keep theirs (re-run with one input replaced)"""
+        self.lib.check(self.lib.plan_clear_table(self.handle, table_slot))
+
     def scan_kernel_ms(self):
         """(device ms, launches) of the dominant scan kernel(s) in the last execute (needs FLAG_TIMING)."""
         n = C.c_int64(0)

@@ -145,6 +145,27 @@ def main():
             assert sum(b.num_rows for b in exp) == 10
             assert_batches_match(got, exp, rtol=1e-9)
         done.append("q3 co-partitioned top-k")
+
+        # ---- 4b. the same plans and state over a DIFFERENT customer table (every second customer): the tables kept pushed from the
+        # previous call are replaced, the exchange's cached buffers and packing index are rebuilt for the new row counts
+        n_c = tpch.num_rows(lib, d, tpch.CUSTOMER)
+        c_lo, c_hi = n_c * rank // world, n_c * (rank + 1) // world
+        half = tpch.device_table(lib, d, tpch.CUSTOMER, c_lo, c_lo + (c_hi - c_lo) // 2, columns=tpch.Q3_CUSTOMER_COLUMNS, device=dev)
+        for _ in range(2):
+            got = sqdist.distributed_join_topk(builder, group, build_plan=cust_plan, build_schemas={0: full_schemas[0]}, build_tables={0: half},
+                                               query_plan=full, query_schemas=full_schemas, query_tables={1: o_shard, 2: l_shard}, build_slot=0,
+                                               order_by=tpch.q3_tail_order_by(), limit=10, state=state)
+        halves = [torch.empty(0, dtype=torch.int64, device=dev) for _ in tpch.Q3_CUSTOMER_COLUMNS]
+        for r in range(world):  # the union of every rank's half shard, in rank order
+            lo_r, hi_r = n_c * r // world, n_c * (r + 1) // world
+            part = tpch.device_table(lib, d, tpch.CUSTOMER, lo_r, lo_r + (hi_r - lo_r) // 2, columns=tpch.Q3_CUSTOMER_COLUMNS, device=dev)
+            halves = [torch.cat([a, b]) for a, b in zip(halves, part.tensors)]
+        if rank == 0:
+            union = sqdist.DeviceBatch(full_schemas[0], halves, int(halves[0].numel()), local)
+            exp = single(full, full_schemas, {0: union, 1: whole(tpch.ORDERS, tpch.Q3_ORDERS_COLUMNS), 2: whole(tpch.LINEITEM, tpch.Q3_LINEITEM_COLUMNS)})
+            assert sum(b.num_rows for b in exp) == 10
+            assert_batches_match(got, exp, rtol=1e-9)
+        done.append("q3 co-partitioned top-k, build table replaced")
     torch.cuda.synchronize(dev)
     dist.barrier()
     dist.destroy_process_group()
