@@ -100,6 +100,20 @@ std::string hash_name(const std::string& full_source) {
 
 std::string jit_full_source(const std::string& skeleton, const std::string& generated) {
   std::string src;
+  // tuning experiments: SQLRS_B200_JIT_DEFINES="SQ_JUNROLL=12;SQ_JMINB=5" puts #defines in front of every kernel source
+  // (the skeletons guard their tunables with #ifndef); part of the source, hence of the cache key
+  if (const char* defs = std::getenv("SQLRS_B200_JIT_DEFINES")) {
+    std::string d(defs);
+    size_t pos = 0;
+    while (pos < d.size()) {
+      size_t semi = d.find(';', pos);
+      if (semi == std::string::npos) semi = d.size();
+      std::string one = d.substr(pos, semi - pos);
+      const size_t eq = one.find('=');
+      if (!one.empty()) src += "#define " + (eq == std::string::npos ? one : one.substr(0, eq) + " " + one.substr(eq + 1)) + "\n";
+      pos = semi + 1;
+    }
+  }
   src += embedded_source("prelude");
   src += "\n// ---- generated row program -------------------------------------------------\n";
   src += generated;

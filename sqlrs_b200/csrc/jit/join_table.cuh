@@ -25,7 +25,9 @@ struct SqJoin {           // mirrors sq::JoinTableView (kernels_aot.hpp)
   i64 n_inserted;
 };
 #define SQ_KV_EMPTY 0xffffffffffffffffULL
+#ifndef SQ_KV_L2_SLOTS
 #define SQ_KV_L2_SLOTS (4u << 20)  /* a kv table with more slots (> 64 MB) is not worth L2 space: its probes are single-use */
+#endif
 
 // (mirrors join_bloom_word / join_bloom_bits of kernels_aot.hpp: all 32-bit arithmetic on the two halves of the hash)
 __device__ __forceinline__ u32 sq_bloom_word(u64 h, u32 mask) { return (u32)(h >> 32) & mask; }

@@ -28,6 +28,12 @@
 #define SQ_JUNROLL 8
 #endif
 #define SQ_JBLOCK 256
+#ifndef SQ_PREFETCH
+#define SQ_PREFETCH 0  // L2 prefetch distance in warp trips (0 = off)
+#endif
+#ifndef SQ_JMINB
+#define SQ_JMINB 1  // __launch_bounds__ minimum CTAs per SM (register budget)
+#endif
 #define SQ_JQUEUE (SQ_JUNROLL * 32 + 32)
 
 // phase B for one candidate row: exact probe, matches in build insertion order, aggregate
@@ -71,7 +77,7 @@ __device__ __forceinline__ void sq_joinagg_candidate(const SqIn& in, const SqInB
   }
 }
 
-extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_kernel(SqIn in, SqInB inb, i64 n, i64 row_base, SqJoin jt, SqTable table, i64 batch_no,
+extern "C" __global__ void __launch_bounds__(SQ_JBLOCK, SQ_JMINB) sq_joinagg_kernel(SqIn in, SqInB inb, i64 n, i64 row_base, SqJoin jt, SqTable table, i64 batch_no,
                                                                            u32* __restrict__ status, u32* __restrict__ err) {
   __shared__ u32 queue_s[SQ_JBLOCK / 32][SQ_JQUEUE];
   __shared__ u64 queue_vs[SQ_JBLOCK / 32][SQ_PQMODE ? SQ_JQUEUE : 1];
@@ -84,6 +90,9 @@ extern "C" __global__ void __launch_bounds__(SQ_JBLOCK) sq_joinagg_kernel(SqIn i
   const u64 pol_keep = sq_l2_evict_last();
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 base = ((i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * SQ_JUNROLL; base < n; base += stride * SQ_JUNROLL) {
+#if SQ_PREFETCH
+    sq_probe_prefetch(in, base + SQ_PREFETCH * stride * SQ_JUNROLL, n, SQ_JUNROLL * 32, lane);  // this warp's rows SQ_PREFETCH trips ahead
+#endif
     SQ_PHASE_A(SQ_JUNROLL, base + u * 32 + lane)  // n < 2^32 (checked by the host)
     // ---- phase B: full warps only
     while (queued >= 32) {

@@ -12,8 +12,18 @@
 //   struct SqChainKey {u64 h; u64 kb; u32 knull;};  sq_chain_key(in, inb, r, b, k, e)  — join 2's build key over the joined row
 // then join_table.cuh.  HBM-bound on the scan of B's Filter/key columns; the inserts are random 16-byte atomics that overlap it.
 #define SQ_CBLOCK 256
+#ifndef SQ_CUNROLL
 #define SQ_CUNROLL 8
+#endif
+#ifndef SQ_CWAY
 #define SQ_CWAY 4  // candidates per lane in one phase-B pass (their dependent chains are interleaved stage by stage)
+#endif
+#ifndef SQ_PREFETCH
+#define SQ_PREFETCH 0  // L2 prefetch distance in trips (0 = off)
+#endif
+#ifndef SQ_CMINB
+#define SQ_CMINB 4  // __launch_bounds__ minimum CTAs per SM: 64 registers, 32 resident warps (72 registers / 24 warps unconstrained:
+#endif              // 6 % slower on the whole Q3' query at SF100, profiles/r02h_q3_knobs.txt)
 #define SQ_CQUEUE (SQ_CUNROLL * 32 + 32 * SQ_CWAY)
 
 struct SqChainOut {
@@ -158,7 +168,7 @@ __device__ __forceinline__ u32 sq_chain_batch(const SqIn& in, const SqInB& inb, 
 #endif
 
 // chunk_step > 1: only every chunk_step-th 2048-row chunk is processed (sampling, with out.kv == nullptr)
-extern "C" __global__ void __launch_bounds__(SQ_CBLOCK) sq_joinchain_kernel(SqIn in, SqInB inb, i64 n, SqJoin jt, SqChainOut out, i64 chunk_step) {
+extern "C" __global__ void __launch_bounds__(SQ_CBLOCK, SQ_CMINB) sq_joinchain_kernel(SqIn in, SqInB inb, i64 n, SqJoin jt, SqChainOut out, i64 chunk_step) {
   __shared__ u32 queue_s[SQ_CBLOCK / 32][SQ_CQUEUE];
   __shared__ u64 queue_vs[SQ_CBLOCK / 32][SQ_PQMODE ? SQ_CQUEUE : 1];
   bool any_err = false;
@@ -172,6 +182,9 @@ extern "C" __global__ void __launch_bounds__(SQ_CBLOCK) sq_joinchain_kernel(SqIn
   for (i64 trip = blockIdx.x;; trip += gridDim.x) {
     const i64 base = trip * chunk_step * (SQ_CBLOCK * SQ_CUNROLL) + (i64)(threadIdx.x & ~31) * SQ_CUNROLL;
     if (base >= n) break;
+#if SQ_PREFETCH
+    sq_probe_prefetch(in, base + SQ_PREFETCH * (i64)gridDim.x * chunk_step * (SQ_CBLOCK * SQ_CUNROLL), n, SQ_CUNROLL * 32, lane);
+#endif
     // ---- phase A: streaming Filter + key hash + Bloom test of join 1 (see joinagg.cuh)
     SQ_PHASE_A(SQ_CUNROLL, base + u * 32 + lane)  // n < 2^32 (checked by the host)
     // ---- phase B: full warps probe join 1's table and insert into join 2's

@@ -17,6 +17,8 @@ __device__ __forceinline__ i64 sq_ldg_i64(const void* p, i64 r) { return __ldg((
 __device__ __forceinline__ int sq_ldg_i32(const void* p, i64 r) { return __ldg(((const int*)p) + r); }
 __device__ __forceinline__ double sq_ldg_f64(const void* p, i64 r) { return __ldg(((const double*)p) + r); }
 __device__ __forceinline__ bool sq_ld_bit(const void* p, i64 r) { return (__ldg(((const u32*)p) + (r >> 5)) >> (r & 31)) & 1u; }
+// one 128-byte line of a column stream into L2 ahead of its use (no register is tied up, unlike an early load)
+__device__ __forceinline__ void sq_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- L2 residency control.  The fused join kernels mix three kinds of traffic through the 126 MB L2: a column stream (GBs,
 // no reuse: evict-first loads above), random single-use accesses to hash tables far larger than the L2 (hundreds of MB), and

@@ -218,9 +218,14 @@ __global__ void __launch_bounds__(kBlock) k_idx_valid(const int64_t* __restrict_
 // Packed (row-major) form of a group table, used for finalisation and for the partial/final exchange:
 // row 0 = header {number of groups, words per row, 0...}; row 1+i = [hash, min_row, knull, key bits x K,
 // accumulator words x W].  Rows land in arbitrary order (the consumer orders by min_row).
-__global__ void __launch_bounds__(kBlock) k_table_pack(TableView t, int n_keys, int n_acc, uint64_t* __restrict__ dst, unsigned long long cap_rows) {
+__global__ void __launch_bounds__(kBlock) k_table_pack(TableView t, int n_keys, int n_acc, uint64_t* __restrict__ dst, unsigned long long cap_rows,
+                                                        int mark_unchecked) {
   const uint32_t stride = gridDim.x * blockDim.x;
   const int words = 3 + n_keys + n_acc;
+  // the table was filled by a launch nobody has checked yet: if that launch ran out of per-CTA slots (status bit 0) or flagged an
+  // arithmetic error, the header count is pushed beyond any capacity — every consumer of the buffer then takes its overflow path
+  if (mark_unchecked && blockIdx.x == 0 && threadIdx.x == 0 && ((t.counters[2] & 1u) || (t.counters[3] & 1u)))
+    atomicAdd((unsigned long long*)dst, 1ULL << 40);
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
     if (t.state[s] != 2u) continue;
     const unsigned long long o = atomicAdd((unsigned long long*)dst, 1ULL);
@@ -516,8 +521,8 @@ void launch_iota_filter_valid(const int64_t* idx, int64_t m, uint32_t* valid_out
   SQ_CUDA(cudaGetLastError());
 }
 
-void launch_table_pack(const TableView& t, int n_keys, int n_acc, uint64_t* dst, uint64_t cap_rows, cudaStream_t stream) {
-  k_table_pack<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, dst, cap_rows);
+void launch_table_pack(const TableView& t, int n_keys, int n_acc, uint64_t* dst, uint64_t cap_rows, cudaStream_t stream, bool mark_unchecked) {
+  k_table_pack<<<grid_for(t.capacity, kBlock, 148 * 8), kBlock, 0, stream>>>(t, n_keys, n_acc, dst, cap_rows, mark_unchecked ? 1 : 0);
   count_launch();
   SQ_CUDA(cudaGetLastError());
 }

@@ -57,7 +57,8 @@ struct TableView {
 // Packed row-major form of a group table: row 0 = header {group count, ...}, row 1+i =
 // [hash, min_row, knull, key bits x K, accumulator words x W] (3+K+W u64 words per row).
 // dst must hold (cap_rows + 1) rows and have its header zeroed; groups beyond cap_rows are counted, not written.
-void launch_table_pack(const TableView& t, int n_keys, int n_acc, uint64_t* dst, uint64_t cap_rows, cudaStream_t stream);
+// mark_unchecked: see k_table_pack (a table filled by a launch whose status bits nobody has read yet)
+void launch_table_pack(const TableView& t, int n_keys, int n_acc, uint64_t* dst, uint64_t cap_rows, cudaStream_t stream, bool mark_unchecked = false);
 // the n groups packed in ascending first-row order (dst: (n + 1) rows; header written)
 // slot_list (optional): a complete device list of the n occupied slots — skips the scan over the capacity;
 // key_bits: number of significant bits of the min_row keys (fewer radix passes)

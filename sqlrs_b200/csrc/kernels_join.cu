@@ -394,8 +394,12 @@ __global__ void __launch_bounds__(kBlock) k_slot_keys(const int32_t* __restrict_
 }  // namespace
 
 uint32_t join_bloom_words(int64_t n_build) {
+  static const int shift = [] {  // tuning experiments: SQLRS_B200_BLOOM_SHIFT (words >= n_build >> shift; 1 = 16+ bits per key)
+    const char* e = std::getenv("SQLRS_B200_BLOOM_SHIFT");
+    return e ? std::min(6, std::max(0, atoi(e))) : 1;
+  }();
   uint64_t w = 1024;
-  while (w < (uint64_t)n_build / 2 && w < (1ULL << 25)) w <<= 1;
+  while (w < ((uint64_t)n_build >> shift) && w < (1ULL << 25)) w <<= 1;
   return (uint32_t)w;
 }
 

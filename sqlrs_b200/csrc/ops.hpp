@@ -120,7 +120,16 @@ class AggOp {
   // consumer (finish / settle), and a table that turned out too small raises RetrySizingError there
   void push_join(const DBatch& probe, class JoinOp& join, const ExprCopy& probe_pred, bool defer = false);
   void settle();  // reads the counters of a deferred push_join now (one synchronisation)
+  void settle_hint_sized() {  // only if the table was sized from a hint whose validity nobody has checked yet
+    if (hint_sized_) settle();
+  }
   void set_row_base(int64_t first_global_row);
+  // partial/final split: let the first batch's sq_agg_small launch go unchecked (no host synchronisation between the scan kernel
+  // and the exchange that follows).  Whether its per-CTA slots overflowed is learnt at the next counter read (RetrySizingError:
+  // the caller re-runs without deferral); export_partials_device does not read counters: it marks the packed buffer's
+  // header (count > any capacity) so that every rank of the exchange sees it.
+  void set_defer_tier_check(bool on) { defer_tier_check_ = on && !defer_disabled_; }
+  bool tier_check_pending() const { return tier_pending_; }
 
   bool has_distinct() const { return distinct_ != nullptr; }
   // DISTINCT aggregates keep one group table per DISTINCT aggregate (the set elements) next to the table of the plain
@@ -187,10 +196,19 @@ class AggOp {
   std::string last_path_;
   double scan_kernel_ms_ = 0;      // SQLRS_FLAG_TIMING: device time of the scan kernels (CUDA events on ctx_.stream)
   int64_t scan_kernel_launches_ = 0;
+  bool defer_tier_check_ = false, defer_disabled_ = false, tier_pending_ = false;
+  cudaEvent_t pend_e0_ = nullptr, pend_e1_ = nullptr;  // the deferred launch's timer, resolved on demand
+  void resolve_pending_timer();
 
  public:
-  double scan_kernel_ms() const { return scan_kernel_ms_; }
-  int64_t scan_kernel_launches() const { return scan_kernel_launches_; }
+  double scan_kernel_ms() {
+    resolve_pending_timer();
+    return scan_kernel_ms_;
+  }
+  int64_t scan_kernel_launches() {
+    resolve_pending_timer();
+    return scan_kernel_launches_;
+  }
 };
 
 }  // namespace sq

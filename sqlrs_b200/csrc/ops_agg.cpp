@@ -95,6 +95,11 @@ struct ScanTimer {
     cudaEventElapsedTime(&ms, e0, e1);
     return ms;
   }
+  void release(cudaEvent_t* a, cudaEvent_t* b) {  // hands the events over (a launch whose end nobody waits for here)
+    *a = e0;
+    *b = e1;
+    e0 = e1 = nullptr;
+  }
   ~ScanTimer() {
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
@@ -203,6 +208,20 @@ AggOp::AggOp(std::vector<AggSpec> aggs, std::vector<ExprCopy> group_by, std::vec
 }
 AggOp::~AggOp() {
   if (pinned_) cudaFreeHost(pinned_);
+  if (pend_e0_) cudaEventDestroy(pend_e0_);
+  if (pend_e1_) cudaEventDestroy(pend_e1_);
+}
+
+void AggOp::resolve_pending_timer() {
+  if (!pend_e1_) return;
+  float ms = 0.f;
+  cudaEventSynchronize(pend_e1_);
+  cudaEventElapsedTime(&ms, pend_e0_, pend_e1_);
+  scan_kernel_ms_ += ms;
+  scan_kernel_launches_ += 1;
+  cudaEventDestroy(pend_e0_);
+  cudaEventDestroy(pend_e1_);
+  pend_e0_ = pend_e1_ = nullptr;
 }
 
 // ------------------------------------------------------------------ code generation
@@ -588,6 +607,8 @@ void AggOp::reset() {
   slot_list_complete_ = false;
   slot_list_pending_ = false;
   hint_sized_ = false;
+  tier_pending_ = false;
+  resolve_pending_timer();  // (into the totals that are zeroed below)
   if (table_) init_table_contents(*table_);
   rows_seen_ = 0;
   batches_seen_ = 0;
@@ -619,6 +640,15 @@ void AggOp::read_counters(uint32_t* out4) {
     slot_list_pending_ = false;
     slot_list_complete_ = out4[1] == out4[0];
     SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 1, 0, 4, ctx_.stream));
+  }
+  if (tier_pending_) {  // a deferred sq_agg_small launch: did its per-CTA slots hold every group?
+    tier_pending_ = false;
+    if (out4[2] & 1u) {
+      defer_disabled_ = true;  // this operator's input has more groups than the small tier holds: never defer again
+      defer_tier_check_ = false;
+      SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 2, 0, 4, ctx_.stream));
+      throw RetrySizingError{};
+    }
   }
   if (hint_sized_) {
     hint_sized_ = false;
@@ -662,6 +692,7 @@ void AggOp::push(const DBatch& batch_in) {
   slot_list_complete_ = false;
   ctx_.activate();
   ctx_.reap();
+  if (tier_pending_) settle();  // a second batch after a deferred first one: its tier is decided now
   Compiled& c0 = compiled_for(batch_in);
   // MIN / MAX over Utf8 columns: re-express what has been accumulated so far and this batch's ids in the string pool's
   // CURRENT byte-wise ranks (the pool may have grown since the last batch), as rank << 32 | id
@@ -757,6 +788,18 @@ void AggOp::push(const DBatch& batch_in) {
     timer.stop();
     void* args_merge[] = {&part, &n_entries, &tv, &bn, &status};
     jit_launch(c.merge, (unsigned)div_up(n_entries, 128), 128, 0, ctx_.stream, args_merge);
+    if (defer_tier_check_ && batch_no == 0 && (K == 0 || opt_.match_mode == SQLRS_MATCH_HASH_AND_KEY) && c.utf8_minmax_cols.empty()) {
+      // partial/final split: nothing synchronises here; the overflow bit is looked at by the next counter read, or travels
+      // in the header of the packed partial buffer (see set_defer_tier_check)
+      tier_pending_ = true;
+      counters_stale_ = true;
+      resolve_pending_timer();
+      if (timer.enabled) timer.release(&pend_e0_, &pend_e1_);
+      SQ_CUDA(cudaMemsetAsync((uint32_t*)table_->counters->p + 1, 0, 4, ctx_.stream));  // (what flush_new_slots does)
+      last_path_ = "sq_agg_small (private shared-memory accumulators, " + std::to_string(c.slots) + " slots x " + std::to_string(c.block) +
+                   " threads, grid " + std::to_string(grid) + ") + sq_agg_merge, tier check deferred";
+      return;
+    }
     read_counters(hc);
     scan_kernel_ms_ += timer.elapsed_ms();
     scan_kernel_launches_ += timer.enabled ? 1 : 0;
@@ -1465,7 +1508,7 @@ void AggOp::export_partials_device(uint64_t* dst, int64_t cap_rows) {
   ctx_.activate();
   const int words = partial_row_words();
   SQ_CUDA(cudaMemsetAsync(dst, 0, (size_t)words * 8, ctx_.stream));
-  if (table_ && cap_rows > 0) launch_table_pack(table_->view(), table_->n_keys, table_->n_acc, dst, (uint64_t)cap_rows, ctx_.stream);
+  if (table_ && cap_rows > 0) launch_table_pack(table_->view(), table_->n_keys, table_->n_acc, dst, (uint64_t)cap_rows, ctx_.stream, tier_pending_);
 }
 
 int64_t AggOp::export_partials_partitioned(uint64_t* dst, int n_parts, int64_t cap_rows) {
@@ -1485,6 +1528,7 @@ int64_t AggOp::export_partials_partitioned(uint64_t* dst, int n_parts, int64_t c
 
 void AggOp::clear_partials() {
   ctx_.activate();
+  tier_pending_ = false;  // (the state the check was about is discarded; a packed export already carries the overflow mark)
   slot_list_complete_ = false;
   if (table_) init_table_contents(*table_);
   level_ = 0;

@@ -59,6 +59,12 @@ ProbeProgram gen_probe_program(const std::vector<ColInfo>& cols, const std::vect
       if (std::find(tile_cols.begin(), tile_cols.end(), c) == tile_cols.end()) tile_cols.push_back(c);
     }
   }
+  // L2 prefetch of the 8-byte columns the probe program streams: `rows` rows starting at row0 (lane L takes the L-th 128-byte line)
+  s << "__device__ __forceinline__ void sq_probe_prefetch(const SqIn& in, i64 row0, i64 n, int rows, int lane) {\n";
+  s << "  const i64 r = row0 + (i64)lane * 16;\n  if (lane * 16 >= rows || r >= n) return;\n";
+  if (ok)
+    for (int c : tile_cols) s << "  sq_prefetch_l2((const char*)in.col[" << c << "] + r * 8);\n";
+  s << "}\n";
   if (ok && !tile_cols.empty() && tile_cols.size() <= 3) {
     std::string tb = body;
     auto replace_all = [&](const std::string& from, const std::string& to) {

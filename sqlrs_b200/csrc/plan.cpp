@@ -117,6 +117,7 @@ AggOp& Plan::run_agg(int idx) {
   description_ += op.describe() + "; ";
   scan_kernel_ms_ = op.scan_kernel_ms();
   scan_kernel_launches_ = op.scan_kernel_launches();
+  scan_from_partial_ = false;
   return op;
 }
 
@@ -252,15 +253,39 @@ void Plan::execute_partial(int64_t row_base) {
     partial_op_->reset();
     partial_active_ = true;
     partial_sel_ = 0;
+    partial_row_base_ = row_base;
+    partial_op_->set_defer_tier_check(fusion() && partial_defer_ok_);
     partial_op_->set_row_base(row_base);
     const Needed need = fusion() ? agg_child_needs(n, fused, width_of(child)) : Needed();
     if (!feed_fused_join(*partial_op_, child, fused, need))
       for (const DBatch& b : run(child, need)) partial_op_->push(b);
-    partial_op_->settle();  // a hint-sized group table is checked here (one counter read), before anything is exported
+    partial_op_->settle_hint_sized();  // a hint-sized group table is checked here (one counter read), before anything is exported
   });
   description_ += partial_op_->describe() + "; ";
-  scan_kernel_ms_ = partial_op_->scan_kernel_ms();
-  scan_kernel_launches_ = partial_op_->scan_kernel_launches();
+  scan_from_partial_ = true;  // (read on demand: a deferred launch's timer is not waited for here)
+}
+
+// a partial run whose first sq_agg_small launch went unchecked (AggOp::set_defer_tier_check): read its status now; if it ran out
+// of slots, run the partial aggregation again the checked way (the tier escalates inside that run)
+void Plan::settle_partial() {
+  if (!partial_op_ || !partial_op_->tier_check_pending()) return;
+  try {
+    partial_op_->settle();
+  } catch (const RetrySizingError&) {
+    const int sel = partial_sel_;
+    partial_defer_ok_ = false;
+    execute_partial(partial_row_base_);
+    partial_defer_ok_ = true;  // (the operator itself remembers that deferring does not pay for this input)
+    partial_sel_ = sel;
+  }
+}
+double Plan::scan_kernel_ms() {
+  if (scan_from_partial_ && partial_op_) scan_kernel_ms_ = partial_op_->scan_kernel_ms();
+  return scan_kernel_ms_;
+}
+int64_t Plan::scan_kernel_launches() {
+  if (scan_from_partial_ && partial_op_) scan_kernel_launches_ = partial_op_->scan_kernel_launches();
+  return scan_kernel_launches_;
 }
 int Plan::partials_tables() const {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "partials_tables before execute_partial");
@@ -284,6 +309,7 @@ void Plan::export_partials_device(uint64_t* dst, int64_t cap_rows) {
 }
 int64_t Plan::export_partials_partitioned(uint64_t* dst, int n_parts, int64_t cap_rows) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
+  settle_partial();
   const int64_t g = partial_op_->partial_table(partial_sel_).export_partials_partitioned(dst, n_parts, cap_rows);
   if (ctx_.own_stream) SQ_CUDA(cudaStreamSynchronize(ctx_.stream));
   return g;
@@ -344,10 +370,12 @@ void Plan::push_table_batched(int slot, const DBatch& whole, int64_t batch_rows)
 }
 void Plan::merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
+  settle_partial();
   partial_op_->partial_table(partial_sel_).merge_partials_device(src, n_bufs, cap_rows);
 }
 void Plan::export_partials(ArrowArray* out, ArrowSchema* out_schema) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "export_partials before execute_partial");
+  settle_partial();
   partial_op_->partial_table(partial_sel_).export_partials(out, out_schema);
 }
 void Plan::clear_partials() {
@@ -356,10 +384,12 @@ void Plan::clear_partials() {
 }
 void Plan::merge_partials(const DBatch& partials) {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "merge_partials before execute_partial");
+  settle_partial();
   partial_op_->partial_table(partial_sel_).merge_partials(partials);
 }
 void Plan::finish_partial() {
   if (!partial_active_) fail(SQLRS_ERR_INVALID_ARG, "finish before execute_partial");
+  settle_partial();
   results_.emplace_back();
   partial_op_->finish_host(&results_.back().arr, &results_.back().sch);
   results_.back().on_host = true;

@@ -36,8 +36,8 @@ class Plan {
   void push_table_batched(int slot, const DBatch& whole, int64_t batch_rows);
   void merge_partials_device(const uint64_t* src, int n_bufs, int64_t cap_rows);
   const char* describe() const { return description_.c_str(); }
-  double scan_kernel_ms() const { return scan_kernel_ms_; }
-  int64_t scan_kernel_launches() const { return scan_kernel_launches_; }
+  double scan_kernel_ms();
+  int64_t scan_kernel_launches();
   Ctx& ctx() { return ctx_; }
 
  private:
@@ -89,6 +89,10 @@ class Plan {
   std::unique_ptr<AggOp> partial_op_;  // root aggregate of execute_partial(), kept across runs
   bool partial_active_ = false;        // between execute_partial and finish_partial
   int partial_sel_ = 0;                // table of partial_op_ the partial-state calls address
+  int64_t partial_row_base_ = 0;
+  bool partial_defer_ok_ = true;       // execute_partial may leave the first scan launch unchecked (settle_partial)
+  bool scan_from_partial_ = false;     // scan_kernel_ms() reports partial_op_'s timers
+  void settle_partial();
   std::string description_;
   std::vector<JoinChainOp*> pending_chains_;  // runs sized by hints, to be validated once the stream has been synchronised
   double scan_kernel_ms_ = 0;

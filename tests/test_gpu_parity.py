@@ -507,11 +507,50 @@ def test_distinct_aggregates_in_the_partial_final_split(cuda_lib, oracle, groupe
             sqdist._merge_partials(target, piece)
     cuda_lib.check(cuda_lib.plan_finish_partial(target.handle))
     assert_batches_match(target.collect(), exp)
-    with pytest.raises(ex.ExecutorError):
+    with pytest.raises(ffi.ExecutorError):
         cuda_lib.check(cuda_lib.plan_execute_partial(a.handle, 0))
         cuda_lib.check(cuda_lib.plan_select_partials_table(a.handle, 3))
     for p in plans:
         p.close()
+
+
+def test_partial_run_defers_the_tier_check_and_recovers(cuda_lib, oracle):
+    """execute_partial leaves the first sq_agg_small launch unchecked (no synchronisation before the exchange).  With more groups
+    than that tier holds, the packed device export carries an impossible count (every rank of an exchange sees it), and any
+    call that needs the real state re-runs the partial aggregation the checked way; later runs of the plan do not defer."""
+    import torch
+    from sqlrs_b200.host import distributed as sqdist
+    from sqlrs_b200.host.plan import PhysicalHashAgg, PhysicalTableScan
+
+    rng = np.random.default_rng(5)
+    n, groups = 300_000, 2000
+    schema = pa.schema([pa.field("k", pa.int64()), pa.field("v", pa.int64())])
+    table = pa.RecordBatch.from_arrays([pa.array(rng.integers(0, groups, n)), pa.array(rng.integers(-100, 100, n))], schema=schema)
+    plan = PhysicalHashAgg([AggFunc("Sum", [InputRef(1, I64)]), AggFunc("Count", [InputRef(1, I64)])], [InputRef(0, I64)], PhysicalTableScan(0))
+    opts = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    exp, _ = _run_plan(oracle, plan, {0: schema}, {0: table}, None, **opts)
+    p = ExecutorBuilder(cuda_lib, cuda_lib.options(**opts)).build(plan, {0: schema})
+    p.push_table(0, table)
+    words = C.c_int32(0)
+    cap = 1 << 16
+    for attempt in range(2):
+        cuda_lib.check(cuda_lib.plan_execute_partial(p.handle, 0))
+        cuda_lib.check(cuda_lib.plan_partials_row_words(p.handle, C.byref(words)))
+        buf = torch.zeros((cap + 1) * words.value, dtype=torch.int64, device="cuda")
+        cuda_lib.check(cuda_lib.plan_export_partials_device(p.handle, C.c_void_p(buf.data_ptr()), cap))
+        torch.cuda.synchronize()
+        header = int(buf[0].item())
+        if attempt == 0:
+            assert header >= 1 << 40, header  # unchecked and overflowed: marked
+        else:
+            assert header == groups  # the operator remembered: checked run, the real group table
+        part = sqdist._export_partials(p)  # needs the real state: settles, re-runs if the deferred launch had overflowed
+        assert part.num_rows == groups
+        cuda_lib.check(cuda_lib.plan_clear_partials(p.handle))
+        sqdist._merge_partials(p, part)
+        cuda_lib.check(cuda_lib.plan_finish_partial(p.handle))
+        assert_batches_match(p.collect(), exp)
+    p.close()
 
 
 def test_partial_merge_hash_only_first_rows_keys_win(cuda_lib, oracle):
