@@ -167,7 +167,7 @@ __device__ __forceinline__ u32 sq_chain_batch(const SqIn& in, const SqInB& inb, 
 #define SQ_CHAIN_BATCHED 0
 #endif
 
-// chunk_step > 1: only every chunk_step-th 2048-row chunk is processed (sampling, with out.kv == nullptr)
+// chunk_step > 1: only every chunk_step-th chunk (SQ_CBLOCK x SQ_CUNROLL rows) is processed (sampling, with out.kv == nullptr)
 extern "C" __global__ void __launch_bounds__(SQ_CBLOCK, SQ_CMINB) sq_joinchain_kernel(SqIn in, SqInB inb, i64 n, SqJoin jt, SqChainOut out, i64 chunk_step) {
   __shared__ u32 queue_s[SQ_CBLOCK / 32][SQ_CQUEUE];
   __shared__ u64 queue_vs[SQ_CBLOCK / 32][SQ_PQMODE ? SQ_CQUEUE : 1];

@@ -697,6 +697,18 @@ bool JoinOp::finish(DBatch* result) {
 }
 
 // ------------------------------------------------------------------ join chain (csrc/jit/joinchain.cuh)
+namespace {
+// rows per lane per trip of sq_joinchain_kernel (SQ_CUNROLL; tuning experiments: SQLRS_B200_CUNROLL)
+int chain_unroll() {
+  static const int u = [] {
+    const char* e = std::getenv("SQLRS_B200_CUNROLL");
+    return e ? std::min(16, std::max(1, atoi(e))) : 8;
+  }();
+  return u;
+}
+int64_t chain_trip_rows() { return 256LL * chain_unroll(); }  // SQ_CBLOCK x SQ_CUNROLL
+}  // namespace
+
 JoinChainOp::JoinChainOp(const Options& opt) : ctx_(opt), opt_(opt) {}
 JoinChainOp::~JoinChainOp() {
   if (host_) cudaFreeHost(host_);
@@ -705,6 +717,7 @@ JoinChainOp::~JoinChainOp() {
 std::string JoinChainOp::debug_source(const std::vector<ColInfo>& build_cols, const std::vector<ColInfo>& probe_cols, const std::vector<ExprCopy>& right_keys1,
                                       const ExprCopy& probe_pred1, const ExprCopy& key2, int* key_dtype) {
   std::ostringstream s;
+  s << "#define SQ_CUNROLL " << chain_unroll() << "\n";
   s << gen_input_decls(probe_cols) << gen_build_decls(build_cols);
   s << gen_probe_program(probe_cols, right_keys1, probe_pred1, true).src;
   RowProgram prog(build_cols, probe_cols);  // joined mode: join 1's output row
@@ -812,7 +825,7 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
     int64_t n_arg = n, step = chunk_step;
     JoinTableView jv = jt;
     void* args[] = {in_blob.data(), inb_blob.data(), &n_arg, &jv, &out, &step};
-    const int64_t trips = div_up(div_up(n, 2048), chunk_step);
+    const int64_t trips = div_up(div_up(n, chain_trip_rows()), chunk_step);
     const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(trips, 1), (int64_t)sms * per_sm);
     KernelEvent ev(opt_.flags, ctx_.stream, out.kv ? "sq_joinchain_kernel" : "sq_joinchain_kernel (sample count)");
     jit_launch(kernel, grid, 256, 0, ctx_.stream, args);
@@ -821,7 +834,7 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
   // ---- how many rows will join 1 yield?  Exact count of the previous run over tables of the same size, else a strided sample
   int64_t est = hint_inserted_;
   if (!optimistic) {
-    const int64_t chunks = div_up(n, 2048);
+    const int64_t chunks = div_up(n, chain_trip_rows());
     const int64_t step = std::max<int64_t>(1, chunks / 4096);  // ~8 M sampled rows at most
     ChainOut cnt{nullptr, nullptr, 0, 0, (uint32_t*)status->p, (unsigned long long*)((uint32_t*)status->p + 4)};
     launch(cnt, step);
