@@ -64,15 +64,21 @@ def measured_peak():
 
 
 def source_fingerprint():
-    """Hash of the kernel sources: `roofline.traffic` comes from a committed ncu capture and is only reported while the
-    kernels are the ones that were captured (profiles/r02_traffic.json carries the fingerprint of its capture)."""
-    h = hashlib.sha1()
-    base = os.path.join(ROOT, "sqlrs_b200", "csrc")
-    names = sorted(os.listdir(os.path.join(base, "jit")))
-    for name in [os.path.join("jit", n) for n in names if n.endswith(".cuh")] + ["codegen.cpp", "ops_agg.cpp", "ops_join.cpp", "kernels_join.cu"]:
-        with open(os.path.join(base, name), "rb") as f:
-            h.update(f.read())
-    return h.hexdigest()[:16]
+    """Hash of the complete CUDA sources (prelude + generated row program + skeletons) of the kernels the benchmark plans run:
+    `roofline.traffic` comes from a committed ncu capture and is only reported while the kernels are the ones that were
+    captured (profiles/r02_traffic.json carries the fingerprint of its capture)."""
+    if not _FINGERPRINT:
+        import __graft_entry__ as entry
+        from sqlrs_b200.host import ffi
+
+        h = hashlib.sha1()
+        for src in entry.benchmark_kernel_sources(ffi.load(), compile=False):
+            h.update(src.encode())
+        _FINGERPRINT.append(h.hexdigest()[:16])
+    return _FINGERPRINT[0]
+
+
+_FINGERPRINT = []
 
 
 def ncu_traffic(workload, kernel):

@@ -68,8 +68,8 @@ extern "C" {
 #define SQLRS_DT_INT32 2
 #define SQLRS_DT_INT64 3
 #define SQLRS_DT_FLOAT64 4
-#define SQLRS_DT_UTF8 5 /* CUDA library: dictionary-encoded on ingest (string pool ids in HBM), decoded on export; ordering comparisons in
-                           expressions (<, <=, >, >=) and MIN / MAX over Utf8 EXPRESSIONS return SQLRS_ERR_UNSUPPORTED */
+#define SQLRS_DT_UTF8 5 /* CUDA library: dictionary-encoded on ingest (string pool ids in HBM), decoded on export; =, <> compare ids, <, <=, >, >=
+                           the pool's byte-wise ranks; MIN / MAX over Utf8 EXPRESSIONS and Utf8 casts return SQLRS_ERR_UNSUPPORTED */
 
 /* ---- expression bytecode: flattened BoundExpr, src/binder/expression/mod.rs:18-27
  * Postfix order: children first (left then right), then the node.  `Alias` is

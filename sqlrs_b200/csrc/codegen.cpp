@@ -270,12 +270,15 @@ Val RowProgram::comparison(const Val& l, const Val& r, int op) {
   if (l.dtype != r.dtype)
     fail(SQLRS_ERR_ARROW, std::string("Invalid argument error: comparing ") + dtype_name(l.dtype) + " with " + dtype_name(r.dtype));
   if (l.dtype == SQLRS_DT_NULL) fail(SQLRS_ERR_ARROW, "comparison of Null arrays is not supported");
-  // Utf8 values are string-pool ids: equal strings have equal ids; the ORDER of two strings is not the order of their ids
-  if (l.dtype == SQLRS_DT_UTF8 && op != SQLRS_OP_EQ && op != SQLRS_OP_NE)
-    fail(SQLRS_ERR_UNSUPPORTED, "ordering comparisons (<, <=, >, >=) of Utf8 values are not supported by the CUDA backend");
   const char* o = op == SQLRS_OP_GT ? ">" : op == SQLRS_OP_LT ? "<" : op == SQLRS_OP_GE ? ">=" : op == SQLRS_OP_LE ? "<=" : op == SQLRS_OP_EQ ? "==" : "!=";
   std::string key = "cmp" + std::to_string(op) + "_" + std::to_string(l.id) + "_" + std::to_string(r.id);
   std::string a = vname(l.id), b = vname(r.id);
+  // Utf8 values are string-pool ids: equal strings have equal ids; the ORDER of two strings is the order of their byte-wise
+  // ranks (csrc/jit/strrank.cuh; a NULL row's id is not looked up)
+  if (l.dtype == SQLRS_DT_UTF8 && op != SQLRS_OP_EQ && op != SQLRS_OP_NE) {
+    a = "sq_str_rank(" + nname(l.id) + " ? " + a + " : 0)";
+    b = "sq_str_rank(" + nname(r.id) + " ? " + b + " : 0)";
+  }
   if (l.dtype == SQLRS_DT_BOOL) {
     a = "(int)" + a;
     b = "(int)" + b;

@@ -92,6 +92,10 @@ struct KernelEvent {
   }
 };
 
+// device copy of the string pool's byte-wise rank table (int32 per pool id) on the current device, brought up to date with the
+// pool on `stream` (device.cpp); what Utf8 ordering comparisons inside expressions read (csrc/jit/strrank.cuh)
+const void* string_rank_table(cudaStream_t stream);
+
 inline const char* dtype_name(int dt) {
   switch (dt) {
     case SQLRS_DT_NULL: return "Null";

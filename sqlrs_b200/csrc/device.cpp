@@ -52,6 +52,36 @@ std::vector<int32_t> StringPool::ranks() const {
   return rank;
 }
 
+// One rank table per device, rebuilt when the pool has grown since the last call.  The upload is ordered on the caller's stream
+// and waited for (the staging vector is reused); kernels already enqueued on that stream read the previous contents first.
+// A table that outgrows its buffer moves to a new one; old buffers are kept (a kernel on another stream may still read them).
+const void* string_rank_table(cudaStream_t stream) {
+  struct Entry {
+    void* buf = nullptr;
+    size_t capacity = 0;
+    int64_t ranked = -1;
+  };
+  static std::mutex mu;
+  static std::map<int, Entry> tables;
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  SQ_CUDA(cudaGetDevice(&dev));
+  Entry& e = tables[dev];
+  const int64_t n = StringPool::instance().size();
+  if (e.ranked == n && e.buf) return e.buf;
+  const std::vector<int32_t> ranks = StringPool::instance().ranks();
+  if (!e.buf || ranks.size() > e.capacity) {
+    e.capacity = std::max<size_t>(2 * ranks.size(), 1024);
+    SQ_CUDA(cudaMalloc(&e.buf, e.capacity * 4));
+  }
+  if (!ranks.empty()) {
+    SQ_CUDA(cudaMemcpyAsync(e.buf, ranks.data(), ranks.size() * 4, cudaMemcpyHostToDevice, stream));
+    SQ_CUDA(cudaStreamSynchronize(stream));
+  }
+  e.ranked = (int64_t)ranks.size();
+  return e.buf;
+}
+
 // ------------------------------------------------------------------ kernel events (SQLRS_FLAG_KERNEL_EVENTS)
 namespace {
 struct EventRec {

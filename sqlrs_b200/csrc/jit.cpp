@@ -20,6 +20,8 @@ struct JitKernel {
   CUfunction fn = nullptr;
   CUmodule mod = nullptr;
   size_t smem_opt_in = 0;
+  CUdeviceptr rank_sym = 0;          // address of the module's sq_rank_table (0: the kernel compares no strings by order)
+  const void** rank_value = nullptr; // persistent host cell the pointer is copied from
 };
 
 namespace {
@@ -32,6 +34,8 @@ struct Driver {
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+  CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
+  CUresult (*MemcpyHtoDAsync)(CUdeviceptr, const void*, size_t, CUstream) = nullptr;
 };
 
 std::mutex g_mu;
@@ -58,6 +62,8 @@ void ensure_driver() {
   resolve("cuFuncSetAttribute", g_drv.FuncSetAttribute);
   resolve("cuGetErrorString", g_drv.GetErrorString);
   resolve("cuOccupancyMaxActiveBlocksPerMultiprocessor", g_drv.OccupancyMaxActiveBlocksPerMultiprocessor);
+  resolve("cuModuleGetGlobal", g_drv.ModuleGetGlobal);
+  resolve("cuMemcpyHtoDAsync", g_drv.MemcpyHtoDAsync);
   g_drv_ready = true;
 }
 
@@ -115,6 +121,7 @@ std::string jit_full_source(const std::string& skeleton, const std::string& gene
     }
   }
   src += embedded_source("prelude");
+  if (generated.find("sq_str_rank(") != std::string::npos) src += embedded_source("strrank");  // Utf8 ordering comparisons
   src += "\n// ---- generated row program -------------------------------------------------\n";
   src += generated;
   src += "\n// ---- skeleton: ";
@@ -217,6 +224,11 @@ JitKernel* jit_get(const std::string& skeleton, const std::string& generated, co
   auto* k = new JitKernel();
   k->mod = mod;
   cu_check(g_drv.ModuleGetFunction(&k->fn, mod, kernel_name.c_str()), ("cuModuleGetFunction " + kernel_name).c_str());
+  if (generated.find("sq_str_rank(") != std::string::npos) {
+    size_t bytes = 0;
+    cu_check(g_drv.ModuleGetGlobal(&k->rank_sym, &bytes, mod, "sq_rank_table"), "cuModuleGetGlobal sq_rank_table");
+    k->rank_value = new const void*(nullptr);
+  }
   g_kernels[key] = k;
   return k;
 }
@@ -226,6 +238,13 @@ void jit_launch(JitKernel* k, unsigned grid, unsigned block, size_t dyn_smem, cu
     cu_check(g_drv.FuncSetAttribute(k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn_smem),
              "cuFuncSetAttribute(max dynamic shared)");
     k->smem_opt_in = dyn_smem;
+  }
+  if (k->rank_sym) {  // the kernel compares strings by order: point it at the current rank table (stream-ordered)
+    const void* table = string_rank_table(stream);
+    if (*k->rank_value != table) {
+      *k->rank_value = table;
+      cu_check(g_drv.MemcpyHtoDAsync(k->rank_sym, k->rank_value, sizeof(void*), (CUstream)stream), "cuMemcpyHtoDAsync sq_rank_table");
+    }
   }
   cu_check(g_drv.LaunchKernel(k->fn, grid, 1, 1, block, 1, 1, (unsigned)dyn_smem, (CUstream)stream, args, nullptr), "cuLaunchKernel");
   count_launch();

@@ -100,13 +100,17 @@ def test_eval_program_compiles_and_type_errors_surface_without_a_gpu(cuda_lib):
             cuda_lib.check(cuda_lib.debug_compile_eval(bad.ptr, bad.n, 0, C.byref(sch), 0, None))
         assert err.value.code == ffi.ERR_INTERNAL
         utf8 = ffi.export_schema(pa.schema([pa.field("s", pa.utf8())]))
-        # Utf8 columns are string-pool ids on the device: equality compiles, an ORDERING comparison of strings is refused
+        # Utf8 columns are string-pool ids on the device: equality compares the ids, an ORDERING comparison of strings their
+        # byte-wise ranks (csrc/jit/strrank.cuh is compiled in only then)
         one = ExprArray([BinaryOp("=", InputRef(0, ffi.DT_UTF8), Constant("CO"), ffi.DT_BOOL)])
-        cuda_lib.check(cuda_lib.debug_compile_eval(one.ptr, one.n, 0, C.byref(utf8), 1, None))
+        cuda_lib.check(cuda_lib.debug_compile_eval(one.ptr, one.n, 0, C.byref(utf8), 1, C.byref(src)))
+        assert "sq_rank_table" not in C.string_at(src.value).decode()
+        cuda_lib.free(src)
         less = ExprArray([BinaryOp("<", InputRef(0, ffi.DT_UTF8), Constant("CO"), ffi.DT_BOOL)])
-        with pytest.raises(ffi.ExecutorError) as err:
-            cuda_lib.check(cuda_lib.debug_compile_eval(less.ptr, less.n, 0, C.byref(utf8), 0, None))
-        assert err.value.code == ffi.ERR_UNSUPPORTED
+        cuda_lib.check(cuda_lib.debug_compile_eval(less.ptr, less.n, 0, C.byref(utf8), 1, C.byref(src)))
+        text = C.string_at(src.value).decode()
+        cuda_lib.free(src)
+        assert "sq_rank_table" in text and "sq_str_rank(" in text
         ffi.release_schema(utf8)
     finally:
         ffi.release_schema(sch)

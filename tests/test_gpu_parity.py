@@ -959,6 +959,41 @@ def test_utf8_group_keys_min_max_order_distinct(cuda_lib, oracle, seed):
     assert_batches_match(got, exp)
 
 
+def test_utf8_ordering_comparisons_in_filters_and_join_filters(cuda_lib, oracle):
+    """<, <=, >, >= over Utf8 columns and literals (gt_dyn & co, array_compute.rs:80-83): in a Filter, in a Filter fused below an
+    aggregate, and in a non-equi join filter.  A later batch brings strings the pool has not ranked yet (the device rank table
+    is rebuilt before the next launch); prefixes, the empty string, multi-byte characters and NULLs are in the mix."""
+    rng = np.random.default_rng(11)
+    vocab1 = ["", "a", "ab", "abc", "b", "Zebra", "zebra", "CO", "CA", "é", "日本", "a b"]
+    vocab2 = vocab1 + ["0", "A", "aa", "zz", "~", "CO ", "ß", "1000", "20"]
+    batches = [_utf8_batch(rng, 400, vocab1), _utf8_batch(rng, 600, vocab2)]
+    s, v, t = InputRef(0, U8), InputRef(1, I64), InputRef(2, U8)
+    BOOL = ffi.DT_BOOL
+    for op in ("<", "<=", ">", ">="):
+        pred = BinaryOp("OR", BinaryOp(op, s, t, BOOL), BinaryOp("AND", BinaryOp(op, t, Constant("b"), BOOL), BinaryOp(">", v, Constant(0), BOOL), BOOL), BOOL)
+        got, exp = both(lambda l: ex.try_collect(ex.FilterExecutor(pred, batches, lib=l).execute()), cuda_lib, oracle)
+        assert_batches_match(got, exp)
+        assert 0 < sum(b.num_rows for b in got) < 1000
+    # fused below an aggregate (the plan fuses Filter into HashAgg): group by t where s < t
+    from sqlrs_b200.host.plan import PhysicalFilter, PhysicalHashAgg, PhysicalTableScan
+
+    schema = batches[0].schema
+    plan = PhysicalHashAgg([AggFunc("Sum", [v]), AggFunc("Count", [s])], [t], PhysicalFilter(BinaryOp("<", s, t, BOOL), PhysicalTableScan(0)))
+    opts = dict(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY)
+    table = pa.Table.from_batches(batches).combine_chunks().to_batches()[0]
+    got, _ = _run_plan(cuda_lib, plan, {0: schema}, {0: table}, 256, **opts)
+    exp, _ = _run_plan(oracle, plan, {0: schema}, {0: table}, 256, **opts)
+    assert_batches_match(got, exp)
+    # non-equi join filter over the joined row: l.s = r.s and l.t < r.t
+    left, right = _utf8_batch(rng, 60, vocab1), _utf8_batch(rng, 80, vocab2)
+    jschema = pa.schema([pa.field(f"l.{f.name}", f.type) for f in left.schema] + [pa.field(f"r.{f.name}", f.type) for f in right.schema])
+    cond = ex.JoinCondition([(InputRef(0, U8), InputRef(0, U8))], filter=BinaryOp("<", InputRef(2, U8), InputRef(5, U8), BOOL))
+    for jt in ("Inner", "Left"):
+        got, exp = both(lambda l: ex.try_collect(ex.HashJoinExecutor([left], [right], jt, cond, jschema, lib=l, options=l.options(match_mode=ffi.MATCH_HASH_AND_KEY)).execute()),
+                        cuda_lib, oracle)
+        assert_batches_match(got, exp)
+
+
 def test_utf8_join_keys_and_payload(cuda_lib, oracle):
     """Utf8 join keys and Utf8 payload columns through every join type (hash_join.rs: keys hashed by create_hashes, payload by take)"""
     rng = np.random.default_rng(5)

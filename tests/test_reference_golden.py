@@ -474,3 +474,15 @@ def test_v2_checked_arithmetic_scalar_function_slt(lib):
     preds = [bind_binary_op(InputRef(0, I64), ">", Constant(1)), bind_binary_op(InputRef(1, I64), "<", Constant(40))]
     out = ex.try_collect(ex.FilterExecutor(fold_and(preds), [t], lib=lib).execute())
     assert rows_of(out) == [(2, 20), (3, 30)]
+
+
+def test_comparison_function_slt_strings_compare_bytewise(lib):
+    """tests/slt/comparison_function.slt:9-19: `select 100 > 20` = true, `select '1000' > '20'` = false — strings compare byte by
+    byte (arrow's gt_utf8 behind gt_dyn, array_compute.rs:80-83), not as numbers; <, <=, >= likewise, NULL propagates"""
+    b = batch(["i", "j", "s", "t"], [100, 3], [20, 3], ["1000", "b"], ["20", None], types=[pa.int64(), pa.int64(), pa.string(), pa.string()])
+    U8 = ffi.DT_UTF8
+    assert ex.eval_column(BinaryOp(">", InputRef(0, I64), InputRef(1, I64), ffi.DT_BOOL), b, lib=lib).to_pylist() == [True, False]
+    assert ex.eval_column(BinaryOp(">", InputRef(2, U8), InputRef(3, U8), ffi.DT_BOOL), b, lib=lib).to_pylist() == [False, None]
+    assert ex.eval_column(BinaryOp("<", InputRef(2, U8), InputRef(3, U8), ffi.DT_BOOL), b, lib=lib).to_pylist() == [True, None]
+    assert ex.eval_column(BinaryOp("<=", InputRef(2, U8), Constant("b"), ffi.DT_BOOL), b, lib=lib).to_pylist() == [True, True]
+    assert ex.eval_column(BinaryOp(">=", InputRef(2, U8), Constant("2"), ffi.DT_BOOL), b, lib=lib).to_pylist() == [False, True]
