@@ -970,7 +970,7 @@ def test_utf8_ordering_comparisons_in_filters_and_join_filters(cuda_lib, oracle)
     s, v, t = InputRef(0, U8), InputRef(1, I64), InputRef(2, U8)
     BOOL = ffi.DT_BOOL
     for op in ("<", "<=", ">", ">="):
-        pred = BinaryOp("OR", BinaryOp(op, s, t, BOOL), BinaryOp("AND", BinaryOp(op, t, Constant("b"), BOOL), BinaryOp(">", v, Constant(0), BOOL), BOOL), BOOL)
+        pred = BinaryOp("OR", BinaryOp(op, s, t, BOOL), BinaryOp("AND", BinaryOp(op, t, Constant("b"), BOOL), bind_binary_op(v, ">", Constant(0)), BOOL), BOOL)
         got, exp = both(lambda l: ex.try_collect(ex.FilterExecutor(pred, batches, lib=l).execute()), cuda_lib, oracle)
         assert_batches_match(got, exp)
         assert 0 < sum(b.num_rows for b in got) < 1000
