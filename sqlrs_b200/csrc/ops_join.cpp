@@ -8,6 +8,16 @@
 
 namespace sq {
 
+// highest load factor a key-in-slot table is sized for, in percent (capacity = the power of two that keeps the load below it;
+// tuning experiments: SQLRS_B200_KV_MAXLOAD)
+static uint64_t kv_max_load_pct() {
+  static const uint64_t pct = [] {
+    const char* e = std::getenv("SQLRS_B200_KV_MAXLOAD");
+    return (uint64_t)(e ? std::min(95, std::max(10, atoi(e))) : 50);
+  }();
+  return pct;
+}
+
 ProbeProgram gen_probe_program(const std::vector<ColInfo>& cols, const std::vector<ExprCopy>& right_keys, const ExprCopy& probe_pred, bool jmatch) {
   std::ostringstream s;
   RowProgram p1(cols);
@@ -245,7 +255,7 @@ bool JoinOp::seal_fused() {
     SQ_CUDA(cudaMemsetAsync(status->p, 0, 40, ctx_.stream));
   }
   uint64_t cap = 1024;
-  while (cap < 2ULL * (uint64_t)n_insert) cap <<= 1;
+  while (cap * kv_max_load_pct() < 100ULL * (uint64_t)n_insert) cap <<= 1;
   if (cap > (1ULL << 30)) return false;
   BufPtr kv = dev_alloc(ctx_, cap * 16);
   SQ_CUDA(cudaMemsetAsync(kv->p, 0xff, cap * 16, ctx_.stream));
@@ -394,7 +404,7 @@ void JoinOp::seal() {
     *(unsigned long long*)(hint_pinned_ + 8) = (unsigned long long)n;
   }
   uint64_t cap = 1024;
-  while (cap < 2ULL * (uint64_t)n_insert) cap <<= 1;
+  while (cap * kv_max_load_pct() < 100ULL * (uint64_t)n_insert) cap <<= 1;
   if (cap > (1ULL << 30)) fail(SQLRS_ERR_UNSUPPORTED, "join build side too large for one table (> 2^29 rows)");
   im.capacity = (uint32_t)cap;
   JoinTableView& v = im.view;
@@ -845,7 +855,7 @@ bool JoinChainOp::run(JoinOp& j1, const DBatch& probe1, const ExprCopy& probe_pr
     SQ_CUDA(cudaMemsetAsync(status->p, 0, 32, ctx_.stream));
   }
   uint64_t cap = 1024;
-  while (cap < 2ULL * (uint64_t)est) cap <<= 1;
+  while (cap * kv_max_load_pct() < 100ULL * (uint64_t)est) cap <<= 1;
   if (cap > (1ULL << 30)) return false;
   cap_used_ = cap;
   BufPtr kv = dev_alloc(ctx_, cap * 16);
