@@ -17,10 +17,12 @@ tabs = {0: tpch.device_table(lib, d, tpch.CUSTOMER, columns=tpch.Q3_CUSTOMER_COL
 rows = {k: t.n_rows for k, t in tabs.items()}
 alg = tpch.q3_algorithmic_bytes(rows[0], rows[1], rows[2])
 full = len(sys.argv) > 3 and sys.argv[3] == "full"  # + Order / Project / Limit on the device
+hash_only = len(sys.argv) > 4 and sys.argv[4] == "hash_only"  # the reference's default group / join identity (quirk K2): unfused path
 plan, schemas = tpch.q3_full_plan() if full else tpch.q3_plan()
 stream = torch.cuda.Stream()
 with torch.cuda.stream(stream):
-    opts = lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY, stream=C.c_void_p(stream.cuda_stream))
+    opts = lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_ONLY if hash_only else ffi.MATCH_HASH_AND_KEY,
+                       stream=C.c_void_p(stream.cuda_stream))
     p = ExecutorBuilder(lib, opts).build(plan, schemas)
     best = 1e9
     for it in range(reps):
