@@ -635,13 +635,22 @@ def distributed_join_topk(builder, group: TorchGroup, *, build_plan, build_schem
         p_query.reset()
         _push(p_build, build_tables)
         later = lambda: _push(p_query, query_tables)  # noqa: E731 — pushed while the row counts of the exchange travel
-    p_build.execute()
-    mark("build-side sub-plan (local shard)")
-    build_side = broadcast_rows(p_build, group, build_plan.output_schema(build_schemas), state, while_waiting=later)
-    mark("all-gather of its rows")
-    p_query.push_table_device(build_slot, build_side)
+    device_path = group.native_a2a and builder.lib.prefix == "sqlrs_"
+    if device_path:
+        p_build.execute()
+        mark("build-side sub-plan (local shard)")
+        build_side = broadcast_rows(p_build, group, build_plan.output_schema(build_schemas), state, while_waiting=later)
+        mark("all-gather of its rows")
+        p_query.push_table_device(build_slot, build_side)
+    else:  # gloo / the CPU checker: the same steps through host batches
+        schema = build_plan.output_schema(build_schemas)
+        rows = all_gather_batches(group, p_build.run(), schema)
+        if later is not None:
+            later()
+        for b in rows or [pa.RecordBatch.from_pylist([], schema=schema)]:
+            p_query.push_table(build_slot, b)
     mark("  query: tables pushed")
-    if group.native_a2a and builder.lib.prefix == "sqlrs_":
+    if device_path:
         p_query.execute()
         mark("query plan (local shards)")
         out = merge_topk_device(p_query, group, query_plan.output_schema(query_schemas), order_by, limit, state, builder)

@@ -194,6 +194,57 @@ def test_copartitioned_q3_full_query_matches_single_process(tmp_path, oracle, wo
     assert (tmp_path / "ok").read_text() == "ok"
 
 
+def _q3_join_topk_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+
+    from sqlrs_b200.host import distributed as sqdist
+    from sqlrs_b200.host import ffi, tpch
+    from sqlrs_b200.host.plan import ExecutorBuilder
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lib = ffi.Library(os.path.join(ROOT, "oracle", "liboracle.so"), "sqlrs_oracle_")
+    d = tpch.dims(0.02)
+    builder = ExecutorBuilder(lib, lib.options(count_mode=ffi.COUNT_SQL_ACCUMULATE, match_mode=ffi.MATCH_HASH_AND_KEY))
+    plan, schemas = tpch.q3_full_plan()
+    cust_plan = plan.child.child.child.child.left.left  # Filter(Scan(customer)) of the query
+    (o_lo, o_hi), (l_lo, l_hi) = sqdist.copartitioned_shard(int(d.n_orders), rank, world)
+    n_c = tpch.num_rows(lib, d, tpch.CUSTOMER)
+    shard = tpch.host_table(lib, d, tpch.CUSTOMER, n_c * rank // world, n_c * (rank + 1) // world, columns=tpch.Q3_CUSTOMER_COLUMNS)  # sharded by rows
+    orders = tpch.host_table(lib, d, tpch.ORDERS, o_lo, o_hi, columns=tpch.Q3_ORDERS_COLUMNS)
+    lineitem = tpch.host_table(lib, d, tpch.LINEITEM, l_lo, l_hi, columns=tpch.Q3_LINEITEM_COLUMNS)
+    group = sqdist.TorchGroup(dist, torch.device("cpu"))
+    state = {}
+    for _ in range(2):  # the second call reuses the plans kept in `state`
+        result = sqdist.distributed_join_topk(builder, group, build_plan=cust_plan, build_schemas={0: schemas[0]}, build_tables={0: shard}, query_plan=plan,
+                                              query_schemas=schemas, query_tables={1: orders, 2: lineitem}, build_slot=0, order_by=tpch.q3_tail_order_by(),
+                                              limit=10, state=state)
+    if rank == 0:
+        whole = builder.build(plan, schemas)
+        whole.push_table(0, tpch.host_table(lib, d, tpch.CUSTOMER, columns=tpch.Q3_CUSTOMER_COLUMNS))
+        whole.push_table(1, tpch.host_table(lib, d, tpch.ORDERS, columns=tpch.Q3_ORDERS_COLUMNS))
+        whole.push_table(2, tpch.host_table(lib, d, tpch.LINEITEM, columns=tpch.Q3_LINEITEM_COLUMNS))
+        expect = whole.run()
+        from util import assert_batches_match
+
+        assert sum(b.num_rows for b in expect) == 10
+        assert_batches_match(result, expect, rtol=1e-9)
+        open(os.path.join(out_dir, "ok"), "w").write("ok")
+    else:
+        assert result == []
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_join_topk_with_a_sharded_dimension_table(tmp_path, oracle, world):
+    """what bench.py times for Q3' at N > 1, through host batches: customer sharded by rows, its filtered rows all-gathered, the
+    whole query per rank over co-partitioned orders / lineitem shards, per-rank top-10 merged == single-process result"""
+    mp.spawn(_q3_join_topk_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok").read_text() == "ok"
+
+
 def test_copartitioned_shard_covers_everything():
     sys.path.insert(0, ROOT)
     from sqlrs_b200.host import distributed as sqdist
