@@ -466,6 +466,16 @@ def merge_topk_device(plan, group: TorchGroup, schema: pa.Schema, order_by, limi
     return p_tail.run()
 
 
+def packing_index(torch, counts, ncols: int, most: int):
+    """Flat positions in an all-gathered buffer recv[W, ncols, most] (rank r filled its first counts[r] rows of every column) of
+    the packed layout [ncols, sum(counts)] whose rows are the ranks' rows in rank order: torch.take(recv, index) packs them."""
+    W, total = len(counts), int(sum(counts))
+    rank_of = torch.repeat_interleave(torch.arange(W), torch.tensor(counts, dtype=torch.int64))
+    starts = torch.cumsum(torch.tensor((0,) + tuple(counts[:-1]), dtype=torch.int64), 0)
+    within = torch.arange(total, dtype=torch.int64) - starts[rank_of]
+    return (rank_of * (ncols * most) + within).unsqueeze(0) + (torch.arange(ncols, dtype=torch.int64) * most).unsqueeze(1)
+
+
 def broadcast_rows(plan, group: TorchGroup, schema: pa.Schema, state: Optional[dict] = None, while_waiting=None) -> DeviceBatch:
     """The rows `plan` (already executed on this rank's shard; ONE pending device result of fixed-width, NULL-free columns)
     produced on every rank, concatenated in rank order, on every rank — all-gathered device to device.  This is the
@@ -493,11 +503,7 @@ def broadcast_rows(plan, group: TorchGroup, schema: pa.Schema, state: Optional[d
     most, total = max(max(counts), 1), int(sum(counts))
     key = ("bc_bufs", ncols, counts)
     if state.get("bc_key") != key:
-        # flat positions in recv [W, ncols, most] of the packed [ncols, total] layout: rank order = row order
-        rank_of = torch.repeat_interleave(torch.arange(W), torch.tensor(counts, dtype=torch.int64))
-        starts = torch.cumsum(torch.tensor((0,) + counts[:-1], dtype=torch.int64), 0)
-        within = torch.arange(total, dtype=torch.int64) - starts[rank_of]
-        flat = (rank_of * (ncols * most) + within).unsqueeze(0) + (torch.arange(ncols, dtype=torch.int64) * most).unsqueeze(1)
+        flat = packing_index(torch, counts, ncols, most)
         state["bc_key"] = key
         state["bc_bufs"] = (torch.empty((ncols, most), dtype=torch.int64, device=group.device),
                             torch.empty((W, ncols, most), dtype=torch.int64, device=group.device),

@@ -245,6 +245,27 @@ def test_distributed_join_topk_with_a_sharded_dimension_table(tmp_path, oracle, 
     assert (tmp_path / "ok").read_text() == "ok"
 
 
+def test_packing_index_concatenates_ragged_rank_buffers():
+    """the device all-gather moves fixed-size buffers; one gather through this index packs the ranks' rows in rank order"""
+    sys.path.insert(0, ROOT)
+    import torch
+
+    from sqlrs_b200.host import distributed as sqdist
+
+    for counts in ((2, 0, 3), (0, 0, 0, 1), (5,), (1, 1, 1, 1, 1, 1, 1, 7)):
+        W, ncols, most = len(counts), 3, max(max(counts), 1)
+        recv = torch.arange(W * ncols * most).view(W, ncols, most)
+        index = sqdist.packing_index(torch, counts, ncols, most)
+        expect = torch.cat([recv[r, :, :counts[r]] for r in range(W)], dim=1)
+        assert index.shape == (ncols, sum(counts))
+        assert torch.equal(torch.take(recv, index), expect)
+    a, b = object(), object()
+    assert sqdist._same_tables({0: a, 1: b}, {0: a, 1: b}) and not sqdist._same_tables({0: a, 1: b}, {0: a, 1: a})
+    assert not sqdist._same_tables({0: a}, {0: a, 1: b}) and not sqdist._same_tables({1: a}, {0: a})
+    host = pa.RecordBatch.from_pylist([{"x": 1}])
+    assert not sqdist._same_tables({0: host}, {0: host})  # a host batch is this call's input: copied to the device every time
+
+
 def test_copartitioned_shard_covers_everything():
     sys.path.insert(0, ROOT)
     from sqlrs_b200.host import distributed as sqdist

@@ -486,3 +486,23 @@ def test_comparison_function_slt_strings_compare_bytewise(lib):
     assert ex.eval_column(BinaryOp("<", InputRef(2, U8), InputRef(3, U8), ffi.DT_BOOL), b, lib=lib).to_pylist() == [True, None]
     assert ex.eval_column(BinaryOp("<=", InputRef(2, U8), Constant("b"), ffi.DT_BOOL), b, lib=lib).to_pylist() == [True, True]
     assert ex.eval_column(BinaryOp(">=", InputRef(2, U8), Constant("2"), ffi.DT_BOOL), b, lib=lib).to_pylist() == [False, True]
+
+
+def test_plan_rerun_with_one_table_replaced(lib):
+    """sqlrs_plan_clear_table: a plan keeps its pushed tables across runs; one slot is emptied and refilled, the other stays.
+    (t1 join t2 on t1.a = t2.b -> nothing matches; t1' join t2 with t1'.a in t2.b -> rows in the reference's order)"""
+    from sqlrs_b200.host.plan import ExecutorBuilder, PhysicalHashJoin, PhysicalTableScan
+
+    schema = _join_schema(t1(), "t1", t2(), "t2", "Inner")
+    cond = ex.JoinCondition([(InputRef(0, I64), InputRef(1, I64))])
+    plan = PhysicalHashJoin(PhysicalTableScan(0), PhysicalTableScan(1), "Inner", cond, schema)
+    p = ExecutorBuilder(lib).build(plan, {0: t1().schema, 1: t2().schema})
+    p.push_table(0, t1())
+    p.push_table(1, t2())
+    first = rows_of(p.run())
+    assert first == [(2, 7, 9, 10, 2, 7), (2, 8, 1, 10, 2, 7), (2, 7, 9, 20, 2, 5), (2, 8, 1, 20, 2, 5)]
+    assert rows_of(p.run()) == first  # nothing is consumed by a run
+    p.clear_table(0)
+    p.push_table(0, batch(["a", "b", "c"], [4, 3, 9], [1, 1, 1], [5, 6, 7]))
+    assert rows_of(p.run()) == [(3, 1, 6, 30, 3, 6), (4, 1, 5, 40, 4, 6)]
+    p.close()
