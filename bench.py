@@ -63,22 +63,24 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def source_fingerprint():
-    """Hash of the complete CUDA sources (prelude + generated row program + skeletons) of the kernels the benchmark plans run:
-    `roofline.traffic` comes from a committed ncu capture and is only reported while the kernels are the ones that were
-    captured (profiles/r02_traffic.json carries the fingerprint of its capture)."""
-    if not _FINGERPRINT:
+def source_fingerprint(query):
+    """Hash of the complete CUDA sources (prelude + generated row program + skeletons) of the kernels the benchmark plan of
+    `query` ("q1" | "q3") runs: `roofline.traffic` comes from a committed ncu capture and is only reported while the kernels are
+    the ones that were captured (profiles/r02_traffic.json carries the fingerprints of its captures, per query)."""
+    if not _FINGERPRINTS:
         import __graft_entry__ as entry
         from sqlrs_b200.host import ffi
 
-        h = hashlib.sha1()
-        for src in entry.benchmark_kernel_sources(ffi.load(), compile=False):
-            h.update(src.encode())
-        _FINGERPRINT.append(h.hexdigest()[:16])
-    return _FINGERPRINT[0]
+        sources = entry.benchmark_kernel_sources(ffi.load(), compile=False)  # [Q1' aggregate x 2 modes, Q3' chain, probe / build, probe + aggregate]
+        for name, part in (("q1", sources[:2]), ("q3", sources[2:])):
+            h = hashlib.sha1()
+            for src in part:
+                h.update(src.encode())
+            _FINGERPRINTS[name] = h.hexdigest()[:16]
+    return _FINGERPRINTS[query]
 
 
-_FINGERPRINT = []
+_FINGERPRINTS = {}
 
 
 def ncu_traffic(workload, kernel):
@@ -86,7 +88,8 @@ def ncu_traffic(workload, kernel):
     try:
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f)
-        if t.get("source_fingerprint") != source_fingerprint():
+        query = "q1" if "_q1_" in workload else "q3"
+        if t.get("source_fingerprints", {}).get(query) != source_fingerprint(query):
             return None
         k = t["workloads"][workload][kernel]
         return int(k["dram_bytes_read"] + k["dram_bytes_write"])

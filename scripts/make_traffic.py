@@ -18,8 +18,18 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us"
 
 out = {"note": "DRAM bytes of ONE launch from ncu --set full --clock-control none (scripts/final_r02.sh); bench.py reports them as "
                "roofline.traffic while source_fingerprint matches the kernel sources",
-       "source_fingerprint": bench.source_fingerprint(), "workloads": {}}
+       "source_fingerprints": {"q1": bench.source_fingerprint("q1"), "q3": bench.source_fingerprint("q3")}, "workloads": {}}
+only = sys.argv[1:]  # e.g. "q3": refresh the Q3' captures only, keep the other workloads (and their fingerprint) as committed
+if only:
+    with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+        old = json.load(f)
+    for q in ("q1", "q3"):
+        if q not in only:
+            out["source_fingerprints"][q] = old["source_fingerprints"][q]
+    out["workloads"] = {w: v for w, v in old["workloads"].items() if not any(f"_{q}_" in w for q in only)}
 for workload, rep in REPORTS.items():
+    if only and not any(f"_{q}_" in workload for q in only):
+        continue
     raw = subprocess.run(["ncu", "-i", os.path.join(ROOT, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
