@@ -32,7 +32,7 @@
 #define SQ_PREFETCH 0  // L2 prefetch distance in warp trips (0 = off)
 #endif
 #ifndef SQ_JMINB
-#define SQ_JMINB 1  // __launch_bounds__ minimum CTAs per SM (register budget)
+#define SQ_JMINB 4  // __launch_bounds__ minimum CTAs per SM: 64 registers, 32 resident warps (80 registers / 24 warps unconstrained)
 #endif
 #define SQ_JQUEUE (SQ_JUNROLL * 32 + 32)
 
